@@ -1,0 +1,466 @@
+/*
+ * pll_b200.h -- public C interface of the B200-native likelihood engine.
+ *
+ * Drop-in boundary for the phylogenetic-likelihood hot path of libpll-2.
+ * Every type and entry point below replaces the reference declaration cited
+ * next to it (paths relative to the reference tree); struct field order, types
+ * and function signatures are ABI and are kept identical so that a caller
+ * built against the reference header can link against libpll_b200.so and flip
+ * one attribute bit (PLL_ATTRIB_ARCH_CUDA).
+ *
+ * Pointer fields of a CUDA partition:
+ *   - clv[], scale_buffer[], pmatrix[], ttlookup hold DEVICE addresses (HBM).
+ *     They are dereferenceable on the host only when the partition was created
+ *     with PLL_CUDA_MANAGED=1 in the environment (cudaMallocManaged).  Use
+ *     pll_cuda_download_clv()/..._scaler()/..._pmatrix() to read them.
+ *   - rates, rate_weights, subst_params, frequencies, prop_invar, invariant,
+ *     pattern_weights, eigen*, tipchars[], charmap, tipmap and every field of
+ *     pll_repeats_t are HOST arrays exactly as in the reference; the engine
+ *     keeps device mirrors and re-uploads them when they change.
+ */
+#ifndef PLL_B200_H_
+#define PLL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLL_EXPORT __attribute__((visibility("default")))
+
+/* ---- constants (src/pll.h:82-137) ------------------------------------- */
+
+#define PLL_FAILURE 0
+#define PLL_SUCCESS 1
+#define PLL_FALSE 0
+#define PLL_TRUE 1
+
+#define PLL_ALIGNMENT_CPU 8
+#define PLL_ALIGNMENT_SSE 16
+#define PLL_ALIGNMENT_AVX 32
+#define PLL_ALIGNMENT_CUDA 32   /* same as AVX: identical buffer layouts */
+
+#define PLL_ASCII_SIZE 256
+
+/* 2^256 and 2^-256, both exactly representable (src/pll.h:96-97) */
+#define PLL_SCALE_FACTOR 0x1p+256
+#define PLL_SCALE_THRESHOLD 0x1p-256
+#define PLL_SCALE_BUFFER_NONE (-1)
+#define PLL_SCALE_RATE_MAXDIFF 4      /* src/pll.h:104 */
+
+#define PLL_MISC_EPSILON 1e-8
+#define PLL_EIGEN_MINFREQ 1e-6
+
+/* attribute bits (src/pll.h:114-137) */
+#define PLL_ATTRIB_ARCH_CPU 0
+#define PLL_ATTRIB_ARCH_SSE (1 << 0)
+#define PLL_ATTRIB_ARCH_AVX (1 << 1)
+#define PLL_ATTRIB_ARCH_AVX2 (1 << 2)
+#define PLL_ATTRIB_ARCH_AVX512 (1 << 3)
+#define PLL_ATTRIB_ARCH_MASK 0xF
+#define PLL_ATTRIB_PATTERN_TIP (1 << 4)
+#define PLL_ATTRIB_AB_LEWIS (1 << 5)
+#define PLL_ATTRIB_AB_FELSENSTEIN (2 << 5)
+#define PLL_ATTRIB_AB_STAMATAKIS (3 << 5)
+#define PLL_ATTRIB_AB_MASK (7 << 5)
+#define PLL_ATTRIB_AB_FLAG (1 << 8)
+#define PLL_ATTRIB_RATE_SCALERS (1 << 9)
+#define PLL_ATTRIB_SITE_REPEATS (1 << 10)
+#define PLL_REPEATS_LOOKUP_SIZE 2000000
+
+/* NEW: the CUDA (sm_100a) architecture selector.  Bit 16 is outside the
+ * reference's PLL_ATTRIB_MASK ((1<<11)-1) so it cannot collide with flags of
+ * newer reference revisions; it counts as an architecture in the
+ * one-architecture check of pll_partition_create (src/pll.c:438-443). */
+#define PLL_ATTRIB_ARCH_CUDA (1 << 16)
+#define PLL_ATTRIB_MASK (((1 << 11) - 1) | PLL_ATTRIB_ARCH_CUDA)
+
+/* error codes used on this path (src/pll.h:156-190) */
+#define PLL_ERROR_MEM_ALLOC 112
+#define PLL_ERROR_PARAM_INVALID 113
+#define PLL_ERROR_TIPDATA_ILLEGALSTATE 114
+#define PLL_ERROR_TIPDATA_ILLEGALFUNCTION 115
+#define PLL_ERROR_INVAR_INCOMPAT 117
+#define PLL_ERROR_INVAR_PROPORTION 118
+#define PLL_ERROR_INVAR_PARAMINDEX 119
+#define PLL_ERROR_INVAR_NONEFOUND 120
+#define PLL_ERROR_AB_INVALIDMETHOD 121
+#define PLL_ERROR_AB_NOSUPPORT 122
+/* NEW: CUDA runtime / device failures */
+#define PLL_ERROR_CUDA 900
+#define PLL_ERROR_CUDA_UNSUPPORTED 901
+
+#define PLL_GAMMA_RATES_MEAN 0
+#define PLL_GAMMA_RATES_MEDIAN 1
+
+/* ---- types (src/pll.h:222-335) ---------------------------------------- */
+
+typedef unsigned long long pll_state_t;
+typedef int pll_bool_t;
+
+/* src/pll.h:222-239; the CPU feature words are kept for layout, a CUDA
+ * partition does not consult them */
+typedef struct pll_hardware_s
+{
+  int init;
+  int altivec_present;
+  int mmx_present;
+  int sse_present;
+  int sse2_present;
+  int sse3_present;
+  int ssse3_present;
+  int sse41_present;
+  int sse42_present;
+  int popcnt_present;
+  int avx_present;
+  int avx2_present;
+} pll_hardware_t;
+
+struct pll_repeats;
+
+/* src/pll.h:241-288 */
+typedef struct pll_partition
+{
+  unsigned int tips;
+  unsigned int clv_buffers;
+  unsigned int nodes;
+  unsigned int states;
+  unsigned int sites;
+  unsigned int pattern_weight_sum;
+  unsigned int rate_matrices;
+  unsigned int prob_matrices;
+  unsigned int rate_cats;
+  unsigned int scale_buffers;
+  unsigned int attributes;
+
+  size_t alignment;
+  unsigned int states_padded;
+
+  double ** clv;                 /* [node] -> DEVICE [site][rate][state_padded] */
+  double ** pmatrix;             /* [matrix] -> DEVICE [rate][row][col_padded]  */
+  double * rates;
+  double * rate_weights;
+  double ** subst_params;
+  unsigned int ** scale_buffer;  /* [buffer] -> DEVICE [site] or [site][rate]   */
+  double ** frequencies;
+  double * prop_invar;
+  int * invariant;
+  unsigned int * pattern_weights;
+
+  int * eigen_decomp_valid;
+  double ** eigenvecs;
+  double ** inv_eigenvecs;
+  double ** eigenvals;
+
+  unsigned int maxstates;
+  unsigned char ** tipchars;     /* [tip] -> HOST [site]; device mirror inside  */
+  unsigned char * charmap;
+  double * ttlookup;             /* unused by the CUDA path (tables live in smem) */
+  pll_state_t * tipmap;
+
+  int asc_bias_alloc;
+  int asc_additional_sites;
+
+  struct pll_repeats * repeats;
+} pll_partition_t;
+
+/* src/pll.h:290-321 */
+typedef struct pll_repeats
+{
+  unsigned int ** pernode_site_id;
+  unsigned int ** pernode_id_site;
+  unsigned int * pernode_ids;
+  unsigned int * perscale_ids;
+  unsigned int * pernode_allocated_clvs;
+  unsigned int (*enable_repeats)(struct pll_partition * partition,
+                                 unsigned int left_clv,
+                                 unsigned int right_clv);
+  void (*reallocate_repeats)(struct pll_partition * partition,
+                             unsigned int parent,
+                             int scaler_index,
+                             unsigned int sites_to_alloc);
+  unsigned int * lookup_buffer;
+  unsigned int * toclean_buffer;
+  unsigned int * id_site_buffer;
+  double * bclv_buffer;
+  unsigned int lookup_buffer_size;
+  char * charmap;
+} pll_repeats_t;
+
+/* src/pll.h:325-335 */
+typedef struct pll_operation
+{
+  unsigned int parent_clv_index;
+  int parent_scaler_index;
+  unsigned int child1_clv_index;
+  unsigned int child1_matrix_index;
+  int child1_scaler_index;
+  unsigned int child2_clv_index;
+  unsigned int child2_matrix_index;
+  int child2_scaler_index;
+} pll_operation_t;
+
+/* ---- thread-local status (src/pll.h:553-555, src/pll.c:24-27) ---------- */
+
+PLL_EXPORT extern __thread int pll_errno;
+PLL_EXPORT extern __thread char pll_errmsg[200];
+PLL_EXPORT extern __thread pll_hardware_t pll_hardware;
+
+/* character -> state-mask tables (src/pll.h:557-560, values src/maps.c:26-180) */
+PLL_EXPORT extern const pll_state_t pll_map_bin[256];
+PLL_EXPORT extern const pll_state_t pll_map_nt[256];
+PLL_EXPORT extern const pll_state_t pll_map_aa[256];
+
+/* ---- partition lifecycle and tips (src/pll.h:638-667, src/pll.c) ------- */
+
+/* src/pll.c:424 */
+PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips,
+                                                  unsigned int clv_buffers,
+                                                  unsigned int states,
+                                                  unsigned int sites,
+                                                  unsigned int rate_matrices,
+                                                  unsigned int prob_matrices,
+                                                  unsigned int rate_cats,
+                                                  unsigned int scale_buffers,
+                                                  unsigned int attributes);
+/* src/pll.c:870 */
+PLL_EXPORT void pll_partition_destroy(pll_partition_t * partition);
+/* src/pll.c:1026 */
+PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition,
+                                  unsigned int tip_index,
+                                  const pll_state_t * map,
+                                  const char * sequence);
+/* src/pll.c:1066 */
+PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
+                               unsigned int tip_index,
+                               const double * clv,
+                               int padding);
+/* src/pll.c:1131 */
+PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition,
+                                        const unsigned int * pattern_weights);
+/* src/pll.c:1145,1192: accepted for ABI completeness; ascertainment-bias math
+ * is outside this round's hot path and fails with PLL_ERROR_CUDA_UNSUPPORTED */
+PLL_EXPORT int pll_set_asc_bias_type(pll_partition_t * partition,
+                                     int asc_bias_type);
+PLL_EXPORT void pll_set_asc_state_weights(pll_partition_t * partition,
+                                          const unsigned int * state_weights);
+/* src/pll.c:1202: pure host helper on host arrays, kept for callers */
+PLL_EXPORT void pll_fill_parent_scaler(unsigned int scaler_size,
+                                       unsigned int * parent_scaler,
+                                       const unsigned int * left_scaler,
+                                       const unsigned int * right_scaler);
+/* src/pll.c:134,148 */
+PLL_EXPORT void * pll_aligned_alloc(size_t size, size_t alignment);
+PLL_EXPORT void pll_aligned_free(void * ptr);
+
+/* ---- model parameters and P-matrices (src/pll.h:736-776, src/models.c) -- */
+
+PLL_EXPORT void pll_set_subst_params(pll_partition_t * partition,
+                                     unsigned int params_index,
+                                     const double * params);          /* models.c:485 */
+PLL_EXPORT void pll_set_frequencies(pll_partition_t * partition,
+                                    unsigned int params_index,
+                                    const double * frequencies);      /* models.c:445 */
+PLL_EXPORT void pll_set_category_rates(pll_partition_t * partition,
+                                       const double * rates);         /* models.c:470 */
+PLL_EXPORT void pll_set_category_weights(pll_partition_t * partition,
+                                         const double * rate_weights);/* models.c:476 */
+PLL_EXPORT int pll_update_eigen(pll_partition_t * partition,
+                                unsigned int params_index);           /* models.c:293 */
+PLL_EXPORT int pll_update_prob_matrices(pll_partition_t * partition,
+                                        const unsigned int * params_indices,
+                                        const unsigned int * matrix_indices,
+                                        const double * branch_lengths,
+                                        unsigned int count);          /* models.c:412 */
+PLL_EXPORT unsigned int pll_count_invariant_sites(pll_partition_t * partition,
+                                                  unsigned int * state_inv_count); /* models.c:546 */
+PLL_EXPORT int pll_update_invariant_sites(pll_partition_t * partition);           /* models.c:651 */
+PLL_EXPORT int pll_update_invariant_sites_proportion(pll_partition_t * partition,
+                                                     unsigned int params_index,
+                                                     double prop_invar);          /* models.c:495 */
+
+/* ---- CLV updates (src/pll.h:818-828, src/partials.c:237-291) ----------- */
+
+PLL_EXPORT void pll_update_partials(pll_partition_t * partition,
+                                    const pll_operation_t * operations,
+                                    unsigned int count);
+PLL_EXPORT void pll_update_partials_rep(pll_partition_t * partition,
+                                        const pll_operation_t * operations,
+                                        unsigned int count,
+                                        unsigned int update_repeats);
+
+/* ---- log-likelihood (src/pll.h:782-797, src/likelihood.c:122,586) ------ */
+
+PLL_EXPORT double pll_compute_root_loglikelihood(pll_partition_t * partition,
+                                                 unsigned int clv_index,
+                                                 int scaler_index,
+                                                 const unsigned int * freqs_indices,
+                                                 double * persite_lnl);
+PLL_EXPORT double pll_compute_edge_loglikelihood(pll_partition_t * partition,
+                                                 unsigned int parent_clv_index,
+                                                 int parent_scaler_index,
+                                                 unsigned int child_clv_index,
+                                                 int child_scaler_index,
+                                                 unsigned int matrix_index,
+                                                 const unsigned int * freqs_indices,
+                                                 double * persite_lnl);
+
+/* ---- derivatives (src/pll.h:832-849, src/derivatives.c:239,333) -------- *
+ * `sumtable` is the caller's host buffer in the reference.  Here it is an
+ * opaque handle: the table itself lives in HBM, keyed by this pointer value,
+ * and the host bytes are written only when PLL_CUDA_SUMTABLE_MIRROR=1. */
+PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition,
+                                   unsigned int parent_clv_index,
+                                   unsigned int child_clv_index,
+                                   int parent_scaler_index,
+                                   int child_scaler_index,
+                                   const unsigned int * params_indices,
+                                   double * sumtable);
+PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition,
+                                                  int parent_scaler_index,
+                                                  int child_scaler_index,
+                                                  double branch_length,
+                                                  const unsigned int * params_indices,
+                                                  const double * sumtable,
+                                                  double * d_f,
+                                                  double * dd_f);
+
+/* ---- site repeats (src/pll.h:685-734, src/repeats.c) ------------------- */
+
+#define PLL_GET_ID(site_id, site) ((site_id) ? ((site_id)[(site)]) : (site))
+#define PLL_GET_SITE(id_site, site) ((id_site) ? ((id_site)[(site)]) : (site))
+
+PLL_EXPORT int pll_repeats_enabled(const pll_partition_t * partition);          /* repeats.c:46 */
+PLL_EXPORT void pll_resize_repeats_lookup(pll_partition_t * partition,
+                                          unsigned int size);                   /* repeats.c:51 */
+PLL_EXPORT unsigned int pll_get_sites_number(const pll_partition_t * partition,
+                                             unsigned int clv_index);           /* repeats.c:62 */
+PLL_EXPORT unsigned int * pll_get_site_id(const pll_partition_t * partition,
+                                          unsigned int clv_index);              /* repeats.c:79 */
+PLL_EXPORT unsigned int * pll_get_id_site(const pll_partition_t * partition,
+                                          unsigned int clv_index);              /* repeats.c:89 */
+PLL_EXPORT unsigned int pll_get_clv_size(const pll_partition_t * partition,
+                                         unsigned int clv_index);               /* repeats.c:72 */
+PLL_EXPORT unsigned int pll_default_enable_repeats(pll_partition_t * partition,
+                                                   unsigned int left_clv,
+                                                   unsigned int right_clv);     /* repeats.c:100 */
+PLL_EXPORT unsigned int pll_no_enable_repeats(pll_partition_t * partition,
+                                              unsigned int left_clv,
+                                              unsigned int right_clv);          /* repeats.c:112 */
+PLL_EXPORT void pll_default_reallocate_repeats(pll_partition_t * partition,
+                                               unsigned int parent,
+                                               int scaler_index,
+                                               unsigned int sites_to_alloc);    /* repeats.c:256 */
+PLL_EXPORT int pll_update_repeats_tips(pll_partition_t * partition,
+                                       unsigned int tip_index,
+                                       const pll_state_t * map,
+                                       const char * sequence);                  /* repeats.c:189 */
+PLL_EXPORT void pll_update_repeats(pll_partition_t * partition,
+                                   const pll_operation_t * op);                 /* repeats.c:299 */
+PLL_EXPORT void pll_disable_bclv(pll_partition_t * partition);                  /* repeats.c:384 */
+
+/* ---- hardware probe (src/pll.h:2694-2698, src/hardware.c) -------------- */
+
+PLL_EXPORT int pll_hardware_probe(void);
+PLL_EXPORT void pll_hardware_dump(void);
+PLL_EXPORT void pll_hardware_ignore(void);
+
+/* ---- debug printers (src/pll.h:858-866, src/output.c:26,56) ------------ */
+
+PLL_EXPORT void pll_show_pmatrix(const pll_partition_t * partition,
+                                 unsigned int index,
+                                 unsigned int float_precision);
+PLL_EXPORT void pll_show_clv(const pll_partition_t * partition,
+                             unsigned int clv_index,
+                             int scaler_index,
+                             unsigned int float_precision);
+
+/* ======================================================================= *
+ *  Additive CUDA surface (nothing above changes meaning)                   *
+ * ======================================================================= */
+
+/* number of visible CUDA devices; 0 (and pll_errno set) if the runtime fails */
+PLL_EXPORT int pll_cuda_device_count(void);
+/* device used by partitions created afterwards on this thread.  Default:
+ * $PLL_CUDA_DEVICE, else $LOCAL_RANK, else 0. */
+PLL_EXPORT int pll_cuda_set_device(int device);
+PLL_EXPORT int pll_cuda_get_device(const pll_partition_t * partition);
+/* block until all work queued on the partition's stream has finished */
+PLL_EXPORT int pll_cuda_synchronize(const pll_partition_t * partition);
+
+/* explicit device->host reads of device-resident buffers; sizes in elements
+ * are those of the reference buffers (pll_get_clv_size() doubles, etc.) */
+PLL_EXPORT int pll_cuda_download_clv(const pll_partition_t * partition,
+                                     unsigned int clv_index, double * host_out);
+PLL_EXPORT int pll_cuda_download_scaler(const pll_partition_t * partition,
+                                        unsigned int scaler_index,
+                                        unsigned int * host_out);
+PLL_EXPORT int pll_cuda_download_pmatrix(const pll_partition_t * partition,
+                                         unsigned int matrix_index,
+                                         double * host_out);
+/* host->device write of a P-matrix block (parity mode: feed the engine
+ * matrices produced elsewhere) */
+PLL_EXPORT int pll_cuda_upload_pmatrix(pll_partition_t * partition,
+                                       unsigned int matrix_index,
+                                       const double * host_in);
+PLL_EXPORT int pll_cuda_download_sumtable(const pll_partition_t * partition,
+                                          const double * sumtable_handle,
+                                          double * host_out);
+/* number of elements of a scale buffer as currently allocated */
+PLL_EXPORT unsigned int pll_cuda_scaler_size(const pll_partition_t * partition,
+                                             unsigned int scaler_index);
+
+/* Asynchronous variants for multi-GPU site sharding: results (logL, or
+ * {d_f, dd_f}) are left in DEVICE memory at `dev_out` on the partition's
+ * stream, so that a collective (NCCL all-reduce) can consume them without a
+ * host round trip.  `dev_out` must be a device pointer on the partition's
+ * device.  pll_cuda_synchronize() orders the stream with the host. */
+PLL_EXPORT int pll_cuda_edge_loglikelihood_async(pll_partition_t * partition,
+                                                 unsigned int parent_clv_index,
+                                                 int parent_scaler_index,
+                                                 unsigned int child_clv_index,
+                                                 int child_scaler_index,
+                                                 unsigned int matrix_index,
+                                                 const unsigned int * freqs_indices,
+                                                 double * dev_out);
+PLL_EXPORT int pll_cuda_root_loglikelihood_async(pll_partition_t * partition,
+                                                 unsigned int clv_index,
+                                                 int scaler_index,
+                                                 const unsigned int * freqs_indices,
+                                                 double * dev_out);
+PLL_EXPORT int pll_cuda_likelihood_derivatives_async(pll_partition_t * partition,
+                                                     int parent_scaler_index,
+                                                     int child_scaler_index,
+                                                     double branch_length,
+                                                     const unsigned int * params_indices,
+                                                     const double * sumtable,
+                                                     double * dev_out2);
+
+/* Level schedule of an operation list (pure host logic, no device needed):
+ * writes for each op the launch level it is batched into (ops of one level are
+ * mutually independent and run in one kernel launch); returns the number of
+ * levels, or -1 on error.  RAW, WAR and WAW hazards on CLV and scaler indices
+ * are honoured (reference semantics: strictly sequential, src/partials.c:253). */
+PLL_EXPORT int pll_cuda_schedule_levels(const pll_operation_t * operations,
+                                        unsigned int count,
+                                        unsigned int * level_of_op);
+
+/* counters for benchmarking: kernels launched by this library on this thread */
+PLL_EXPORT unsigned long long pll_cuda_kernel_launches(void);
+
+/* host eigendecomposition used by pll_update_eigen, exposed for tests:
+ * same inputs/outputs as the reference routine (models.c:293-410) on plain
+ * arrays; returns PLL_SUCCESS/PLL_FAILURE */
+PLL_EXPORT int pll_cuda_host_eigen(unsigned int states, unsigned int states_padded,
+                                   const double * subst_params,
+                                   const double * freqs,
+                                   double * eigenvecs, double * inv_eigenvecs,
+                                   double * eigenvals);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PLL_B200_H_ */
