@@ -387,8 +387,18 @@ PLL_EXPORT int pll_cuda_device_count(void);
  * $PLL_CUDA_DEVICE, else $LOCAL_RANK, else 0. */
 PLL_EXPORT int pll_cuda_set_device(int device);
 PLL_EXPORT int pll_cuda_get_device(const pll_partition_t * partition);
+/* the CUDA stream (a cudaStream_t) every kernel and copy of this partition is
+ * queued on: record events on it to time the device work, or order a
+ * collective after it */
+PLL_EXPORT void * pll_cuda_get_stream(const pll_partition_t * partition);
 /* block until all work queued on the partition's stream has finished */
 PLL_EXPORT int pll_cuda_synchronize(const pll_partition_t * partition);
+
+/* pattern_weights / tipmap are host arrays with device mirrors refreshed by
+ * their setters; after writing to those struct fields directly call this so the
+ * next evaluation re-uploads them (small model arrays are compared byte-wise
+ * on every call and need no notification) */
+PLL_EXPORT int pll_cuda_invalidate_host_arrays(pll_partition_t * partition);
 
 /* explicit device->host reads of device-resident buffers; sizes in elements
  * are those of the reference buffers (pll_get_clv_size() doubles, etc.) */

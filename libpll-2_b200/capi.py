@@ -137,6 +137,8 @@ _PROTOS = {
     "pll_repeats_enabled": (C.c_int, [PartitionP]),
     "pll_get_sites_number": (C.c_uint, [PartitionP, C.c_uint]),
     "pll_get_clv_size": (C.c_uint, [PartitionP, C.c_uint]),
+    "pll_get_site_id": (c_uint_p, [PartitionP, C.c_uint]),
+    "pll_get_id_site": (c_uint_p, [PartitionP, C.c_uint]),
     "pll_resize_repeats_lookup": (None, [PartitionP, C.c_uint]),
     "pll_disable_bclv": (None, [PartitionP]),
     "pll_aligned_alloc": (C.c_void_p, [C.c_size_t, C.c_size_t]),
@@ -149,6 +151,7 @@ _CUDA_PROTOS = {
     "pll_cuda_device_count": (C.c_int, []),
     "pll_cuda_set_device": (C.c_int, [C.c_int]),
     "pll_cuda_get_device": (C.c_int, [PartitionP]),
+    "pll_cuda_get_stream": (C.c_void_p, [PartitionP]),
     "pll_cuda_synchronize": (C.c_int, [PartitionP]),
     "pll_cuda_download_clv": (C.c_int, [PartitionP, C.c_uint, c_double_p]),
     "pll_cuda_download_scaler": (C.c_int, [PartitionP, C.c_uint, c_uint_p]),
@@ -165,6 +168,7 @@ _CUDA_PROTOS = {
         C.c_int,
         [PartitionP, C.c_int, C.c_int, C.c_double, c_uint_p, c_double_p, C.c_void_p],
     ),
+    "pll_cuda_invalidate_host_arrays": (C.c_int, [PartitionP]),
     "pll_cuda_schedule_levels": (C.c_int, [C.POINTER(Operation), C.c_uint, c_uint_p]),
     "pll_cuda_kernel_launches": (C.c_ulonglong, []),
     "pll_cuda_host_eigen": (
@@ -216,6 +220,7 @@ def exported_symbols_declared_in_header(header_path: str) -> list[str]:
 
     text = open(header_path).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"#define[^\n]*", "", text)
     names = []
     for m in re.finditer(r"PLL_EXPORT\s+[^;{]*?\b(pll_[A-Za-z0-9_]+)\s*(\(|\[|;)", text):
         names.append(m.group(1))

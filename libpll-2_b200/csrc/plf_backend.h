@@ -1,0 +1,191 @@
+/*
+ * plf_backend.h -- thin C-ABI between the C host layer (pll_host.c) and the
+ * sm_100a CUDA translation units (plf_*.cu).  Plain pointers and sizes only.
+ * Internal: callers of the library use include/pll_b200.h.
+ */
+#ifndef PLF_BACKEND_H_
+#define PLF_BACKEND_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct plf_ctx plf_ctx_t; /* device, stream, workspaces */
+
+typedef struct plf_shape
+{
+  unsigned int states;
+  unsigned int states_padded;
+  unsigned int rate_cats;
+  int per_rate_scalers; /* PLL_ATTRIB_RATE_SCALERS */
+} plf_shape_t;
+
+/* One CLV update as the device sees it (pointers already resolved).
+ * kind: 0 inner-inner, 1 tip-inner (tip is always "left"), 2 tip-tip.
+ * The *_id arrays are NULL unless site repeats compress the node. */
+enum { PLF_OP_II = 0, PLF_OP_TI = 1, PLF_OP_TT = 2 };
+typedef struct plf_op
+{
+  double * parent_clv;
+  const double * left_clv;
+  const double * right_clv;
+  const unsigned char * left_tip;
+  const unsigned char * right_tip;
+  const double * left_matrix;
+  const double * right_matrix;
+  unsigned int * parent_scaler;
+  const unsigned int * left_scaler;
+  const unsigned int * right_scaler;
+  const unsigned int * parent_id_site;
+  const unsigned int * left_site_id;
+  const unsigned int * right_site_id;
+  unsigned int nsites;
+  unsigned int kind;
+} plf_op_t;
+
+/* Model block in device memory, all doubles, per RATE CATEGORY (indices
+ * already resolved through params_indices / freqs_indices):
+ *   rates[R] weights[R] pinv[R] freqs[R][sp] evals[R][sp]
+ *   evecs[R][st*sp] ievecs[R][st*sp]                                   */
+static inline size_t plf_model_doubles(unsigned int R, unsigned int st,
+                                       unsigned int sp)
+{
+  return (size_t)3 * R + (size_t)2 * R * sp + (size_t)2 * R * st * sp;
+}
+
+/* arguments of the log-likelihood kernels (edge when pmatrix != NULL) */
+typedef struct plf_lk
+{
+  unsigned int sites;
+  const double * clvp;
+  const unsigned int * pscaler;
+  const unsigned int * p_site_id; /* repeats gather or NULL */
+  const double * clvc;            /* NULL for tip child / root */
+  const unsigned int * cscaler;
+  const unsigned int * c_site_id;
+  const unsigned char * tipchars; /* child is a pattern tip */
+  const unsigned long long * tipmap;
+  const double * pmatrix;         /* NULL => root log-likelihood */
+  const double * model;
+  const unsigned int * pattern_weights;
+  const int * invariant;          /* NULL when no +I */
+  double * persite;               /* device [sites] or NULL */
+} plf_lk_t;
+
+typedef struct plf_sumtable
+{
+  unsigned int sites;
+  const double * clvp;            /* "parent" side: uses pi * Vinv */
+  const unsigned int * pscaler;
+  const unsigned int * p_site_id;
+  const double * clvc;            /* "child" side: uses V */
+  const unsigned int * cscaler;
+  const unsigned int * c_site_id;
+  const unsigned char * tipchars; /* parent side is a pattern tip */
+  const unsigned long long * tipmap;
+  const double * model;
+  double * sumtable;              /* device [sites][R][sp] */
+} plf_sumtable_t;
+
+typedef struct plf_deriv
+{
+  unsigned int sites;
+  const double * sumtable;
+  const double * model;
+  const unsigned int * pattern_weights;
+  const int * invariant;
+  double branch_length;
+} plf_deriv_t;
+
+/* ---- context and memory ------------------------------------------------ */
+int plf_device_count(char * err, size_t errlen);
+int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * err,
+                   size_t errlen);
+void plf_ctx_destroy(plf_ctx_t * ctx);
+int plf_ctx_device(const plf_ctx_t * ctx);
+void * plf_ctx_stream(const plf_ctx_t * ctx);
+const char * plf_last_error(const plf_ctx_t * ctx);
+void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero);
+void plf_free(plf_ctx_t * ctx, void * p);
+int plf_upload(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
+int plf_download(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
+int plf_memset0(plf_ctx_t * ctx, void * dst, size_t bytes);
+int plf_sync(plf_ctx_t * ctx);
+unsigned long long plf_kernel_launches(void);
+void plf_device_description(const plf_ctx_t * ctx, char * buf, size_t len);
+
+/* ---- the hot path ------------------------------------------------------ */
+
+/* P = I + Vinv diag(expm1(lambda r t / (1-pinv))) V for `count` matrices.
+ * h_expd: NULL => expm1 on device; else host-computed expm1 values
+ * [count][R][states] (bit-exact parity mode). */
+int plf_update_pmatrices(plf_ctx_t * ctx, const plf_shape_t * sh,
+                         const double * d_model, double * d_pmatrix_base,
+                         const unsigned int * h_matrix_indices,
+                         const double * h_branch_lengths, unsigned int count,
+                         const double * h_expd);
+
+/* CLV updates: ops grouped into `nlevels` levels (level l = ops
+ * [h_level_start[l], h_level_start[l+1]) ); one kernel launch per level */
+int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh,
+                        const plf_op_t * h_ops, unsigned int nops,
+                        const unsigned int * h_level_start,
+                        unsigned int nlevels,
+                        const unsigned long long * d_tipmap,
+                        unsigned int maxstates);
+
+/* results: d_out (device, may be NULL) and/or h_out (host, may be NULL; when
+ * given the call synchronises the stream) */
+int plf_loglikelihood(plf_ctx_t * ctx, const plf_shape_t * sh,
+                      const plf_lk_t * a, double * d_out, double * h_out);
+int plf_update_sumtable(plf_ctx_t * ctx, const plf_shape_t * sh,
+                        const plf_sumtable_t * a);
+int plf_derivatives(plf_ctx_t * ctx, const plf_shape_t * sh,
+                    const plf_deriv_t * a, double * d_out2, double * h_out2);
+
+/* invariant-site detection (models.c:651-752): AND over tips of the per-site
+ * state masks; out[site] = state index or -1 */
+int plf_invariant_sites(plf_ctx_t * ctx, const plf_shape_t * sh,
+                        unsigned int sites, unsigned int tips,
+                        const unsigned char * const * d_tipchars_or_null,
+                        const double * const * d_tipclv_or_null,
+                        const unsigned int * const * d_tip_site_id_or_null,
+                        const unsigned long long * d_tipmap, int * d_out);
+
+/* site-repeat class identifiers of a parent node (repeats.c:299-382) computed
+ * on device; returns the class count through *h_ids (0 = no compression).
+ * d_lookup: lookup_size entries, all 0xFFFFFFFF on entry and on exit. */
+int plf_repeats_ids(plf_ctx_t * ctx, unsigned int sites,
+                    const unsigned int * d_site_id_left, unsigned int ids_left,
+                    const unsigned int * d_site_id_right,
+                    unsigned int * d_site_id_parent,
+                    unsigned int * d_id_site_parent, unsigned int * d_lookup,
+                    unsigned int * h_ids);
+
+/* tip CLV from a sequence of state characters: entry n (site id_site[n] when
+ * repeats compress the tip) gets bit j of map[seq[site]] replicated over rates
+ * (src/pll.c:959-1024) */
+int plf_tip_clv_from_states(plf_ctx_t * ctx, const plf_shape_t * sh,
+                            double * d_clv, const unsigned char * d_seq,
+                            const unsigned long long * d_map,
+                            const unsigned int * d_id_site,
+                            unsigned int entries);
+/* keys[s] = charmap[seq[s]] (tip class codes for plf_repeats_ids with
+ * d_site_id_right == NULL, where the key is the left identifier itself) */
+int plf_tip_keys(plf_ctx_t * ctx, const unsigned char * d_seq,
+                 const unsigned char * d_charmap, unsigned int sites,
+                 unsigned int * d_keys);
+int plf_copy_d2d(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
+int plf_fill_u32(plf_ctx_t * ctx, unsigned int * d, unsigned int value,
+                 size_t n);
+/* like plf_upload but does not wait: `src` must be pageable memory owned by
+ * the library (the driver stages it before returning) */
+int plf_upload_async(plf_ctx_t * ctx, void * dst, const void * src,
+                     size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

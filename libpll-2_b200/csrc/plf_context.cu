@@ -1,0 +1,314 @@
+/*
+ * plf_context.cu -- device context, memory plumbing and the P-matrix kernel.
+ */
+#include "plf_backend.h"
+#include "plf_device.cuh"
+#include "plf_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static __thread unsigned long long g_launches = 0;
+void plf_count_launch(void) { ++g_launches; }
+extern "C" unsigned long long plf_kernel_launches(void) { return g_launches; }
+
+void plf_set_error(plf_ctx * ctx, const char * fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char * plf_last_error(const plf_ctx_t * ctx) { return ctx->err; }
+extern "C" int plf_ctx_device(const plf_ctx_t * ctx) { return ctx->device; }
+extern "C" void * plf_ctx_stream(const plf_ctx_t * ctx) { return (void *)ctx->stream; }
+
+extern "C" int plf_device_count(char * err, size_t errlen)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess)
+  {
+    if (err) snprintf(err, errlen, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * err, size_t errlen)
+{
+  *out = NULL;
+  int n = plf_device_count(err, errlen);
+  if (n <= 0)
+  {
+    if (err && !err[0]) snprintf(err, errlen, "no CUDA device is visible (there is no CPU fallback)");
+    return 0;
+  }
+  if (device < 0 || device >= n)
+  {
+    if (err) snprintf(err, errlen, "CUDA device %d requested, %d visible", device, n);
+    return 0;
+  }
+  plf_ctx * ctx = (plf_ctx *)calloc(1, sizeof(plf_ctx));
+  if (!ctx) return 0;
+  ctx->device = device;
+  ctx->managed = managed;
+  cudaError_t e = cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess && prop.major < 10)
+  {
+    if (err)
+      snprintf(err, errlen, "device %d (%s, sm_%d%d) is not Blackwell: this library is built for sm_100a only",
+               device, prop.name, prop.major, prop.minor);
+    free(ctx);
+    return 0;
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_result, 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_result, 4 * sizeof(double));
+  if (e != cudaSuccess)
+  {
+    if (err) snprintf(err, errlen, "CUDA context setup failed: %s", cudaGetErrorString(e));
+    free(ctx);
+    return 0;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  snprintf(ctx->name, sizeof(ctx->name), "%s sm_%d%d, %d SMs, %.1f GB", prop.name, prop.major, prop.minor,
+           prop.multiProcessorCount, (double)prop.totalGlobalMem / 1e9);
+  *out = ctx;
+  return 1;
+}
+
+extern "C" void plf_device_description(const plf_ctx_t * ctx, char * buf, size_t len)
+{
+  snprintf(buf, len, "%s", ctx->name);
+}
+
+extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->ws_ops.ptr);
+  cudaFree(ctx->ws_small.ptr);
+  cudaFree(ctx->ws_partial.ptr);
+  cudaFree(ctx->d_result);
+  cudaFreeHost(ctx->h_result);
+  cudaStreamDestroy(ctx->stream);
+  free(ctx);
+}
+
+void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes)
+{
+  if (ws->bytes >= bytes && ws->ptr) return ws->ptr;
+  if (ws->ptr)
+  {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ws->ptr);
+    ws->ptr = NULL;
+    ws->bytes = 0;
+  }
+  size_t want = bytes < 4096 ? 4096 : bytes + bytes / 2;
+  cudaError_t e = cudaMalloc(&ws->ptr, want);
+  if (e != cudaSuccess)
+  {
+    plf_set_error(ctx, "workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    ws->ptr = NULL;
+    return NULL;
+  }
+  ws->bytes = want;
+  return ws->ptr;
+}
+
+extern "C" void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero)
+{
+  void * p = NULL;
+  if (!bytes) bytes = 8;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return NULL;
+  cudaError_t e;
+  if (ctx->managed)
+  {
+    e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
+    if (e == cudaSuccess) cudaMemPrefetchAsync(p, bytes, ctx->device, ctx->stream);
+  }
+  else
+    e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess)
+  {
+    plf_set_error(ctx, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return NULL;
+  }
+  if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+  return p;
+}
+
+extern "C" void plf_free(plf_ctx_t * ctx, void * p)
+{
+  if (!p) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(p);
+}
+
+extern "C" int plf_upload(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes)
+{
+  if (!bytes) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  /* the source may be a caller buffer that is reused right away: pageable
+   * copies are staged by the driver before returning, pinned ones are not */
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+extern "C" int plf_upload_async(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes)
+{
+  if (!bytes) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 1;
+}
+
+extern "C" int plf_download(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes)
+{
+  if (!bytes) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+extern "C" int plf_memset0(plf_ctx_t * ctx, void * dst, size_t bytes)
+{
+  if (!bytes) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+  return 1;
+}
+
+extern "C" int plf_sync(plf_ctx_t * ctx)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+/* ------------------------------------------------------------------------ *
+ *  P-matrices: one block per (matrix, rate category).                       *
+ *  Reference: pll_core_update_pmatrix (src/core_pmatrix.c:24), 4x4 AVX       *
+ *  (src/core_pmatrix_avx.c:42) and 20x20 AVX2 (src/core_pmatrix_avx2.c:49)   *
+ *  evaluation orders, see oracle/plf_oracle.c:orc_update_pmatrix.            *
+ * ------------------------------------------------------------------------ */
+__global__ void k_pmatrix(double * __restrict__ pbase, const double * __restrict__ model,
+                          const unsigned int * __restrict__ matrix_indices,
+                          const double * __restrict__ branch_lengths,
+                          const double * __restrict__ expd_host, int st, int sp, int R)
+{
+  extern __shared__ double sm[];
+  double * e = sm;            /* [sp]      expm1 values       */
+  double * tmp = sm + sp;     /* [st][st]  Vinv * diag(e)     */
+  const int i = blockIdx.x, n = blockIdx.y;
+  const double t = branch_lengths[i];
+  double * pmat = pbase + ((size_t)matrix_indices[i] * R + n) * st * sp;
+  const double rate = model[n];
+  const double pinv = model[2 * R + n];
+  const double * evals = model + 3 * R + (size_t)R * sp + (size_t)n * sp;
+  const double * evecs = model + 3 * R + (size_t)2 * R * sp + (size_t)n * st * sp;
+  const double * ievecs = evecs + (size_t)R * st * sp;
+  const bool fixed = (st == 4 || st == 20);
+
+  if (!(t > 0.0))
+  {
+    /* identity (core_pmatrix.c:243-248; the 4/20 kernels also clear padding) */
+    const int cols = fixed ? sp : st;
+    for (int x = threadIdx.x; x < st * cols; x += blockDim.x)
+    {
+      const int j = x / cols, k = x % cols;
+      pmat[j * sp + k] = (j == k) ? 1.0 : 0.0;
+    }
+    return;
+  }
+  for (int j = threadIdx.x; j < st; j += blockDim.x)
+  {
+    if (expd_host)
+      e[j] = expd_host[((size_t)i * R + n) * st + j];
+    else
+    {
+      double x = (evals[j] * rate) * t;
+      if (pinv > 1e-8) x = x / (1.0 - pinv);
+      e[j] = expm1(x);
+    }
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < st * st; x += blockDim.x)
+  {
+    const int j = x / st, m = x % st;
+    tmp[x] = (st == 20) ? e[m] * ievecs[j * sp + m] : ievecs[j * sp + m] * e[m];
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < st * st; x += blockDim.x)
+  {
+    const int j = x / st, k = x % st;
+    const double * tj = tmp + j * st;
+    double v;
+    if (st == 4)
+    {
+      const double p0 = tj[0] * evecs[0 * 4 + k], p1 = tj[1] * evecs[1 * 4 + k];
+      const double p2 = tj[2] * evecs[2 * 4 + k], p3 = tj[3] * evecs[3 * 4 + k];
+      v = ((p0 + p1) + (p2 + p3)) + ((j == k) ? 1.0 : 0.0);
+    }
+    else if (st == 20)
+    {
+      double a[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+      {
+        a[l] = tj[l] * evecs[l * 20 + k];
+        for (int q = 1; q < 5; ++q) a[l] = fma(tj[l + 4 * q], evecs[(l + 4 * q) * 20 + k], a[l]);
+      }
+      v = (a[0] + a[1]) + (a[2] + a[3]);
+      if (j == k) v += 1.0;
+    }
+    else
+    {
+      v = (j == k) ? 1.0 : 0.0;
+      for (int m = 0; m < st; ++m) v += tj[m] * evecs[m * sp + k];
+    }
+    pmat[j * sp + k] = v;
+  }
+}
+
+extern "C" int plf_update_pmatrices(plf_ctx_t * ctx, const plf_shape_t * sh, const double * d_model,
+                                    double * d_pmatrix_base, const unsigned int * h_matrix_indices,
+                                    const double * h_branch_lengths, unsigned int count,
+                                    const double * h_expd)
+{
+  if (!count) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  const unsigned int R = sh->rate_cats, st = sh->states, sp = sh->states_padded;
+  const size_t nb_idx = ((size_t)count * sizeof(unsigned int) + 15) & ~(size_t)15;
+  const size_t nb_bl = (size_t)count * sizeof(double);
+  const size_t nb_ex = h_expd ? (size_t)count * R * st * sizeof(double) : 0;
+  char * ws = (char *)plf_ws_reserve(ctx, &ctx->ws_small, nb_idx + nb_bl + nb_ex);
+  if (!ws) return 0;
+  PLF_CHECK(ctx, cudaMemcpyAsync(ws, h_matrix_indices, count * sizeof(unsigned int), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  PLF_CHECK(ctx, cudaMemcpyAsync(ws + nb_idx, h_branch_lengths, nb_bl, cudaMemcpyHostToDevice, ctx->stream));
+  if (h_expd)
+    PLF_CHECK(ctx, cudaMemcpyAsync(ws + nb_idx + nb_bl, h_expd, nb_ex, cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid(count, R);
+  const int threads = st * st >= 256 ? 256 : (st * st >= 64 ? 128 : 32);
+  const size_t smem = ((size_t)sp + (size_t)st * st) * sizeof(double);
+  k_pmatrix<<<grid, threads, smem, ctx->stream>>>(d_pmatrix_base, d_model, (const unsigned int *)ws,
+                                                 (const double *)(ws + nb_idx),
+                                                 h_expd ? (const double *)(ws + nb_idx + nb_bl) : NULL, (int)st,
+                                                 (int)sp, (int)R);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}

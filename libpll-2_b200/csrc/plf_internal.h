@@ -1,0 +1,44 @@
+/* plf_internal.h -- shared by the .cu translation units only. */
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+struct plf_ws
+{
+  void * ptr;
+  size_t bytes;
+};
+
+struct plf_ctx
+{
+  int device;
+  int managed;
+  int sm_count;
+  size_t smem_optin;
+  size_t gen20_smem_set;
+  size_t lk20_smem_set;
+  cudaStream_t stream;
+  plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
+  plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
+  plf_ws ws_partial;  /* per-block partial sums of the reductions              */
+  double * d_result;  /* 4 doubles                                             */
+  double * h_result;  /* pinned, 4 doubles                                     */
+  char err[256];
+  char name[128];
+};
+
+void plf_set_error(plf_ctx * ctx, const char * fmt, ...);
+void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes);
+void plf_count_launch(void);
+
+#define PLF_CHECK(ctx, call)                                                         \
+  do                                                                                 \
+  {                                                                                  \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess)                                                           \
+    {                                                                                \
+      plf_set_error((ctx), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                    __FILE__, __LINE__);                                             \
+      return 0;                                                                      \
+    }                                                                                \
+  } while (0)

@@ -1,0 +1,265 @@
+/*
+ * plf_misc.cu -- small device passes around the hot path:
+ *   - tip CLVs from state masks            (reference set_tipclv, src/pll.c:959-1024)
+ *   - invariant-site detection             (src/models.c:651-752)
+ *   - site-repeat class identifiers        (src/repeats.c:299-382), bit-exact
+ */
+#include "plf_backend.h"
+#include "plf_device.cuh"
+#include "plf_internal.h"
+
+/* ---- tip CLVs ------------------------------------------------------------ */
+__global__ void k_tip_clv(double * __restrict__ clv, const unsigned char * __restrict__ seq,
+                          const plf_state_t * __restrict__ map, const unsigned int * __restrict__ id_site,
+                          unsigned int entries, int st, int sp, int R)
+{
+  const size_t total = (size_t)entries * R * sp;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x)
+  {
+    const unsigned int n = (unsigned int)(x / ((size_t)R * sp));
+    const int j = (int)(x % sp);
+    const unsigned int site = id_site ? id_site[n] : n;
+    const plf_state_t m = map[seq[site]];
+    clv[x] = (j < st && ((m >> j) & 1ull)) ? 1.0 : 0.0;
+  }
+}
+
+extern "C" int plf_tip_clv_from_states(plf_ctx_t * ctx, const plf_shape_t * sh, double * d_clv,
+                                       const unsigned char * d_seq, const unsigned long long * d_map,
+                                       const unsigned int * d_id_site, unsigned int entries)
+{
+  if (!entries) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  const size_t total = (size_t)entries * sh->rate_cats * sh->states_padded;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+  k_tip_clv<<<(unsigned int)blocks, 256, 0, ctx->stream>>>(d_clv, d_seq, d_map, d_id_site, entries,
+                                                          (int)sh->states, (int)sh->states_padded,
+                                                          (int)sh->rate_cats);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
+/* ---- invariant sites ------------------------------------------------------ */
+__global__ void k_invariant(int * __restrict__ out, unsigned int sites, unsigned int tips,
+                            const unsigned char * const * __restrict__ tipchars,
+                            const double * const * __restrict__ tipclv,
+                            const unsigned int * const * __restrict__ tip_site_id,
+                            const plf_state_t * __restrict__ tipmap, int st, int sp, int R)
+{
+  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+  {
+    plf_state_t acc = (st >= 64) ? ~0ull : ((1ull << st) - 1ull);
+    for (unsigned int t = 0; t < tips && acc; ++t)
+    {
+      plf_state_t m = 0;
+      if (tipchars)
+      {
+        const unsigned int c = tipchars[t][s];
+        m = (st == 4) ? (plf_state_t)c : tipmap[c];
+      }
+      else
+      {
+        const unsigned int id = (tip_site_id && tip_site_id[t]) ? tip_site_id[t][s] : s;
+        const double * c = tipclv[t] + (size_t)id * R * sp;
+        for (int k = 0; k < st; ++k) m |= ((plf_state_t)c[k]) << k;
+      }
+      acc &= m;
+    }
+    out[s] = (acc == 0 || __popcll(acc) > 1) ? -1 : (__ffsll((long long)acc) - 1);
+  }
+}
+
+extern "C" int plf_invariant_sites(plf_ctx_t * ctx, const plf_shape_t * sh, unsigned int sites, unsigned int tips,
+                                   const unsigned char * const * d_tipchars, const double * const * d_tipclv,
+                                   const unsigned int * const * d_tip_site_id,
+                                   const unsigned long long * d_tipmap, int * d_out)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  unsigned int blocks = (sites + 255) / 256;
+  if (blocks > (unsigned int)ctx->sm_count * 8) blocks = (unsigned int)ctx->sm_count * 8;
+  k_invariant<<<blocks, 256, 0, ctx->stream>>>(d_out, sites, tips, d_tipchars, d_tipclv, d_tip_site_id, d_tipmap,
+                                              (int)sh->states, (int)sh->states_padded, (int)sh->rate_cats);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
+/* ---- site-repeat identifiers ----------------------------------------------- *
+ * The reference numbers the classes of a parent node by order of FIRST
+ * OCCURRENCE while scanning sites 0..S-1 of the key
+ *     key[s] = id_left[s] + id_right[s] * ids_left
+ * through a dense lookup table (repeats.c:334-347).  Deterministic parallel
+ * equivalent:
+ *   1. lookup[key[s]] = min over s (atomicMin)        -> first site of each class
+ *   2. first[s] = (lookup[key[s]] == s); exclusive scan of first[] -> rank
+ *   3. site_id[s] = rank[lookup[key[s]]]; id_site[rank[s]] = s where first[s]
+ *   4. lookup[key[s]] = EMPTY again
+ * The scan is a three-kernel block scan over 1024-site tiles.                  */
+
+#define SCAN_TILE 1024
+/* idr == NULL: the key is idl[s] itself (tip class codes) */
+#define REP_KEY(s) (idr ? idl[(s)] + idr[(s)] * ids_left : idl[(s)])
+
+__global__ void k_rep_min(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
+                          unsigned int ids_left, unsigned int sites, unsigned int * __restrict__ lookup)
+{
+  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+    atomicMin(&lookup[REP_KEY(s)], s);
+}
+
+/* per-tile count of first occurrences */
+__global__ void k_rep_count(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
+                            unsigned int ids_left, unsigned int sites, const unsigned int * __restrict__ lookup,
+                            unsigned int * __restrict__ tile_count)
+{
+  __shared__ unsigned int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const unsigned int base = blockIdx.x * SCAN_TILE;
+  unsigned int mine = 0;
+  for (unsigned int s = base + threadIdx.x; s < base + SCAN_TILE && s < sites; s += blockDim.x)
+    mine += (lookup[REP_KEY(s)] == s);
+  atomicAdd(&cnt, mine); /* integer: order-independent */
+  __syncthreads();
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = cnt;
+}
+
+/* exclusive scan of tile counts by one block; total to *total */
+__global__ void k_rep_scan_tiles(unsigned int * __restrict__ tile_count, unsigned int ntiles,
+                                 unsigned int * __restrict__ total)
+{
+  __shared__ unsigned int buf[1024];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (unsigned int base = 0; base < ntiles; base += 1024)
+  {
+    const unsigned int i = base + threadIdx.x;
+    const unsigned int v = i < ntiles ? tile_count[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (unsigned int o = 1; o < 1024; o <<= 1)
+    {
+      unsigned int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_count[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+/* rank of each first occurrence; stored in-place of the lookup entry's class:
+ * rank_of_site[s] for first occurrences, and id_site[rank] = s */
+__global__ void k_rep_rank(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
+                           unsigned int ids_left, unsigned int sites, const unsigned int * __restrict__ lookup,
+                           const unsigned int * __restrict__ tile_offset, unsigned int * __restrict__ rank_of_site,
+                           unsigned int * __restrict__ id_site)
+{
+  __shared__ unsigned int buf[SCAN_TILE];
+  const unsigned int s = blockIdx.x * SCAN_TILE + threadIdx.x;
+  const unsigned int f = (s < sites) ? (lookup[REP_KEY(s)] == s) : 0u;
+  buf[threadIdx.x] = f;
+  __syncthreads();
+  for (unsigned int o = 1; o < SCAN_TILE; o <<= 1)
+  {
+    unsigned int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+    __syncthreads();
+    buf[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (f)
+  {
+    const unsigned int r = tile_offset[blockIdx.x] + buf[threadIdx.x] - 1;
+    rank_of_site[s] = r;
+    id_site[r] = s;
+  }
+}
+
+__global__ void k_rep_assign(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
+                             unsigned int ids_left, unsigned int sites, const unsigned int * __restrict__ lookup,
+                             const unsigned int * __restrict__ rank_of_site, unsigned int * __restrict__ site_id)
+{
+  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+    site_id[s] = rank_of_site[lookup[REP_KEY(s)]];
+}
+
+__global__ void k_rep_clean(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
+                            unsigned int ids_left, unsigned int sites, unsigned int * __restrict__ lookup)
+{
+  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+    lookup[REP_KEY(s)] = 0xFFFFFFFFu;
+}
+
+extern "C" int plf_repeats_ids(plf_ctx_t * ctx, unsigned int sites, const unsigned int * d_idl,
+                               unsigned int ids_left, const unsigned int * d_idr, unsigned int * d_site_id,
+                               unsigned int * d_id_site, unsigned int * d_lookup, unsigned int * h_ids)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  const unsigned int ntiles = (sites + SCAN_TILE - 1) / SCAN_TILE;
+  /* workspace: tile counts [ntiles] + total [1] + rank_of_site [sites] */
+  unsigned int * ws = (unsigned int *)plf_ws_reserve(ctx, &ctx->ws_partial,
+                                                     ((size_t)ntiles + 1 + sites) * sizeof(unsigned int));
+  if (!ws) return 0;
+  unsigned int * tile = ws, * total = ws + ntiles, * rank = ws + ntiles + 1;
+  unsigned int blocks = (sites + 255) / 256;
+  if (blocks > (unsigned int)ctx->sm_count * 8) blocks = (unsigned int)ctx->sm_count * 8;
+  k_rep_min<<<blocks, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup);
+  k_rep_count<<<ntiles, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup, tile);
+  k_rep_scan_tiles<<<1, 1024, 0, ctx->stream>>>(tile, ntiles, total);
+  k_rep_rank<<<ntiles, SCAN_TILE, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup, tile, rank, d_id_site);
+  k_rep_assign<<<blocks, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup, rank, d_site_id);
+  k_rep_clean<<<blocks, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup);
+  for (int i = 0; i < 6; ++i) plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  PLF_CHECK(ctx, cudaMemcpyAsync(ctx->h_result, total, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  *h_ids = *(unsigned int *)ctx->h_result;
+  return 1;
+}
+
+/* keys[s] = class code of the tip character at site s (repeats.c:204-216) */
+__global__ void k_tip_keys(const unsigned char * __restrict__ seq, const unsigned char * __restrict__ charmap,
+                           unsigned int sites, unsigned int * __restrict__ keys)
+{
+  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+    keys[s] = charmap[seq[s]];
+}
+
+extern "C" int plf_tip_keys(plf_ctx_t * ctx, const unsigned char * d_seq, const unsigned char * d_charmap,
+                            unsigned int sites, unsigned int * d_keys)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  unsigned int blocks = (sites + 255) / 256;
+  if (blocks > (unsigned int)ctx->sm_count * 8) blocks = (unsigned int)ctx->sm_count * 8;
+  k_tip_keys<<<blocks, 256, 0, ctx->stream>>>(d_seq, d_charmap, sites, d_keys);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
+extern "C" int plf_copy_d2d(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes)
+{
+  if (!bytes) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 1;
+}
+
+extern "C" int plf_fill_u32(plf_ctx_t * ctx, unsigned int * d, unsigned int value, size_t n)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (value == 0 || value == 0xFFFFFFFFu)
+  {
+    PLF_CHECK(ctx, cudaMemsetAsync(d, value ? 0xFF : 0, n * sizeof(unsigned int), ctx->stream));
+    return 1;
+  }
+  plf_set_error(ctx, "plf_fill_u32: only 0 and 0xFFFFFFFF are supported");
+  return 0;
+}

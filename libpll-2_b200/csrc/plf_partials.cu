@@ -1,0 +1,501 @@
+/*
+ * plf_partials.cu -- CLV update kernels (sm_100a), one launch per LEVEL of the
+ * operation list: blockIdx.y selects the op, blockIdx.x strides over its sites.
+ *
+ * Replaces pll_core_update_partial_{ii,ti,tt} and the repeats variants
+ * (reference src/core_partials.c:82,354,510,612 and their AVX/AVX2 versions)
+ * plus the separate scaler pass pll_fill_parent_scaler (src/pll.c:1202), which
+ * is fused here.
+ *
+ * Thread mapping: one thread per (site, rate) block of states_padded doubles
+ * when rate_cats is a power of two <= 32 (the R lanes of a site are adjacent
+ * lanes of one warp and agree on per-site scaling with shuffles); otherwise one
+ * thread per site looping over the rates.  For DNA a (site, rate) block is 32
+ * bytes = one 256-bit load/store, a warp touches 1 KB contiguous per access,
+ * and the two 4x4 P-matrices of the thread's rate live in registers for the
+ * whole kernel.
+ */
+#include "plf_backend.h"
+#include "plf_device.cuh"
+#include "plf_internal.h"
+
+/* ------------------------------------------------------------------------ *
+ *  DNA (4 states)                                                           *
+ * ------------------------------------------------------------------------ */
+
+struct DnaItem
+{
+  dbl4 l, r;
+  unsigned int n, lid, rid, lcode, rcode;
+  bool active;
+};
+
+template <int ONE_RATE>
+__global__ void __launch_bounds__(256, 2)
+k_partials_dna(const plf_op_t * __restrict__ ops, int R, int per_rate)
+{
+  extern __shared__ double smem[];
+  const plf_op_t op = ops[blockIdx.y];
+  const int kind = (int)op.kind;
+  const unsigned int nsites = op.nsites;
+
+  /* per-call tip lookup: tab[code][rate][i] = masked pairwise sum of row i
+   * (core_partials_avx.c:1336-1395 for ti, :295-351 for the two tt halves) */
+  double * tl = smem;
+  double * tr = smem + 64 * R;
+  if (kind != PLF_OP_II)
+  {
+    for (int e = threadIdx.x; e < 64 * R; e += blockDim.x)
+    {
+      const int code = e / (4 * R), r = (e >> 2) % R, i = e & 3;
+      tl[e] = masked_sum4(op.left_matrix + r * 16 + i * 4, code);
+      if (kind == PLF_OP_TT)
+        tr[e] = masked_sum4(op.right_matrix + r * 16 + i * 4, code);
+    }
+    __syncthreads();
+  }
+
+  const int L = ONE_RATE ? R : 1;
+  const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned int nthreads = gridDim.x * blockDim.x;
+  const unsigned int lane_in_site = tid & (L - 1);
+  const unsigned int sites_per_iter = nthreads / L;
+  const unsigned int my_site0 = tid / L;
+  const unsigned int warp_site0 = (tid & ~31u) / L;
+
+  double Lm[16], Rm[16];
+  if (ONE_RATE)
+  {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+      Lm[i] = (kind == PLF_OP_II) ? op.left_matrix[lane_in_site * 16 + i] : 0.0;
+      Rm[i] = (kind != PLF_OP_TT) ? op.right_matrix[lane_in_site * 16 + i] : 0.0;
+    }
+  }
+
+  for (unsigned int s0 = warp_site0; s0 < nsites; s0 += sites_per_iter)
+  {
+    const unsigned int n = s0 + (my_site0 - warp_site0);
+    const bool active = n < nsites;
+    unsigned int site = n, lid = n, rid = n, lcode = 0, rcode = 0;
+    if (active)
+    {
+      if (op.parent_id_site) site = op.parent_id_site[n];
+      lid = op.left_site_id ? op.left_site_id[site] : site;
+      rid = op.right_site_id ? op.right_site_id[site] : site;
+      if (kind != PLF_OP_II) lcode = op.left_tip[site];
+      if (kind == PLF_OP_TT) rcode = op.right_tip[site];
+    }
+
+    if (ONE_RATE)
+    {
+      const unsigned int rate = lane_in_site;
+      dbl4 l = {0, 0, 0, 0}, r = {0, 0, 0, 0};
+      if (active)
+      {
+        if (kind == PLF_OP_II) l = ld256_stream(op.left_clv + ((size_t)lid * R + rate) * 4);
+        if (kind != PLF_OP_TT) r = ld256_stream(op.right_clv + ((size_t)rid * R + rate) * 4);
+      }
+      double a[4], b[4];
+      if (kind == PLF_OP_II)
+      {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = dot4_pairwise(Lm + 4 * i, l);
+      }
+      else
+      {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = tl[(lcode * R + rate) * 4 + i];
+      }
+      if (kind != PLF_OP_TT)
+      {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b[i] = dot4_pairwise(Rm + 4 * i, r);
+      }
+      else
+      {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b[i] = tr[(rcode * R + rate) * 4 + i];
+      }
+      dbl4 v = {a[0] * b[0], a[1] * b[1], a[2] * b[2], a[3] * b[3]};
+
+      if (op.parent_scaler)
+      {
+        /* tip-tip never scales and zeroes the scaler (core_partials_avx.c:1007) */
+        int below = (kind != PLF_OP_TT) && (v.x < PLF_SCALE_THRESHOLD) && (v.y < PLF_SCALE_THRESHOLD) &&
+                    (v.z < PLF_SCALE_THRESHOLD) && (v.w < PLF_SCALE_THRESHOLD);
+        if (per_rate)
+        {
+          if (active)
+          {
+            unsigned int sc = 0;
+            if (kind == PLF_OP_II && op.left_scaler) sc += op.left_scaler[(size_t)lid * R + rate];
+            if (kind != PLF_OP_TT && op.right_scaler) sc += op.right_scaler[(size_t)rid * R + rate];
+            if (below)
+            {
+              v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
+              v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
+              sc += 1;
+            }
+            op.parent_scaler[(size_t)n * R + rate] = sc;
+          }
+        }
+        else
+        {
+          const int all = group_and(below, L); /* every lane of the warp takes part */
+          if (all)
+          {
+            v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
+            v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
+          }
+          if (active && lane_in_site == 0)
+          {
+            unsigned int sc = all ? 1u : 0u;
+            if (kind == PLF_OP_II && op.left_scaler) sc += op.left_scaler[lid];
+            if (kind != PLF_OP_TT && op.right_scaler) sc += op.right_scaler[rid];
+            op.parent_scaler[n] = sc;
+          }
+        }
+      }
+      if (active) st256(op.parent_clv + ((size_t)n * R + rate) * 4, v);
+    }
+    else
+    {
+      /* rate_cats not a power of two: one thread per site, rates in a loop,
+       * matrices through L1; outputs are stored unscaled and rescaled in the
+       * (rare) case the whole site falls below the threshold */
+      if (!active) continue;
+      int site_below = 1;
+      for (int rate = 0; rate < R; ++rate)
+      {
+        dbl4 l = {0, 0, 0, 0}, r = {0, 0, 0, 0};
+        if (kind == PLF_OP_II) l = ld256(op.left_clv + ((size_t)lid * R + rate) * 4);
+        if (kind != PLF_OP_TT) r = ld256(op.right_clv + ((size_t)rid * R + rate) * 4);
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+          a[i] = (kind == PLF_OP_II) ? dot4_pairwise(op.left_matrix + rate * 16 + 4 * i, l)
+                                     : tl[(lcode * R + rate) * 4 + i];
+          b[i] = (kind != PLF_OP_TT) ? dot4_pairwise(op.right_matrix + rate * 16 + 4 * i, r)
+                                     : tr[(rcode * R + rate) * 4 + i];
+        }
+        dbl4 v = {a[0] * b[0], a[1] * b[1], a[2] * b[2], a[3] * b[3]};
+        const int below = (kind != PLF_OP_TT) && (v.x < PLF_SCALE_THRESHOLD) && (v.y < PLF_SCALE_THRESHOLD) &&
+                          (v.z < PLF_SCALE_THRESHOLD) && (v.w < PLF_SCALE_THRESHOLD);
+        if (op.parent_scaler && per_rate)
+        {
+          unsigned int sc = 0;
+          if (kind == PLF_OP_II && op.left_scaler) sc += op.left_scaler[(size_t)lid * R + rate];
+          if (kind != PLF_OP_TT && op.right_scaler) sc += op.right_scaler[(size_t)rid * R + rate];
+          if (below)
+          {
+            v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
+            v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
+            sc += 1;
+          }
+          op.parent_scaler[(size_t)n * R + rate] = sc;
+        }
+        site_below &= below;
+        st256(op.parent_clv + ((size_t)n * R + rate) * 4, v);
+      }
+      if (op.parent_scaler && !per_rate)
+      {
+        unsigned int sc = 0;
+        if (kind == PLF_OP_II && op.left_scaler) sc += op.left_scaler[lid];
+        if (kind != PLF_OP_TT && op.right_scaler) sc += op.right_scaler[rid];
+        if (site_below)
+        {
+          for (int rate = 0; rate < R; ++rate)
+          {
+            double * p = op.parent_clv + ((size_t)n * R + rate) * 4;
+            dbl4 v = ld256(p);
+            v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
+            v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
+            st256(p, v);
+          }
+          sc += 1;
+        }
+        op.parent_scaler[n] = sc;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ *
+ *  Other state counts.  ST = 20: matrices and tip tables staged in shared    *
+ *  memory, child vectors in registers.  ST = 0: run-time state count,        *
+ *  matrices through L1, and -- as the reference's generic AVX2 kernels do    *
+ *  (core_partials_avx2.c:1101-1227) -- all states_padded rows are computed,  *
+ *  the padded ones running into the following matrix; they land in the       *
+ *  padded CLV lanes and take part in the scaling test.                       *
+ * ------------------------------------------------------------------------ */
+
+template <int ST>
+__global__ void __launch_bounds__(128)
+k_partials_gen(const plf_op_t * __restrict__ ops, int R, int per_rate, int st_rt, int sp_rt,
+               const plf_state_t * __restrict__ tipmap, int maxstates, int L)
+{
+  extern __shared__ double smem[];
+  const plf_op_t op = ops[blockIdx.y];
+  const int kind = (int)op.kind;
+  const unsigned int nsites = op.nsites;
+  const int st = ST ? ST : st_rt;
+  const int sp = ST ? ((ST + 3) & ~3) : sp_rt;
+  const int msz = st * sp; /* one rate's matrix */
+
+  /* ST=20 staging: [Lmat R*400][Rmat R*400][tl maxstates*R*20][tr ...] */
+  const double * lmat = op.left_matrix;
+  const double * rmat = op.right_matrix;
+  double * tl = nullptr;
+  double * tr = nullptr;
+  if (ST == 20)
+  {
+    double * sl = smem;
+    double * sr = smem + R * msz;
+    for (int e = threadIdx.x; e < R * msz; e += blockDim.x)
+    {
+      sl[e] = op.left_matrix[e];
+      sr[e] = op.right_matrix[e];
+    }
+    lmat = sl;
+    rmat = sr;
+    if (kind != PLF_OP_II)
+    {
+      /* scalar sums in increasing column order (core_partials_avx2.c:387-456,
+       * core_partials_avx.c:160-185) */
+      tl = smem + 2 * R * msz;
+      tr = tl + maxstates * R * sp;
+      for (int e = threadIdx.x; e < maxstates * R * sp; e += blockDim.x)
+      {
+        const int c = e / (R * sp), r = (e / sp) % R, i = e % sp;
+        const plf_state_t mask = tipmap[c];
+        tl[e] = masked_sum_seq(op.left_matrix + r * msz + i * sp, mask, st);
+        if (kind == PLF_OP_TT) tr[e] = masked_sum_seq(op.right_matrix + r * msz + i * sp, mask, st);
+      }
+    }
+    __syncthreads();
+  }
+
+  const int RT = R / L;
+  const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned int nthreads = gridDim.x * blockDim.x;
+  const unsigned int lane_in_site = tid & (L - 1);
+  const unsigned int sites_per_iter = nthreads / L;
+  const unsigned int my_site0 = tid / L;
+  const unsigned int warp_site0 = (tid & ~31u) / L;
+  const size_t span = (size_t)sp * R;
+
+  for (unsigned int s0 = warp_site0; s0 < nsites; s0 += sites_per_iter)
+  {
+    const unsigned int n = s0 + (my_site0 - warp_site0);
+    const bool active = n < nsites;
+    unsigned int site = n, lid = n, rid = n, lcode = 0, rcode = 0;
+    plf_state_t lmask = 0, rmask = 0;
+    if (active)
+    {
+      if (op.parent_id_site) site = op.parent_id_site[n];
+      lid = op.left_site_id ? op.left_site_id[site] : site;
+      rid = op.right_site_id ? op.right_site_id[site] : site;
+      if (kind != PLF_OP_II) { lcode = op.left_tip[site]; lmask = tipmap[lcode]; }
+      if (kind == PLF_OP_TT) { rcode = op.right_tip[site]; rmask = tipmap[rcode]; }
+    }
+    int my_below = 1;
+    if (active)
+    {
+      for (int rr = 0; rr < RT; ++rr)
+      {
+        const int rate = lane_in_site * RT + rr;
+        double * pout = op.parent_clv + (size_t)n * span + (size_t)rate * sp;
+        const double * lc = (kind == PLF_OP_II) ? op.left_clv + (size_t)lid * span + (size_t)rate * sp : nullptr;
+        const double * rc = (kind != PLF_OP_TT) ? op.right_clv + (size_t)rid * span + (size_t)rate * sp : nullptr;
+        int below = 1;
+        if (ST == 20)
+        {
+          double l[20], r[20];
+          if (lc)
+          {
+#pragma unroll
+            for (int j = 0; j < 20; j += 4)
+            {
+              dbl4 t = ld256_stream(lc + j);
+              l[j] = t.x; l[j + 1] = t.y; l[j + 2] = t.z; l[j + 3] = t.w;
+            }
+          }
+          if (rc)
+          {
+#pragma unroll
+            for (int j = 0; j < 20; j += 4)
+            {
+              dbl4 t = ld256_stream(rc + j);
+              r[j] = t.x; r[j + 1] = t.y; r[j + 2] = t.z; r[j + 3] = t.w;
+            }
+          }
+#pragma unroll 1
+          for (int i = 0; i < 20; i += 4)
+          {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+              const double * lrow = lmat + rate * 400 + (i + q) * 20;
+              const double * rrow = rmat + rate * 400 + (i + q) * 20;
+              const double a = (kind == PLF_OP_II) ? dot_lanes_fma(lrow, l, 20)
+                                                   : tl[((size_t)lcode * R + rate) * 20 + i + q];
+              const double b = (kind != PLF_OP_TT) ? dot_lanes_fma(rrow, r, 20)
+                                                   : tr[((size_t)rcode * R + rate) * 20 + i + q];
+              v[q] = a * b;
+              below &= (v[q] < PLF_SCALE_THRESHOLD);
+            }
+            dbl4 o = {v[0], v[1], v[2], v[3]};
+            st256(pout + i, o);
+          }
+        }
+        else
+        {
+          for (int i = 0; i < sp; ++i)
+          {
+            const double * lrow = lmat + (size_t)rate * msz + (size_t)i * sp;
+            const double * rrow = rmat + (size_t)rate * msz + (size_t)i * sp;
+            double v;
+            if (kind == PLF_OP_TT)
+            {
+              /* generic tip-tip table: real rows only, padded lanes zero
+               * (core_partials_avx.c:63-101) */
+              v = (i < st) ? masked_sum_seq(lrow, lmask, st) * masked_sum_seq(rrow, rmask, st) : 0.0;
+            }
+            else
+            {
+              const double a = (kind == PLF_OP_II) ? dot_lanes_fma(lrow, lc, sp) : masked_sum_lanes(lrow, lmask, sp);
+              const double b = dot_lanes_fma(rrow, rc, sp);
+              v = a * b;
+            }
+            below &= (v < PLF_SCALE_THRESHOLD);
+            pout[i] = v;
+          }
+        }
+        if (kind == PLF_OP_TT) below = 0;
+        if (op.parent_scaler && per_rate)
+        {
+          unsigned int sc = 0;
+          if (kind == PLF_OP_II && op.left_scaler) sc += op.left_scaler[(size_t)lid * R + rate];
+          if (kind != PLF_OP_TT && op.right_scaler) sc += op.right_scaler[(size_t)rid * R + rate];
+          if (below)
+          {
+            for (int i = 0; i < sp; ++i) pout[i] *= PLF_SCALE_FACTOR;
+            sc += 1;
+          }
+          op.parent_scaler[(size_t)n * R + rate] = sc;
+        }
+        my_below &= below;
+      }
+    }
+    if (op.parent_scaler && !per_rate)
+    {
+      const int all = group_and(my_below, L);
+      if (active)
+      {
+        if (all)
+          for (int rr = 0; rr < RT; ++rr)
+          {
+            double * pout = op.parent_clv + (size_t)n * span + (size_t)(lane_in_site * RT + rr) * sp;
+            for (int i = 0; i < sp; ++i) pout[i] *= PLF_SCALE_FACTOR;
+          }
+        if (lane_in_site == 0)
+        {
+          unsigned int sc = all ? 1u : 0u;
+          if (kind == PLF_OP_II && op.left_scaler) sc += op.left_scaler[lid];
+          if (kind != PLF_OP_TT && op.right_scaler) sc += op.right_scaler[rid];
+          op.parent_scaler[n] = sc;
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+
+static int is_pow2(unsigned int x) { return x && !(x & (x - 1)); }
+
+extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops,
+                                   unsigned int nops, const unsigned int * h_level_start,
+                                   unsigned int nlevels, const unsigned long long * d_tipmap,
+                                   unsigned int maxstates)
+{
+  if (!nops) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  plf_op_t * d_ops = (plf_op_t *)plf_ws_reserve(ctx, &ctx->ws_ops, (size_t)nops * sizeof(plf_op_t));
+  if (!d_ops) return 0;
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_ops, (size_t)nops * sizeof(plf_op_t), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  const int R = (int)sh->rate_cats;
+  const int one_rate = is_pow2(sh->rate_cats) && sh->rate_cats <= 32;
+  const int L = one_rate ? R : 1;
+
+  for (unsigned int lv = 0; lv < nlevels; ++lv)
+  {
+    const unsigned int a = h_level_start[lv], b = h_level_start[lv + 1];
+    if (b <= a) continue;
+    unsigned int max_sites = 0;
+    int any_tip = 0;
+    for (unsigned int i = a; i < b; ++i)
+    {
+      if (h_ops[i].nsites > max_sites) max_sites = h_ops[i].nsites;
+      any_tip |= (h_ops[i].kind != PLF_OP_II);
+    }
+    if (!max_sites) continue;
+    if (sh->states == 4)
+    {
+      const int threads = 256;
+      const unsigned long long work = (unsigned long long)max_sites * L;
+      unsigned int bx = (unsigned int)((work + threads - 1) / threads);
+      /* persistent-style grid: a few waves of the 148 SMs x 2 resident CTAs,
+       * shared between the ops of the level */
+      unsigned int cap = (unsigned int)(ctx->sm_count * 2 * 4) / (b - a);
+      if (cap < 1) cap = 1;
+      if (bx > cap) bx = cap;
+      dim3 grid(bx, b - a);
+      const size_t smem = any_tip ? (size_t)2 * 64 * R * sizeof(double) : 0;
+      if (one_rate)
+        k_partials_dna<1><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers);
+      else
+        k_partials_dna<0><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers);
+    }
+    else
+    {
+      const int threads = 128;
+      const unsigned long long work = (unsigned long long)max_sites * L;
+      unsigned int bx = (unsigned int)((work + threads - 1) / threads);
+      unsigned int cap = (unsigned int)(ctx->sm_count * 4 * 2) / (b - a);
+      if (cap < 1) cap = 1;
+      if (bx > cap) bx = cap;
+      dim3 grid(bx, b - a);
+      if (sh->states == 20)
+      {
+        size_t smem = (size_t)2 * R * 400 * sizeof(double);
+        if (any_tip) smem += (size_t)2 * maxstates * R * 20 * sizeof(double);
+        if (smem > ctx->smem_optin)
+        {
+          plf_set_error(ctx, "protein tip tables need %zu B of shared memory (> %zu)", smem, ctx->smem_optin);
+          return 0;
+        }
+        if (smem > ctx->gen20_smem_set)
+        {
+          PLF_CHECK(ctx, cudaFuncSetAttribute(k_partials_gen<20>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+          ctx->gen20_smem_set = smem;
+        }
+        k_partials_gen<20><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers, 20, 20,
+                                                                  d_tipmap, (int)maxstates, L);
+      }
+      else
+        k_partials_gen<0><<<grid, threads, 0, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers,
+                                                             (int)sh->states, (int)sh->states_padded, d_tipmap,
+                                                             (int)maxstates, L);
+    }
+    plf_count_launch();
+    PLF_CHECK(ctx, cudaGetLastError());
+  }
+  return 1;
+}

@@ -1,0 +1,2048 @@
+/*
+ * pll_host.c -- the C host layer of the B200-native likelihood engine.
+ *
+ * Implements the partition API of libpll-2 (reference src/pll.h:636-849,
+ * front ends in src/pll.c, models.c, partials.c, likelihood.c, derivatives.c,
+ * repeats.c) for partitions created with PLL_ATTRIB_ARCH_CUDA.  This file owns
+ * the host-side state (the public pll_partition_t plus a private tail), decides
+ * WHAT to run -- which kernel variant, on which buffers, in which launch level
+ * -- and calls the sm_100a kernels through the thin C-ABI of plf_backend.h.
+ * There is no arithmetic on CLVs here and no CPU fallback: without a CUDA
+ * device pll_partition_create fails.
+ *
+ * Memory model
+ *   device-canonical : clv[], scale_buffer[], pmatrix[] (the pointer fields
+ *                      hold HBM addresses), tipchars mirrors, repeat-id arrays,
+ *                      sumtables (keyed by the caller's host pointer)
+ *   host-canonical   : rates, weights, frequencies, subst_params, eigen*,
+ *                      prop_invar, pattern_weights, tipchars[], charmap, tipmap
+ *                      and every field of pll_repeats_t.  Small model arrays are
+ *                      packed per call and re-uploaded only when their bytes
+ *                      changed, so direct writes to the struct fields are seen.
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pll_b200.h"
+#include "plf_backend.h"
+
+__thread int pll_errno;
+__thread char pll_errmsg[200] = {0};
+__thread pll_hardware_t pll_hardware = {0};
+
+static __thread int tls_device = -1;
+
+#define PLL_CUDA_MAGIC 0xB200C0DEu
+#define EMPTY_ELEMENT 0xFFFFFFFFu
+#define MAX_SUMTABLES 8
+
+typedef struct sumtable_slot
+{
+  const double * key; /* caller's host pointer */
+  double * dev;
+  size_t doubles;
+  unsigned long long stamp;
+} sumtable_slot_t;
+
+typedef struct cuda_partition
+{
+  pll_partition_t pub; /* MUST be first: callers hold &pub */
+  unsigned int magic;
+  plf_ctx_t * ctx;
+  plf_shape_t shape;
+
+  double * d_pmatrix_block;
+  size_t pmatrix_doubles;
+
+  double * h_model;      /* packed per-rate-category model block */
+  double * h_model_sent; /* bytes last uploaded                  */
+  double * d_model;
+  size_t model_doubles;
+  int model_sent_valid;
+
+  unsigned int * d_pattern_weights;
+  int weights_dirty;
+  int * d_invariant;
+
+  unsigned char ** d_tipchars; /* [tips] device mirrors of tipchars[] */
+  unsigned long long * d_tipmap;
+  int tipmap_dirty;
+
+  unsigned int * clv_entries;    /* site entries allocated per node          */
+  unsigned int * scaler_entries; /* uints allocated per scale buffer          */
+
+  sumtable_slot_t sumtabs[MAX_SUMTABLES];
+  unsigned long long stamp;
+  int sumtable_mirror;
+  double * d_persite;
+  size_t persite_cap;
+
+  /* scratch for pll_set_tip_states */
+  unsigned char * d_seq;
+  unsigned long long * d_map;
+
+  /* site repeats: device-canonical identifier arrays */
+  unsigned int ** d_site_id;    /* [nodes] -> device [sites]               */
+  unsigned int ** d_id_site;    /* [nodes] -> device [id_site_count]       */
+  unsigned int * id_site_count; /* classes found at the last id computation */
+  unsigned char * ids_stale;    /* host mirrors older than the device copy */
+  unsigned int * d_lookup;
+  unsigned int * d_keys;
+  unsigned int * d_id_site_tmp;
+  unsigned char * d_rep_charmap;
+  int repeats_mirror;
+
+  int host_expm1; /* bit-exact P-matrices: expm1 from the host libm */
+
+  /* reusable host scratch for operation lists */
+  plf_op_t * h_ops;
+  plf_op_t * h_ops_sorted;
+  unsigned int * h_level;
+  unsigned int * h_level_start;
+  unsigned int ops_cap;
+} cuda_partition_t;
+
+/* ------------------------------------------------------------------------ */
+
+static void set_error(int code, const char * fmt, const char * detail)
+{
+  pll_errno = code;
+  snprintf(pll_errmsg, sizeof(pll_errmsg), fmt, detail ? detail : "");
+}
+
+static cuda_partition_t * CP(const pll_partition_t * p)
+{
+  cuda_partition_t * cp = (cuda_partition_t *)p;
+  if (!cp || cp->magic != PLL_CUDA_MAGIC)
+  {
+    set_error(PLL_ERROR_CUDA_UNSUPPORTED, "partition was not created by libpll_b200%s", NULL);
+    return NULL;
+  }
+  return cp;
+}
+
+static int cuda_fail(cuda_partition_t * cp)
+{
+  set_error(PLL_ERROR_CUDA, "CUDA: %s", plf_last_error(cp->ctx));
+  return PLL_FAILURE;
+}
+
+static int env_flag(const char * name)
+{
+  const char * v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+
+PLL_EXPORT void * pll_aligned_alloc(size_t size, size_t alignment)
+{
+  void * mem = NULL;
+  if (posix_memalign(&mem, alignment < sizeof(void *) ? sizeof(void *) : alignment, size ? size : alignment))
+    return NULL;
+  return mem;
+}
+
+PLL_EXPORT void pll_aligned_free(void * ptr) { free(ptr); }
+
+/* ---- hardware probe ------------------------------------------------------ */
+
+PLL_EXPORT int pll_hardware_probe(void)
+{
+  memset(&pll_hardware, 0, sizeof(pll_hardware));
+  pll_hardware.init = 1;
+#if defined(__x86_64__)
+  pll_hardware.sse3_present = __builtin_cpu_supports("sse3");
+  pll_hardware.avx_present = __builtin_cpu_supports("avx");
+  pll_hardware.avx2_present = __builtin_cpu_supports("avx2");
+  pll_hardware.popcnt_present = __builtin_cpu_supports("popcnt");
+#endif
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT void pll_hardware_dump(void)
+{
+  char err[128] = {0};
+  int n = plf_device_count(err, sizeof(err));
+  fprintf(stderr, "CUDA devices: %d%s%s\n", n, err[0] ? " -- " : "", err);
+}
+
+PLL_EXPORT void pll_hardware_ignore(void)
+{
+  memset(&pll_hardware, 0, sizeof(pll_hardware));
+  pll_hardware.init = 1;
+}
+
+PLL_EXPORT int pll_cuda_device_count(void)
+{
+  char err[160] = {0};
+  int n = plf_device_count(err, sizeof(err));
+  if (n <= 0 && err[0]) set_error(PLL_ERROR_CUDA, "%s", err);
+  return n;
+}
+
+PLL_EXPORT int pll_cuda_set_device(int device)
+{
+  if (device < 0)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "negative CUDA device index%s", NULL);
+    return PLL_FAILURE;
+  }
+  tls_device = device;
+  return PLL_SUCCESS;
+}
+
+static int pick_device(void)
+{
+  const char * v;
+  if (tls_device >= 0) return tls_device;
+  if ((v = getenv("PLL_CUDA_DEVICE")) && v[0]) return atoi(v);
+  if ((v = getenv("LOCAL_RANK")) && v[0]) return atoi(v);
+  return 0;
+}
+
+/* ---- partition lifecycle -------------------------------------------------- */
+
+static void free_repeats(cuda_partition_t * cp)
+{
+  pll_partition_t * p = &cp->pub;
+  pll_repeats_t * r = p->repeats;
+  unsigned int i;
+  if (!r) return;
+  for (i = 0; i < p->nodes; ++i)
+  {
+    if (r->pernode_site_id) free(r->pernode_site_id[i]);
+    if (r->pernode_id_site) free(r->pernode_id_site[i]);
+    if (cp->d_site_id) plf_free(cp->ctx, cp->d_site_id[i]);
+    if (cp->d_id_site) plf_free(cp->ctx, cp->d_id_site[i]);
+  }
+  free(r->pernode_site_id);
+  free(r->pernode_id_site);
+  free(r->pernode_ids);
+  free(r->perscale_ids);
+  free(r->pernode_allocated_clvs);
+  free(r->lookup_buffer);
+  free(r->toclean_buffer);
+  free(r->id_site_buffer);
+  free(r->charmap);
+  free(r);
+  p->repeats = NULL;
+  free(cp->d_site_id);
+  free(cp->d_id_site);
+  free(cp->id_site_count);
+  free(cp->ids_stale);
+  plf_free(cp->ctx, cp->d_lookup);
+  plf_free(cp->ctx, cp->d_keys);
+  plf_free(cp->ctx, cp->d_id_site_tmp);
+  plf_free(cp->ctx, cp->d_rep_charmap);
+}
+
+static void destroy(cuda_partition_t * cp)
+{
+  pll_partition_t * p = &cp->pub;
+  unsigned int i;
+  if (cp->ctx)
+  {
+    plf_sync(cp->ctx);
+    free_repeats(cp);
+    if (p->clv)
+      for (i = 0; i < p->nodes; ++i) plf_free(cp->ctx, p->clv[i]);
+    if (p->scale_buffer)
+      for (i = 0; i < p->scale_buffers; ++i) plf_free(cp->ctx, p->scale_buffer[i]);
+    if (cp->d_tipchars)
+      for (i = 0; i < p->tips; ++i) plf_free(cp->ctx, cp->d_tipchars[i]);
+    for (i = 0; i < MAX_SUMTABLES; ++i) plf_free(cp->ctx, cp->sumtabs[i].dev);
+    plf_free(cp->ctx, cp->d_pmatrix_block);
+    plf_free(cp->ctx, cp->d_model);
+    plf_free(cp->ctx, cp->d_pattern_weights);
+    plf_free(cp->ctx, cp->d_invariant);
+    plf_free(cp->ctx, cp->d_tipmap);
+    plf_free(cp->ctx, cp->d_persite);
+    plf_free(cp->ctx, cp->d_seq);
+    plf_free(cp->ctx, cp->d_map);
+    plf_ctx_destroy(cp->ctx);
+  }
+  if (p->tipchars)
+    for (i = 0; i < p->tips; ++i) free(p->tipchars[i]);
+  for (i = 0; i < p->rate_matrices; ++i)
+  {
+    if (p->eigenvecs) free(p->eigenvecs[i]);
+    if (p->inv_eigenvecs) free(p->inv_eigenvecs[i]);
+    if (p->eigenvals) free(p->eigenvals[i]);
+    if (p->subst_params) free(p->subst_params[i]);
+    if (p->frequencies) free(p->frequencies[i]);
+  }
+  free(p->tipchars);
+  free(p->charmap);
+  free(p->tipmap);
+  free(p->eigenvecs);
+  free(p->inv_eigenvecs);
+  free(p->eigenvals);
+  free(p->subst_params);
+  free(p->frequencies);
+  free(p->eigen_decomp_valid);
+  free(p->rates);
+  free(p->rate_weights);
+  free(p->prop_invar);
+  free(p->pattern_weights);
+  free(p->invariant);
+  free(p->clv);
+  free(p->pmatrix);
+  free(p->scale_buffer);
+  free(cp->d_tipchars);
+  free(cp->clv_entries);
+  free(cp->scaler_entries);
+  free(cp->h_model);
+  free(cp->h_model_sent);
+  free(cp->h_ops);
+  free(cp->h_ops_sorted);
+  free(cp->h_level);
+  free(cp->h_level_start);
+  cp->magic = 0;
+  free(cp);
+}
+
+static int repeats_initialize(cuda_partition_t * cp)
+{
+  pll_partition_t * p = &cp->pub;
+  unsigned int i;
+  pll_repeats_t * r = (pll_repeats_t *)calloc(1, sizeof(pll_repeats_t));
+  if (!r) return PLL_FAILURE;
+  p->repeats = r;
+  r->enable_repeats = pll_default_enable_repeats;
+  r->reallocate_repeats = pll_default_reallocate_repeats;
+  r->pernode_site_id = (unsigned int **)calloc(p->nodes, sizeof(unsigned int *));
+  r->pernode_id_site = (unsigned int **)calloc(p->nodes, sizeof(unsigned int *));
+  r->pernode_ids = (unsigned int *)calloc(p->nodes, sizeof(unsigned int));
+  r->perscale_ids = (unsigned int *)calloc(p->scale_buffers ? p->scale_buffers : 1, sizeof(unsigned int));
+  r->pernode_allocated_clvs = (unsigned int *)calloc(p->nodes, sizeof(unsigned int));
+  r->toclean_buffer = (unsigned int *)malloc(p->sites * sizeof(unsigned int));
+  r->id_site_buffer = (unsigned int *)malloc(p->sites * sizeof(unsigned int));
+  r->charmap = (char *)calloc(PLL_ASCII_SIZE, sizeof(char));
+  r->bclv_buffer = NULL; /* the device kernels need no pre-multiplied child buffer */
+  cp->d_site_id = (unsigned int **)calloc(p->nodes, sizeof(unsigned int *));
+  cp->d_id_site = (unsigned int **)calloc(p->nodes, sizeof(unsigned int *));
+  cp->id_site_count = (unsigned int *)calloc(p->nodes, sizeof(unsigned int));
+  cp->ids_stale = (unsigned char *)calloc(p->nodes, 1);
+  if (!r->pernode_site_id || !r->pernode_id_site || !r->pernode_ids || !r->perscale_ids ||
+      !r->pernode_allocated_clvs || !r->toclean_buffer || !r->id_site_buffer || !r->charmap ||
+      !cp->d_site_id || !cp->d_id_site || !cp->id_site_count || !cp->ids_stale)
+    return PLL_FAILURE;
+  for (i = 0; i < p->nodes; ++i)
+  {
+    r->pernode_site_id[i] = (unsigned int *)calloc(p->sites, sizeof(unsigned int));
+    r->pernode_id_site[i] = (unsigned int *)calloc(p->sites, sizeof(unsigned int));
+    cp->d_site_id[i] = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 1);
+    if (!r->pernode_site_id[i] || !r->pernode_id_site[i] || !cp->d_site_id[i]) return PLL_FAILURE;
+  }
+  cp->d_keys = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 0);
+  cp->d_id_site_tmp = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 0);
+  cp->d_rep_charmap = (unsigned char *)plf_alloc(cp->ctx, PLL_ASCII_SIZE, 0);
+  if (!cp->d_keys || !cp->d_id_site_tmp || !cp->d_rep_charmap) return PLL_FAILURE;
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned int clv_buffers,
+                                                  unsigned int states, unsigned int sites,
+                                                  unsigned int rate_matrices, unsigned int prob_matrices,
+                                                  unsigned int rate_cats, unsigned int scale_buffers,
+                                                  unsigned int attributes)
+{
+  unsigned int i, sp;
+  int narch = __builtin_popcount(attributes & PLL_ATTRIB_ARCH_MASK) + ((attributes & PLL_ATTRIB_ARCH_CUDA) ? 1 : 0);
+  char err[200] = {0};
+  cuda_partition_t * cp;
+  pll_partition_t * p;
+
+  /* the CUDA bit counts as an architecture (src/pll.c:438-443) */
+  if (narch > 1)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "Multiple architecture flags specified.%s", NULL);
+    return NULL;
+  }
+  if (!(attributes & PLL_ATTRIB_ARCH_CUDA))
+  {
+    if (!env_flag("PLL_CUDA_FORCE"))
+    {
+      set_error(PLL_ERROR_CUDA_UNSUPPORTED,
+                "libpll_b200 implements PLL_ATTRIB_ARCH_CUDA only (set it, or PLL_CUDA_FORCE=1)%s", NULL);
+      return NULL;
+    }
+    attributes = (attributes & ~(unsigned int)PLL_ATTRIB_ARCH_MASK) | PLL_ATTRIB_ARCH_CUDA;
+  }
+  if (attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG))
+  {
+    set_error(PLL_ERROR_CUDA_UNSUPPORTED, "ascertainment bias correction is not implemented for CUDA partitions%s",
+              NULL);
+    return NULL;
+  }
+  /* too few sites: repeats silently off (src/pll.c:446-449) */
+  if (sites < 16) attributes &= ~(unsigned int)PLL_ATTRIB_SITE_REPEATS;
+  if ((attributes & PLL_ATTRIB_SITE_REPEATS) && (attributes & PLL_ATTRIB_PATTERN_TIP))
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "PLL_ATTRIB_PATTERN_TIP and PLL_ATTRIB_SITE_REPEATS are mutually exclusive%s",
+              NULL);
+    return NULL;
+  }
+  if (!states || !sites || !rate_cats || !rate_matrices || states > 63)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "invalid partition dimensions%s", NULL);
+    return NULL;
+  }
+
+  cp = (cuda_partition_t *)calloc(1, sizeof(cuda_partition_t));
+  if (!cp)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate memory for partition.%s", NULL);
+    return NULL;
+  }
+  p = &cp->pub;
+  cp->magic = PLL_CUDA_MAGIC;
+  p->tips = tips;
+  p->clv_buffers = clv_buffers;
+  p->nodes = tips + clv_buffers;
+  p->states = states;
+  p->sites = sites;
+  p->pattern_weight_sum = sites;
+  p->rate_matrices = rate_matrices;
+  p->prob_matrices = prob_matrices;
+  p->rate_cats = rate_cats;
+  p->scale_buffers = scale_buffers;
+  p->attributes = attributes;
+  p->alignment = PLL_ALIGNMENT_CUDA;
+  p->states_padded = sp = (states + 3) & 0xFFFFFFFCu;
+  cp->shape.states = states;
+  cp->shape.states_padded = sp;
+  cp->shape.rate_cats = rate_cats;
+  cp->shape.per_rate_scalers = (attributes & PLL_ATTRIB_RATE_SCALERS) ? 1 : 0;
+  cp->host_expm1 = !env_flag("PLL_CUDA_DEVICE_EXPM1");
+  cp->sumtable_mirror = env_flag("PLL_CUDA_SUMTABLE_MIRROR");
+  cp->repeats_mirror = env_flag("PLL_CUDA_REPEATS_MIRROR");
+  cp->weights_dirty = 1;
+
+  if (!plf_ctx_create(pick_device(), env_flag("PLL_CUDA_MANAGED"), &cp->ctx, err, sizeof(err)))
+  {
+    set_error(PLL_ERROR_CUDA, "%s", err[0] ? err : "cannot create a CUDA context");
+    cp->ctx = NULL;
+    destroy(cp);
+    return NULL;
+  }
+
+#define NEED(x)                                                                              \
+  do                                                                                         \
+  {                                                                                          \
+    if (!(x))                                                                                \
+    {                                                                                        \
+      const char * ce = plf_last_error(cp->ctx);                                             \
+      set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory. %s", ce ? ce : ""); \
+      destroy(cp);                                                                           \
+      return NULL;                                                                           \
+    }                                                                                        \
+  } while (0)
+
+  NEED(p->eigen_decomp_valid = (int *)calloc(rate_matrices, sizeof(int)));
+  NEED(p->clv = (double **)calloc(p->nodes ? p->nodes : 1, sizeof(double *)));
+  NEED(cp->clv_entries = (unsigned int *)calloc(p->nodes ? p->nodes : 1, sizeof(unsigned int)));
+  NEED(p->scale_buffer = (unsigned int **)calloc(scale_buffers ? scale_buffers : 1, sizeof(unsigned int *)));
+  NEED(cp->scaler_entries = (unsigned int *)calloc(scale_buffers ? scale_buffers : 1, sizeof(unsigned int)));
+  NEED(p->pmatrix = (double **)calloc(prob_matrices ? prob_matrices : 1, sizeof(double *)));
+
+  /* CLVs: under repeats they are sized per node later; pattern tips have none
+   * (src/pll.c:556-581) */
+  if (!(attributes & PLL_ATTRIB_SITE_REPEATS))
+  {
+    const size_t n = (size_t)sites * sp * rate_cats;
+    for (i = (attributes & PLL_ATTRIB_PATTERN_TIP) ? tips : 0; i < p->nodes; ++i)
+    {
+      NEED(p->clv[i] = (double *)plf_alloc(cp->ctx, n * sizeof(double), 1));
+      cp->clv_entries[i] = sites;
+    }
+    for (i = 0; i < scale_buffers; ++i)
+    {
+      const size_t m = (size_t)sites * (cp->shape.per_rate_scalers ? rate_cats : 1);
+      NEED(p->scale_buffer[i] = (unsigned int *)plf_alloc(cp->ctx, m * sizeof(unsigned int), 1));
+      cp->scaler_entries[i] = (unsigned int)m;
+    }
+  }
+
+  /* one contiguous P-matrix block plus the displacement the padded rows of
+   * the last matrix run into (src/pll.c:597-617) */
+  cp->pmatrix_doubles = (size_t)prob_matrices * states * sp * rate_cats + (size_t)(sp - states) * sp;
+  NEED(cp->d_pmatrix_block = (double *)plf_alloc(cp->ctx, cp->pmatrix_doubles * sizeof(double), 1));
+  for (i = 0; i < prob_matrices; ++i) p->pmatrix[i] = cp->d_pmatrix_block + (size_t)i * states * sp * rate_cats;
+
+  NEED(p->eigenvecs = (double **)calloc(rate_matrices, sizeof(double *)));
+  NEED(p->inv_eigenvecs = (double **)calloc(rate_matrices, sizeof(double *)));
+  NEED(p->eigenvals = (double **)calloc(rate_matrices, sizeof(double *)));
+  NEED(p->subst_params = (double **)calloc(rate_matrices, sizeof(double *)));
+  NEED(p->frequencies = (double **)calloc(rate_matrices, sizeof(double *)));
+  for (i = 0; i < rate_matrices; ++i)
+  {
+    NEED(p->eigenvecs[i] = (double *)pll_aligned_alloc((size_t)states * sp * sizeof(double), p->alignment));
+    NEED(p->inv_eigenvecs[i] = (double *)pll_aligned_alloc((size_t)states * sp * sizeof(double), p->alignment));
+    NEED(p->eigenvals[i] = (double *)pll_aligned_alloc(sp * sizeof(double), p->alignment));
+    NEED(p->subst_params[i] =
+             (double *)pll_aligned_alloc((states * (states - 1) / 2 + 1) * sizeof(double), p->alignment));
+    NEED(p->frequencies[i] = (double *)pll_aligned_alloc(sp * sizeof(double), p->alignment));
+    memset(p->eigenvecs[i], 0, (size_t)states * sp * sizeof(double));
+    memset(p->inv_eigenvecs[i], 0, (size_t)states * sp * sizeof(double));
+    memset(p->eigenvals[i], 0, sp * sizeof(double));
+    memset(p->subst_params[i], 0, (states * (states - 1) / 2 + 1) * sizeof(double));
+    memset(p->frequencies[i], 0, sp * sizeof(double));
+  }
+  NEED(p->rates = (double *)calloc(rate_cats, sizeof(double)));
+  NEED(p->rate_weights = (double *)calloc(rate_cats, sizeof(double)));
+  for (i = 0; i < rate_cats; ++i) p->rate_weights[i] = 1.0 / rate_cats;
+  NEED(p->prop_invar = (double *)calloc(rate_matrices, sizeof(double)));
+  NEED(p->pattern_weights = (unsigned int *)malloc((size_t)sites * sizeof(unsigned int)));
+  for (i = 0; i < sites; ++i) p->pattern_weights[i] = 1;
+  NEED(cp->d_pattern_weights = (unsigned int *)plf_alloc(cp->ctx, (size_t)sites * sizeof(unsigned int), 0));
+
+  cp->model_doubles = plf_model_doubles(rate_cats, states, sp);
+  NEED(cp->h_model = (double *)calloc(cp->model_doubles, sizeof(double)));
+  NEED(cp->h_model_sent = (double *)calloc(cp->model_doubles, sizeof(double)));
+  NEED(cp->d_model = (double *)plf_alloc(cp->ctx, cp->model_doubles * sizeof(double), 1));
+  NEED(cp->d_seq = (unsigned char *)plf_alloc(cp->ctx, sites, 0));
+  NEED(cp->d_map = (unsigned long long *)plf_alloc(cp->ctx, PLL_ASCII_SIZE * sizeof(unsigned long long), 0));
+  NEED(cp->d_tipmap = (unsigned long long *)plf_alloc(cp->ctx, PLL_ASCII_SIZE * sizeof(unsigned long long), 1));
+
+  if (attributes & PLL_ATTRIB_SITE_REPEATS) NEED(repeats_initialize(cp));
+#undef NEED
+  return p;
+}
+
+PLL_EXPORT void pll_partition_destroy(pll_partition_t * partition)
+{
+  cuda_partition_t * cp;
+  if (!partition) return;
+  if (!(cp = CP(partition))) return;
+  destroy(cp);
+}
+
+PLL_EXPORT int pll_cuda_get_device(const pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  return cp ? plf_ctx_device(cp->ctx) : -1;
+}
+
+PLL_EXPORT void * pll_cuda_get_stream(const pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  return cp ? plf_ctx_stream(cp->ctx) : NULL;
+}
+
+PLL_EXPORT int pll_cuda_synchronize(const pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  return plf_sync(cp->ctx) ? PLL_SUCCESS : cuda_fail(cp);
+}
+
+PLL_EXPORT unsigned long long pll_cuda_kernel_launches(void) { return plf_kernel_launches(); }
+
+/* ---- site repeats: bookkeeping (src/repeats.c) ------------------------------ */
+
+PLL_EXPORT int pll_repeats_enabled(const pll_partition_t * partition)
+{
+  return PLL_ATTRIB_SITE_REPEATS & partition->attributes;
+}
+
+PLL_EXPORT void pll_resize_repeats_lookup(pll_partition_t * partition, unsigned int size)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp || !size || !partition->repeats) return;
+  plf_free(cp->ctx, cp->d_lookup);
+  partition->repeats->lookup_buffer_size = size;
+  cp->d_lookup = (unsigned int *)plf_alloc(cp->ctx, (size_t)size * sizeof(unsigned int), 0);
+  if (!cp->d_lookup || !plf_fill_u32(cp->ctx, cp->d_lookup, EMPTY_ELEMENT, size)) cuda_fail(cp);
+}
+
+PLL_EXPORT unsigned int pll_get_sites_number(const pll_partition_t * partition, unsigned int clv_index)
+{
+  unsigned int sites = (partition->attributes & PLL_ATTRIB_SITE_REPEATS) ? partition->repeats->pernode_ids[clv_index] : 0;
+  return sites ? sites : partition->sites;
+}
+
+PLL_EXPORT unsigned int pll_get_clv_size(const pll_partition_t * partition, unsigned int clv_index)
+{
+  return pll_get_sites_number(partition, clv_index) * partition->states_padded * partition->rate_cats;
+}
+
+/* bring the host mirrors of a node's identifier arrays up to date */
+static void sync_ids_to_host(cuda_partition_t * cp, unsigned int node)
+{
+  pll_repeats_t * r = cp->pub.repeats;
+  if (!r || !cp->ids_stale[node]) return;
+  plf_download(cp->ctx, r->pernode_site_id[node], cp->d_site_id[node], (size_t)cp->pub.sites * sizeof(unsigned int));
+  if (cp->id_site_count[node] && cp->d_id_site[node])
+    plf_download(cp->ctx, r->pernode_id_site[node], cp->d_id_site[node],
+                 (size_t)cp->id_site_count[node] * sizeof(unsigned int));
+  cp->ids_stale[node] = 0;
+}
+
+PLL_EXPORT unsigned int * pll_get_site_id(const pll_partition_t * partition, unsigned int clv_index)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp || !pll_repeats_enabled(partition) || !partition->repeats->pernode_ids[clv_index]) return NULL;
+  sync_ids_to_host(cp, clv_index);
+  return partition->repeats->pernode_site_id[clv_index];
+}
+
+PLL_EXPORT unsigned int * pll_get_id_site(const pll_partition_t * partition, unsigned int clv_index)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp || !pll_repeats_enabled(partition) || !partition->repeats->pernode_ids[clv_index]) return NULL;
+  sync_ids_to_host(cp, clv_index);
+  return partition->repeats->pernode_id_site[clv_index];
+}
+
+PLL_EXPORT unsigned int pll_default_enable_repeats(pll_partition_t * partition, unsigned int left_clv,
+                                                   unsigned int right_clv)
+{
+  const pll_repeats_t * r = partition->repeats;
+  const unsigned long long nl = r->pernode_ids[left_clv], nr = r->pernode_ids[right_clv];
+  const unsigned long long pairs = nl * nr;
+  if (!pairs || (unsigned long long)r->lookup_buffer_size <= pairs) return 0;
+  if (nl > partition->sites / 2 || nr > partition->sites / 2) return 0;
+  return 1;
+}
+
+PLL_EXPORT unsigned int pll_no_enable_repeats(pll_partition_t * partition, unsigned int left_clv,
+                                              unsigned int right_clv)
+{
+  (void)partition;
+  (void)left_clv;
+  (void)right_clv;
+  return 0;
+}
+
+PLL_EXPORT void pll_disable_bclv(pll_partition_t * partition) { (void)partition; }
+
+/* resize the parent's CLV, scale buffer and id->site array to the class count
+ * (src/repeats.c:256-296) */
+PLL_EXPORT void pll_default_reallocate_repeats(pll_partition_t * partition, unsigned int parent, int scaler_index,
+                                               unsigned int sites_to_alloc)
+{
+  cuda_partition_t * cp = CP(partition);
+  pll_repeats_t * r;
+  if (!cp) return;
+  r = partition->repeats;
+  if (sites_to_alloc == r->pernode_allocated_clvs[parent]) return;
+  r->pernode_allocated_clvs[parent] = sites_to_alloc;
+  plf_free(cp->ctx, partition->clv[parent]);
+  partition->clv[parent] = (double *)plf_alloc(
+      cp->ctx, (size_t)sites_to_alloc * partition->states_padded * partition->rate_cats * sizeof(double), 1);
+  cp->clv_entries[parent] = sites_to_alloc;
+  if (!partition->clv[parent])
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory for repeats structure. %s",
+              plf_last_error(cp->ctx));
+    return;
+  }
+  if (scaler_index != PLL_SCALE_BUFFER_NONE)
+  {
+    size_t n = sites_to_alloc;
+    if (partition->attributes & PLL_ATTRIB_RATE_SCALERS) n *= partition->rate_cats;
+    plf_free(cp->ctx, partition->scale_buffer[scaler_index]);
+    partition->scale_buffer[scaler_index] = (unsigned int *)plf_alloc(cp->ctx, n * sizeof(unsigned int), 1);
+    cp->scaler_entries[scaler_index] = (unsigned int)n;
+  }
+  free(r->pernode_id_site[parent]);
+  r->pernode_id_site[parent] = (unsigned int *)malloc((size_t)(sites_to_alloc ? sites_to_alloc : 1) * sizeof(unsigned int));
+  plf_free(cp->ctx, cp->d_id_site[parent]);
+  cp->d_id_site[parent] =
+      (unsigned int *)plf_alloc(cp->ctx, (size_t)(sites_to_alloc ? sites_to_alloc : 1) * sizeof(unsigned int), 0);
+}
+
+/* class identifiers of a tip: classes are the distinct map values, numbered
+ * by first occurrence along the sequence (src/repeats.c:189-254) */
+PLL_EXPORT int pll_update_repeats_tips(pll_partition_t * partition, unsigned int tip_index, const pll_state_t * map,
+                                       const char * sequence)
+{
+  cuda_partition_t * cp = CP(partition);
+  pll_repeats_t * r;
+  unsigned int i, j, ids = 0;
+  unsigned char next = 0;
+  unsigned char * cm;
+  if (!cp) return PLL_FAILURE;
+  r = partition->repeats;
+  if (!cp->d_lookup) pll_resize_repeats_lookup(partition, PLL_REPEATS_LOOKUP_SIZE);
+  if (!cp->d_lookup) return PLL_FAILURE;
+
+  /* dense class code per character (src/repeats.c:28-45) */
+  cm = (unsigned char *)r->charmap;
+  for (i = 0; i < PLL_ASCII_SIZE; ++i)
+  {
+    for (j = 0; j < i; ++j)
+      if (map[i] == map[j])
+      {
+        cm[i] = cm[j];
+        break;
+      }
+    if (!cm[i]) cm[i] = ++next;
+  }
+  if (!plf_upload(cp->ctx, cp->d_seq, sequence, partition->sites) ||
+      !plf_upload(cp->ctx, cp->d_rep_charmap, cm, PLL_ASCII_SIZE) ||
+      !plf_tip_keys(cp->ctx, cp->d_seq, cp->d_rep_charmap, partition->sites, cp->d_keys) ||
+      !plf_repeats_ids(cp->ctx, partition->sites, cp->d_keys, 0, NULL, cp->d_site_id[tip_index], cp->d_id_site_tmp,
+                       cp->d_lookup, &ids))
+    return cuda_fail(cp);
+  r->pernode_ids[tip_index] = ids;
+  cp->id_site_count[tip_index] = ids;
+
+  free(r->pernode_id_site[tip_index]);
+  r->pernode_id_site[tip_index] = (unsigned int *)malloc((size_t)(ids ? ids : 1) * sizeof(unsigned int));
+  plf_free(cp->ctx, cp->d_id_site[tip_index]);
+  cp->d_id_site[tip_index] = (unsigned int *)plf_alloc(cp->ctx, (size_t)(ids ? ids : 1) * sizeof(unsigned int), 0);
+  plf_free(cp->ctx, partition->clv[tip_index]);
+  partition->clv[tip_index] =
+      (double *)plf_alloc(cp->ctx, (size_t)ids * partition->states_padded * partition->rate_cats * sizeof(double), 1);
+  cp->clv_entries[tip_index] = ids;
+  r->pernode_allocated_clvs[tip_index] = ids;
+  if (!r->pernode_id_site[tip_index] || !cp->d_id_site[tip_index] || !partition->clv[tip_index])
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory for repeats structure. %s",
+              plf_last_error(cp->ctx));
+    return PLL_FAILURE;
+  }
+  if (!plf_copy_d2d(cp->ctx, cp->d_id_site[tip_index], cp->d_id_site_tmp, (size_t)ids * sizeof(unsigned int)))
+    return cuda_fail(cp);
+  cp->ids_stale[tip_index] = 1;
+  if (cp->repeats_mirror) sync_ids_to_host(cp, tip_index);
+  return PLL_SUCCESS;
+}
+
+/* class identifiers of the parent of `op` from its children's
+ * (src/repeats.c:299-382); identifiers are computed on the device */
+PLL_EXPORT void pll_update_repeats(pll_partition_t * partition, const pll_operation_t * op)
+{
+  cuda_partition_t * cp = CP(partition);
+  pll_repeats_t * r;
+  unsigned int left, right, parent, ids = 0, sites_to_alloc;
+  if (!cp) return;
+  r = partition->repeats;
+  left = op->child1_clv_index;
+  right = op->child2_clv_index;
+  parent = op->parent_clv_index;
+  if (!cp->d_lookup) pll_resize_repeats_lookup(partition, PLL_REPEATS_LOOKUP_SIZE);
+  if (!cp->d_lookup) return;
+
+  if (!r->enable_repeats(partition, left, right))
+  {
+    sites_to_alloc = partition->sites;
+    r->pernode_ids[parent] = 0;
+    if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = 0;
+  }
+  else
+  {
+    if (!plf_repeats_ids(cp->ctx, partition->sites, cp->d_site_id[left], r->pernode_ids[left], cp->d_site_id[right],
+                         cp->d_site_id[parent], cp->d_id_site_tmp, cp->d_lookup, &ids))
+    {
+      cuda_fail(cp);
+      return;
+    }
+    r->pernode_ids[parent] = ids;
+    if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = ids;
+    sites_to_alloc = ids;
+    cp->ids_stale[parent] = 1;
+  }
+  r->reallocate_repeats(partition, parent, op->parent_scaler_index, sites_to_alloc);
+  /* no compression on this node: tell the kernels not to gather */
+  if (sites_to_alloc >= partition->sites)
+  {
+    r->pernode_ids[parent] = 0;
+    if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = 0;
+  }
+  cp->id_site_count[parent] = ids;
+  if (ids && cp->d_id_site[parent] &&
+      !plf_copy_d2d(cp->ctx, cp->d_id_site[parent], cp->d_id_site_tmp, (size_t)ids * sizeof(unsigned int)))
+    cuda_fail(cp);
+  if (cp->repeats_mirror) sync_ids_to_host(cp, parent);
+}
+
+/* ---- tips ------------------------------------------------------------------- */
+
+static unsigned int ceil_log2(unsigned int x)
+{
+  unsigned int l = 0;
+  while ((1u << l) < x) ++l;
+  return l;
+}
+
+/* first call: dense codes for the distinct non-zero map values, in order of
+ * the first character that carries them (src/pll.c:295-422) */
+static int charmap_create(cuda_partition_t * cp, const pll_state_t * usermap)
+{
+  pll_partition_t * p = &cp->pub;
+  unsigned int i, j, k = 0;
+  pll_state_t top = 0;
+  p->charmap = (unsigned char *)calloc(PLL_ASCII_SIZE, sizeof(unsigned char));
+  p->tipmap = (pll_state_t *)calloc(PLL_ASCII_SIZE, sizeof(pll_state_t));
+  p->tipchars = (unsigned char **)calloc(p->tips ? p->tips : 1, sizeof(unsigned char *));
+  cp->d_tipchars = (unsigned char **)calloc(p->tips ? p->tips : 1, sizeof(unsigned char *));
+  if (!p->charmap || !p->tipmap || !p->tipchars || !cp->d_tipchars)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate charmap for tip-tip precomputation.%s", NULL);
+    return PLL_FAILURE;
+  }
+  for (i = 0; i < PLL_ASCII_SIZE; ++i)
+  {
+    if (!usermap[i]) continue;
+    for (j = 0; j < i; ++j)
+      if (usermap[j] == usermap[i]) break;
+    if (j < i)
+      p->charmap[i] = p->charmap[j];
+    else
+    {
+      if (usermap[i] > top) top = usermap[i];
+      p->charmap[i] = (unsigned char)k;
+      p->tipmap[k++] = usermap[i];
+    }
+  }
+  /* 4 states: tipchars hold the raw mask, code 0 is a fictive unused state */
+  p->maxstates = (p->states == 4) ? (unsigned int)top + 1 : k;
+  (void)ceil_log2; /* tip-tip tables live in shared memory: no ttlookup allocation */
+  for (i = 0; i < p->tips; ++i)
+  {
+    p->tipchars[i] = (unsigned char *)malloc(p->sites);
+    cp->d_tipchars[i] = (unsigned char *)plf_alloc(cp->ctx, p->sites, 1);
+    if (!p->tipchars[i] || !cp->d_tipchars[i])
+    {
+      set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate space for storing tip characters.%s", NULL);
+      return PLL_FAILURE;
+    }
+  }
+  cp->tipmap_dirty = 1;
+  return PLL_SUCCESS;
+}
+
+/* later calls with a (possibly different) map: known values keep their code,
+ * new ones are appended (src/pll.c:157-286) */
+static int charmap_update(cuda_partition_t * cp, const pll_state_t * map)
+{
+  pll_partition_t * p = &cp->pub;
+  unsigned int i, j, k = 0, added = 0;
+  unsigned char newmap[PLL_ASCII_SIZE];
+  pll_state_t newtips[PLL_ASCII_SIZE];
+  while (k < PLL_ASCII_SIZE && p->tipmap[k]) ++k;
+  memset(newmap, 0, sizeof(newmap));
+  memcpy(newtips, p->tipmap, sizeof(newtips));
+  for (i = 0; i < PLL_ASCII_SIZE; ++i)
+  {
+    if (!map[i]) continue;
+    for (j = 0; j < k + added; ++j)
+      if (newtips[j] == map[i]) break;
+    if (j == k + added)
+    {
+      if (k + added + 1 >= PLL_ASCII_SIZE)
+      {
+        memset(p->charmap, 0, PLL_ASCII_SIZE);
+        snprintf(pll_errmsg, 200, "Cannot specify 256 or more states with PLL_ATTRIB_PATTERN_TIP.");
+        return PLL_FAILURE;
+      }
+      newtips[j] = map[i];
+      ++added;
+    }
+    newmap[i] = (unsigned char)j;
+  }
+  memcpy(p->charmap, newmap, PLL_ASCII_SIZE);
+  if (added)
+  {
+    memcpy(p->tipmap, newtips, sizeof(newtips));
+    if (p->states == 4)
+    {
+      pll_state_t top = 0;
+      for (i = 0; p->tipmap[i]; ++i)
+        if (p->tipmap[i] > top) top = p->tipmap[i];
+      p->maxstates = (unsigned int)top + 1;
+    }
+    else
+      p->maxstates += added;
+    cp->tipmap_dirty = 1;
+  }
+  return PLL_SUCCESS;
+}
+
+static int check_sequence(const pll_partition_t * p, const pll_state_t * map, const char * sequence)
+{
+  unsigned int i;
+  for (i = 0; i < p->sites; ++i)
+    if (map[(unsigned char)sequence[i]] == 0)
+    {
+      pll_errno = PLL_ERROR_TIPDATA_ILLEGALSTATE;
+      snprintf(pll_errmsg, 200, "Illegal state code in tip \"%c\"", sequence[i]);
+      return PLL_FAILURE;
+    }
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_index, const pll_state_t * map,
+                                  const char * sequence)
+{
+  cuda_partition_t * cp = CP(partition);
+  unsigned int i;
+  if (!cp) return PLL_FAILURE;
+  if (tip_index >= partition->tips)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "tip index out of range%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!check_sequence(partition, map, sequence)) return PLL_FAILURE;
+
+  if (pll_repeats_enabled(partition) && !pll_update_repeats_tips(partition, tip_index, map, sequence))
+    return PLL_FAILURE;
+
+  if (partition->attributes & PLL_ATTRIB_PATTERN_TIP)
+  {
+    unsigned char * tc;
+    if (partition->tipchars)
+      charmap_update(cp, map);
+    else if (!charmap_create(cp, map))
+      return PLL_FAILURE;
+    tc = partition->tipchars[tip_index];
+    if (partition->states == 4)
+      for (i = 0; i < partition->sites; ++i) tc[i] = (unsigned char)map[(unsigned char)sequence[i]];
+    else
+      for (i = 0; i < partition->sites; ++i) tc[i] = partition->charmap[(unsigned char)sequence[i]];
+    if (!plf_upload(cp->ctx, cp->d_tipchars[tip_index], tc, partition->sites)) return cuda_fail(cp);
+    return PLL_SUCCESS;
+  }
+
+  /* tip CLV: bit j of the state mask -> entry j, replicated over the rates;
+   * built on the device from the raw characters (src/pll.c:959-1024) */
+  {
+    const int rep = pll_repeats_enabled(partition);
+    const unsigned int entries = rep ? partition->repeats->pernode_ids[tip_index] : partition->sites;
+    if (!plf_upload(cp->ctx, cp->d_seq, sequence, partition->sites) ||
+        !plf_upload(cp->ctx, cp->d_map, map, PLL_ASCII_SIZE * sizeof(pll_state_t)) ||
+        !plf_tip_clv_from_states(cp->ctx, &cp->shape, partition->clv[tip_index], cp->d_seq, cp->d_map,
+                                 rep ? cp->d_id_site[tip_index] : NULL, entries))
+      return cuda_fail(cp);
+  }
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition, unsigned int tip_index, const double * clv, int padding)
+{
+  cuda_partition_t * cp = CP(partition);
+  unsigned int i, j, entries;
+  const unsigned int sp = partition->states_padded, st = partition->states, R = partition->rate_cats;
+  const unsigned int in_states = padding ? sp : st;
+  const unsigned int * id_site = NULL;
+  double * staged;
+  int ok;
+  if (!cp) return PLL_FAILURE;
+  if (partition->attributes & PLL_ATTRIB_PATTERN_TIP)
+  {
+    pll_errno = PLL_ERROR_TIPDATA_ILLEGALFUNCTION;
+    snprintf(pll_errmsg, 200, "Cannot use pll_set_tip_clv with PLL_ATTRIB_PATTERN_TIP.");
+    return PLL_FAILURE;
+  }
+  entries = partition->sites;
+  if (pll_repeats_enabled(partition))
+  {
+    entries = partition->repeats->pernode_ids[tip_index];
+    sync_ids_to_host(cp, tip_index);
+    id_site = partition->repeats->pernode_id_site[tip_index];
+  }
+  if (!partition->clv[tip_index] || cp->clv_entries[tip_index] < entries)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "tip CLV buffer is not allocated%s", NULL);
+    return PLL_FAILURE;
+  }
+  staged = (double *)calloc((size_t)entries * R * sp, sizeof(double));
+  if (!staged)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+    return PLL_FAILURE;
+  }
+  for (i = 0; i < entries; ++i)
+  {
+    const double * src = clv + (size_t)(id_site ? id_site[i] : i) * in_states;
+    for (j = 0; j < R; ++j) memcpy(staged + ((size_t)i * R + j) * sp, src, st * sizeof(double));
+  }
+  ok = plf_upload(cp->ctx, partition->clv[tip_index], staged, (size_t)entries * R * sp * sizeof(double));
+  free(staged);
+  return ok ? PLL_SUCCESS : cuda_fail(cp);
+}
+
+PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition, const unsigned int * pattern_weights)
+{
+  cuda_partition_t * cp = CP(partition);
+  unsigned int i;
+  memcpy(partition->pattern_weights, pattern_weights, sizeof(unsigned int) * partition->sites);
+  partition->pattern_weight_sum = 0;
+  for (i = 0; i < partition->sites; ++i) partition->pattern_weight_sum += pattern_weights[i];
+  if (cp) cp->weights_dirty = 1;
+}
+
+PLL_EXPORT int pll_set_asc_bias_type(pll_partition_t * partition, int asc_bias_type)
+{
+  (void)asc_bias_type;
+  if (!partition->asc_bias_alloc)
+  {
+    set_error(PLL_ERROR_AB_NOSUPPORT, "Partition was not created with ascertainment bias support%s", NULL);
+    return PLL_FAILURE;
+  }
+  return PLL_FAILURE;
+}
+
+PLL_EXPORT void pll_set_asc_state_weights(pll_partition_t * partition, const unsigned int * state_weights)
+{
+  (void)partition;
+  (void)state_weights;
+  set_error(PLL_ERROR_AB_NOSUPPORT, "Partition was not created with ascertainment bias support%s", NULL);
+}
+
+PLL_EXPORT void pll_fill_parent_scaler(unsigned int scaler_size, unsigned int * parent_scaler,
+                                       const unsigned int * left_scaler, const unsigned int * right_scaler)
+{
+  unsigned int i;
+  for (i = 0; i < scaler_size; ++i)
+    parent_scaler[i] = (left_scaler ? left_scaler[i] : 0u) + (right_scaler ? right_scaler[i] : 0u);
+}
+
+/* ---- model parameters --------------------------------------------------------- */
+
+PLL_EXPORT void pll_set_frequencies(pll_partition_t * partition, unsigned int params_index,
+                                    const double * frequencies)
+{
+  unsigned int i;
+  double sum = 0.;
+  double * f = partition->frequencies[params_index];
+  memcpy(f, frequencies, partition->states * sizeof(double));
+  for (i = 0; i < partition->states; ++i) sum += f[i];
+  if (fabs(sum - 1.0) > PLL_MISC_EPSILON)
+    for (i = 0; i < partition->states; ++i) f[i] /= sum;
+  partition->eigen_decomp_valid[params_index] = 0;
+}
+
+PLL_EXPORT void pll_set_category_rates(pll_partition_t * partition, const double * rates)
+{
+  memcpy(partition->rates, rates, partition->rate_cats * sizeof(double));
+}
+
+PLL_EXPORT void pll_set_category_weights(pll_partition_t * partition, const double * rate_weights)
+{
+  memcpy(partition->rate_weights, rate_weights, partition->rate_cats * sizeof(double));
+}
+
+PLL_EXPORT void pll_set_subst_params(pll_partition_t * partition, unsigned int params_index, const double * params)
+{
+  memcpy(partition->subst_params[params_index], params,
+         (size_t)(partition->states * (partition->states - 1) / 2) * sizeof(double));
+  partition->eigen_decomp_valid[params_index] = 0;
+}
+
+PLL_EXPORT int pll_update_eigen(pll_partition_t * partition, unsigned int params_index)
+{
+  if (!pll_cuda_host_eigen(partition->states, partition->states_padded, partition->subst_params[params_index],
+                           partition->frequencies[params_index], partition->eigenvecs[params_index],
+                           partition->inv_eigenvecs[params_index], partition->eigenvals[params_index]))
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "eigen-decomposition did not converge%s", NULL);
+    return PLL_FAILURE;
+  }
+  partition->eigen_decomp_valid[params_index] = 1;
+  return PLL_SUCCESS;
+}
+
+/* pack the per-rate-category model block (layout in plf_backend.h) through
+ * `indices` and upload it if any byte differs from what the device holds */
+static const double * model_on_device(cuda_partition_t * cp, const unsigned int * indices)
+{
+  const pll_partition_t * p = &cp->pub;
+  const unsigned int R = p->rate_cats, st = p->states, sp = p->states_padded;
+  double * m = cp->h_model;
+  double * freqs = m + 3 * R;
+  double * evals = freqs + (size_t)R * sp;
+  double * evecs = evals + (size_t)R * sp;
+  double * ievecs = evecs + (size_t)R * st * sp;
+  unsigned int r;
+  for (r = 0; r < R; ++r)
+  {
+    const unsigned int x = indices ? indices[r] : 0;
+    m[r] = p->rates[r];
+    m[R + r] = p->rate_weights[r];
+    m[2 * R + r] = p->prop_invar[x];
+    memcpy(freqs + (size_t)r * sp, p->frequencies[x], sp * sizeof(double));
+    memcpy(evals + (size_t)r * sp, p->eigenvals[x], sp * sizeof(double));
+    memcpy(evecs + (size_t)r * st * sp, p->eigenvecs[x], (size_t)st * sp * sizeof(double));
+    memcpy(ievecs + (size_t)r * st * sp, p->inv_eigenvecs[x], (size_t)st * sp * sizeof(double));
+  }
+  if (!cp->model_sent_valid || memcmp(cp->h_model, cp->h_model_sent, cp->model_doubles * sizeof(double)))
+  {
+    if (!plf_upload_async(cp->ctx, cp->d_model, cp->h_model, cp->model_doubles * sizeof(double))) return NULL;
+    memcpy(cp->h_model_sent, cp->h_model, cp->model_doubles * sizeof(double));
+    cp->model_sent_valid = 1;
+  }
+  return cp->d_model;
+}
+
+static int weights_on_device(cuda_partition_t * cp)
+{
+  if (cp->weights_dirty)
+  {
+    if (!plf_upload(cp->ctx, cp->d_pattern_weights, cp->pub.pattern_weights,
+                    (size_t)cp->pub.sites * sizeof(unsigned int)))
+      return 0;
+    cp->weights_dirty = 0;
+  }
+  return 1;
+}
+
+static int tipmap_on_device(cuda_partition_t * cp)
+{
+  if (cp->tipmap_dirty && cp->pub.tipmap)
+  {
+    if (!plf_upload(cp->ctx, cp->d_tipmap, cp->pub.tipmap, PLL_ASCII_SIZE * sizeof(pll_state_t))) return 0;
+    cp->tipmap_dirty = 0;
+  }
+  return 1;
+}
+
+PLL_EXPORT int pll_cuda_invalidate_host_arrays(pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  cp->weights_dirty = 1;
+  cp->tipmap_dirty = 1;
+  cp->model_sent_valid = 0;
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT int pll_update_prob_matrices(pll_partition_t * partition, const unsigned int * params_indices,
+                                        const unsigned int * matrix_indices, const double * branch_lengths,
+                                        unsigned int count)
+{
+  cuda_partition_t * cp = CP(partition);
+  const double * d_model;
+  double * expd = NULL;
+  unsigned int i, n, j;
+  int ok;
+  if (!cp) return PLL_FAILURE;
+  for (n = 0; n < partition->rate_cats; ++n)
+    if (!partition->eigen_decomp_valid[params_indices[n]] && !pll_update_eigen(partition, params_indices[n]))
+      return PLL_FAILURE;
+  for (i = 0; i < count; ++i)
+    if (matrix_indices[i] >= partition->prob_matrices)
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "P-matrix index out of range%s", NULL);
+      return PLL_FAILURE;
+    }
+  if (!(d_model = model_on_device(cp, params_indices))) return cuda_fail(cp);
+
+  if (cp->host_expm1)
+  {
+    /* expm1 of (lambda * rate) * t [/ (1 - pinv)] with the host libm, as the
+     * reference does (src/core_pmatrix.c:206-216, core_pmatrix_avx.c:99-134):
+     * identical inputs to the matrix products => bit-identical P-matrices */
+    const unsigned int R = partition->rate_cats, st = partition->states;
+    expd = (double *)malloc((size_t)count * R * st * sizeof(double));
+    if (!expd)
+    {
+      set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+      return PLL_FAILURE;
+    }
+    for (i = 0; i < count; ++i)
+      for (n = 0; n < R; ++n)
+      {
+        const double pinv = partition->prop_invar[params_indices[n]];
+        const double * ev = partition->eigenvals[params_indices[n]];
+        double * e = expd + ((size_t)i * R + n) * st;
+        for (j = 0; j < st; ++j)
+        {
+          double x = (ev[j] * partition->rates[n]) * branch_lengths[i];
+          if (pinv > PLL_MISC_EPSILON) x = x / (1.0 - pinv);
+          e[j] = expm1(x);
+        }
+      }
+  }
+  ok = plf_update_pmatrices(cp->ctx, &cp->shape, d_model, cp->d_pmatrix_block, matrix_indices, branch_lengths, count,
+                            expd);
+  free(expd);
+  return ok ? PLL_SUCCESS : cuda_fail(cp);
+}
+
+/* ---- invariant sites ------------------------------------------------------------ */
+
+static int invariant_on_device(cuda_partition_t * cp, int * d_out)
+{
+  pll_partition_t * p = &cp->pub;
+  const int pattern = (p->attributes & PLL_ATTRIB_PATTERN_TIP) != 0;
+  const size_t nb = (size_t)p->tips * sizeof(void *);
+  void ** h = (void **)calloc(2 * (size_t)p->tips + 1, sizeof(void *));
+  void ** d = (void **)plf_alloc(cp->ctx, 2 * nb + 8, 0);
+  unsigned int i;
+  int ok = 0, any_ids = 0;
+  if (!h || !d) goto done;
+  if (pattern)
+  {
+    if (!cp->d_tipchars) goto done;
+    for (i = 0; i < p->tips; ++i) h[i] = cp->d_tipchars[i];
+    if (!tipmap_on_device(cp)) goto done;
+  }
+  else
+    for (i = 0; i < p->tips; ++i)
+    {
+      h[i] = p->clv[i];
+      if (p->repeats && p->repeats->pernode_ids[i])
+      {
+        h[p->tips + i] = cp->d_site_id[i];
+        any_ids = 1;
+      }
+    }
+  if (!plf_upload(cp->ctx, d, h, 2 * nb)) goto done;
+  ok = plf_invariant_sites(cp->ctx, &cp->shape, p->sites, p->tips, pattern ? (const unsigned char * const *)d : NULL,
+                           pattern ? NULL : (const double * const *)d,
+                           any_ids ? (const unsigned int * const *)(d + p->tips) : NULL, cp->d_tipmap, d_out);
+done:
+  if (d) plf_free(cp->ctx, d);
+  free(h);
+  return ok;
+}
+
+PLL_EXPORT int pll_update_invariant_sites(pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  if (!partition->invariant) partition->invariant = (int *)malloc((size_t)partition->sites * sizeof(int));
+  if (!cp->d_invariant) cp->d_invariant = (int *)plf_alloc(cp->ctx, (size_t)partition->sites * sizeof(int), 0);
+  if (!partition->invariant || !cp->d_invariant)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate charmap for invariant sites array.%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!invariant_on_device(cp, cp->d_invariant) ||
+      !plf_download(cp->ctx, partition->invariant, cp->d_invariant, (size_t)partition->sites * sizeof(int)))
+    return cuda_fail(cp);
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT unsigned int pll_count_invariant_sites(pll_partition_t * partition, unsigned int * state_inv_count)
+{
+  cuda_partition_t * cp = CP(partition);
+  unsigned int i, total = 0;
+  int * inv, * tmp = NULL;
+  if (!cp) return 0;
+  if (state_inv_count) memset(state_inv_count, 0, partition->states * sizeof(unsigned int));
+  inv = partition->invariant;
+  if (!inv)
+  {
+    int * d_tmp = (int *)plf_alloc(cp->ctx, (size_t)partition->sites * sizeof(int), 0);
+    tmp = (int *)malloc((size_t)partition->sites * sizeof(int));
+    if (!d_tmp || !tmp || !invariant_on_device(cp, d_tmp) ||
+        !plf_download(cp->ctx, tmp, d_tmp, (size_t)partition->sites * sizeof(int)))
+    {
+      plf_free(cp->ctx, d_tmp);
+      free(tmp);
+      cuda_fail(cp);
+      return 0;
+    }
+    plf_free(cp->ctx, d_tmp);
+    inv = tmp;
+  }
+  for (i = 0; i < partition->sites; ++i)
+    if (inv[i] > -1)
+    {
+      total += partition->pattern_weights[i];
+      if (state_inv_count) state_inv_count[inv[i]]++;
+    }
+  free(tmp);
+  return total;
+}
+
+PLL_EXPORT int pll_update_invariant_sites_proportion(pll_partition_t * partition, unsigned int params_index,
+                                                     double prop_invar)
+{
+  if (prop_invar < 0 || prop_invar >= 1)
+  {
+    pll_errno = PLL_ERROR_INVAR_PROPORTION;
+    snprintf(pll_errmsg, 200, "Invalid proportion of invariant sites (%f)", prop_invar);
+    return PLL_FAILURE;
+  }
+  if (params_index > partition->rate_matrices)
+  {
+    pll_errno = PLL_ERROR_INVAR_PARAMINDEX;
+    snprintf(pll_errmsg, 200, "Invalid params index (%u)", params_index);
+    return PLL_FAILURE;
+  }
+  if (prop_invar > 0.0 && !partition->invariant && !pll_update_invariant_sites(partition))
+  {
+    pll_errno = PLL_ERROR_INVAR_NONEFOUND;
+    snprintf(pll_errmsg, 200, "No invariant sites found");
+    return PLL_FAILURE;
+  }
+  partition->prop_invar[params_index] = prop_invar;
+  return PLL_SUCCESS;
+}
+
+/* ---- level schedule ------------------------------------------------------------ */
+
+/* Ops are strictly sequential in the reference (src/partials.c:253).  Here an
+ * op goes into the earliest launch level that keeps every read-after-write,
+ * write-after-read and write-after-write order on CLV and scaler indices. */
+PLL_EXPORT int pll_cuda_schedule_levels(const pll_operation_t * operations, unsigned int count,
+                                        unsigned int * level_of_op)
+{
+  unsigned int i, max_clv = 0, max_sc = 0, nlevels = 0;
+  int * clv_w, * clv_r, * sc_w, * sc_r;
+  if (!count) return 0;
+  for (i = 0; i < count; ++i)
+  {
+    const pll_operation_t * o = operations + i;
+    if (o->parent_clv_index > max_clv) max_clv = o->parent_clv_index;
+    if (o->child1_clv_index > max_clv) max_clv = o->child1_clv_index;
+    if (o->child2_clv_index > max_clv) max_clv = o->child2_clv_index;
+    if (o->parent_scaler_index > (int)max_sc) max_sc = (unsigned int)o->parent_scaler_index;
+    if (o->child1_scaler_index > (int)max_sc) max_sc = (unsigned int)o->child1_scaler_index;
+    if (o->child2_scaler_index > (int)max_sc) max_sc = (unsigned int)o->child2_scaler_index;
+  }
+  /* level of the last write / of the latest read since that write, -1 = none */
+  clv_w = (int *)malloc(((size_t)max_clv + 1) * sizeof(int));
+  clv_r = (int *)malloc(((size_t)max_clv + 1) * sizeof(int));
+  sc_w = (int *)malloc(((size_t)max_sc + 1) * sizeof(int));
+  sc_r = (int *)malloc(((size_t)max_sc + 1) * sizeof(int));
+  if (!clv_w || !clv_r || !sc_w || !sc_r)
+  {
+    free(clv_w);
+    free(clv_r);
+    free(sc_w);
+    free(sc_r);
+    return -1;
+  }
+  for (i = 0; i <= max_clv; ++i) clv_w[i] = clv_r[i] = -1;
+  for (i = 0; i <= max_sc; ++i) sc_w[i] = sc_r[i] = -1;
+#define AFTER(x) do { if ((x) + 1 > lv) lv = (x) + 1; } while (0)
+  for (i = 0; i < count; ++i)
+  {
+    const pll_operation_t * o = operations + i;
+    int lv = 0;
+    AFTER(clv_w[o->child1_clv_index]);
+    AFTER(clv_w[o->child2_clv_index]);
+    if (o->child1_scaler_index >= 0) AFTER(sc_w[o->child1_scaler_index]);
+    if (o->child2_scaler_index >= 0) AFTER(sc_w[o->child2_scaler_index]);
+    AFTER(clv_w[o->parent_clv_index]);
+    AFTER(clv_r[o->parent_clv_index]);
+    if (o->parent_scaler_index >= 0)
+    {
+      AFTER(sc_w[o->parent_scaler_index]);
+      AFTER(sc_r[o->parent_scaler_index]);
+    }
+    level_of_op[i] = (unsigned int)lv;
+    if ((unsigned int)lv + 1 > nlevels) nlevels = (unsigned int)lv + 1;
+    if (clv_r[o->child1_clv_index] < lv) clv_r[o->child1_clv_index] = lv;
+    if (clv_r[o->child2_clv_index] < lv) clv_r[o->child2_clv_index] = lv;
+    if (o->child1_scaler_index >= 0 && sc_r[o->child1_scaler_index] < lv) sc_r[o->child1_scaler_index] = lv;
+    if (o->child2_scaler_index >= 0 && sc_r[o->child2_scaler_index] < lv) sc_r[o->child2_scaler_index] = lv;
+    clv_w[o->parent_clv_index] = lv;
+    clv_r[o->parent_clv_index] = -1;
+    if (o->parent_scaler_index >= 0)
+    {
+      sc_w[o->parent_scaler_index] = lv;
+      sc_r[o->parent_scaler_index] = -1;
+    }
+  }
+#undef AFTER
+  free(clv_w);
+  free(clv_r);
+  free(sc_w);
+  free(sc_r);
+  return (int)nlevels;
+}
+
+/* ---- CLV updates ---------------------------------------------------------------- */
+
+static int reserve_ops(cuda_partition_t * cp, unsigned int count)
+{
+  if (count <= cp->ops_cap) return 1;
+  free(cp->h_ops);
+  free(cp->h_ops_sorted);
+  free(cp->h_level);
+  free(cp->h_level_start);
+  cp->h_ops = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
+  cp->h_ops_sorted = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
+  cp->h_level = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  cp->h_level_start = (unsigned int *)malloc(((size_t)count + 2) * sizeof(unsigned int));
+  cp->ops_cap = (cp->h_ops && cp->h_ops_sorted && cp->h_level && cp->h_level_start) ? count : 0;
+  return cp->ops_cap != 0;
+}
+
+/* turn one pll_operation_t into device pointers + kernel variant
+ * (dispatch of src/partials.c:245-291) */
+static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_t * out)
+{
+  const pll_partition_t * p = &cp->pub;
+  const unsigned int c1 = op->child1_clv_index, c2 = op->child2_clv_index, par = op->parent_clv_index;
+  unsigned int * const * sb = p->scale_buffer;
+  memset(out, 0, sizeof(*out));
+  if (par >= p->nodes || c1 >= p->nodes || c2 >= p->nodes || op->child1_matrix_index >= p->prob_matrices ||
+      op->child2_matrix_index >= p->prob_matrices || op->parent_scaler_index >= (int)p->scale_buffers ||
+      op->child1_scaler_index >= (int)p->scale_buffers || op->child2_scaler_index >= (int)p->scale_buffers)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "operation refers to a buffer index out of range%s", NULL);
+    return 0;
+  }
+  out->parent_clv = p->clv[par];
+  out->parent_scaler = op->parent_scaler_index >= 0 ? sb[op->parent_scaler_index] : NULL;
+  out->nsites = p->sites;
+  if (pll_repeats_enabled(p))
+  {
+    const pll_repeats_t * r = p->repeats;
+    out->kind = PLF_OP_II;
+    out->left_clv = p->clv[c1];
+    out->right_clv = p->clv[c2];
+    out->left_matrix = p->pmatrix[op->child1_matrix_index];
+    out->right_matrix = p->pmatrix[op->child2_matrix_index];
+    out->left_scaler = op->child1_scaler_index >= 0 ? sb[op->child1_scaler_index] : NULL;
+    out->right_scaler = op->child2_scaler_index >= 0 ? sb[op->child2_scaler_index] : NULL;
+    if (r->pernode_ids[par])
+    {
+      out->parent_id_site = cp->d_id_site[par];
+      out->nsites = r->pernode_ids[par];
+    }
+    if (r->pernode_ids[c1]) out->left_site_id = cp->d_site_id[c1];
+    if (r->pernode_ids[c2]) out->right_site_id = cp->d_site_id[c2];
+  }
+  else
+  {
+    const int pattern = (p->attributes & PLL_ATTRIB_PATTERN_TIP) != 0;
+    const int t1 = pattern && c1 < p->tips, t2 = pattern && c2 < p->tips;
+    if (t1 && t2)
+    {
+      out->kind = PLF_OP_TT;
+      out->left_tip = cp->d_tipchars ? cp->d_tipchars[c1] : NULL;
+      out->right_tip = cp->d_tipchars ? cp->d_tipchars[c2] : NULL;
+      out->left_matrix = p->pmatrix[op->child1_matrix_index];
+      out->right_matrix = p->pmatrix[op->child2_matrix_index];
+      if (!out->left_tip || !out->right_tip) goto missing;
+    }
+    else if (t1 || t2)
+    {
+      /* the tip is always passed as "left" (src/partials.c:68-128) */
+      const unsigned int tip = t1 ? c1 : c2, inner = t1 ? c2 : c1;
+      const unsigned int mt = t1 ? op->child1_matrix_index : op->child2_matrix_index;
+      const unsigned int mi = t1 ? op->child2_matrix_index : op->child1_matrix_index;
+      const int si = t1 ? op->child2_scaler_index : op->child1_scaler_index;
+      out->kind = PLF_OP_TI;
+      out->left_tip = cp->d_tipchars ? cp->d_tipchars[tip] : NULL;
+      out->right_clv = p->clv[inner];
+      out->left_matrix = p->pmatrix[mt];
+      out->right_matrix = p->pmatrix[mi];
+      out->right_scaler = si >= 0 ? sb[si] : NULL;
+      if (!out->left_tip || !out->right_clv) goto missing;
+    }
+    else
+    {
+      out->kind = PLF_OP_II;
+      out->left_clv = p->clv[c1];
+      out->right_clv = p->clv[c2];
+      out->left_matrix = p->pmatrix[op->child1_matrix_index];
+      out->right_matrix = p->pmatrix[op->child2_matrix_index];
+      out->left_scaler = op->child1_scaler_index >= 0 ? sb[op->child1_scaler_index] : NULL;
+      out->right_scaler = op->child2_scaler_index >= 0 ? sb[op->child2_scaler_index] : NULL;
+    }
+  }
+  if (!out->parent_clv || (out->kind == PLF_OP_II && (!out->left_clv || !out->right_clv))) goto missing;
+  return 1;
+missing:
+  set_error(PLL_ERROR_PARAM_INVALID, "operation refers to a CLV or tip buffer that was never set%s", NULL);
+  return 0;
+}
+
+static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+{
+  unsigned int i, nlevels;
+  int nl;
+  if (!reserve_ops(cp, count))
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+    return 0;
+  }
+  for (i = 0; i < count; ++i)
+    if (!resolve_op(cp, ops + i, cp->h_ops + i)) return 0;
+  nl = pll_cuda_schedule_levels(ops, count, cp->h_level);
+  if (nl < 0)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+    return 0;
+  }
+  nlevels = (unsigned int)nl;
+  /* counting sort by level (stable) */
+  for (i = 0; i <= nlevels; ++i) cp->h_level_start[i] = 0;
+  for (i = 0; i < count; ++i) cp->h_level_start[cp->h_level[i] + 1]++;
+  for (i = 0; i < nlevels; ++i) cp->h_level_start[i + 1] += cp->h_level_start[i];
+  {
+    unsigned int * cursor = (unsigned int *)malloc(((size_t)nlevels + 1) * sizeof(unsigned int));
+    if (!cursor) return 0;
+    memcpy(cursor, cp->h_level_start, ((size_t)nlevels + 1) * sizeof(unsigned int));
+    for (i = 0; i < count; ++i) cp->h_ops_sorted[cursor[cp->h_level[i]]++] = cp->h_ops[i];
+    free(cursor);
+  }
+  if (!tipmap_on_device(cp) ||
+      !plf_update_partials(cp->ctx, &cp->shape, cp->h_ops_sorted, count, cp->h_level_start, nlevels, cp->d_tipmap,
+                           cp->pub.maxstates))
+  {
+    cuda_fail(cp);
+    return 0;
+  }
+  return 1;
+}
+
+/* does a later op overwrite a CLV that an earlier op of the list touched? */
+static int reuses_buffers(const pll_operation_t * ops, unsigned int count, unsigned int nodes)
+{
+  unsigned char * seen = (unsigned char *)calloc(nodes ? nodes : 1, 1);
+  unsigned int i;
+  int reuse = 0;
+  if (!seen) return 1;
+  for (i = 0; i < count && !reuse; ++i)
+  {
+    if (ops[i].parent_clv_index < nodes && seen[ops[i].parent_clv_index]) reuse = 1;
+    if (ops[i].parent_clv_index < nodes) seen[ops[i].parent_clv_index] = 1;
+    if (ops[i].child1_clv_index < nodes) seen[ops[i].child1_clv_index] = 1;
+    if (ops[i].child2_clv_index < nodes) seen[ops[i].child2_clv_index] = 1;
+  }
+  free(seen);
+  return reuse;
+}
+
+PLL_EXPORT void pll_update_partials_rep(pll_partition_t * partition, const pll_operation_t * operations,
+                                        unsigned int count, unsigned int update_repeats)
+{
+  cuda_partition_t * cp = CP(partition);
+  unsigned int i;
+  if (!cp || !count) return;
+  if (pll_repeats_enabled(partition) && update_repeats)
+  {
+    if (reuses_buffers(operations, count, partition->nodes))
+    {
+      /* identifier arrays are overwritten in place: keep the reference's
+       * strict op order when the list recycles CLV indices */
+      for (i = 0; i < count; ++i)
+      {
+        pll_update_repeats(partition, operations + i);
+        if (!launch_levels(cp, operations + i, 1)) return;
+      }
+      return;
+    }
+    /* identifiers depend on the children's identifiers only, not on CLV
+     * values: compute them for the whole list first, then run the levels */
+    for (i = 0; i < count; ++i) pll_update_repeats(partition, operations + i);
+  }
+  launch_levels(cp, operations, count);
+}
+
+PLL_EXPORT void pll_update_partials(pll_partition_t * partition, const pll_operation_t * operations,
+                                    unsigned int count)
+{
+  pll_update_partials_rep(partition, operations, count, 1);
+}
+
+/* ---- log-likelihood ---------------------------------------------------------------- */
+
+static double * persite_buffer(cuda_partition_t * cp)
+{
+  if (cp->persite_cap < cp->pub.sites)
+  {
+    plf_free(cp->ctx, cp->d_persite);
+    cp->d_persite = (double *)plf_alloc(cp->ctx, (size_t)cp->pub.sites * sizeof(double), 0);
+    cp->persite_cap = cp->d_persite ? cp->pub.sites : 0;
+  }
+  return cp->d_persite;
+}
+
+static int fill_edge_args(cuda_partition_t * cp, plf_lk_t * a, unsigned int parent_clv_index,
+                          int parent_scaler_index, unsigned int child_clv_index, int child_scaler_index,
+                          unsigned int matrix_index, const unsigned int * freqs_indices)
+{
+  const pll_partition_t * p = &cp->pub;
+  unsigned int * const * sb = p->scale_buffer;
+  memset(a, 0, sizeof(*a));
+  if (parent_clv_index >= p->nodes || child_clv_index >= p->nodes || matrix_index >= p->prob_matrices ||
+      parent_scaler_index >= (int)p->scale_buffers || child_scaler_index >= (int)p->scale_buffers)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "buffer index out of range%s", NULL);
+    return 0;
+  }
+  a->sites = p->sites;
+  a->pmatrix = p->pmatrix[matrix_index];
+  a->pattern_weights = cp->d_pattern_weights;
+  a->invariant = cp->d_invariant;
+  if ((p->attributes & PLL_ATTRIB_PATTERN_TIP) && (parent_clv_index < p->tips || child_clv_index < p->tips))
+  {
+    /* tip-inner: the inner node plays "parent" (src/likelihood.c:612-624) */
+    const int ptip = parent_clv_index < p->tips;
+    const unsigned int inner = ptip ? child_clv_index : parent_clv_index;
+    const unsigned int tip = ptip ? parent_clv_index : child_clv_index;
+    const int sc = ptip ? child_scaler_index : parent_scaler_index;
+    if (inner < p->tips || !cp->d_tipchars)
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "edge log-likelihood between two pattern tips is not defined%s", NULL);
+      return 0;
+    }
+    a->clvp = p->clv[inner];
+    a->pscaler = sc >= 0 ? sb[sc] : NULL;
+    a->tipchars = cp->d_tipchars[tip];
+    a->tipmap = cp->d_tipmap;
+    if (!tipmap_on_device(cp)) return 0;
+  }
+  else
+  {
+    a->clvp = p->clv[parent_clv_index];
+    a->clvc = p->clv[child_clv_index];
+    a->pscaler = parent_scaler_index >= 0 ? sb[parent_scaler_index] : NULL;
+    a->cscaler = child_scaler_index >= 0 ? sb[child_scaler_index] : NULL;
+    if (pll_repeats_enabled(p))
+    {
+      if (p->repeats->pernode_ids[parent_clv_index]) a->p_site_id = cp->d_site_id[parent_clv_index];
+      if (p->repeats->pernode_ids[child_clv_index]) a->c_site_id = cp->d_site_id[child_clv_index];
+    }
+    if (!a->clvc)
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "child CLV was never set%s", NULL);
+      return 0;
+    }
+  }
+  if (!a->clvp)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "parent CLV was never set%s", NULL);
+    return 0;
+  }
+  if (!weights_on_device(cp) || !(a->model = model_on_device(cp, freqs_indices)))
+  {
+    cuda_fail(cp);
+    return 0;
+  }
+  return 1;
+}
+
+static int fill_root_args(cuda_partition_t * cp, plf_lk_t * a, unsigned int clv_index, int scaler_index,
+                          const unsigned int * freqs_indices)
+{
+  const pll_partition_t * p = &cp->pub;
+  memset(a, 0, sizeof(*a));
+  if (clv_index >= p->nodes || scaler_index >= (int)p->scale_buffers || !p->clv[clv_index])
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "root CLV index out of range or never set%s", NULL);
+    return 0;
+  }
+  a->sites = p->sites;
+  a->clvp = p->clv[clv_index];
+  a->pscaler = scaler_index >= 0 ? p->scale_buffer[scaler_index] : NULL;
+  a->pattern_weights = cp->d_pattern_weights;
+  a->invariant = cp->d_invariant;
+  if (pll_repeats_enabled(p) && p->repeats->pernode_ids[clv_index]) a->p_site_id = cp->d_site_id[clv_index];
+  if (!weights_on_device(cp) || !(a->model = model_on_device(cp, freqs_indices)))
+  {
+    cuda_fail(cp);
+    return 0;
+  }
+  return 1;
+}
+
+static double run_loglikelihood(cuda_partition_t * cp, plf_lk_t * a, double * persite_lnl)
+{
+  double logl = 0;
+  if (persite_lnl && !(a->persite = persite_buffer(cp)))
+  {
+    cuda_fail(cp);
+    return -INFINITY;
+  }
+  if (!plf_loglikelihood(cp->ctx, &cp->shape, a, NULL, &logl) ||
+      (persite_lnl && !plf_download(cp->ctx, persite_lnl, a->persite, (size_t)cp->pub.sites * sizeof(double))))
+  {
+    cuda_fail(cp);
+    return -INFINITY;
+  }
+  return logl;
+}
+
+PLL_EXPORT double pll_compute_edge_loglikelihood(pll_partition_t * partition, unsigned int parent_clv_index,
+                                                 int parent_scaler_index, unsigned int child_clv_index,
+                                                 int child_scaler_index, unsigned int matrix_index,
+                                                 const unsigned int * freqs_indices, double * persite_lnl)
+{
+  cuda_partition_t * cp = CP(partition);
+  plf_lk_t a;
+  if (!cp || !fill_edge_args(cp, &a, parent_clv_index, parent_scaler_index, child_clv_index, child_scaler_index,
+                             matrix_index, freqs_indices))
+    return -INFINITY;
+  return run_loglikelihood(cp, &a, persite_lnl);
+}
+
+PLL_EXPORT double pll_compute_root_loglikelihood(pll_partition_t * partition, unsigned int clv_index,
+                                                 int scaler_index, const unsigned int * freqs_indices,
+                                                 double * persite_lnl)
+{
+  cuda_partition_t * cp = CP(partition);
+  plf_lk_t a;
+  if (!cp || !fill_root_args(cp, &a, clv_index, scaler_index, freqs_indices)) return -INFINITY;
+  return run_loglikelihood(cp, &a, persite_lnl);
+}
+
+PLL_EXPORT int pll_cuda_edge_loglikelihood_async(pll_partition_t * partition, unsigned int parent_clv_index,
+                                                 int parent_scaler_index, unsigned int child_clv_index,
+                                                 int child_scaler_index, unsigned int matrix_index,
+                                                 const unsigned int * freqs_indices, double * dev_out)
+{
+  cuda_partition_t * cp = CP(partition);
+  plf_lk_t a;
+  if (!cp || !dev_out ||
+      !fill_edge_args(cp, &a, parent_clv_index, parent_scaler_index, child_clv_index, child_scaler_index,
+                      matrix_index, freqs_indices))
+    return PLL_FAILURE;
+  return plf_loglikelihood(cp->ctx, &cp->shape, &a, dev_out, NULL) ? PLL_SUCCESS : cuda_fail(cp);
+}
+
+PLL_EXPORT int pll_cuda_root_loglikelihood_async(pll_partition_t * partition, unsigned int clv_index,
+                                                 int scaler_index, const unsigned int * freqs_indices,
+                                                 double * dev_out)
+{
+  cuda_partition_t * cp = CP(partition);
+  plf_lk_t a;
+  if (!cp || !dev_out || !fill_root_args(cp, &a, clv_index, scaler_index, freqs_indices)) return PLL_FAILURE;
+  return plf_loglikelihood(cp->ctx, &cp->shape, &a, dev_out, NULL) ? PLL_SUCCESS : cuda_fail(cp);
+}
+
+/* ---- sumtable and derivatives ---------------------------------------------------------- */
+
+static sumtable_slot_t * sumtable_slot(cuda_partition_t * cp, const double * key, int create)
+{
+  const size_t need = (size_t)cp->pub.sites * cp->pub.rate_cats * cp->pub.states_padded;
+  sumtable_slot_t * victim = &cp->sumtabs[0];
+  int i;
+  for (i = 0; i < MAX_SUMTABLES; ++i)
+    if (cp->sumtabs[i].dev && cp->sumtabs[i].key == key)
+    {
+      cp->sumtabs[i].stamp = ++cp->stamp;
+      return &cp->sumtabs[i];
+    }
+  if (!create) return NULL;
+  for (i = 0; i < MAX_SUMTABLES; ++i)
+  {
+    if (!cp->sumtabs[i].dev)
+    {
+      victim = &cp->sumtabs[i];
+      break;
+    }
+    if (cp->sumtabs[i].stamp < victim->stamp) victim = &cp->sumtabs[i];
+  }
+  if (victim->dev && victim->doubles < need)
+  {
+    plf_free(cp->ctx, victim->dev);
+    victim->dev = NULL;
+  }
+  if (!victim->dev)
+  {
+    victim->dev = (double *)plf_alloc(cp->ctx, need * sizeof(double), 0);
+    victim->doubles = victim->dev ? need : 0;
+    if (!victim->dev) return NULL;
+  }
+  victim->key = key;
+  victim->stamp = ++cp->stamp;
+  return victim;
+}
+
+PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition, unsigned int parent_clv_index,
+                                   unsigned int child_clv_index, int parent_scaler_index, int child_scaler_index,
+                                   const unsigned int * params_indices, double * sumtable)
+{
+  cuda_partition_t * cp = CP(partition);
+  const pll_partition_t * p = partition;
+  plf_sumtable_t a;
+  sumtable_slot_t * slot;
+  unsigned int * const * sb;
+  if (!cp) return PLL_FAILURE;
+  sb = p->scale_buffer;
+  memset(&a, 0, sizeof(a));
+  if (parent_clv_index >= p->nodes || child_clv_index >= p->nodes || parent_scaler_index >= (int)p->scale_buffers ||
+      child_scaler_index >= (int)p->scale_buffers || !sumtable)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "buffer index out of range%s", NULL);
+    return PLL_FAILURE;
+  }
+  a.sites = p->sites;
+  if ((p->attributes & PLL_ATTRIB_PATTERN_TIP) && (parent_clv_index < p->tips || child_clv_index < p->tips))
+  {
+    const int ptip = parent_clv_index < p->tips;
+    const unsigned int inner = ptip ? child_clv_index : parent_clv_index;
+    const unsigned int tip = ptip ? parent_clv_index : child_clv_index;
+    const int sc = ptip ? child_scaler_index : parent_scaler_index;
+    if (inner < p->tips)
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "pll_update_sumtable() was called for the tip-tip case!%s", NULL);
+      return PLL_FAILURE;
+    }
+    /* the tip takes the pi * V^-1 side, the inner CLV the V side
+     * (src/derivatives.c:24-98, src/core_derivatives.c:473) */
+    a.tipchars = cp->d_tipchars ? cp->d_tipchars[tip] : NULL;
+    a.tipmap = cp->d_tipmap;
+    a.clvc = p->clv[inner];
+    a.cscaler = sc >= 0 ? sb[sc] : NULL;
+    if (!a.tipchars || !tipmap_on_device(cp))
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "tip states were never set%s", NULL);
+      return PLL_FAILURE;
+    }
+  }
+  else
+  {
+    a.clvp = p->clv[parent_clv_index];
+    a.clvc = p->clv[child_clv_index];
+    a.pscaler = parent_scaler_index >= 0 ? sb[parent_scaler_index] : NULL;
+    a.cscaler = child_scaler_index >= 0 ? sb[child_scaler_index] : NULL;
+    if (pll_repeats_enabled(p))
+    {
+      if (p->repeats->pernode_ids[parent_clv_index]) a.p_site_id = cp->d_site_id[parent_clv_index];
+      if (p->repeats->pernode_ids[child_clv_index]) a.c_site_id = cp->d_site_id[child_clv_index];
+    }
+    if (!a.clvp)
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "parent CLV was never set%s", NULL);
+      return PLL_FAILURE;
+    }
+  }
+  if (!a.clvc)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "child CLV was never set%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!(slot = sumtable_slot(cp, sumtable, 1)) || !(a.model = model_on_device(cp, params_indices))) return cuda_fail(cp);
+  a.sumtable = slot->dev;
+  if (!plf_update_sumtable(cp->ctx, &cp->shape, &a)) return cuda_fail(cp);
+  if (cp->sumtable_mirror &&
+      !plf_download(cp->ctx, sumtable, slot->dev, (size_t)p->sites * p->rate_cats * p->states_padded * sizeof(double)))
+    return cuda_fail(cp);
+  return PLL_SUCCESS;
+}
+
+static int derivative_args(cuda_partition_t * cp, plf_deriv_t * a, double branch_length,
+                           const unsigned int * params_indices, const double * sumtable)
+{
+  const pll_partition_t * p = &cp->pub;
+  sumtable_slot_t * slot = sumtable_slot(cp, sumtable, 0);
+  memset(a, 0, sizeof(*a));
+  if (!slot)
+  {
+    /* a table this library did not compute: the host bytes are the data */
+    if (!sumtable || !(slot = sumtable_slot(cp, sumtable, 1)) ||
+        !plf_upload(cp->ctx, slot->dev, sumtable, (size_t)p->sites * p->rate_cats * p->states_padded * sizeof(double)))
+    {
+      cuda_fail(cp);
+      return 0;
+    }
+  }
+  a->sites = p->sites;
+  a->sumtable = slot->dev;
+  a->pattern_weights = cp->d_pattern_weights;
+  a->invariant = cp->d_invariant;
+  a->branch_length = branch_length;
+  if (!weights_on_device(cp) || !(a->model = model_on_device(cp, params_indices)))
+  {
+    cuda_fail(cp);
+    return 0;
+  }
+  return 1;
+}
+
+PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition, int parent_scaler_index,
+                                                  int child_scaler_index, double branch_length,
+                                                  const unsigned int * params_indices, const double * sumtable,
+                                                  double * d_f, double * dd_f)
+{
+  cuda_partition_t * cp = CP(partition);
+  plf_deriv_t a;
+  double out[2] = {0, 0};
+  (void)parent_scaler_index; /* per-site ratios cancel the scaling (src/core_derivatives.c:825-848) */
+  (void)child_scaler_index;
+  if (!cp || !derivative_args(cp, &a, branch_length, params_indices, sumtable)) return PLL_FAILURE;
+  if (!plf_derivatives(cp->ctx, &cp->shape, &a, NULL, out)) return cuda_fail(cp);
+  *d_f = out[0];
+  *dd_f = out[1];
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT int pll_cuda_likelihood_derivatives_async(pll_partition_t * partition, int parent_scaler_index,
+                                                     int child_scaler_index, double branch_length,
+                                                     const unsigned int * params_indices, const double * sumtable,
+                                                     double * dev_out2)
+{
+  cuda_partition_t * cp = CP(partition);
+  plf_deriv_t a;
+  (void)parent_scaler_index;
+  (void)child_scaler_index;
+  if (!cp || !dev_out2 || !derivative_args(cp, &a, branch_length, params_indices, sumtable)) return PLL_FAILURE;
+  return plf_derivatives(cp->ctx, &cp->shape, &a, dev_out2, NULL) ? PLL_SUCCESS : cuda_fail(cp);
+}
+
+/* ---- explicit reads of device-resident buffers ---------------------------------------------- */
+
+PLL_EXPORT int pll_cuda_download_clv(const pll_partition_t * partition, unsigned int clv_index, double * host_out)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  if (clv_index >= partition->nodes || !partition->clv[clv_index])
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "no such CLV%s", NULL);
+    return PLL_FAILURE;
+  }
+  return plf_download(cp->ctx, host_out, partition->clv[clv_index],
+                      (size_t)pll_get_clv_size(partition, clv_index) * sizeof(double))
+             ? PLL_SUCCESS
+             : cuda_fail(cp);
+}
+
+PLL_EXPORT unsigned int pll_cuda_scaler_size(const pll_partition_t * partition, unsigned int scaler_index)
+{
+  cuda_partition_t * cp = CP(partition);
+  unsigned int n;
+  if (!cp || scaler_index >= partition->scale_buffers) return 0;
+  n = partition->sites;
+  if (pll_repeats_enabled(partition) && partition->repeats->perscale_ids[scaler_index])
+    n = partition->repeats->perscale_ids[scaler_index];
+  if (partition->attributes & PLL_ATTRIB_RATE_SCALERS) n *= partition->rate_cats;
+  return n <= cp->scaler_entries[scaler_index] ? n : cp->scaler_entries[scaler_index];
+}
+
+PLL_EXPORT int pll_cuda_download_scaler(const pll_partition_t * partition, unsigned int scaler_index,
+                                        unsigned int * host_out)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  if (scaler_index >= partition->scale_buffers || !partition->scale_buffer[scaler_index])
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "no such scale buffer%s", NULL);
+    return PLL_FAILURE;
+  }
+  return plf_download(cp->ctx, host_out, partition->scale_buffer[scaler_index],
+                      (size_t)pll_cuda_scaler_size(partition, scaler_index) * sizeof(unsigned int))
+             ? PLL_SUCCESS
+             : cuda_fail(cp);
+}
+
+static size_t pmatrix_doubles(const pll_partition_t * p)
+{
+  return (size_t)p->states * p->states_padded * p->rate_cats;
+}
+
+PLL_EXPORT int pll_cuda_download_pmatrix(const pll_partition_t * partition, unsigned int matrix_index,
+                                         double * host_out)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  if (matrix_index >= partition->prob_matrices)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "no such P-matrix%s", NULL);
+    return PLL_FAILURE;
+  }
+  return plf_download(cp->ctx, host_out, partition->pmatrix[matrix_index], pmatrix_doubles(partition) * sizeof(double))
+             ? PLL_SUCCESS
+             : cuda_fail(cp);
+}
+
+PLL_EXPORT int pll_cuda_upload_pmatrix(pll_partition_t * partition, unsigned int matrix_index, const double * host_in)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  if (matrix_index >= partition->prob_matrices)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "no such P-matrix%s", NULL);
+    return PLL_FAILURE;
+  }
+  return plf_upload(cp->ctx, partition->pmatrix[matrix_index], host_in, pmatrix_doubles(partition) * sizeof(double))
+             ? PLL_SUCCESS
+             : cuda_fail(cp);
+}
+
+PLL_EXPORT int pll_cuda_download_sumtable(const pll_partition_t * partition, const double * sumtable_handle,
+                                          double * host_out)
+{
+  cuda_partition_t * cp = CP(partition);
+  sumtable_slot_t * slot;
+  if (!cp) return PLL_FAILURE;
+  if (!(slot = sumtable_slot(cp, sumtable_handle, 0)))
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "unknown sumtable handle%s", NULL);
+    return PLL_FAILURE;
+  }
+  return plf_download(cp->ctx, host_out, slot->dev,
+                      (size_t)partition->sites * partition->rate_cats * partition->states_padded * sizeof(double))
+             ? PLL_SUCCESS
+             : cuda_fail(cp);
+}
+
+/* ---- debug printers (format of src/output.c:26-101) ---------------------------------------------- */
+
+PLL_EXPORT void pll_show_pmatrix(const pll_partition_t * partition, unsigned int index, unsigned int float_precision)
+{
+  const unsigned int st = partition->states, sp = partition->states_padded;
+  double * m = (double *)malloc(pmatrix_doubles(partition) * sizeof(double));
+  unsigned int i, j, k;
+  if (!m || !pll_cuda_download_pmatrix(partition, index, m))
+  {
+    free(m);
+    return;
+  }
+  for (k = 0; k < partition->rate_cats; ++k)
+  {
+    for (i = 0; i < st; ++i)
+    {
+      for (j = 0; j < st; ++j) printf("%+2.*f   ", float_precision, m[(size_t)k * st * sp + i * sp + j]);
+      printf("\n");
+    }
+    printf("\n");
+  }
+  free(m);
+}
+
+PLL_EXPORT void pll_show_clv(const pll_partition_t * partition, unsigned int clv_index, int scaler_index,
+                             unsigned int float_precision)
+{
+  const unsigned int st = partition->states, sp = partition->states_padded, R = partition->rate_cats;
+  unsigned int s, i, j, k, t;
+  double * clv;
+  unsigned int * scaler = NULL;
+  const unsigned int * site_id;
+  if ((clv_index < partition->tips) && (partition->attributes & PLL_ATTRIB_PATTERN_TIP)) return;
+  clv = (double *)malloc((size_t)pll_get_clv_size(partition, clv_index) * sizeof(double));
+  if (!clv || !pll_cuda_download_clv(partition, clv_index, clv))
+  {
+    free(clv);
+    return;
+  }
+  if (scaler_index != PLL_SCALE_BUFFER_NONE)
+  {
+    scaler = (unsigned int *)malloc((size_t)(pll_cuda_scaler_size(partition, scaler_index) + 1) * sizeof(unsigned int));
+    if (!scaler || !pll_cuda_download_scaler(partition, scaler_index, scaler))
+    {
+      free(scaler);
+      free(clv);
+      return;
+    }
+  }
+  site_id = pll_get_site_id(partition, clv_index);
+  printf("[ ");
+  for (s = 0; s < partition->sites; ++s)
+  {
+    i = site_id ? site_id[s] : s;
+    printf("{");
+    for (j = 0; j < R; ++j)
+    {
+      printf("(");
+      for (k = 0; k < st; ++k)
+      {
+        double prob = clv[(size_t)i * R * sp + j * sp + k];
+        if (scaler)
+          for (t = 0; t < scaler[i]; ++t) prob *= PLL_SCALE_THRESHOLD;
+        printf("%.*f%s", float_precision, prob, k + 1 < st ? "," : ")");
+      }
+      if (j < R - 1) printf(",");
+    }
+    printf("} ");
+  }
+  printf("]\n");
+  free(scaler);
+  free(clv);
+}

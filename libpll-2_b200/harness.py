@@ -180,10 +180,16 @@ class Engine:
         return np.ctypeslib.as_array(getattr(self.part, field)[idx], shape=(n,)).copy()
 
     def repeat_ids(self, node: int):
+        """(class count, site->class, class->first site) through the public
+        accessors; count 0 means the node is not compressed."""
         rep = self.part.repeats.contents
         ids = int(rep.pernode_ids[node])
-        site_id = np.ctypeslib.as_array(rep.pernode_site_id[node], shape=(self.sites,)).copy()
-        id_site = np.ctypeslib.as_array(rep.pernode_id_site[node], shape=(max(ids, 1),)).copy()[:ids]
+        if not ids:
+            return 0, None, None
+        sp = self.lib.pll_get_site_id(self.p, node)
+        ip = self.lib.pll_get_id_site(self.p, node)
+        site_id = np.ctypeslib.as_array(sp, shape=(self.sites,)).copy()
+        id_site = np.ctypeslib.as_array(ip, shape=(ids,)).copy()
         return ids, site_id, id_site
 
     def close(self):

@@ -1,0 +1,307 @@
+"""Parity of the CUDA engine (libpll_b200.so, through its C ABI) with the
+UNMODIFIED reference (oracle/_ref/libpll_ref.so run with PLL_ATTRIB_ARCH_AVX2)
+on identical seeded inputs.
+
+Contract (BASELINE.json north_star): P-matrices, CLVs, integer scalers and
+site-repeat identifiers bit-exact; log-likelihood within 1e-10 relative;
+derivatives within 1e-9 relative.  Needs a B200: every test is marked gpu.
+"""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+pkg = importlib.import_module("libpll-2_b200")
+capi = pkg.capi
+synth = importlib.import_module("libpll-2_b200.synth")
+harness = importlib.import_module("libpll-2_b200.harness")
+
+pytestmark = pytest.mark.gpu
+
+LOGL_RTOL = 1e-10
+DERIV_RTOL = 1e-9
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def make_ds(kind, tips, sites, tree, seed=11, **kw):
+    if kind == "dna":
+        return synth.dna_dataset(tips, sites, seed=seed, tree_kind=tree, alpha=0.4, **kw)
+    if kind == "aa":
+        return synth.aa_dataset(tips, sites, seed=seed + 1, tree_kind=tree, alpha=0.4)
+    return synth.generic_dataset(int(kind[1:]), tips, sites, seed=seed + 2, tree_kind=tree)
+
+
+def pair(reflib, cudalib, ds, extra, per_rate=False):
+    flags = extra | (capi.RATE_SCALERS if per_rate else 0)
+    ref = harness.Engine(reflib, ds, capi.ARCH_AVX2 | flags)
+    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | flags)
+    return ref, gpu
+
+
+def assert_rel(a, b, rtol, what):
+    assert abs(a - b) <= rtol * max(abs(b), 1e-300), f"{what}: {a!r} vs {b!r} rel {abs(a - b) / abs(b):.3e}"
+
+
+def check_edge_and_derivatives(ref, gpu, ds, per_rate, edges=None):
+    for edge in edges or [ds.tree.root_edge]:
+        l_ref, ps_ref = ref.edge_logl(edge, persite=True)
+        l_gpu, ps_gpu = gpu.edge_logl(edge, persite=True)
+        assert_rel(l_gpu, l_ref, LOGL_RTOL, f"edge logL {edge}")
+        np.testing.assert_allclose(ps_gpu, ps_ref, rtol=1e-12, atol=0)
+        st_ref = ref.sumtable_alloc()
+        st_gpu = gpu.sumtable_alloc()
+        ref.update_sumtable(st_ref, edge)
+        gpu.update_sumtable(st_gpu, edge)
+        for t in (0.003, 0.1, 0.9):
+            d_ref = ref.derivatives(st_ref, t, edge)
+            d_gpu = gpu.derivatives(st_gpu, t, edge)
+            # the derivative is a sum of per-site terms of both signs: relative
+            # to the magnitude the terms reach (golden fragility)
+            scale1 = max(abs(d_ref[0]), 1e-6 * ds.sites)
+            scale2 = max(abs(d_ref[1]), 1e-6 * ds.sites)
+            assert abs(d_gpu[0] - d_ref[0]) <= DERIV_RTOL * scale1, (t, d_gpu, d_ref)
+            assert abs(d_gpu[1] - d_ref[1]) <= DERIV_RTOL * scale2, (t, d_gpu, d_ref)
+
+
+CASES = [
+    # kind, tips, sites, tree, attrs, per_rate
+    ("dna", 12, 97, "random", capi.PATTERN_TIP, False),
+    ("dna", 12, 97, "random", 0, False),
+    ("dna", 40, 1501, "random", capi.PATTERN_TIP, False),
+    ("dna", 300, 61, "caterpillar", capi.PATTERN_TIP, False),
+    ("dna", 300, 61, "caterpillar", capi.PATTERN_TIP, True),
+    ("dna", 200, 33, "caterpillar", 0, True),
+    ("dna", 200, 33, "caterpillar", 0, False),
+    ("aa", 10, 53, "random", capi.PATTERN_TIP, False),
+    ("aa", 10, 53, "random", 0, False),
+    ("aa", 120, 21, "caterpillar", capi.PATTERN_TIP, False),
+    ("aa", 120, 21, "caterpillar", capi.PATTERN_TIP, True),
+    ("aa", 110, 17, "caterpillar", 0, False),
+    ("g5", 10, 41, "random", capi.PATTERN_TIP, False),
+    ("g5", 150, 19, "caterpillar", capi.PATTERN_TIP, False),
+    ("g7", 150, 19, "caterpillar", 0, True),
+    ("g7", 12, 40, "random", 0, False),
+]
+
+
+@pytest.mark.parametrize("kind,tips,sites,tree,extra,per_rate", CASES)
+def test_traversal_parity(reflib, cudalib, kind, tips, sites, tree, extra, per_rate):
+    ds = make_ds(kind, tips, sites, tree)
+    ref, gpu = pair(reflib, cudalib, ds, extra, per_rate)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    p = ref.part
+    st = p.states
+    for mi in ref.matrix_indices:
+        a = ref.pmatrix(mi).reshape(p.rate_cats, st, p.states_padded)[:, :, :st]
+        b = gpu.pmatrix(mi).reshape(p.rate_cats, st, p.states_padded)[:, :, :st]
+        assert np.array_equal(bits(a), bits(b)), f"pmatrix {mi}"
+    n_scaled = 0
+    for op in ref.ops:
+        a, b = ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index)
+        assert np.array_equal(bits(a), bits(b)), f"clv {op.parent_clv_index}"
+        if op.parent_scaler_index >= 0:
+            sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
+            assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
+            n_scaled += int(sa.sum())
+    if tree == "caterpillar":
+        assert n_scaled > 0, "case was meant to trigger scaling"
+    check_edge_and_derivatives(ref, gpu, ds, per_rate)
+    # a tip edge and a second inner edge
+    last = ref.ops[len(ref.ops) - 1]
+    extra_edges = [(last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index)]
+    if not (extra & capi.PATTERN_TIP and last.child1_clv_index < ds.tree.tips and last.parent_clv_index < ds.tree.tips):
+        check_edge_and_derivatives(ref, gpu, ds, per_rate, extra_edges)
+    if not per_rate:  # the reference's root logL ignores per-rate scalers
+        r_ref, rp_ref = ref.root_logl(persite=True)
+        r_gpu, rp_gpu = gpu.root_logl(persite=True)
+        assert_rel(r_gpu, r_ref, LOGL_RTOL, "root logL")
+        np.testing.assert_allclose(rp_gpu, rp_ref, rtol=1e-12)
+    ref.close()
+    gpu.close()
+
+
+@pytest.mark.parametrize("kind,extra", [("dna", capi.PATTERN_TIP), ("dna", 0), ("aa", capi.PATTERN_TIP), ("g5", 0)])
+@pytest.mark.parametrize("pinv", [0.3])
+def test_invariant_sites_parity(reflib, cudalib, kind, extra, pinv):
+    ds = make_ds(kind, 9, 257, "random", seed=21)
+    # make a good share of columns invariant
+    seqs = [bytearray(s) for s in ds.seqs]
+    for col in range(0, ds.sites, 3):
+        for s in seqs:
+            s[col] = seqs[0][col]
+    ds.seqs = [bytes(s) for s in seqs]
+    ds.prop_invar = pinv
+    ds.pattern_weights = np.random.default_rng(3).integers(1, 6, size=ds.sites).astype(np.uint32)
+    ref, gpu = pair(reflib, cudalib, ds, extra)
+    inv_ref = np.ctypeslib.as_array(ref.part.invariant, shape=(ds.sites,)).copy()
+    inv_gpu = np.ctypeslib.as_array(gpu.part.invariant, shape=(ds.sites,)).copy()
+    assert np.array_equal(inv_ref, inv_gpu)
+    assert (inv_ref >= 0).sum() > 10
+    cnt_ref = np.zeros(ds.states, dtype=np.uint32)
+    cnt_gpu = np.zeros(ds.states, dtype=np.uint32)
+    n_ref = reflib.pll_count_invariant_sites(ref.p, cnt_ref.ctypes.data_as(capi.c_uint_p))
+    n_gpu = cudalib.pll_count_invariant_sites(gpu.p, cnt_gpu.ctypes.data_as(capi.c_uint_p))
+    assert n_ref == n_gpu and np.array_equal(cnt_ref, cnt_gpu)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    for mi in ref.matrix_indices[:4]:
+        assert np.array_equal(bits(ref.pmatrix(mi)), bits(gpu.pmatrix(mi)))
+    check_edge_and_derivatives(ref, gpu, ds, False)
+    assert_rel(gpu.root_logl(), ref.root_logl(), LOGL_RTOL, "root logL +I")
+    ref.close()
+    gpu.close()
+
+
+REPEAT_CASES = [
+    ("dna", 24, 400, "random", False, (0.002, 0.05)),
+    ("dna", 64, 3000, "random", False, (0.002, 0.05)),
+    ("dna", 300, 128, "caterpillar", False, (0.02, 0.22)),
+    ("dna", 300, 128, "caterpillar", True, (0.02, 0.22)),
+    ("aa", 40, 300, "random", False, (0.002, 0.05)),
+    ("g5", 30, 200, "random", False, (0.002, 0.05)),
+]
+
+
+@pytest.mark.parametrize("kind,tips,sites,tree,per_rate,brlen", REPEAT_CASES)
+def test_site_repeats_parity(reflib, cudalib, kind, tips, sites, tree, per_rate, brlen):
+    if kind == "dna":
+        ds = synth.dna_dataset(tips, sites, seed=31, tree_kind=tree, alpha=0.3, brlen=brlen)
+    elif kind == "aa":
+        ds = synth.aa_dataset(tips, sites, seed=32, tree_kind=tree, alpha=0.3, brlen=brlen)
+    else:
+        ds = synth.generic_dataset(5, tips, sites, seed=33, tree_kind=tree, brlen=brlen)
+    ref, gpu = pair(reflib, cudalib, ds, capi.SITE_REPEATS, per_rate)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    compressed = 0
+    for node in range(ds.tree.nodes):
+        ids_r, sid_r, ids_site_r = ref.repeat_ids(node)
+        ids_g, sid_g, ids_site_g = gpu.repeat_ids(node)
+        assert ids_r == ids_g, f"class count of node {node}"
+        if ids_r:
+            compressed += node >= tips
+            assert np.array_equal(sid_r, sid_g), f"site_id of node {node}"
+            assert np.array_equal(ids_site_r, ids_site_g), f"id_site of node {node}"
+        assert ref.clv_size(node) == gpu.clv_size(node)
+    assert compressed > 0, "case was meant to compress inner nodes"
+    n_scaled = 0
+    for op in ref.ops:
+        a, b = ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index)
+        assert np.array_equal(bits(a), bits(b)), f"clv {op.parent_clv_index}"
+        sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
+        assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
+        n_scaled += int(sa.sum())
+    if tree == "caterpillar":
+        assert n_scaled > 0
+    last = ref.ops[len(ref.ops) - 1]
+    edges = [ds.tree.root_edge, (last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index)]
+    check_edge_and_derivatives(ref, gpu, ds, per_rate, edges)
+    if not per_rate:
+        assert_rel(gpu.root_logl(), ref.root_logl(), LOGL_RTOL, "root logL")
+    # a second traversal without recomputing identifiers (update_repeats = 0)
+    bl = ds.tree.branch_lengths[ref.matrix_indices] * 1.5
+    for e, lib in ((ref, reflib), (gpu, cudalib)):
+        e.update_pmatrices(branch_lengths=bl)
+        lib.pll_update_partials_rep(e.p, e.ops, len(e.ops), 0)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL after re-traversal")
+    ref.close()
+    gpu.close()
+
+
+def test_unrooted_example_golden(cudalib):
+    """Config 1: examples/unrooted/unrooted.c:43-124 -- 4 tips x 6 sites GTR+G4;
+    expected values from the reference's own run."""
+    from test_reference_examples import run_unrooted
+
+    vals = run_unrooted(cudalib, capi.ARCH_CUDA)
+    assert vals == pytest.approx([-33.387713, -34.550204, -36.830297], abs=5e-7)
+
+
+def test_buffer_reuse_in_one_op_list(reflib, cudalib):
+    """test/src/derivatives.c:91-98 recycles a CLV index inside one operation
+    list; the level scheduler must keep the sequential meaning."""
+    ds = make_ds("dna", 8, 120, "random", seed=41)
+    t = ds.tree
+    ops = t.ops.copy()
+    # rewrite the last-but-one op's parent into a recycled CLV: append an op that
+    # recomputes the first inner node from two other tips after it was consumed
+    first_parent = int(ops[0][0])
+    extra_op = np.array([[first_parent, int(ops[0][1]), 2, 2, -1, 3, 3, -1]], dtype=np.int64)
+    ds.tree.ops = np.concatenate([ops, extra_op])
+    ref, gpu = pair(reflib, cudalib, ds, 0)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    for op in ref.ops:
+        assert np.array_equal(bits(ref.clv(op.parent_clv_index)), bits(gpu.clv(op.parent_clv_index)))
+        assert np.array_equal(ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index))
+    ref.close()
+    gpu.close()
+
+
+def test_device_expm1_mode_within_tolerance(reflib, cudalib, monkeypatch):
+    """PLL_CUDA_DEVICE_EXPM1=1 evaluates expm1 on the GPU: P-matrices may differ
+    in the last place, log-likelihood stays within the 1e-10 contract."""
+    ds = make_ds("dna", 60, 500, "random", seed=51)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    a, b = ref.pmatrix(3), gpu.pmatrix(3)
+    np.testing.assert_allclose(b, a, rtol=1e-14, atol=1e-17)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL, device expm1")
+    ref.close()
+    gpu.close()
+
+
+def test_full_size_properties(cudalib):
+    """Config-2-shaped run (100 taxa, pattern tips, GTR+G4) at a size the CPU
+    reference would take minutes for: size-independent properties instead.
+    (a) logL is additive over contiguous site slices; (b) the per-site values
+    sum to the total; (c) doubling pattern weights doubles logL."""
+    sites = 200_000
+    ds = synth.dna_dataset(100, sites, seed=1, simulate_down_tree=False)
+    full = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    total, persite = (full.full_traversal(), None)
+    total2, persite = full.edge_logl(persite=True)
+    assert total == total2
+    assert_rel(float(np.sum(persite)), total, 1e-12, "sum of per-site logL")
+    parts = 0.0
+    for lo, hi in ((0, 70_016), (70_016, sites)):
+        e = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP, sites_slice=slice(lo, hi))
+        parts += e.full_traversal()
+        e.close()
+    assert_rel(parts, total, 1e-12, "site-slice additivity")
+    w = np.full(sites, 2, dtype=np.uint32)
+    cudalib.pll_set_pattern_weights(full.p, w.ctypes.data_as(capi.c_uint_p))
+    assert_rel(full.edge_logl(), 2 * total, 1e-13, "pattern weights")
+    full.close()
+
+
+def test_oracle_port_agrees_with_cuda(oracle, cudalib):
+    """The scalar C restatement (oracle/plf_oracle.c) replayed on the CUDA
+    engine's own P-matrices gives the same CLVs and scalers bit for bit."""
+    from test_oracle_vs_reference import run_oracle_traversal
+
+    ds = make_ds("dna", 150, 77, "caterpillar", seed=61)
+    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    gpu.update_pmatrices()
+    gpu.update_partials()
+    p = gpu.part
+    msz = p.states * p.states_padded * p.rate_cats
+    block = np.zeros(p.prob_matrices * msz + 64)
+    for mi in gpu.matrix_indices:
+        block[mi * msz:(mi + 1) * msz] = gpu.pmatrix(mi)
+    clv, scal, _, _ = run_oracle_traversal(oracle, gpu, block, False)
+    for op in gpu.ops:
+        assert np.array_equal(bits(gpu.clv(op.parent_clv_index)), bits(clv[op.parent_clv_index]))
+        assert np.array_equal(gpu.scaler(op.parent_scaler_index), scal[op.parent_scaler_index])
+    gpu.close()

@@ -1,0 +1,139 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every
+symbol include/pll_b200.h declares, fails loudly without a device, the host
+eigendecomposition matches the reference bit for bit, and the level scheduler
+honours RAW/WAR/WAW hazards."""
+import ctypes as C
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+pkg = importlib.import_module("libpll-2_b200")
+capi = pkg.capi
+synth = importlib.import_module("libpll-2_b200.synth")
+harness = importlib.import_module("libpll-2_b200.harness")
+
+HEADER = os.path.join(pkg.REPO_DIR, "include", "pll_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return pkg.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    names = capi.exported_symbols_declared_in_header(HEADER)
+    assert len(names) > 60
+    missing = [n for n in names if not hasattr(lib.lib, n)]
+    assert not missing
+
+
+def test_no_oracle_or_reference_linked(lib):
+    """The product library must not depend on anything under oracle/."""
+    import subprocess
+
+    out = subprocess.run(["ldd", lib.path], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libpll_ref" not in out and "plf_oracle" not in out
+
+
+def test_create_fails_loudly_without_device_or_cuda_bit(lib):
+    import torch
+
+    p = lib.pll_partition_create(4, 2, 4, 100, 1, 6, 4, 2, capi.ARCH_AVX2)
+    assert not p and lib.errno == 901
+    p = lib.pll_partition_create(4, 2, 4, 100, 1, 6, 4, 2, capi.ARCH_CUDA | capi.ARCH_AVX)
+    assert not p and "Multiple architecture" in lib.errmsg
+    if not torch.cuda.is_available():
+        p = lib.pll_partition_create(4, 2, 4, 100, 1, 6, 4, 2, capi.ARCH_CUDA)
+        assert not p and lib.errno == 900  # no CPU fallback
+
+
+def _ref_eigen(reflib, ds, index=0):
+    p = reflib.pll_partition_create(4, 2, ds.states, 16, len(ds.subst_params), 6, ds.rate_cats, 2, capi.ARCH_AVX2)
+    part = p.contents
+    f = np.ascontiguousarray(ds.freqs[index])
+    s = np.ascontiguousarray(ds.subst_params[index])
+    reflib.pll_set_frequencies(p, index, f.ctypes.data_as(capi.c_double_p))
+    reflib.pll_set_subst_params(p, index, s.ctypes.data_as(capi.c_double_p))
+    assert reflib.pll_update_eigen(p, index) == 1
+    st, sp = part.states, part.states_padded
+    out = (
+        np.ctypeslib.as_array(part.eigenvecs[index], shape=(st * sp,)).copy(),
+        np.ctypeslib.as_array(part.inv_eigenvecs[index], shape=(st * sp,)).copy(),
+        np.ctypeslib.as_array(part.eigenvals[index], shape=(sp,)).copy(),
+        np.ctypeslib.as_array(part.frequencies[index], shape=(sp,)).copy(),
+        sp,
+    )
+    reflib.pll_partition_destroy(p)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["dna", "aa", "g5", "g7", "dna_zero_freq"])
+def test_host_eigen_bit_exact(lib, reflib, kind):
+    if kind == "dna":
+        ds = synth.dna_dataset(4, 16, seed=1, simulate_down_tree=False)
+    elif kind == "dna_zero_freq":
+        ds = synth.dna_dataset(4, 16, seed=1, simulate_down_tree=False)
+        ds.freqs[0] = np.array([0.5, 0.0, 0.3, 0.2])
+    elif kind == "aa":
+        ds = synth.aa_dataset(4, 16, seed=2, simulate_down_tree=False)
+    else:
+        ds = synth.generic_dataset(int(kind[1:]), 4, 16, seed=3)
+    for index in range(len(ds.subst_params)):
+        ev, iev, evals, freqs, sp = _ref_eigen(reflib, ds, index)
+        st = ds.states
+        my_ev, my_iev, my_evals = np.zeros(st * sp), np.zeros(st * sp), np.zeros(sp)
+        s = np.ascontiguousarray(ds.subst_params[index])
+        rc = lib.pll_cuda_host_eigen(
+            st, sp, s.ctypes.data_as(capi.c_double_p), freqs.ctypes.data_as(capi.c_double_p),
+            my_ev.ctypes.data_as(capi.c_double_p), my_iev.ctypes.data_as(capi.c_double_p),
+            my_evals.ctypes.data_as(capi.c_double_p),
+        )
+        assert rc == 1
+        assert np.array_equal(my_evals.view(np.uint64), evals.view(np.uint64))
+        assert np.array_equal(my_ev.view(np.uint64), ev.view(np.uint64))
+        assert np.array_equal(my_iev.view(np.uint64), iev.view(np.uint64))
+
+
+def _levels(lib, rows):
+    ops = (capi.Operation * len(rows))()
+    for i, r in enumerate(rows):
+        ops[i] = capi.Operation(*r)
+    lv = np.zeros(len(rows), dtype=np.uint32)
+    n = lib.pll_cuda_schedule_levels(ops, len(rows), lv.ctypes.data_as(capi.c_uint_p))
+    return n, lv.tolist()
+
+
+def test_schedule_levels_tree(lib):
+    # ((0,1)4,(2,3)5)6 : two independent cherries then their join
+    rows = [(4, 0, 0, 0, -1, 1, 1, -1), (5, 1, 2, 2, -1, 3, 3, -1), (6, 2, 4, 4, 0, 5, 5, 1)]
+    assert _levels(lib, rows) == (2, [0, 0, 1])
+
+
+def test_schedule_levels_buffer_reuse(lib):
+    # op2 overwrites CLV 4 that op1 reads (WAR), op3 reads the new CLV 4 (RAW);
+    # op4 rewrites scaler 0 that op3 read (WAR on a scaler)
+    rows = [
+        (4, 0, 0, 0, -1, 1, 1, -1),
+        (5, 1, 4, 4, 0, 2, 2, -1),
+        (4, 2, 2, 2, -1, 3, 3, -1),
+        (6, 3, 4, 4, 2, 5, 5, 1),
+        (7, 0, 0, 0, -1, 3, 3, -1),
+    ]
+    n, lv = _levels(lib, rows)
+    assert lv[1] > lv[0] and lv[2] > lv[1] and lv[3] > lv[2]
+    assert lv[4] > lv[1]  # scaler 0 was read by op 1
+    assert n == max(lv) + 1
+
+
+def test_schedule_levels_random_tree_matches_depth(lib):
+    ds = synth.dna_dataset(64, 16, seed=5, simulate_down_tree=False)
+    rows = [tuple(int(x) for x in r) for r in ds.tree.ops]
+    n, lv = _levels(lib, rows)
+    depth = {}
+    for r, l in zip(rows, lv):
+        d = 1 + max(depth.get(r[2], -1), depth.get(r[5], -1))
+        depth[r[0]] = d
+        assert l == d
+    assert n == max(depth.values()) + 1
