@@ -350,7 +350,7 @@ def run_b200_arm(args):
                 "note": "pll_update_prob_matrices + pll_update_partials + pll_compute_edge_loglikelihood with host "
                         "arguments, synchronous host double back; tip data stays resident as in the reference"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_partials_dna<1>" if ds.states == 4 else "k_partials_gen<20>",
+        "roofline": {"bound": "hbm", "kernel": "k_clv_dna_{ii,ti,tt}<2,4>" if ds.states == 4 else "k_partials_gen<20>",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": None,
                      "algorithmic_bytes_per_step": clv_bytes, "launches_per_step": int(n_levels),

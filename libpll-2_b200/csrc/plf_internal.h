@@ -17,6 +17,7 @@ struct plf_ctx
   size_t smem_optin;
   size_t gen20_smem_set;
   size_t lk20_smem_set;
+  int dna_occupancy[3][6]; /* resident CTAs per SM of the DNA CLV kernels [kind][log2 rates] */
   cudaStream_t stream;
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
   plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
@@ -30,6 +31,9 @@ struct plf_ctx
 void plf_set_error(plf_ctx * ctx, const char * fmt, ...);
 void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes);
 void plf_count_launch(void);
+struct plf_op;
+int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
+                         unsigned int rate_cats, int per_rate, unsigned int max_sites);
 
 #define PLF_CHECK(ctx, call)                                                         \
   do                                                                                 \

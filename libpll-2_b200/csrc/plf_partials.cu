@@ -445,22 +445,35 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
       any_tip |= (h_ops[i].kind != PLF_OP_II);
     }
     if (!max_sites) continue;
+    if (sh->states == 4 && one_rate)
+    {
+      /* specialised kernels per op kind (plf_partials_dna.cu): one launch per
+       * run of same-kind ops; the host layer sorts a level by kind */
+      for (unsigned int i = a; i < b;)
+      {
+        unsigned int j = i, run_sites = 0;
+        while (j < b && h_ops[j].kind == h_ops[i].kind)
+        {
+          if (h_ops[j].nsites > run_sites) run_sites = h_ops[j].nsites;
+          ++j;
+        }
+        if (run_sites && !plf_launch_dna_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
+                                               sh->per_rate_scalers, run_sites))
+          return 0;
+        i = j;
+      }
+      continue;
+    }
     if (sh->states == 4)
     {
       const int threads = 256;
-      const unsigned long long work = (unsigned long long)max_sites * L;
-      unsigned int bx = (unsigned int)((work + threads - 1) / threads);
-      /* persistent-style grid: a few waves of the 148 SMs x 2 resident CTAs,
-       * shared between the ops of the level */
+      unsigned int bx = (unsigned int)(((unsigned long long)max_sites + threads - 1) / threads);
       unsigned int cap = (unsigned int)(ctx->sm_count * 2 * 4) / (b - a);
       if (cap < 1) cap = 1;
       if (bx > cap) bx = cap;
       dim3 grid(bx, b - a);
       const size_t smem = any_tip ? (size_t)2 * 64 * R * sizeof(double) : 0;
-      if (one_rate)
-        k_partials_dna<1><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers);
-      else
-        k_partials_dna<0><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers);
+      k_partials_dna<0><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers);
     }
     else
     {

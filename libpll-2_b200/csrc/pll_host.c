@@ -1364,7 +1364,7 @@ static int reserve_ops(cuda_partition_t * cp, unsigned int count)
   cp->h_ops = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
   cp->h_ops_sorted = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
   cp->h_level = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
-  cp->h_level_start = (unsigned int *)malloc(((size_t)count + 2) * sizeof(unsigned int));
+  cp->h_level_start = (unsigned int *)malloc((3 * (size_t)count + 2) * sizeof(unsigned int));
   cp->ops_cap = (cp->h_ops && cp->h_ops_sorted && cp->h_level && cp->h_level_start) ? count : 0;
   return cp->ops_cap != 0;
 }
@@ -1469,7 +1469,10 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
     return 0;
   }
   nlevels = (unsigned int)nl;
-  /* counting sort by level (stable) */
+  /* counting sort by (level, op kind), stable: each launch group is a run of
+   * same-kind ops of one level */
+  for (i = 0; i < count; ++i) cp->h_level[i] = cp->h_level[i] * 3 + cp->h_ops[i].kind;
+  nlevels *= 3;
   for (i = 0; i <= nlevels; ++i) cp->h_level_start[i] = 0;
   for (i = 0; i < count; ++i) cp->h_level_start[cp->h_level[i] + 1]++;
   for (i = 0; i < nlevels; ++i) cp->h_level_start[i + 1] += cp->h_level_start[i];
