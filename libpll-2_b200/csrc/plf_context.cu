@@ -56,6 +56,7 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
   if (!ctx) return 0;
   ctx->device = device;
   ctx->managed = managed;
+  ctx->dna_stream = -1;
   cudaError_t e = cudaSetDevice(device);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);

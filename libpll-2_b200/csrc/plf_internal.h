@@ -18,6 +18,10 @@ struct plf_ctx
   size_t gen20_smem_set;
   size_t lk20_smem_set;
   int dna_occupancy[3][6]; /* resident CTAs per SM of the DNA CLV kernels [kind][log2 rates] */
+  int dna_stream_occupancy[2][6];
+  int dna_stream;          /* -1 = read PLF_DNA_STREAM / PLF_DNA_STAGES on first use */
+  int dna_stages;
+  int dna_items;
   cudaStream_t stream;
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
   plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
@@ -33,7 +37,7 @@ void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes);
 void plf_count_launch(void);
 struct plf_op;
 int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
-                         unsigned int rate_cats, int per_rate, unsigned int max_sites);
+                         unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous);
 
 #define PLF_CHECK(ctx, call)                                                         \
   do                                                                                 \

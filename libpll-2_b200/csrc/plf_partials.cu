@@ -452,13 +452,15 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
       for (unsigned int i = a; i < b;)
       {
         unsigned int j = i, run_sites = 0;
+        int contiguous = 1;
         while (j < b && h_ops[j].kind == h_ops[i].kind)
         {
           if (h_ops[j].nsites > run_sites) run_sites = h_ops[j].nsites;
+          if (h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id) contiguous = 0;
           ++j;
         }
         if (run_sites && !plf_launch_dna_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
-                                               sh->per_rate_scalers, run_sites))
+                                               sh->per_rate_scalers, run_sites, contiguous))
           return 0;
         i = j;
       }

@@ -27,6 +27,8 @@
 #include "plf_device.cuh"
 #include "plf_internal.h"
 
+#include <stdlib.h>
+
 #define DNA_THREADS 128
 
 struct SiteRef
@@ -214,53 +216,275 @@ k_clv_dna_ti(const plf_op_t * __restrict__ ops, int per_rate)
  * (src/core_partials_avx.c:255-400,992-1030: the reference builds the 16x16      *
  * product table once per op; multiplying the two half-tables per site gives the   *
  * same bits)                                                                       */
+#define TT_GROUP 8 /* consecutive sites per thread: their 8 tip codes are one 64-bit load per tip */
+
 template <int LOG2R, int U>
-__global__ void __launch_bounds__(DNA_THREADS, 4)
-k_clv_dna_tt(const plf_op_t * __restrict__ ops, int per_rate)
+__global__ void __launch_bounds__(DNA_THREADS, 6)
+k_clv_dna_tt(const plf_op_t * __restrict__ ops, int per_rate_and_nops)
 {
+  /* A write-only kernel (134 B/site out, 2 B/site in).  One thread owns the
+   * (rate) block of TT_GROUP consecutive sites: a single round of load latency
+   * (two 64-bit code loads) is followed by 8 table products and 8 256-bit
+   * stores.  The two half-tables are read with the 16-byte halves swapped
+   * between the even and odd site group of a quarter-warp, which makes the
+   * LDS.128 accesses conflict-free. */
   constexpr int R = 1 << LOG2R;
-  __shared__ __align__(16) double tl[64 * R];
-  __shared__ __align__(16) double tr[64 * R];
-  const plf_op_t op = ops[blockIdx.y];
+  __shared__ __align__(128) double tl[64 * R];
+  __shared__ __align__(128) double tr[64 * R];
+  const int per_rate = per_rate_and_nops & 1;
+  const unsigned int nops = (unsigned int)per_rate_and_nops >> 1;
+  const unsigned int tid = blockIdx.x * DNA_THREADS + threadIdx.x;
+  const int rate = tid & (R - 1);
+  const unsigned int grp0 = tid >> LOG2R;
+  const unsigned int pass = (gridDim.x * DNA_THREADS) >> LOG2R;
+  /* gridDim.y == 1: the whole grid sweeps one op after the other, so that the
+   * chip writes ONE parent CLV at a time (few open DRAM pages) */
+  for (unsigned int o = blockIdx.y; o < nops; o += gridDim.y)
+  {
+  const plf_op_t op = ops[o];
+  __syncthreads();
   build_tip_table(tl, op.left_matrix, R);
   build_tip_table(tr, op.right_matrix, R);
   __syncthreads();
-  const unsigned int tid = blockIdx.x * DNA_THREADS + threadIdx.x;
-  const int rate = tid & (R - 1);
-  const unsigned int site0 = tid >> LOG2R;
-  const unsigned int pass = (gridDim.x * DNA_THREADS) >> LOG2R;
+  const unsigned int ngroups = (op.nsites + TT_GROUP - 1) / TT_GROUP;
+  const bool direct = !(op.parent_id_site || op.left_site_id || op.right_site_id);
+  const int swap = (R <= 4) ? ((threadIdx.x >> LOG2R) & 1) : 0; /* odd group of the quarter-warp */
 
-  for (unsigned int base = 0; base < op.nsites; base += pass * U)
+  for (unsigned int g = grp0; g < ngroups; g += pass)
   {
-    unsigned int n[U], lc[U], rc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
+    const unsigned int first = g * TT_GROUP;
+    unsigned long long lc8 = 0, rc8 = 0;
+    if (direct)
     {
-      n[u] = base + u * pass + site0;
-      lc[u] = rc[u] = 0;
-      if (n[u] < op.nsites)
+      /* the host layer pads tip buffers by 16 bytes: the last group may read past nsites */
+      lc8 = *reinterpret_cast<const unsigned long long *>(op.left_tip + first);
+      rc8 = *reinterpret_cast<const unsigned long long *>(op.right_tip + first);
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < TT_GROUP; ++j)
       {
-        const unsigned int site = op.parent_id_site ? op.parent_id_site[n[u]] : n[u];
-        lc[u] = op.left_tip[op.left_site_id ? op.left_site_id[site] : site];
-        rc[u] = op.right_tip[op.right_site_id ? op.right_site_id[site] : site];
+        const unsigned int n = first + j;
+        if (n < op.nsites)
+        {
+          const unsigned int site = op.parent_id_site ? op.parent_id_site[n] : n;
+          lc8 |= (unsigned long long)op.left_tip[op.left_site_id ? op.left_site_id[site] : site] << (8 * j);
+          rc8 |= (unsigned long long)op.right_tip[op.right_site_id ? op.right_site_id[site] : site] << (8 * j);
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int j = 0; j < TT_GROUP; ++j)
     {
-      if (n[u] >= op.nsites) continue;
-      const dbl4 a = lds_dbl4(tl + (lc[u] * R + rate) * 4);
-      const dbl4 b = lds_dbl4(tr + (rc[u] * R + rate) * 4);
-      const dbl4 v = {a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w};
-      st256(op.parent_clv + ((size_t)n[u] * R + rate) * 4, v);
-      if (op.parent_scaler)
-      {
-        if (per_rate)
-          op.parent_scaler[(size_t)n[u] * R + rate] = 0;
-        else if (rate == 0)
-          op.parent_scaler[n[u]] = 0;
-      }
+      const unsigned int n = first + j;
+      if (n >= op.nsites) break;
+      const unsigned int lc = (unsigned int)(lc8 >> (8 * j)) & 0xFFu, rc = (unsigned int)(rc8 >> (8 * j)) & 0xFFu;
+      const double * pl = tl + (lc * R + rate) * 4;
+      const double * pr = tr + (rc * R + rate) * 4;
+      const double2 a0 = *reinterpret_cast<const double2 *>(pl + 2 * swap);
+      const double2 b0 = *reinterpret_cast<const double2 *>(pr + 2 * swap);
+      const double2 a1 = *reinterpret_cast<const double2 *>(pl + 2 * (swap ^ 1));
+      const double2 b1 = *reinterpret_cast<const double2 *>(pr + 2 * (swap ^ 1));
+      const double p0 = a0.x * b0.x, p1 = a0.y * b0.y, q0 = a1.x * b1.x, q1 = a1.y * b1.y;
+      const dbl4 v = swap ? dbl4{q0, q1, p0, p1} : dbl4{p0, p1, q0, q1};
+      st256(op.parent_clv + ((size_t)n * R + rate) * 4, v);
+      if (op.parent_scaler && per_rate) op.parent_scaler[(size_t)n * R + rate] = 0;
     }
+    if (op.parent_scaler && !per_rate && rate == 0)
+    {
+      if (first + TT_GROUP <= op.nsites)
+      {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(op.parent_scaler + first) = z;
+        *reinterpret_cast<uint4 *>(op.parent_scaler + first + 4) = z;
+      }
+      else
+        for (unsigned int n = first; n < op.nsites; ++n) op.parent_scaler[n] = 0;
+    }
+  }
+  }
+}
+
+/* ------------------------------------------------------------------------ *
+ *  Streaming variants for contiguous (non-repeats) CLVs: the child tiles,    *
+ *  their scalers and the tip codes are brought into a shared-memory ring by  *
+ *  1-D bulk async copies (cp.async.bulk, the non-tensor TMA path; UBLKCP in  *
+ *  SASS) that complete on an mbarrier.  Bytes in flight are then set by the  *
+ *  ring depth (NSTAGE x ~36 KB per CTA), not by registers or warp count, and *
+ *  the copy engine keeps issuing while every warp is busy with arithmetic.   *
+ * ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ unsigned int smem_u32(const void * p)
+{
+  return (unsigned int)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long * bar, unsigned int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long * bar, unsigned int bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long * bar, unsigned int parity)
+{
+  unsigned int ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void * dst, const void * src, unsigned int bytes, unsigned long long * bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+/* ITEMS = (site, rate) blocks per thread and tile */
+template <int LOG2R, int ITEMS>
+struct StreamLayout
+{
+  static constexpr int R = 1 << LOG2R;
+  static constexpr int TILE = (DNA_THREADS * ITEMS) >> LOG2R; /* sites per tile */
+  static constexpr int CLV_BYTES = TILE * R * 32;
+  static constexpr int SC_BYTES = TILE * R * 4; /* per-rate worst case */
+  static constexpr int OFF_L = 0;
+  static constexpr int OFF_R = CLV_BYTES;
+  static constexpr int OFF_LSC = 2 * CLV_BYTES;
+  static constexpr int OFF_RSC = OFF_LSC + SC_BYTES;
+  static constexpr int OFF_CODE = OFF_RSC + SC_BYTES;
+  static constexpr int STAGE_BYTES = (OFF_CODE + TILE + 127) & ~127;
+};
+
+/* thread 0: queue the copies of tile `t` of `op` into ring slot `slot` */
+template <int LOG2R, int KIND, int ITEMS>
+__device__ __forceinline__ void stream_issue(const plf_op_t & op, unsigned int t, unsigned char * slot,
+                                             unsigned long long * bar, int per_rate)
+{
+  typedef StreamLayout<LOG2R, ITEMS> Ly;
+  const unsigned int first = t * Ly::TILE;
+  const unsigned int n = min((unsigned int)Ly::TILE, op.nsites - first);
+  const unsigned int clv_bytes = n * Ly::R * 32;
+  /* 4-byte scalers / 1-byte codes: sizes rounded up to the 16-byte copy
+   * granule; the host layer pads those allocations by 16 bytes */
+  const unsigned int sc_bytes = ((per_rate ? n * Ly::R : n) * 4 + 15) & ~15u;
+  const size_t sc_first = per_rate ? (size_t)first * Ly::R : first;
+  unsigned int total = clv_bytes;
+  if (KIND == PLF_OP_II) total += clv_bytes + (op.left_scaler && op.parent_scaler ? sc_bytes : 0);
+  if (KIND == PLF_OP_TI) total += (n + 15) & ~15u;
+  if (op.right_scaler && op.parent_scaler) total += sc_bytes;
+  mbar_expect_tx(bar, total);
+  if (KIND == PLF_OP_II)
+  {
+    bulk_g2s(slot + Ly::OFF_L, op.left_clv + (size_t)first * Ly::R * 4, clv_bytes, bar);
+    if (op.left_scaler && op.parent_scaler) bulk_g2s(slot + Ly::OFF_LSC, op.left_scaler + sc_first, sc_bytes, bar);
+  }
+  else
+    bulk_g2s(slot + Ly::OFF_CODE, op.left_tip + first, (n + 15) & ~15u, bar);
+  bulk_g2s(slot + Ly::OFF_R, op.right_clv + (size_t)first * Ly::R * 4, clv_bytes, bar);
+  if (op.right_scaler && op.parent_scaler) bulk_g2s(slot + Ly::OFF_RSC, op.right_scaler + sc_first, sc_bytes, bar);
+}
+
+template <int LOG2R, int KIND, int NSTAGE, int ITEMS>
+__global__ void __launch_bounds__(DNA_THREADS)
+k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
+{
+  typedef StreamLayout<LOG2R, ITEMS> Ly;
+  constexpr int R = Ly::R;
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(8) unsigned long long full[NSTAGE];
+  __shared__ __align__(16) double tl[KIND == PLF_OP_TI ? 64 * R : 2];
+
+  const plf_op_t op = ops[blockIdx.y];
+  const unsigned int ntiles = (op.nsites + Ly::TILE - 1) / Ly::TILE;
+  const int rate = threadIdx.x & (R - 1);
+
+  if (threadIdx.x == 0)
+  {
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    unsigned int t = blockIdx.x;
+    for (int s = 0; s < NSTAGE && t < ntiles; ++s, t += gridDim.x)
+      stream_issue<LOG2R, KIND, ITEMS>(op, t, ring + (size_t)s * Ly::STAGE_BYTES, &full[s], per_rate);
+  }
+
+  double Lm[KIND == PLF_OP_II ? 16 : 1], Rm[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+  {
+    if (KIND == PLF_OP_II) Lm[i] = op.left_matrix[rate * 16 + i];
+    Rm[i] = op.right_matrix[rate * 16 + i];
+  }
+  if (KIND == PLF_OP_TI)
+  {
+    build_tip_table(tl, op.left_matrix, R);
+    __syncthreads();
+  }
+
+  unsigned int it = 0;
+  for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it)
+  {
+    const int s = it % NSTAGE;
+    const unsigned int parity = (it / NSTAGE) & 1u;
+    unsigned char * slot = ring + (size_t)s * Ly::STAGE_BYTES;
+    while (!mbar_try_wait(&full[s], parity)) {}
+
+    const unsigned int first = t * Ly::TILE;
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u)
+    {
+      const unsigned int item = threadIdx.x + u * DNA_THREADS; /* (site in tile, rate) */
+      const unsigned int ls = item >> LOG2R;
+      SiteRef sr;
+      sr.n = first + ls;
+      sr.lid = sr.rid = sr.n;
+      sr.active = sr.n < op.nsites;
+      const dbl4 r = lds_dbl4(reinterpret_cast<const double *>(slot + Ly::OFF_R) + (size_t)item * 4);
+      dbl4 a;
+      unsigned int sc = 0;
+      if (KIND == PLF_OP_II)
+      {
+        const dbl4 l = lds_dbl4(reinterpret_cast<const double *>(slot + Ly::OFF_L) + (size_t)item * 4);
+        a.x = dot4_pairwise(Lm + 0, l);
+        a.y = dot4_pairwise(Lm + 4, l);
+        a.z = dot4_pairwise(Lm + 8, l);
+        a.w = dot4_pairwise(Lm + 12, l);
+      }
+      else
+      {
+        const unsigned int code = sr.active ? slot[Ly::OFF_CODE + ls] : 0u;
+        a = lds_dbl4(tl + (code * R + rate) * 4);
+      }
+      if (op.parent_scaler && sr.active && (per_rate || rate == 0))
+      {
+        const unsigned int k = per_rate ? item : ls;
+        if (KIND == PLF_OP_II && op.left_scaler) sc += reinterpret_cast<const unsigned int *>(slot + Ly::OFF_LSC)[k];
+        if (op.right_scaler) sc += reinterpret_cast<const unsigned int *>(slot + Ly::OFF_RSC)[k];
+      }
+      dbl4 v;
+      v.x = a.x * dot4_pairwise(Rm + 0, r);
+      v.y = a.y * dot4_pairwise(Rm + 4, r);
+      v.z = a.z * dot4_pairwise(Rm + 8, r);
+      v.w = a.w * dot4_pairwise(Rm + 12, r);
+      if (!sr.active) v = dbl4{1.0, 1.0, 1.0, 1.0}; /* stale ring bytes must not reach the scaling vote */
+      scale_and_store<LOG2R>(op, sr, rate, per_rate, sc, v);
+    }
+    __syncthreads(); /* every warp is done with this slot */
+    const unsigned int tn = t + (unsigned int)NSTAGE * gridDim.x;
+    if (threadIdx.x == 0 && tn < ntiles) stream_issue<LOG2R, KIND, ITEMS>(op, tn, slot, &full[s], per_rate);
   }
 }
 
@@ -278,15 +502,91 @@ static dna_kernel_t pick_kernel(unsigned int kind)
 
 static const int DNA_UNROLL = 4;
 
+template <int LOG2R, int NSTAGE, int ITEMS>
+static dna_kernel_t pick_stream_kernel(unsigned int kind)
+{
+  if (kind == PLF_OP_II) return k_clv_dna_stream<LOG2R, PLF_OP_II, NSTAGE, ITEMS>;
+  return k_clv_dna_stream<LOG2R, PLF_OP_TI, NSTAGE, ITEMS>;
+}
+
+template <int LOG2R, int ITEMS>
+static dna_kernel_t pick_stream_kernel_stages(unsigned int kind, int nstage, size_t * smem, unsigned int * tile)
+{
+  *smem = (size_t)nstage * StreamLayout<LOG2R, ITEMS>::STAGE_BYTES;
+  *tile = StreamLayout<LOG2R, ITEMS>::TILE;
+  switch (nstage)
+  {
+    case 2: return pick_stream_kernel<LOG2R, 2, ITEMS>(kind);
+    case 3: return pick_stream_kernel<LOG2R, 3, ITEMS>(kind);
+    case 4: return pick_stream_kernel<LOG2R, 4, ITEMS>(kind);
+    default: return pick_stream_kernel<LOG2R, 6, ITEMS>(kind);
+  }
+}
+
+template <int LOG2R>
+static dna_kernel_t pick_stream_kernel_items(unsigned int kind, int nstage, int items, size_t * smem, unsigned int * tile)
+{
+  if (items == 2) return pick_stream_kernel_stages<LOG2R, 2>(kind, nstage, smem, tile);
+  if (items == 1) return pick_stream_kernel_stages<LOG2R, 1>(kind, nstage, smem, tile);
+  return pick_stream_kernel_stages<LOG2R, 4>(kind, nstage, smem, tile);
+}
+
+static int env_int(const char * name, int dflt)
+{
+  const char * v = getenv(name);
+  return (v && v[0]) ? atoi(v) : dflt;
+}
+
 /* launch one group of same-kind DNA ops (rate_cats a power of two <= 32) as a
  * single persistent wave: gridDim.y = ops, gridDim.x = CTAs striding over the
- * sites of each op */
+ * sites of each op.  `contiguous`: no op of the group gathers through repeat
+ * identifiers, so the bulk-copy streaming kernels apply. */
 int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nops, unsigned int kind,
-                         unsigned int rate_cats, int per_rate, unsigned int max_sites)
+                         unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous)
 {
-  dna_kernel_t k = nullptr;
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
+  if (ctx->dna_stream < 0)
+  {
+    ctx->dna_stream = env_int("PLF_DNA_STREAM", 1);
+    ctx->dna_stages = env_int("PLF_DNA_STAGES", 6);
+    ctx->dna_items = env_int("PLF_DNA_ITEMS", 2);
+    if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
+  }
+
+  if (contiguous && ctx->dna_stream && kind != PLF_OP_TT)
+  {
+    dna_kernel_t k = nullptr;
+    size_t smem = 0;
+    unsigned int tile = 0;
+    switch (log2r)
+    {
+      case 0: k = pick_stream_kernel_items<0>(kind, ctx->dna_stages, ctx->dna_items, &smem, &tile); break;
+      case 1: k = pick_stream_kernel_items<1>(kind, ctx->dna_stages, ctx->dna_items, &smem, &tile); break;
+      case 2: k = pick_stream_kernel_items<2>(kind, ctx->dna_stages, ctx->dna_items, &smem, &tile); break;
+      case 3: k = pick_stream_kernel_items<3>(kind, ctx->dna_stages, ctx->dna_items, &smem, &tile); break;
+      case 4: k = pick_stream_kernel_items<4>(kind, ctx->dna_stages, ctx->dna_items, &smem, &tile); break;
+      default: k = pick_stream_kernel_items<5>(kind, ctx->dna_stages, ctx->dna_items, &smem, &tile); break;
+    }
+    int & occ = ctx->dna_stream_occupancy[kind == PLF_OP_II ? 0 : 1][log2r];
+    if (!occ)
+    {
+      PLF_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, DNA_THREADS, smem));
+      if (occ < 1) occ = 1;
+    }
+    const unsigned long long ntiles = ((unsigned long long)max_sites + tile - 1) / tile;
+    unsigned long long bx = ((unsigned long long)ctx->sm_count * occ) / nops;
+    if (bx < 1) bx = 1;
+    if (bx > ntiles) bx = ntiles;
+    dim3 grid((unsigned int)bx, nops);
+    k<<<grid, DNA_THREADS, smem, ctx->stream>>>(d_ops, per_rate);
+    plf_count_launch();
+    PLF_CHECK(ctx, cudaGetLastError());
+    return 1;
+  }
+
+  dna_kernel_t k = nullptr;
   switch (log2r)
   {
     case 0: k = pick_kernel<0>(kind); break;
@@ -303,13 +603,25 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     if (occ < 1) occ = 1;
   }
   const unsigned long long lanes = (unsigned long long)max_sites << log2r;
-  unsigned long long need = (lanes + (unsigned long long)DNA_THREADS * DNA_UNROLL - 1) / ((unsigned long long)DNA_THREADS * DNA_UNROLL);
+  const unsigned int per_thread = (kind == PLF_OP_TT) ? TT_GROUP : DNA_UNROLL;
+  unsigned long long need = (lanes + (unsigned long long)DNA_THREADS * per_thread - 1) / ((unsigned long long)DNA_THREADS * per_thread);
   unsigned long long bx = ((unsigned long long)ctx->sm_count * occ) / nops;
   if (bx < 1) bx = 1;
   if (bx > need) bx = need;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned int)bx, nops);
-  k<<<grid, DNA_THREADS, 0, ctx->stream>>>(d_ops, per_rate);
+  int arg = per_rate;
+  if (kind == PLF_OP_TT)
+  {
+    arg = (per_rate & 1) | (int)(nops << 1);
+    if (env_int("PLF_TT_SEQ", 1))
+    {
+      unsigned long long all = (unsigned long long)ctx->sm_count * occ;
+      if (all > need) all = need;
+      grid = dim3((unsigned int)(all < 1 ? 1 : all), 1);
+    }
+  }
+  k<<<grid, DNA_THREADS, 0, ctx->stream>>>(d_ops, arg);
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;

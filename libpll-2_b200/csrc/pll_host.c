@@ -38,6 +38,9 @@ static __thread int tls_device = -1;
 #define PLL_CUDA_MAGIC 0xB200C0DEu
 #define EMPTY_ELEMENT 0xFFFFFFFFu
 #define MAX_SUMTABLES 8
+/* the streaming kernels fetch scalers and tip codes with 16-byte bulk copies:
+ * the last copy of a buffer may read up to 15 bytes past its logical end */
+#define BULK_PAD 16
 
 typedef struct sumtable_slot
 {
@@ -461,7 +464,7 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     for (i = 0; i < scale_buffers; ++i)
     {
       const size_t m = (size_t)sites * (cp->shape.per_rate_scalers ? rate_cats : 1);
-      NEED(p->scale_buffer[i] = (unsigned int *)plf_alloc(cp->ctx, m * sizeof(unsigned int), 1));
+      NEED(p->scale_buffer[i] = (unsigned int *)plf_alloc(cp->ctx, m * sizeof(unsigned int) + BULK_PAD, 1));
       cp->scaler_entries[i] = (unsigned int)m;
     }
   }
@@ -645,7 +648,7 @@ PLL_EXPORT void pll_default_reallocate_repeats(pll_partition_t * partition, unsi
     size_t n = sites_to_alloc;
     if (partition->attributes & PLL_ATTRIB_RATE_SCALERS) n *= partition->rate_cats;
     plf_free(cp->ctx, partition->scale_buffer[scaler_index]);
-    partition->scale_buffer[scaler_index] = (unsigned int *)plf_alloc(cp->ctx, n * sizeof(unsigned int), 1);
+    partition->scale_buffer[scaler_index] = (unsigned int *)plf_alloc(cp->ctx, n * sizeof(unsigned int) + BULK_PAD, 1);
     cp->scaler_entries[scaler_index] = (unsigned int)n;
   }
   free(r->pernode_id_site[parent]);
@@ -806,7 +809,7 @@ static int charmap_create(cuda_partition_t * cp, const pll_state_t * usermap)
   for (i = 0; i < p->tips; ++i)
   {
     p->tipchars[i] = (unsigned char *)malloc(p->sites);
-    cp->d_tipchars[i] = (unsigned char *)plf_alloc(cp->ctx, p->sites, 1);
+    cp->d_tipchars[i] = (unsigned char *)plf_alloc(cp->ctx, (size_t)p->sites + BULK_PAD, 1);
     if (!p->tipchars[i] || !cp->d_tipchars[i])
     {
       set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate space for storing tip characters.%s", NULL);
