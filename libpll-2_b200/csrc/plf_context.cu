@@ -57,6 +57,10 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
   ctx->device = device;
   ctx->managed = managed;
   ctx->dna_stream = -1;
+  {
+    const char * v = getenv("PLF_AA_FAST");
+    ctx->aa_fast = !(v && v[0] == '0');
+  }
   cudaError_t e = cudaSetDevice(device);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);

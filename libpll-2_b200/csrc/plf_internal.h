@@ -21,6 +21,9 @@ struct plf_ctx
   int dna_stream_occupancy[2][6];
   int dna_stream;          /* -1 = read PLF_DNA_STREAM / PLF_DNA_STAGES on first use */
   int dna_stages;
+  size_t aa_smem_set[2];
+  int aa_occupancy[2];
+  int aa_fast;             /* PLF_AA_FAST=0 forces the generic 20-state kernel */
   int dna_items;
   cudaStream_t stream;
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
@@ -36,6 +39,9 @@ void plf_set_error(plf_ctx * ctx, const char * fmt, ...);
 void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes);
 void plf_count_launch(void);
 struct plf_op;
+int plf_launch_aa_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
+                        unsigned int rate_cats, int per_rate, unsigned int max_sites,
+                        const unsigned long long * d_tipmap, unsigned int maxstates);
 int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
                          unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous);
 

@@ -479,35 +479,62 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
     }
     else
     {
-      const int threads = 128;
-      const unsigned long long work = (unsigned long long)max_sites * L;
-      unsigned int bx = (unsigned int)((work + threads - 1) / threads);
-      unsigned int cap = (unsigned int)(ctx->sm_count * 4 * 2) / (b - a);
-      if (cap < 1) cap = 1;
-      if (bx > cap) bx = cap;
-      dim3 grid(bx, b - a);
-      if (sh->states == 20)
+      /* runs of same-kind ops: 20-state ii / ti runs go to the register-tiled
+       * kernels of plf_partials_aa.cu, everything else to the generic kernel */
+      for (unsigned int i = a; i < b;)
       {
-        size_t smem = (size_t)2 * R * 400 * sizeof(double);
-        if (any_tip) smem += (size_t)2 * maxstates * R * 20 * sizeof(double);
-        if (smem > ctx->smem_optin)
+        unsigned int j = i, run_sites = 0;
+        int run_tip = (h_ops[i].kind != PLF_OP_II);
+        while (j < b && h_ops[j].kind == h_ops[i].kind)
         {
-          plf_set_error(ctx, "protein tip tables need %zu B of shared memory (> %zu)", smem, ctx->smem_optin);
-          return 0;
+          if (h_ops[j].nsites > run_sites) run_sites = h_ops[j].nsites;
+          ++j;
         }
-        if (smem > ctx->gen20_smem_set)
+        int done = 0;
+        if (run_sites && sh->states == 20 && h_ops[i].kind != PLF_OP_TT && ctx->aa_fast)
         {
-          PLF_CHECK(ctx, cudaFuncSetAttribute(k_partials_gen<20>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
-          ctx->gen20_smem_set = smem;
+          const int rc = plf_launch_aa_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
+                                             sh->per_rate_scalers, run_sites, d_tipmap, maxstates);
+          if (rc == 0) return 0;
+          done = (rc == 1);
         }
-        k_partials_gen<20><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers, 20, 20,
-                                                                  d_tipmap, (int)maxstates, L);
+        if (run_sites && !done)
+        {
+          const int threads = 128;
+          const unsigned long long work = (unsigned long long)run_sites * L;
+          unsigned int bx = (unsigned int)((work + threads - 1) / threads);
+          unsigned int cap = (unsigned int)(ctx->sm_count * 4 * 2) / (j - i);
+          if (cap < 1) cap = 1;
+          if (bx > cap) bx = cap;
+          dim3 grid(bx, j - i);
+          if (sh->states == 20)
+          {
+            size_t smem = (size_t)2 * R * 400 * sizeof(double);
+            if (run_tip) smem += (size_t)2 * maxstates * R * 20 * sizeof(double);
+            if (smem > ctx->smem_optin)
+            {
+              plf_set_error(ctx, "protein tip tables need %zu B of shared memory (> %zu)", smem, ctx->smem_optin);
+              return 0;
+            }
+            if (smem > ctx->gen20_smem_set)
+            {
+              PLF_CHECK(ctx, cudaFuncSetAttribute(k_partials_gen<20>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)smem));
+              ctx->gen20_smem_set = smem;
+            }
+            k_partials_gen<20><<<grid, threads, smem, ctx->stream>>>(d_ops + i, R, sh->per_rate_scalers, 20, 20,
+                                                                      d_tipmap, (int)maxstates, L);
+          }
+          else
+            k_partials_gen<0><<<grid, threads, 0, ctx->stream>>>(d_ops + i, R, sh->per_rate_scalers,
+                                                                 (int)sh->states, (int)sh->states_padded, d_tipmap,
+                                                                 (int)maxstates, L);
+          plf_count_launch();
+          PLF_CHECK(ctx, cudaGetLastError());
+        }
+        i = j;
       }
-      else
-        k_partials_gen<0><<<grid, threads, 0, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers,
-                                                             (int)sh->states, (int)sh->states_padded, d_tipmap,
-                                                             (int)maxstates, L);
+      continue;
     }
     plf_count_launch();
     PLF_CHECK(ctx, cudaGetLastError());

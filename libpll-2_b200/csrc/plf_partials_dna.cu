@@ -250,15 +250,26 @@ k_clv_dna_tt(const plf_op_t * __restrict__ ops, int per_rate_and_nops)
   const bool direct = !(op.parent_id_site || op.left_site_id || op.right_site_id);
   const int swap = (R <= 4) ? ((threadIdx.x >> LOG2R) & 1) : 0; /* odd group of the quarter-warp */
 
+  /* the codes of the NEXT group are fetched before the current one is
+   * processed: the only load latency on this path is hidden behind 8 stores */
+  unsigned long long lc8_next = 0, rc8_next = 0;
+  if (direct && grp0 < ngroups)
+  {
+    /* the host layer pads tip buffers by 16 bytes: the last group may read past nsites */
+    lc8_next = *reinterpret_cast<const unsigned long long *>(op.left_tip + (size_t)grp0 * TT_GROUP);
+    rc8_next = *reinterpret_cast<const unsigned long long *>(op.right_tip + (size_t)grp0 * TT_GROUP);
+  }
   for (unsigned int g = grp0; g < ngroups; g += pass)
   {
     const unsigned int first = g * TT_GROUP;
-    unsigned long long lc8 = 0, rc8 = 0;
+    unsigned long long lc8 = lc8_next, rc8 = rc8_next;
     if (direct)
     {
-      /* the host layer pads tip buffers by 16 bytes: the last group may read past nsites */
-      lc8 = *reinterpret_cast<const unsigned long long *>(op.left_tip + first);
-      rc8 = *reinterpret_cast<const unsigned long long *>(op.right_tip + first);
+      if (g + pass < ngroups)
+      {
+        lc8_next = *reinterpret_cast<const unsigned long long *>(op.left_tip + (size_t)(g + pass) * TT_GROUP);
+        rc8_next = *reinterpret_cast<const unsigned long long *>(op.right_tip + (size_t)(g + pass) * TT_GROUP);
+      }
     }
     else
     {
