@@ -23,6 +23,7 @@ struct plf_ctx
   int dna_stages;
   size_t aa_smem_set[2];
   int aa_occupancy[2];
+  int aa_spt;              /* PLF_AA_SPT: sites per thread of the 20-state kernels (1 or 2) */
   int aa_fast;             /* PLF_AA_FAST=0 forces the generic 20-state kernel */
   int dna_items;
   cudaStream_t stream;
