@@ -164,6 +164,24 @@ int plf_repeats_ids(plf_ctx_t * ctx, unsigned int sites,
                     unsigned int * d_id_site_parent, unsigned int * d_lookup,
                     unsigned int * h_ids);
 
+/* the same for a batch of independent parents (one traversal level): job j
+ * uses the lookup entries [lookup_offset, lookup_offset + ids_left*ids_right)
+ * of the pool; id_site_parent needs room for min(sites, ids_left*ids_right)
+ * entries.  One host synchronisation per batch; class counts to h_ids[]. */
+typedef struct plf_rep_job
+{
+  const unsigned int * site_id_left;
+  const unsigned int * site_id_right; /* NULL: the key is the left id itself */
+  unsigned int * site_id_parent;
+  unsigned int * id_site_parent;
+  unsigned int ids_left;
+  unsigned int lookup_offset;
+} plf_rep_job_t;
+size_t plf_repeats_batch_workspace(unsigned int sites, unsigned int njobs);
+int plf_repeats_ids_batch(plf_ctx_t * ctx, unsigned int sites,
+                          const plf_rep_job_t * h_jobs, unsigned int njobs,
+                          unsigned int * d_lookup_pool, unsigned int * h_ids);
+
 /* tip CLV from a sequence of state characters: entry n (site id_site[n] when
  * repeats compress the tip) gets bit j of map[seq[site]] replicated over rates
  * (src/pll.c:959-1024) */

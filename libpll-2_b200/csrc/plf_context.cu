@@ -75,6 +75,24 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
     return 0;
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess && !managed)
+  {
+    /* stream-ordered pool private to this context: site-repeat reallocation
+     * (CLVs, scalers resized to the class count) never synchronises and freed
+     * blocks are recycled without a trip to the driver */
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    e = cudaMemPoolCreate(&ctx->pool, &props);
+    if (e == cudaSuccess)
+    {
+      unsigned long long keep = ~0ull;
+      e = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_result, 4 * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_result, 4 * sizeof(double));
   if (e != cudaSuccess)
@@ -106,6 +124,7 @@ extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
   cudaFree(ctx->ws_partial.ptr);
   cudaFree(ctx->d_result);
   cudaFreeHost(ctx->h_result);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   cudaStreamDestroy(ctx->stream);
   free(ctx);
 }
@@ -144,9 +163,10 @@ extern "C" void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero)
     if (e == cudaSuccess) cudaMemPrefetchAsync(p, bytes, ctx->device, ctx->stream);
   }
   else
-    e = cudaMalloc(&p, bytes);
+    e = cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream);
   if (e != cudaSuccess)
   {
+    cudaGetLastError();
     plf_set_error(ctx, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     return NULL;
   }
@@ -158,6 +178,12 @@ extern "C" void plf_free(plf_ctx_t * ctx, void * p)
 {
   if (!p) return;
   cudaSetDevice(ctx->device);
+  if (ctx->pool)
+  {
+    /* stream-ordered: every kernel queued so far that uses `p` finishes first */
+    cudaFreeAsync(p, ctx->stream);
+    return;
+  }
   cudaStreamSynchronize(ctx->stream);
   cudaFree(p);
 }

@@ -27,6 +27,7 @@ struct plf_ctx
   int aa_fast;             /* PLF_AA_FAST=0 forces the generic 20-state kernel */
   int dna_items;
   cudaStream_t stream;
+  cudaMemPool_t pool;    /* stream-ordered allocator behind plf_alloc/plf_free (NULL in managed mode) */
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
   plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
   plf_ws ws_partial;  /* per-block partial sums of the reductions              */

@@ -101,19 +101,30 @@ extern "C" int plf_invariant_sites(plf_ctx_t * ctx, const plf_shape_t * sh, unsi
 #define SCAN_TILE 1024
 /* idr == NULL: the key is idl[s] itself (tip class codes) */
 #define REP_KEY(s) (idr ? idl[(s)] + idr[(s)] * ids_left : idl[(s)])
+/* blockIdx.y selects the job: independent nodes of one traversal level are
+ * numbered by the same six launches, each in its own slice of the lookup pool */
+#define REP_JOB                                                     \
+  const plf_rep_job_t jb = jobs[blockIdx.y];                        \
+  const unsigned int * __restrict__ idl = jb.site_id_left;          \
+  const unsigned int * __restrict__ idr = jb.site_id_right;         \
+  const unsigned int ids_left = jb.ids_left;                        \
+  unsigned int * __restrict__ lookup = lookup_pool + jb.lookup_offset
 
-__global__ void k_rep_min(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
-                          unsigned int ids_left, unsigned int sites, unsigned int * __restrict__ lookup)
+__global__ void k_rep_min(const plf_rep_job_t * __restrict__ jobs, unsigned int sites,
+                          unsigned int * __restrict__ lookup_pool)
 {
+  REP_JOB;
   for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
     atomicMin(&lookup[REP_KEY(s)], s);
 }
 
 /* per-tile count of first occurrences */
-__global__ void k_rep_count(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
-                            unsigned int ids_left, unsigned int sites, const unsigned int * __restrict__ lookup,
-                            unsigned int * __restrict__ tile_count)
+__global__ void k_rep_count(const plf_rep_job_t * __restrict__ jobs, unsigned int sites,
+                            unsigned int * __restrict__ lookup_pool, unsigned int * __restrict__ tile_count_all,
+                            unsigned int ntiles)
 {
+  REP_JOB;
+  unsigned int * tile_count = tile_count_all + (size_t)blockIdx.y * ntiles;
   __shared__ unsigned int cnt;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
@@ -126,10 +137,11 @@ __global__ void k_rep_count(const unsigned int * __restrict__ idl, const unsigne
   if (threadIdx.x == 0) tile_count[blockIdx.x] = cnt;
 }
 
-/* exclusive scan of tile counts by one block; total to *total */
-__global__ void k_rep_scan_tiles(unsigned int * __restrict__ tile_count, unsigned int ntiles,
-                                 unsigned int * __restrict__ total)
+/* exclusive scan of one job's tile counts by one block; total to totals[job] */
+__global__ void k_rep_scan_tiles(unsigned int * __restrict__ tile_count_all, unsigned int ntiles,
+                                 unsigned int * __restrict__ totals)
 {
+  unsigned int * tile_count = tile_count_all + (size_t)blockIdx.y * ntiles;
   __shared__ unsigned int buf[1024];
   __shared__ unsigned int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -152,16 +164,18 @@ __global__ void k_rep_scan_tiles(unsigned int * __restrict__ tile_count, unsigne
     if (threadIdx.x == 1023) carry += buf[1023];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry;
+  if (threadIdx.x == 0) totals[blockIdx.y] = carry;
 }
 
-/* rank of each first occurrence; stored in-place of the lookup entry's class:
- * rank_of_site[s] for first occurrences, and id_site[rank] = s */
-__global__ void k_rep_rank(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
-                           unsigned int ids_left, unsigned int sites, const unsigned int * __restrict__ lookup,
-                           const unsigned int * __restrict__ tile_offset, unsigned int * __restrict__ rank_of_site,
-                           unsigned int * __restrict__ id_site)
+/* rank of each first occurrence: rank_of_site[s] for first occurrences, and
+ * id_site[rank] = s */
+__global__ void k_rep_rank(const plf_rep_job_t * __restrict__ jobs, unsigned int sites,
+                           unsigned int * __restrict__ lookup_pool, const unsigned int * __restrict__ tile_count_all,
+                           unsigned int ntiles, unsigned int * __restrict__ rank_all)
 {
+  REP_JOB;
+  const unsigned int * tile_offset = tile_count_all + (size_t)blockIdx.y * ntiles;
+  unsigned int * rank_of_site = rank_all + (size_t)blockIdx.y * sites;
   __shared__ unsigned int buf[SCAN_TILE];
   const unsigned int s = blockIdx.x * SCAN_TILE + threadIdx.x;
   const unsigned int f = (s < sites) ? (lookup[REP_KEY(s)] == s) : 0u;
@@ -178,50 +192,84 @@ __global__ void k_rep_rank(const unsigned int * __restrict__ idl, const unsigned
   {
     const unsigned int r = tile_offset[blockIdx.x] + buf[threadIdx.x] - 1;
     rank_of_site[s] = r;
-    id_site[r] = s;
+    jb.id_site_parent[r] = s;
   }
 }
 
-__global__ void k_rep_assign(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
-                             unsigned int ids_left, unsigned int sites, const unsigned int * __restrict__ lookup,
-                             const unsigned int * __restrict__ rank_of_site, unsigned int * __restrict__ site_id)
+/* site_id[s] = rank of the class of s; the lookup entries go back to EMPTY */
+__global__ void k_rep_assign(const plf_rep_job_t * __restrict__ jobs, unsigned int sites,
+                             unsigned int * __restrict__ lookup_pool, const unsigned int * __restrict__ rank_all)
 {
+  REP_JOB;
+  const unsigned int * rank_of_site = rank_all + (size_t)blockIdx.y * sites;
   for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
-    site_id[s] = rank_of_site[lookup[REP_KEY(s)]];
+    jb.site_id_parent[s] = rank_of_site[lookup[REP_KEY(s)]];
 }
 
-__global__ void k_rep_clean(const unsigned int * __restrict__ idl, const unsigned int * __restrict__ idr,
-                            unsigned int ids_left, unsigned int sites, unsigned int * __restrict__ lookup)
+__global__ void k_rep_clean(const plf_rep_job_t * __restrict__ jobs, unsigned int sites,
+                            unsigned int * __restrict__ lookup_pool)
 {
+  REP_JOB;
   for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
     lookup[REP_KEY(s)] = 0xFFFFFFFFu;
+}
+
+extern "C" size_t plf_repeats_batch_workspace(unsigned int sites, unsigned int njobs)
+{
+  const size_t ntiles = ((size_t)sites + SCAN_TILE - 1) / SCAN_TILE;
+  return (size_t)njobs * (sizeof(plf_rep_job_t) + (ntiles + 1 + sites) * sizeof(unsigned int)) + 64;
+}
+
+/* class identifiers of `njobs` independent parent nodes: six launches and ONE
+ * host synchronisation for the whole batch; class counts to h_ids[njobs] */
+extern "C" int plf_repeats_ids_batch(plf_ctx_t * ctx, unsigned int sites, const plf_rep_job_t * h_jobs,
+                                     unsigned int njobs, unsigned int * d_lookup_pool, unsigned int * h_ids)
+{
+  if (!njobs) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  const unsigned int ntiles = (sites + SCAN_TILE - 1) / SCAN_TILE;
+  /* workspace: jobs [njobs] | totals [njobs] | tile counts [njobs][ntiles] | rank_of_site [njobs][sites] */
+  const size_t jobs_bytes = ((size_t)njobs * sizeof(plf_rep_job_t) + 15) & ~(size_t)15;
+  char * ws = (char *)plf_ws_reserve(ctx, &ctx->ws_partial,
+                                     jobs_bytes + ((size_t)njobs * (1 + (size_t)ntiles + sites)) * sizeof(unsigned int));
+  if (!ws) return 0;
+  plf_rep_job_t * d_jobs = (plf_rep_job_t *)ws;
+  unsigned int * totals = (unsigned int *)(ws + jobs_bytes);
+  unsigned int * tile = totals + njobs;
+  unsigned int * rank = tile + (size_t)njobs * ntiles;
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_jobs, h_jobs, (size_t)njobs * sizeof(plf_rep_job_t), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  unsigned int blocks = (sites + 255) / 256;
+  const unsigned int cap = (unsigned int)ctx->sm_count * 8;
+  const unsigned int share = cap / njobs > 4 ? cap / njobs : 4; /* one wave over the whole batch */
+  if (blocks > share) blocks = share;
+  const dim3 gs(blocks, njobs), gt(ntiles, njobs);
+  k_rep_min<<<gs, 256, 0, ctx->stream>>>(d_jobs, sites, d_lookup_pool);
+  k_rep_count<<<gt, 256, 0, ctx->stream>>>(d_jobs, sites, d_lookup_pool, tile, ntiles);
+  k_rep_scan_tiles<<<dim3(1, njobs), 1024, 0, ctx->stream>>>(tile, ntiles, totals);
+  k_rep_rank<<<gt, SCAN_TILE, 0, ctx->stream>>>(d_jobs, sites, d_lookup_pool, tile, ntiles, rank);
+  k_rep_assign<<<gs, 256, 0, ctx->stream>>>(d_jobs, sites, d_lookup_pool, rank);
+  k_rep_clean<<<gs, 256, 0, ctx->stream>>>(d_jobs, sites, d_lookup_pool);
+  for (int i = 0; i < 6; ++i) plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  PLF_CHECK(ctx, cudaMemcpyAsync(h_ids, totals, (size_t)njobs * sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
 }
 
 extern "C" int plf_repeats_ids(plf_ctx_t * ctx, unsigned int sites, const unsigned int * d_idl,
                                unsigned int ids_left, const unsigned int * d_idr, unsigned int * d_site_id,
                                unsigned int * d_id_site, unsigned int * d_lookup, unsigned int * h_ids)
 {
-  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
-  const unsigned int ntiles = (sites + SCAN_TILE - 1) / SCAN_TILE;
-  /* workspace: tile counts [ntiles] + total [1] + rank_of_site [sites] */
-  unsigned int * ws = (unsigned int *)plf_ws_reserve(ctx, &ctx->ws_partial,
-                                                     ((size_t)ntiles + 1 + sites) * sizeof(unsigned int));
-  if (!ws) return 0;
-  unsigned int * tile = ws, * total = ws + ntiles, * rank = ws + ntiles + 1;
-  unsigned int blocks = (sites + 255) / 256;
-  if (blocks > (unsigned int)ctx->sm_count * 8) blocks = (unsigned int)ctx->sm_count * 8;
-  k_rep_min<<<blocks, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup);
-  k_rep_count<<<ntiles, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup, tile);
-  k_rep_scan_tiles<<<1, 1024, 0, ctx->stream>>>(tile, ntiles, total);
-  k_rep_rank<<<ntiles, SCAN_TILE, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup, tile, rank, d_id_site);
-  k_rep_assign<<<blocks, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup, rank, d_site_id);
-  k_rep_clean<<<blocks, 256, 0, ctx->stream>>>(d_idl, d_idr, ids_left, sites, d_lookup);
-  for (int i = 0; i < 6; ++i) plf_count_launch();
-  PLF_CHECK(ctx, cudaGetLastError());
-  PLF_CHECK(ctx, cudaMemcpyAsync(ctx->h_result, total, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  *h_ids = *(unsigned int *)ctx->h_result;
-  return 1;
+  plf_rep_job_t job;
+  job.site_id_left = d_idl;
+  job.site_id_right = d_idr;
+  job.site_id_parent = d_site_id;
+  job.id_site_parent = d_id_site;
+  job.ids_left = ids_left;
+  job.lookup_offset = 0;
+  return plf_repeats_ids_batch(ctx, sites, &job, 1, d_lookup, h_ids);
 }
 
 /* keys[s] = class code of the tip character at site s (repeats.c:204-216) */

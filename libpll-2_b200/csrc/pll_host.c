@@ -41,6 +41,10 @@ static __thread int tls_device = -1;
 /* the streaming kernels fetch scalers and tip codes with 16-byte bulk copies:
  * the last copy of a buffer may read up to 15 bytes past its logical end */
 #define BULK_PAD 16
+/* site-repeat identifiers, batched per traversal level: lookup pool = this many
+ * times lookup_buffer_size entries; workspace budget for the rank arrays */
+#define REPEATS_POOL_FACTOR 16
+#define REPEATS_BATCH_WS_BYTES ((size_t)1 << 30)
 
 typedef struct sumtable_slot
 {
@@ -93,8 +97,9 @@ typedef struct cuda_partition
   unsigned int * id_site_count; /* classes found at the last id computation */
   unsigned char * ids_stale;    /* host mirrors older than the device copy */
   unsigned int * d_lookup;
+  unsigned int * d_lookup_pool;           /* slices for the nodes of one traversal level */
+  unsigned long long lookup_pool_entries;
   unsigned int * d_keys;
-  unsigned int * d_id_site_tmp;
   unsigned char * d_rep_charmap;
   int repeats_mirror;
 
@@ -236,8 +241,8 @@ static void free_repeats(cuda_partition_t * cp)
   free(cp->id_site_count);
   free(cp->ids_stale);
   plf_free(cp->ctx, cp->d_lookup);
+  plf_free(cp->ctx, cp->d_lookup_pool);
   plf_free(cp->ctx, cp->d_keys);
-  plf_free(cp->ctx, cp->d_id_site_tmp);
   plf_free(cp->ctx, cp->d_rep_charmap);
 }
 
@@ -337,12 +342,16 @@ static int repeats_initialize(cuda_partition_t * cp)
     r->pernode_site_id[i] = (unsigned int *)calloc(p->sites, sizeof(unsigned int));
     r->pernode_id_site[i] = (unsigned int *)calloc(p->sites, sizeof(unsigned int));
     cp->d_site_id[i] = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 1);
-    if (!r->pernode_site_id[i] || !r->pernode_id_site[i] || !cp->d_site_id[i]) return PLL_FAILURE;
+    /* id -> site arrays keep room for `sites` classes on the device so that the
+     * identifier kernels write them in place, whatever the class count turns
+     * out to be (the host mirrors are sized exactly, as in the reference) */
+    cp->d_id_site[i] = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 0);
+    if (!r->pernode_site_id[i] || !r->pernode_id_site[i] || !cp->d_site_id[i] || !cp->d_id_site[i])
+      return PLL_FAILURE;
   }
   cp->d_keys = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 0);
-  cp->d_id_site_tmp = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 0);
   cp->d_rep_charmap = (unsigned char *)plf_alloc(cp->ctx, PLL_ASCII_SIZE, 0);
-  if (!cp->d_keys || !cp->d_id_site_tmp || !cp->d_rep_charmap) return PLL_FAILURE;
+  if (!cp->d_keys || !cp->d_rep_charmap) return PLL_FAILURE;
   return PLL_SUCCESS;
 }
 
@@ -653,9 +662,6 @@ PLL_EXPORT void pll_default_reallocate_repeats(pll_partition_t * partition, unsi
   }
   free(r->pernode_id_site[parent]);
   r->pernode_id_site[parent] = (unsigned int *)malloc((size_t)(sites_to_alloc ? sites_to_alloc : 1) * sizeof(unsigned int));
-  plf_free(cp->ctx, cp->d_id_site[parent]);
-  cp->d_id_site[parent] =
-      (unsigned int *)plf_alloc(cp->ctx, (size_t)(sites_to_alloc ? sites_to_alloc : 1) * sizeof(unsigned int), 0);
 }
 
 /* class identifiers of a tip: classes are the distinct map values, numbered
@@ -688,68 +694,41 @@ PLL_EXPORT int pll_update_repeats_tips(pll_partition_t * partition, unsigned int
   if (!plf_upload(cp->ctx, cp->d_seq, sequence, partition->sites) ||
       !plf_upload(cp->ctx, cp->d_rep_charmap, cm, PLL_ASCII_SIZE) ||
       !plf_tip_keys(cp->ctx, cp->d_seq, cp->d_rep_charmap, partition->sites, cp->d_keys) ||
-      !plf_repeats_ids(cp->ctx, partition->sites, cp->d_keys, 0, NULL, cp->d_site_id[tip_index], cp->d_id_site_tmp,
-                       cp->d_lookup, &ids))
+      !plf_repeats_ids(cp->ctx, partition->sites, cp->d_keys, 0, NULL, cp->d_site_id[tip_index],
+                       cp->d_id_site[tip_index], cp->d_lookup, &ids))
     return cuda_fail(cp);
   r->pernode_ids[tip_index] = ids;
   cp->id_site_count[tip_index] = ids;
 
   free(r->pernode_id_site[tip_index]);
   r->pernode_id_site[tip_index] = (unsigned int *)malloc((size_t)(ids ? ids : 1) * sizeof(unsigned int));
-  plf_free(cp->ctx, cp->d_id_site[tip_index]);
-  cp->d_id_site[tip_index] = (unsigned int *)plf_alloc(cp->ctx, (size_t)(ids ? ids : 1) * sizeof(unsigned int), 0);
   plf_free(cp->ctx, partition->clv[tip_index]);
   partition->clv[tip_index] =
       (double *)plf_alloc(cp->ctx, (size_t)ids * partition->states_padded * partition->rate_cats * sizeof(double), 1);
   cp->clv_entries[tip_index] = ids;
   r->pernode_allocated_clvs[tip_index] = ids;
-  if (!r->pernode_id_site[tip_index] || !cp->d_id_site[tip_index] || !partition->clv[tip_index])
+  if (!r->pernode_id_site[tip_index] || !partition->clv[tip_index])
   {
     set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory for repeats structure. %s",
               plf_last_error(cp->ctx));
     return PLL_FAILURE;
   }
-  if (!plf_copy_d2d(cp->ctx, cp->d_id_site[tip_index], cp->d_id_site_tmp, (size_t)ids * sizeof(unsigned int)))
-    return cuda_fail(cp);
   cp->ids_stale[tip_index] = 1;
   if (cp->repeats_mirror) sync_ids_to_host(cp, tip_index);
   return PLL_SUCCESS;
 }
 
-/* class identifiers of the parent of `op` from its children's
- * (src/repeats.c:299-382); identifiers are computed on the device */
-PLL_EXPORT void pll_update_repeats(pll_partition_t * partition, const pll_operation_t * op)
+/* bookkeeping after the class count of `op`'s parent is known
+ * (src/repeats.c:349-381): `ids` = 0 means repeats are off for this node */
+static void repeats_finish_op(cuda_partition_t * cp, const pll_operation_t * op, unsigned int ids)
 {
-  cuda_partition_t * cp = CP(partition);
-  pll_repeats_t * r;
-  unsigned int left, right, parent, ids = 0, sites_to_alloc;
-  if (!cp) return;
-  r = partition->repeats;
-  left = op->child1_clv_index;
-  right = op->child2_clv_index;
-  parent = op->parent_clv_index;
-  if (!cp->d_lookup) pll_resize_repeats_lookup(partition, PLL_REPEATS_LOOKUP_SIZE);
-  if (!cp->d_lookup) return;
-
-  if (!r->enable_repeats(partition, left, right))
-  {
-    sites_to_alloc = partition->sites;
-    r->pernode_ids[parent] = 0;
-    if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = 0;
-  }
-  else
-  {
-    if (!plf_repeats_ids(cp->ctx, partition->sites, cp->d_site_id[left], r->pernode_ids[left], cp->d_site_id[right],
-                         cp->d_site_id[parent], cp->d_id_site_tmp, cp->d_lookup, &ids))
-    {
-      cuda_fail(cp);
-      return;
-    }
-    r->pernode_ids[parent] = ids;
-    if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = ids;
-    sites_to_alloc = ids;
-    cp->ids_stale[parent] = 1;
-  }
+  pll_partition_t * partition = &cp->pub;
+  pll_repeats_t * r = partition->repeats;
+  const unsigned int parent = op->parent_clv_index;
+  unsigned int sites_to_alloc = ids ? ids : partition->sites;
+  r->pernode_ids[parent] = ids;
+  if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = ids;
+  if (ids) cp->ids_stale[parent] = 1;
   r->reallocate_repeats(partition, parent, op->parent_scaler_index, sites_to_alloc);
   /* no compression on this node: tell the kernels not to gather */
   if (sites_to_alloc >= partition->sites)
@@ -758,10 +737,156 @@ PLL_EXPORT void pll_update_repeats(pll_partition_t * partition, const pll_operat
     if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = 0;
   }
   cp->id_site_count[parent] = ids;
-  if (ids && cp->d_id_site[parent] &&
-      !plf_copy_d2d(cp->ctx, cp->d_id_site[parent], cp->d_id_site_tmp, (size_t)ids * sizeof(unsigned int)))
-    cuda_fail(cp);
   if (cp->repeats_mirror) sync_ids_to_host(cp, parent);
+}
+
+/* class identifiers of the parent of `op` from its children's
+ * (src/repeats.c:299-382); identifiers are computed on the device */
+PLL_EXPORT void pll_update_repeats(pll_partition_t * partition, const pll_operation_t * op)
+{
+  cuda_partition_t * cp = CP(partition);
+  pll_repeats_t * r;
+  unsigned int left, right, parent, ids = 0;
+  if (!cp) return;
+  r = partition->repeats;
+  left = op->child1_clv_index;
+  right = op->child2_clv_index;
+  parent = op->parent_clv_index;
+  if (!cp->d_lookup) pll_resize_repeats_lookup(partition, PLL_REPEATS_LOOKUP_SIZE);
+  if (!cp->d_lookup) return;
+
+  if (r->enable_repeats(partition, left, right) &&
+      !plf_repeats_ids(cp->ctx, partition->sites, cp->d_site_id[left], r->pernode_ids[left], cp->d_site_id[right],
+                       cp->d_site_id[parent], cp->d_id_site[parent], cp->d_lookup, &ids))
+  {
+    cuda_fail(cp);
+    return;
+  }
+  repeats_finish_op(cp, op, ids);
+}
+
+/* Identifiers of a whole operation list.  A parent's identifiers depend only
+ * on its children's, so the list is walked level by level (the CLV launch
+ * levels): within a level every node that keeps repeats on is numbered by the
+ * SAME six kernel launches, each in its own slice of a pooled lookup table,
+ * and the host synchronises once per level to learn the class counts -- which
+ * it needs before the next level, because enable_repeats (a caller-installable
+ * host callback) looks at the children's counts, and reallocate_repeats sizes
+ * the CLV and scale buffers by them. */
+static int update_repeats_levels(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+{
+  pll_partition_t * partition = &cp->pub;
+  pll_repeats_t * r = partition->repeats;
+  unsigned int i, j, nlevels, njobs = 0, max_jobs;
+  unsigned long long pool_used = 0;
+  unsigned int * level, * order, * start;
+  plf_rep_job_t * jobs;
+  unsigned int * job_op, * ids;
+  int nl, ok = 1;
+  if (!cp->d_lookup) pll_resize_repeats_lookup(partition, PLL_REPEATS_LOOKUP_SIZE);
+  if (!cp->d_lookup) return 0;
+  if (cp->lookup_pool_entries < (unsigned long long)r->lookup_buffer_size * REPEATS_POOL_FACTOR)
+  {
+    const unsigned long long want = (unsigned long long)r->lookup_buffer_size * REPEATS_POOL_FACTOR;
+    plf_free(cp->ctx, cp->d_lookup_pool);
+    cp->d_lookup_pool = (unsigned int *)plf_alloc(cp->ctx, (size_t)want * sizeof(unsigned int), 0);
+    cp->lookup_pool_entries = 0;
+    if (!cp->d_lookup_pool || !plf_fill_u32(cp->ctx, cp->d_lookup_pool, EMPTY_ELEMENT, (size_t)want))
+      return cuda_fail(cp);
+    cp->lookup_pool_entries = want;
+  }
+  /* workspace budget: rank arrays of sites entries per job */
+  max_jobs = (unsigned int)(REPEATS_BATCH_WS_BYTES / ((size_t)partition->sites * sizeof(unsigned int) + 64));
+  if (max_jobs < 1) max_jobs = 1;
+  if (max_jobs > 32768) max_jobs = 32768;
+
+  level = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  order = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  start = (unsigned int *)calloc((size_t)count + 2, sizeof(unsigned int));
+  jobs = (plf_rep_job_t *)malloc((size_t)(count < max_jobs ? count : max_jobs) * sizeof(plf_rep_job_t));
+  job_op = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  ids = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  nl = (level && order && start && jobs && job_op && ids) ? pll_cuda_schedule_levels(ops, count, level) : -1;
+  if (nl < 0)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+    ok = 0;
+    goto done;
+  }
+  nlevels = (unsigned int)nl;
+  for (i = 0; i < count; ++i) start[level[i] + 1]++;
+  for (i = 0; i < nlevels; ++i) start[i + 1] += start[i];
+  {
+    unsigned int * cursor = (unsigned int *)malloc(((size_t)nlevels + 1) * sizeof(unsigned int));
+    if (!cursor)
+    {
+      ok = 0;
+      goto done;
+    }
+    memcpy(cursor, start, ((size_t)nlevels + 1) * sizeof(unsigned int));
+    for (i = 0; i < count; ++i) order[cursor[level[i]]++] = i;
+    free(cursor);
+  }
+
+#define FLUSH_JOBS()                                                                                          \
+  do                                                                                                          \
+  {                                                                                                           \
+    if (njobs)                                                                                                \
+    {                                                                                                         \
+      if (!plf_repeats_ids_batch(cp->ctx, partition->sites, jobs, njobs, cp->d_lookup_pool, ids))             \
+      {                                                                                                       \
+        cuda_fail(cp);                                                                                        \
+        ok = 0;                                                                                               \
+        goto done;                                                                                            \
+      }                                                                                                       \
+      for (j = 0; j < njobs; ++j) repeats_finish_op(cp, ops + job_op[j], ids[j]);                             \
+      njobs = 0;                                                                                              \
+      pool_used = 0;                                                                                          \
+    }                                                                                                         \
+  } while (0)
+
+  for (i = 0; i < nlevels; ++i)
+  {
+    unsigned int k;
+    for (k = start[i]; k < start[i + 1]; ++k)
+    {
+      const pll_operation_t * op = ops + order[k];
+      const unsigned int left = op->child1_clv_index, right = op->child2_clv_index, parent = op->parent_clv_index;
+      unsigned long long need;
+      if (!r->enable_repeats(partition, left, right))
+      {
+        repeats_finish_op(cp, op, 0);
+        continue;
+      }
+      need = (unsigned long long)r->pernode_ids[left] * r->pernode_ids[right];
+      if (!need || need > cp->lookup_pool_entries)
+      {
+        /* a caller-installed enable_repeats asked for more than the pool holds */
+        repeats_finish_op(cp, op, 0);
+        continue;
+      }
+      if (pool_used + need > cp->lookup_pool_entries || njobs == max_jobs) FLUSH_JOBS();
+      jobs[njobs].site_id_left = cp->d_site_id[left];
+      jobs[njobs].site_id_right = cp->d_site_id[right];
+      jobs[njobs].site_id_parent = cp->d_site_id[parent];
+      jobs[njobs].id_site_parent = cp->d_id_site[parent];
+      jobs[njobs].ids_left = r->pernode_ids[left];
+      jobs[njobs].lookup_offset = (unsigned int)pool_used;
+      job_op[njobs] = order[k];
+      pool_used += need;
+      ++njobs;
+    }
+    FLUSH_JOBS(); /* the next level reads this level's class counts */
+  }
+#undef FLUSH_JOBS
+done:
+  free(level);
+  free(order);
+  free(start);
+  free(jobs);
+  free(job_op);
+  free(ids);
+  return ok;
 }
 
 /* ---- tips ------------------------------------------------------------------- */
@@ -1534,8 +1659,9 @@ PLL_EXPORT void pll_update_partials_rep(pll_partition_t * partition, const pll_o
       return;
     }
     /* identifiers depend on the children's identifiers only, not on CLV
-     * values: compute them for the whole list first, then run the levels */
-    for (i = 0; i < count; ++i) pll_update_repeats(partition, operations + i);
+     * values: compute them for the whole list first (one batch of launches
+     * and one host synchronisation per level), then run the CLV levels */
+    if (!update_repeats_levels(cp, operations, count)) return;
   }
   launch_levels(cp, operations, count);
 }
