@@ -60,6 +60,8 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
   {
     const char * v = getenv("PLF_AA_FAST");
     ctx->aa_fast = !(v && v[0] == '0');
+    v = getenv("PLF_EDGE_FAST");
+    ctx->edge_fast = !(v && v[0] == '0');
     v = getenv("PLF_AA_SPT");
     ctx->aa_spt = (v && v[0] >= '1' && v[0] <= '4') ? (v[0] - '0') : 2;
   }
@@ -94,6 +96,8 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
     }
   }
   if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_result, 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_ticket, 64);
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_ticket, 0, 64);
   if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_result, 4 * sizeof(double));
   if (e != cudaSuccess)
   {
@@ -123,6 +127,8 @@ extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
   cudaFree(ctx->ws_small.ptr);
   cudaFree(ctx->ws_partial.ptr);
   cudaFree(ctx->d_result);
+  cudaFree(ctx->d_ticket);
+  cudaFree(ctx->ws_edge.ptr);
   cudaFreeHost(ctx->h_result);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   cudaStreamDestroy(ctx->stream);
@@ -154,7 +160,10 @@ void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes)
 extern "C" void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero)
 {
   void * p = NULL;
-  if (!bytes) bytes = 8;
+  /* every buffer carries >= 16 bytes of slack: the bulk-copy kernels round the
+   * last tile of 1- and 4-byte arrays (tip codes, scalers, weights, invariant
+   * flags) up to the 16-byte copy granule */
+  bytes = (bytes + 16 + 255) & ~(size_t)255;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return NULL;
   cudaError_t e;
   if (ctx->managed)

@@ -142,3 +142,42 @@ __device__ __forceinline__ double block_sum(double v, double * red)
   }
   return r;
 }
+
+/* ---- fused grid reduction ------------------------------------------------- *
+ * Every block leaves its NV partial sums in partial[v * gridDim.x + block];
+ * the block that arrives last (ticket counter) adds them in a fixed order and
+ * writes out[v] (and hout[v], pinned host memory, when given): one launch, the
+ * same bits run to run for a given grid size.  `red` >= 32 doubles.          */
+template <int NV>
+__device__ __forceinline__ void grid_reduce_finish(const double (&v)[NV], double * __restrict__ partial,
+                                                   unsigned int * ticket, double * out, double * hout, double * red)
+{
+  __shared__ int s_last;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    const double r = block_sum(v[i], red);
+    if (threadIdx.x == 0) partial[(size_t)i * gridDim.x + blockIdx.x] = r;
+  }
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    double acc = 0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) acc += __ldcg(partial + (size_t)i * gridDim.x + b);
+    const double r = block_sum(acc, red);
+    if (threadIdx.x == 0)
+    {
+      out[i] = r;
+      if (hout) hout[i] = r;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}

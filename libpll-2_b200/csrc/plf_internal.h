@@ -26,12 +26,17 @@ struct plf_ctx
   int aa_spt;              /* PLF_AA_SPT: sites per thread of the 20-state kernels (1 or 2) */
   int aa_fast;             /* PLF_AA_FAST=0 forces the generic 20-state kernel */
   int dna_items;
+  int edge_occupancy[4][4]; /* DNA edge kernels [mode][log2 rates] */
+  int edge_items;           /* 0 = read PLF_EDGE_ITEMS on first use */
+  int edge_fast;            /* PLF_EDGE_FAST=0 forces the generic log-likelihood / sumtable / derivative kernels */
   cudaStream_t stream;
   cudaMemPool_t pool;    /* stream-ordered allocator behind plf_alloc/plf_free (NULL in managed mode) */
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
   plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
   plf_ws ws_partial;  /* per-block partial sums of the reductions              */
+  plf_ws ws_edge;     /* synthetic op + matrices of the DNA/AA sumtable launches */
   double * d_result;  /* 4 doubles                                             */
+  unsigned int * d_ticket; /* arrival counter of the fused (last block) reductions; zero between kernels */
   double * h_result;  /* pinned, 4 doubles                                     */
   char err[256];
   char name[128];
@@ -46,6 +51,16 @@ int plf_launch_aa_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int
                         const unsigned long long * d_tipmap, unsigned int maxstates);
 int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
                          unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous);
+
+/* 4-state fast paths (plf_edge_dna.cu); the lk/derivative ones return -1 when the call is not eligible */
+struct plf_lk;
+struct plf_deriv;
+struct plf_sumtable;
+struct plf_shape;
+int plf_loglikelihood_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_lk * a, double * dst, double * hdst);
+int plf_derivatives_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_deriv * a, double * dst, double * hdst);
+int plf_sumtable_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_sumtable * a);
+int plf_finish_reduction(plf_ctx * ctx, int nvals, double * h_out);
 
 #define PLF_CHECK(ctx, call)                                                         \
   do                                                                                 \

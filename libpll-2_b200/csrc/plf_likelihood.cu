@@ -35,26 +35,13 @@ struct Model
   }
 };
 
-/* final pass: out[v] = sum of partial[v][0..n) in a fixed order */
-__global__ void k_reduce_final(const double * __restrict__ partial, int n, int nvals, double * __restrict__ out)
-{
-  __shared__ double red[32];
-  for (int v = 0; v < nvals; ++v)
-  {
-    double acc = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[(size_t)v * n + i];
-    const double r = block_sum(acc, red);
-    if (threadIdx.x == 0) out[v] = r;
-    __syncthreads();
-  }
-}
-
 /* ------------------------------------------------------------------------ *
  *  log-likelihood (root when a.pmatrix == NULL)                              *
  * ------------------------------------------------------------------------ */
 template <int ST>
 __global__ void __launch_bounds__(256)
-k_loglik(plf_lk_t a, int R, int st_rt, int sp_rt, int per_rate, int L, double * __restrict__ partial)
+k_loglik(plf_lk_t a, int R, int st_rt, int sp_rt, int per_rate, int L, double * __restrict__ partial,
+         unsigned int * ticket, double * out, double * hout)
 {
   __shared__ double red[32];
   const int st = ST ? ST : st_rt;
@@ -193,8 +180,8 @@ k_loglik(plf_lk_t a, int R, int st_rt, int sp_rt, int per_rate, int L, double * 
       acc += site_lk;
     }
   }
-  const double r = block_sum(acc, red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+  const double v[1] = {acc};
+  grid_reduce_finish<1>(v, partial, ticket, out, hout, red);
 }
 
 static unsigned int pick_L(unsigned int R) { return (R && !(R & (R - 1)) && R <= 32) ? R : 1; }
@@ -208,17 +195,13 @@ static unsigned int pick_blocks(plf_ctx * ctx, unsigned long long work, int thre
   return (unsigned int)b;
 }
 
-static int finish_reduction(plf_ctx * ctx, const double * d_partial, int nblocks, int nvals, double * d_out,
-                            double * h_out)
+/* results land in `dst` (device) and, when the caller wants them on the host,
+ * in the pinned ctx->h_result written by the reducing block itself: the only
+ * host-side cost is one stream synchronisation */
+int plf_finish_reduction(plf_ctx * ctx, int nvals, double * h_out)
 {
-  double * dst = d_out ? d_out : ctx->d_result;
-  k_reduce_final<<<1, 256, 0, ctx->stream>>>(d_partial, nblocks, nvals, dst);
-  plf_count_launch();
-  PLF_CHECK(ctx, cudaGetLastError());
   if (h_out)
   {
-    PLF_CHECK(ctx, cudaMemcpyAsync(ctx->h_result, dst, nvals * sizeof(double), cudaMemcpyDeviceToHost,
-                                   ctx->stream));
     PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < nvals; ++i) h_out[i] = ctx->h_result[i];
   }
@@ -229,6 +212,13 @@ extern "C" int plf_loglikelihood(plf_ctx_t * ctx, const plf_shape_t * sh, const 
                                  double * h_out)
 {
   PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  double * dst = d_out ? d_out : ctx->d_result;
+  double * hdst = h_out ? ctx->h_result : nullptr;
+  if (ctx->edge_fast)
+  {
+    const int rc = plf_loglikelihood_dna(ctx, sh, a, dst, hdst);
+    if (rc >= 0) return rc ? plf_finish_reduction(ctx, 1, h_out) : 0;
+  }
   const int R = (int)sh->rate_cats;
   const int L = (int)pick_L(sh->rate_cats);
   const int threads = 256;
@@ -236,15 +226,17 @@ extern "C" int plf_loglikelihood(plf_ctx_t * ctx, const plf_shape_t * sh, const 
   double * partial = (double *)plf_ws_reserve(ctx, &ctx->ws_partial, (size_t)blocks * 2 * sizeof(double));
   if (!partial) return 0;
   if (sh->states == 4)
-    k_loglik<4><<<blocks, threads, 0, ctx->stream>>>(*a, R, 4, 4, sh->per_rate_scalers, L, partial);
+    k_loglik<4><<<blocks, threads, 0, ctx->stream>>>(*a, R, 4, 4, sh->per_rate_scalers, L, partial, ctx->d_ticket,
+                                                    dst, hdst);
   else if (sh->states == 20)
-    k_loglik<20><<<blocks, threads, 0, ctx->stream>>>(*a, R, 20, 20, sh->per_rate_scalers, L, partial);
+    k_loglik<20><<<blocks, threads, 0, ctx->stream>>>(*a, R, 20, 20, sh->per_rate_scalers, L, partial,
+                                                     ctx->d_ticket, dst, hdst);
   else
     k_loglik<0><<<blocks, threads, 0, ctx->stream>>>(*a, R, (int)sh->states, (int)sh->states_padded,
-                                                    sh->per_rate_scalers, L, partial);
+                                                    sh->per_rate_scalers, L, partial, ctx->d_ticket, dst, hdst);
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
-  return finish_reduction(ctx, partial, (int)blocks, 1, d_out, h_out);
+  return plf_finish_reduction(ctx, 1, h_out);
 }
 
 /* ------------------------------------------------------------------------ *
@@ -339,6 +331,8 @@ extern "C" int plf_update_sumtable(plf_ctx_t * ctx, const plf_shape_t * sh, cons
 {
   PLF_CHECK(ctx, cudaSetDevice(ctx->device));
   const int R = (int)sh->rate_cats;
+  if (ctx->edge_fast && sh->states == 4 && !sh->per_rate_scalers && R > 0 && !(R & (R - 1)) && R <= 32 && a->sites)
+    return plf_sumtable_dna(ctx, sh, a);
   const int L = (int)pick_L(sh->rate_cats);
   const int threads = 256;
   const unsigned int blocks = pick_blocks(ctx, (unsigned long long)a->sites * L, threads, 16);
@@ -361,7 +355,8 @@ extern "C" int plf_update_sumtable(plf_ctx_t * ctx, const plf_shape_t * sh, cons
  * ------------------------------------------------------------------------ */
 template <int ST>
 __global__ void __launch_bounds__(256)
-k_derivatives(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __restrict__ partial)
+k_derivatives(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __restrict__ partial,
+              unsigned int * ticket, double * out, double * hout)
 {
   extern __shared__ double diag[]; /* [R][st][3] */
   __shared__ double red[32];
@@ -448,19 +443,21 @@ k_derivatives(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __rest
       acc2 = fma(w, d2, acc2);
     }
   }
-  const double r1 = block_sum(acc1, red);
-  const double r2 = block_sum(acc2, red);
-  if (threadIdx.x == 0)
-  {
-    partial[blockIdx.x] = r1;
-    partial[gridDim.x + blockIdx.x] = r2;
-  }
+  const double v[2] = {acc1, acc2};
+  grid_reduce_finish<2>(v, partial, ticket, out, hout, red);
 }
 
 extern "C" int plf_derivatives(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_deriv_t * a, double * d_out2,
                                double * h_out2)
 {
   PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  double * dst = d_out2 ? d_out2 : ctx->d_result;
+  double * hdst = h_out2 ? ctx->h_result : nullptr;
+  if (ctx->edge_fast)
+  {
+    const int rc = plf_derivatives_dna(ctx, sh, a, dst, hdst);
+    if (rc >= 0) return rc ? plf_finish_reduction(ctx, 2, h_out2) : 0;
+  }
   const int R = (int)sh->rate_cats;
   const int L = (int)pick_L(sh->rate_cats);
   const int threads = 256;
@@ -474,13 +471,13 @@ extern "C" int plf_derivatives(plf_ctx_t * ctx, const plf_shape_t * sh, const pl
     return 0;
   }
   if (sh->states == 4)
-    k_derivatives<4><<<blocks, threads, smem, ctx->stream>>>(*a, R, 4, 4, L, partial);
+    k_derivatives<4><<<blocks, threads, smem, ctx->stream>>>(*a, R, 4, 4, L, partial, ctx->d_ticket, dst, hdst);
   else if (sh->states == 20)
-    k_derivatives<20><<<blocks, threads, smem, ctx->stream>>>(*a, R, 20, 20, L, partial);
+    k_derivatives<20><<<blocks, threads, smem, ctx->stream>>>(*a, R, 20, 20, L, partial, ctx->d_ticket, dst, hdst);
   else
     k_derivatives<0><<<blocks, threads, smem, ctx->stream>>>(*a, R, (int)sh->states, (int)sh->states_padded, L,
-                                                            partial);
+                                                            partial, ctx->d_ticket, dst, hdst);
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
-  return finish_reduction(ctx, partial, (int)blocks, 2, d_out2, h_out2);
+  return plf_finish_reduction(ctx, 2, h_out2);
 }

@@ -120,6 +120,21 @@ def main():
         ms = timed(eng, ext, lambda: eng.derivatives(st, 0.1, edge), reps=20)
         out[f"{name}_derivatives_ms"] = ms
         out[f"{name}_derivatives_gbs"] = (blk + 4) * sites / ms / 1e6
+        # the same two reductions queued without host synchronisation (device time per call)
+        import ctypes as C
+        dev = torch.zeros(2, dtype=torch.float64, device="cuda")
+        t = ds.tree
+        pidx = eng.params_indices.ctypes.data_as(capi.c_uint_p)
+        a, b_, m = edge
+        ms = timed(eng, ext, lambda: lib.pll_cuda_edge_loglikelihood_async(
+            eng.p, a, t.scaler_of.get(a, -1), b_, t.scaler_of.get(b_, -1), m, pidx, C.c_void_p(dev.data_ptr())), reps=50)
+        out[f"{name}_logl_async_ms"] = ms
+        out[f"{name}_logl_async_gbs"] = eb / ms / 1e6
+        ms = timed(eng, ext, lambda: lib.pll_cuda_likelihood_derivatives_async(
+            eng.p, t.scaler_of.get(a, -1), t.scaler_of.get(b_, -1), 0.1, pidx, st.ctypes.data_as(capi.c_double_p),
+            C.c_void_p(dev.data_ptr())), reps=50)
+        out[f"{name}_derivatives_async_ms"] = ms
+        out[f"{name}_derivatives_async_gbs"] = (blk + 4) * sites / ms / 1e6
     if args.config == "repeats":
         # Newton-style sweep: every branch, sumtable + 4 derivative evaluations (examples/newton/newton.c:31-96)
         st = eng.sumtable_alloc()

@@ -159,6 +159,50 @@ def test_invariant_sites_parity(reflib, cudalib, kind, extra, pinv):
     gpu.close()
 
 
+@pytest.mark.parametrize("cats", [1, 2, 3, 4, 8, 16])
+@pytest.mark.parametrize("extra", [capi.PATTERN_TIP, 0])
+def test_dna_edge_kernels_rate_counts(reflib, cudalib, cats, extra):
+    """The streaming 4-state edge / sumtable / derivative kernels are specialised per
+    rate count (1, 2, 4, 8); 3 and 16 take the generic kernels.  Site counts that are
+    not a multiple of the 64-site tile, +I, non-unit pattern weights, scaling."""
+    ds = synth.dna_dataset(90, 1003, seed=41 + cats, tree_kind="caterpillar", alpha=0.5, cats=cats)
+    ds.prop_invar = 0.2
+    ds.pattern_weights = np.random.default_rng(5).integers(1, 9, size=ds.sites).astype(np.uint32)
+    ref, gpu = pair(reflib, cudalib, ds, extra)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    last = ref.ops[len(ref.ops) - 1]
+    first = ref.ops[0]
+    edges = [ds.tree.root_edge,
+             (last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index),
+             (first.parent_clv_index, first.child1_clv_index, first.child1_matrix_index),
+             (last.parent_clv_index, last.child2_clv_index, last.child2_matrix_index)]
+    check_edge_and_derivatives(ref, gpu, ds, False, edges)
+    r_ref, rp_ref = ref.root_logl(persite=True)
+    r_gpu, rp_gpu = gpu.root_logl(persite=True)
+    assert_rel(r_gpu, r_ref, LOGL_RTOL, "root logL")
+    np.testing.assert_allclose(rp_gpu, rp_ref, rtol=1e-12)
+    ref.close()
+    gpu.close()
+
+
+def test_edge_fast_and_generic_kernels_agree(cudalib, monkeypatch):
+    """PLF_EDGE_FAST=0 forces the generic kernels: both families answer the same calls."""
+    ds = synth.dna_dataset(30, 5000, seed=77, tree_kind="random", alpha=0.6)
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PLF_EDGE_FAST", flag)
+        gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+        logl = gpu.full_traversal()
+        st = gpu.sumtable_alloc()
+        gpu.update_sumtable(st)
+        out.append((logl, gpu.root_logl(), *gpu.derivatives(st, 0.07)))
+        gpu.close()
+    for a, b in zip(*out):
+        assert abs(a - b) <= 1e-12 * abs(b), out
+
+
 REPEAT_CASES = [
     ("dna", 24, 400, "random", False, (0.002, 0.05)),
     ("dna", 64, 3000, "random", False, (0.002, 0.05)),
