@@ -57,9 +57,13 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
   ctx->device = device;
   ctx->managed = managed;
   ctx->dna_stream = -1;
+  ctx->aa_stream = -1;
+  ctx->aam_log2r[0] = ctx->aam_log2r[1] = -1;
   {
     const char * v = getenv("PLF_AA_FAST");
     ctx->aa_fast = !(v && v[0] == '0');
+    v = getenv("PLF_AA_MMA");
+    ctx->aa_mma = !(v && v[0] == '0');
     v = getenv("PLF_EDGE_FAST");
     ctx->edge_fast = !(v && v[0] == '0');
     v = getenv("PLF_AA_SPT");

@@ -25,6 +25,11 @@ struct plf_ctx
   int aa_occupancy[2];
   int aa_spt;              /* PLF_AA_SPT: sites per thread of the 20-state kernels (1 or 2) */
   int aa_fast;             /* PLF_AA_FAST=0 forces the generic 20-state kernel */
+  int aa_mma;              /* PLF_AA_MMA=0: 20-state ii/ti on the bit-exact DFMA kernels instead of DMMA */
+  size_t aam_smem_set[5];  /* [ii, ti, tt, stream ii, stream ti] */
+  int aam_occupancy[5];
+  int aam_log2r[2];
+  int aa_stream;           /* -1 = read PLF_AA_STREAM on first use; 0 keeps contiguous ops on the direct-load DMMA kernel */
   int dna_items;
   int edge_occupancy[4][4]; /* DNA edge kernels [mode][log2 rates] */
   int edge_items;           /* 0 = read PLF_EDGE_ITEMS on first use */
@@ -49,6 +54,9 @@ struct plf_op;
 int plf_launch_aa_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
                         unsigned int rate_cats, int per_rate, unsigned int max_sites,
                         const unsigned long long * d_tipmap, unsigned int maxstates);
+int plf_launch_aa_mma_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
+                            unsigned int rate_cats, int per_rate, unsigned int max_sites,
+                            const unsigned long long * d_tipmap, unsigned int maxstates, int contiguous);
 int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
                          unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous);
 

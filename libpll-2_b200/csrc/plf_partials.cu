@@ -485,16 +485,25 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
       {
         unsigned int j = i, run_sites = 0;
         int run_tip = (h_ops[i].kind != PLF_OP_II);
+        int contiguous = 1;
         while (j < b && h_ops[j].kind == h_ops[i].kind)
         {
           if (h_ops[j].nsites > run_sites) run_sites = h_ops[j].nsites;
+          if (h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id) contiguous = 0;
           ++j;
         }
         int done = 0;
-        if (run_sites && sh->states == 20 && h_ops[i].kind != PLF_OP_TT && ctx->aa_fast)
+        if (run_sites && sh->states == 20 && ctx->aa_fast)
         {
-          const int rc = plf_launch_aa_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
-                                             sh->per_rate_scalers, run_sites, d_tipmap, maxstates);
+          /* tensor-core (DMMA) kernels by default, tip-tip always on its own write-only kernel;
+           * PLF_AA_MMA=0 keeps inner-inner / tip-inner on the bit-exact DFMA kernels */
+          int rc = -1;
+          if (ctx->aa_mma || h_ops[i].kind == PLF_OP_TT)
+            rc = plf_launch_aa_mma_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats, sh->per_rate_scalers,
+                                         run_sites, d_tipmap, maxstates, contiguous);
+          if (rc == -1 && h_ops[i].kind != PLF_OP_TT)
+            rc = plf_launch_aa_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats, sh->per_rate_scalers,
+                                     run_sites, d_tipmap, maxstates);
           if (rc == 0) return 0;
           done = (rc == 1);
         }

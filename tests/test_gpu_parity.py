@@ -21,6 +21,7 @@ pytestmark = pytest.mark.gpu
 
 LOGL_RTOL = 1e-10
 DERIV_RTOL = 1e-9
+CLV_MMA_RTOL = 1e-12
 
 
 def bits(a):
@@ -81,6 +82,9 @@ CASES = [
     ("aa", 120, 21, "caterpillar", capi.PATTERN_TIP, False),
     ("aa", 120, 21, "caterpillar", capi.PATTERN_TIP, True),
     ("aa", 110, 17, "caterpillar", 0, False),
+    # more sites than one sweep of the persistent grid covers (8 sites per warp step)
+    ("aa", 6, 25003, "random", capi.PATTERN_TIP, False),
+    ("aa", 6, 25003, "random", 0, True),
     ("g5", 10, 41, "random", capi.PATTERN_TIP, False),
     ("g5", 150, 19, "caterpillar", capi.PATTERN_TIP, False),
     ("g7", 150, 19, "caterpillar", 0, True),
@@ -88,8 +92,26 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("kind,tips,sites,tree,extra,per_rate", CASES)
-def test_traversal_parity(reflib, cudalib, kind, tips, sites, tree, extra, per_rate):
+def assert_clv_equal(a, b, exact, what):
+    """bit-exact, or -- on the 20-state tensor-core (DMMA) kernels, whose
+    accumulation order differs from the AVX2 lanes -- equal to a few ulp per level"""
+    if exact:
+        assert np.array_equal(bits(a), bits(b)), what
+    else:
+        np.testing.assert_allclose(b, a, rtol=CLV_MMA_RTOL, atol=0, err_msg=what)
+
+
+# 20-state cases run twice: PLF_AA_MMA=0 (DFMA kernels, CLVs bit-exact) and the
+# default DMMA kernels (CLVs within CLV_MMA_RTOL, integer scalers still exact)
+CASES_MODES = [(c, m) for c in CASES for m in (("dfma", "dmma") if c[0] == "aa" else ("default",))]
+
+
+@pytest.mark.parametrize("case,mode", CASES_MODES, ids=lambda v: v if isinstance(v, str) else "-".join(map(str, v)))
+def test_traversal_parity(reflib, cudalib, case, mode, monkeypatch):
+    kind, tips, sites, tree, extra, per_rate = case
+    if mode != "default":
+        monkeypatch.setenv("PLF_AA_MMA", "0" if mode == "dfma" else "1")
+    exact = mode != "dmma"
     ds = make_ds(kind, tips, sites, tree)
     ref, gpu = pair(reflib, cudalib, ds, extra, per_rate)
     for e in (ref, gpu):
@@ -104,7 +126,7 @@ def test_traversal_parity(reflib, cudalib, kind, tips, sites, tree, extra, per_r
     n_scaled = 0
     for op in ref.ops:
         a, b = ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index)
-        assert np.array_equal(bits(a), bits(b)), f"clv {op.parent_clv_index}"
+        assert_clv_equal(a, b, exact, f"clv {op.parent_clv_index}")
         if op.parent_scaler_index >= 0:
             sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
             assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
@@ -203,6 +225,28 @@ def test_edge_fast_and_generic_kernels_agree(cudalib, monkeypatch):
         assert abs(a - b) <= 1e-12 * abs(b), out
 
 
+@pytest.mark.parametrize("cats", [1, 2, 3, 8])
+@pytest.mark.parametrize("per_rate", [False, True])
+def test_aa_kernels_rate_counts(reflib, cudalib, cats, per_rate):
+    """20-state DMMA kernels: the streaming variant is specialised for 1, 2, 4, 8 rate
+    categories, 3 takes the direct-load DMMA kernel.  Deep caterpillar => scaling."""
+    ds = synth.aa_dataset(400, 45, seed=51 + cats, tree_kind="caterpillar", alpha=0.4, cats=cats)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    n_scaled = 0
+    for op in ref.ops:
+        assert_clv_equal(ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index), False, f"clv {op.parent_clv_index}")
+        sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
+        assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
+        n_scaled += int(sa.sum())
+    assert n_scaled > 0
+    check_edge_and_derivatives(ref, gpu, ds, per_rate)
+    ref.close()
+    gpu.close()
+
+
 REPEAT_CASES = [
     ("dna", 24, 400, "random", False, (0.002, 0.05)),
     ("dna", 64, 3000, "random", False, (0.002, 0.05)),
@@ -213,8 +257,16 @@ REPEAT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("kind,tips,sites,tree,per_rate,brlen", REPEAT_CASES)
-def test_site_repeats_parity(reflib, cudalib, kind, tips, sites, tree, per_rate, brlen):
+REPEAT_CASES_MODES = [(c, m) for c in REPEAT_CASES for m in (("dfma", "dmma") if c[0] == "aa" else ("default",))]
+
+
+@pytest.mark.parametrize("case,mode", REPEAT_CASES_MODES,
+                         ids=lambda v: v if isinstance(v, str) else "-".join(map(str, v[:5])))
+def test_site_repeats_parity(reflib, cudalib, case, mode, monkeypatch):
+    kind, tips, sites, tree, per_rate, brlen = case
+    if mode != "default":
+        monkeypatch.setenv("PLF_AA_MMA", "0" if mode == "dfma" else "1")
+    exact = mode != "dmma"
     if kind == "dna":
         ds = synth.dna_dataset(tips, sites, seed=31, tree_kind=tree, alpha=0.3, brlen=brlen)
     elif kind == "aa":
@@ -239,7 +291,7 @@ def test_site_repeats_parity(reflib, cudalib, kind, tips, sites, tree, per_rate,
     n_scaled = 0
     for op in ref.ops:
         a, b = ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index)
-        assert np.array_equal(bits(a), bits(b)), f"clv {op.parent_clv_index}"
+        assert_clv_equal(a, b, exact, f"clv {op.parent_clv_index}")
         sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
         assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
         n_scaled += int(sa.sum())
