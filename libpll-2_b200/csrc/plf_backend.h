@@ -85,6 +85,7 @@ typedef struct plf_sumtable
   const unsigned int * c_site_id;
   const unsigned char * tipchars; /* parent side is a pattern tip */
   const unsigned long long * tipmap;
+  unsigned int maxstates;         /* entries of tipmap in use */
   const double * model;
   double * sumtable;              /* device [sites][R][sp] */
 } plf_sumtable_t;

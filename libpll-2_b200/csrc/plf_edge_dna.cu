@@ -392,19 +392,19 @@ k_deriv_dna(plf_deriv_t a, double * __restrict__ partial, unsigned int * ticket,
  *  ws = [plf_op_t (128 B)] [left R x 16] [right R x 16]                       *
  *  left[r][j][k] = pi_k Vinv[k][j] ("parent" side), right[r][j][k] = V[j][k]   *
  * ------------------------------------------------------------------------ */
-__global__ void k_sumtable_op_dna(plf_sumtable_t a, int R, unsigned char * ws)
+__global__ void k_sumtable_op(plf_sumtable_t a, int R, int st, int sp, unsigned char * ws)
 {
   plf_op_t * op = reinterpret_cast<plf_op_t *>(ws);
   double * lm = reinterpret_cast<double *>(ws + 128);
-  double * rm = lm + R * 16;
+  double * rm = lm + R * st * sp;
   const double * freqs = a.model + 3 * R;
-  const double * evecs = freqs + 2 * R * 4;
-  const double * ievecs = evecs + R * 16;
-  for (int e = threadIdx.x; e < R * 16; e += blockDim.x)
+  const double * evecs = freqs + 2 * R * sp;
+  const double * ievecs = evecs + R * st * sp;
+  for (int e = threadIdx.x; e < R * st * sp; e += blockDim.x)
   {
-    const int r = e >> 4, j = (e >> 2) & 3, k = e & 3;
-    lm[e] = freqs[r * 4 + k] * ievecs[r * 16 + k * 4 + j];
-    rm[e] = evecs[r * 16 + j * 4 + k];
+    const int r = e / (st * sp), j = (e / sp) % st, k = e % sp;
+    lm[e] = (k < st) ? freqs[r * sp + k] * ievecs[r * st * sp + k * sp + j] : 0.0;
+    rm[e] = (k < st) ? evecs[r * st * sp + j * sp + k] : 0.0;
   }
   if (threadIdx.x == 0)
   {
@@ -427,18 +427,25 @@ __global__ void k_sumtable_op_dna(plf_sumtable_t a, int R, unsigned char * ws)
   }
 }
 
-int plf_sumtable_dna(plf_ctx * ctx, const plf_shape_t * sh, const plf_sumtable_t * a)
+/* 4 states: the streaming / gathering DNA CLV kernels; 20 states: the DMMA kernels */
+int plf_sumtable_as_clv(plf_ctx * ctx, const plf_shape_t * sh, const plf_sumtable_t * a,
+                        const unsigned long long * d_tipmap, unsigned int maxstates)
 {
-  const int R = (int)sh->rate_cats;
-  unsigned char * ws = (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_edge, 128 + (size_t)2 * R * 16 * sizeof(double));
+  const int R = (int)sh->rate_cats, st = (int)sh->states, sp = (int)sh->states_padded;
+  unsigned char * ws =
+      (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_edge, 128 + (size_t)2 * R * st * sp * sizeof(double));
   if (!ws) return 0;
   static_assert(sizeof(plf_op_t) <= 128, "op descriptor must fit its slot");
-  k_sumtable_op_dna<<<1, 128, 0, ctx->stream>>>(*a, R, ws);
+  k_sumtable_op<<<1, 256, 0, ctx->stream>>>(*a, R, st, sp, ws);
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   const int contiguous = !(a->p_site_id || a->c_site_id);
-  return plf_launch_dna_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, a->tipchars ? PLF_OP_TI : PLF_OP_II,
-                              sh->rate_cats, 0, a->sites, contiguous);
+  const unsigned int kind = a->tipchars ? PLF_OP_TI : PLF_OP_II;
+  if (st == 4)
+    return plf_launch_dna_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
+                                contiguous);
+  return plf_launch_aa_mma_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
+                                 d_tipmap, maxstates, contiguous);
 }
 
 /* ------------------------------------------------------------------------ */

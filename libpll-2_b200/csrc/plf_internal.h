@@ -67,7 +67,8 @@ struct plf_sumtable;
 struct plf_shape;
 int plf_loglikelihood_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_lk * a, double * dst, double * hdst);
 int plf_derivatives_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_deriv * a, double * dst, double * hdst);
-int plf_sumtable_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_sumtable * a);
+int plf_sumtable_as_clv(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_sumtable * a,
+                        const unsigned long long * d_tipmap, unsigned int maxstates);
 int plf_finish_reduction(plf_ctx * ctx, int nvals, double * h_out);
 
 #define PLF_CHECK(ctx, call)                                                         \

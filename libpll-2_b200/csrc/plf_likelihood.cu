@@ -331,8 +331,14 @@ extern "C" int plf_update_sumtable(plf_ctx_t * ctx, const plf_shape_t * sh, cons
 {
   PLF_CHECK(ctx, cudaSetDevice(ctx->device));
   const int R = (int)sh->rate_cats;
-  if (ctx->edge_fast && sh->states == 4 && !sh->per_rate_scalers && R > 0 && !(R & (R - 1)) && R <= 32 && a->sites)
-    return plf_sumtable_dna(ctx, sh, a);
+  /* sum[j] = (sum_k clvp_k pi_k Vinv_kj)(sum_k V_jk clvc_k) is a CLV update without scaling:
+   * 4 states run it on the DNA CLV kernels, 20 states on the DMMA kernels (plf_edge_dna.cu) */
+  if (ctx->edge_fast && !sh->per_rate_scalers && a->sites &&
+      ((sh->states == 4 && R > 0 && !(R & (R - 1)) && R <= 32) || (sh->states == 20 && ctx->aa_fast && ctx->aa_mma)))
+  {
+    const int rc = plf_sumtable_as_clv(ctx, sh, a, a->tipmap, a->maxstates);
+    if (rc >= 0) return rc;
+  }
   const int L = (int)pick_L(sh->rate_cats);
   const int threads = 256;
   const unsigned int blocks = pick_blocks(ctx, (unsigned long long)a->sites * L, threads, 16);

@@ -301,24 +301,26 @@ k_clv_aa_mma(const plf_op_t * __restrict__ ops, int R, int per_rate, const plf_s
  *  tile of 64/R sites (all rates, 10 KB per child, contiguous in memory)      *
  *  lands in a shared-memory ring through ONE bulk async copy per child        *
  *  (cp.async.bulk + mbarrier), 4 tiles in flight per CTA, so DRAM sees whole  *
- *  lines once and bytes in flight do not depend on registers.  Each of the 8  *
- *  warps owns one rate category and one 8-site block of the tile for the      *
- *  whole kernel: its 2 x 15 B fragments (P^T) stay in registers, A fragments  *
- *  come from the ring with 16-byte LDS.                                       *
+ *  lines once and bytes in flight do not depend on registers.  Each warp owns *
+ *  one rate category and one 8-site block of the tile for the whole kernel:   *
+ *  its 2 x 15 B fragments (P^T) stay in registers, A fragments come from the  *
+ *  ring with 16-byte LDS.  CTAs are 4 warps (1, 2, 4 rates; the barrier per   *
+ *  tile then only joins the warps that must exchange scaling flags and 4      *
+ *  independent CTAs per SM keep the DMMA pipe fed) or 8 warps (8 rates).      *
  * ------------------------------------------------------------------------ */
 #include "plf_stream.cuh"
 
 #define AAS_NSTAGE 4
 
-template <int KIND, int LOG2R>
-__global__ void __launch_bounds__(AAM_THREADS, 2)
+template <int KIND, int LOG2R, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 512 / (NWARPS * 32))
 k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_state_t * __restrict__ tipmap,
                     int maxstates)
 {
   constexpr int R = 1 << LOG2R;
-  constexpr int SB = 8 / R;               /* 8-site blocks per tile */
+  constexpr int SB = NWARPS / R;          /* 8-site blocks per tile */
   constexpr int TILE = 8 * SB;            /* sites per tile */
-  constexpr int CH_BYTES = TILE * R * 160; /* one child's tile: 10 KB */
+  constexpr int CH_BYTES = TILE * R * 160; /* one child's tile: 5 KB (4 warps) or 10 KB (8 warps) */
   constexpr int NCH = (KIND == PLF_OP_II) ? 2 : 1;
   constexpr int STAGE = NCH * CH_BYTES;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -579,10 +581,10 @@ k_clv_aa_tt(const plf_op_t * __restrict__ ops, int R, int per_rate, const plf_st
 
 /* returns 1 launched, 0 error, -1 not applicable (caller falls back) */
 typedef void (*aas_kernel_t)(const plf_op_t *, int, const plf_state_t *, int);
-template <int LOG2R>
+template <int LOG2R, int NWARPS>
 static aas_kernel_t aas_pick(int ii)
 {
-  return ii ? k_clv_aa_mma_stream<PLF_OP_II, LOG2R> : k_clv_aa_mma_stream<PLF_OP_TI, LOG2R>;
+  return ii ? k_clv_aa_mma_stream<PLF_OP_II, LOG2R, NWARPS> : k_clv_aa_mma_stream<PLF_OP_TI, LOG2R, NWARPS>;
 }
 
 static int launch_aa_stream(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nops, unsigned int kind,
@@ -592,8 +594,17 @@ static int launch_aa_stream(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
   const int ii = (kind == PLF_OP_II);
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
-  aas_kernel_t k = log2r == 0 ? aas_pick<0>(ii) : log2r == 1 ? aas_pick<1>(ii) : log2r == 2 ? aas_pick<2>(ii) : aas_pick<3>(ii);
-  size_t smem = (size_t)AAS_NSTAGE * (ii ? 2 : 1) * 10240;
+  static int wide = -1; /* PLF_AA_WARPS=8: 8-warp CTAs for every rate count (A/B switch) */
+  if (wide < 0)
+  {
+    const char * v = getenv("PLF_AA_WARPS");
+    wide = (v && v[0] == '8');
+  }
+  const int nwarps = (log2r == 3 || wide) ? 8 : 4;
+  aas_kernel_t k = log2r == 3   ? aas_pick<3, 8>(ii)
+                   : nwarps == 8 ? (log2r == 0 ? aas_pick<0, 8>(ii) : log2r == 1 ? aas_pick<1, 8>(ii) : aas_pick<2, 8>(ii))
+                                 : (log2r == 0 ? aas_pick<0, 4>(ii) : log2r == 1 ? aas_pick<1, 4>(ii) : aas_pick<2, 4>(ii));
+  size_t smem = (size_t)AAS_NSTAGE * (ii ? 2 : 1) * 1280 * nwarps;
   if (!ii) smem += (size_t)maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);
   if (smem > ctx->smem_optin) return -1;
   const int slot = 3 + (ii ? 0 : 1);
@@ -607,16 +618,16 @@ static int launch_aa_stream(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
   int & occ = ctx->aam_occupancy[slot];
   if (!occ)
   {
-    PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, AAM_THREADS, smem));
+    PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, nwarps * 32, smem));
     if (occ < 1) occ = 1;
   }
-  const unsigned int tile = 64 / rate_cats;
+  const unsigned int tile = 8 * nwarps / rate_cats;
   const unsigned long long need = ((unsigned long long)max_sites + tile - 1) / tile;
   unsigned long long bx = ((unsigned long long)ctx->sm_count * occ) / nops;
   if (bx < 1) bx = 1;
   if (bx > need) bx = need;
   dim3 grid((unsigned int)bx, nops);
-  k<<<grid, AAM_THREADS, smem, ctx->stream>>>(d_ops, per_rate, d_tipmap, (int)maxstates);
+  k<<<grid, nwarps * 32, smem, ctx->stream>>>(d_ops, per_rate, d_tipmap, (int)maxstates);
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;

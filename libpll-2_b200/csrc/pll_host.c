@@ -1911,6 +1911,7 @@ PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition, unsigned int par
      * (src/derivatives.c:24-98, src/core_derivatives.c:473) */
     a.tipchars = cp->d_tipchars ? cp->d_tipchars[tip] : NULL;
     a.tipmap = cp->d_tipmap;
+    a.maxstates = p->maxstates;
     a.clvc = p->clv[inner];
     a.cscaler = sc >= 0 ? sb[sc] : NULL;
     if (!a.tipchars || !tipmap_on_device(cp))
