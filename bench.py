@@ -228,8 +228,11 @@ def run_reference_arm(args):
 
 
 def workload_config(args, world):
-    name = ("synthetic DNA 100 taxa x 1M sites GTR+G4, pattern-tip on, full traversal + edge logL"
-            if args.kind == "dna" else "synthetic protein LG4M-style 4 matrices, pattern-tip on, full traversal + edge logL")
+    per = f"{args.sites // 1_000_000}M" if args.sites % 1_000_000 == 0 else str(args.sites)
+    name = (f"synthetic DNA {args.tips} taxa x {per} sites per GPU GTR+G4, pattern-tip on, full traversal + edge logL"
+            if args.kind == "dna" else
+            f"synthetic protein {args.tips} taxa x {per} sites per GPU, LG4M-style 4 matrices, pattern-tip on, "
+            "full traversal + edge logL")
     return {"workload": name, "taxa": args.tips, "sites_per_gpu": args.sites, "sites_total": args.sites * world,
             "states": 4 if args.kind == "dna" else 20, "rate_cats": 4, "attributes": "ARCH_CUDA|PATTERN_TIP",
             "sharding": f"contiguous site slices x{world}, one NCCL all-reduce of logL" if world > 1 else "single GPU",

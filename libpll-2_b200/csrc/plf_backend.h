@@ -67,6 +67,7 @@ typedef struct plf_lk
   const unsigned int * c_site_id;
   const unsigned char * tipchars; /* child is a pattern tip */
   const unsigned long long * tipmap;
+  unsigned int maxstates;         /* entries of tipmap in use */
   const double * pmatrix;         /* NULL => root log-likelihood */
   const double * model;
   const unsigned int * pattern_weights;

@@ -31,6 +31,8 @@ struct plf_ctx
   int aam_log2r[2];
   int aa_stream;           /* -1 = read PLF_AA_STREAM on first use; 0 keeps contiguous ops on the direct-load DMMA kernel */
   int dna_items;
+  int lka_occupancy[3][4];  /* 20-state log-likelihood kernels [mode][log2 rates] */
+  size_t lka_smem_set[3][4];
   int edge_occupancy[4][4]; /* DNA edge kernels [mode][log2 rates] */
   int edge_items;           /* 0 = read PLF_EDGE_ITEMS on first use */
   int edge_fast;            /* PLF_EDGE_FAST=0 forces the generic log-likelihood / sumtable / derivative kernels */
@@ -66,6 +68,8 @@ struct plf_deriv;
 struct plf_sumtable;
 struct plf_shape;
 int plf_loglikelihood_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_lk * a, double * dst, double * hdst);
+int plf_loglikelihood_aa(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_lk * a, unsigned int maxstates,
+                         double * dst, double * hdst);
 int plf_derivatives_dna(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_deriv * a, double * dst, double * hdst);
 int plf_sumtable_as_clv(plf_ctx * ctx, const struct plf_shape * sh, const struct plf_sumtable * a,
                         const unsigned long long * d_tipmap, unsigned int maxstates);

@@ -216,7 +216,8 @@ extern "C" int plf_loglikelihood(plf_ctx_t * ctx, const plf_shape_t * sh, const 
   double * hdst = h_out ? ctx->h_result : nullptr;
   if (ctx->edge_fast)
   {
-    const int rc = plf_loglikelihood_dna(ctx, sh, a, dst, hdst);
+    int rc = plf_loglikelihood_dna(ctx, sh, a, dst, hdst);
+    if (rc < 0 && ctx->aa_fast && ctx->aa_mma) rc = plf_loglikelihood_aa(ctx, sh, a, a->maxstates, dst, hdst);
     if (rc >= 0) return rc ? plf_finish_reduction(ctx, 1, h_out) : 0;
   }
   const int R = (int)sh->rate_cats;

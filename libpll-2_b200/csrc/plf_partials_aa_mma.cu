@@ -41,16 +41,7 @@
 
 #include <stdlib.h>
 
-#define AAM_THREADS 256
-#define AAM_TAB_STRIDE 22 /* doubles per tip-table row (16-byte aligned rows, codes spread over banks) */
-#define AAM_FRAGS 15      /* 3 n-tiles x 5 k-tiles */
-
-__device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
-{
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
-}
+#include "plf_mma.cuh"
 
 /* L2::256B: the 160-byte block of one (site, rate) straddles 128-byte lines that the
  * neighbouring rate steps of the same site need a moment later; asking L2 to bring the
@@ -75,14 +66,6 @@ __device__ __forceinline__ double ldg_stream(const double * p)
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void stg_v2(double * p, double x, double y)
-{
-  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x), "d"(y) : "memory");
-}
-
-/* state a lane's slot q of k-tile kt stands for */
-__device__ __forceinline__ int aam_state(int kt, int q) { return kt < 4 ? (kt >> 1) * 8 + 2 * q + (kt & 1) : 16 + q; }
-
 struct AamSite
 {
   unsigned int n, lid, rid, code;

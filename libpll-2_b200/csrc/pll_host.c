@@ -1718,6 +1718,7 @@ static int fill_edge_args(cuda_partition_t * cp, plf_lk_t * a, unsigned int pare
     a->pscaler = sc >= 0 ? sb[sc] : NULL;
     a->tipchars = cp->d_tipchars[tip];
     a->tipmap = cp->d_tipmap;
+    a->maxstates = p->maxstates;
     if (!tipmap_on_device(cp)) return 0;
   }
   else

@@ -209,9 +209,13 @@ def test_dna_edge_kernels_rate_counts(reflib, cudalib, cats, extra):
     gpu.close()
 
 
-def test_edge_fast_and_generic_kernels_agree(cudalib, monkeypatch):
+@pytest.mark.parametrize("kind", ["dna", "aa"])
+def test_edge_fast_and_generic_kernels_agree(cudalib, monkeypatch, kind):
     """PLF_EDGE_FAST=0 forces the generic kernels: both families answer the same calls."""
-    ds = synth.dna_dataset(30, 5000, seed=77, tree_kind="random", alpha=0.6)
+    if kind == "dna":
+        ds = synth.dna_dataset(30, 5000, seed=77, tree_kind="random", alpha=0.6)
+    else:
+        ds = synth.aa_dataset(12, 5003, seed=78, tree_kind="random", alpha=0.6)
     out = []
     for flag in ("1", "0"):
         monkeypatch.setenv("PLF_EDGE_FAST", flag)
