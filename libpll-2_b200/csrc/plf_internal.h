@@ -19,6 +19,7 @@ struct plf_ctx
   size_t lk20_smem_set;
   int dna_occupancy[3][6]; /* resident CTAs per SM of the DNA CLV kernels [kind][log2 rates] */
   int dna_stream_occupancy[2][6];
+  int dna_tt_bulk_occupancy[4];
   int dna_stream;          /* -1 = read PLF_DNA_STREAM / PLF_DNA_STAGES on first use */
   int dna_stages;
   size_t aa_smem_set[2];

@@ -300,6 +300,100 @@ k_clv_dna_tt(const plf_op_t * __restrict__ ops, int per_rate_and_nops)
   }
 }
 
+/* ---- tip-tip through shared memory and bulk stores ------------------------------ *
+ * Same arithmetic, but the parent tile is assembled in shared memory and leaves the  *
+ * SM as ONE bulk async store (cp.async.bulk.global.shared::cta, the copy engine       *
+ * writes whole lines while the warps build the next tile); NOUT tiles in flight.     */
+__device__ __forceinline__ void bulk_s2g(void * gdst, const void * ssrc, unsigned int bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
+
+template <int LOG2R, int ITEMS, int NOUT>
+__global__ void __launch_bounds__(DNA_THREADS)
+k_clv_dna_tt_bulk(const plf_op_t * __restrict__ ops, int per_rate_and_nops)
+{
+  constexpr int R = 1 << LOG2R;
+  constexpr int TILE = (DNA_THREADS * ITEMS) >> LOG2R;
+  constexpr int OUT_BYTES = TILE * R * 32;
+  extern __shared__ __align__(128) unsigned char obuf[]; /* [NOUT][OUT_BYTES] */
+  __shared__ __align__(128) double tl[64 * R];
+  __shared__ __align__(128) double tr[64 * R];
+  const int per_rate = per_rate_and_nops & 1;
+  const unsigned int nops = (unsigned int)per_rate_and_nops >> 1;
+  const int rate = threadIdx.x & (R - 1);
+  const int swap = (R <= 4) ? ((threadIdx.x >> LOG2R) & 1) : 0; /* odd site of the quarter-warp: halves swapped */
+  unsigned int ob = 0;
+  for (unsigned int o = blockIdx.y; o < nops; o += gridDim.y)
+  {
+    const plf_op_t op = ops[o];
+    __syncthreads();
+    build_tip_table(tl, op.left_matrix, R);
+    build_tip_table(tr, op.right_matrix, R);
+    __syncthreads();
+    const unsigned int ntiles = (op.nsites + TILE - 1) / TILE;
+    unsigned int lc_next[ITEMS], rc_next[ITEMS];
+    auto fetch_codes = [&](unsigned int t) {
+#pragma unroll
+      for (int u = 0; u < ITEMS; ++u)
+      {
+        const unsigned int n = t * TILE + ((threadIdx.x + u * DNA_THREADS) >> LOG2R);
+        const unsigned int nn = n < op.nsites ? n : op.nsites - 1;
+        lc_next[u] = op.left_tip[nn];
+        rc_next[u] = op.right_tip[nn];
+      }
+    };
+    if (blockIdx.x < ntiles) fetch_codes(blockIdx.x);
+    for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ob)
+    {
+      unsigned int lc[ITEMS], rc[ITEMS];
+#pragma unroll
+      for (int u = 0; u < ITEMS; ++u)
+      {
+        lc[u] = lc_next[u];
+        rc[u] = rc_next[u];
+      }
+      if (t + gridDim.x < ntiles) fetch_codes(t + gridDim.x);
+      /* the buffer about to be overwritten must have been read by its bulk store */
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NOUT - 1) : "memory");
+      __syncthreads();
+      unsigned char * buf = obuf + (size_t)(ob % NOUT) * OUT_BYTES;
+#pragma unroll
+      for (int u = 0; u < ITEMS; ++u)
+      {
+        const unsigned int item = threadIdx.x + u * DNA_THREADS;
+        const double * pl = tl + (lc[u] * R + rate) * 4;
+        const double * pr = tr + (rc[u] * R + rate) * 4;
+        const double2 a0 = *reinterpret_cast<const double2 *>(pl + 2 * swap);
+        const double2 b0 = *reinterpret_cast<const double2 *>(pr + 2 * swap);
+        const double2 a1 = *reinterpret_cast<const double2 *>(pl + 2 * (swap ^ 1));
+        const double2 b1 = *reinterpret_cast<const double2 *>(pr + 2 * (swap ^ 1));
+        *reinterpret_cast<double2 *>(buf + (size_t)item * 32 + 16 * swap) = make_double2(a0.x * b0.x, a0.y * b0.y);
+        *reinterpret_cast<double2 *>(buf + (size_t)item * 32 + 16 * (swap ^ 1)) = make_double2(a1.x * b1.x, a1.y * b1.y);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      const unsigned int first = t * TILE;
+      const unsigned int n = min((unsigned int)TILE, op.nsites - first);
+      if (threadIdx.x == 0)
+      {
+        bulk_s2g(op.parent_clv + (size_t)first * R * 4, buf, n * R * 32);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (op.parent_scaler)
+      {
+        const unsigned int entries = per_rate ? n * R : n;
+        unsigned int * sc = op.parent_scaler + (per_rate ? (size_t)first * R : first);
+        for (unsigned int e = threadIdx.x; e < entries; e += DNA_THREADS) sc[e] = 0;
+      }
+    }
+  }
+  /* shared memory must stay valid until the last stores have read it */
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 /* ------------------------------------------------------------------------ *
  *  Streaming variants for contiguous (non-repeats) CLVs: the child tiles,    *
  *  their scalers and the tip codes are brought into a shared-memory ring by  *
@@ -541,6 +635,37 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     if (bx > ntiles) bx = ntiles;
     dim3 grid((unsigned int)bx, nops);
     k<<<grid, DNA_THREADS, smem, ctx->stream>>>(d_ops, per_rate);
+    plf_count_launch();
+    PLF_CHECK(ctx, cudaGetLastError());
+    return 1;
+  }
+
+  if (kind == PLF_OP_TT && contiguous && ctx->dna_stream && log2r <= 3 && env_int("PLF_TT_BULK", 1))
+  {
+    const int items = env_int("PLF_TT_ITEMS", 2) == 4 ? 4 : 2;
+    dna_kernel_t kb = nullptr;
+    switch (log2r)
+    {
+      case 0: kb = items == 4 ? k_clv_dna_tt_bulk<0, 4, 3> : k_clv_dna_tt_bulk<0, 2, 4>; break;
+      case 1: kb = items == 4 ? k_clv_dna_tt_bulk<1, 4, 3> : k_clv_dna_tt_bulk<1, 2, 4>; break;
+      case 2: kb = items == 4 ? k_clv_dna_tt_bulk<2, 4, 3> : k_clv_dna_tt_bulk<2, 2, 4>; break;
+      default: kb = items == 4 ? k_clv_dna_tt_bulk<3, 4, 3> : k_clv_dna_tt_bulk<3, 2, 4>; break;
+    }
+    const size_t smem = items == 4 ? (size_t)3 * 16384 : (size_t)4 * 8192;
+    const unsigned int tile = (DNA_THREADS * items) >> log2r;
+    int & occ = ctx->dna_tt_bulk_occupancy[log2r];
+    if (!occ)
+    {
+      PLF_CHECK(ctx, cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, DNA_THREADS, smem));
+      if (occ < 1) occ = 1;
+    }
+    const unsigned long long ntiles = ((unsigned long long)max_sites + tile - 1) / tile;
+    unsigned long long all = (unsigned long long)ctx->sm_count * occ;
+    if (all > ntiles) all = ntiles;
+    /* the whole grid sweeps one op after the other (few open DRAM pages) */
+    kb<<<dim3((unsigned int)(all < 1 ? 1 : all), 1), DNA_THREADS, smem, ctx->stream>>>(
+        d_ops, (per_rate & 1) | (int)(nops << 1));
     plf_count_launch();
     PLF_CHECK(ctx, cudaGetLastError());
     return 1;
