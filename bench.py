@@ -76,6 +76,16 @@ def traversal_bytes(ds, sites: int) -> tuple[int, int]:
     return total * sites, edge * sites
 
 
+def captured_traffic(kind: str, tips: int, sites: int):
+    """DRAM bytes per step of the CLV launches from the committed ncu capture of this
+    workload (profiles/r1_traffic.json), or None when the shape was not captured."""
+    try:
+        doc = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))
+        return doc[f"{kind}_{tips}x{sites}"]["traffic_bytes_per_step"]
+    except Exception:
+        return None
+
+
 def measured_peak_gbs() -> tuple[float, str]:
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     try:
@@ -218,7 +228,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": knd, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -328,10 +338,22 @@ def run_b200_arm(args):
     barrier_sync()
     e2e_s = time.perf_counter() - t0
 
-    times = torch.tensor([ms_total, ms_partials, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    # the same with the alignment itself re-sent every step (pll_set_tip_states for every tip: host
+    # characters -> state codes on the host -> HBM); a libpll-2 client does this once per analysis
+    cold_steps = min(args.steps, 3)
+    eng.set_tips()
+    barrier_sync()
+    t0 = time.perf_counter()
+    for _ in range(cold_steps):
+        eng.set_tips()
+        step_e2e()
+    barrier_sync()
+    cold_s = time.perf_counter() - t0
+
+    times = torch.tensor([ms_total, ms_partials, e2e_s * 1e3, cold_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_partials, e2e_ms = [float(x) for x in times.tolist()]
+    ms_total, ms_partials, e2e_ms, cold_ms = [float(x) for x in times.tolist()]
 
     n_ops = len(ds.tree.ops)
     updates_per_step = n_ops * args.sites * world
@@ -344,18 +366,27 @@ def run_b200_arm(args):
     h2d = len(eng.matrix_indices) * (4 + 8 + 8 * ds.rate_cats * ds.states) + n_ops * 96
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "traversals_per_s": args.steps / (ms_total * 1e-3), "logl": logl_device, "logl_e2e": logl_e2e,
         "clocks": clk,
         "e2e": {"value": updates_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / args.steps,
                 "note": "pll_update_prob_matrices + pll_update_partials + pll_compute_edge_loglikelihood with host "
-                        "arguments, synchronous host double back; tip data stays resident as in the reference"},
+                        "arguments (branch lengths, expm1 values, operation list) copied in and the host double "
+                        "copied back every step; the alignment stays resident between evaluations as in the reference",
+                "with_alignment_upload": {
+                    "value": updates_per_step * cold_steps / (cold_ms * 1e-3), "unit": UNIT, "steps": cold_steps,
+                    "ms_per_step": cold_ms / cold_steps, "h2d_bytes_per_step": h2d + args.tips * args.sites,
+                    "note": "additionally pll_set_tip_states for every tip inside the timed region (host char -> "
+                            "state code mapping on one host core, then H2D)"}},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_clv_dna_{ii,ti,tt}<2,4>" if ds.states == 4 else "k_partials_gen<20>",
+        "roofline": {"bound": "hbm", "kernel": ("k_clv_dna_stream<ii|ti> + k_clv_dna_tt_bulk (all CLV launches of the step)" if ds.states == 4
+                                else "k_clv_aa_mma_stream<ii|ti> + k_clv_aa_tt (all CLV launches of the step)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": captured_traffic(args.kind, args.tips, args.sites),
+                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the CLV launches of one step "
+                                       "(profiles/r1_traffic.json); same unit as algorithmic_bytes_per_step",
                      "algorithmic_bytes_per_step": clv_bytes, "launches_per_step": int(n_levels),
                      "ms_per_step_in_kernel": ms_partials / args.steps,
                      "whole_step_gbs": (clv_bytes + edge_bytes) * args.steps / (ms_total * 1e-3) / 1e9},
@@ -388,12 +419,19 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--kind", choices=["dna", "aa"], default="dna")
     ap.add_argument("--tips", type=int, default=100)
-    ap.add_argument("--sites", type=int, default=1_000_000, help="sites per GPU")
+    ap.add_argument("--sites", type=int, default=1_000_000, help="sites per GPU (weak scaling)")
+    ap.add_argument("--total-sites", type=int, default=0,
+                    help="strong scaling (BASELINE config 5): this many sites split into contiguous slices over the GPUs")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--cpu-sites-per-thread", type=int, default=50_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.scaling = "weak"
+    if args.total_sites:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        args.sites = (args.total_sites + world - 1) // world
+        args.scaling = "strong"
     if args.impl == "reference":
         run_reference_arm(args)
     else:

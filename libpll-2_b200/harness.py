@@ -55,10 +55,7 @@ class Engine:
             self.map = self._map_np.ctypes.data_as(C.POINTER(capi.pll_state_t))
         else:
             self.map = lib.map(ds.map_name)
-        for tip, seq in enumerate(ds.seqs):
-            rc = lib.pll_set_tip_states(self.p, tip, self.map, seq[self.site_lo:self.site_hi])
-            if rc != 1:
-                raise RuntimeError(f"pll_set_tip_states failed: {lib.errno} {lib.errmsg}")
+        self.set_tips()
         if ds.pattern_weights is not None:
             pw = np.ascontiguousarray(ds.pattern_weights[self.site_lo:self.site_hi], dtype=np.uint32)
             lib.pll_set_pattern_weights(self.p, _up(pw))
@@ -71,6 +68,15 @@ class Engine:
             self.ops[k] = Operation(*[int(x) for x in row])
         self.matrix_indices = t.matrix_indices()
         self.branch_lengths = np.ascontiguousarray(t.branch_lengths[self.matrix_indices], dtype=np.float64)
+
+    def set_tips(self):
+        """pll_set_tip_states for every tip: host characters -> state codes (or tip CLVs) in HBM"""
+        lo, hi = self.site_lo, self.site_hi
+        whole = lo == 0 and hi == self.ds.sites
+        for tip, seq in enumerate(self.ds.seqs):
+            rc = self.lib.pll_set_tip_states(self.p, tip, self.map, seq if whole else seq[lo:hi])
+            if rc != 1:
+                raise RuntimeError(f"pll_set_tip_states failed: {self.lib.errno} {self.lib.errmsg}")
 
     # -- the hot path -------------------------------------------------------
     def update_pmatrices(self, matrix_indices=None, branch_lengths=None):
