@@ -66,8 +66,6 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
     ctx->aa_mma = !(v && v[0] == '0');
     v = getenv("PLF_EDGE_FAST");
     ctx->edge_fast = !(v && v[0] == '0');
-    v = getenv("PLF_AA_SPT");
-    ctx->aa_spt = (v && v[0] >= '1' && v[0] <= '4') ? (v[0] - '0') : 2;
   }
   cudaError_t e = cudaSetDevice(device);
   cudaDeviceProp prop;

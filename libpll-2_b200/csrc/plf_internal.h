@@ -24,7 +24,6 @@ struct plf_ctx
   int dna_stages;
   size_t aa_smem_set[2];
   int aa_occupancy[2];
-  int aa_spt;              /* PLF_AA_SPT: sites per thread of the 20-state kernels (1 or 2) */
   int aa_fast;             /* PLF_AA_FAST=0 forces the generic 20-state kernel */
   int aa_mma;              /* PLF_AA_MMA=0: 20-state ii/ti on the bit-exact DFMA kernels instead of DMMA */
   size_t aam_smem_set[5];  /* [ii, ti, tt, stream ii, stream ti] */

@@ -42,6 +42,7 @@
 #include <stdlib.h>
 
 #include "plf_mma.cuh"
+#include "plf_stream.cuh"
 
 /* L2::256B: the 160-byte block of one (site, rate) straddles 128-byte lines that the
  * neighbouring rate steps of the same site need a moment later; asking L2 to bring the
@@ -291,10 +292,19 @@ k_clv_aa_mma(const plf_op_t * __restrict__ ops, int R, int per_rate, const plf_s
  *  tile then only joins the warps that must exchange scaling flags and 4      *
  *  independent CTAs per SM keep the DMMA pipe fed) or 8 warps (8 rates).      *
  * ------------------------------------------------------------------------ */
-#include "plf_stream.cuh"
-
 #define AAS_NSTAGE 4
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long * bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+/* No CTA-wide barrier in the tile loop.  Ring slots are handed back through `empty` mbarriers (every
+ * warp arrives as soon as its A fragments are in registers, i.e. before its DMMAs), so the copy engine
+ * runs up to AAS_NSTAGE tiles ahead of the slowest warp.  Per-site scaling needs the verdict of all
+ * rate warps of a site: each warp stores its block unscaled, publishes its flag (`flagbar` mbarrier)
+ * and settles the tile one iteration later, when every flag has long arrived: the rare site that
+ * scales is rescaled in place by the lanes that stored it. */
 template <int KIND, int LOG2R, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 512 / (NWARPS * 32))
 k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_state_t * __restrict__ tipmap,
@@ -308,6 +318,8 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
   constexpr int STAGE = NCH * CH_BYTES;
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ __align__(8) unsigned long long full[AAS_NSTAGE];
+  __shared__ __align__(8) unsigned long long empty[AAS_NSTAGE];
+  __shared__ __align__(8) unsigned long long flagbar[2];
   __shared__ int flags[2][TILE][R];
   unsigned char * ring = dyn;
   double * tl = reinterpret_cast<double *>(dyn + (size_t)AAS_NSTAGE * STAGE); /* TI: [maxstates][R][AAM_TAB_STRIDE] */
@@ -317,10 +329,17 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
   const int rate = warp & (R - 1), sb = warp >> LOG2R;
   const unsigned int ntiles = (op.nsites + TILE - 1) / TILE;
   const size_t span = (size_t)R * 20;
+  const bool site_scaling = op.parent_scaler && !per_rate;
 
   if (threadIdx.x == 0)
   {
-    for (int s = 0; s < AAS_NSTAGE; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < AAS_NSTAGE; ++s)
+    {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NWARPS);
+    }
+    mbar_init(&flagbar[0], NWARPS);
+    mbar_init(&flagbar[1], NWARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (KIND == PLF_OP_TI)
@@ -367,12 +386,46 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     code_next = op.left_tip[n0 < op.nsites ? n0 : op.nsites - 1];
   }
 
+  /* settle per-site scaling of the tile processed in iteration `itp` (site n_prev, child scalers sc_prev) */
+  unsigned int n_prev = 0, sc_prev = 0;
+  bool act_prev = false;
+  auto settle = [&](unsigned int itp) {
+    while (!mbar_try_wait(&flagbar[itp & 1], (itp >> 1) & 1u)) {}
+    int fire = 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) fire &= flags[itp & 1][my][r];
+    if (!act_prev) return;
+    if (fire)
+    {
+      double * out = op.parent_clv + (size_t)n_prev * span + rate * 20 + 2 * q;
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+        if (nt < 2 || q < 2)
+        {
+          const double2 tv = *reinterpret_cast<double2 *>(out + 8 * nt);
+          stg_v2(out + 8 * nt, tv.x * PLF_SCALE_FACTOR, tv.y * PLF_SCALE_FACTOR);
+        }
+    }
+    if (q == 0 && rate == 0) op.parent_scaler[n_prev] = sc_prev + (fire ? 1u : 0u);
+  };
+
   unsigned int it = 0;
   for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it)
   {
     const int s = it % AAS_NSTAGE;
     const unsigned int parity = (it / AAS_NSTAGE) & 1u;
     const unsigned char * slot = ring + (size_t)s * STAGE;
+    /* producer duty: refill the slot of the previous iteration once every warp has handed it back */
+    if (threadIdx.x == 0 && it > 0)
+    {
+      const unsigned int tn = t + (unsigned int)(AAS_NSTAGE - 1) * gridDim.x;
+      if (tn < ntiles)
+      {
+        const int sp = (it - 1) % AAS_NSTAGE;
+        while (!mbar_try_wait(&empty[sp], ((it - 1) / AAS_NSTAGE) & 1u)) {}
+        issue(tn, sp);
+      }
+    }
     const unsigned int n = t * TILE + my;
     const bool act = n < op.nsites;
     const unsigned int code = code_next;
@@ -399,6 +452,11 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
       const double2 v0 = *reinterpret_cast<const double2 *>(pr + 2 * q);
       const double2 v1 = *reinterpret_cast<const double2 *>(pr + 8 + 2 * q);
       const double a[5] = {v0.x, v0.y, v1.x, v1.y, pr[16 + q]};
+      if (KIND != PLF_OP_II)
+      {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]); /* this warp is done with the slot */
+      }
 #pragma unroll
       for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
@@ -410,6 +468,8 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
       const double2 v0 = *reinterpret_cast<const double2 *>(pl + 2 * q);
       const double2 v1 = *reinterpret_cast<const double2 *>(pl + 8 + 2 * q);
       const double a[5] = {v0.x, v0.y, v1.x, v1.y, pl[16 + q]};
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
 #pragma unroll
       for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
@@ -427,6 +487,9 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
           accL[nt][1] = tv.y;
         }
     }
+    /* the previous tile's flags have all arrived by now */
+    if (site_scaling && it > 0) settle(it - 1);
+
     double v[3][2];
     int below = 1;
 #pragma unroll
@@ -436,51 +499,42 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
       v[nt][1] = accL[nt][1] * accR[nt][1];
       if (nt < 2 || q < 2) below &= (v[nt][0] < PLF_SCALE_THRESHOLD) && (v[nt][1] < PLF_SCALE_THRESHOLD);
     }
-    int fire = 0;
     if (op.parent_scaler)
     {
       below &= __shfl_xor_sync(0xffffffffu, below, 1);
       below &= __shfl_xor_sync(0xffffffffu, below, 2);
       if (per_rate)
-        fire = below;
-      else if (q == 0)
-        flags[it & 1][my][rate] = below;
-    }
-    __syncthreads(); /* every warp is done with this ring slot; the tile's flags are visible */
-    {
-      const unsigned int tn = t + (unsigned int)AAS_NSTAGE * gridDim.x;
-      if (threadIdx.x == 0 && tn < ntiles) issue(tn, s);
-    }
-    if (op.parent_scaler && !per_rate)
-    {
-      fire = 1;
+      {
+        if (below)
+        {
 #pragma unroll
-      for (int r = 0; r < R; ++r) fire &= flags[it & 1][my][r];
+          for (int nt = 0; nt < 3; ++nt)
+          {
+            v[nt][0] *= PLF_SCALE_FACTOR;
+            v[nt][1] *= PLF_SCALE_FACTOR;
+          }
+        }
+        if (act && q == 0) op.parent_scaler[(size_t)n * R + rate] = sc + (below ? 1u : 0u);
+      }
+      else
+      {
+        if (q == 0) flags[it & 1][my][rate] = below;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&flagbar[it & 1]);
+      }
     }
     if (act)
     {
-      if (fire)
-      {
-#pragma unroll
-        for (int nt = 0; nt < 3; ++nt)
-        {
-          v[nt][0] *= PLF_SCALE_FACTOR;
-          v[nt][1] *= PLF_SCALE_FACTOR;
-        }
-      }
       double * out = op.parent_clv + (size_t)n * span + rate * 20 + 2 * q;
       stg_v2(out, v[0][0], v[0][1]);
       stg_v2(out + 8, v[1][0], v[1][1]);
       if (q < 2) stg_v2(out + 16, v[2][0], v[2][1]);
-      if (op.parent_scaler && q == 0)
-      {
-        if (per_rate)
-          op.parent_scaler[(size_t)n * R + rate] = sc + (fire ? 1u : 0u);
-        else if (rate == 0)
-          op.parent_scaler[n] = sc + (fire ? 1u : 0u);
-      }
     }
+    n_prev = n;
+    sc_prev = sc;
+    act_prev = act;
   }
+  if (site_scaling && it > 0) settle(it - 1);
 }
 
 /* ------------------------------------------------------------------------ *

@@ -56,7 +56,7 @@ __device__ __forceinline__ SiteRef resolve_site(const plf_op_t & op, unsigned in
 /* scaling test + scaler store for one (site, rate) block `v`; LOG2R = log2(rate_cats) */
 template <int LOG2R>
 __device__ __forceinline__ void scale_and_store(const plf_op_t & op, const SiteRef & s, int rate, int per_rate,
-                                                unsigned int sc_in, dbl4 & v, double * smem_dst = nullptr)
+                                                unsigned int sc_in, dbl4 & v)
 {
   constexpr int R = 1 << LOG2R;
   if (op.parent_scaler)
@@ -77,15 +77,7 @@ __device__ __forceinline__ void scale_and_store(const plf_op_t & op, const SiteR
         op.parent_scaler[s.n] = sc_in + (fire ? 1u : 0u);
     }
   }
-  if (smem_dst)
-  {
-    /* streaming kernels: the parent block replaces the thread's own child block in the ring slot; the
-     * tile leaves as one bulk store */
-    *reinterpret_cast<double2 *>(smem_dst) = make_double2(v.x, v.y);
-    *reinterpret_cast<double2 *>(smem_dst + 2) = make_double2(v.z, v.w);
-  }
-  else if (s.active)
-    st256(op.parent_clv + ((size_t)s.n * R + rate) * 4, v);
+  if (s.active) st256(op.parent_clv + ((size_t)s.n * R + rate) * 4, v);
 }
 
 /* ---- inner-inner ------------------------------------------------------------ */
@@ -456,7 +448,7 @@ __device__ __forceinline__ void stream_issue(const plf_op_t & op, unsigned int t
   if (op.right_scaler && op.parent_scaler) bulk_g2s(slot + Ly::OFF_RSC, op.right_scaler + sc_first, sc_bytes, bar);
 }
 
-template <int LOG2R, int KIND, int NSTAGE, int ITEMS, int BULKST>
+template <int LOG2R, int KIND, int NSTAGE, int ITEMS>
 __global__ void __launch_bounds__(DNA_THREADS)
 k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
 {
@@ -542,38 +534,12 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
       v.z = a.z * dot4_pairwise(Rm + 8, r);
       v.w = a.w * dot4_pairwise(Rm + 12, r);
       if (!sr.active) v = dbl4{1.0, 1.0, 1.0, 1.0}; /* stale ring bytes must not reach the scaling vote */
-      scale_and_store<LOG2R>(op, sr, rate, per_rate, sc, v,
-                             BULKST ? reinterpret_cast<double *>(slot + Ly::OFF_R) + (size_t)item * 4 : nullptr);
+      scale_and_store<LOG2R>(op, sr, rate, per_rate, sc, v);
     }
-    if (BULKST)
-    {
-      /* the slot now holds the parent tile (over the right child's): one bulk async store; the slot is
-       * reloaded one iteration later, once the store has read it (wait_group.read 1) */
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      if (threadIdx.x == 0)
-      {
-        const unsigned int n = min((unsigned int)Ly::TILE, op.nsites - first);
-        bulk_s2g(op.parent_clv + (size_t)first * R * 4, slot + Ly::OFF_R, n * R * 32);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (it > 0)
-        {
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          const int sp = (it - 1) % NSTAGE;
-          const unsigned int tn = (t - gridDim.x) + (unsigned int)NSTAGE * gridDim.x;
-          if (tn < ntiles)
-            stream_issue<LOG2R, KIND, ITEMS>(op, tn, ring + (size_t)sp * Ly::STAGE_BYTES, &full[sp], per_rate);
-        }
-      }
-    }
-    else
-    {
-      __syncthreads(); /* every warp is done with this slot */
-      const unsigned int tn = t + (unsigned int)NSTAGE * gridDim.x;
-      if (threadIdx.x == 0 && tn < ntiles) stream_issue<LOG2R, KIND, ITEMS>(op, tn, slot, &full[s], per_rate);
-    }
+    __syncthreads(); /* every warp is done with this slot */
+    const unsigned int tn = t + (unsigned int)NSTAGE * gridDim.x;
+    if (threadIdx.x == 0 && tn < ntiles) stream_issue<LOG2R, KIND, ITEMS>(op, tn, slot, &full[s], per_rate);
   }
-  if (BULKST && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 /* ------------------------------------------------------------------------ */
@@ -590,18 +556,11 @@ static dna_kernel_t pick_kernel(unsigned int kind)
 
 static const int DNA_UNROLL = 4;
 
-static int g_stream_bulkst = 0; /* PLF_DNA_BULKST=1: parent tiles leave through bulk stores (measured slower: 4.33 vs 4.16 ms per config-2 traversal, the extra barrier and the delayed slot reuse cost more than the stores save) */
-
 template <int LOG2R, int NSTAGE, int ITEMS>
 static dna_kernel_t pick_stream_kernel(unsigned int kind)
 {
-  if (g_stream_bulkst)
-  {
-    if (kind == PLF_OP_II) return k_clv_dna_stream<LOG2R, PLF_OP_II, NSTAGE, ITEMS, 1>;
-    return k_clv_dna_stream<LOG2R, PLF_OP_TI, NSTAGE, ITEMS, 1>;
-  }
-  if (kind == PLF_OP_II) return k_clv_dna_stream<LOG2R, PLF_OP_II, NSTAGE, ITEMS, 0>;
-  return k_clv_dna_stream<LOG2R, PLF_OP_TI, NSTAGE, ITEMS, 0>;
+  if (kind == PLF_OP_II) return k_clv_dna_stream<LOG2R, PLF_OP_II, NSTAGE, ITEMS>;
+  return k_clv_dna_stream<LOG2R, PLF_OP_TI, NSTAGE, ITEMS>;
 }
 
 template <int LOG2R, int ITEMS>
@@ -646,7 +605,6 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     ctx->dna_stream = env_int("PLF_DNA_STREAM", 1);
     ctx->dna_stages = env_int("PLF_DNA_STAGES", 6);
     ctx->dna_items = env_int("PLF_DNA_ITEMS", 2);
-    g_stream_bulkst = env_int("PLF_DNA_BULKST", 0);
     if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
   }
 
