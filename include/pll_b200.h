@@ -240,8 +240,14 @@ PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
 /* src/pll.c:1131 */
 PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition,
                                         const unsigned int * pattern_weights);
-/* src/pll.c:1145,1192: accepted for ABI completeness; ascertainment-bias math
- * is outside this round's hot path and fails with PLL_ERROR_CUDA_UNSUPPORTED */
+/* src/pll.c:1145,1192.  Ascertainment bias correction (PLL_ATTRIB_AB_LEWIS / _FELSENSTEIN /
+ * _STAMATAKIS on a partition created with PLL_ATTRIB_AB_FLAG or one of the types): the `states`
+ * pseudo-sites are appended to every CLV, scaler, tipchars and sumtable buffer and go through the
+ * same kernels as the alignment; the correction terms of the log-likelihood
+ * (src/likelihood.c:24-120,190-268,342-440) and of the derivatives (src/core_derivatives.c:851-924)
+ * are O(states^2 x rates) host arithmetic on a small download of those pseudo-site blocks.
+ * Not supported together with PLL_ATTRIB_SITE_REPEATS (pll_errno 901) and not applied by the
+ * pll_cuda_*_async entry points. */
 PLL_EXPORT int pll_set_asc_bias_type(pll_partition_t * partition,
                                      int asc_bias_type);
 PLL_EXPORT void pll_set_asc_state_weights(pll_partition_t * partition,

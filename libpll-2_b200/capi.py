@@ -24,6 +24,9 @@ ARCH_AVX = 1 << 1
 ARCH_AVX2 = 1 << 2
 PATTERN_TIP = 1 << 4
 AB_LEWIS = 1 << 5
+AB_FELSENSTEIN = 2 << 5
+AB_STAMATAKIS = 3 << 5
+AB_MASK = 7 << 5
 AB_FLAG = 1 << 8
 RATE_SCALERS = 1 << 9
 SITE_REPEATS = 1 << 10
@@ -134,6 +137,8 @@ _PROTOS = {
         C.c_int,
         [PartitionP, C.c_int, C.c_int, C.c_double, c_uint_p, c_double_p, c_double_p, c_double_p],
     ),
+    "pll_set_asc_bias_type": (C.c_int, [PartitionP, C.c_int]),
+    "pll_set_asc_state_weights": (None, [PartitionP, c_uint_p]),
     "pll_repeats_enabled": (C.c_int, [PartitionP]),
     "pll_get_sites_number": (C.c_uint, [PartitionP, C.c_uint]),
     "pll_get_clv_size": (C.c_uint, [PartitionP, C.c_uint]),

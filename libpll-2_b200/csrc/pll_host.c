@@ -52,11 +52,16 @@ typedef struct sumtable_slot
   double * dev;
   size_t doubles;
   unsigned long long stamp;
+  double * asc_host; /* ascertainment bias: host copy of the `states` pseudo-site blocks */
 } sumtable_slot_t;
 
 typedef struct cuda_partition
 {
   pll_partition_t pub; /* MUST be first: callers hold &pub */
+  unsigned long long partials_generation; /* bumped by every pll_update_partials */
+  unsigned int * asc_sc;                  /* cached pseudo-site scalers [parent states][child states] */
+  int asc_sc_valid, asc_sc_parent, asc_sc_child;
+  unsigned long long asc_sc_generation;
   unsigned int magic;
   plf_ctx_t * ctx;
   plf_shape_t shape;
@@ -136,6 +141,13 @@ static int cuda_fail(cuda_partition_t * cp)
 {
   set_error(PLL_ERROR_CUDA, "CUDA: %s", plf_last_error(cp->ctx));
   return PLL_FAILURE;
+}
+
+/* per-site allocations carry `states` extra pseudo-sites under ascertainment bias correction
+ * (src/pll.c:524-531): CLVs, scalers, tipchars, pattern weights, sumtables */
+static unsigned int sites_alloc(const pll_partition_t * p)
+{
+  return p->sites + (p->asc_bias_alloc ? p->states : 0);
 }
 
 static int env_flag(const char * name)
@@ -260,7 +272,11 @@ static void destroy(cuda_partition_t * cp)
       for (i = 0; i < p->scale_buffers; ++i) plf_free(cp->ctx, p->scale_buffer[i]);
     if (cp->d_tipchars)
       for (i = 0; i < p->tips; ++i) plf_free(cp->ctx, cp->d_tipchars[i]);
-    for (i = 0; i < MAX_SUMTABLES; ++i) plf_free(cp->ctx, cp->sumtabs[i].dev);
+    for (i = 0; i < MAX_SUMTABLES; ++i)
+    {
+      plf_free(cp->ctx, cp->sumtabs[i].dev);
+      free(cp->sumtabs[i].asc_host);
+    }
     plf_free(cp->ctx, cp->d_pmatrix_block);
     plf_free(cp->ctx, cp->d_model);
     plf_free(cp->ctx, cp->d_pattern_weights);
@@ -301,6 +317,7 @@ static void destroy(cuda_partition_t * cp)
   free(cp->d_tipchars);
   free(cp->clv_entries);
   free(cp->scaler_entries);
+  free(cp->asc_sc);
   free(cp->h_model);
   free(cp->h_model_sent);
   free(cp->h_ops);
@@ -383,14 +400,14 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     }
     attributes = (attributes & ~(unsigned int)PLL_ATTRIB_ARCH_MASK) | PLL_ATTRIB_ARCH_CUDA;
   }
-  if (attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG))
-  {
-    set_error(PLL_ERROR_CUDA_UNSUPPORTED, "ascertainment bias correction is not implemented for CUDA partitions%s",
-              NULL);
-    return NULL;
-  }
   /* too few sites: repeats silently off (src/pll.c:446-449) */
   if (sites < 16) attributes &= ~(unsigned int)PLL_ATTRIB_SITE_REPEATS;
+  if ((attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG)) && (attributes & PLL_ATTRIB_SITE_REPEATS))
+  {
+    set_error(PLL_ERROR_CUDA_UNSUPPORTED,
+              "ascertainment bias correction together with site repeats is not implemented for CUDA partitions%s", NULL);
+    return NULL;
+  }
   if ((attributes & PLL_ATTRIB_SITE_REPEATS) && (attributes & PLL_ATTRIB_PATTERN_TIP))
   {
     set_error(PLL_ERROR_PARAM_INVALID, "PLL_ATTRIB_PATTERN_TIP and PLL_ATTRIB_SITE_REPEATS are mutually exclusive%s",
@@ -418,6 +435,8 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
   p->sites = sites;
   p->pattern_weight_sum = sites;
   p->rate_matrices = rate_matrices;
+  p->asc_bias_alloc = (attributes & (PLL_ATTRIB_AB_MASK | PLL_ATTRIB_AB_FLAG)) > 0;
+  p->asc_additional_sites = p->asc_bias_alloc ? (int)states : 0;
   p->prob_matrices = prob_matrices;
   p->rate_cats = rate_cats;
   p->scale_buffers = scale_buffers;
@@ -464,7 +483,7 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
    * (src/pll.c:556-581) */
   if (!(attributes & PLL_ATTRIB_SITE_REPEATS))
   {
-    const size_t n = (size_t)sites * sp * rate_cats;
+    const size_t n = (size_t)sites_alloc(p) * sp * rate_cats;
     for (i = (attributes & PLL_ATTRIB_PATTERN_TIP) ? tips : 0; i < p->nodes; ++i)
     {
       NEED(p->clv[i] = (double *)plf_alloc(cp->ctx, n * sizeof(double), 1));
@@ -472,7 +491,7 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     }
     for (i = 0; i < scale_buffers; ++i)
     {
-      const size_t m = (size_t)sites * (cp->shape.per_rate_scalers ? rate_cats : 1);
+      const size_t m = (size_t)sites_alloc(p) * (cp->shape.per_rate_scalers ? rate_cats : 1);
       NEED(p->scale_buffer[i] = (unsigned int *)plf_alloc(cp->ctx, m * sizeof(unsigned int) + BULK_PAD, 1));
       cp->scaler_entries[i] = (unsigned int)m;
     }
@@ -507,9 +526,10 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
   NEED(p->rate_weights = (double *)calloc(rate_cats, sizeof(double)));
   for (i = 0; i < rate_cats; ++i) p->rate_weights[i] = 1.0 / rate_cats;
   NEED(p->prop_invar = (double *)calloc(rate_matrices, sizeof(double)));
-  NEED(p->pattern_weights = (unsigned int *)malloc((size_t)sites * sizeof(unsigned int)));
+  NEED(p->pattern_weights = (unsigned int *)malloc((size_t)sites_alloc(p) * sizeof(unsigned int)));
   for (i = 0; i < sites; ++i) p->pattern_weights[i] = 1;
-  NEED(cp->d_pattern_weights = (unsigned int *)plf_alloc(cp->ctx, (size_t)sites * sizeof(unsigned int), 0));
+  for (i = sites; i < sites_alloc(p); ++i) p->pattern_weights[i] = 0; /* src/pll.c:823-824 */
+  NEED(cp->d_pattern_weights = (unsigned int *)plf_alloc(cp->ctx, (size_t)sites_alloc(p) * sizeof(unsigned int), 0));
 
   cp->model_doubles = plf_model_doubles(rate_cats, states, sp);
   NEED(cp->h_model = (double *)calloc(cp->model_doubles, sizeof(double)));
@@ -573,7 +593,8 @@ PLL_EXPORT void pll_resize_repeats_lookup(pll_partition_t * partition, unsigned 
 PLL_EXPORT unsigned int pll_get_sites_number(const pll_partition_t * partition, unsigned int clv_index)
 {
   unsigned int sites = (partition->attributes & PLL_ATTRIB_SITE_REPEATS) ? partition->repeats->pernode_ids[clv_index] : 0;
-  return sites ? sites : partition->sites;
+  sites = sites ? sites : partition->sites;
+  return sites + (partition->asc_bias_alloc ? partition->states : 0); /* src/repeats.c:66-70 */
 }
 
 PLL_EXPORT unsigned int pll_get_clv_size(const pll_partition_t * partition, unsigned int clv_index)
@@ -933,8 +954,8 @@ static int charmap_create(cuda_partition_t * cp, const pll_state_t * usermap)
   (void)ceil_log2; /* tip-tip tables live in shared memory: no ttlookup allocation */
   for (i = 0; i < p->tips; ++i)
   {
-    p->tipchars[i] = (unsigned char *)malloc(p->sites);
-    cp->d_tipchars[i] = (unsigned char *)plf_alloc(cp->ctx, (size_t)p->sites + BULK_PAD, 1);
+    p->tipchars[i] = (unsigned char *)malloc(sites_alloc(p));
+    cp->d_tipchars[i] = (unsigned char *)plf_alloc(cp->ctx, (size_t)sites_alloc(p) + BULK_PAD, 1);
     if (!p->tipchars[i] || !cp->d_tipchars[i])
     {
       set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate space for storing tip characters.%s", NULL);
@@ -1005,6 +1026,24 @@ static int check_sequence(const pll_partition_t * p, const pll_state_t * map, co
   return PLL_SUCCESS;
 }
 
+/* ascertainment bias: pseudo-site i of a tip CLV is the unit vector of state i, replicated over the
+ * rates (src/pll.c:1002-1020, 1112-1126) */
+static int upload_asc_tip_clv(cuda_partition_t * cp, unsigned int tip_index)
+{
+  const pll_partition_t * p = &cp->pub;
+  const unsigned int st = p->states, sp = p->states_padded, R = p->rate_cats;
+  const size_t n = (size_t)st * R * sp;
+  double * extra = (double *)calloc(n, sizeof(double));
+  unsigned int i, j;
+  int ok;
+  if (!extra) return 0;
+  for (i = 0; i < st; ++i)
+    for (j = 0; j < R; ++j) extra[((size_t)i * R + j) * sp + i] = 1.0;
+  ok = plf_upload(cp->ctx, p->clv[tip_index] + (size_t)p->sites * R * sp, extra, n * sizeof(double));
+  free(extra);
+  return ok;
+}
+
 PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_index, const pll_state_t * map,
                                   const char * sequence)
 {
@@ -1033,7 +1072,27 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_
       for (i = 0; i < partition->sites; ++i) tc[i] = (unsigned char)map[(unsigned char)sequence[i]];
     else
       for (i = 0; i < partition->sites; ++i) tc[i] = partition->charmap[(unsigned char)sequence[i]];
-    if (!plf_upload(cp->ctx, cp->d_tipchars[tip_index], tc, partition->sites)) return cuda_fail(cp);
+    if (partition->asc_bias_alloc)
+    {
+      /* pseudo-site i: every tip shows state i (src/pll.c:897-905, 935-957) */
+      unsigned char * extra = tc + partition->sites;
+      if (partition->states == 4)
+        for (i = 0; i < 4; ++i) extra[i] = (unsigned char)(1u << i);
+      else
+      {
+        memset(extra, 0, partition->states);
+        for (i = 0; i < partition->maxstates; ++i)
+        {
+          const pll_state_t state = partition->tipmap[i];
+          if (state && !(state & (state - 1)))
+          {
+            const unsigned int pos = (unsigned int)__builtin_ctzll(state);
+            if (pos < partition->states) extra[pos] = (unsigned char)i;
+          }
+        }
+      }
+    }
+    if (!plf_upload(cp->ctx, cp->d_tipchars[tip_index], tc, sites_alloc(partition))) return cuda_fail(cp);
     return PLL_SUCCESS;
   }
 
@@ -1047,6 +1106,7 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_
         !plf_tip_clv_from_states(cp->ctx, &cp->shape, partition->clv[tip_index], cp->d_seq, cp->d_map,
                                  rep ? cp->d_id_site[tip_index] : NULL, entries))
       return cuda_fail(cp);
+    if (partition->asc_bias_alloc && !upload_asc_tip_clv(cp, tip_index)) return cuda_fail(cp);
   }
   return PLL_SUCCESS;
 }
@@ -1092,6 +1152,7 @@ PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition, unsigned int tip_ind
   }
   ok = plf_upload(cp->ctx, partition->clv[tip_index], staged, (size_t)entries * R * sp * sizeof(double));
   free(staged);
+  if (ok && partition->asc_bias_alloc) ok = upload_asc_tip_clv(cp, tip_index);
   return ok ? PLL_SUCCESS : cuda_fail(cp);
 }
 
@@ -1105,22 +1166,45 @@ PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition, const unsig
   if (cp) cp->weights_dirty = 1;
 }
 
+/* src/pll.c:1145-1190 */
 PLL_EXPORT int pll_set_asc_bias_type(pll_partition_t * partition, int asc_bias_type)
 {
-  (void)asc_bias_type;
+  unsigned int i;
+  int prop_invar = 0;
+  const int asc_bias_attr = asc_bias_type & PLL_ATTRIB_AB_MASK;
   if (!partition->asc_bias_alloc)
   {
     set_error(PLL_ERROR_AB_NOSUPPORT, "Partition was not created with ascertainment bias support%s", NULL);
     return PLL_FAILURE;
   }
-  return PLL_FAILURE;
+  for (i = 0; i < partition->rate_matrices; ++i) prop_invar |= (partition->prop_invar[i] > 0);
+  if (asc_bias_type != 0 && prop_invar)
+  {
+    set_error(PLL_ERROR_INVAR_INCOMPAT, "Invariant sites are not compatible with asc bias correction%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (asc_bias_attr != asc_bias_type)
+  {
+    pll_errno = PLL_ERROR_AB_INVALIDMETHOD;
+    snprintf(pll_errmsg, 200, "Illegal ascertainment bias algorithm \"%d\"", asc_bias_type);
+    return PLL_FAILURE;
+  }
+  partition->attributes &= (unsigned int)~PLL_ATTRIB_AB_MASK;
+  partition->attributes |= (unsigned int)asc_bias_attr;
+  return PLL_SUCCESS;
 }
 
+/* src/pll.c:1192-1199 */
 PLL_EXPORT void pll_set_asc_state_weights(pll_partition_t * partition, const unsigned int * state_weights)
 {
-  (void)partition;
-  (void)state_weights;
-  set_error(PLL_ERROR_AB_NOSUPPORT, "Partition was not created with ascertainment bias support%s", NULL);
+  cuda_partition_t * cp = CP(partition);
+  if (!partition->asc_bias_alloc)
+  {
+    set_error(PLL_ERROR_AB_NOSUPPORT, "Partition was not created with ascertainment bias support%s", NULL);
+    return;
+  }
+  memcpy(partition->pattern_weights + partition->sites, state_weights, sizeof(unsigned int) * partition->states);
+  if (cp) cp->weights_dirty = 1;
 }
 
 PLL_EXPORT void pll_fill_parent_scaler(unsigned int scaler_size, unsigned int * parent_scaler,
@@ -1213,7 +1297,7 @@ static int weights_on_device(cuda_partition_t * cp)
   if (cp->weights_dirty)
   {
     if (!plf_upload(cp->ctx, cp->d_pattern_weights, cp->pub.pattern_weights,
-                    (size_t)cp->pub.sites * sizeof(unsigned int)))
+                    (size_t)sites_alloc(&cp->pub) * sizeof(unsigned int)))
       return 0;
     cp->weights_dirty = 0;
   }
@@ -1384,6 +1468,11 @@ PLL_EXPORT unsigned int pll_count_invariant_sites(pll_partition_t * partition, u
 PLL_EXPORT int pll_update_invariant_sites_proportion(pll_partition_t * partition, unsigned int params_index,
                                                      double prop_invar)
 {
+  if (prop_invar != 0.0 && (partition->attributes & PLL_ATTRIB_AB_MASK))
+  {
+    set_error(PLL_ERROR_INVAR_INCOMPAT, "Invariant sites are not compatible with asc bias correction%s", NULL);
+    return PLL_FAILURE;
+  }
   if (prop_invar < 0 || prop_invar >= 1)
   {
     pll_errno = PLL_ERROR_INVAR_PROPORTION;
@@ -1514,7 +1603,7 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
   }
   out->parent_clv = p->clv[par];
   out->parent_scaler = op->parent_scaler_index >= 0 ? sb[op->parent_scaler_index] : NULL;
-  out->nsites = p->sites;
+  out->nsites = sites_alloc(p); /* src/partials.c:33-35: the pseudo-sites are updated with the alignment */
   if (pll_repeats_enabled(p))
   {
     const pll_repeats_t * r = p->repeats;
@@ -1645,6 +1734,7 @@ PLL_EXPORT void pll_update_partials_rep(pll_partition_t * partition, const pll_o
   cuda_partition_t * cp = CP(partition);
   unsigned int i;
   if (!cp || !count) return;
+  ++cp->partials_generation;
   if (pll_repeats_enabled(partition) && update_repeats)
   {
     if (reuses_buffers(operations, count, partition->nodes))
@@ -1775,6 +1865,127 @@ static int fill_root_args(cuda_partition_t * cp, plf_lk_t * a, unsigned int clv_
   return 1;
 }
 
+
+/* ---- ascertainment bias correction ------------------------------------------------------- *
+ * The `states` pseudo-sites travel through the CLV kernels with the alignment; what is left    *
+ * is O(states^2 x rates) scalar work per evaluation (src/likelihood.c:24-120,190-268,342-440;  *
+ * src/core_derivatives.c:851-924).  It runs here on the host from a small download of the      *
+ * pseudo-site blocks, in the reference's own evaluation order.                                  */
+
+static double asc_correction(const pll_partition_t * p, double base, unsigned int sum_w_inv)
+{
+  switch (p->attributes & PLL_ATTRIB_AB_MASK)
+  {
+    case PLL_ATTRIB_AB_LEWIS: return -(p->pattern_weight_sum * log(1 - base));
+    case PLL_ATTRIB_AB_STAMATAKIS: return base;
+    case PLL_ATTRIB_AB_FELSENSTEIN: return sum_w_inv * log(base);
+    default:
+      set_error(PLL_ERROR_AB_INVALIDMETHOD, "Illegal ascertainment bias algorithm%s", NULL);
+      return -INFINITY;
+  }
+}
+
+/* pseudo-site blocks of a CLV ([states][R][sp]) and of a scale buffer ([states], zero when none) */
+static int asc_download(cuda_partition_t * cp, unsigned int first, unsigned int clv_index, int scaler_index,
+                        double * clv_out, unsigned int * scaler_out)
+{
+  const pll_partition_t * p = &cp->pub;
+  const size_t blk = (size_t)p->rate_cats * p->states_padded;
+  if (clv_out && !plf_download(cp->ctx, clv_out, p->clv[clv_index] + (size_t)first * blk,
+                               (size_t)p->states * blk * sizeof(double)))
+    return 0;
+  memset(scaler_out, 0, p->states * sizeof(unsigned int));
+  if (scaler_index >= 0 &&
+      !plf_download(cp->ctx, scaler_out, p->scale_buffer[scaler_index] + first, p->states * sizeof(unsigned int)))
+    return 0;
+  return 1;
+}
+
+/* child_clv_index < 0: root; child_is_tip: pattern tip (pseudo-site n shows state n) */
+static double asc_loglikelihood(cuda_partition_t * cp, unsigned int parent_clv_index, int parent_scaler_index,
+                                int child_clv_index, int child_scaler_index, int child_is_tip, int matrix_index,
+                                const unsigned int * freqs_indices)
+{
+  const pll_partition_t * p = &cp->pub;
+  const unsigned int st = p->states, sp = p->states_padded, R = p->rate_cats;
+  const size_t blk = (size_t)R * sp;
+  const int type = p->attributes & PLL_ATTRIB_AB_MASK;
+  double * clvp = (double *)malloc(st * blk * sizeof(double));
+  double * clvc = (double *)malloc(st * blk * sizeof(double));
+  double * pm = (double *)malloc((size_t)R * st * sp * sizeof(double));
+  unsigned int * psc = (unsigned int *)malloc(st * sizeof(unsigned int));
+  unsigned int * csc = (unsigned int *)malloc(st * sizeof(unsigned int));
+  /* the root variant of the reference locates the pseudo-sites at pll_get_sites_number() - rate_cats
+   * = sites + states - rate_cats (src/likelihood.c:180), which is `sites` only when states ==
+   * rate_cats.  With more rates than states it reads the last alignment sites instead: reproduced,
+   * the parity contract is the reference's output.  With fewer rates than states the reference reads
+   * past the end of its buffers (undefined); here the pseudo-sites themselves are used. */
+  const unsigned int first = (child_clv_index < 0 && R > st && p->sites + st >= R) ? p->sites + st - R : p->sites;
+  const unsigned int * w = p->pattern_weights + first;
+  double logl_correction = 0, result = -INFINITY;
+  unsigned int sum_w_inv = 0, n, i, j, k;
+  if (!clvp || !clvc || !pm || !psc || !csc)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+    goto done;
+  }
+  if (!asc_download(cp, first, parent_clv_index, parent_scaler_index, clvp, psc)) goto fail;
+  memset(csc, 0, st * sizeof(unsigned int));
+  if (child_clv_index >= 0 && !child_is_tip &&
+      !asc_download(cp, first, (unsigned int)child_clv_index, child_scaler_index, clvc, csc))
+    goto fail;
+  if (matrix_index >= 0 && !plf_download(cp->ctx, pm, p->pmatrix[matrix_index], (size_t)R * st * sp * sizeof(double)))
+    goto fail;
+  for (n = 0; n < st; ++n)
+  {
+    double term = 0, site_lk;
+    unsigned int scale_factors;
+    for (i = 0; i < R; ++i)
+    {
+      const double * freqs = p->frequencies[freqs_indices[i]];
+      const double * cp_ = clvp + n * blk + (size_t)i * sp;
+      const double * cc_ = clvc + n * blk + (size_t)i * sp;
+      const double * pmat = pm + (size_t)i * st * sp;
+      double term_r = 0;
+      for (j = 0; j < st; ++j)
+      {
+        if (child_clv_index < 0)
+          term_r += cp_[j] * freqs[j];                           /* likelihood.c:84-87 */
+        else if (child_is_tip)
+          term_r += cp_[j] * freqs[j] * pmat[(size_t)j * sp + n]; /* likelihood.c:231-235 */
+        else
+        {
+          double termb = 0;
+          for (k = 0; k < st; ++k) termb += pmat[(size_t)j * sp + k] * cc_[k];
+          term_r += cp_[j] * freqs[j] * termb;                   /* likelihood.c:396-404 */
+        }
+      }
+      term += term_r * p->rate_weights[i];
+    }
+    scale_factors = psc[n] + csc[n];
+    sum_w_inv += w[n];
+    if (type == PLL_ATTRIB_AB_STAMATAKIS)
+    {
+      site_lk = log(term) * w[n];
+      if (scale_factors) site_lk += scale_factors * log(PLL_SCALE_THRESHOLD);
+    }
+    else
+      site_lk = term * pow(PLL_SCALE_THRESHOLD, scale_factors);
+    logl_correction += site_lk;
+  }
+  result = asc_correction(p, logl_correction, sum_w_inv);
+  goto done;
+fail:
+  cuda_fail(cp);
+done:
+  free(clvp);
+  free(clvc);
+  free(pm);
+  free(psc);
+  free(csc);
+  return result;
+}
+
 static double run_loglikelihood(cuda_partition_t * cp, plf_lk_t * a, double * persite_lnl)
 {
   double logl = 0;
@@ -1799,10 +2010,26 @@ PLL_EXPORT double pll_compute_edge_loglikelihood(pll_partition_t * partition, un
 {
   cuda_partition_t * cp = CP(partition);
   plf_lk_t a;
+  double logl;
   if (!cp || !fill_edge_args(cp, &a, parent_clv_index, parent_scaler_index, child_clv_index, child_scaler_index,
                              matrix_index, freqs_indices))
     return -INFINITY;
-  return run_loglikelihood(cp, &a, persite_lnl);
+  logl = run_loglikelihood(cp, &a, persite_lnl);
+  if (partition->attributes & PLL_ATTRIB_AB_MASK)
+  {
+    /* src/likelihood.c:325-337, 569-581: the inner node plays "parent" on a pattern-tip edge */
+    if (a.tipchars)
+    {
+      const int ptip = parent_clv_index < partition->tips;
+      logl += asc_loglikelihood(cp, ptip ? child_clv_index : parent_clv_index,
+                                ptip ? child_scaler_index : parent_scaler_index, 0, -1, 1, (int)matrix_index,
+                                freqs_indices);
+    }
+    else
+      logl += asc_loglikelihood(cp, parent_clv_index, parent_scaler_index, (int)child_clv_index, child_scaler_index,
+                                0, (int)matrix_index, freqs_indices);
+  }
+  return logl;
 }
 
 PLL_EXPORT double pll_compute_root_loglikelihood(pll_partition_t * partition, unsigned int clv_index,
@@ -1811,8 +2038,12 @@ PLL_EXPORT double pll_compute_root_loglikelihood(pll_partition_t * partition, un
 {
   cuda_partition_t * cp = CP(partition);
   plf_lk_t a;
+  double logl;
   if (!cp || !fill_root_args(cp, &a, clv_index, scaler_index, freqs_indices)) return -INFINITY;
-  return run_loglikelihood(cp, &a, persite_lnl);
+  logl = run_loglikelihood(cp, &a, persite_lnl);
+  if (partition->attributes & PLL_ATTRIB_AB_MASK) /* src/likelihood.c:176-188 */
+    logl += asc_loglikelihood(cp, clv_index, scaler_index, -1, -1, 0, -1, freqs_indices);
+  return logl;
 }
 
 PLL_EXPORT int pll_cuda_edge_loglikelihood_async(pll_partition_t * partition, unsigned int parent_clv_index,
@@ -1822,6 +2053,11 @@ PLL_EXPORT int pll_cuda_edge_loglikelihood_async(pll_partition_t * partition, un
 {
   cuda_partition_t * cp = CP(partition);
   plf_lk_t a;
+  if (cp && (partition->attributes & PLL_ATTRIB_AB_MASK))
+  {
+    set_error(PLL_ERROR_CUDA_UNSUPPORTED, "the asynchronous entry points do not apply the ascertainment bias correction%s", NULL);
+    return PLL_FAILURE;
+  }
   if (!cp || !dev_out ||
       !fill_edge_args(cp, &a, parent_clv_index, parent_scaler_index, child_clv_index, child_scaler_index,
                       matrix_index, freqs_indices))
@@ -1843,7 +2079,7 @@ PLL_EXPORT int pll_cuda_root_loglikelihood_async(pll_partition_t * partition, un
 
 static sumtable_slot_t * sumtable_slot(cuda_partition_t * cp, const double * key, int create)
 {
-  const size_t need = (size_t)cp->pub.sites * cp->pub.rate_cats * cp->pub.states_padded;
+  const size_t need = (size_t)sites_alloc(&cp->pub) * cp->pub.rate_cats * cp->pub.states_padded;
   sumtable_slot_t * victim = &cp->sumtabs[0];
   int i;
   for (i = 0; i < MAX_SUMTABLES; ++i)
@@ -1896,7 +2132,7 @@ PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition, unsigned int par
     set_error(PLL_ERROR_PARAM_INVALID, "buffer index out of range%s", NULL);
     return PLL_FAILURE;
   }
-  a.sites = p->sites;
+  a.sites = sites_alloc(p); /* src/derivatives.c:56-58,131-133,191-193 */
   if ((p->attributes & PLL_ATTRIB_PATTERN_TIP) && (parent_clv_index < p->tips || child_clv_index < p->tips))
   {
     const int ptip = parent_clv_index < p->tips;
@@ -1946,9 +2182,18 @@ PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition, unsigned int par
   if (!(slot = sumtable_slot(cp, sumtable, 1)) || !(a.model = model_on_device(cp, params_indices))) return cuda_fail(cp);
   a.sumtable = slot->dev;
   if (!plf_update_sumtable(cp->ctx, &cp->shape, &a)) return cuda_fail(cp);
-  if (cp->sumtable_mirror &&
-      !plf_download(cp->ctx, sumtable, slot->dev, (size_t)p->sites * p->rate_cats * p->states_padded * sizeof(double)))
+  if (cp->sumtable_mirror && !plf_download(cp->ctx, sumtable, slot->dev,
+                                           (size_t)sites_alloc(p) * p->rate_cats * p->states_padded * sizeof(double)))
     return cuda_fail(cp);
+  if (p->asc_bias_alloc)
+  {
+    /* the derivative calls need the pseudo-site blocks on the host (core_derivatives.c:851-924) */
+    const size_t blk = (size_t)p->rate_cats * p->states_padded;
+    if (!slot->asc_host) slot->asc_host = (double *)malloc(p->states * blk * sizeof(double));
+    if (!slot->asc_host || !plf_download(cp->ctx, slot->asc_host, slot->dev + (size_t)p->sites * blk,
+                                         p->states * blk * sizeof(double)))
+      return cuda_fail(cp);
+  }
   return PLL_SUCCESS;
 }
 
@@ -1962,13 +2207,22 @@ static int derivative_args(cuda_partition_t * cp, plf_deriv_t * a, double branch
   {
     /* a table this library did not compute: the host bytes are the data */
     if (!sumtable || !(slot = sumtable_slot(cp, sumtable, 1)) ||
-        !plf_upload(cp->ctx, slot->dev, sumtable, (size_t)p->sites * p->rate_cats * p->states_padded * sizeof(double)))
+        !plf_upload(cp->ctx, slot->dev, sumtable,
+                    (size_t)sites_alloc(p) * p->rate_cats * p->states_padded * sizeof(double)))
     {
       cuda_fail(cp);
       return 0;
     }
+    if (p->asc_bias_alloc)
+    {
+      const size_t blk = (size_t)p->rate_cats * p->states_padded;
+      if (!slot->asc_host) slot->asc_host = (double *)malloc(p->states * blk * sizeof(double));
+      if (!slot->asc_host) return 0;
+      memcpy(slot->asc_host, sumtable + (size_t)p->sites * blk, p->states * blk * sizeof(double));
+    }
   }
-  a->sites = p->sites;
+  /* Stamatakis: the pseudo-sites are ordinary weighted sites of the sums (core_derivatives.c:733-741) */
+  a->sites = p->sites + (((p->attributes & PLL_ATTRIB_AB_MASK) == PLL_ATTRIB_AB_STAMATAKIS) ? p->states : 0);
   a->sumtable = slot->dev;
   a->pattern_weights = cp->d_pattern_weights;
   a->invariant = cp->d_invariant;
@@ -1981,6 +2235,102 @@ static int derivative_args(cuda_partition_t * cp, plf_deriv_t * a, double branch
   return 1;
 }
 
+/* Lewis / Felsenstein terms of the derivatives (src/core_derivatives.c:851-924) from the host copy of
+ * the pseudo-site sums; the pseudo-site scalers are cached until the next pll_update_partials */
+static int asc_derivatives(cuda_partition_t * cp, int parent_scaler_index, int child_scaler_index, double branch_length,
+                           const unsigned int * params_indices, const double * sumtable, double * d_f, double * dd_f)
+{
+  const pll_partition_t * p = &cp->pub;
+  const unsigned int st = p->states, sp = p->states_padded, R = p->rate_cats;
+  const int type = p->attributes & PLL_ATTRIB_AB_MASK;
+  const sumtable_slot_t * slot = sumtable_slot(cp, sumtable, 0);
+  double asc_Lk[3] = {0.0, 0.0, 0.0};
+  unsigned int sum_w_inv = 0, n, i, j;
+  double * diag;
+  if (!slot || !slot->asc_host)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "sumtable was not computed for this partition%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!cp->asc_sc_valid || cp->asc_sc_parent != parent_scaler_index || cp->asc_sc_child != child_scaler_index ||
+      cp->asc_sc_generation != cp->partials_generation)
+  {
+    if (!cp->asc_sc) cp->asc_sc = (unsigned int *)malloc((size_t)2 * st * sizeof(unsigned int));
+    if (!cp->asc_sc || !asc_download(cp, p->sites, 0, parent_scaler_index, NULL, cp->asc_sc) ||
+        !asc_download(cp, p->sites, 0, child_scaler_index, NULL, cp->asc_sc + st))
+      return cuda_fail(cp);
+    cp->asc_sc_parent = parent_scaler_index;
+    cp->asc_sc_child = child_scaler_index;
+    cp->asc_sc_generation = cp->partials_generation;
+    cp->asc_sc_valid = 1;
+  }
+  diag = (double *)malloc((size_t)R * st * 4 * sizeof(double));
+  if (!diag)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate memory for diagptable%s", NULL);
+    return PLL_FAILURE;
+  }
+  for (i = 0; i < R; ++i)
+  {
+    const double * ev = p->eigenvals[params_indices[i]];
+    const double ki = p->rates[i] / (1.0 - p->prop_invar[params_indices[i]]);
+    for (j = 0; j < st; ++j)
+    {
+      double * d = diag + ((size_t)i * st + j) * 4;
+      d[0] = exp(ev[j] * ki * branch_length);
+      d[1] = ev[j] * ki * d[0];
+      d[2] = ev[j] * ki * ev[j] * ki * d[0];
+      d[3] = 0;
+    }
+  }
+  for (n = 0; n < st; ++n)
+  {
+    const double * sum = slot->asc_host + (size_t)n * R * sp;
+    double site_lk[3] = {0, 0, 0};
+    double asc_scaling;
+    for (i = 0; i < R; ++i)
+    {
+      const double * d = diag + (size_t)i * st * 4;
+      double c[3] = {0, 0, 0};
+      for (j = 0; j < st; ++j)
+      {
+        c[0] += sum[j] * d[4 * j + 0];
+        c[1] += sum[j] * d[4 * j + 1];
+        c[2] += sum[j] * d[4 * j + 2];
+      }
+      site_lk[0] += c[0] * p->rate_weights[i];
+      site_lk[1] += c[1] * p->rate_weights[i];
+      site_lk[2] += c[2] * p->rate_weights[i];
+      sum += sp;
+    }
+    asc_scaling = pow(PLL_SCALE_THRESHOLD, (double)(cp->asc_sc[n] + cp->asc_sc[st + n]));
+    asc_Lk[0] += site_lk[0] * asc_scaling;
+    asc_Lk[1] += site_lk[1] * asc_scaling;
+    asc_Lk[2] += site_lk[2] * asc_scaling;
+    sum_w_inv += p->pattern_weights[p->sites + n];
+  }
+  free(diag);
+  if (type == PLL_ATTRIB_AB_LEWIS)
+  {
+    unsigned int pattern_weight_sum = 0;
+    for (n = 0; n < p->sites; ++n) pattern_weight_sum += p->pattern_weights[n];
+    *d_f += pattern_weight_sum * (asc_Lk[1] / (asc_Lk[0] - 1.0));
+    *dd_f += pattern_weight_sum *
+             (((asc_Lk[0] - 1.0) * asc_Lk[2] - asc_Lk[1] * asc_Lk[1]) / ((asc_Lk[0] - 1.0) * (asc_Lk[0] - 1.0)));
+  }
+  else if (type == PLL_ATTRIB_AB_FELSENSTEIN)
+  {
+    *d_f -= sum_w_inv * (asc_Lk[1] / asc_Lk[0]);
+    *dd_f -= sum_w_inv * (((asc_Lk[2] * asc_Lk[0]) - asc_Lk[1] * asc_Lk[1]) / (asc_Lk[0] * asc_Lk[0]));
+  }
+  else
+  {
+    set_error(PLL_ERROR_AB_INVALIDMETHOD, "Illegal ascertainment bias algorithm%s", NULL);
+    return PLL_FAILURE;
+  }
+  return PLL_SUCCESS;
+}
+
 PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition, int parent_scaler_index,
                                                   int child_scaler_index, double branch_length,
                                                   const unsigned int * params_indices, const double * sumtable,
@@ -1989,12 +2339,16 @@ PLL_EXPORT int pll_compute_likelihood_derivatives(pll_partition_t * partition, i
   cuda_partition_t * cp = CP(partition);
   plf_deriv_t a;
   double out[2] = {0, 0};
-  (void)parent_scaler_index; /* per-site ratios cancel the scaling (src/core_derivatives.c:825-848) */
-  (void)child_scaler_index;
+  /* per-site ratios cancel the scaling (src/core_derivatives.c:825-848); only the ascertainment
+   * bias terms need the scalers */
   if (!cp || !derivative_args(cp, &a, branch_length, params_indices, sumtable)) return PLL_FAILURE;
   if (!plf_derivatives(cp->ctx, &cp->shape, &a, NULL, out)) return cuda_fail(cp);
   *d_f = out[0];
   *dd_f = out[1];
+  if ((partition->attributes & PLL_ATTRIB_AB_MASK) &&
+      (partition->attributes & PLL_ATTRIB_AB_MASK) != PLL_ATTRIB_AB_STAMATAKIS)
+    return asc_derivatives(cp, parent_scaler_index, child_scaler_index, branch_length, params_indices, sumtable, d_f,
+                           dd_f);
   return PLL_SUCCESS;
 }
 
@@ -2033,7 +2387,7 @@ PLL_EXPORT unsigned int pll_cuda_scaler_size(const pll_partition_t * partition, 
   cuda_partition_t * cp = CP(partition);
   unsigned int n;
   if (!cp || scaler_index >= partition->scale_buffers) return 0;
-  n = partition->sites;
+  n = sites_alloc(partition);
   if (pll_repeats_enabled(partition) && partition->repeats->perscale_ids[scaler_index])
     n = partition->repeats->perscale_ids[scaler_index];
   if (partition->attributes & PLL_ATTRIB_RATE_SCALERS) n *= partition->rate_cats;

@@ -115,7 +115,9 @@ class Engine:
 
     def sumtable_alloc(self):
         # 64-byte aligned: the reference's AVX kernels use aligned stores
-        n = self.sites * self.ds.rate_cats * self.part.states_padded
+        # ascertainment bias: `states` pseudo-sites follow the alignment (src/derivatives.c:131-133)
+        asc = self.ds.states if self.part.asc_bias_alloc else 0
+        n = (self.sites + asc) * self.ds.rate_cats * self.part.states_padded
         raw = np.zeros(n + 8, dtype=np.float64)
         off = (-raw.ctypes.data % 64) // 8
         return raw[off:off + n]

@@ -251,6 +251,55 @@ def test_aa_kernels_rate_counts(reflib, cudalib, cats, per_rate):
     gpu.close()
 
 
+ASC_TYPES = {"lewis": capi.AB_LEWIS, "felsenstein": capi.AB_FELSENSTEIN, "stamatakis": capi.AB_STAMATAKIS}
+
+
+@pytest.mark.parametrize("kind,extra", [("dna", capi.PATTERN_TIP), ("dna", 0), ("aa", capi.PATTERN_TIP), ("aa", 0), ("g5", 0)])
+def test_ascertainment_bias_parity(reflib, cudalib, kind, extra):
+    """PLL_ATTRIB_AB_*: the `states` pseudo-sites go through the CLV kernels with the alignment, the
+    correction terms of logL and of the derivatives follow src/likelihood.c:24-120,190-268,342-440 and
+    src/core_derivatives.c:851-924 (reference test: test/src/asc-bias.c).  A deep tree so that the
+    pseudo-sites carry scaling factors too."""
+    ds = make_ds(kind, 120 if kind != "aa" else 160, 203, "caterpillar", seed=71)
+    ref, gpu = pair(reflib, cudalib, ds, extra | capi.AB_FLAG)
+    w = np.random.default_rng(9).integers(1, 6, size=ds.states).astype(np.uint32)
+    last = ref.ops[len(ref.ops) - 1]
+    edges = [ds.tree.root_edge, (last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index),
+             (ref.ops[0].parent_clv_index, ref.ops[0].child1_clv_index, ref.ops[0].child1_matrix_index)]
+    for name, typ in ASC_TYPES.items():
+        for lib, e in ((reflib, ref), (cudalib, gpu)):
+            assert lib.pll_set_asc_bias_type(e.p, typ) == 1, lib.errmsg
+            lib.pll_set_asc_state_weights(e.p, w.ctypes.data_as(capi.c_uint_p))
+            e.update_pmatrices()
+            e.update_partials()
+        for edge in edges:
+            l_ref, l_gpu = ref.edge_logl(edge), gpu.edge_logl(edge)
+            assert np.isfinite(l_ref)
+            assert_rel(l_gpu, l_ref, LOGL_RTOL, f"{name} edge logL {edge}")
+            st_ref, st_gpu = ref.sumtable_alloc(), gpu.sumtable_alloc()
+            ref.update_sumtable(st_ref, edge)
+            gpu.update_sumtable(st_gpu, edge)
+            for t in (0.01, 0.2):
+                d_ref, d_gpu = ref.derivatives(st_ref, t, edge), gpu.derivatives(st_gpu, t, edge)
+                for a, b in zip(d_gpu, d_ref):
+                    assert abs(a - b) <= DERIV_RTOL * max(abs(b), 1e-6 * ds.sites), (name, edge, t, d_gpu, d_ref)
+        if ds.states == ds.rate_cats:
+            # src/likelihood.c:180 locates the pseudo-sites at sites + states - rate_cats: only defined
+            # behaviour in the reference when the two counts agree (see asc_loglikelihood in pll_host.c)
+            assert_rel(gpu.root_logl(), ref.root_logl(), LOGL_RTOL, f"{name} root logL")
+        else:
+            assert np.isfinite(gpu.root_logl())
+    # correction off again: plain likelihood on a partition that carries the pseudo-sites
+    for lib, e in ((reflib, ref), (cudalib, gpu)):
+        assert lib.pll_set_asc_bias_type(e.p, 0) == 1
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL, correction off")
+    # +I is incompatible (src/models.c:500-507)
+    assert cudalib.pll_set_asc_bias_type(gpu.p, capi.AB_LEWIS) == 1
+    assert cudalib.pll_update_invariant_sites_proportion(gpu.p, 0, 0.2) == 0 and cudalib.errno == 117
+    ref.close()
+    gpu.close()
+
+
 REPEAT_CASES = [
     ("dna", 24, 400, "random", False, (0.002, 0.05)),
     ("dna", 64, 3000, "random", False, (0.002, 0.05)),
