@@ -88,6 +88,7 @@ extern "C" {
 #define PLL_ERROR_INVAR_NONEFOUND 120
 #define PLL_ERROR_AB_INVALIDMETHOD 121
 #define PLL_ERROR_AB_NOSUPPORT 122
+#define PLL_ERROR_EINVAL 130
 /* NEW: CUDA runtime / device failures */
 #define PLL_ERROR_CUDA 900
 #define PLL_ERROR_CUDA_UNSUPPORTED 901
@@ -237,6 +238,28 @@ PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
                                unsigned int tip_index,
                                const double * clv,
                                int padding);
+/* src/likelihood.c:762,639 (pll.h:741-760): marginal ancestral state probabilities of a node,
+ * ancestral[site][state]; the scratch buffers of the _extbuf variant must be non-NULL as in the
+ * reference but are not used (the temporaries live in HBM) */
+PLL_EXPORT int pll_compute_node_ancestral(pll_partition_t * partition,
+                                          unsigned int node_clv_index,
+                                          int node_scaler_index,
+                                          unsigned int other_clv_index,
+                                          int other_scaler_index,
+                                          unsigned int matrix_index,
+                                          const unsigned int * freqs_indices,
+                                          double * ancestral);
+PLL_EXPORT int pll_compute_node_ancestral_extbuf(pll_partition_t * partition,
+                                                 unsigned int node_clv_index,
+                                                 int node_scaler_index,
+                                                 unsigned int other_clv_index,
+                                                 int other_scaler_index,
+                                                 unsigned int pmatrix_index,
+                                                 const unsigned int * freqs_indices,
+                                                 double * ancestral,
+                                                 double * temp_clv,
+                                                 unsigned int * temp_scaler,
+                                                 double * ident_pmat);
 /* src/pll.c:1131 */
 PLL_EXPORT void pll_set_pattern_weights(pll_partition_t * partition,
                                         const unsigned int * pattern_weights);

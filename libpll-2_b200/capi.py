@@ -137,6 +137,8 @@ _PROTOS = {
         C.c_int,
         [PartitionP, C.c_int, C.c_int, C.c_double, c_uint_p, c_double_p, c_double_p, c_double_p],
     ),
+    "pll_compute_node_ancestral": (
+        C.c_int, [PartitionP, C.c_uint, C.c_int, C.c_uint, C.c_int, C.c_uint, c_uint_p, c_double_p]),
     "pll_set_asc_bias_type": (C.c_int, [PartitionP, C.c_int]),
     "pll_set_asc_state_weights": (None, [PartitionP, c_uint_p]),
     "pll_repeats_enabled": (C.c_int, [PartitionP]),

@@ -197,6 +197,10 @@ int plf_tip_clv_from_states(plf_ctx_t * ctx, const plf_shape_t * sh,
 int plf_tip_keys(plf_ctx_t * ctx, const unsigned char * d_seq,
                  const unsigned char * d_charmap, unsigned int sites,
                  unsigned int * d_keys);
+/* marginal ancestral probabilities from the CLV of a virtual root placed on the node
+ * (src/likelihood.c:733-760): d_out[site][state] */
+int plf_ancestral(plf_ctx_t * ctx, const plf_shape_t * sh, const double * d_clv,
+                  const double * d_model, unsigned int sites, double * d_out);
 int plf_copy_d2d(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_fill_u32(plf_ctx_t * ctx, unsigned int * d, unsigned int value,
                  size_t n);

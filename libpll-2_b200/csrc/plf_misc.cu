@@ -311,3 +311,42 @@ extern "C" int plf_fill_u32(plf_ctx_t * ctx, unsigned int * d, unsigned int valu
   plf_set_error(ctx, "plf_fill_u32: only 0 and 0xFFFFFFFF are supported");
   return 0;
 }
+
+/* ---- marginal ancestral state probabilities ------------------------------------- *
+ * anc[site][j] = sum_r clv[site][r][j] pi_r[j] w_r, normalised over j                *
+ * (src/likelihood.c:733-760); one thread per site                                    */
+__global__ void k_ancestral(const double * __restrict__ clv, const double * __restrict__ model, unsigned int sites,
+                            int R, int st, int sp, double * __restrict__ out)
+{
+  const double * weights = model + R;
+  const double * freqs = model + 3 * R;
+  for (unsigned int n = blockIdx.x * blockDim.x + threadIdx.x; n < sites; n += gridDim.x * blockDim.x)
+  {
+    const double * c = clv + (size_t)n * R * sp;
+    double * a = out + (size_t)n * st;
+    double sum = 0;
+    for (int j = 0; j < st; ++j)
+    {
+      double v = 0;
+      for (int r = 0; r < R; ++r) v += c[(size_t)r * sp + j] * freqs[(size_t)r * sp + j] * weights[r];
+      a[j] = v;
+      sum += v;
+    }
+    for (int j = 0; j < st; ++j) a[j] /= sum;
+  }
+}
+
+extern "C" int plf_ancestral(plf_ctx_t * ctx, const plf_shape_t * sh, const double * d_clv, const double * d_model,
+                             unsigned int sites, double * d_out)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  unsigned int blocks = (sites + 127) / 128;
+  const unsigned int cap = (unsigned int)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_ancestral<<<blocks, 128, 0, ctx->stream>>>(d_clv, d_model, sites, (int)sh->rate_cats, (int)sh->states,
+                                              (int)sh->states_padded, d_out);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}

@@ -2075,6 +2075,139 @@ PLL_EXPORT int pll_cuda_root_loglikelihood_async(pll_partition_t * partition, un
   return plf_loglikelihood(cp->ctx, &cp->shape, &a, dev_out, NULL) ? PLL_SUCCESS : cuda_fail(cp);
 }
 
+/* ---- ancestral states --------------------------------------------------------------------- */
+
+/* src/likelihood.c:639-760: CLV of a virtual root placed ON `node` (identity matrix towards the
+ * node, P-matrix towards `other`), then per-site posterior state probabilities.  The caller's
+ * scratch buffers of the _extbuf variant are host memory and are not needed here: the temporary
+ * CLV, scaler and identity matrix live in HBM for the duration of the call. */
+PLL_EXPORT int pll_compute_node_ancestral_extbuf(pll_partition_t * partition, unsigned int node_clv_index,
+                                                 int node_scaler_index, unsigned int other_clv_index,
+                                                 int other_scaler_index, unsigned int pmatrix_index,
+                                                 const unsigned int * freqs_indices, double * ancestral,
+                                                 double * temp_clv, unsigned int * temp_scaler, double * ident_pmat)
+{
+  cuda_partition_t * cp = CP(partition);
+  const pll_partition_t * p = partition;
+  unsigned int st, sp, R, i, j;
+  size_t clv_doubles, sc_entries, pm_doubles;
+  double * d_tmp = NULL, * d_ident = NULL, * d_anc = NULL, * h_ident = NULL;
+  unsigned int * d_sc = NULL;
+  const double * d_model;
+  plf_op_t op;
+  unsigned int level_start[2] = {0, 1};
+  int ok = 0;
+  if (!partition || !ancestral)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "Parameter value is NULL!%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!temp_clv || !temp_scaler || !ident_pmat)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "NULL buffer pointer%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!cp) return PLL_FAILURE;
+  if (pll_repeats_enabled(partition))
+  {
+    set_error(PLL_ERROR_EINVAL, "Site repeats are not compatible with ancestral state reconstruction!%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (node_clv_index >= p->nodes || other_clv_index >= p->nodes || pmatrix_index >= p->prob_matrices ||
+      node_scaler_index >= (int)p->scale_buffers || other_scaler_index >= (int)p->scale_buffers ||
+      !p->clv[node_clv_index])
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "buffer index out of range or CLV never set%s", NULL);
+    return PLL_FAILURE;
+  }
+  st = p->states;
+  sp = p->states_padded;
+  R = p->rate_cats;
+  clv_doubles = (size_t)sites_alloc(p) * R * sp;
+  sc_entries = (size_t)sites_alloc(p) * ((p->attributes & PLL_ATTRIB_RATE_SCALERS) ? R : 1);
+  pm_doubles = (size_t)R * st * sp + (size_t)(sp - st) * sp;
+  h_ident = (double *)calloc(pm_doubles, sizeof(double));
+  d_tmp = (double *)plf_alloc(cp->ctx, clv_doubles * sizeof(double), 0);
+  d_sc = (unsigned int *)plf_alloc(cp->ctx, sc_entries * sizeof(unsigned int) + BULK_PAD, 1);
+  d_ident = (double *)plf_alloc(cp->ctx, pm_doubles * sizeof(double), 0);
+  d_anc = (double *)plf_alloc(cp->ctx, (size_t)p->sites * st * sizeof(double), 0);
+  if (!h_ident || !d_tmp || !d_sc || !d_ident || !d_anc)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate memory%s", NULL);
+    goto done;
+  }
+  for (i = 0; i < R; ++i)
+    for (j = 0; j < st; ++j) h_ident[((size_t)i * st + j) * sp + j] = 1.0;
+  if (!plf_upload(cp->ctx, d_ident, h_ident, pm_doubles * sizeof(double))) goto fail;
+
+  memset(&op, 0, sizeof(op));
+  op.parent_clv = d_tmp;
+  op.parent_scaler = d_sc;
+  op.nsites = sites_alloc(p);
+  if (other_clv_index < p->tips && (p->attributes & PLL_ATTRIB_PATTERN_TIP))
+  {
+    /* src/likelihood.c:692-706: the tip side takes the P-matrix, the node the identity */
+    if (!cp->d_tipchars || !cp->d_tipchars[other_clv_index] || !tipmap_on_device(cp))
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "tip states were never set%s", NULL);
+      goto done;
+    }
+    op.kind = PLF_OP_TI;
+    op.left_tip = cp->d_tipchars[other_clv_index];
+    op.left_matrix = p->pmatrix[pmatrix_index];
+    op.right_clv = p->clv[node_clv_index];
+    op.right_matrix = d_ident;
+    op.right_scaler = node_scaler_index >= 0 ? p->scale_buffer[node_scaler_index] : NULL;
+  }
+  else
+  {
+    if (!p->clv[other_clv_index])
+    {
+      set_error(PLL_ERROR_PARAM_INVALID, "CLV was never set%s", NULL);
+      goto done;
+    }
+    op.kind = PLF_OP_II;
+    op.left_clv = p->clv[node_clv_index];
+    op.left_matrix = d_ident;
+    op.left_scaler = node_scaler_index >= 0 ? p->scale_buffer[node_scaler_index] : NULL;
+    op.right_clv = p->clv[other_clv_index];
+    op.right_matrix = p->pmatrix[pmatrix_index];
+    op.right_scaler = other_scaler_index >= 0 ? p->scale_buffer[other_scaler_index] : NULL;
+  }
+  if (!(d_model = model_on_device(cp, freqs_indices)) ||
+      !plf_update_partials(cp->ctx, &cp->shape, &op, 1, level_start, 1, cp->d_tipmap, p->maxstates) ||
+      !plf_ancestral(cp->ctx, &cp->shape, d_tmp, d_model, p->sites, d_anc) ||
+      !plf_download(cp->ctx, ancestral, d_anc, (size_t)p->sites * st * sizeof(double)))
+    goto fail;
+  ok = 1;
+  goto done;
+fail:
+  cuda_fail(cp);
+done:
+  free(h_ident);
+  if (cp)
+  {
+    plf_free(cp->ctx, d_tmp);
+    plf_free(cp->ctx, d_sc);
+    plf_free(cp->ctx, d_ident);
+    plf_free(cp->ctx, d_anc);
+  }
+  return ok ? PLL_SUCCESS : PLL_FAILURE;
+}
+
+/* src/likelihood.c:762-823 */
+PLL_EXPORT int pll_compute_node_ancestral(pll_partition_t * partition, unsigned int node_clv_index,
+                                          int node_scaler_index, unsigned int other_clv_index,
+                                          int other_scaler_index, unsigned int matrix_index,
+                                          const unsigned int * freqs_indices, double * ancestral)
+{
+  double dummy_clv = 0, dummy_pmat = 0;
+  unsigned int dummy_scaler = 0;
+  return pll_compute_node_ancestral_extbuf(partition, node_clv_index, node_scaler_index, other_clv_index,
+                                           other_scaler_index, matrix_index, freqs_indices, ancestral, &dummy_clv,
+                                           &dummy_scaler, &dummy_pmat);
+}
+
 /* ---- sumtable and derivatives ---------------------------------------------------------- */
 
 static sumtable_slot_t * sumtable_slot(cuda_partition_t * cp, const double * key, int create)

@@ -251,6 +251,36 @@ def test_aa_kernels_rate_counts(reflib, cudalib, cats, per_rate):
     gpu.close()
 
 
+@pytest.mark.parametrize("kind,extra,per_rate", [("dna", capi.PATTERN_TIP, False), ("dna", 0, False), ("dna", 0, True),
+                                                  ("aa", capi.PATTERN_TIP, False), ("g7", 0, False)])
+def test_node_ancestral_parity(reflib, cudalib, kind, extra, per_rate):
+    """pll_compute_node_ancestral (src/likelihood.c:762): posterior state probabilities per site at an
+    inner node, against an inner neighbour and against a tip neighbour; deep tree => scaled CLVs."""
+    ds = make_ds(kind, 150, 97, "caterpillar", seed=81)
+    ref, gpu = pair(reflib, cudalib, ds, extra, per_rate)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    t = ds.tree
+    last, first = ref.ops[len(ref.ops) - 1], ref.ops[0]
+    cases = [(t.root_edge[0], t.root_edge[1], t.root_edge[2]),
+             (last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index),
+             (first.parent_clv_index, first.child1_clv_index, first.child1_matrix_index)]
+    for node, other, m in cases:
+        out = []
+        for lib, e in ((reflib, ref), (cudalib, gpu)):
+            anc = np.zeros(ds.sites * ds.states)
+            rc = lib.pll_compute_node_ancestral(e.p, node, t.scaler_of.get(node, -1), other, t.scaler_of.get(other, -1),
+                                                m, e.params_indices.ctypes.data_as(capi.c_uint_p),
+                                                anc.ctypes.data_as(capi.c_double_p))
+            assert rc == 1, lib.errmsg
+            out.append(anc.reshape(ds.sites, ds.states))
+        np.testing.assert_allclose(out[1].sum(axis=1), 1.0, rtol=1e-12)
+        np.testing.assert_allclose(out[1], out[0], rtol=1e-10, atol=1e-300)
+    ref.close()
+    gpu.close()
+
+
 ASC_TYPES = {"lewis": capi.AB_LEWIS, "felsenstein": capi.AB_FELSENSTEIN, "stamatakis": capi.AB_STAMATAKIS}
 
 
