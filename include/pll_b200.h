@@ -89,6 +89,8 @@ extern "C" {
 #define PLL_ERROR_AB_INVALIDMETHOD 121
 #define PLL_ERROR_AB_NOSUPPORT 122
 #define PLL_ERROR_EINVAL 130
+#define PLL_ERROR_MSA_EMPTY 131
+#define PLL_ERROR_MSA_MAP_INVALID 132
 /* NEW: CUDA runtime / device failures */
 #define PLL_ERROR_CUDA 900
 #define PLL_ERROR_CUDA_UNSUPPORTED 901
@@ -238,6 +240,26 @@ PLL_EXPORT int pll_set_tip_clv(pll_partition_t * partition,
                                unsigned int tip_index,
                                const double * clv,
                                int padding);
+/* src/pll.h:347-354 */
+typedef struct pll_msa_s
+{
+  int count;
+  int length;
+  char ** sequence;
+  char ** label;
+} pll_msa_t;
+
+/* src/compress.c:391,399 (pll.h:1095-1105): site pattern compression, on the device
+ * (plf_compress.cu); identical output to the reference: unique columns in ascending order
+ * written over `sequence`, their weights returned (caller frees), *length updated */
+PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence,
+                                                     const pll_state_t * map,
+                                                     int count,
+                                                     int * length);
+PLL_EXPORT unsigned int * pll_compress_site_patterns_msa(pll_msa_t * msa,
+                                                         const pll_state_t * map,
+                                                         unsigned int * site_pattern_map);
+
 /* src/likelihood.c:762,639 (pll.h:741-760): marginal ancestral state probabilities of a node,
  * ancestral[site][state]; the scratch buffers of the _extbuf variant must be non-NULL as in the
  * reference but are not used (the temporaries live in HBM) */

@@ -139,6 +139,8 @@ _PROTOS = {
     ),
     "pll_compute_node_ancestral": (
         C.c_int, [PartitionP, C.c_uint, C.c_int, C.c_uint, C.c_int, C.c_uint, c_uint_p, c_double_p]),
+    "pll_compress_site_patterns": (c_uint_p, [C.POINTER(C.c_char_p), C.POINTER(pll_state_t), C.c_int, C.POINTER(C.c_int)]),
+    "pll_compress_site_patterns_msa": (c_uint_p, [C.c_void_p, C.POINTER(pll_state_t), c_uint_p]),
     "pll_set_asc_bias_type": (C.c_int, [PartitionP, C.c_int]),
     "pll_set_asc_state_weights": (None, [PartitionP, c_uint_p]),
     "pll_repeats_enabled": (C.c_int, [PartitionP]),

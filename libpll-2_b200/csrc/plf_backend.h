@@ -201,6 +201,14 @@ int plf_tip_keys(plf_ctx_t * ctx, const unsigned char * d_seq,
  * (src/likelihood.c:733-760): d_out[site][state] */
 int plf_ancestral(plf_ctx_t * ctx, const plf_shape_t * sh, const double * d_clv,
                   const double * d_model, unsigned int sites, double * d_out);
+/* site pattern compression (src/compress.c:171-410) on `count` host strings of `n`
+ * characters; see plf_compress.cu.  1 ok, 0 CUDA failure, -1 character not in the map */
+int plf_compress_patterns(plf_ctx_t * ctx, char ** h_rows, unsigned int count,
+                          unsigned int n, const unsigned char * h_charmap,
+                          const unsigned char * h_inv_charmap,
+                          unsigned int * h_weight, unsigned int * h_site_pattern,
+                          unsigned int * compressed, unsigned int * bad_seq,
+                          unsigned int * bad_pos);
 int plf_copy_d2d(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_fill_u32(plf_ctx_t * ctx, unsigned int * d, unsigned int value,
                  size_t n);

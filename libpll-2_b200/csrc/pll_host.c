@@ -2498,6 +2498,127 @@ PLL_EXPORT int pll_cuda_likelihood_derivatives_async(pll_partition_t * partition
   return plf_derivatives(cp->ctx, &cp->shape, &a, dev_out2, NULL) ? PLL_SUCCESS : cuda_fail(cp);
 }
 
+/* ---- site pattern compression (the step before the path) ------------------------------------ */
+
+/* src/compress.c:171-410.  Same contract: `sequence` is overwritten with the unique columns in
+ * ascending order of their encoded characters (decoded back with the lowest-ASCII representative,
+ * '-' for gaps), *length becomes their number, the returned malloc'ed array holds their weights and
+ * site_pattern_map[site] (optional) the pattern every original site went to.  Runs on the device
+ * selected by pll_cuda_set_device() / $PLL_CUDA_DEVICE / $LOCAL_RANK. */
+static unsigned int * compress_site_patterns(char ** sequence, const pll_state_t * map, int count, int * length,
+                                             unsigned int * site_pattern_map)
+{
+  unsigned char charmap[PLL_ASCII_SIZE], inv_charmap[PLL_ASCII_SIZE];
+  pll_state_t max = 0;
+  plf_ctx_t * ctx = NULL;
+  unsigned int * weight = NULL, * fitted;
+  unsigned int compressed = 0, bad_seq = 0, bad_pos = 0;
+  char err[256] = "";
+  int i, rc;
+  if (!count)
+  {
+    set_error(PLL_ERROR_MSA_EMPTY, "Number of sequences must be greater than 0.%s", NULL);
+    return NULL;
+  }
+  if (!map)
+  {
+    set_error(PLL_ERROR_MSA_MAP_INVALID, "Map is undefined.%s", NULL);
+    return NULL;
+  }
+  if (map[0])
+  {
+    set_error(PLL_ERROR_MSA_MAP_INVALID, "'0' cannot be used as a state.%s", NULL);
+    return NULL;
+  }
+  for (i = 0; i < PLL_ASCII_SIZE; ++i)
+    if (map[i] > max) max = map[i];
+  if (max >= PLL_ASCII_SIZE)
+  {
+    /* states outside the byte range: number the distinct values in order of first use
+     * (src/compress.c:99-122) */
+    pll_state_t seen[PLL_ASCII_SIZE];
+    unsigned char k = 1;
+    int j;
+    memcpy(seen, map, sizeof(seen));
+    memset(charmap, 0, sizeof(charmap));
+    for (i = 0; i < PLL_ASCII_SIZE; ++i)
+      if (seen[i])
+      {
+        charmap[i] = k;
+        for (j = i + 1; j < PLL_ASCII_SIZE; ++j)
+          if (seen[i] == seen[j])
+          {
+            charmap[j] = k;
+            seen[j] = 0;
+          }
+        ++k;
+      }
+  }
+  else
+    for (i = 0; i < PLL_ASCII_SIZE; ++i) charmap[i] = (unsigned char)map[i];
+  memset(inv_charmap, 0, sizeof(inv_charmap));
+  for (i = 0; i < PLL_ASCII_SIZE; ++i)
+    if (map[i] && (!inv_charmap[charmap[i]] || i == '-')) inv_charmap[charmap[i]] = (unsigned char)i;
+
+  if (*length <= 0)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "alignment length must be positive%s", NULL);
+    return NULL;
+  }
+  weight = (unsigned int *)malloc((size_t)(*length) * sizeof(unsigned int));
+  if (!weight)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate space for storing site weights.%s", NULL);
+    return NULL;
+  }
+  if (!plf_ctx_create(pick_device(), 0, &ctx, err, sizeof(err)))
+  {
+    set_error(PLL_ERROR_CUDA, "CUDA: %s", err);
+    free(weight);
+    return NULL;
+  }
+  rc = plf_compress_patterns(ctx, sequence, (unsigned int)count, (unsigned int)*length, charmap, inv_charmap, weight,
+                             site_pattern_map, &compressed, &bad_seq, &bad_pos);
+  if (rc == 1)
+  {
+    for (i = 0; i < count; ++i) sequence[i][compressed] = 0;
+    *length = (int)compressed;
+    fitted = (unsigned int *)malloc((size_t)compressed * sizeof(unsigned int));
+    if (fitted)
+    {
+      memcpy(fitted, weight, (size_t)compressed * sizeof(unsigned int));
+      free(weight);
+      weight = fitted;
+    }
+  }
+  else
+  {
+    if (rc == -1)
+    {
+      pll_errno = PLL_ERROR_TIPDATA_ILLEGALSTATE;
+      snprintf(pll_errmsg, 200, "Cannot encode character %c at sequence %d position %d.", sequence[bad_seq][bad_pos],
+               (int)bad_seq + 1, (int)bad_pos + 1);
+    }
+    else
+      set_error(PLL_ERROR_CUDA, "CUDA: %s", plf_last_error(ctx));
+    free(weight);
+    weight = NULL;
+  }
+  plf_ctx_destroy(ctx);
+  return weight;
+}
+
+PLL_EXPORT unsigned int * pll_compress_site_patterns(char ** sequence, const pll_state_t * map, int count, int * length)
+{
+  return compress_site_patterns(sequence, map, count, length, NULL);
+}
+
+PLL_EXPORT unsigned int * pll_compress_site_patterns_msa(pll_msa_t * msa, const pll_state_t * map,
+                                                         unsigned int * site_pattern_map)
+{
+  return compress_site_patterns(msa->sequence, map, msa->count, &msa->length, site_pattern_map);
+}
+
 /* ---- explicit reads of device-resident buffers ---------------------------------------------- */
 
 PLL_EXPORT int pll_cuda_download_clv(const pll_partition_t * partition, unsigned int clv_index, double * host_out)
