@@ -91,6 +91,13 @@ extern "C" {
 #define PLL_ERROR_EINVAL 130
 #define PLL_ERROR_MSA_EMPTY 131
 #define PLL_ERROR_MSA_MAP_INVALID 132
+#define PLL_ERROR_TREE_INVALID 133
+#define PLL_ERROR_FILE_OPEN 100
+#define PLL_ERROR_NEWICK_SYNTAX 111
+
+/* src/pll.h:147-148 */
+#define PLL_TREE_TRAVERSE_POSTORDER 1
+#define PLL_TREE_TRAVERSE_PREORDER 2
 /* NEW: CUDA runtime / device failures */
 #define PLL_ERROR_CUDA 900
 #define PLL_ERROR_CUDA_UNSUPPORTED 901
@@ -519,6 +526,98 @@ PLL_EXPORT int pll_cuda_host_eigen(unsigned int states, unsigned int states_padd
                                    const double * freqs,
                                    double * eigenvecs, double * inv_eigenvecs,
                                    double * eigenvals);
+
+/* ---- tree structures and operation-list producers (pll_tree.c; host only) ------------------ */
+
+/* src/pll.h:388-438: same layouts */
+typedef struct pll_unode_s
+{
+  char * label;
+  double length;
+  unsigned int node_index;
+  unsigned int clv_index;
+  int scaler_index;
+  unsigned int pmatrix_index;
+  struct pll_unode_s * next;
+  struct pll_unode_s * back;
+  void * data;
+} pll_unode_t;
+
+typedef struct pll_utree_s
+{
+  unsigned int tip_count;
+  unsigned int inner_count;
+  unsigned int edge_count;
+  int binary;
+  pll_unode_t ** nodes;
+  pll_unode_t * vroot;
+} pll_utree_t;
+
+typedef struct pll_rnode_s
+{
+  char * label;
+  double length;
+  unsigned int node_index;
+  unsigned int clv_index;
+  int scaler_index;
+  unsigned int pmatrix_index;
+  struct pll_rnode_s * left;
+  struct pll_rnode_s * right;
+  struct pll_rnode_s * parent;
+  void * data;
+} pll_rnode_t;
+
+typedef struct pll_rtree_s
+{
+  unsigned int tip_count;
+  unsigned int inner_count;
+  unsigned int edge_count;
+  pll_rnode_t ** nodes;
+  pll_rnode_t * root;
+} pll_rtree_t;
+
+/* src/parse_utree.y (pll.h:907-937): hand-written recursive-descent reader of the same grammar */
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick(const char * filename);
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick_rooted(const char * filename);
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick_unroot(const char * filename);
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick_string(const char * s);
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick_string_rooted(const char * s);
+PLL_EXPORT pll_utree_t * pll_utree_parse_newick_string_unroot(const char * s);
+PLL_EXPORT pll_unode_t * pll_utree_unroot_inplace(pll_unode_t * root);
+PLL_EXPORT void pll_utree_destroy(pll_utree_t * tree, void (*cb_destroy)(void *));
+PLL_EXPORT void pll_utree_reset_template_indices(pll_unode_t * node, unsigned int tip_count);
+PLL_EXPORT void pll_utree_graph_destroy(pll_unode_t * root, void (*cb_destroy)(void *));
+PLL_EXPORT pll_utree_t * pll_utree_wraptree(pll_unode_t * root, unsigned int tip_count);
+PLL_EXPORT pll_utree_t * pll_utree_wraptree_multi(pll_unode_t * root, unsigned int tip_count,
+                                                  unsigned int inner_count);
+PLL_EXPORT int pll_utree_is_rooted(const pll_utree_t * tree);
+/* src/utree.c:305-463 (pll.h:943-977) */
+PLL_EXPORT char * pll_utree_export_newick(const pll_unode_t * root,
+                                          char * (*cb_serialize)(const pll_unode_t *));
+PLL_EXPORT char * pll_utree_export_newick_rooted(const pll_unode_t * root, double root_brlen);
+PLL_EXPORT int pll_utree_traverse(pll_unode_t * root, int traversal, int (*cbtrav)(pll_unode_t *),
+                                  pll_unode_t ** outbuffer, unsigned int * trav_size);
+PLL_EXPORT void pll_utree_create_operations(pll_unode_t * const * trav_buffer,
+                                            unsigned int trav_buffer_size, double * branches,
+                                            unsigned int * pmatrix_indices, pll_operation_t * ops,
+                                            unsigned int * matrix_count, unsigned int * ops_count);
+PLL_EXPORT int pll_utree_check_integrity(const pll_utree_t * root);
+PLL_EXPORT int pll_utree_every(pll_utree_t * tree, int (*cb)(const pll_utree_t *, const pll_unode_t *));
+/* src/parse_rtree.y, src/rtree.c (pll.h:890-905, 1005-1030) */
+PLL_EXPORT pll_rtree_t * pll_rtree_parse_newick(const char * filename);
+PLL_EXPORT pll_rtree_t * pll_rtree_parse_newick_string(const char * s);
+PLL_EXPORT void pll_rtree_destroy(pll_rtree_t * root, void (*cb_destroy)(void *));
+PLL_EXPORT void pll_rtree_reset_template_indices(pll_rnode_t * node, unsigned int tip_count);
+PLL_EXPORT void pll_rtree_graph_destroy(pll_rnode_t * root, void (*cb_destroy)(void *));
+PLL_EXPORT pll_rtree_t * pll_rtree_wraptree(pll_rnode_t * root, unsigned int tip_count);
+PLL_EXPORT char * pll_rtree_export_newick(const pll_rnode_t * root,
+                                          char * (*cb_serialize)(const pll_rnode_t *));
+PLL_EXPORT int pll_rtree_traverse(pll_rnode_t * root, int traversal, int (*cbtrav)(pll_rnode_t *),
+                                  pll_rnode_t ** outbuffer, unsigned int * trav_size);
+PLL_EXPORT void pll_rtree_create_operations(pll_rnode_t * const * trav_buffer,
+                                            unsigned int trav_buffer_size, double * branches,
+                                            unsigned int * pmatrix_indices, pll_operation_t * ops,
+                                            unsigned int * matrix_count, unsigned int * ops_count);
 
 #ifdef __cplusplus
 }

@@ -75,3 +75,56 @@ def test_compress_rejects_unmapped_character(reflib, cudalib):
     assert cudalib.errno == 114 and "sequence 2 position 7" in cudalib.errmsg
     assert run(reflib, seqs, "pll_map_nt", False) is None
     assert reflib.errno == 114 and "sequence 2 position 7" in reflib.errmsg
+
+
+# ---- the reference's own golden file (test/src/compress-patterns.c -> test/out/compress-patterns.out) ----
+
+def odd7_map():
+    m = (capi.pll_state_t * 256)()
+    for ch in "*-?":
+        m[ord(ch)] = 0x3F
+    for k, v in enumerate([0x01, 0x02, 0x04, 0x08, 0x0C, 0x10, 0x20]):
+        m[ord("A") + k] = v
+        m[ord("a") + k] = v
+    return m
+
+
+def golden_blocks():
+    import os
+    import re
+
+    text = open(os.path.join(os.path.dirname(__file__), "golden", "compress-patterns.out")).read()
+    for blk in text.split("* TEST: ")[1:]:
+        head = blk.splitlines()[0]
+        dt = re.search(r"DATATYPE = (\w+)", head).group(1)
+        backmap = "BACKMAP = YES" in head
+        orig = re.search(r"ORIGINAL MSA \((\d+)\):\n((?:.+\n)+)", blk).group(2).split()
+        comp = re.search(r"COMPRESSED MSA \((\d+)\):\n((?:.+\n)+)", blk).group(2).split()
+        weights = [int(x) for x in re.search(r"PATTERN WEIGHTS: ([\d ]+)", blk).group(1).split()]
+        smap = re.search(r"SITE-TO-PATTERN MAP: ([\d ]+)", blk)
+        yield dt, backmap, orig, comp, weights, ([int(x) for x in smap.group(1).split()] if smap else None)
+
+
+def run_golden(lib, dt, backmap, orig):
+    seqs = [s.encode() for s in orig]
+    count, length = len(seqs), len(seqs[0])
+    bufs = [C.create_string_buffer(s, length + 1) for s in seqs]
+    arr = (C.c_char_p * count)(*[C.cast(b, C.c_char_p) for b in bufs])
+    m = {"DNA": lambda: lib.map("pll_map_nt"), "AA": lambda: lib.map("pll_map_aa"), "ODD7": odd7_map}[dt]()
+    site_map = np.zeros(length, dtype=np.uint32)
+    msa = Msa(count, length, C.cast(arr, C.POINTER(C.c_char_p)), None)
+    w = lib.pll_compress_site_patterns_msa(C.byref(msa), m, site_map.ctypes.data_as(capi.c_uint_p) if backmap else None)
+    assert w, lib.errmsg
+    n = msa.length
+    return [b.raw[:n].decode() for b in bufs], list(np.ctypeslib.as_array(w, shape=(n,))), list(site_map)
+
+
+def test_compress_reference_golden_file(cudalib):
+    n = 0
+    for dt, backmap, orig, comp, weights, smap in golden_blocks():
+        got_comp, got_w, got_map = run_golden(cudalib, dt, backmap, orig)
+        assert got_comp == comp and got_w == weights, (dt, backmap)
+        if smap is not None:
+            assert got_map == smap, (dt, backmap)
+        n += 1
+    assert n == 6

@@ -484,3 +484,51 @@ def test_oracle_port_agrees_with_cuda(oracle, cudalib):
         assert np.array_equal(bits(gpu.clv(op.parent_clv_index)), bits(clv[op.parent_clv_index]))
         assert np.array_equal(gpu.scaler(op.parent_scaler_index), scal[op.parent_scaler_index])
     gpu.close()
+
+
+def test_newick_to_loglikelihood_end_to_end(reflib, cudalib):
+    """The call sequence of examples/newick-fasta-unrooted: Newick string -> pll_utree_traverse ->
+    pll_utree_create_operations (this library's tree layer, pll_tree.c) -> P-matrices, CLV updates and the
+    edge log-likelihood at the virtual root, on the CUDA engine and on the reference with the same lists."""
+    import ctypes as C
+    import test_tree_cpu as tt
+
+    own = tt.bind(C.CDLL(pkg.LIB_PATH), True)
+    rng = np.random.default_rng(91)
+    tips, sites = 37, 1201
+    tree = own.pll_utree_parse_newick_string(tt.random_newick(rng, tips).encode())
+    assert tree
+    t = tree.contents
+    n_nodes = t.tip_count + t.inner_count
+    buf = (C.POINTER(tt.UNode) * n_nodes)()
+    size = C.c_uint(0)
+    assert own.pll_utree_traverse(t.vroot, 1, tt.UCB(lambda n: 1), buf, C.byref(size)) == 1
+    ops = (capi.Operation * n_nodes)()
+    branches = (C.c_double * n_nodes)()
+    pm = (C.c_uint * n_nodes)()
+    n_mat, n_ops = C.c_uint(0), C.c_uint(0)
+    own.pll_utree_create_operations(buf, size.value, branches, pm, ops, C.byref(n_mat), C.byref(n_ops))
+    assert n_ops.value == tips - 2 and n_mat.value == 2 * tips - 3
+    seqs = synth.mutate_alignment(tips, sites, rng, synth.DNA_CODES, synth.DNA_AMBIG)
+    rates = synth.gamma_rates(0.8, 4)
+    params = np.zeros(4, dtype=np.uint32)
+    root = t.vroot.contents
+    logl = []
+    for lib, arch in ((reflib, capi.ARCH_AVX2), (cudalib, capi.ARCH_CUDA)):
+        p = lib.pll_partition_create(tips, tips - 2, 4, sites, 1, 2 * tips - 3, 4, tips - 2, arch | capi.PATTERN_TIP)
+        assert p, lib.errmsg
+        lib.pll_set_frequencies(p, 0, synth.GTR_FREQS.ctypes.data_as(capi.c_double_p))
+        lib.pll_set_subst_params(p, 0, synth.GTR_RATES.ctypes.data_as(capi.c_double_p))
+        lib.pll_set_category_rates(p, rates.ctypes.data_as(capi.c_double_p))
+        for i in range(tips):
+            label = t.nodes[i].contents.label.decode()           # tips are t0..tN-1 in the Newick string
+            assert lib.pll_set_tip_states(p, t.nodes[i].contents.clv_index, lib.map("pll_map_nt"), seqs[int(label[1:])]) == 1
+        assert lib.pll_update_prob_matrices(p, params.ctypes.data_as(capi.c_uint_p), pm, branches, n_mat.value) == 1
+        lib.pll_update_partials(p, ops, n_ops.value)
+        logl.append(lib.pll_compute_edge_loglikelihood(p, root.clv_index, root.scaler_index, root.back.contents.clv_index,
+                                                       root.back.contents.scaler_index, root.pmatrix_index,
+                                                       params.ctypes.data_as(capi.c_uint_p), None))
+        lib.pll_partition_destroy(p)
+    own.pll_utree_destroy(tree, None)
+    assert np.isfinite(logl[0]) and logl[0] < 0
+    assert_rel(logl[1], logl[0], LOGL_RTOL, "edge logL from a Newick tree")
