@@ -443,7 +443,7 @@ int plf_sumtable_as_clv(plf_ctx * ctx, const plf_shape_t * sh, const plf_sumtabl
   const unsigned int kind = a->tipchars ? PLF_OP_TI : PLF_OP_II;
   if (st == 4)
     return plf_launch_dna_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
-                                contiguous);
+                                contiguous, nullptr, 0);
   return plf_launch_aa_mma_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
                                  d_tipmap, maxstates, contiguous);
 }

@@ -20,6 +20,7 @@ struct plf_ctx
   int dna_occupancy[3][6]; /* resident CTAs per SM of the DNA CLV kernels [kind][log2 rates] */
   int dna_stream_occupancy[2][6];
   int dna_tt_bulk_occupancy[4];
+  int dna_balanced_occupancy[6];
   int dna_stream;          /* -1 = read PLF_DNA_STREAM / PLF_DNA_STAGES on first use */
   int dna_stages;
   size_t aa_smem_set[2];
@@ -60,7 +61,9 @@ int plf_launch_aa_mma_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned
                             unsigned int rate_cats, int per_rate, unsigned int max_sites,
                             const unsigned long long * d_tipmap, unsigned int maxstates, int contiguous);
 int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
-                         unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous);
+                         unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous,
+                         const unsigned int * d_tile_prefix, unsigned int total_tiles);
+unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats);
 
 /* 4-state fast paths (plf_edge_dna.cu); the lk/derivative ones return -1 when the call is not eligible */
 struct plf_lk;

@@ -425,10 +425,16 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
 {
   if (!nops) return 1;
   PLF_CHECK(ctx, cudaSetDevice(ctx->device));
-  plf_op_t * d_ops = (plf_op_t *)plf_ws_reserve(ctx, &ctx->ws_ops, (size_t)nops * sizeof(plf_op_t));
+  /* workspace: the op descriptors, then one tile-prefix array per (level, kind) run of gathering
+   * 4-state inner-inner ops (site repeats; see k_clv_dna_ii_balanced) */
+  const size_t prefix_entries = (size_t)nops + 3 * (size_t)nlevels + 1;
+  const size_t ops_bytes = (size_t)nops * sizeof(plf_op_t);
+  plf_op_t * d_ops = (plf_op_t *)plf_ws_reserve(ctx, &ctx->ws_ops, ops_bytes + prefix_entries * sizeof(unsigned int));
   if (!d_ops) return 0;
-  PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_ops, (size_t)nops * sizeof(plf_op_t), cudaMemcpyHostToDevice,
-                                 ctx->stream));
+  unsigned int * d_prefix = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(d_ops) + ops_bytes);
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_ops, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned int * h_prefix = nullptr;
+  size_t prefix_used = 0;
   const int R = (int)sh->rate_cats;
   const int one_rate = is_pow2(sh->rate_cats) && sh->rate_cats <= 32;
   const int L = one_rate ? R : 1;
@@ -459,9 +465,32 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
           if (h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id) contiguous = 0;
           ++j;
         }
+        const unsigned int * d_run_prefix = nullptr;
+        unsigned int total_tiles = 0;
+        if (!contiguous && h_ops[i].kind == PLF_OP_II && j - i > 1)
+        {
+          if (!h_prefix) h_prefix = (unsigned int *)malloc(prefix_entries * sizeof(unsigned int));
+          if (h_prefix && prefix_used + (j - i) + 1 <= prefix_entries)
+          {
+            unsigned int * pre = h_prefix + prefix_used;
+            for (unsigned int k = i; k < j; ++k)
+            {
+              pre[k - i] = total_tiles;
+              total_tiles += plf_dna_balanced_tiles(h_ops[k].nsites, sh->rate_cats);
+            }
+            pre[j - i] = total_tiles;
+            if (cudaMemcpyAsync(d_prefix + prefix_used, pre, (size_t)(j - i + 1) * sizeof(unsigned int),
+                                cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess)
+              d_run_prefix = d_prefix + prefix_used;
+            prefix_used += (j - i) + 1;
+          }
+        }
         if (run_sites && !plf_launch_dna_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
-                                               sh->per_rate_scalers, run_sites, contiguous))
+                                               sh->per_rate_scalers, run_sites, contiguous, d_run_prefix, total_tiles))
+        {
+          free(h_prefix);
           return 0;
+        }
         i = j;
       }
       continue;
@@ -548,5 +577,6 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
     plf_count_launch();
     PLF_CHECK(ctx, cudaGetLastError());
   }
+  free(h_prefix);
   return 1;
 }

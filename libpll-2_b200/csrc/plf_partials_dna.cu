@@ -138,6 +138,106 @@ k_clv_dna_ii(const plf_op_t * __restrict__ ops, int per_rate)
   }
 }
 
+/* ---- inner-inner under site repeats: ops of very different sizes in one launch ---- *
+ * The ops of a level are compressed to their own class counts (a few dozen to all the   *
+ * sites), so giving every op the same share of the grid (gridDim.y = ops) leaves most   *
+ * of the chip waiting for the largest one (ncu: a 91-op level took 689 us for 71 MB).    *
+ * Here the level is ONE list of tiles (DNA_THREADS x U (site, rate) items each,          *
+ * tile_prefix[op] = first tile of the op, built by the host from the class counts) and   *
+ * every CTA takes a contiguous share of it, reloading the op descriptor and its two      *
+ * P-matrices only when it crosses into the next op.                                      */
+template <int LOG2R, int U>
+__global__ void __launch_bounds__(DNA_THREADS, 3)
+k_clv_dna_ii_balanced(const plf_op_t * __restrict__ ops, int per_rate_and_nops,
+                      const unsigned int * __restrict__ tile_prefix)
+{
+  constexpr int R = 1 << LOG2R;
+  constexpr unsigned int TILE_SITES = (DNA_THREADS * U) >> LOG2R;
+  const int per_rate = per_rate_and_nops & 1;
+  const unsigned int nops = (unsigned int)per_rate_and_nops >> 1;
+  const unsigned int total = tile_prefix[nops];
+  const unsigned int share = (total + gridDim.x - 1) / gridDim.x;
+  const unsigned int lo = blockIdx.x * share;
+  const unsigned int hi = min(lo + share, total);
+  if (lo >= hi) return;
+  const int rate = threadIdx.x & (R - 1);
+  const unsigned int site_in_tile = threadIdx.x >> LOG2R;
+  constexpr unsigned int PASS = DNA_THREADS >> LOG2R; /* sites one sweep of the CTA covers */
+
+  /* op of the first tile: binary search in the prefix array */
+  unsigned int cur = 0;
+  {
+    unsigned int a = 0, b = nops;
+    while (b - a > 1)
+    {
+      const unsigned int m = (a + b) >> 1;
+      if (tile_prefix[m] <= lo)
+        a = m;
+      else
+        b = m;
+    }
+    cur = a;
+  }
+  plf_op_t op = ops[cur];
+  double Lm[16], Rm[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+  {
+    Lm[i] = op.left_matrix[rate * 16 + i];
+    Rm[i] = op.right_matrix[rate * 16 + i];
+  }
+  for (unsigned int t = lo; t < hi; ++t)
+  {
+    if (t >= tile_prefix[cur + 1])
+    {
+      do
+        ++cur;
+      while (t >= tile_prefix[cur + 1]);
+      op = ops[cur];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+      {
+        Lm[i] = op.left_matrix[rate * 16 + i];
+        Rm[i] = op.right_matrix[rate * 16 + i];
+      }
+    }
+    const unsigned int base = (t - tile_prefix[cur]) * TILE_SITES;
+    SiteRef s[U];
+    dbl4 l[U], r[U];
+    unsigned int sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      s[u] = resolve_site(op, base + u * PASS + site_in_tile);
+      l[u] = r[u] = dbl4{0, 0, 0, 0};
+      sc[u] = 0;
+      if (s[u].active)
+      {
+        l[u] = ld256_stream(op.left_clv + ((size_t)s[u].lid * R + rate) * 4);
+        r[u] = ld256_stream(op.right_clv + ((size_t)s[u].rid * R + rate) * 4);
+        if (op.parent_scaler)
+        {
+          if (per_rate)
+            sc[u] = (op.left_scaler ? op.left_scaler[(size_t)s[u].lid * R + rate] : 0u) +
+                    (op.right_scaler ? op.right_scaler[(size_t)s[u].rid * R + rate] : 0u);
+          else if (rate == 0)
+            sc[u] = (op.left_scaler ? op.left_scaler[s[u].lid] : 0u) + (op.right_scaler ? op.right_scaler[s[u].rid] : 0u);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      dbl4 v;
+      v.x = dot4_pairwise(Lm + 0, l[u]) * dot4_pairwise(Rm + 0, r[u]);
+      v.y = dot4_pairwise(Lm + 4, l[u]) * dot4_pairwise(Rm + 4, r[u]);
+      v.z = dot4_pairwise(Lm + 8, l[u]) * dot4_pairwise(Rm + 8, r[u]);
+      v.w = dot4_pairwise(Lm + 12, l[u]) * dot4_pairwise(Rm + 12, r[u]);
+      scale_and_store<LOG2R>(op, s[u], rate, per_rate, sc[u], v);
+    }
+  }
+}
+
 /* ---- tip-inner (the tip is "left") --------------------------------------------- */
 template <int LOG2R, int U>
 __global__ void __launch_bounds__(DNA_THREADS, 4)
@@ -595,8 +695,18 @@ static int env_int(const char * name, int dflt)
  * single persistent wave: gridDim.y = ops, gridDim.x = CTAs striding over the
  * sites of each op.  `contiguous`: no op of the group gathers through repeat
  * identifiers, so the bulk-copy streaming kernels apply. */
+typedef void (*dna_balanced_kernel_t)(const plf_op_t *, int, const unsigned int *);
+
+/* tiles of one op for the balanced inner-inner kernel (DNA_THREADS x 4 items per tile) */
+unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats)
+{
+  const unsigned int tile_sites = (DNA_THREADS * 4u) / rate_cats;
+  return (nsites + tile_sites - 1) / tile_sites;
+}
+
 int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nops, unsigned int kind,
-                         unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous)
+                         unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous,
+                         const unsigned int * d_tile_prefix, unsigned int total_tiles)
 {
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
@@ -666,6 +776,32 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     /* the whole grid sweeps one op after the other (few open DRAM pages) */
     kb<<<dim3((unsigned int)(all < 1 ? 1 : all), 1), DNA_THREADS, smem, ctx->stream>>>(
         d_ops, (per_rate & 1) | (int)(nops << 1));
+    plf_count_launch();
+    PLF_CHECK(ctx, cudaGetLastError());
+    return 1;
+  }
+
+  if (kind == PLF_OP_II && !contiguous && d_tile_prefix && total_tiles && nops > 1 && env_int("PLF_DNA_BALANCED", 1))
+  {
+    dna_balanced_kernel_t kb = nullptr;
+    switch (log2r)
+    {
+      case 0: kb = k_clv_dna_ii_balanced<0, 4>; break;
+      case 1: kb = k_clv_dna_ii_balanced<1, 4>; break;
+      case 2: kb = k_clv_dna_ii_balanced<2, 4>; break;
+      case 3: kb = k_clv_dna_ii_balanced<3, 4>; break;
+      case 4: kb = k_clv_dna_ii_balanced<4, 4>; break;
+      default: kb = k_clv_dna_ii_balanced<5, 4>; break;
+    }
+    int & occ = ctx->dna_balanced_occupancy[log2r];
+    if (!occ)
+    {
+      PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, DNA_THREADS, 0));
+      if (occ < 1) occ = 1;
+    }
+    unsigned int grid = (unsigned int)ctx->sm_count * occ;
+    if (grid > total_tiles) grid = total_tiles;
+    kb<<<grid, DNA_THREADS, 0, ctx->stream>>>(d_ops, (per_rate & 1) | (int)(nops << 1), d_tile_prefix);
     plf_count_launch();
     PLF_CHECK(ctx, cudaGetLastError());
     return 1;
