@@ -243,7 +243,8 @@ def workload_config(args, world):
             if args.kind == "dna" else
             f"synthetic protein {args.tips} taxa x {per} sites per GPU, LG4M-style 4 matrices, pattern-tip on, "
             "full traversal + edge logL")
-    return {"workload": name, "taxa": args.tips, "sites_per_gpu": args.sites, "sites_total": args.sites * world,
+    return {"workload": name, "taxa": args.tips, "sites_per_gpu": args.sites,
+            "sites_total": args.total_sites if getattr(args, "total_sites", 0) else args.sites * world,
             "states": 4 if args.kind == "dna" else 20, "rate_cats": 4, "attributes": "ARCH_CUDA|PATTERN_TIP",
             "sharding": f"contiguous site slices x{world}, one NCCL all-reduce of logL" if world > 1 else "single GPU",
             "l2": "inputs larger than L2: each step streams all CLVs (>= 12 GB per GPU at 1M sites) vs 126 MB L2"}
@@ -356,7 +357,7 @@ def run_b200_arm(args):
     ms_total, ms_partials, e2e_ms, cold_ms = [float(x) for x in times.tolist()]
 
     n_ops = len(ds.tree.ops)
-    updates_per_step = n_ops * args.sites * world
+    updates_per_step = n_ops * (args.total_sites if args.total_sites else args.sites * world)
     value = updates_per_step * args.steps / (ms_total * 1e-3)
     clv_bytes, edge_bytes = traversal_bytes(ds, args.sites)
     peak, peak_src = measured_peak_gbs()
@@ -429,8 +430,11 @@ def main():
     args = ap.parse_args()
     args.scaling = "weak"
     if args.total_sites:
+        # contiguous site slices, boundaries at multiples of 32 sites (libpll-2_b200/sharding.py)
+        sharding = importlib.import_module("libpll-2_b200.sharding")
         world = int(os.environ.get("WORLD_SIZE", "1"))
-        args.sites = (args.total_sites + world - 1) // world
+        lo, hi = sharding.shard_bounds(args.total_sites, world, int(os.environ.get("RANK", "0")))
+        args.sites = hi - lo
         args.scaling = "strong"
     if args.impl == "reference":
         run_reference_arm(args)
