@@ -527,6 +527,10 @@ PLL_EXPORT int pll_cuda_host_eigen(unsigned int states, unsigned int states_padd
                                    double * eigenvecs, double * inv_eigenvecs,
                                    double * eigenvals);
 
+/* src/gamma.c:220 (pll.h:781-785): discrete Gamma category rates (pll_gamma.c; host only) */
+PLL_EXPORT int pll_compute_gamma_cats(double alpha, unsigned int categories, double * output_rates,
+                                      int rates_mode);
+
 /* ---- tree structures and operation-list producers (pll_tree.c; host only) ------------------ */
 
 /* src/pll.h:388-438: same layouts */

@@ -631,13 +631,7 @@ static int launch_aa_stream(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
   const int ii = (kind == PLF_OP_II);
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
-  static int wide = -1; /* PLF_AA_WARPS=8: 8-warp CTAs for every rate count (A/B switch) */
-  if (wide < 0)
-  {
-    const char * v = getenv("PLF_AA_WARPS");
-    wide = (v && v[0] == '8');
-  }
-  const int nwarps = (log2r == 3 || wide) ? 8 : 4;
+  const int nwarps = (log2r == 3 || ctx->aa_warps8) ? 8 : 4; /* PLF_AA_WARPS=8: 8-warp CTAs for every rate count */
   aas_kernel_t k = log2r == 3   ? aas_pick<3, 8>(ii)
                    : nwarps == 8 ? (log2r == 0 ? aas_pick<0, 8>(ii) : log2r == 1 ? aas_pick<1, 8>(ii) : aas_pick<2, 8>(ii))
                                  : (log2r == 0 ? aas_pick<0, 4>(ii) : log2r == 1 ? aas_pick<1, 4>(ii) : aas_pick<2, 4>(ii));
@@ -679,6 +673,10 @@ int plf_launch_aa_mma_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
   {
     const char * v = getenv("PLF_AA_STREAM");
     ctx->aa_stream = !(v && v[0] == '0');
+    v = getenv("PLF_AA_WARPS");
+    ctx->aa_warps8 = (v && v[0] == '8');
+    v = getenv("PLF_AAM_L2PF");
+    ctx->aa_l2pf = !(v && v[0] == '0');
   }
   if (kind != PLF_OP_TT && contiguous && ctx->aa_stream &&
       (rate_cats == 1 || rate_cats == 2 || rate_cats == 4 || rate_cats == 8))
@@ -702,13 +700,7 @@ int plf_launch_aa_mma_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
   else
   {
     const int ii = (kind == PLF_OP_II);
-    static int l2pf = -1;
-    if (l2pf < 0)
-    {
-      const char * v = getenv("PLF_AAM_L2PF");
-      l2pf = !(v && v[0] == '0');
-    }
-    k = l2pf ? (ii ? k_clv_aa_mma<PLF_OP_II, 1> : k_clv_aa_mma<PLF_OP_TI, 1>)
+    k = ctx->aa_l2pf ? (ii ? k_clv_aa_mma<PLF_OP_II, 1> : k_clv_aa_mma<PLF_OP_TI, 1>)
              : (ii ? k_clv_aa_mma<PLF_OP_II, 0> : k_clv_aa_mma<PLF_OP_TI, 0>);
     smem = (size_t)(ii ? 2 : 1) * rate_cats * AAM_FRAGS * 32 * sizeof(double);
     if (!ii) smem += (size_t)maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);

@@ -715,6 +715,10 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     ctx->dna_stream = env_int("PLF_DNA_STREAM", 1);
     ctx->dna_stages = env_int("PLF_DNA_STAGES", 6);
     ctx->dna_items = env_int("PLF_DNA_ITEMS", 2);
+    ctx->dna_tt_bulk = env_int("PLF_TT_BULK", 1);
+    ctx->dna_tt_items = env_int("PLF_TT_ITEMS", 2) == 4 ? 4 : 2;
+    ctx->dna_tt_seq = env_int("PLF_TT_SEQ", 1);
+    ctx->dna_balanced = env_int("PLF_DNA_BALANCED", 1);
     if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
   }
 
@@ -750,9 +754,9 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     return 1;
   }
 
-  if (kind == PLF_OP_TT && contiguous && ctx->dna_stream && log2r <= 3 && env_int("PLF_TT_BULK", 1))
+  if (kind == PLF_OP_TT && contiguous && ctx->dna_stream && log2r <= 3 && ctx->dna_tt_bulk)
   {
-    const int items = env_int("PLF_TT_ITEMS", 2) == 4 ? 4 : 2;
+    const int items = ctx->dna_tt_items;
     dna_kernel_t kb = nullptr;
     switch (log2r)
     {
@@ -781,7 +785,7 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     return 1;
   }
 
-  if (kind == PLF_OP_II && !contiguous && d_tile_prefix && total_tiles && nops > 1 && env_int("PLF_DNA_BALANCED", 1))
+  if (kind == PLF_OP_II && !contiguous && d_tile_prefix && total_tiles && nops > 1 && ctx->dna_balanced)
   {
     dna_balanced_kernel_t kb = nullptr;
     switch (log2r)
@@ -835,7 +839,7 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
   if (kind == PLF_OP_TT)
   {
     arg = (per_rate & 1) | (int)(nops << 1);
-    if (env_int("PLF_TT_SEQ", 1))
+    if (ctx->dna_tt_seq)
     {
       unsigned long long all = (unsigned long long)ctx->sm_count * occ;
       if (all > need) all = need;

@@ -137,3 +137,27 @@ def test_schedule_levels_random_tree_matches_depth(lib):
         depth[r[0]] = d
         assert l == d
     assert n == max(depth.values()) + 1
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gamma_category_rates_match_reference(lib, reflib, mode):
+    """pll_compute_gamma_cats (src/gamma.c:220): same published algorithms, constants and termination
+    rules => the same bits, over the alpha range clients use and 1..16 categories."""
+    import ctypes as C
+
+    for dll in (lib.lib, reflib.lib):
+        dll.pll_compute_gamma_cats.restype = C.c_int
+        dll.pll_compute_gamma_cats.argtypes = [C.c_double, C.c_uint, C.POINTER(C.c_double), C.c_int]
+    rng = np.random.default_rng(17)
+    alphas = [0.02, 0.05, 0.1, 0.3, 0.5, 0.7, 1.0, 1.5, 2.0, 5.0, 10.0, 50.0, 99.0] + list(rng.uniform(0.02, 20, 40))
+    for alpha in alphas:
+        for cats in (1, 2, 3, 4, 5, 8, 16):
+            a = (C.c_double * cats)()
+            b = (C.c_double * cats)()
+            assert reflib.lib.pll_compute_gamma_cats(alpha, cats, a, mode) == 1
+            assert lib.lib.pll_compute_gamma_cats(alpha, cats, b, mode) == 1
+            assert list(a) == list(b), (alpha, cats, list(a), list(b))
+            assert abs(sum(b) / cats - 1.0) < 1e-5
+    out = (C.c_double * 4)()
+    assert lib.lib.pll_compute_gamma_cats(0.001, 4, out, 0) == 0 and lib.errno == 113
+    assert lib.lib.pll_compute_gamma_cats(1.0, 4, out, 7) == 0
