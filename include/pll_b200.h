@@ -22,6 +22,7 @@
 #define PLL_B200_H_
 
 #include <stddef.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -93,6 +94,12 @@ extern "C" {
 #define PLL_ERROR_MSA_MAP_INVALID 132
 #define PLL_ERROR_TREE_INVALID 133
 #define PLL_ERROR_FILE_OPEN 100
+#define PLL_ERROR_FILE_SEEK 101
+#define PLL_ERROR_FILE_EOF 102
+#define PLL_ERROR_FASTA_ILLEGALCHAR 201
+#define PLL_ERROR_FASTA_UNPRINTABLECHAR 202
+#define PLL_ERROR_FASTA_INVALIDHEADER 203
+#define PLL_ERROR_FASTA_NONALIGNED 204
 #define PLL_ERROR_NEWICK_SYNTAX 111
 
 /* src/pll.h:147-148 */
@@ -530,6 +537,38 @@ PLL_EXPORT int pll_cuda_host_eigen(unsigned int states, unsigned int states_padd
 /* src/gamma.c:220 (pll.h:781-785): discrete Gamma category rates (pll_gamma.c; host only) */
 PLL_EXPORT int pll_compute_gamma_cats(double alpha, unsigned int categories, double * output_rates,
                                       int rates_mode);
+
+/* ---- FASTA reader (pll_fasta.c; host only) ------------------------------------------------- */
+
+#define PLL_LINEALLOC 2048
+
+/* src/pll.h:358-370: same layout */
+typedef struct pll_fasta
+{
+  FILE * fp;
+  char line[PLL_LINEALLOC];
+  const unsigned int * chrstatus;
+  long no;
+  long filesize;
+  long lineno;
+  long stripped_count;
+  long stripped[256];
+} pll_fasta_t;
+
+/* src/maps.c:207,242 */
+PLL_EXPORT extern const unsigned int pll_map_fasta[256];
+PLL_EXPORT extern const unsigned int pll_map_generic[256];
+
+/* src/fasta.c:40-417 (pll.h:864-887) */
+PLL_EXPORT pll_fasta_t * pll_fasta_open(const char * filename, const unsigned int * map);
+PLL_EXPORT int pll_fasta_getnext(pll_fasta_t * fd, char ** head, long * head_len, char ** seq,
+                                 long * seq_len, long * seqno);
+PLL_EXPORT void pll_fasta_close(pll_fasta_t * fd);
+PLL_EXPORT long pll_fasta_getfilesize(const pll_fasta_t * fd);
+PLL_EXPORT long pll_fasta_getfilepos(pll_fasta_t * fd);
+PLL_EXPORT int pll_fasta_rewind(pll_fasta_t * fd);
+PLL_EXPORT pll_msa_t * pll_fasta_load(const char * fname);
+PLL_EXPORT void pll_msa_destroy(pll_msa_t * msa);
 
 /* ---- tree structures and operation-list producers (pll_tree.c; host only) ------------------ */
 
