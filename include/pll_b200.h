@@ -21,9 +21,17 @@
 #ifndef PLL_B200_H_
 #define PLL_B200_H_
 
+/* the standard headers the reference pll.h pulls in for its clients (src/pll.h:24-41) */
+#include <assert.h>
+#include <ctype.h>
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
 #include <stddef.h>
-#include <stdio.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -83,6 +91,7 @@ extern "C" {
 #define PLL_ERROR_PARAM_INVALID 113
 #define PLL_ERROR_TIPDATA_ILLEGALSTATE 114
 #define PLL_ERROR_TIPDATA_ILLEGALFUNCTION 115
+#define PLL_ERROR_TREE_CONVERSION 116
 #define PLL_ERROR_INVAR_INCOMPAT 117
 #define PLL_ERROR_INVAR_PROPORTION 118
 #define PLL_ERROR_INVAR_PARAMINDEX 119
@@ -101,6 +110,14 @@ extern "C" {
 #define PLL_ERROR_FASTA_INVALIDHEADER 203
 #define PLL_ERROR_FASTA_NONALIGNED 204
 #define PLL_ERROR_NEWICK_SYNTAX 111
+
+/* src/pll.h:194-199 */
+#define PLL_UTREE_SHOW_LABEL (1 << 0)
+#define PLL_UTREE_SHOW_BRANCH_LENGTH (1 << 1)
+#define PLL_UTREE_SHOW_CLV_INDEX (1 << 2)
+#define PLL_UTREE_SHOW_SCALER_INDEX (1 << 3)
+#define PLL_UTREE_SHOW_PMATRIX_INDEX (1 << 4)
+#define PLL_UTREE_SHOW_DATA (1 << 5)
 
 /* src/pll.h:147-148 */
 #define PLL_TREE_TRAVERSE_POSTORDER 1
@@ -635,6 +652,7 @@ PLL_EXPORT pll_utree_t * pll_utree_wraptree_multi(pll_unode_t * root, unsigned i
                                                   unsigned int inner_count);
 PLL_EXPORT int pll_utree_is_rooted(const pll_utree_t * tree);
 /* src/utree.c:305-463 (pll.h:943-977) */
+PLL_EXPORT void pll_utree_show_ascii(const pll_unode_t * tree, int options);
 PLL_EXPORT char * pll_utree_export_newick(const pll_unode_t * root,
                                           char * (*cb_serialize)(const pll_unode_t *));
 PLL_EXPORT char * pll_utree_export_newick_rooted(const pll_unode_t * root, double root_brlen);
@@ -645,6 +663,7 @@ PLL_EXPORT void pll_utree_create_operations(pll_unode_t * const * trav_buffer,
                                             unsigned int * pmatrix_indices, pll_operation_t * ops,
                                             unsigned int * matrix_count, unsigned int * ops_count);
 PLL_EXPORT int pll_utree_check_integrity(const pll_utree_t * root);
+PLL_EXPORT pll_utree_t * pll_rtree_unroot(pll_rtree_t * tree);
 PLL_EXPORT int pll_utree_every(pll_utree_t * tree, int (*cb)(const pll_utree_t *, const pll_unode_t *));
 /* src/parse_rtree.y, src/rtree.c (pll.h:890-905, 1005-1030) */
 PLL_EXPORT pll_rtree_t * pll_rtree_parse_newick(const char * filename);

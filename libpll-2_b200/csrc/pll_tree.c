@@ -968,6 +968,104 @@ PLL_EXPORT char * pll_utree_export_newick_rooted(const pll_unode_t * root, doubl
   return utree_export(root, 1, root_brlen, NULL);
 }
 
+/* ---- ASCII rendering (src/utree.c:26-160) ------------------------------------------------ *
+ * One spacer line and one "+---" line per node, children indented by four columns, a '|' in   *
+ * every column whose branch still has children to come.  Iterative pre-order.                 */
+static void show_node_info(const pll_unode_t * node, int options)
+{
+  if (options & PLL_UTREE_SHOW_LABEL) printf(" %s", node->label ? node->label : "(null)");
+  if (options & PLL_UTREE_SHOW_BRANCH_LENGTH) printf(" %f", node->length);
+  if (options & PLL_UTREE_SHOW_CLV_INDEX) printf(" %u", node->clv_index);
+  if (options & PLL_UTREE_SHOW_SCALER_INDEX) printf(" %d", node->scaler_index);
+  if (options & PLL_UTREE_SHOW_PMATRIX_INDEX) printf(" %u", node->pmatrix_index);
+  if (options & PLL_UTREE_SHOW_DATA) printf(" %p", node->data);
+  printf("\n");
+}
+
+PLL_EXPORT void pll_utree_show_ascii(const pll_unode_t * root, int options)
+{
+  struct item
+  {
+    const pll_unode_t * node;
+    unsigned int depth;
+    int last;
+  } * stack;
+  size_t cap = 64, top = 0, bars_cap = 64;
+  unsigned char * is_last; /* is_last[d]: the node of the current path at depth d is its parent's last child */
+  const pll_unode_t * s;
+  unsigned int i;
+  if (!root->next) root = root->back;
+  stack = (struct item *)malloc(cap * sizeof(*stack));
+  is_last = (unsigned char *)calloc(bars_cap, 1);
+  if (!stack || !is_last)
+  {
+    free(stack);
+    free(is_last);
+    tree_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return;
+  }
+  /* children of the virtual root, pushed in reverse so that they pop in order */
+  {
+    size_t n = 0, k;
+    s = root;
+    do
+    {
+      ++n;
+      s = s->next;
+    } while (s != root);
+    while (cap < n) cap *= 2;
+    stack = (struct item *)realloc(stack, cap * sizeof(*stack));
+    for (k = 0, s = root; k < n; ++k, s = s->next)
+    {
+      stack[n - 1 - k].node = s->back;
+      stack[n - 1 - k].depth = 1;
+      stack[n - 1 - k].last = (s->next == root);
+    }
+    top = n;
+  }
+  while (top)
+  {
+    const struct item it = stack[--top];
+    const unsigned int d = it.depth;
+    if (d >= bars_cap)
+    {
+      unsigned char * grown = (unsigned char *)realloc(is_last, bars_cap * 2);
+      if (!grown) break;
+      memset(grown + bars_cap, 0, bars_cap);
+      is_last = grown;
+      bars_cap *= 2;
+    }
+    is_last[d] = (unsigned char)it.last;
+    for (i = 0; i + 1 < d; ++i) printf(is_last[i + 1] ? "    " : "|   ");
+    printf("|   \n");
+    for (i = 0; i + 1 < d; ++i) printf(is_last[i + 1] ? "    " : "|   ");
+    printf(it.node->next ? "+---+" : "+---");
+    show_node_info(it.node, options);
+    if (it.node->next)
+    {
+      size_t n = 0, k;
+      for (s = it.node->next; s != it.node; s = s->next) ++n;
+      if (top + n > cap)
+      {
+        struct item * grown;
+        while (cap < top + n) cap *= 2;
+        grown = (struct item *)realloc(stack, cap * sizeof(*stack));
+        if (!grown) break;
+        stack = grown;
+      }
+      for (k = 0, s = it.node->next; k < n; ++k, s = s->next)
+      {
+        stack[top + n - 1 - k].node = s->back;
+        stack[top + n - 1 - k].depth = d + 1;
+        stack[top + n - 1 - k].last = (s->next == it.node);
+      }
+      top += n;
+    }
+  }
+  free(stack);
+  free(is_last);
+}
+
 /* ======================================================================== *
  *  rooted trees                                                              *
  * ======================================================================== */
@@ -1430,4 +1528,122 @@ PLL_EXPORT char * pll_rtree_export_newick(const pll_rnode_t * root, char * (*cb_
     return NULL;
   }
   return b.s;
+}
+
+/* ---- rooted -> unrooted (src/utree.c:635-760) ------------------------------------------------ *
+ * The first root child that has descendants becomes the virtual root; the other child hangs off   *
+ * it through one edge whose length is the sum of the two root branches.  Indices are left zero:   *
+ * callers follow up with pll_utree_reset_template_indices (as the reference's examples do).       */
+static char * dup_label(const char * s)
+{
+  char * p;
+  if (!s) return NULL;
+  p = (char *)malloc(strlen(s) + 1);
+  if (p) strcpy(p, s);
+  return p;
+}
+
+/* converts the subtree below `rnode` into unode structures hanging off `back` */
+static pll_unode_t * unroot_subtree(const pll_rnode_t * rnode, pll_unode_t * back)
+{
+  struct job
+  {
+    const pll_rnode_t * rnode;
+    pll_unode_t * link; /* the node of the parent ring that will point at the converted subtree */
+  } * stack;
+  size_t cap = 64, top = 0;
+  pll_unode_t * result = NULL;
+  int failed = 0;
+  stack = (struct job *)malloc(cap * sizeof(*stack));
+  if (!stack) return NULL;
+  stack[top].rnode = rnode;
+  stack[top].link = back;
+  ++top;
+  while (top)
+  {
+    const struct job j = stack[--top];
+    pll_unode_t * u = unode_new();
+    if (!u)
+    {
+      failed = 1;
+      break;
+    }
+    u->back = j.link;
+    u->label = dup_label(j.rnode->label);
+    u->length = j.link->length;
+    if (j.link == back)
+      result = u;
+    j.link->back = u;
+    if (!j.rnode->left) continue;
+    u->next = unode_new();
+    if (u->next) u->next->next = unode_new();
+    if (!u->next || !u->next->next)
+    {
+      failed = 1;
+      break;
+    }
+    u->next->next->next = u;
+    u->next->length = j.rnode->left->length;
+    u->next->next->length = j.rnode->right->length;
+    if (top + 2 > cap)
+    {
+      struct job * grown = (struct job *)realloc(stack, 2 * cap * sizeof(*stack));
+      if (!grown)
+      {
+        failed = 1;
+        break;
+      }
+      stack = grown;
+      cap *= 2;
+    }
+    stack[top].rnode = j.rnode->right;
+    stack[top].link = u->next->next;
+    ++top;
+    stack[top].rnode = j.rnode->left;
+    stack[top].link = u->next;
+    ++top;
+  }
+  free(stack);
+  if (failed)
+  {
+    tree_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return NULL; /* the partial graph is reachable from `back` and released by the caller */
+  }
+  return result;
+}
+
+PLL_EXPORT pll_utree_t * pll_rtree_unroot(pll_rtree_t * tree)
+{
+  const pll_rnode_t * root = tree->root, * new_root, * other;
+  pll_unode_t * uroot;
+  if (!root->left->left && !root->right->left)
+  {
+    tree_error(PLL_ERROR_TREE_CONVERSION, "Tree requires at least three tips to be converted to unrooted");
+    return NULL;
+  }
+  new_root = root->left->left ? root->left : root->right;
+  other = root->left->left ? root->right : root->left;
+  uroot = unode_new();
+  if (uroot) uroot->next = unode_new();
+  if (uroot && uroot->next) uroot->next->next = unode_new();
+  if (!uroot || !uroot->next || !uroot->next->next)
+  {
+    if (uroot) free(uroot->next);
+    free(uroot);
+    tree_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return NULL;
+  }
+  uroot->next->next->next = uroot;
+  uroot->length = root->left->length + root->right->length;
+  uroot->label = dup_label(new_root->label);
+  uroot->next->label = uroot->next->next->label = uroot->label;
+  uroot->next->length = new_root->left->length;
+  uroot->next->next->length = new_root->right->length;
+  if (!unroot_subtree(other, uroot) || !unroot_subtree(new_root->left, uroot->next) ||
+      !unroot_subtree(new_root->right, uroot->next->next))
+  {
+    pll_utree_graph_destroy(uroot, NULL);
+    return NULL;
+  }
+  return pll_utree_wraptree(uroot, 0);
 }

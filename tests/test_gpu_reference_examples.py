@@ -1,0 +1,139 @@
+"""The reference's own example programs, UNMODIFIED, as clients of this library (the drop-in check).
+
+tests/examples/Makefile compiles them from the sources where they lie under /root/reference/examples twice:
+against include/pll_b200.h + libpll_b200.so (tests/examples/_bin/<name>) and, where no Newick parser is
+needed, against the reference build (tests/examples/_bin/ref/<name>).  The programs request
+PLL_ATTRIB_ARCH_AVX / SSE; PLL_CUDA_FORCE=1 redirects them to the CUDA engine.
+
+* self-contained examples (unrooted, rooted, rooted-tacg, newton, heterotachy): the two binaries must
+  print the same text -- P-matrices, CLVs (pll_show_*), log-likelihoods, Newton iterates;
+* file-driven examples (newick-fasta-unrooted/-rooted, partial-traversal, load-utree, newick-export): run on a
+  generated tree + alignment; the printed log-likelihood is checked against the reference library driven
+  through the ctypes binding with the operation list of this library's tree layer."""
+import ctypes as C
+import importlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pkg = importlib.import_module("libpll-2_b200")
+capi = pkg.capi
+synth = importlib.import_module("libpll-2_b200.synth")
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "examples", "_bin")
+NUM = re.compile(r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?")
+
+
+def run(path, *args, force_cuda=False):
+    env = dict(os.environ)
+    if force_cuda:
+        env["PLL_CUDA_FORCE"] = "1"
+    r = subprocess.run([path, *args], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (path, r.returncode, r.stdout[-500:], r.stderr[-500:])
+    return r.stdout
+
+
+def same_text(a, b, rtol):
+    la, lb = a.splitlines(), b.splitlines()
+    assert len(la) == len(lb)
+    for x, y in zip(la, lb):
+        if x == y:
+            continue
+        assert NUM.sub("#", x) == NUM.sub("#", y), (x, y)
+        for u, v in zip(NUM.findall(x), NUM.findall(y)):
+            assert abs(float(u) - float(v)) <= rtol * max(abs(float(v)), 1e-6) + 1e-12, (x, y)
+
+
+@pytest.mark.parametrize("name", ["unrooted", "rooted", "rooted-tacg", "newton", "heterotachy"])
+def test_self_contained_examples_print_the_same(cudalib, name):
+    ours, ref = os.path.join(BIN, name), os.path.join(BIN, "ref", name)
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("example binaries not built (tests/examples/Makefile needs /root/reference)")
+    out_ref = run(ref)
+    out_gpu = run(ours, force_cuda=True)
+    assert "Log-L" in out_gpu
+    same_text(out_gpu, out_ref, 1e-9)
+
+
+def write_inputs(tmp_path, tips, sites, rooted):
+    import test_tree_cpu as tt
+
+    rng = np.random.default_rng(5)
+    newick = tt.random_newick(rng, tips, rooted=rooted)
+    seqs = synth.mutate_alignment(tips, sites, rng, synth.DNA_CODES, synth.DNA_AMBIG)
+    tree, fasta = tmp_path / "tree.nwk", tmp_path / "aln.fa"
+    tree.write_text(newick + "\n")
+    with open(fasta, "w") as f:
+        for i in rng.permutation(tips):  # file order differs from tree order: the examples match by label
+            s = seqs[i].decode()
+            f.write(f">t{i}\n" + "\n".join(s[k:k + 70] for k in range(0, len(s), 70)) + "\n")
+    return newick, seqs, str(tree), str(fasta)
+
+
+def expected_unrooted_logl(reflib, newick, seqs):
+    """examples/newick-fasta-unrooted/newick-fasta-unrooted.c:216-375 through the reference library"""
+    import test_tree_cpu as tt
+
+    own = tt.bind(C.CDLL(pkg.LIB_PATH), True)
+    tree = own.pll_utree_parse_newick_string(newick.encode())
+    t = tree.contents
+    tips, n_nodes = t.tip_count, t.tip_count + t.inner_count
+    root = t.nodes[n_nodes - 1]
+    buf = (C.POINTER(tt.UNode) * n_nodes)()
+    size = C.c_uint(0)
+    assert own.pll_utree_traverse(root, 1, tt.UCB(lambda n: 1), buf, C.byref(size)) == 1
+    ops = (capi.Operation * n_nodes)()
+    branches, pm = (C.c_double * n_nodes)(), (C.c_uint * n_nodes)()
+    n_mat, n_ops = C.c_uint(0), C.c_uint(0)
+    own.pll_utree_create_operations(buf, size.value, branches, pm, ops, C.byref(n_mat), C.byref(n_ops))
+    rates = (C.c_double * 4)()
+    own.pll_compute_gamma_cats.argtypes = [C.c_double, C.c_uint, C.POINTER(C.c_double), C.c_int]
+    assert own.pll_compute_gamma_cats(1.0, 4, rates, 0) == 1
+    p = reflib.pll_partition_create(tips, tips - 2, 4, len(seqs[0]), 1, 2 * tips - 3, 4, tips - 2, capi.ARCH_AVX)
+    freqs = np.array([0.17, 0.19, 0.25, 0.39])
+    reflib.pll_set_frequencies(p, 0, freqs.ctypes.data_as(capi.c_double_p))
+    reflib.pll_set_subst_params(p, 0, np.ones(6).ctypes.data_as(capi.c_double_p))
+    reflib.pll_set_category_rates(p, rates)
+    for i in range(tips):
+        node = t.nodes[i].contents
+        assert reflib.pll_set_tip_states(p, node.clv_index, reflib.map("pll_map_nt"), seqs[int(node.label[1:])]) == 1
+    params = np.zeros(4, dtype=np.uint32)
+    reflib.pll_update_prob_matrices(p, params.ctypes.data_as(capi.c_uint_p), pm, branches, n_mat.value)
+    reflib.pll_update_partials(p, ops, n_ops.value)
+    r = root.contents
+    logl = reflib.pll_compute_edge_loglikelihood(p, r.clv_index, r.scaler_index, r.back.contents.clv_index,
+                                                 r.back.contents.scaler_index, r.pmatrix_index,
+                                                 params.ctypes.data_as(capi.c_uint_p), None)
+    reflib.pll_partition_destroy(p)
+    own.pll_utree_destroy(tree, None)
+    return logl
+
+
+def test_newick_fasta_unrooted_example(cudalib, reflib, tmp_path):
+    exe = os.path.join(BIN, "newick-fasta-unrooted")
+    if not os.path.exists(exe):
+        pytest.skip("example binaries not built")
+    newick, seqs, tree, fasta = write_inputs(tmp_path, 23, 400, rooted=False)
+    out = run(exe, tree, fasta, force_cuda=True)
+    got = float(re.search(r"Log-L: (-?[\d.]+)", out).group(1))
+    want = expected_unrooted_logl(reflib, newick, seqs)
+    assert abs(got - want) <= 5e-7 * abs(want) + 1e-6, (got, want)  # printed with 6 decimals
+    assert f"Number of tip/leaf nodes in tree: 23" in out
+
+
+@pytest.mark.parametrize("name,rooted,nargs", [("partial-traversal", False, 2), ("newick-fasta-rooted", True, 2),
+                                               ("load-utree", False, 1), ("newick-export", False, 1)])
+def test_file_driven_examples_run(cudalib, tmp_path, name, rooted, nargs):
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        pytest.skip("example binaries not built")
+    _, _, tree, fasta = write_inputs(tmp_path, 17, 300, rooted=rooted)
+    out = run(exe, *([tree, fasta][:nargs]), force_cuda=True)
+    assert out.strip()
+    for m in re.findall(r"Log-L[^:]*: (-?[\d.]+(?:[eE][-+]?\d+)?|-?inf|nan)", out):
+        assert np.isfinite(float(m)) and float(m) < 0, out[-400:]

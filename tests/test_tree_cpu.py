@@ -85,6 +85,7 @@ def bind(dll, own):
         dll.pll_rtree_destroy.argtypes = [C.POINTER(RTree), C.c_void_p]
         dll.pll_utree_is_rooted.argtypes = [C.POINTER(UTree)]
         dll.pll_utree_check_integrity.argtypes = [C.POINTER(UTree)]
+        dll.pll_utree_show_ascii.argtypes = [C.POINTER(UNode), C.c_int]
     return dll
 
 
@@ -113,6 +114,24 @@ def print_cb(node):
     p = libc.malloc(len(s) + 1)
     C.memmove(p, s, len(s) + 1)
     return p
+
+
+def capture_stdout(fn):
+    """what a C function printf()s"""
+    import tempfile
+
+    libc.fflush(None)
+    saved = os.dup(1)
+    with tempfile.TemporaryFile() as tmp:
+        os.dup2(tmp.fileno(), 1)
+        try:
+            fn()
+            libc.fflush(None)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        tmp.seek(0)
+        return tmp.read().decode()
 
 
 GOLDEN_STRINGS = [
@@ -151,6 +170,9 @@ def test_newick_golden_string_cases(own):
         assert take_string(own.pll_utree_export_newick(t.vroot, None)) == want["default"]
         assert take_string(own.pll_utree_export_newick(t.vroot, C.cast(print_cb, C.c_void_p))) == want["custom"]
         assert take_string(own.pll_utree_export_newick_rooted(t.vroot, 6.13)) == want["rooted"]
+        # the ASCII rendering: everything between the counts line and the first export line
+        art = blk.split("edges in tree:")[1].split("\n", 1)[1].split("Newick export (default)")[0]
+        assert capture_stdout(lambda: own.pll_utree_show_ascii(t.vroot, 1 | 2 | 4)) == art
         own.pll_utree_destroy(tree, None)
 
 
@@ -262,3 +284,26 @@ def test_newick_syntax_errors(own):
     assert not own.pll_rtree_parse_newick_string(b"(A,B,C);")
     assert not own.pll_utree_parse_newick(b"/nonexistent/file.tree")
     assert C.c_int.in_dll(own, "pll_errno").value == 100
+
+
+def test_rtree_unroot(own):
+    own.pll_rtree_unroot.restype, own.pll_rtree_unroot.argtypes = C.POINTER(UTree), [C.POINTER(RTree)]
+    own.pll_utree_reset_template_indices.argtypes = [C.POINTER(UNode), C.c_uint]
+    cases = {
+        "((A:1,B:2)ab:3,(C:4,D:5)cd:6);": "((C:4.000000,D:5.000000)cd:9.000000,A:1.000000,B:2.000000)ab;",
+        "(A:1,((B:2,C:3)x:4,D:5)y:6);": "(A:7.000000,(B:2.000000,C:3.000000)x:4.000000,D:5.000000)y;",
+    }
+    for rooted, unrooted in cases.items():
+        rt = own.pll_rtree_parse_newick_string(rooted.encode())
+        ut = own.pll_rtree_unroot(rt)
+        assert ut
+        u = ut.contents
+        own.pll_utree_reset_template_indices(u.vroot, u.tip_count)
+        assert own.pll_utree_check_integrity(ut) == 1 and not own.pll_utree_is_rooted(ut)
+        assert (u.tip_count, u.inner_count, u.binary) == (4, 2, 1)
+        assert take_string(own.pll_utree_export_newick(u.vroot, None)) == unrooted
+        own.pll_utree_destroy(ut, None)
+        own.pll_rtree_destroy(rt, None)
+    rt = own.pll_rtree_parse_newick_string(b"(A:1,B:2);")
+    assert not own.pll_rtree_unroot(rt) and C.c_int.in_dll(own, "pll_errno").value == 116
+    own.pll_rtree_destroy(rt, None)
