@@ -447,36 +447,41 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     double accL[3][2], accR[3][2];
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) accL[nt][0] = accL[nt][1] = accR[nt][0] = accR[nt][1] = 0.0;
+    if (KIND == PLF_OP_II)
+    {
+      /* both children's A fragments first (the slot is released before any arithmetic), then the two
+       * DMMA chains interleaved: 6 independent accumulators in flight */
+      const double * pr = reinterpret_cast<const double *>(slot) + ((size_t)my * R + rate) * 20;
+      const double * pl = reinterpret_cast<const double *>(slot + CH_BYTES) + ((size_t)my * R + rate) * 20;
+      const double2 r0 = *reinterpret_cast<const double2 *>(pr + 2 * q);
+      const double2 r1 = *reinterpret_cast<const double2 *>(pr + 8 + 2 * q);
+      const double2 l0 = *reinterpret_cast<const double2 *>(pl + 2 * q);
+      const double2 l1 = *reinterpret_cast<const double2 *>(pl + 8 + 2 * q);
+      const double ar[5] = {r0.x, r0.y, r1.x, r1.y, pr[16 + q]};
+      const double al[5] = {l0.x, l0.y, l1.x, l1.y, pl[16 + q]};
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]); /* this warp is done with the slot */
+#pragma unroll
+      for (int kt = 0; kt < 5; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+        {
+          dmma(accR[nt], ar[kt], br[nt * 5 + kt]);
+          dmma(accL[nt], al[kt], bl[nt * 5 + kt]);
+        }
+    }
+    else
     {
       const double * pr = reinterpret_cast<const double *>(slot) + ((size_t)my * R + rate) * 20;
       const double2 v0 = *reinterpret_cast<const double2 *>(pr + 2 * q);
       const double2 v1 = *reinterpret_cast<const double2 *>(pr + 8 + 2 * q);
       const double a[5] = {v0.x, v0.y, v1.x, v1.y, pr[16 + q]};
-      if (KIND != PLF_OP_II)
-      {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]); /* this warp is done with the slot */
-      }
-#pragma unroll
-      for (int kt = 0; kt < 5; ++kt)
-#pragma unroll
-        for (int nt = 0; nt < 3; ++nt) dmma(accR[nt], a[kt], br[nt * 5 + kt]);
-    }
-    if (KIND == PLF_OP_II)
-    {
-      const double * pl = reinterpret_cast<const double *>(slot + CH_BYTES) + ((size_t)my * R + rate) * 20;
-      const double2 v0 = *reinterpret_cast<const double2 *>(pl + 2 * q);
-      const double2 v1 = *reinterpret_cast<const double2 *>(pl + 8 + 2 * q);
-      const double a[5] = {v0.x, v0.y, v1.x, v1.y, pl[16 + q]};
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
 #pragma unroll
       for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) dmma(accL[nt], a[kt], bl[nt * 5 + kt]);
-    }
-    else
-    {
+        for (int nt = 0; nt < 3; ++nt) dmma(accR[nt], a[kt], br[nt * 5 + kt]);
       const double * row = tl + ((size_t)code * R + rate) * AAM_TAB_STRIDE + 2 * q;
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt)
