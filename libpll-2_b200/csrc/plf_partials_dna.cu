@@ -722,7 +722,9 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
   }
 
-  if (contiguous && ctx->dna_stream && kind != PLF_OP_TT)
+  /* the ring copies tip codes and scalers in 16-byte granules from tile-aligned offsets: a tile must
+   * hold at least 16 sites (32 rate categories with 2 items per thread would give 8) */
+  if (contiguous && ctx->dna_stream && kind != PLF_OP_TT && ((DNA_THREADS * (unsigned int)ctx->dna_items) >> log2r) >= 16)
   {
     dna_kernel_t k = nullptr;
     size_t smem = 0;

@@ -532,3 +532,54 @@ def test_newick_to_loglikelihood_end_to_end(reflib, cudalib):
     own.pll_utree_destroy(tree, None)
     assert np.isfinite(logl[0]) and logl[0] < 0
     assert_rel(logl[1], logl[0], LOGL_RTOL, "edge logL from a Newick tree")
+
+
+EDGE_SHAPES = [
+    # kind, tips, sites, cats, attrs, per_rate
+    ("dna", 3, 1, 4, capi.PATTERN_TIP, False),     # one site, one operation
+    ("dna", 3, 1, 1, 0, False),
+    ("dna", 4, 2, 3, capi.PATTERN_TIP, True),      # rate count that is not a power of two
+    ("dna", 5, 7, 5, 0, False),
+    ("dna", 4, 31, 7, capi.PATTERN_TIP, False),
+    ("dna", 6, 33, 2, 0, True),
+    ("dna", 7, 65, 8, capi.PATTERN_TIP, False),    # one site more than a 64-site tile
+    ("dna", 5, 63, 16, 0, False),
+    ("dna", 4, 129, 32, capi.PATTERN_TIP, False),  # largest specialised rate count
+    ("aa", 3, 1, 4, capi.PATTERN_TIP, False),
+    ("aa", 4, 7, 1, 0, False),                      # fewer sites than one 8-site DMMA block
+    ("aa", 5, 9, 3, capi.PATTERN_TIP, True),
+    ("aa", 4, 33, 2, 0, False),
+    ("aa", 6, 17, 8, capi.PATTERN_TIP, False),
+    ("g2", 5, 19, 4, 0, False),                     # binary data
+    ("g2", 4, 5, 3, capi.PATTERN_TIP, True),
+    ("g3", 5, 21, 4, capi.PATTERN_TIP, False),
+    ("g11", 4, 13, 2, 0, False),
+    ("g23", 4, 9, 4, capi.PATTERN_TIP, False),      # more states than amino acids (padded to 24)
+]
+
+
+@pytest.mark.parametrize("kind,tips,sites,cats,extra,per_rate", EDGE_SHAPES)
+def test_small_and_odd_shapes(reflib, cudalib, kind, tips, sites, cats, extra, per_rate):
+    """Shapes around the tile sizes of the specialised kernels and shapes only the generic kernels take:
+    single sites, single operations, rate counts 1..32 incl. non powers of two, 2 to 23 states."""
+    if kind == "dna":
+        ds = synth.dna_dataset(tips, sites, seed=101, cats=cats, alpha=0.5)
+    elif kind == "aa":
+        ds = synth.aa_dataset(tips, sites, seed=102, cats=cats, alpha=0.5)
+    else:
+        ds = synth.generic_dataset(int(kind[1:]), tips, sites, seed=103, cats=cats)
+    ref, gpu = pair(reflib, cudalib, ds, extra, per_rate)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    for op in ref.ops:
+        assert_clv_equal(ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index), kind != "aa",
+                         f"clv {op.parent_clv_index}")
+        assert np.array_equal(ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index))
+    last = ref.ops[len(ref.ops) - 1]
+    edges = [ds.tree.root_edge, (last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index)]
+    check_edge_and_derivatives(ref, gpu, ds, per_rate, edges)
+    if not per_rate:
+        assert_rel(gpu.root_logl(), ref.root_logl(), LOGL_RTOL, "root logL")
+    ref.close()
+    gpu.close()
