@@ -583,3 +583,39 @@ def test_small_and_odd_shapes(reflib, cudalib, kind, tips, sites, cats, extra, p
         assert_rel(gpu.root_logl(), ref.root_logl(), LOGL_RTOL, "root logL")
     ref.close()
     gpu.close()
+
+
+def test_concurrent_partitions_from_threads(cudalib):
+    """Distinct partitions used concurrently from distinct threads (the RAxML-NG pattern, SURVEY 8b
+    "Threading"): every thread owns a partition, a context and a stream; results equal the serial ones."""
+    import threading
+
+    datasets = [synth.dna_dataset(20 + 3 * i, 4000 + 137 * i, seed=200 + i, alpha=0.5) for i in range(4)]
+    datasets.append(synth.aa_dataset(12, 1500, seed=210, alpha=0.5))
+
+    def evaluate(ds):
+        e = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+        out = []
+        for _ in range(5):
+            logl = e.full_traversal()
+            st = e.sumtable_alloc()
+            e.update_sumtable(st)
+            out.append((logl, *e.derivatives(st, 0.11)))
+        e.close()
+        return out
+
+    serial = [evaluate(ds) for ds in datasets]
+    results = [None] * len(datasets)
+    errors = []
+
+    def work(i):
+        try:
+            results[i] = evaluate(datasets[i])
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(datasets))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    assert results == serial
