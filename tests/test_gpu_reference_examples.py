@@ -137,3 +137,49 @@ def test_file_driven_examples_run(cudalib, tmp_path, name, rooted, nargs):
     assert out.strip()
     for m in re.findall(r"Log-L[^:]*: (-?[\d.]+(?:[eE][-+]?\d+)?|-?inf|nan)", out):
         assert np.isfinite(float(m)) and float(m) < 0, out[-400:]
+
+
+# ---- the reference's own test programs against their golden outputs ------------------------------
+
+REF_TESTS = ["pmatrix", "alpha-cats", "hky", "derivatives", "derivatives-oddstates", "00010_NMDU_lkcalc",
+             "00012_NMOU_lkcalc", "00020_NMDR_lkcalc", "00022_NMOR_lkcalc", "00030_NMDU_gamma", "00032_NMOU_gamma",
+             "compress-patterns"]
+
+
+def same_as_golden(out, golden, name):
+    """the reference's runner does an exact diff; here numbers may differ in their last printed digit"""
+    la, lb = out.splitlines(), golden.splitlines()
+    assert len(la) == len(lb), (name, len(la), len(lb))
+    bad = 0
+    for x, y in zip(la, lb):
+        if x == y:
+            continue
+        assert NUM.sub("#", x) == NUM.sub("#", y), (name, x, y)
+        for u, v in zip(NUM.findall(x), NUM.findall(y)):
+            digits = len(v.split(".")[1].split("e")[0].split("E")[0]) if "." in v else 0
+            ulp = 10.0 ** (-digits) * (10.0 ** int(re.split("[eE]", v)[1]) if re.search("[eE]", v) else 1.0)
+            assert abs(float(u) - float(v)) <= 1.5 * ulp + 1e-9 * abs(float(v)), (name, x, y)
+        bad += 1
+    return bad
+
+
+@pytest.mark.parametrize("name", REF_TESTS)
+@pytest.mark.parametrize("attrs", ["", "tv", "sr"])
+def test_reference_test_programs_match_their_golden_outputs(cudalib, name, attrs):
+    """test/src/<name>.c (+ common.c) of the reference, compiled unmodified against this library and run with
+    the runner's attribute words ("tv" = pattern tips, "sr" = site repeats; the arch words are moot under
+    PLL_CUDA_FORCE=1), compared with test/out/<name>.out (tests/golden/)."""
+    exe = os.path.join(BIN, "reftests", name)
+    golden_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if not os.path.exists(exe):
+        pytest.skip("reference test programs not built (tests/examples/Makefile needs /root/reference)")
+    env = dict(os.environ, PLL_CUDA_FORCE="1")
+    if name == "pmatrix":
+        # test/src/pmatrix.c:47-56 reads partition->pmatrix[i] on the host: device-resident buffers become
+        # host-dereferenceable with managed allocations (include/pll_b200.h, "PLL_CUDA_MANAGED")
+        env["PLL_CUDA_MANAGED"] = "1"
+    r = subprocess.run([exe] + attrs.split(), capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, (r.returncode, r.stdout[-400:], r.stderr[-400:])
+    if r.stdout == open(os.path.join(golden_dir, "skip.out")).read():
+        pytest.skip("the program skips this attribute set")
+    same_as_golden(r.stdout, open(os.path.join(golden_dir, name + ".out")).read(), name)
