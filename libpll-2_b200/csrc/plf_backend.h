@@ -111,6 +111,7 @@ void * plf_ctx_stream(const plf_ctx_t * ctx);
 const char * plf_last_error(const plf_ctx_t * ctx);
 void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero);
 void plf_free(plf_ctx_t * ctx, void * p);
+int plf_pool_reserve(plf_ctx_t * ctx, size_t bytes);
 int plf_upload(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_download(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_memset0(plf_ctx_t * ctx, void * dst, size_t bytes);

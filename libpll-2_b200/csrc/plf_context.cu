@@ -185,6 +185,25 @@ extern "C" void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero)
   return p;
 }
 
+/* Grows the stream-ordered pool by `bytes` (capped at 40 % of the free device memory) and hands the block
+ * straight back: it stays cached in the pool (release threshold = max), so the many small allocations
+ * that follow are carved out of it without a trip to the driver. */
+extern "C" int plf_pool_reserve(plf_ctx_t * ctx, size_t bytes)
+{
+  if (!ctx->pool || !bytes) return 1;
+  size_t free_b = 0, total_b = 0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
+  if (bytes > free_b / 5 * 2) bytes = free_b / 5 * 2;
+  void * p = NULL;
+  if (cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream) != cudaSuccess)
+  {
+    cudaGetLastError(); /* a warm-up only: failure is not an error */
+    return 1;
+  }
+  cudaFreeAsync(p, ctx->stream);
+  return 1;
+}
+
 extern "C" void plf_free(plf_ctx_t * ctx, void * p)
 {
   if (!p) return;

@@ -369,6 +369,9 @@ static int repeats_initialize(cuda_partition_t * cp)
   cp->d_keys = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 0);
   cp->d_rep_charmap = (unsigned char *)plf_alloc(cp->ctx, PLL_ASCII_SIZE, 0);
   if (!cp->d_keys || !cp->d_rep_charmap) return PLL_FAILURE;
+  /* the first traversal sizes every CLV and scaler to its class count (~2 allocations per node): warm the
+   * pool with a quarter of the uncompressed CLV volume so that they do not each grow it through the driver */
+  plf_pool_reserve(cp->ctx, (size_t)p->nodes * p->sites * p->rate_cats * p->states_padded * sizeof(double) / 4);
   return PLL_SUCCESS;
 }
 
