@@ -619,3 +619,15 @@ def test_concurrent_partitions_from_threads(cudalib):
     [t.join() for t in threads]
     assert not errors, errors
     assert results == serial
+
+
+def test_out_of_memory_is_an_error_not_a_crash(cudalib):
+    """A partition that cannot fit in HBM (100 taxa x 60M sites = 750 GB of CLVs): pll_partition_create returns
+    NULL with pll_errno set, frees what it had allocated, and the next partition works."""
+    p = cudalib.pll_partition_create(100, 98, 4, 60_000_000, 1, 197, 4, 98, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert not p
+    assert cudalib.errno in (112, 900), (cudalib.errno, cudalib.errmsg)
+    ds = synth.dna_dataset(8, 500, seed=3)
+    e = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert np.isfinite(e.full_traversal())
+    e.close()
