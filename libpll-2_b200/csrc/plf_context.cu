@@ -12,6 +12,7 @@
 
 static __thread unsigned long long g_launches = 0;
 void plf_count_launch(void) { ++g_launches; }
+void plf_count_launches(unsigned long long n) { g_launches += n; }
 extern "C" unsigned long long plf_kernel_launches(void) { return g_launches; }
 
 void plf_set_error(plf_ctx * ctx, const char * fmt, ...)
@@ -57,6 +58,7 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
   ctx->device = device;
   ctx->managed = managed;
   ctx->dna_stream = -1;
+  ctx->graph_mode = -1;
   ctx->aa_stream = -1;
   ctx->aam_log2r[0] = ctx->aam_log2r[1] = -1;
   {
@@ -125,6 +127,7 @@ extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  plf_graph_cache_destroy(ctx);
   cudaFree(ctx->ws_ops.ptr);
   cudaFree(ctx->ws_small.ptr);
   cudaFree(ctx->ws_partial.ptr);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "plf_backend.h"
+
 struct plf_ws
 {
   void * ptr;
@@ -48,6 +50,16 @@ struct plf_ctx
   double * d_result;  /* 4 doubles                                             */
   unsigned int * d_ticket; /* arrival counter of the fused (last block) reductions; zero between kernels */
   double * h_result;  /* pinned, 4 doubles                                     */
+  /* one CUDA graph per traversal (plf_partials.cu): the last op list and its instantiated graph */
+  int graph_mode;          /* -1 = read PLF_GRAPH on first use; 0 = plain launches */
+  int graph_valid;
+  struct plf_op * graph_ops;
+  unsigned int * graph_levels;
+  unsigned int graph_nops, graph_nlevels, graph_cap_ops, graph_cap_levels, graph_maxstates;
+  struct plf_shape graph_shape;
+  const unsigned long long * graph_tipmap;
+  cudaGraphExec_t graph_exec;
+  unsigned long long graph_launches;
   char err[256];
   char name[128];
 };
@@ -55,6 +67,8 @@ struct plf_ctx
 void plf_set_error(plf_ctx * ctx, const char * fmt, ...);
 void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes);
 void plf_count_launch(void);
+void plf_count_launches(unsigned long long n);
+void plf_graph_cache_destroy(plf_ctx * ctx);
 struct plf_op;
 int plf_launch_aa_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
                         unsigned int rate_cats, int per_rate, unsigned int max_sites,

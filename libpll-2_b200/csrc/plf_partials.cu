@@ -19,6 +19,9 @@
 #include "plf_device.cuh"
 #include "plf_internal.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 /* ------------------------------------------------------------------------ *
  *  DNA (4 states)                                                           *
  * ------------------------------------------------------------------------ */
@@ -418,13 +421,12 @@ k_partials_gen(const plf_op_t * __restrict__ ops, int R, int per_rate, int st_rt
 
 static int is_pow2(unsigned int x) { return x && !(x & (x - 1)); }
 
-extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops,
-                                   unsigned int nops, const unsigned int * h_level_start,
-                                   unsigned int nlevels, const unsigned long long * d_tipmap,
-                                   unsigned int maxstates)
+/* queues the launches of a level-sorted op list.  `upload` = 0: the op descriptors and tile-prefix arrays
+ * are already in the workspace (identical call being captured into a CUDA graph): no host-to-device copy */
+static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops, unsigned int nops,
+                          const unsigned int * h_level_start, unsigned int nlevels,
+                          const unsigned long long * d_tipmap, unsigned int maxstates, int upload)
 {
-  if (!nops) return 1;
-  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
   /* workspace: the op descriptors, then one tile-prefix array per (level, kind) run of gathering
    * 4-state inner-inner ops (site repeats; see k_clv_dna_ii_balanced) */
   const size_t prefix_entries = (size_t)nops + 3 * (size_t)nlevels + 1;
@@ -432,7 +434,7 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
   plf_op_t * d_ops = (plf_op_t *)plf_ws_reserve(ctx, &ctx->ws_ops, ops_bytes + prefix_entries * sizeof(unsigned int));
   if (!d_ops) return 0;
   unsigned int * d_prefix = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(d_ops) + ops_bytes);
-  PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_ops, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (upload) PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_ops, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
   unsigned int * h_prefix = nullptr;
   size_t prefix_used = 0;
   const int R = (int)sh->rate_cats;
@@ -479,8 +481,8 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
               total_tiles += plf_dna_balanced_tiles(h_ops[k].nsites, sh->rate_cats);
             }
             pre[j - i] = total_tiles;
-            if (cudaMemcpyAsync(d_prefix + prefix_used, pre, (size_t)(j - i + 1) * sizeof(unsigned int),
-                                cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess)
+            if (!upload || cudaMemcpyAsync(d_prefix + prefix_used, pre, (size_t)(j - i + 1) * sizeof(unsigned int),
+                                           cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess)
               d_run_prefix = d_prefix + prefix_used;
             prefix_used += (j - i) + 1;
           }
@@ -578,5 +580,109 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
     PLF_CHECK(ctx, cudaGetLastError());
   }
   free(h_prefix);
+  return 1;
+}
+
+/* ------------------------------------------------------------------------ *
+ *  One CUDA graph per traversal.  Clients evaluate the same operation list   *
+ *  over and over (branch-length and model optimisation change P-matrices,    *
+ *  not the list), and on narrow alignments a traversal is bound by the       *
+ *  launch path: 12 launches of ~5 us kernels.  The resolved descriptors      *
+ *  (device pointers included) of the last call are kept; the second          *
+ *  identical call is captured, later ones replay the graph.                  *
+ * ------------------------------------------------------------------------ */
+static void graph_cache_drop(plf_ctx * ctx)
+{
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  ctx->graph_exec = nullptr;
+  ctx->graph_valid = 0;
+}
+
+void plf_graph_cache_destroy(plf_ctx * ctx)
+{
+  graph_cache_drop(ctx);
+  free(ctx->graph_ops);
+  free(ctx->graph_levels);
+  ctx->graph_ops = nullptr;
+  ctx->graph_levels = nullptr;
+}
+
+extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops,
+                                   unsigned int nops, const unsigned int * h_level_start,
+                                   unsigned int nlevels, const unsigned long long * d_tipmap,
+                                   unsigned int maxstates)
+{
+  if (!nops) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (ctx->graph_mode < 0)
+  {
+    const char * v = getenv("PLF_GRAPH");
+    ctx->graph_mode = !(v && v[0] == '0');
+  }
+  if (!ctx->graph_mode) return enqueue_levels(ctx, sh, h_ops, nops, h_level_start, nlevels, d_tipmap, maxstates, 1);
+
+  const int same = ctx->graph_valid && ctx->graph_nops == nops && ctx->graph_nlevels == nlevels &&
+                   ctx->graph_tipmap == d_tipmap && ctx->graph_maxstates == maxstates &&
+                   !memcmp(&ctx->graph_shape, sh, sizeof(*sh)) &&
+                   !memcmp(ctx->graph_ops, h_ops, (size_t)nops * sizeof(plf_op_t)) &&
+                   !memcmp(ctx->graph_levels, h_level_start, ((size_t)nlevels + 1) * sizeof(unsigned int));
+  if (same && ctx->graph_exec)
+  {
+    PLF_CHECK(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    plf_count_launches(ctx->graph_launches);
+    return 1;
+  }
+  if (same)
+  {
+    /* second identical call: capture it (descriptors are resident, nothing is uploaded) */
+    cudaGraph_t graph = nullptr;
+    const unsigned long long before = plf_kernel_launches();
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
+    {
+      const int ok = enqueue_levels(ctx, sh, h_ops, nops, h_level_start, nlevels, d_tipmap, maxstates, 0);
+      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      const unsigned long long captured = plf_kernel_launches() - before;
+      if (ok && e == cudaSuccess && graph &&
+          cudaGraphInstantiate(&ctx->graph_exec, graph, 0) == cudaSuccess)
+      {
+        cudaGraphDestroy(graph);
+        ctx->graph_launches = captured;
+        PLF_CHECK(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+        return 1; /* the launches were counted while they were captured */
+      }
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ctx->graph_exec = nullptr;
+      plf_count_launches(0ull - captured); /* nothing ran */
+    }
+    ctx->graph_mode = 0; /* capture is not available here: plain launches from now on */
+    return enqueue_levels(ctx, sh, h_ops, nops, h_level_start, nlevels, d_tipmap, maxstates, 1);
+  }
+  /* a new list: run it and remember it */
+  graph_cache_drop(ctx);
+  if (ctx->graph_cap_ops < nops)
+  {
+    free(ctx->graph_ops);
+    ctx->graph_ops = (plf_op_t *)malloc((size_t)nops * sizeof(plf_op_t));
+    ctx->graph_cap_ops = ctx->graph_ops ? nops : 0;
+  }
+  if (ctx->graph_cap_levels < nlevels + 1)
+  {
+    free(ctx->graph_levels);
+    ctx->graph_levels = (unsigned int *)malloc(((size_t)nlevels + 1) * sizeof(unsigned int));
+    ctx->graph_cap_levels = ctx->graph_levels ? nlevels + 1 : 0;
+  }
+  if (!enqueue_levels(ctx, sh, h_ops, nops, h_level_start, nlevels, d_tipmap, maxstates, 1)) return 0;
+  if (ctx->graph_ops && ctx->graph_levels)
+  {
+    memcpy(ctx->graph_ops, h_ops, (size_t)nops * sizeof(plf_op_t));
+    memcpy(ctx->graph_levels, h_level_start, ((size_t)nlevels + 1) * sizeof(unsigned int));
+    ctx->graph_nops = nops;
+    ctx->graph_nlevels = nlevels;
+    ctx->graph_shape = *sh;
+    ctx->graph_tipmap = d_tipmap;
+    ctx->graph_maxstates = maxstates;
+    ctx->graph_valid = 1;
+  }
   return 1;
 }

@@ -631,3 +631,34 @@ def test_out_of_memory_is_an_error_not_a_crash(cudalib):
     e = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
     assert np.isfinite(e.full_traversal())
     e.close()
+
+
+@pytest.mark.parametrize("kind,extra", [("dna", capi.PATTERN_TIP), ("dna", capi.SITE_REPEATS), ("aa", capi.PATTERN_TIP)])
+def test_repeated_traversals_replay_a_cuda_graph(reflib, cudalib, kind, extra, monkeypatch):
+    """The same operation list evaluated again and again with new branch lengths (what branch-length and
+    model optimisation do): from the third call on the traversal is a CUDA graph replay.  Every
+    evaluation must equal the reference's, and the graph-free path (PLF_GRAPH=0)."""
+    ds = make_ds(kind, 40, 777, "random", seed=131)
+    ref, gpu = pair(reflib, cudalib, ds, extra)
+    monkeypatch.setenv("PLF_GRAPH", "0")
+    plain = harness.Engine(cudalib, ds, capi.ARCH_CUDA | extra)
+    monkeypatch.delenv("PLF_GRAPH")
+    rng = np.random.default_rng(7)
+    launches = []
+    for it in range(6):
+        bl = ds.tree.branch_lengths[ref.matrix_indices] * rng.uniform(0.5, 1.5)
+        vals = []
+        for e in (ref, gpu, plain):
+            e.update_pmatrices(branch_lengths=bl)
+            before = cudalib.pll_cuda_kernel_launches()
+            e.update_partials()
+            if e is gpu:
+                launches.append(cudalib.pll_cuda_kernel_launches() - before)
+            vals.append(e.edge_logl())
+        assert_rel(vals[1], vals[0], LOGL_RTOL, f"iteration {it}")
+        assert vals[1] == vals[2], "graph replay and plain launches must give the same bits"
+    assert len(set(launches[1:])) == 1 and launches[1] > 0, launches  # replays are counted like launches
+    for op in ref.ops:
+        assert_clv_equal(ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index), kind != "aa", "clv after replays")
+    for e in (ref, gpu, plain):
+        e.close()
