@@ -217,7 +217,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = args.cpu_threads or host_threads()
-    spt = args.cpu_sites_per_thread
+    spt = args.cpu_sites_per_thread or -(-args.sites // threads)
     res = cpu_reference_run(args.kind, args.tips, spt, threads, args.steps, args.warmup, args.seed)
     sample = f"{args.tips} taxa x {spt * threads} sites ({spt} per thread) per step, AVX2+PATTERN_TIP"
     if res is None:
@@ -394,11 +394,12 @@ def run_b200_arm(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = args.cpu_threads or host_threads()
-        res = cpu_reference_run(args.kind, args.tips, args.cpu_sites_per_thread, threads, 3, 1, args.seed)
+        spt = args.cpu_sites_per_thread or -(-args.sites // threads)
+        res = cpu_reference_run(args.kind, args.tips, spt, threads, 10, 1, args.seed)
         if res is not None:
             v, ms, _, knd = res
-            sample = (f"{args.tips} taxa x {args.cpu_sites_per_thread * threads} sites ({args.cpu_sites_per_thread} per "
-                      f"thread), 3 timed traversals, AVX2+PATTERN_TIP, one partition per thread")
+            sample = (f"{args.tips} taxa x {spt * threads} sites ({spt} per thread), 10 timed traversals, "
+                      f"AVX2+PATTERN_TIP, one partition per thread")
         else:
             v, ms, _, knd = cpu_port_run(args.kind, args.tips, 20000, args.seed)
             threads, sample = 1, f"{args.tips} taxa x 20000 sites, scalar port, 1 traversal"
@@ -425,7 +426,9 @@ def main():
                     help="strong scaling (BASELINE config 5): this many sites split into contiguous slices over the GPUs")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-threads", type=int, default=0)
-    ap.add_argument("--cpu-sites-per-thread", type=int, default=50_000)
+    ap.add_argument("--cpu-sites-per-thread", type=int, default=0,
+                    help="site slice per host thread of the reference arm (default: --sites split over the host threads, "
+                         "i.e. the same alignment as one GPU's share)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.scaling = "weak"
