@@ -110,6 +110,10 @@ extern "C" {
 #define PLL_ERROR_FASTA_INVALIDHEADER 203
 #define PLL_ERROR_FASTA_NONALIGNED 204
 #define PLL_ERROR_NEWICK_SYNTAX 111
+/* src/pll.h:184-186 */
+#define PLL_ERROR_STEPWISE_STRUCT 127
+#define PLL_ERROR_STEPWISE_TIPS 128
+#define PLL_ERROR_STEPWISE_UNSUPPORTED 129
 
 /* src/pll.h:194-199 */
 #define PLL_UTREE_SHOW_LABEL (1 << 0)
@@ -680,6 +684,97 @@ PLL_EXPORT void pll_rtree_create_operations(pll_rnode_t * const * trav_buffer,
                                             unsigned int trav_buffer_size, double * branches,
                                             unsigned int * pmatrix_indices, pll_operation_t * ops,
                                             unsigned int * matrix_count, unsigned int * ops_count);
+
+/* ---- Fitch parsimony on packed bit vectors (src/fast_parsimony.c, src/stepwise.c) ----------------
+ * SURVEY.md 8(f)-4.  The structure keeps the reference's layout (src/pll.h:467-492).  Differences of the
+ * CUDA engine: packedvector[i] holds DEVICE addresses (row k of node i starts at packedvector[i] +
+ * k*packedvector_count; read one with pll_cuda_download_parsimony_vector); node_cost[], const_cost,
+ * informative[] and the counts live on the host and are current whenever a call returns.  The weighted
+ * (Sankoff) members are unused.  pll_fastparsimony_init reads the tip states from the partition's device
+ * buffers; the parsimony object is independent of the partition afterwards. */
+typedef struct pll_parsimony_s
+{
+  unsigned int tips;
+  unsigned int inner_nodes;
+  unsigned int sites;
+  unsigned int states;
+  unsigned int attributes;
+  size_t alignment;
+
+  unsigned int ** packedvector;
+  unsigned int * node_cost;
+  unsigned int packedvector_count;
+  unsigned int const_cost;
+  int * informative;
+  unsigned int informative_count;
+
+  unsigned int score_buffers;
+  unsigned int ancestral_buffers;
+  double * score_matrix;
+  double ** sbuffer;
+  unsigned int ** anc_states;
+} pll_parsimony_t;
+
+/* src/pll.h:495-500 */
+typedef struct pll_pars_buildop_s
+{
+  unsigned int parent_score_index;
+  unsigned int child1_score_index;
+  unsigned int child2_score_index;
+} pll_pars_buildop_t;
+
+/* src/fast_parsimony.c:532-570 (pll.h:2574) */
+PLL_EXPORT pll_parsimony_t * pll_fastparsimony_init(const pll_partition_t * partition);
+/* src/fast_parsimony.c:721-729 (pll.h:2576): the whole list is ONE launch */
+PLL_EXPORT void pll_fastparsimony_update_vectors(pll_parsimony_t * parsimony, const pll_pars_buildop_t * ops,
+                                                 unsigned int count);
+/* src/fast_parsimony.c:731-773 (pll.h:2580) */
+PLL_EXPORT unsigned int pll_fastparsimony_edge_score(const pll_parsimony_t * parsimony,
+                                                     unsigned int node1_score_index,
+                                                     unsigned int node2_score_index);
+/* src/fast_parsimony.c:776-781 (pll.h:2584) */
+PLL_EXPORT unsigned int pll_fastparsimony_root_score(const pll_parsimony_t * parsimony, unsigned int root_index);
+/* src/parsimony.c:350-383 (pll.h:2559) */
+PLL_EXPORT void pll_parsimony_destroy(pll_parsimony_t * pars);
+/* src/utree.c:762-785 (pll.h:1003) */
+PLL_EXPORT void pll_utree_create_pars_buildops(pll_unode_t * const * trav_buffer, unsigned int trav_buffer_size,
+                                               pll_pars_buildop_t * ops, unsigned int * ops_count);
+/* src/stepwise.c:883-1082 (pll.h:2587): randomised stepwise addition; every insertion evaluates ALL
+ * candidate edges in one launch.  Same tree and cost as the reference for the same seed. */
+PLL_EXPORT pll_utree_t * pll_fastparsimony_stepwise(pll_parsimony_t ** list, char * const * labels,
+                                                    unsigned int * cost, unsigned int count, unsigned int seed);
+/* NEW (additive): a batch of edge scores in one launch; pairs = n x {node1, node2} score indices */
+PLL_EXPORT int pll_cuda_fastparsimony_edge_scores(const pll_parsimony_t * parsimony, const unsigned int * pairs,
+                                                  unsigned int n, unsigned int * scores);
+/* NEW (additive): copy node `index`'s vector (states x packedvector_count words) to the host */
+PLL_EXPORT int pll_cuda_download_parsimony_vector(const pll_parsimony_t * parsimony, unsigned int index,
+                                                  unsigned int * dst);
+
+/* Re-entrant random numbers, src/random.c (pll.h:534-547, 2592-2612): glibc's random_r family (additive
+ * feedback generator r[i] = r[i-3] + r[i-31] for the default 128-byte state), so that seeds give the
+ * reference's sequences. */
+struct pll_random_data
+{
+  int * fptr;
+  int * rptr;
+  int * state;
+  int rand_type;
+  int rand_deg;
+  int rand_sep;
+  int * end_ptr;
+};
+typedef struct pll_random_state_s
+{
+  struct pll_random_data rdata;
+  char * state_buf;
+} pll_random_state;
+PLL_EXPORT int pll_random_r(struct pll_random_data * buf, int * result);
+PLL_EXPORT int pll_srandom_r(unsigned int seed, struct pll_random_data * buf);
+PLL_EXPORT int pll_initstate_r(unsigned int seed, char * arg_state, size_t n, struct pll_random_data * buf);
+PLL_EXPORT int pll_setstate_r(char * arg_state, struct pll_random_data * buf);
+PLL_EXPORT pll_random_state * pll_random_create(unsigned int seed);
+PLL_EXPORT int pll_random_getint(pll_random_state * rstate, int maxval);
+PLL_EXPORT void pll_random_destroy(pll_random_state * rstate);
 
 #ifdef __cplusplus
 }

@@ -110,6 +110,76 @@ class Operation(C.Structure):
 
 PartitionP = C.POINTER(Partition)
 
+
+class Parsimony(C.Structure):
+    """pll_parsimony_t (src/pll.h:467-492)"""
+    _fields_ = [
+        ("tips", C.c_uint),
+        ("inner_nodes", C.c_uint),
+        ("sites", C.c_uint),
+        ("states", C.c_uint),
+        ("attributes", C.c_uint),
+        ("alignment", C.c_size_t),
+        ("packedvector", C.POINTER(c_uint_p)),
+        ("node_cost", c_uint_p),
+        ("packedvector_count", C.c_uint),
+        ("const_cost", C.c_uint),
+        ("informative", C.POINTER(C.c_int)),
+        ("informative_count", C.c_uint),
+        ("score_buffers", C.c_uint),
+        ("ancestral_buffers", C.c_uint),
+        ("score_matrix", c_double_p),
+        ("sbuffer", C.POINTER(c_double_p)),
+        ("anc_states", C.POINTER(c_uint_p)),
+    ]
+
+
+class ParsBuildOp(C.Structure):
+    _fields_ = [("parent_score_index", C.c_uint), ("child1_score_index", C.c_uint), ("child2_score_index", C.c_uint)]
+
+
+class UNode(C.Structure):
+    """pll_unode_t (src/pll.h:388-400)"""
+
+
+UNode._fields_ = [("label", C.c_char_p), ("length", C.c_double), ("node_index", C.c_uint), ("clv_index", C.c_uint),
+                  ("scaler_index", C.c_int), ("pmatrix_index", C.c_uint), ("next", C.POINTER(UNode)),
+                  ("back", C.POINTER(UNode)), ("data", C.c_void_p)]
+
+
+class UTree(C.Structure):
+    _fields_ = [("tip_count", C.c_uint), ("inner_count", C.c_uint), ("edge_count", C.c_uint), ("binary", C.c_int),
+                ("nodes", C.POINTER(C.POINTER(UNode))), ("vroot", C.POINTER(UNode))]
+
+
+class RandomData(C.Structure):
+    """struct pll_random_data (src/pll.h:534-543)"""
+    _fields_ = [("fptr", C.POINTER(C.c_int)), ("rptr", C.POINTER(C.c_int)), ("state", C.POINTER(C.c_int)),
+                ("rand_type", C.c_int), ("rand_deg", C.c_int), ("rand_sep", C.c_int), ("end_ptr", C.POINTER(C.c_int))]
+
+
+ParsimonyP = C.POINTER(Parsimony)
+
+# Fitch parsimony and the random_r family: the same names in the reference build and in ours
+_PARS_PROTOS = {
+    "pll_fastparsimony_init": (ParsimonyP, [PartitionP]),
+    "pll_fastparsimony_update_vectors": (None, [ParsimonyP, C.POINTER(ParsBuildOp), C.c_uint]),
+    "pll_fastparsimony_edge_score": (C.c_uint, [ParsimonyP, C.c_uint, C.c_uint]),
+    "pll_fastparsimony_root_score": (C.c_uint, [ParsimonyP, C.c_uint]),
+    "pll_parsimony_destroy": (None, [ParsimonyP]),
+    "pll_fastparsimony_stepwise": (
+        C.POINTER(UTree), [C.POINTER(ParsimonyP), C.POINTER(C.c_char_p), c_uint_p, C.c_uint, C.c_uint]),
+    "pll_utree_create_pars_buildops": (
+        None, [C.POINTER(C.POINTER(UNode)), C.c_uint, C.POINTER(ParsBuildOp), c_uint_p]),
+    "pll_random_r": (C.c_int, [C.POINTER(RandomData), C.POINTER(C.c_int)]),
+    "pll_srandom_r": (C.c_int, [C.c_uint, C.POINTER(RandomData)]),
+    "pll_initstate_r": (C.c_int, [C.c_uint, C.c_char_p, C.c_size_t, C.POINTER(RandomData)]),
+    "pll_setstate_r": (C.c_int, [C.c_char_p, C.POINTER(RandomData)]),
+    "pll_random_create": (C.c_void_p, [C.c_uint]),
+    "pll_random_getint": (C.c_int, [C.c_void_p, C.c_int]),
+    "pll_random_destroy": (None, [C.c_void_p]),
+}
+
 _PROTOS = {
     "pll_partition_create": (PartitionP, [C.c_uint] * 9),
     "pll_partition_destroy": (None, [PartitionP]),
@@ -180,6 +250,8 @@ _CUDA_PROTOS = {
     "pll_cuda_invalidate_host_arrays": (C.c_int, [PartitionP]),
     "pll_cuda_schedule_levels": (C.c_int, [C.POINTER(Operation), C.c_uint, c_uint_p]),
     "pll_cuda_kernel_launches": (C.c_ulonglong, []),
+    "pll_cuda_fastparsimony_edge_scores": (C.c_int, [ParsimonyP, c_uint_p, C.c_uint, c_uint_p]),
+    "pll_cuda_download_parsimony_vector": (C.c_int, [ParsimonyP, C.c_uint, c_uint_p]),
     "pll_cuda_host_eigen": (
         C.c_int,
         [C.c_uint, C.c_uint, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p],
@@ -202,6 +274,11 @@ class PllLibrary:
             fn = getattr(self.lib, name)
             fn.restype, fn.argtypes = res, args
             setattr(self, name, fn)
+        for name, (res, args) in _PARS_PROTOS.items():
+            if hasattr(self.lib, name):
+                fn = getattr(self.lib, name)
+                fn.restype, fn.argtypes = res, args
+                setattr(self, name, fn)
         self.is_cuda = hasattr(self.lib, "pll_cuda_device_count") if cuda is None else cuda
         if self.is_cuda:
             for name, (res, args) in _CUDA_PROTOS.items():

@@ -218,6 +218,49 @@ int plf_fill_u32(plf_ctx_t * ctx, unsigned int * d, unsigned int value,
 int plf_upload_async(plf_ctx_t * ctx, void * dst, const void * src,
                      size_t bytes);
 
+/* ---- Fitch parsimony on packed bit vectors (src/fast_parsimony.c) -------- */
+typedef struct plf_pars plf_pars_t; /* pinned staging + small device lists */
+
+/* where the tip states come from (all device pointers): pattern-tip codes or
+ * tip CLVs, optionally compressed by site repeats */
+typedef struct plf_pars_tips
+{
+  unsigned int tips, sites, states, states_padded, rate_cats;
+  const unsigned char * const * d_tipchars;    /* [tips] or NULL */
+  const double * const * d_tipclv;             /* [tips] when d_tipchars==NULL */
+  const unsigned int * const * d_tip_site_id;  /* [tips] (entries may be NULL) or NULL */
+  const unsigned long long * d_tipmap;         /* code -> state mask (states != 4) */
+  const unsigned int * d_weights;              /* pattern weights [sites] */
+} plf_pars_tips_t;
+
+int plf_pars_create(plf_ctx_t * ctx, plf_pars_t ** out);
+void plf_pars_destroy(plf_pars_t * ps);
+/* informative flags [sites], bit position of every site [sites+1]; totals to
+ * the host (fast_parsimony.c:381-413 and :251-254) */
+int plf_pars_informative(plf_pars_t * ps, const plf_pars_tips_t * tp,
+                         int * d_informative, unsigned int * d_bitpos,
+                         unsigned int * h_bitcount, unsigned int * h_const_cost,
+                         unsigned int * h_informative_count);
+/* tip vectors [tips][states][words] (fast_parsimony.c:268-340) */
+int plf_pars_pack(plf_pars_t * ps, const plf_pars_tips_t * tp,
+                  const unsigned int * d_bitpos, unsigned int bitcount,
+                  unsigned int words, unsigned int * d_vec);
+/* h_ops: count x {parent, child1, child2}; one launch for the whole list */
+int plf_pars_update(plf_pars_t * ps, unsigned int * d_vec, unsigned int states,
+                    unsigned int words, const unsigned int * h_ops,
+                    unsigned int count, unsigned int * h_scores);
+/* h_pairs: n x {node1, node2}; one launch for the whole batch */
+int plf_pars_edge_scores(plf_pars_t * ps, const unsigned int * d_vec,
+                         unsigned int states, unsigned int words,
+                         const unsigned int * h_pairs, unsigned int n,
+                         unsigned int * h_scores);
+/* stepwise addition: mutations of merging pair e plus mutations of the merge
+ * against vector `third`, for all n candidate edges in one launch */
+int plf_pars_insert_scan(plf_pars_t * ps, const unsigned int * d_vec,
+                         unsigned int states, unsigned int words,
+                         const unsigned int * h_pairs, unsigned int n,
+                         unsigned int third, unsigned int * h_scores);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@
 
 #include "pll_b200.h"
 #include "plf_backend.h"
+#include "pll_host_internal.h"
 
 __thread int pll_errno;
 __thread char pll_errmsg[200] = {0};
@@ -1416,6 +1417,60 @@ done:
   if (d) plf_free(cp->ctx, d);
   free(h);
   return ok;
+}
+
+/* tip states as the parsimony kernels read them (pll_parsimony.c); same pointer-table layout as
+ * invariant_on_device.  Sets pll_errno on failure. */
+int pll_cuda_internal_tipsource(const pll_partition_t * partition, pll_cuda_tipsource_t * out)
+{
+  cuda_partition_t * cp = CP(partition);
+  pll_partition_t * p;
+  const size_t nb = cp ? (size_t)cp->pub.tips * sizeof(void *) : 0;
+  void ** h = NULL, ** d = NULL;
+  unsigned int i;
+  int pattern, any_ids = 0;
+  if (!cp) return PLL_FAILURE;
+  p = &cp->pub;
+  pattern = (p->attributes & PLL_ATTRIB_PATTERN_TIP) != 0;
+  memset(out, 0, sizeof(*out));
+  h = (void **)calloc(2 * (size_t)p->tips + 1, sizeof(void *));
+  d = (void **)plf_alloc(cp->ctx, 2 * nb + 8, 0);
+  if (!h || !d) goto fail;
+  if (pattern)
+  {
+    if (!cp->d_tipchars) goto fail;
+    for (i = 0; i < p->tips; ++i) h[i] = cp->d_tipchars[i];
+    if (!tipmap_on_device(cp)) goto fail;
+  }
+  else
+    for (i = 0; i < p->tips; ++i)
+    {
+      h[i] = p->clv[i];
+      if (p->repeats && p->repeats->pernode_ids[i])
+      {
+        h[p->tips + i] = cp->d_site_id[i];
+        any_ids = 1;
+      }
+    }
+  if (!weights_on_device(cp) || !plf_upload(cp->ctx, d, h, 2 * nb) || !plf_sync(cp->ctx)) goto fail;
+  free(h);
+  out->ctx = cp->ctx;
+  out->d_ptrs = d;
+  out->tips.tips = p->tips;
+  out->tips.sites = p->sites;
+  out->tips.states = p->states;
+  out->tips.states_padded = p->states_padded;
+  out->tips.rate_cats = p->rate_cats;
+  out->tips.d_tipchars = pattern ? (const unsigned char * const *)d : NULL;
+  out->tips.d_tipclv = pattern ? NULL : (const double * const *)d;
+  out->tips.d_tip_site_id = any_ids ? (const unsigned int * const *)(d + p->tips) : NULL;
+  out->tips.d_tipmap = cp->d_tipmap;
+  out->tips.d_weights = cp->d_pattern_weights;
+  return PLL_SUCCESS;
+fail:
+  if (d) plf_free(cp->ctx, d);
+  free(h);
+  return cuda_fail(cp);
 }
 
 PLL_EXPORT int pll_update_invariant_sites(pll_partition_t * partition)

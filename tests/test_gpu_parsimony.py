@@ -1,0 +1,295 @@
+"""Fitch parsimony on the GPU (libpll-2_b200/csrc/plf_parsimony.cu + pll_parsimony.c) against
+the UNMODIFIED reference (src/fast_parsimony.c, src/stepwise.c in oracle/_ref) on identical seeded inputs.
+
+Everything is integer work: informative flags, constant cost, packed tip vectors, every updated vector, node
+costs, edge and root scores, and the stepwise-addition tree and its cost must be IDENTICAL.  The reference runs
+with PLL_ATTRIB_ARCH_CPU so that its vectors are not padded to a SIMD width (the padding words are all ones and
+never change a score); padded AVX2 vectors are compared on their common prefix in one case.
+"""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+pkg = importlib.import_module("libpll-2_b200")
+capi = pkg.capi
+synth = importlib.import_module("libpll-2_b200.synth")
+harness = importlib.import_module("libpll-2_b200.harness")
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ds(kind, tips, sites, seed, weights=False):
+    if kind == "dna":
+        ds = synth.dna_dataset(tips, sites, seed=seed, alpha=0.5, weights=weights, brlen=(0.05, 0.4))
+    elif kind == "aa":
+        ds = synth.aa_dataset(tips, sites, seed=seed, alpha=0.5, brlen=(0.05, 0.4))
+        if weights:
+            ds.pattern_weights = np.random.default_rng(seed).integers(1, 5, size=sites).astype(np.uint32)
+    else:
+        ds = synth.generic_dataset(int(kind[1:]), tips, sites, seed=seed, brlen=(0.05, 0.4))
+    return ds
+
+
+class Pars:
+    """pll_fastparsimony_init on an Engine's partition, with readers that work for both libraries"""
+
+    def __init__(self, lib, eng):
+        self.lib, self.eng = lib, eng
+        self.p = lib.pll_fastparsimony_init(eng.p)
+        assert self.p, f"pll_fastparsimony_init failed: {lib.errno} {lib.errmsg}"
+        self.c = self.p.contents
+        self.nodes = self.c.tips + 3 * self.c.inner_nodes
+
+    def vector(self, i):
+        n = self.c.states * self.c.packedvector_count
+        if self.lib.is_cuda:
+            out = np.empty(n, dtype=np.uint32)
+            assert self.lib.pll_cuda_download_parsimony_vector(self.p, i, out.ctypes.data_as(capi.c_uint_p)) == 1
+            return out.reshape(self.c.states, -1)
+        return np.ctypeslib.as_array(self.c.packedvector[i], shape=(n,)).copy().reshape(self.c.states, -1)
+
+    def informative(self):
+        return np.ctypeslib.as_array(self.c.informative, shape=(self.c.sites,)).copy()
+
+    def costs(self):
+        return np.ctypeslib.as_array(self.c.node_cost, shape=(self.nodes,)).copy()
+
+    def update(self, triples):
+        ops = (capi.ParsBuildOp * len(triples))(*[capi.ParsBuildOp(*[int(x) for x in t]) for t in triples])
+        self.lib.pll_fastparsimony_update_vectors(self.p, ops, len(triples))
+
+    def close(self):
+        if self.p:
+            self.lib.pll_parsimony_destroy(self.p)
+            self.p = None
+
+
+def pars_pair(reflib, cudalib, ds, flags, ref_arch=capi.ARCH_CPU):
+    ref_eng = harness.Engine(reflib, ds, ref_arch | flags)
+    gpu_eng = harness.Engine(cudalib, ds, capi.ARCH_CUDA | flags)
+    return Pars(reflib, ref_eng), Pars(cudalib, gpu_eng)
+
+
+def tree_triples(ds):
+    return [(int(r[0]), int(r[2]), int(r[5])) for r in ds.tree.ops]
+
+
+CASES = [
+    # kind, tips, sites, attrs, weights
+    ("dna", 8, 1, capi.PATTERN_TIP, False),
+    ("dna", 8, 31, capi.PATTERN_TIP, False),
+    ("dna", 8, 32, capi.PATTERN_TIP, False),
+    ("dna", 9, 33, capi.PATTERN_TIP, True),
+    ("dna", 30, 2501, capi.PATTERN_TIP, False),
+    ("dna", 30, 2501, capi.PATTERN_TIP, True),
+    ("dna", 30, 2501, 0, True),
+    ("dna", 30, 2501, capi.SITE_REPEATS, False),
+    ("dna", 150, 4099, capi.PATTERN_TIP, False),
+    ("aa", 25, 1201, capi.PATTERN_TIP, False),
+    ("aa", 25, 1201, capi.PATTERN_TIP, True),
+    ("aa", 25, 601, 0, False),  # > 8 states from tip CLVs: the O(tips^2) informative kernel
+    ("aa", 25, 601, capi.SITE_REPEATS, False),
+    ("g5", 20, 777, capi.PATTERN_TIP, False),
+    ("g7", 20, 777, 0, False),
+]
+
+
+@pytest.mark.parametrize("kind,tips,sites,attrs,weights", CASES)
+def test_parsimony_matches_reference(reflib, cudalib, kind, tips, sites, attrs, weights):
+    ds = make_ds(kind, tips, sites, seed=tips + sites, weights=weights)
+    ref, gpu = pars_pair(reflib, cudalib, ds, attrs)
+    try:
+        for f in ("tips", "inner_nodes", "sites", "states", "packedvector_count", "const_cost", "informative_count"):
+            assert getattr(gpu.c, f) == getattr(ref.c, f), f
+        np.testing.assert_array_equal(gpu.informative(), ref.informative())
+        for t in range(tips):
+            np.testing.assert_array_equal(gpu.vector(t), ref.vector(t), err_msg=f"tip vector {t}")
+        triples = tree_triples(ds)
+        ref.update(triples)
+        gpu.update(triples)
+        np.testing.assert_array_equal(gpu.costs(), ref.costs())
+        for parent, _, _ in triples:
+            np.testing.assert_array_equal(gpu.vector(parent), ref.vector(parent), err_msg=f"vector {parent}")
+        a, b, _ = ds.tree.root_edge
+        assert cudalib.pll_fastparsimony_edge_score(gpu.p, a, b) == reflib.pll_fastparsimony_edge_score(ref.p, a, b)
+        assert cudalib.pll_fastparsimony_root_score(gpu.p, a) == reflib.pll_fastparsimony_root_score(ref.p, a)
+        # arbitrary pairs, singly and as one batch
+        rng = np.random.default_rng(3)
+        pairs = rng.integers(0, ds.tree.nodes, size=(40, 2)).astype(np.uint32)
+        want = [reflib.pll_fastparsimony_edge_score(ref.p, int(x), int(y)) for x, y in pairs]
+        got = np.zeros(len(pairs), dtype=np.uint32)
+        assert cudalib.pll_cuda_fastparsimony_edge_scores(
+            gpu.p, pairs.ctypes.data_as(capi.c_uint_p), len(pairs), got.ctypes.data_as(capi.c_uint_p)) == 1
+        assert got.tolist() == want
+        assert [cudalib.pll_fastparsimony_edge_score(gpu.p, int(x), int(y)) for x, y in pairs[:5]] == want[:5]
+    finally:
+        ref.close()
+        gpu.close()
+
+
+def test_partial_update_lists_and_recycled_vectors(reflib, cudalib):
+    """ops applied in several calls, and a list that overwrites a vector it read earlier (strict list order)"""
+    ds = make_ds("dna", 40, 3001, seed=5)
+    ref, gpu = pars_pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    try:
+        triples = tree_triples(ds)
+        for lo in range(0, len(triples), 7):
+            ref.update(triples[lo:lo + 7])
+            gpu.update(triples[lo:lo + 7])
+        np.testing.assert_array_equal(gpu.costs(), ref.costs())
+        top = ds.tree.nodes  # first unused directional vector
+        chain = [(top, 0, 1), (top + 1, top, 2), (top, top + 1, 3), (top + 1, top, top + 1), (top + 2, top + 1, top)]
+        ref.update(chain)
+        gpu.update(chain)
+        np.testing.assert_array_equal(gpu.costs(), ref.costs())
+        for v in (top, top + 1, top + 2):
+            np.testing.assert_array_equal(gpu.vector(v), ref.vector(v))
+    finally:
+        ref.close()
+        gpu.close()
+
+
+def test_simd_padded_reference_vectors_agree_on_the_common_prefix(reflib, cudalib):
+    ds = make_ds("dna", 20, 1000, seed=8)
+    ref, gpu = pars_pair(reflib, cudalib, ds, capi.PATTERN_TIP, ref_arch=capi.ARCH_AVX2)
+    try:
+        w = gpu.c.packedvector_count
+        assert ref.c.packedvector_count >= w
+        triples = tree_triples(ds)
+        ref.update(triples)
+        gpu.update(triples)
+        np.testing.assert_array_equal(gpu.costs(), ref.costs())
+        for v in list(range(20)) + [t[0] for t in triples]:
+            rv = ref.vector(v)
+            np.testing.assert_array_equal(gpu.vector(v), rv[:, :w])
+            assert (rv[:, w:] == 0xFFFFFFFF).all()
+    finally:
+        ref.close()
+        gpu.close()
+
+
+def test_parsimony_outlives_its_partition_and_rejects_bad_indices(cudalib):
+    ds = make_ds("dna", 10, 500, seed=2)
+    eng = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    p = Pars(cudalib, eng)
+    eng.close()
+    triples = tree_triples(ds)
+    p.update(triples)
+    a, b, _ = ds.tree.root_edge
+    s1 = cudalib.pll_fastparsimony_edge_score(p.p, a, b)
+    assert s1 == cudalib.pll_fastparsimony_root_score(p.p, a) or s1 > 0
+    before = p.costs()
+    p.update([(p.nodes, 0, 1)])
+    assert cudalib.errno == 113  # PLL_ERROR_PARAM_INVALID, nothing launched
+    np.testing.assert_array_equal(p.costs(), before)
+    p.close()
+
+
+def test_more_than_twenty_states_need_pattern_tips(cudalib):
+    ds = synth.generic_dataset(22, 6, 50, seed=4)
+    eng = harness.Engine(cudalib, ds, capi.ARCH_CUDA)
+    assert not cudalib.pll_fastparsimony_init(eng.p)
+    assert cudalib.errno == 129  # PLL_ERROR_STEPWISE_UNSUPPORTED (src/fast_parsimony.c:538-547)
+    eng.close()
+
+
+# ---- stepwise addition ------------------------------------------------------------------------------------
+
+def splits(tree_p):
+    """the tree as a set of tip-label bipartitions (independent of node order and rooting)"""
+    t = tree_p.contents
+    all_labels = set()
+    out = set()
+
+    def below(n):
+        if not n.next:
+            lab = n.label.decode()
+            all_labels.add(lab)
+            return frozenset([lab])
+        s = below(n.next.contents.back.contents) | below(n.next.contents.next.contents.back.contents)
+        out.add(s)
+        return s
+
+    root = t.vroot.contents
+    a = below(root)
+    b = below(root.back.contents)
+    assert not (a & b)
+    everything = frozenset(all_labels)
+    canon = set()
+    for s in out:
+        if 1 < len(s) < len(everything) - 1:
+            canon.add(min(s, everything - s, key=lambda x: (len(x), sorted(x))))
+    return canon, everything
+
+
+def run_stepwise(lib, pars_list, labels, seed):
+    arr = (capi.ParsimonyP * len(pars_list))(*[p.p for p in pars_list])
+    lab = (C.c_char_p * len(labels))(*[x.encode() for x in labels])
+    cost = C.c_uint(0)
+    tree = lib.pll_fastparsimony_stepwise(arr, lab, C.byref(cost), len(pars_list), seed)
+    assert tree, f"stepwise failed: {lib.errno} {lib.errmsg}"
+    return tree, cost.value
+
+
+@pytest.mark.parametrize("kind,tips,sites,attrs,seed", [
+    ("dna", 3, 200, capi.PATTERN_TIP, 1),
+    ("dna", 4, 200, capi.PATTERN_TIP, 0),
+    ("dna", 25, 1500, capi.PATTERN_TIP, 0),
+    ("dna", 25, 1500, capi.PATTERN_TIP, 1),
+    ("dna", 25, 1500, 0, 42),
+    ("dna", 60, 3000, capi.PATTERN_TIP, 7),
+    ("dna", 60, 40, capi.PATTERN_TIP, 3),  # few sites: many ties, the first minimal edge must win
+    ("aa", 30, 800, capi.PATTERN_TIP, 12345),
+    ("g5", 18, 600, capi.PATTERN_TIP, 99),
+])
+def test_stepwise_addition_builds_the_reference_tree(reflib, cudalib, kind, tips, sites, attrs, seed):
+    ds = make_ds(kind, tips, sites, seed=tips * 3 + sites)
+    ref, gpu = pars_pair(reflib, cudalib, ds, attrs)
+    labels = [f"taxon{i:03d}" for i in range(tips)]
+    try:
+        t_ref, c_ref = run_stepwise(reflib, [ref], labels, seed)
+        t_gpu, c_gpu = run_stepwise(cudalib, [gpu], labels, seed)
+        assert c_gpu == c_ref
+        s_ref, l_ref = splits(t_ref)
+        s_gpu, l_gpu = splits(t_gpu)
+        assert l_gpu == l_ref == frozenset(labels)
+        assert s_gpu == s_ref
+        g = t_gpu.contents
+        assert (g.tip_count, g.inner_count, g.edge_count, g.binary) == (tips, tips - 2, 2 * tips - 3, 1)
+    finally:
+        ref.close()
+        gpu.close()
+
+
+def test_stepwise_over_two_partitions(reflib, cudalib):
+    tips = 20
+    ds1 = make_ds("dna", tips, 900, seed=31)
+    ds2 = make_ds("dna", tips, 400, seed=32, weights=True)
+    r1, g1 = pars_pair(reflib, cudalib, ds1, capi.PATTERN_TIP)
+    r2, g2 = pars_pair(reflib, cudalib, ds2, capi.PATTERN_TIP)
+    labels = [f"t{i}" for i in range(tips)]
+    try:
+        t_ref, c_ref = run_stepwise(reflib, [r1, r2], labels, 5)
+        t_gpu, c_gpu = run_stepwise(cudalib, [g1, g2], labels, 5)
+        assert c_gpu == c_ref
+        assert splits(t_gpu) == splits(t_ref)
+    finally:
+        for p in (r1, r2, g1, g2):
+            p.close()
+
+
+def test_stepwise_error_paths(cudalib):
+    ds = make_ds("dna", 5, 100, seed=1)
+    eng = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    p = Pars(cudalib, eng)
+    p.c.tips = 2
+    arr = (capi.ParsimonyP * 1)(p.p)
+    lab = (C.c_char_p * 5)(*[b"a", b"b", b"c", b"d", b"e"])
+    cost = C.c_uint(0)
+    assert not cudalib.pll_fastparsimony_stepwise(arr, lab, C.byref(cost), 1, 1)
+    assert cudalib.errno == 128  # PLL_ERROR_STEPWISE_TIPS
+    p.c.tips = 5
+    p.close()
+    eng.close()
