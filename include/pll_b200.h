@@ -110,6 +110,12 @@ extern "C" {
 #define PLL_ERROR_FASTA_INVALIDHEADER 203
 #define PLL_ERROR_FASTA_NONALIGNED 204
 #define PLL_ERROR_NEWICK_SYNTAX 111
+/* src/pll.h:163-167 */
+#define PLL_ERROR_PHYLIP_SYNTAX 231
+#define PLL_ERROR_PHYLIP_LONGSEQ 232
+#define PLL_ERROR_PHYLIP_NONALIGNED 233
+#define PLL_ERROR_PHYLIP_ILLEGALCHAR 234
+#define PLL_ERROR_PHYLIP_UNPRINTABLECHAR 235
 /* src/pll.h:184-186 */
 #define PLL_ERROR_STEPWISE_STRUCT 127
 #define PLL_ERROR_STEPWISE_TIPS 128
@@ -590,6 +596,29 @@ PLL_EXPORT long pll_fasta_getfilepos(pll_fasta_t * fd);
 PLL_EXPORT int pll_fasta_rewind(pll_fasta_t * fd);
 PLL_EXPORT pll_msa_t * pll_fasta_load(const char * fname);
 PLL_EXPORT void pll_msa_destroy(pll_msa_t * msa);
+
+/* PHYLIP reader, src/phylip.c (handle: src/pll.h:371-384; prototypes pll.h:986-1001); pll_phylip.c */
+typedef struct pll_phylip_s
+{
+  FILE * fp;
+  char * line;
+  size_t line_size;
+  size_t line_maxsize;
+  char buffer[PLL_LINEALLOC];
+  const unsigned int * chrstatus;
+  long no;
+  long filesize;
+  long lineno;
+  long stripped_count;
+  long stripped[256];
+} pll_phylip_t;
+PLL_EXPORT extern const unsigned int pll_map_phylip[256];
+PLL_EXPORT pll_phylip_t * pll_phylip_open(const char * filename, const unsigned int * map);
+PLL_EXPORT int pll_phylip_rewind(pll_phylip_t * fd);
+PLL_EXPORT void pll_phylip_close(pll_phylip_t * fd);
+PLL_EXPORT pll_msa_t * pll_phylip_parse_interleaved(pll_phylip_t * fd);
+PLL_EXPORT pll_msa_t * pll_phylip_parse_sequential(pll_phylip_t * fd);
+PLL_EXPORT pll_msa_t * pll_phylip_load(const char * fname, pll_bool_t interleaved);
 
 /* ---- tree structures and operation-list producers (pll_tree.c; host only) ------------------ */
 

@@ -85,3 +85,28 @@ void pll_utree_graph_destroy(void * root, void (*cb_destroy)(void *))
   (void)root;
   (void)cb_destroy;
 }
+
+/* src/parse_utree.y: frees what the wrapper above allocated and the node records of a binary tree */
+void pll_utree_destroy(void * vtree, void (*cb_destroy)(void *))
+{
+  stub_utree_t * t = (stub_utree_t *)vtree;
+  unsigned int i;
+  if (!t) return;
+  for (i = 0; i < t->tip_count + t->inner_count; ++i)
+  {
+    stub_unode_t * n = t->nodes[i];
+    if (n->next)
+    {
+      stub_unode_t * a = n->next, * b = n->next->next;
+      if (cb_destroy && a->data) cb_destroy(a->data);
+      if (cb_destroy && b->data) cb_destroy(b->data);
+      free(a);
+      free(b);
+    }
+    if (cb_destroy && n->data) cb_destroy(n->data);
+    free(n->label);
+    free(n);
+  }
+  free(t->nodes);
+  free(t);
+}

@@ -126,6 +126,26 @@ def test_newick_fasta_unrooted_example(cudalib, reflib, tmp_path):
     assert f"Number of tip/leaf nodes in tree: 23" in out
 
 
+def test_newick_phylip_unrooted_matches_the_reference_likelihood(cudalib, reflib, tmp_path):
+    """examples/newick-phylip-unrooted: the same pipeline fed from an interleaved PHYLIP file (pll_phylip.c)"""
+    exe = os.path.join(BIN, "newick-phylip-unrooted")
+    if not os.path.exists(exe):
+        pytest.skip("example binaries not built")
+    newick, seqs, tree, _ = write_inputs(tmp_path, 23, 400, rooted=False)
+    phy = tmp_path / "aln.phy"
+    order = np.random.default_rng(9).permutation(23)
+    with open(phy, "w") as f:
+        f.write(f"23 {len(seqs[0])}\n")
+        for k in range(0, len(seqs[0]), 60):
+            for i in order:
+                f.write((f"t{i}".ljust(10) if k == 0 else "") + seqs[i][k:k + 60].decode() + "\n")
+            f.write("\n")
+    out = run(exe, tree, str(phy), force_cuda=True)
+    got = float(re.search(r"Log-L: (-?[\d.]+)", out).group(1))
+    want = expected_unrooted_logl(reflib, newick, seqs)
+    assert abs(got - want) <= 5e-7 * abs(want) + 1e-6, (got, want)
+
+
 @pytest.mark.parametrize("name,rooted,nargs", [("partial-traversal", False, 2), ("newick-fasta-rooted", True, 2),
                                                ("load-utree", False, 1), ("newick-export", False, 1)])
 def test_file_driven_examples_run(cudalib, tmp_path, name, rooted, nargs):
@@ -137,6 +157,54 @@ def test_file_driven_examples_run(cudalib, tmp_path, name, rooted, nargs):
     assert out.strip()
     for m in re.findall(r"Log-L[^:]*: (-?[\d.]+(?:[eE][-+]?\d+)?|-?inf|nan)", out):
         assert np.isfinite(float(m)) and float(m) < 0, out[-400:]
+
+
+def newick_splits(newick):
+    """tip-label bipartitions of a Newick string (labels are plain words, lengths ignored)"""
+    text = re.sub(r":[-+0-9.eE]+", "", newick.strip().rstrip(";"))
+    stack, out, everything = [[]], [], set()
+    for tok in re.findall(r"[(),]|[^(),]+", text):
+        if tok == "(":
+            stack.append([])
+        elif tok == ")":
+            group = frozenset().union(*stack.pop())
+            out.append(group)
+            stack[-1].append(group)
+        elif tok != ",":
+            everything.add(tok)
+            stack[-1].append(frozenset([tok]))
+    everything = frozenset(everything)
+    canon = {min(s, everything - s, key=lambda x: (len(x), sorted(x))) for s in out if 1 < len(s) < len(everything) - 1}
+    return canon, everything
+
+
+@pytest.mark.parametrize("attrib,states,seed", [("tpcpu", 4, 1), ("cpu", 4, 7), ("tpcpu", 20, 3)])
+def test_stepwise_example_builds_the_same_tree(cudalib, tmp_path, attrib, states, seed):
+    """examples/stepwise/stepwise.c (FASTA -> pattern compression -> partition -> pll_fastparsimony_init ->
+    pll_fastparsimony_stepwise -> Newick), unmodified, linked against this library and against the reference
+    build: same parsimony score and the same tree (the printed Newick strings are rooted at a random inner node
+    of the library's node array, so they are compared as sets of bipartitions)."""
+    ours, ref = os.path.join(BIN, "stepwise"), os.path.join(BIN, "ref", "stepwise")
+    if not (os.path.exists(ours) and os.path.exists(ref)):
+        pytest.skip("example binaries not built (tests/examples/Makefile needs /root/reference)")
+    rng = np.random.default_rng(states + seed)
+    tips, sites = 24, 700
+    if states == 4:
+        ds = synth.dna_dataset(tips, sites, seed=seed, brlen=(0.05, 0.3))
+    else:
+        ds = synth.aa_dataset(tips, sites, seed=seed, brlen=(0.05, 0.3))
+    fasta = tmp_path / "aln.fa"
+    with open(fasta, "w") as f:
+        for i in rng.permutation(tips):
+            f.write(f">taxon{i}\n{ds.seqs[i].decode()}\n")
+    out_ref = run(ref, str(fasta), str(seed), attrib, str(states))
+    out_gpu = run(ours, str(fasta), str(seed), attrib, str(states), force_cuda=True)
+    score = lambda o: [x for x in o.splitlines() if x.startswith("Score:")]
+    assert score(out_gpu) == score(out_ref) and score(out_gpu)
+    tree = lambda o: [x for x in o.splitlines() if x.startswith("(")][0]
+    assert newick_splits(tree(out_gpu)) == newick_splits(tree(out_ref))
+    assert [x for x in out_gpu.splitlines() if x.startswith("Number of")] == \
+           [x for x in out_ref.splitlines() if x.startswith("Number of")]
 
 
 # ---- the reference's own test programs against their golden outputs ------------------------------
