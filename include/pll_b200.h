@@ -772,6 +772,16 @@ PLL_EXPORT void pll_utree_create_pars_buildops(pll_unode_t * const * trav_buffer
  * candidate edges in one launch.  Same tree and cost as the reference for the same seed. */
 PLL_EXPORT pll_utree_t * pll_fastparsimony_stepwise(pll_parsimony_t ** list, char * const * labels,
                                                     unsigned int * cost, unsigned int count, unsigned int seed);
+/* src/stepwise.c:731-881 (pll.h:2599): adds the taxa missing from `tree` by stepwise addition */
+PLL_EXPORT int pll_fastparsimony_stepwise_extend(pll_utree_t * tree, pll_parsimony_t ** pars_list,
+                                                 unsigned int pars_count, char * const * labels,
+                                                 const unsigned int * tip_msa_idmap, unsigned int seed,
+                                                 unsigned int * cost);
+/* src/stepwise.c:585-729 (pll.h:2591): one round of subtree pruning and regrafting, all edges per launch */
+PLL_EXPORT int pll_fastparsimony_stepwise_spr_round(pll_utree_t * tree, pll_parsimony_t ** pars_list,
+                                                    unsigned int pars_count, const unsigned int * tip_msa_idmap,
+                                                    unsigned int seed, const int * clv_index_map,
+                                                    unsigned int * cost);
 /* NEW (additive): a batch of edge scores in one launch; pairs = n x {node1, node2} score indices */
 PLL_EXPORT int pll_cuda_fastparsimony_edge_scores(const pll_parsimony_t * parsimony, const unsigned int * pairs,
                                                   unsigned int n, unsigned int * scores);

@@ -169,6 +169,10 @@ _PARS_PROTOS = {
     "pll_parsimony_destroy": (None, [ParsimonyP]),
     "pll_fastparsimony_stepwise": (
         C.POINTER(UTree), [C.POINTER(ParsimonyP), C.POINTER(C.c_char_p), c_uint_p, C.c_uint, C.c_uint]),
+    "pll_fastparsimony_stepwise_extend": (
+        C.c_int, [C.POINTER(UTree), C.POINTER(ParsimonyP), C.c_uint, C.POINTER(C.c_char_p), c_uint_p, C.c_uint, c_uint_p]),
+    "pll_fastparsimony_stepwise_spr_round": (
+        C.c_int, [C.POINTER(UTree), C.POINTER(ParsimonyP), C.c_uint, c_uint_p, C.c_uint, C.POINTER(C.c_int), c_uint_p]),
     "pll_utree_create_pars_buildops": (
         None, [C.POINTER(C.POINTER(UNode)), C.c_uint, C.POINTER(ParsBuildOp), c_uint_p]),
     "pll_random_r": (C.c_int, [C.POINTER(RandomData), C.POINTER(C.c_int)]),

@@ -276,30 +276,82 @@ PLL_EXPORT void pll_utree_create_pars_buildops(pll_unode_t * const * trav_buffer
   *ops_count = n;
 }
 
-/* ---- randomised stepwise addition (src/stepwise.c:883-1082) ------------------------------------------------
+/* ---- randomised stepwise addition and SPR rounds (src/stepwise.c) -----------------------------------------
  *
- * Tips are added in a shuffled order; each new tip is tried on every edge of the current tree and stays on the
- * first edge of minimal parsimony length.  The reference evaluates an edge with one vector update plus one edge
- * score (two passes over the vectors and two function calls per edge and partition).  Here:
+ * Tips (or, in an SPR round, pruned subtrees) are tried on every edge of the current tree and stay on the first
+ * edge of minimal parsimony length.  The reference evaluates an edge with one vector update plus one edge score
+ * (two passes over the vectors and two function calls per edge and partition).  Here, per insertion:
  *   1. every directional vector that the previous insertion invalidated is recomputed by ONE launch
  *      (plf_pars_update runs a whole dependency-ordered list),
  *   2. ALL candidate edges are scored by ONE launch (plf_pars_insert_scan: the merge of the edge's two
  *      vectors never leaves registers).
- * Costs are exact integers, the edge list grows in the reference's order and ties go to the first edge, so the
- * tree and its cost are those of the reference for the same seed.
+ * Costs are exact integers, the edge lists are the reference's and ties go to the first edge, so trees and
+ * costs are those of the reference for the same seed.
  */
 
 typedef struct stepwise
 {
+  pll_parsimony_t ** list;
   cuda_parsimony_t ** pars;
   unsigned int pars_count;
+  unsigned int nvec;
   unsigned char * valid;    /* per directional vector (node_index) */
   pll_pars_buildop_t * ops;
   unsigned int ops_count;
   unsigned int * pairs;     /* 2 per candidate edge */
-  unsigned int * scan;      /* per candidate edge */
+  unsigned int * which;     /* candidate -> position in the edge list */
+  unsigned int * scan;      /* per candidate */
   unsigned int * total;
 } stepwise_t;
+
+static void sw_release(stepwise_t * sw)
+{
+  free(sw->pars);
+  free(sw->valid);
+  free(sw->ops);
+  free(sw->pairs);
+  free(sw->which);
+  free(sw->scan);
+  free(sw->total);
+  memset(sw, 0, sizeof(*sw));
+}
+
+/* 1 ok, 0 failure with pll_errno set */
+static int sw_prepare(stepwise_t * sw, pll_parsimony_t ** list, unsigned int count)
+{
+  unsigned int i, tips;
+  memset(sw, 0, sizeof(*sw));
+  if (!list || !count || !list[0])
+  {
+    pars_error(PLL_ERROR_PARAM_INVALID, "Stepwise parsimony needs at least one parsimony structure.");
+    return 0;
+  }
+  tips = list[0]->tips;
+  sw->list = list;
+  sw->pars_count = count;
+  sw->nvec = tips + 3 * list[0]->inner_nodes;
+  sw->pars = (cuda_parsimony_t **)calloc(count, sizeof(cuda_parsimony_t *));
+  sw->valid = (unsigned char *)calloc(sw->nvec, 1);
+  sw->ops = (pll_pars_buildop_t *)malloc((size_t)3 * tips * sizeof(pll_pars_buildop_t));
+  sw->pairs = (unsigned int *)malloc((size_t)4 * tips * sizeof(unsigned int));
+  sw->which = (unsigned int *)malloc((size_t)2 * tips * sizeof(unsigned int));
+  sw->scan = (unsigned int *)malloc((size_t)2 * tips * sizeof(unsigned int));
+  sw->total = (unsigned int *)malloc((size_t)2 * tips * sizeof(unsigned int));
+  if (!sw->pars || !sw->valid || !sw->ops || !sw->pairs || !sw->which || !sw->scan || !sw->total)
+  {
+    sw_release(sw);
+    pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return 0;
+  }
+  for (i = 0; i < count; ++i)
+    if (!(sw->pars[i] = PP(list[i])) || list[i]->tips != tips || list[i]->inner_nodes != list[0]->inner_nodes)
+    {
+      if (sw->pars[i]) pars_error(PLL_ERROR_STEPWISE_STRUCT, "Parsimony structures tips/inner nodes not equal.");
+      sw_release(sw);
+      return 0;
+    }
+  return 1;
+}
 
 static pll_unode_t * sw_inner_create(unsigned int i, unsigned int tips)
 {
@@ -337,6 +389,15 @@ static void sw_split(pll_unode_t * a, pll_unode_t * b, pll_unode_t * c)
   sw_link(a, b);
 }
 
+/* takes the ring of p off the tree; returns one end of the edge that closes the gap (src/stepwise.c:338) */
+static pll_unode_t * sw_prune(pll_unode_t * p)
+{
+  pll_unode_t * a = p->next->back, * b = p->next->next->back;
+  sw_link(a, b);
+  p->next->back = p->next->next->back = NULL;
+  return a;
+}
+
 /* post-order list of the invalid vectors needed for the vector at `n` */
 static void sw_collect(stepwise_t * sw, pll_unode_t * n)
 {
@@ -359,12 +420,112 @@ static void sw_validate_below(stepwise_t * sw, pll_unode_t * n)
   sw_validate_below(sw, n->next->next->back);
 }
 
+/* Places the ring of v (v->back = the tip or pruned subtree to insert; v->next, v->next->next free) on the best
+ * of the edges; src/stepwise.c:436-583.  constraint (by clv_index) restricts the edges, prune_edge is where the
+ * subtree came from (SPR) or NULL (new tip: the two new edges are appended to the list).  Returns the cost of
+ * the tree after the placement; *failed is set on a CUDA error. */
+static unsigned int sw_insert_best(stepwise_t * sw, pll_unode_t ** edges, unsigned int edge_count, pll_unode_t * v,
+                                   const unsigned int * constraint, pll_unode_t * prune_edge, int * failed)
+{
+  const unsigned int third = v->back->node_index;
+  unsigned int e, k, n = 0, best = ~0u, min_cost = ~0u;
+
+  /* 1. bring every directional vector of the tree, and of the subtree to insert, up to date: one launch */
+  sw->ops_count = 0;
+  for (e = 0; e < edge_count; ++e)
+  {
+    sw_collect(sw, edges[e]);
+    sw_collect(sw, edges[e]->back);
+  }
+  sw_collect(sw, v->back);
+  pll_errno = 0;
+  for (k = 0; k < sw->pars_count; ++k)
+  {
+    pll_fastparsimony_update_vectors(sw->list[k], sw->ops, sw->ops_count);
+    if (pll_errno)
+    {
+      *failed = 1;
+      return ~0u;
+    }
+  }
+
+  /* 2. score the insertion on every admissible edge: one launch per partition */
+  for (e = 0; e < edge_count; ++e)
+  {
+    if (constraint)
+    {
+      const unsigned int s = constraint[v->clv_index];
+      if (s && s != constraint[edges[e]->clv_index] && s != constraint[edges[e]->back->clv_index]) continue;
+    }
+    sw->pairs[2 * n] = edges[e]->node_index;
+    sw->pairs[2 * n + 1] = edges[e]->back->node_index;
+    sw->which[n] = e;
+    sw->total[n] = 0;
+    ++n;
+  }
+  if (!n)
+  {
+    /* no admissible edge: back to where it came from (src/stepwise.c:533-544) */
+    sw->pairs[0] = prune_edge->node_index;
+    sw->pairs[1] = prune_edge->back->node_index;
+    sw->total[0] = 0;
+  }
+  for (k = 0; k < sw->pars_count; ++k)
+  {
+    cuda_parsimony_t * cp = sw->pars[k];
+    const unsigned int m = n ? n : 1;
+    if (!plf_pars_insert_scan(cp->ps, cp->d_vec, cp->pub.states, cp->pub.packedvector_count, sw->pairs, m, third,
+                              sw->scan))
+    {
+      pars_cuda_fail(cp);
+      *failed = 1;
+      return ~0u;
+    }
+    for (e = 0; e < m; ++e)
+      sw->total[e] += sw->scan[e] + cp->pub.node_cost[sw->pairs[2 * e]] + cp->pub.node_cost[sw->pairs[2 * e + 1]] +
+                      cp->pub.node_cost[third] + cp->pub.const_cost;
+  }
+  for (e = 0; e < n; ++e)
+    if (sw->total[e] < min_cost)
+    {
+      min_cost = sw->total[e];
+      best = sw->which[e];
+    }
+
+  /* 3. place it */
+  if (n)
+    sw_split(edges[best], v->next, v->next->next);
+  else
+  {
+    sw_split(prune_edge, v->next, v->next->next);
+    min_cost = sw->total[0];
+  }
+  if (!prune_edge)
+  {
+    edges[edge_count] = v;
+    edges[edge_count + 1] = v->next->next;
+  }
+
+  /* 4. after a new tip only the vectors that look away from it are still right; after an SPR none is trusted */
+  memset(sw->valid, 0, sw->nvec);
+  if (!prune_edge)
+  {
+    sw_validate_below(sw, v);
+    sw->valid[v->node_index] = 0; /* never stored: the scan kept the merge in registers */
+  }
+  return min_cost;
+}
+
 /* Fisher-Yates shuffle driven by the glibc-compatible generator (src/stepwise.c:56-106); seed 0 = identity */
 static unsigned int * sw_shuffled(unsigned int n, unsigned int seed)
 {
-  unsigned int * x = (unsigned int *)malloc((size_t)n * sizeof(unsigned int));
+  unsigned int * x = (unsigned int *)malloc(((size_t)n + 1) * sizeof(unsigned int));
   unsigned int i;
-  if (!x) return NULL;
+  if (!x)
+  {
+    pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return NULL;
+  }
   for (i = 0; i < n; ++i) x[i] = i;
   if (seed && n > 1)
   {
@@ -372,6 +533,7 @@ static unsigned int * sw_shuffled(unsigned int n, unsigned int seed)
     if (!rs)
     {
       free(x);
+      pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
       return NULL;
     }
     for (i = n; i-- > 0;)
@@ -390,45 +552,28 @@ static unsigned int * sw_shuffled(unsigned int n, unsigned int seed)
   return x;
 }
 
-static void sw_free_nodes(pll_unode_t ** tipn, unsigned int tips, pll_unode_t ** inner, unsigned int inners,
-                          pll_unode_t * root)
+static void sw_free_ring(pll_unode_t * n)
 {
-  unsigned int i;
-  pll_unode_t * n;
-  if (tipn)
-    for (i = 0; i < tips; ++i)
-      if (tipn[i])
-      {
-        free(tipn[i]->label);
-        free(tipn[i]);
-      }
-  if (inner)
-    for (i = 0; i < inners; ++i)
-      if ((n = inner[i]))
-      {
-        free(n->next->next);
-        free(n->next);
-        free(n);
-      }
-  if (root)
+  if (!n) return;
+  if (n->next)
   {
-    free(root->next->next);
-    free(root->next);
-    free(root);
+    free(n->next->next);
+    free(n->next);
   }
+  free(n->label);
+  free(n);
 }
 
 PLL_EXPORT pll_utree_t * pll_fastparsimony_stepwise(pll_parsimony_t ** list, char * const * labels,
                                                     unsigned int * cost, unsigned int count, unsigned int seed)
 {
-  unsigned int tips, inner_nodes, i, k, e, edge_count, nvec;
+  unsigned int tips, inner_nodes, i, edge_count;
   pll_unode_t * root = NULL, ** tipn = NULL, ** inner = NULL, ** edges = NULL;
   unsigned int * order = NULL;
   stepwise_t sw;
   pll_utree_t * tree = NULL;
   int failed = 0;
 
-  memset(&sw, 0, sizeof(sw));
   if (!list || !count || !list[0])
   {
     pars_error(PLL_ERROR_PARAM_INVALID, "Stepwise parsimony needs at least one parsimony structure.");
@@ -446,32 +591,15 @@ PLL_EXPORT pll_utree_t * pll_fastparsimony_stepwise(pll_parsimony_t ** list, cha
     pars_error(PLL_ERROR_STEPWISE_UNSUPPORTED, "Stepwise parsimony currently supports only unrooted trees.");
     return NULL;
   }
-  for (i = 1; i < count; ++i)
-    if (list[i]->tips != tips || list[i]->inner_nodes != inner_nodes)
-    {
-      pars_error(PLL_ERROR_STEPWISE_STRUCT, "Parsimony structures tips/inner nodes not equal.");
-      return NULL;
-    }
+  if (!sw_prepare(&sw, list, count)) return NULL;
   *cost = ~0u;
 
-  nvec = tips + 3 * inner_nodes;
-  sw.pars_count = count;
-  sw.pars = (cuda_parsimony_t **)calloc(count, sizeof(cuda_parsimony_t *));
-  sw.valid = (unsigned char *)calloc(nvec, 1);
-  sw.ops = (pll_pars_buildop_t *)malloc((size_t)3 * tips * sizeof(pll_pars_buildop_t));
-  sw.pairs = (unsigned int *)malloc((size_t)4 * tips * sizeof(unsigned int));
-  sw.scan = (unsigned int *)malloc((size_t)2 * tips * sizeof(unsigned int));
-  sw.total = (unsigned int *)malloc((size_t)2 * tips * sizeof(unsigned int));
   tipn = (pll_unode_t **)calloc(tips + 1, sizeof(pll_unode_t *));
   inner = (pll_unode_t **)calloc(tips - 2, sizeof(pll_unode_t *));
   edges = (pll_unode_t **)calloc(2 * (size_t)tips - 3, sizeof(pll_unode_t *));
   order = sw_shuffled(tips, seed);
   root = sw_inner_create(tips - 3, tips);
-  if (!sw.pars || !sw.valid || !sw.ops || !sw.pairs || !sw.scan || !sw.total || !tipn || !inner || !edges || !order ||
-      !root)
-    failed = 1;
-  for (i = 0; !failed && i < count; ++i)
-    if (!(sw.pars[i] = PP(list[i]))) failed = 2;
+  if (!tipn || !inner || !edges || !order || !root) failed = 1;
   for (i = 0; !failed && i + 3 < tips; ++i)
     if (!(inner[i] = sw_inner_create(i, tips))) failed = 1;
   for (i = 0; !failed && i < tips; ++i)
@@ -490,8 +618,7 @@ PLL_EXPORT pll_utree_t * pll_fastparsimony_stepwise(pll_parsimony_t ** list, cha
   }
   if (failed)
   {
-    if (failed == 1) pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
-    sw_free_nodes(tipn, tips, inner, tips - 3, root);
+    pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
     goto done;
   }
 
@@ -510,86 +637,266 @@ PLL_EXPORT pll_utree_t * pll_fastparsimony_stepwise(pll_parsimony_t ** list, cha
     *cost = 0;
     for (i = 0; i < count; ++i) *cost += list[i]->const_cost;
   }
-
-  for (i = 3; i < tips; ++i)
+  for (i = 3; i < tips && !failed; ++i)
   {
-    pll_unode_t * v = inner[i - 3]; /* v->back is the tip to insert, v->next / v->next->next are free */
-    unsigned int best = 0, min_cost = ~0u;
-
-    /* 1. bring every directional vector of the current tree up to date: one launch per partition */
-    sw.ops_count = 0;
-    for (e = 0; e < edge_count; ++e)
-    {
-      sw_collect(&sw, edges[e]);
-      sw_collect(&sw, edges[e]->back);
-    }
-    pll_errno = 0;
-    for (k = 0; k < count; ++k)
-    {
-      pll_fastparsimony_update_vectors(list[k], sw.ops, sw.ops_count);
-      if (pll_errno) failed = 2;
-    }
-
-    /* 2. score the new tip on every edge: one launch per partition */
-    for (e = 0; e < edge_count; ++e)
-    {
-      sw.pairs[2 * e] = edges[e]->node_index;
-      sw.pairs[2 * e + 1] = edges[e]->back->node_index;
-      sw.total[e] = 0;
-    }
-    for (k = 0; k < count && !failed; ++k)
-    {
-      cuda_parsimony_t * cp = sw.pars[k];
-      if (!plf_pars_insert_scan(cp->ps, cp->d_vec, cp->pub.states, cp->pub.packedvector_count, sw.pairs, edge_count,
-                                v->back->node_index, sw.scan))
-      {
-        pars_cuda_fail(cp);
-        failed = 2;
-        break;
-      }
-      for (e = 0; e < edge_count; ++e)
-        sw.total[e] += sw.scan[e] + cp->pub.node_cost[sw.pairs[2 * e]] + cp->pub.node_cost[sw.pairs[2 * e + 1]] +
-                       cp->pub.node_cost[v->back->node_index] + cp->pub.const_cost;
-    }
-    if (failed) break;
-    for (e = 0; e < edge_count; ++e)
-      if (sw.total[e] < min_cost)
-      {
-        min_cost = sw.total[e];
-        best = e;
-      }
-
-    /* 3. place it; the two new edges go to the end of the list (src/stepwise.c:546-553) */
-    sw_split(edges[best], v->next, v->next->next);
-    edges[edge_count++] = v;
-    edges[edge_count++] = v->next->next;
-    *cost = min_cost;
-
-    /* 4. only the vectors that look away from the new tip are still right */
-    memset(sw.valid, 0, nvec);
-    sw_validate_below(&sw, v);
-    sw.valid[v->node_index] = 0; /* never computed: the scan kept the merge in registers */
+    *cost = sw_insert_best(&sw, edges, edge_count, inner[i - 3], NULL, NULL, &failed);
+    edge_count += 2;
   }
-
-  if (failed)
-  {
-    /* the records are all linked into one graph or still in the lists: free them through the lists */
-    sw_free_nodes(tipn, tips, inner, tips - 3, root);
-    goto done;
-  }
-  tree = pll_utree_wraptree(root, tips);
-  if (!tree) sw_free_nodes(tipn, tips, inner, tips - 3, root);
+  if (!failed) tree = pll_utree_wraptree(root, tips);
 
 done:
-  free(sw.pars);
-  free(sw.valid);
-  free(sw.ops);
-  free(sw.pairs);
-  free(sw.scan);
-  free(sw.total);
+  if (!tree)
+  {
+    /* every record is still reachable through the lists */
+    for (i = 0; tipn && i < tips; ++i) sw_free_ring(tipn[i]);
+    for (i = 0; inner && i + 3 < tips; ++i) sw_free_ring(inner[i]);
+    sw_free_ring(root);
+  }
+  sw_release(&sw);
   free(tipn);
   free(inner);
   free(edges);
   free(order);
   return tree;
+}
+
+static int sw_cb_all(pll_unode_t * node)
+{
+  (void)node;
+  return 1;
+}
+
+/* the edges of the tree around `root`, one record per edge, in the reference's order (src/stepwise.c:352-375):
+ * the post-order node list with every tip replaced by the record it hangs on, minus the root itself */
+static int sw_collect_edges(pll_unode_t * root, pll_unode_t ** edges, unsigned int * edge_count)
+{
+  unsigned int i;
+  if (!pll_utree_traverse(root, PLL_TREE_TRAVERSE_POSTORDER, sw_cb_all, edges, edge_count)) return 0;
+  for (i = 0; i < *edge_count; ++i)
+    if (!edges[i]->next) edges[i] = edges[i]->back;
+  (*edge_count)--;
+  return 1;
+}
+
+/* src/stepwise.c:731-881: adds the taxa the tree does not have yet (those with index >= tree->tip_count in the
+ * parsimony structures; labels[i] names taxon tip_count + i) by stepwise addition in shuffled order.  The tree's
+ * node array is replaced; inner nodes keep their records, with clv/node indices shifted past the new tips. */
+PLL_EXPORT int pll_fastparsimony_stepwise_extend(pll_utree_t * tree, pll_parsimony_t ** pars_list,
+                                                 unsigned int pars_count, char * const * labels,
+                                                 const unsigned int * tip_msa_idmap, unsigned int seed,
+                                                 unsigned int * cost)
+{
+  stepwise_t sw;
+  unsigned int new_tips, new_inner, old_tips, old_inner, ext, i, edge_count = 0;
+  pll_unode_t ** nodes = NULL, ** edges = NULL;
+  unsigned int * order = NULL;
+  int failed = 0;
+
+  if (!tree || !sw_prepare(&sw, pars_list, pars_count)) return PLL_FAILURE;
+  new_tips = pars_list[0]->tips;
+  new_inner = new_tips - 2;
+  old_tips = tree->tip_count;
+  old_inner = tree->inner_count;
+  if (new_tips < old_tips || old_tips < 3)
+  {
+    sw_release(&sw);
+    pars_error(PLL_ERROR_PARAM_INVALID, "The tree has more tips than the parsimony structures (or fewer than 3).");
+    return PLL_FAILURE;
+  }
+  ext = new_tips - old_tips;
+  nodes = (pll_unode_t **)calloc((size_t)new_tips + new_inner, sizeof(pll_unode_t *));
+  edges = (pll_unode_t **)calloc(2 * (size_t)new_tips - 2, sizeof(pll_unode_t *));
+  order = sw_shuffled(ext, seed);
+  if (!nodes || !edges || !order) failed = 1;
+  for (i = 0; !failed && i < ext; ++i)
+  {
+    /* new tip old_tips+order[i] hangs on new inner node old_inner+i */
+    const unsigned int index = order[i] + old_tips;
+    pll_unode_t * tip = (pll_unode_t *)calloc(1, sizeof(pll_unode_t));
+    pll_unode_t * ring = sw_inner_create(old_inner + i, new_tips);
+    nodes[old_tips + i] = tip;
+    nodes[new_tips + old_inner + i] = ring;
+    if (tip)
+    {
+      tip->clv_index = tip->node_index = index;
+      tip->label = strdup(labels[index - old_tips]);
+    }
+    if (!tip || !ring || !tip->label)
+      failed = 1;
+    else
+      sw_link(ring, tip);
+  }
+  if (failed)
+  {
+    for (i = 0; nodes && i < ext; ++i)
+    {
+      sw_free_ring(nodes[old_tips + i]);
+      sw_free_ring(nodes[new_tips + old_inner + i]);
+    }
+    free(nodes);
+    free(edges);
+    free(order);
+    sw_release(&sw);
+    pars_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate memory for nodes!");
+    return PLL_FAILURE;
+  }
+  /* nothing below fails for lack of memory: the tree may now be changed */
+  for (i = 0; i < old_tips; ++i) nodes[i] = tree->nodes[i];
+  for (i = old_tips; i < old_tips + old_inner; ++i)
+  {
+    pll_unode_t * first = tree->nodes[i], * n = first;
+    nodes[i + ext] = first;
+    do
+    {
+      n->clv_index += ext;
+      n->node_index += ext;
+      n = n->next;
+    } while (n != first);
+  }
+  if (tip_msa_idmap)
+    for (i = 0; i < new_tips; ++i) nodes[i]->node_index = tip_msa_idmap[nodes[i]->node_index];
+
+  if (!sw_collect_edges(tree->vroot, edges, &edge_count)) failed = 1;
+  for (i = 0; i < ext && !failed; ++i)
+  {
+    *cost = sw_insert_best(&sw, edges, edge_count, nodes[new_tips + old_inner + i], NULL, NULL, &failed);
+    edge_count += 2;
+  }
+  if (failed)
+  {
+    /* rings that were not placed are still only in the list */
+    for (; i < ext; ++i)
+    {
+      pll_unode_t * ring = nodes[new_tips + old_inner + i];
+      if (ring->next->back) continue;
+      sw_free_ring(ring->back);
+      sw_free_ring(ring);
+      nodes[old_tips + i] = nodes[new_tips + old_inner + i] = NULL;
+    }
+  }
+  free(tree->nodes);
+  tree->nodes = nodes;
+  tree->tip_count = new_tips;
+  tree->inner_count = new_inner;
+  tree->edge_count = 2 * new_tips - 3;
+  tree->vroot = tree->vroot->next ? tree->vroot : tree->vroot->back;
+  free(edges);
+  free(order);
+  sw_release(&sw);
+  return failed ? PLL_FAILURE : PLL_SUCCESS;
+}
+
+/* src/stepwise.c:585-729: every subtree of the tree (three per inner node, in shuffled order) is pruned and put
+ * back on the best edge of the rest; clv_index_map groups inner nodes for constrained searches (a subtree of
+ * group g may only go next to group g); tip_msa_idmap renumbers tips whose order differs from the alignment's. */
+PLL_EXPORT int pll_fastparsimony_stepwise_spr_round(pll_utree_t * tree, pll_parsimony_t ** pars_list,
+                                                    unsigned int pars_count, const unsigned int * tip_msa_idmap,
+                                                    unsigned int seed, const int * clv_index_map,
+                                                    unsigned int * cost)
+{
+  stepwise_t sw;
+  unsigned int tips, inner, node_count, subtrees, ext, i, edge_count = 0;
+  pll_unode_t ** all = NULL, ** edges = NULL;
+  unsigned int * constraint = NULL, * orig = NULL, * order = NULL;
+  int failed = 0;
+
+  if (!tree || !sw_prepare(&sw, pars_list, pars_count)) return PLL_FAILURE;
+  tips = tree->tip_count;
+  inner = tree->inner_count;
+  node_count = tips + inner;
+  subtrees = 3 * inner;
+  if (pars_list[0]->tips < tips)
+  {
+    sw_release(&sw);
+    pars_error(PLL_ERROR_PARAM_INVALID, "The tree has more tips than the parsimony structures.");
+    return PLL_FAILURE;
+  }
+  ext = pars_list[0]->tips - tips;
+  all = (pll_unode_t **)calloc((size_t)subtrees + 1, sizeof(pll_unode_t *));
+  edges = (pll_unode_t **)calloc((size_t)tree->edge_count + 2, sizeof(pll_unode_t *));
+  constraint = (unsigned int *)calloc((size_t)node_count + ext + 1, sizeof(unsigned int));
+  orig = (unsigned int *)calloc((size_t)pars_list[0]->tips + 1, sizeof(unsigned int));
+  order = sw_shuffled(subtrees, seed);
+  if (!all || !edges || !constraint || !orig || !order)
+  {
+    free(all);
+    free(edges);
+    free(constraint);
+    free(orig);
+    free(order);
+    sw_release(&sw);
+    pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return PLL_FAILURE;
+  }
+  for (i = 0; i < node_count; ++i)
+  {
+    const unsigned int clv = tree->nodes[i]->clv_index;
+    constraint[clv] = (tree->nodes[i]->next && clv_index_map) ? (unsigned int)(clv_index_map[clv] + 1) : 0;
+  }
+  if (tip_msa_idmap)
+  {
+    /* score indices follow the numbering of the parsimony structures */
+    for (i = 0; i < tips; ++i)
+    {
+      const unsigned int old_idx = tree->nodes[i]->node_index, new_idx = tip_msa_idmap[old_idx];
+      tree->nodes[i]->node_index = new_idx;
+      orig[new_idx] = old_idx;
+    }
+    for (i = tips; i < node_count; ++i)
+    {
+      pll_unode_t * n = tree->nodes[i];
+      n->node_index += ext;
+      n->next->node_index += ext;
+      n->next->next->node_index += ext;
+    }
+  }
+  for (i = 0; i < inner; ++i)
+  {
+    pll_unode_t * n = tree->nodes[tips + i];
+    all[3 * i] = n;
+    all[3 * i + 1] = n->next;
+    all[3 * i + 2] = n->next->next;
+  }
+
+  for (i = 0; i < subtrees && !failed; ++i)
+  {
+    pll_unode_t * v = all[order[i]], * prune_edge, * new_root;
+    /* what is left must keep at least three taxa */
+    if (!v->next->back->next && !v->next->next->back->next) continue;
+    prune_edge = sw_prune(v);
+    new_root = prune_edge->next ? prune_edge : prune_edge->back;
+    if (!sw_collect_edges(new_root, edges, &edge_count))
+    {
+      sw_split(prune_edge, v->next, v->next->next);
+      failed = 1;
+      break;
+    }
+    {
+      const unsigned int c = sw_insert_best(&sw, edges, edge_count, v, clv_index_map ? constraint : NULL, prune_edge,
+                                            &failed);
+      if (failed)
+        sw_split(prune_edge, v->next, v->next->next); /* keep the tree whole */
+      else
+        *cost = c;
+    }
+  }
+
+  if (tip_msa_idmap)
+  {
+    for (i = 0; i < tips; ++i) tree->nodes[i]->node_index = orig[tree->nodes[i]->node_index];
+    for (i = tips; i < node_count; ++i)
+    {
+      pll_unode_t * n = tree->nodes[i];
+      n->node_index -= ext;
+      n->next->node_index -= ext;
+      n->next->next->node_index -= ext;
+    }
+  }
+  free(all);
+  free(edges);
+  free(constraint);
+  free(orig);
+  free(order);
+  sw_release(&sw);
+  return failed ? PLL_FAILURE : PLL_SUCCESS;
 }

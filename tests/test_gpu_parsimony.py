@@ -280,6 +280,102 @@ def test_stepwise_over_two_partitions(reflib, cudalib):
             p.close()
 
 
+# ---- extending a tree and SPR rounds: both libraries work on trees parsed by THIS library's Newick reader
+# (identical struct layouts), so node arrays, indices and hence the shuffled orders are the same on both sides
+
+def parse_tree(cudalib, newick):
+    f = cudalib.lib.pll_utree_parse_newick_string
+    f.restype, f.argtypes = C.POINTER(capi.UTree), [C.c_char_p]
+    t = f(newick.encode())
+    assert t, cudalib.errmsg
+    return t
+
+
+def export(cudalib, tree_p):
+    f = cudalib.lib.pll_utree_export_newick
+    f.restype, f.argtypes = C.c_void_p, [C.POINTER(capi.UNode), C.c_void_p]
+    t = tree_p.contents
+    raw = f(t.nodes[t.tip_count + t.inner_count - 1], None)
+    text = C.string_at(raw).decode()
+    return text
+
+
+def idmap_for(tree_p, n_pars_tips):
+    """tip node_index -> taxon number (labels are t<number>); identity beyond the tree's tips"""
+    t = tree_p.contents
+    m = np.arange(n_pars_tips, dtype=np.uint32)
+    for i in range(t.tip_count):
+        n = t.nodes[i].contents
+        m[n.node_index] = int(n.label.decode()[1:])
+    return m
+
+
+@pytest.mark.parametrize("tips,start,sites,seed", [(12, 4, 600, 0), (30, 11, 1500, 3), (30, 29, 900, 8), (16, 16, 300, 1)])
+def test_stepwise_extend_matches_reference(reflib, cudalib, tips, start, sites, seed):
+    import test_tree_cpu as tt
+
+    ds = make_ds("dna", tips, sites, seed=tips + start)
+    ref, gpu = pars_pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    # a random tree over taxa 0..start-1, whatever order they appear in
+    newick = tt.random_newick(np.random.default_rng(seed + 50), start)
+    labels = (C.c_char_p * (tips - start + 1))(*[f"t{i}".encode() for i in range(start, tips)], None)
+    out = []
+    try:
+        for lib, pars in ((reflib, ref), (cudalib, gpu)):
+            tree = parse_tree(cudalib, newick)
+            idmap = idmap_for(tree, tips)
+            arr = (capi.ParsimonyP * 1)(pars.p)
+            cost = C.c_uint(0)
+            rc = lib.pll_fastparsimony_stepwise_extend(tree, arr, 1, labels, idmap.ctypes.data_as(capi.c_uint_p), seed,
+                                                       C.byref(cost))
+            assert rc == 1, (lib.errno, lib.errmsg)
+            t = tree.contents
+            assert (t.tip_count, t.inner_count, t.edge_count) == (tips, tips - 2, 2 * tips - 3)
+            out.append((cost.value if tips > start else None, splits(tree), export(cudalib, tree)))
+        assert out[0][0] == out[1][0]
+        assert out[0][1] == out[1][1]
+        assert out[0][2] == out[1][2]  # same records in the same places: identical Newick text
+        assert out[1][1][1] == frozenset(f"t{i}" for i in range(tips))
+    finally:
+        ref.close()
+        gpu.close()
+
+
+@pytest.mark.parametrize("tips,sites,seed,constrained", [(10, 400, 1, False), (28, 1200, 5, False), (28, 1200, 0, False),
+                                                        (28, 300, 9, True), (45, 60, 4, False)])
+def test_spr_round_matches_reference(reflib, cudalib, tips, sites, seed, constrained):
+    import test_tree_cpu as tt
+
+    ds = make_ds("dna", tips, sites, seed=tips + sites)
+    ref, gpu = pars_pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    newick = tt.random_newick(np.random.default_rng(seed + 70), tips)  # a random (poor) tree: many SPRs improve it
+    rng = np.random.default_rng(seed)
+    # constraint groups per clv index (two groups split the inner nodes; a subtree only moves within its group)
+    cmap = (rng.integers(0, 2, size=2 * tips) if constrained else np.zeros(2 * tips)).astype(np.int32)
+    out = []
+    try:
+        for lib, pars in ((reflib, ref), (cudalib, gpu)):
+            tree = parse_tree(cudalib, newick)
+            idmap = idmap_for(tree, tips)
+            arr = (capi.ParsimonyP * 1)(pars.p)
+            cost = C.c_uint(0)
+            costs = []
+            for rnd in range(2):
+                rc = lib.pll_fastparsimony_stepwise_spr_round(tree, arr, 1, idmap.ctypes.data_as(capi.c_uint_p),
+                                                              seed + rnd, cmap.ctypes.data_as(C.POINTER(C.c_int)),
+                                                              C.byref(cost))
+                assert rc == 1, (lib.errno, lib.errmsg)
+                costs.append(cost.value)
+            out.append((costs, splits(tree), export(cudalib, tree)))
+        assert out[0][0] == out[1][0]
+        assert out[0][1] == out[1][1]
+        assert out[0][2] == out[1][2]
+        assert out[1][0][1] <= out[1][0][0]
+    finally:
+        ref.close()
+        gpu.close()
+
+
 def test_stepwise_error_paths(cudalib):
     ds = make_ds("dna", 5, 100, seed=1)
     eng = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
