@@ -539,6 +539,15 @@ PLL_EXPORT int pll_cuda_likelihood_derivatives_async(pll_partition_t * partition
                                                      const unsigned int * params_indices,
                                                      const double * sumtable,
                                                      double * dev_out2);
+/* NEW (additive): the whole Newton-Raphson loop on one branch (examples/newton/newton.c:67-96) in ONE
+ * cooperative launch and one host synchronisation: evaluate d_f, dd_f at the current length, stop when
+ * |d_f| < tolerance, else length -= d_f / dd_f clamped to [min_length, max_length]; at most max_iters
+ * evaluations.  *d_f, *dd_f are the derivatives at the last evaluated length. */
+PLL_EXPORT int pll_cuda_newton_branch(pll_partition_t * partition, int parent_scaler_index,
+                                      int child_scaler_index, double initial_length, double min_length,
+                                      double max_length, double tolerance, unsigned int max_iters,
+                                      const unsigned int * params_indices, const double * sumtable,
+                                      double * length, double * d_f, double * dd_f, unsigned int * iterations);
 
 /* Level schedule of an operation list (pure host logic, no device needed):
  * writes for each op the launch level it is batched into (ops of one level are

@@ -251,6 +251,11 @@ _CUDA_PROTOS = {
         C.c_int,
         [PartitionP, C.c_int, C.c_int, C.c_double, c_uint_p, c_double_p, C.c_void_p],
     ),
+    "pll_cuda_newton_branch": (
+        C.c_int,
+        [PartitionP, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint, c_uint_p, c_double_p,
+         c_double_p, c_double_p, c_double_p, c_uint_p],
+    ),
     "pll_cuda_invalidate_host_arrays": (C.c_int, [PartitionP]),
     "pll_cuda_schedule_levels": (C.c_int, [C.POINTER(Operation), C.c_uint, c_uint_p]),
     "pll_cuda_kernel_launches": (C.c_ulonglong, []),

@@ -148,6 +148,13 @@ int plf_update_sumtable(plf_ctx_t * ctx, const plf_shape_t * sh,
 int plf_derivatives(plf_ctx_t * ctx, const plf_shape_t * sh,
                     const plf_deriv_t * a, double * d_out2, double * h_out2);
 
+/* Newton-Raphson on one branch in ONE cooperative launch (the loop of
+ * examples/newton/newton.c:67-96): h_out4 = {length, d_f, dd_f, iterations} */
+int plf_newton_branch(plf_ctx_t * ctx, const plf_shape_t * sh,
+                      const plf_deriv_t * a, double t0, double tmin,
+                      double tmax, double tolerance, unsigned int max_iters,
+                      double * h_out4);
+
 /* invariant-site detection (models.c:651-752): AND over tips of the per-site
  * state masks; out[site] = state index or -1 */
 int plf_invariant_sites(plf_ctx_t * ctx, const plf_shape_t * sh,

@@ -19,6 +19,9 @@
 #include "plf_device.cuh"
 #include "plf_internal.h"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 /* model block accessors (layout in plf_backend.h) */
 struct Model
 {
@@ -355,32 +358,11 @@ extern "C" int plf_update_sumtable(plf_ctx_t * ctx, const plf_shape_t * sh, cons
   return 1;
 }
 
-/* ------------------------------------------------------------------------ *
- *  derivatives: per site L, L', L'' from the sumtable and                    *
- *  diag[r][j] = {e, lk e, (lk)^2 e}, e = exp(lambda_j k_r t),                 *
- *  k_r = rate_r / (1 - pinv_r)        (core_derivatives.c:757-772,825-848)   *
- * ------------------------------------------------------------------------ */
+/* per-thread share of sum_sites w (-L'/L) and sum_sites w ((L'/L)^2 - L''/L) for the diag table in shared memory */
 template <int ST>
-__global__ void __launch_bounds__(256)
-k_derivatives(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __restrict__ partial,
-              unsigned int * ticket, double * out, double * hout)
+__device__ __forceinline__ void deriv_accumulate(const plf_deriv_t & a, const Model & M, const double * diag, int R, int st,
+                                                 int sp, int L, double & acc1, double & acc2)
 {
-  extern __shared__ double diag[]; /* [R][st][3] */
-  __shared__ double red[32];
-  const int st = ST ? ST : st_rt;
-  const int sp = ST ? ((ST + 3) & ~3) : sp_rt;
-  const Model M(a.model, R, st, sp);
-  for (int x = threadIdx.x; x < R * st; x += blockDim.x)
-  {
-    const int r = x / st, j = x % st;
-    const double lam = M.evals[(size_t)r * sp + j];
-    const double ki = M.rates[r] / (1.0 - M.pinv[r]);
-    const double e = exp(lam * ki * a.branch_length);
-    diag[x * 3 + 0] = e;
-    diag[x * 3 + 1] = lam * ki * e;
-    diag[x * 3 + 2] = lam * ki * lam * ki * e;
-  }
-  __syncthreads();
   const int RT = R / L;
   const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned int nthreads = gridDim.x * blockDim.x;
@@ -390,7 +372,8 @@ k_derivatives(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __rest
   const unsigned int warp_site0 = (tid & ~31u) / L;
   const size_t span = (size_t)sp * R;
 
-  double acc1 = 0, acc2 = 0;
+  acc1 = 0;
+  acc2 = 0;
   for (unsigned int s0 = warp_site0; s0 < a.sites; s0 += sites_per_iter)
   {
     const unsigned int n = s0 + (my_site0 - warp_site0);
@@ -450,6 +433,42 @@ k_derivatives(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __rest
       acc2 = fma(w, d2, acc2);
     }
   }
+}
+
+/* diag[r][j] = {e, lk e, (lk)^2 e} for branch length t (every thread of the block takes part) */
+__device__ __forceinline__ void deriv_diag_table(const Model & M, double * diag, int R, int st, int sp, double t)
+{
+  for (int x = threadIdx.x; x < R * st; x += blockDim.x)
+  {
+    const int r = x / st, j = x % st;
+    const double lam = M.evals[(size_t)r * sp + j];
+    const double ki = M.rates[r] / (1.0 - M.pinv[r]);
+    const double e = exp(lam * ki * t);
+    diag[x * 3 + 0] = e;
+    diag[x * 3 + 1] = lam * ki * e;
+    diag[x * 3 + 2] = lam * ki * lam * ki * e;
+  }
+}
+
+/* ------------------------------------------------------------------------ *
+ *  derivatives: per site L, L', L'' from the sumtable and                    *
+ *  diag[r][j] = {e, lk e, (lk)^2 e}, e = exp(lambda_j k_r t),                 *
+ *  k_r = rate_r / (1 - pinv_r)        (core_derivatives.c:757-772,825-848)   *
+ * ------------------------------------------------------------------------ */
+template <int ST>
+__global__ void __launch_bounds__(256)
+k_derivatives(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __restrict__ partial,
+              unsigned int * ticket, double * out, double * hout)
+{
+  extern __shared__ double diag[]; /* [R][st][3] */
+  __shared__ double red[32];
+  const int st = ST ? ST : st_rt;
+  const int sp = ST ? ((ST + 3) & ~3) : sp_rt;
+  const Model M(a.model, R, st, sp);
+  deriv_diag_table(M, diag, R, st, sp, a.branch_length);
+  __syncthreads();
+  double acc1, acc2;
+  deriv_accumulate<ST>(a, M, diag, R, st, sp, L, acc1, acc2);
   const double v[2] = {acc1, acc2};
   grid_reduce_finish<2>(v, partial, ticket, out, hout, red);
 }
@@ -487,4 +506,167 @@ extern "C" int plf_derivatives(plf_ctx_t * ctx, const plf_shape_t * sh, const pl
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return plf_finish_reduction(ctx, 2, h_out2);
+}
+
+/* ------------------------------------------------------------------------ *
+ *  Newton-Raphson on one branch, entirely on the device (the loop of          *
+ *  examples/newton/newton.c:67-96, which calls                                *
+ *  pll_compute_likelihood_derivatives up to 32 times per branch and pays a    *
+ *  host round trip each time).  One cooperative launch: every iteration        *
+ *  re-reads the sumtable (L2-resident up to ~1M DNA sites), leaves per-block   *
+ *  partial sums in a ping-pong buffer, crosses ONE grid barrier, and every     *
+ *  block then adds all partials in the same fixed order, so all blocks take    *
+ *  the same step and agree on convergence without another exchange.            *
+ *  out[4] = {length, d_f, dd_f, iterations}.                                   *
+ * ------------------------------------------------------------------------ */
+struct plf_newton_args
+{
+  double t0, tmin, tmax, tolerance;
+  unsigned int max_iters;
+};
+
+/* two deterministic block sums for the price of one (results valid in thread 0); red >= 64 doubles */
+__device__ __forceinline__ void block_sum2(double & a, double & b, double * red)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0)
+  {
+    red[w] = a;
+    red[32 + w] = b;
+  }
+  __syncthreads();
+  if (w == 0)
+  {
+    const int nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(lane < nw ? red[lane] : 0.0);
+    b = warp_sum(lane < nw ? red[32 + lane] : 0.0);
+  }
+}
+
+template <int ST>
+__global__ void __launch_bounds__(1024)
+k_newton(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __restrict__ partial, plf_newton_args nw,
+         double * out, double * hout)
+{
+  extern __shared__ double diag2[]; /* two tables [R][st][3], used alternately */
+  __shared__ double red[64];
+  __shared__ double s_sum[2];
+  cg::grid_group grid = cg::this_grid();
+  const int st = ST ? ST : st_rt;
+  const int sp = ST ? ((ST + 3) & ~3) : sp_rt;
+  const Model M(a.model, R, st, sp);
+  double t = nw.t0, d1 = 0, d2 = 0;
+  unsigned int iters = 0;
+  for (unsigned int it = 0; it < nw.max_iters; ++it)
+  {
+    double * buf = partial + (size_t)(it & 1u) * 2 * gridDim.x;
+    double * diag = diag2 + (size_t)(it & 1u) * R * st * 3;
+    deriv_diag_table(M, diag, R, st, sp, t);
+    __syncthreads();
+    double acc1, acc2;
+    deriv_accumulate<ST>(a, M, diag, R, st, sp, L, acc1, acc2);
+    block_sum2(acc1, acc2, red);
+    if (threadIdx.x == 0)
+    {
+      buf[blockIdx.x] = acc1;
+      buf[gridDim.x + blockIdx.x] = acc2;
+    }
+    grid.sync();
+    /* the same additions in the same order in every block */
+    double p1 = 0, p2 = 0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+    {
+      p1 += __ldcg(buf + b);
+      p2 += __ldcg(buf + gridDim.x + b);
+    }
+    block_sum2(p1, p2, red);
+    if (threadIdx.x == 0)
+    {
+      s_sum[0] = p1;
+      s_sum[1] = p2;
+    }
+    __syncthreads();
+    d1 = s_sum[0];
+    d2 = s_sum[1];
+    iters = it + 1;
+    if (fabs(d1) < nw.tolerance) break;
+    double tn = t - d1 / d2;
+    if (tn < nw.tmin) tn = nw.tmin;
+    if (tn > nw.tmax) tn = nw.tmax;
+    if (!(tn == tn) || tn == t) break; /* NaN step, or pinned at a bound */
+    t = tn;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const double r[4] = {t, d1, d2, (double)iters};
+    for (int i = 0; i < 4; ++i)
+    {
+      out[i] = r[i];
+      if (hout) hout[i] = r[i];
+    }
+  }
+}
+
+template <int ST>
+static int newton_launch(plf_ctx * ctx, const plf_deriv_t * a, int R, int st, int sp, int L, const plf_newton_args & nw,
+                         size_t smem, double * dst, double * hdst)
+{
+  /* few, large blocks: the grid barrier and the re-reduction of the partials grow with the block count, and the
+   * table is L2-resident, so occupancy buys little (PLF_NEWTON_THREADS / PLF_NEWTON_BPS override for experiments) */
+  static int threads = 0, bps = 0;
+  if (!threads)
+  {
+    const char * v = getenv("PLF_NEWTON_THREADS");
+    const int t = v ? atoi(v) : 0;
+    threads = (t == 256 || t == 512 || t == 1024) ? t : 1024;
+    v = getenv("PLF_NEWTON_BPS");
+    bps = (v && atoi(v) > 0) ? atoi(v) : 1;
+  }
+  int per_sm = 0;
+  PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_newton<ST>, threads, smem));
+  if (per_sm < 1)
+  {
+    plf_set_error(ctx, "newton: kernel does not fit an SM");
+    return 0;
+  }
+  if (per_sm > bps) per_sm = bps;
+  unsigned int blocks = pick_blocks(ctx, (unsigned long long)a->sites * L, threads, per_sm);
+  double * partial = (double *)plf_ws_reserve(ctx, &ctx->ws_partial, (size_t)blocks * 4 * sizeof(double));
+  if (!partial) return 0;
+  plf_deriv_t args = *a;
+  plf_newton_args nwa = nw;
+  void * params[] = {&args, &R, &st, &sp, &L, &partial, &nwa, &dst, &hdst};
+  PLF_CHECK(ctx, cudaLaunchCooperativeKernel((const void *)k_newton<ST>, dim3(blocks), dim3(threads), params, smem,
+                                             ctx->stream));
+  plf_count_launch();
+  return 1;
+}
+
+/* h_out4 = {length, d_f, dd_f, iterations}; synchronises the stream */
+extern "C" int plf_newton_branch(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_deriv_t * a, double t0, double tmin,
+                                 double tmax, double tolerance, unsigned int max_iters, double * h_out4)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  const int R = (int)sh->rate_cats;
+  const int L = (int)pick_L(sh->rate_cats);
+  const size_t smem = (size_t)2 * R * sh->states * 3 * sizeof(double);
+  if (smem > 48 * 1024)
+  {
+    plf_set_error(ctx, "newton: rate_cats*states too large for the diag table (%zu B)", smem);
+    return 0;
+  }
+  plf_newton_args nw = {t0, tmin, tmax, tolerance, max_iters};
+  int ok;
+  if (sh->states == 4)
+    ok = newton_launch<4>(ctx, a, R, 4, 4, L, nw, smem, ctx->d_result, ctx->h_result);
+  else if (sh->states == 20)
+    ok = newton_launch<20>(ctx, a, R, 20, 20, L, nw, smem, ctx->d_result, ctx->h_result);
+  else
+    ok = newton_launch<0>(ctx, a, R, (int)sh->states, (int)sh->states_padded, L, nw, smem, ctx->d_result,
+                          ctx->h_result);
+  if (!ok) return 0;
+  return plf_finish_reduction(ctx, 4, h_out4);
 }

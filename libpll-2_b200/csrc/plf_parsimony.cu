@@ -267,6 +267,20 @@ fail:
 
 /* ---- bit packing ---------------------------------------------------------------------------------------- */
 
+/* bits [s, e) of the output word that site j covers, 0 when it covers none; stop = the walk is past the word */
+__device__ __forceinline__ unsigned int pars_site_mask(const unsigned int * __restrict__ bitpos, unsigned int j,
+                                                       unsigned long long lo, bool & stop)
+{
+  const unsigned long long b0 = bitpos[j], b1 = bitpos[j + 1];
+  stop = b0 >= lo + 32u;
+  if (stop || b1 == b0) return 0u;
+  const unsigned int s = (unsigned int)((b0 > lo ? b0 : lo) - lo);
+  const unsigned int e = (unsigned int)((b1 < lo + 32u ? b1 : lo + 32u) - lo); /* 1..32 */
+  const unsigned int upto = e == 32u ? ~0u : ((1u << e) - 1u);
+  return upto & ~((1u << s) - 1u);
+}
+
+template <int ST>
 __global__ void __launch_bounds__(128)
 k_pars_pack(pars_tips_dev a, const unsigned int * __restrict__ bitpos, unsigned int bitcount, unsigned int words,
             unsigned int * __restrict__ vec)
@@ -290,28 +304,39 @@ k_pars_pack(pars_tips_dev a, const unsigned int * __restrict__ bitpos, unsigned 
     if (bitpos[m + 1] > lo) r = m;
     else l = m + 1;
   }
-  unsigned long long code[32];
-  unsigned int mask[32];
-  int n = 0;
-  for (unsigned int j = l; j < a.sites; ++j)
-  {
-    const unsigned long long b0 = bitpos[j], b1 = bitpos[j + 1];
-    if (b0 >= lo + 32u) break;
-    if (b1 == b0) continue;
-    const unsigned int s = (unsigned int)((b0 > lo ? b0 : lo) - lo);
-    const unsigned int e = (unsigned int)((b1 < lo + 32u ? b1 : lo + 32u) - lo); /* 1..32 */
-    const unsigned int upto = e == 32u ? ~0u : ((1u << e) - 1u);
-    mask[n] = upto & ~((1u << s) - 1u);
-    code[n] = pars_tip_mask(a, t, j);
-    ++n;
-  }
   /* the unused tail of the last word is filled with ones (fast_parsimony.c:323-334) */
   const unsigned int pad = (bitcount - lo < 32u) ? ~((1u << (unsigned int)(bitcount - lo)) - 1u) : 0u;
+  if constexpr (ST > 0)
+  {
+    constexpr int N = ST > 0 ? ST : 1;
+    unsigned int v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = pad;
+    for (unsigned int j = l; j < a.sites; ++j)
+    {
+      bool stop;
+      const unsigned int m = pars_site_mask(bitpos, j, lo, stop);
+      if (stop) break;
+      if (!m) continue;
+      const unsigned long long c = pars_tip_mask(a, t, j);
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        if ((c >> k) & 1ull) v[k] |= m;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[(size_t)k * words] = v[k];
+  }
+  else /* any state count: one walk over the (at most 32) sites of the word per state row */
   for (unsigned int k = 0; k < a.states; ++k)
   {
     unsigned int v = pad;
-    for (int i = 0; i < n; ++i)
-      if ((code[i] >> k) & 1ull) v |= mask[i];
+    for (unsigned int j = l; j < a.sites; ++j)
+    {
+      bool stop;
+      const unsigned int m = pars_site_mask(bitpos, j, lo, stop);
+      if (stop) break;
+      if (m && ((pars_tip_mask(a, t, j) >> k) & 1ull)) v |= m;
+    }
     out[(size_t)k * words] = v;
   }
 }
@@ -331,7 +356,13 @@ extern "C" int plf_pars_pack(plf_pars_t * ps, const plf_pars_tips_t * tp, const 
   a.tipclv = tp->d_tipclv;
   a.site_id = tp->d_tip_site_id;
   a.tipmap = tp->d_tipmap;
-  k_pars_pack<<<dim3((words + 127) / 128, tp->tips), 128, 0, ctx->stream>>>(a, d_bitpos, bitcount, words, d_vec);
+  const dim3 grid((words + 127) / 128, tp->tips);
+  if (tp->states == 4)
+    k_pars_pack<4><<<grid, 128, 0, ctx->stream>>>(a, d_bitpos, bitcount, words, d_vec);
+  else if (tp->states == 20)
+    k_pars_pack<20><<<grid, 128, 0, ctx->stream>>>(a, d_bitpos, bitcount, words, d_vec);
+  else
+    k_pars_pack<0><<<grid, 128, 0, ctx->stream>>>(a, d_bitpos, bitcount, words, d_vec);
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;
@@ -341,7 +372,11 @@ extern "C" int plf_pars_pack(plf_pars_t * ps, const plf_pars_tips_t * tp, const 
 
 #define PARS_THREADS 128
 
-/* ST > 0: the state count is known at compile time and both children stay in registers */
+/* ST > 0: the state count is known at compile time and both children stay in registers.  The list is walked
+ * with one operation of look-ahead: the children of the next operation are fetched before the current one is
+ * finished, except a child that IS the current parent (the usual case in a post-order list: a subtree root is
+ * consumed right after it was made), which is handed over in registers.  The dependent store -> load round trip
+ * through L2 disappears from the chain and the remaining loads overlap the current operation. */
 template <int ST>
 __global__ void __launch_bounds__(PARS_THREADS)
 k_pars_update(unsigned int * vec, size_t node_stride, unsigned int states, unsigned int words,
@@ -350,40 +385,72 @@ k_pars_update(unsigned int * vec, size_t node_stride, unsigned int states, unsig
   const unsigned int word = blockIdx.x * PARS_THREADS + threadIdx.x;
   const bool active = word < words;
   const unsigned int w = active ? word : 0;
-  for (unsigned int o = 0; o < count; ++o)
+  if constexpr (ST > 0)
   {
-    /* plain (coherent) loads: a child may be a parent this same thread wrote earlier in the list */
-    unsigned int * parent = vec + ops[3 * o] * node_stride + w;
-    const unsigned int * c1 = vec + ops[3 * o + 1] * node_stride + w;
-    const unsigned int * c2 = vec + ops[3 * o + 2] * node_stride + w;
-    unsigned int orvand = 0;
-    if (ST > 0)
+    constexpr int N = ST > 0 ? ST : 1;
+    unsigned int x[N], y[N], nx[N], ny[N];
     {
-      unsigned int x[ST > 0 ? ST : 1], y[ST > 0 ? ST : 1];
+      const unsigned int * c1 = vec + ops[1] * node_stride + w;
+      const unsigned int * c2 = vec + ops[2] * node_stride + w;
 #pragma unroll
-      for (int j = 0; j < ST; ++j)
+      for (int j = 0; j < N; ++j)
       {
         x[j] = c1[(size_t)j * words];
         y[j] = c2[(size_t)j * words];
       }
-#pragma unroll
-      for (int j = 0; j < ST; ++j) orvand |= x[j] & y[j];
-      if (active)
-      {
-#pragma unroll
-        for (int j = 0; j < ST; ++j) parent[(size_t)j * words] = (x[j] & y[j]) | (~orvand & (x[j] | y[j]));
-      }
     }
-    else
+    for (unsigned int o = 0; o < count; ++o)
     {
-      for (unsigned int j = 0; j < states; ++j) orvand |= c1[(size_t)j * words] & c2[(size_t)j * words];
-      if (active)
-        for (unsigned int j = 0; j < states; ++j)
+      const unsigned int p = ops[3 * o];
+      unsigned int n1 = p, n2 = p;
+      if (o + 1 < count)
+      {
+        /* plain (coherent) loads: these vectors may have been written by this thread earlier in the list */
+        n1 = ops[3 * o + 4];
+        n2 = ops[3 * o + 5];
+        if (n1 != p)
         {
-          const unsigned int x = c1[(size_t)j * words], y = c2[(size_t)j * words];
-          parent[(size_t)j * words] = (x & y) | (~orvand & (x | y));
+          const unsigned int * c = vec + n1 * node_stride + w;
+#pragma unroll
+          for (int j = 0; j < N; ++j) nx[j] = c[(size_t)j * words];
         }
+        if (n2 != p)
+        {
+          const unsigned int * c = vec + n2 * node_stride + w;
+#pragma unroll
+          for (int j = 0; j < N; ++j) ny[j] = c[(size_t)j * words];
+        }
+      }
+      unsigned int orvand = 0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) orvand |= x[j] & y[j];
+      unsigned int * parent = vec + p * node_stride + w;
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+      {
+        const unsigned int v = (x[j] & y[j]) | (~orvand & (x[j] | y[j]));
+        if (active) parent[(size_t)j * words] = v;
+        x[j] = (n1 == p) ? v : nx[j];
+        y[j] = (n2 == p) ? v : ny[j];
+      }
+      const unsigned int pc = __reduce_add_sync(0xffffffffu, active ? (unsigned int)__popc(~orvand) : 0u);
+      if ((threadIdx.x & 31) == 0 && pc) atomicAdd(scores + o, pc);
     }
+  }
+  else
+  for (unsigned int o = 0; o < count; ++o)
+  {
+    unsigned int * parent = vec + ops[3 * o] * node_stride + w;
+    const unsigned int * c1 = vec + ops[3 * o + 1] * node_stride + w;
+    const unsigned int * c2 = vec + ops[3 * o + 2] * node_stride + w;
+    unsigned int orvand = 0;
+    for (unsigned int j = 0; j < states; ++j) orvand |= c1[(size_t)j * words] & c2[(size_t)j * words];
+    if (active)
+      for (unsigned int j = 0; j < states; ++j)
+      {
+        const unsigned int a = c1[(size_t)j * words], b = c2[(size_t)j * words];
+        parent[(size_t)j * words] = (a & b) | (~orvand & (a | b));
+      }
     const unsigned int pc = __reduce_add_sync(0xffffffffu, active ? (unsigned int)__popc(~orvand) : 0u);
     if ((threadIdx.x & 31) == 0 && pc) atomicAdd(scores + o, pc);
   }

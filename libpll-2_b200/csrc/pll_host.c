@@ -39,6 +39,8 @@ static __thread int tls_device = -1;
 #define PLL_CUDA_MAGIC 0xB200C0DEu
 #define EMPTY_ELEMENT 0xFFFFFFFFu
 #define MAX_SUMTABLES 8
+/* pll_cuda_newton_branch: tables up to this size use the one-launch loop (they stay in the 126 MB L2) */
+#define NEWTON_FUSED_MAX_BYTES ((size_t)96 << 20)
 /* the streaming kernels fetch scalers and tip codes with 16-byte bulk copies:
  * the last copy of a buffer may read up to 15 bytes past its logical end */
 #define BULK_PAD 16
@@ -2554,6 +2556,71 @@ PLL_EXPORT int pll_cuda_likelihood_derivatives_async(pll_partition_t * partition
   (void)child_scaler_index;
   if (!cp || !dev_out2 || !derivative_args(cp, &a, branch_length, params_indices, sumtable)) return PLL_FAILURE;
   return plf_derivatives(cp->ctx, &cp->shape, &a, dev_out2, NULL) ? PLL_SUCCESS : cuda_fail(cp);
+}
+
+/* NEW (additive).  The Newton-Raphson loop a client runs around pll_compute_likelihood_derivatives
+ * (examples/newton/newton.c:67-96: evaluate d_f, dd_f at the current length; stop when |d_f| < tolerance;
+ * otherwise length -= d_f / dd_f) as ONE device launch and ONE host synchronisation instead of one round
+ * trip per iteration.  Steps are clamped to [min_length, max_length]; the loop also stops when a step no
+ * longer changes the length.  Returns the length, the derivatives at the last evaluated length and the
+ * number of evaluations.  Not available with the Lewis / Felsenstein ascertainment corrections, whose
+ * terms are formed on the host per evaluation (use the per-call API there). */
+PLL_EXPORT int pll_cuda_newton_branch(pll_partition_t * partition, int parent_scaler_index, int child_scaler_index,
+                                      double initial_length, double min_length, double max_length, double tolerance,
+                                      unsigned int max_iters, const unsigned int * params_indices,
+                                      const double * sumtable, double * length, double * d_f, double * dd_f,
+                                      unsigned int * iterations)
+{
+  cuda_partition_t * cp = CP(partition);
+  plf_deriv_t a;
+  double out[4] = {0, 0, 0, 0};
+  (void)parent_scaler_index;
+  (void)child_scaler_index;
+  if (!cp) return PLL_FAILURE;
+  if ((partition->attributes & PLL_ATTRIB_AB_MASK) &&
+      (partition->attributes & PLL_ATTRIB_AB_MASK) != PLL_ATTRIB_AB_STAMATAKIS)
+  {
+    set_error(PLL_ERROR_CUDA_UNSUPPORTED, "pll_cuda_newton_branch: not with Lewis/Felsenstein ascertainment bias%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!max_iters || !(min_length <= max_length) || !(tolerance >= 0))
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "pll_cuda_newton_branch: invalid bounds, tolerance or iteration limit%s", NULL);
+    return PLL_FAILURE;
+  }
+  if (!derivative_args(cp, &a, initial_length, params_indices, sumtable)) return PLL_FAILURE;
+  if ((size_t)a.sites * partition->rate_cats * partition->states_padded * sizeof(double) > NEWTON_FUSED_MAX_BYTES)
+  {
+    /* a table that does not stay in L2 is streamed from HBM on every evaluation: there the streaming
+     * derivative kernels win and the host round trip is a small share, so the same rule is driven from here */
+    double t = initial_length, d[2] = {0, 0};
+    unsigned int it;
+    for (it = 0; it < max_iters;)
+    {
+      double tn;
+      a.branch_length = t;
+      if (!plf_derivatives(cp->ctx, &cp->shape, &a, NULL, d)) return cuda_fail(cp);
+      ++it;
+      if (fabs(d[0]) < tolerance) break;
+      tn = t - d[0] / d[1];
+      if (tn < min_length) tn = min_length;
+      if (tn > max_length) tn = max_length;
+      if (!(tn == tn) || tn == t) break;
+      t = tn;
+    }
+    out[0] = t;
+    out[1] = d[0];
+    out[2] = d[1];
+    out[3] = (double)it;
+  }
+  else if (!plf_newton_branch(cp->ctx, &cp->shape, &a, initial_length, min_length, max_length, tolerance, max_iters,
+                              out))
+    return cuda_fail(cp);
+  if (length) *length = out[0];
+  if (d_f) *d_f = out[1];
+  if (dd_f) *dd_f = out[2];
+  if (iterations) *iterations = (unsigned int)out[3];
+  return PLL_SUCCESS;
 }
 
 /* ---- site pattern compression (the step before the path) ------------------------------------ */

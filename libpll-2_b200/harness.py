@@ -143,6 +143,34 @@ class Engine:
             raise RuntimeError(f"derivatives failed: {self.lib.errno} {self.lib.errmsg}")
         return d1.value, d2.value
 
+    def newton(self, sumtable: np.ndarray, t0: float, edge=None, tmin=1e-8, tmax=100.0, tol=1e-5, max_iters=32):
+        """Newton-Raphson on one branch: (length, d_f, dd_f, evaluations).  One fused launch on the CUDA
+        engine (pll_cuda_newton_branch); the same rule driven from the host through
+        pll_compute_likelihood_derivatives otherwise (examples/newton/newton.c:67-96 plus clamping)."""
+        a, b, _ = edge or self.ds.tree.root_edge
+        t = self.ds.tree
+        if self.lib.is_cuda:
+            ln, d1, d2, it = C.c_double(), C.c_double(), C.c_double(), C.c_uint()
+            rc = self.lib.pll_cuda_newton_branch(
+                self.p, t.scaler_of.get(a, -1), t.scaler_of.get(b, -1), t0, tmin, tmax, tol, max_iters,
+                _up(self.params_indices), _dp(sumtable), C.byref(ln), C.byref(d1), C.byref(d2), C.byref(it))
+            if rc != 1:
+                raise RuntimeError(f"pll_cuda_newton_branch failed: {self.lib.errno} {self.lib.errmsg}")
+            return ln.value, d1.value, d2.value, it.value
+        return self.newton_host(sumtable, t0, edge, tmin, tmax, tol, max_iters)
+
+    def newton_host(self, sumtable, t0, edge=None, tmin=1e-8, tmax=100.0, tol=1e-5, max_iters=32):
+        ln, d1, d2, it = t0, 0.0, 0.0, 0
+        for it in range(1, max_iters + 1):
+            d1, d2 = self.derivatives(sumtable, ln, edge)
+            if abs(d1) < tol:
+                break
+            new = min(max(ln - d1 / d2, tmin), tmax)
+            if new != new or new == ln:
+                break
+            ln = new
+        return ln, d1, d2, it
+
     # -- buffer readers (host pointers for the reference, downloads for CUDA) -
     def clv_size(self, idx: int) -> int:
         return int(self.lib.pll_get_clv_size(self.p, idx))

@@ -149,6 +149,20 @@ def main():
                 nb += 1
         out["newton_branches"] = nb
         out["newton_ms_per_branch_wall"] = 1e3 * (time.perf_counter() - t0) / nb
+        # the same sweep with the whole Newton loop on the device (pll_cuda_newton_branch): sumtable + one launch
+        for fused in (False, True):
+            t0 = time.perf_counter()
+            nb = evals = 0
+            for op in list(eng.ops)[:200]:
+                for child, m in ((op.child1_clv_index, op.child1_matrix_index), (op.child2_clv_index, op.child2_matrix_index)):
+                    edge = (op.parent_clv_index, child, m)
+                    eng.update_sumtable(st, edge)
+                    r = (eng.newton if fused else eng.newton_host)(st, 1.5 * float(ds.tree.branch_lengths[m]), edge)
+                    evals += r[3]
+                    nb += 1
+            key = "newton_fused" if fused else "newton_host_loop"
+            out[key + "_ms_per_branch_wall"] = 1e3 * (time.perf_counter() - t0) / nb
+            out[key + "_evaluations_per_branch"] = evals / nb
     eng.close()
     if args.ref and os.path.exists(pkg.REF_PATH):
         ref = capi.PllLibrary(pkg.REF_PATH, cuda=False)

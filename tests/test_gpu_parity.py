@@ -662,3 +662,68 @@ def test_repeated_traversals_replay_a_cuda_graph(reflib, cudalib, kind, extra, m
         assert_clv_equal(ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index), kind != "aa", "clv after replays")
     for e in (ref, gpu, plain):
         e.close()
+
+
+# ---- the fused Newton-Raphson loop (pll_cuda_newton_branch) --------------------------------------
+
+@pytest.mark.parametrize("kind,tips,sites,attrs", [
+    ("dna", 20, 3001, capi.PATTERN_TIP),
+    ("dna", 20, 3001, 0),
+    ("dna", 60, 2000, capi.SITE_REPEATS),
+    ("aa", 12, 800, capi.PATTERN_TIP),
+    ("g5", 10, 500, capi.PATTERN_TIP),
+    ("dna", 8, 40000, capi.PATTERN_TIP),
+    ("dna", 5, 800000, capi.PATTERN_TIP),  # table > 96 MB: the same rule over the streaming derivative kernel
+])
+def test_fused_newton_matches_the_host_driven_loop(reflib, cudalib, kind, tips, sites, attrs):
+    """One cooperative launch per branch against (a) the same rule driven through the reference's
+    pll_compute_likelihood_derivatives and (b) through this library's own blocking call."""
+    ds = make_ds(kind, tips, sites, "random", seed=21)
+    ref, gpu = pair(reflib, cudalib, ds, attrs)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    last = ds.tree.ops[-1]
+    edges = [ds.tree.root_edge, (int(last[0]), int(last[2]), int(last[3])), (int(last[0]), int(last[5]), int(last[6]))]
+    st_ref, st_gpu = ref.sumtable_alloc(), gpu.sumtable_alloc()
+    for edge in edges:
+        ref.update_sumtable(st_ref, edge)
+        gpu.update_sumtable(st_gpu, edge)
+        for t0 in (0.01, 0.1, 0.7):
+            want = ref.newton_host(st_ref, t0, edge)
+            own = gpu.newton_host(st_gpu, t0, edge)
+            got = gpu.newton(st_gpu, t0, edge)
+            for other in (want, own):
+                assert abs(got[3] - other[3]) <= 1, (got, other)
+                if got[3] == other[3]:
+                    assert abs(got[0] - other[0]) <= 1e-9 * max(abs(other[0]), 1e-3), (edge, t0, got, other)
+                    # near the optimum d_f is a cancellation sum: it moves by dd_f * (error of the length)
+                    assert abs(got[1] - other[1]) <= DERIV_RTOL * max(abs(other[1]), 1e-6 * ds.sites,
+                                                                      abs(other[2] * other[0])), (got, other)
+                    assert abs(got[2] - other[2]) <= DERIV_RTOL * max(abs(other[2]), 1e-6 * ds.sites), (got, other)
+                else:
+                    assert abs(got[0] - other[0]) <= 1e-4 * max(abs(other[0]), 1e-3), (edge, t0, got, other)
+            assert 1e-8 <= got[0] <= 100.0
+    # bounds and iteration limit
+    t1 = gpu.newton(st_gpu, 0.1, edges[0], max_iters=1)
+    d = gpu.derivatives(st_gpu, 0.1, edges[0])
+    assert t1[3] == 1 and abs(t1[1] - d[0]) <= DERIV_RTOL * max(abs(d[0]), 1e-6 * ds.sites)
+    lo = gpu.newton(st_gpu, 0.5, edges[0], tmin=0.4, tmax=0.6)
+    assert 0.4 <= lo[0] <= 0.6
+    ref.close()
+    gpu.close()
+
+
+def test_fused_newton_rejects_bad_arguments(cudalib):
+    ds = make_ds("dna", 6, 200, "random", seed=3)
+    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    gpu.update_pmatrices()
+    gpu.update_partials()
+    st = gpu.sumtable_alloc()
+    gpu.update_sumtable(st)
+    with pytest.raises(RuntimeError):
+        gpu.newton(st, 0.1, max_iters=0)
+    with pytest.raises(RuntimeError):
+        gpu.newton(st, 0.1, tmin=1.0, tmax=0.5)
+    assert gpu.newton(st, 0.1)[3] >= 1
+    gpu.close()
