@@ -761,6 +761,35 @@ typedef struct pll_pars_buildop_s
   unsigned int child2_score_index;
 } pll_pars_buildop_t;
 
+/* src/pll.h:502-508 */
+typedef struct pll_pars_recop_s
+{
+  unsigned int node_score_index;
+  unsigned int node_ancestral_index;
+  unsigned int parent_score_index;
+  unsigned int parent_ancestral_index;
+} pll_pars_recop_t;
+
+/* Weighted (Sankoff) parsimony, src/parsimony.c (pll.h:2535-2557).  Objects live on the GPU selected by
+ * pll_cuda_set_device() / $PLL_CUDA_DEVICE / $LOCAL_RANK; sbuffer[i] ([site][state] doubles) and anc_states[i]
+ * are managed allocations, so clients may read them on the host after any call, as with the reference. */
+PLL_EXPORT pll_parsimony_t * pll_parsimony_create(unsigned int tips, unsigned int states, unsigned int sites,
+                                                  const double * score_matrix, unsigned int score_buffers,
+                                                  unsigned int ancestral_buffers);
+PLL_EXPORT int pll_set_parsimony_sequence(pll_parsimony_t * pars, unsigned int tip_index, const pll_state_t * map,
+                                          const char * sequence);
+/* one launch for the whole operation list; returns pll_parsimony_score of the last parent */
+PLL_EXPORT double pll_parsimony_build(pll_parsimony_t * pars, const pll_pars_buildop_t * operations,
+                                      unsigned int count);
+PLL_EXPORT double pll_parsimony_score(pll_parsimony_t * pars, unsigned int score_buffer_index);
+PLL_EXPORT void pll_parsimony_reconstruct(pll_parsimony_t * pars, const pll_state_t * map,
+                                          const pll_pars_recop_t * operations, unsigned int count);
+/* src/rtree.c:458-520 (pll.h:1032-1040) */
+PLL_EXPORT void pll_rtree_create_pars_buildops(pll_rnode_t * const * trav_buffer, unsigned int trav_buffer_size,
+                                               pll_pars_buildop_t * ops, unsigned int * ops_count);
+PLL_EXPORT void pll_rtree_create_pars_recops(pll_rnode_t * const * trav_buffer, unsigned int trav_buffer_size,
+                                             pll_pars_recop_t * ops, unsigned int * ops_count);
+
 /* src/fast_parsimony.c:532-570 (pll.h:2574) */
 PLL_EXPORT pll_parsimony_t * pll_fastparsimony_init(const pll_partition_t * partition);
 /* src/fast_parsimony.c:721-729 (pll.h:2576): the whole list is ONE launch */

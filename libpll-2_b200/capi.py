@@ -160,8 +160,19 @@ class RandomData(C.Structure):
 
 ParsimonyP = C.POINTER(Parsimony)
 
+
+class ParsRecOp(C.Structure):
+    _fields_ = [("node_score_index", C.c_uint), ("node_ancestral_index", C.c_uint), ("parent_score_index", C.c_uint),
+                ("parent_ancestral_index", C.c_uint)]
+
+
 # Fitch parsimony and the random_r family: the same names in the reference build and in ours
 _PARS_PROTOS = {
+    "pll_parsimony_create": (ParsimonyP, [C.c_uint, C.c_uint, C.c_uint, c_double_p, C.c_uint, C.c_uint]),
+    "pll_set_parsimony_sequence": (C.c_int, [ParsimonyP, C.c_uint, C.POINTER(pll_state_t), C.c_char_p]),
+    "pll_parsimony_build": (C.c_double, [ParsimonyP, C.POINTER(ParsBuildOp), C.c_uint]),
+    "pll_parsimony_score": (C.c_double, [ParsimonyP, C.c_uint]),
+    "pll_parsimony_reconstruct": (None, [ParsimonyP, C.POINTER(pll_state_t), C.POINTER(ParsRecOp), C.c_uint]),
     "pll_fastparsimony_init": (ParsimonyP, [PartitionP]),
     "pll_fastparsimony_update_vectors": (None, [ParsimonyP, C.POINTER(ParsBuildOp), C.c_uint]),
     "pll_fastparsimony_edge_score": (C.c_uint, [ParsimonyP, C.c_uint, C.c_uint]),

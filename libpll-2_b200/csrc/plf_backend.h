@@ -268,6 +268,24 @@ int plf_pars_insert_scan(plf_pars_t * ps, const unsigned int * d_vec,
                          const unsigned int * h_pairs, unsigned int n,
                          unsigned int third, unsigned int * h_scores);
 
+/* ---- weighted (Sankoff) parsimony, src/parsimony.c: score buffers [site][state] f64 -------------- */
+int plf_wpars_tip(plf_ctx_t * ctx, double * d_out, const char * h_seq,
+                  const unsigned long long * h_map, unsigned int sites,
+                  unsigned int states, double inf);
+/* h_ops: count x {parent, child1, child2} score buffer indices into d_sbuf_table */
+int plf_wpars_build(plf_ctx_t * ctx, double * const * d_sbuf_table,
+                    const unsigned int * h_ops, unsigned int count,
+                    unsigned int states, unsigned int sites, const double * d_matrix);
+int plf_wpars_site_min(plf_ctx_t * ctx, const double * d_buf, unsigned int states,
+                       unsigned int sites, double * h_out);
+/* h_recops: count x {node score, node ancestral, parent score, parent ancestral} */
+int plf_wpars_reconstruct(plf_ctx_t * ctx, double * const * d_sbuf_table,
+                          unsigned int * const * d_anc_table,
+                          const unsigned int * h_recops, unsigned int count,
+                          unsigned int states, unsigned int sites,
+                          const unsigned int * h_revmap,
+                          const unsigned long long * h_map);
+
 #ifdef __cplusplus
 }
 #endif

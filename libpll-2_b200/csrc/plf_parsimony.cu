@@ -601,3 +601,205 @@ extern "C" int plf_pars_insert_scan(plf_pars_t * ps, const unsigned int * d_vec,
 {
   return pars_pairs<1>(ps, d_vec, states, words, h_pairs, n, third, h_scores);
 }
+
+/* ---- weighted (Sankoff) parsimony, src/parsimony.c ----------------------------------------------------------
+ * Score buffers are [site][state] doubles.  Sites are independent, so as with the bit vectors one thread per
+ * site runs the WHOLE operation list: a traversal (and a reconstruction pass) is one launch.  The arithmetic is
+ * the reference's, operation for operation (sequential fmin over the child states, child 1 then child 2), so
+ * buffers are bit-identical. */
+
+template <int ST>
+__global__ void __launch_bounds__(128)
+k_wpars_build(double * const * __restrict__ sbuf, const unsigned int * __restrict__ ops, unsigned int count,
+              unsigned int states_rt, unsigned int sites, const double * __restrict__ matrix)
+{
+  extern __shared__ double M[]; /* [states][states] */
+  const unsigned int states = ST ? ST : states_rt;
+  for (unsigned int i = threadIdx.x; i < states * states; i += blockDim.x) M[i] = matrix[i];
+  __syncthreads();
+  const unsigned int site = blockIdx.x * blockDim.x + threadIdx.x;
+  if (site >= sites) return;
+  for (unsigned int o = 0; o < count; ++o)
+  {
+    double * parent = sbuf[ops[3 * o]] + (size_t)site * states;
+    const double * c1 = sbuf[ops[3 * o + 1]] + (size_t)site * states;
+    const double * c2 = sbuf[ops[3 * o + 2]] + (size_t)site * states;
+    if constexpr (ST > 0)
+    {
+      double a[ST > 0 ? ST : 1], b[ST > 0 ? ST : 1];
+#pragma unroll
+      for (int k = 0; k < ST; ++k)
+      {
+        a[k] = c1[k];
+        b[k] = c2[k];
+      }
+#pragma unroll
+      for (int n = 0; n < ST; ++n)
+      {
+        double m1 = a[0] + M[n], m2 = b[0] + M[n];
+#pragma unroll
+        for (int k = 1; k < ST; ++k)
+        {
+          m1 = fmin(a[k] + M[k * ST + n], m1);
+          m2 = fmin(b[k] + M[k * ST + n], m2);
+        }
+        parent[n] = m1 + m2;
+      }
+    }
+    else
+    {
+      /* the parent may alias a child only in lists the reference would also get wrong: no staging */
+      for (unsigned int n = 0; n < states; ++n)
+      {
+        double m1 = c1[0] + M[n], m2 = c2[0] + M[n];
+        for (unsigned int k = 1; k < states; ++k)
+        {
+          m1 = fmin(c1[k] + M[k * states + n], m1);
+          m2 = fmin(c2[k] + M[k * states + n], m2);
+        }
+        parent[n] = m1 + m2;
+      }
+    }
+  }
+}
+
+__global__ void k_wpars_tip(double * __restrict__ out, const unsigned char * __restrict__ seq,
+                            const unsigned long long * __restrict__ map, unsigned int sites, unsigned int states,
+                            double inf)
+{
+  const unsigned int site = blockIdx.x * blockDim.x + threadIdx.x;
+  if (site >= sites) return;
+  const unsigned long long c = map[seq[site]];
+  for (unsigned int j = 0; j < states; ++j) out[(size_t)site * states + j] = ((c >> j) & 1ull) ? 0.0 : inf;
+}
+
+__global__ void k_wpars_site_min(const double * __restrict__ buf, unsigned int states, unsigned int sites,
+                                 double * __restrict__ out)
+{
+  const unsigned int site = blockIdx.x * blockDim.x + threadIdx.x;
+  if (site >= sites) return;
+  const double * s = buf + (size_t)site * states;
+  double m = s[0];
+  for (unsigned int j = 1; j < states; ++j) m = fmin(s[j], m);
+  out[site] = m;
+}
+
+/* recops: count x {node score, node ancestral, parent score, parent ancestral}; op 0 is the subtree root
+ * (src/parsimony.c:301-382).  revmap[state] = character of the one-state code, ctz[ch] = its state. */
+__global__ void __launch_bounds__(128)
+k_wpars_reconstruct(double * const * __restrict__ sbuf, unsigned int * const * __restrict__ anc,
+                    const unsigned int * __restrict__ ops, unsigned int count, unsigned int states, unsigned int sites,
+                    const unsigned int * __restrict__ revmap_g, const unsigned long long * __restrict__ map_g)
+{
+  __shared__ unsigned int revmap[256];
+  __shared__ unsigned char ctz[256];
+  for (unsigned int i = threadIdx.x; i < 256; i += blockDim.x)
+  {
+    revmap[i] = revmap_g[i];
+    ctz[i] = map_g[i] ? (unsigned char)(__ffsll((long long)map_g[i]) - 1) : 64;
+  }
+  __syncthreads();
+  const unsigned int site = blockIdx.x * blockDim.x + threadIdx.x;
+  if (site >= sites) return;
+  for (unsigned int o = 0; o < count; ++o)
+  {
+    const double * score = sbuf[ops[4 * o]] + (size_t)site * states;
+    unsigned int minindex = 0;
+    for (unsigned int j = 1; j < states; ++j)
+      if (score[j] < score[minindex]) minindex = j;
+    unsigned int * mine = anc[ops[4 * o + 1]] + site;
+    if (o == 0)
+    {
+      *mine = revmap[minindex];
+      continue;
+    }
+    const unsigned int pch = anc[ops[4 * o + 3]][site];
+    const double parent_val = (sbuf[ops[4 * o + 2]] + (size_t)site * states)[ctz[pch & 255u] & 63];
+    *mine = (score[minindex] + 1 > parent_val) ? pch : revmap[minindex];
+  }
+}
+
+extern "C" int plf_wpars_tip(plf_ctx_t * ctx, double * d_out, const char * h_seq, const unsigned long long * h_map,
+                             unsigned int sites, unsigned int states, double inf)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (!sites) return 1;
+  unsigned char * d = (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_small, (size_t)sites + 256 * sizeof(unsigned long long) + 64);
+  if (!d) return 0;
+  unsigned long long * d_map = (unsigned long long *)d;
+  unsigned char * d_seq = d + 256 * sizeof(unsigned long long);
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_map, h_map, 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_seq, h_seq, sites, cudaMemcpyHostToDevice, ctx->stream));
+  k_wpars_tip<<<(sites + 255) / 256, 256, 0, ctx->stream>>>(d_out, d_seq, d_map, sites, states, inf);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+extern "C" int plf_wpars_build(plf_ctx_t * ctx, double * const * d_sbuf_table, const unsigned int * h_ops,
+                               unsigned int count, unsigned int states, unsigned int sites, const double * d_matrix)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (!count || !sites) return 1;
+  unsigned int * d_ops = (unsigned int *)plf_ws_reserve(ctx, &ctx->ws_ops, (size_t)3 * count * sizeof(unsigned int));
+  if (!d_ops) return 0;
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_ops, (size_t)3 * count * sizeof(unsigned int), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  const size_t smem = (size_t)states * states * sizeof(double);
+  if (smem > 48 * 1024)
+  {
+    plf_set_error(ctx, "weighted parsimony: %u states need a %zu-byte score matrix in shared memory", states, smem);
+    return 0;
+  }
+  const unsigned int grid = (sites + 127) / 128;
+  if (states == 4)
+    k_wpars_build<4><<<grid, 128, smem, ctx->stream>>>(d_sbuf_table, d_ops, count, states, sites, d_matrix);
+  else if (states == 20)
+    k_wpars_build<20><<<grid, 128, smem, ctx->stream>>>(d_sbuf_table, d_ops, count, states, sites, d_matrix);
+  else
+    k_wpars_build<0><<<grid, 128, smem, ctx->stream>>>(d_sbuf_table, d_ops, count, states, sites, d_matrix);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); /* the op list came from pageable memory; results are host-visible */
+  return 1;
+}
+
+extern "C" int plf_wpars_site_min(plf_ctx_t * ctx, const double * d_buf, unsigned int states, unsigned int sites,
+                                  double * h_out)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (!sites) return 1;
+  double * d_min = (double *)plf_ws_reserve(ctx, &ctx->ws_partial, (size_t)sites * sizeof(double));
+  if (!d_min) return 0;
+  k_wpars_site_min<<<(sites + 255) / 256, 256, 0, ctx->stream>>>(d_buf, states, sites, d_min);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  PLF_CHECK(ctx, cudaMemcpyAsync(h_out, d_min, (size_t)sites * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+extern "C" int plf_wpars_reconstruct(plf_ctx_t * ctx, double * const * d_sbuf_table, unsigned int * const * d_anc_table,
+                                     const unsigned int * h_recops, unsigned int count, unsigned int states,
+                                     unsigned int sites, const unsigned int * h_revmap,
+                                     const unsigned long long * h_map)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (!count || !sites) return 1;
+  unsigned int * d_ops = (unsigned int *)plf_ws_reserve(ctx, &ctx->ws_ops, (size_t)4 * count * sizeof(unsigned int));
+  unsigned char * d = (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_small, 256 * (sizeof(unsigned long long) + sizeof(unsigned int)));
+  if (!d_ops || !d) return 0;
+  unsigned long long * d_map = (unsigned long long *)d;
+  unsigned int * d_rev = (unsigned int *)(d + 256 * sizeof(unsigned long long));
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_recops, (size_t)4 * count * sizeof(unsigned int), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_map, h_map, 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_rev, h_revmap, 256 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+  k_wpars_reconstruct<<<(sites + 127) / 128, 128, 0, ctx->stream>>>(d_sbuf_table, d_anc_table, d_ops, count, states,
+                                                                     sites, d_rev, d_map);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
+}

@@ -1421,6 +1421,8 @@ done:
   return ok;
 }
 
+int pll_cuda_internal_pick_device(void) { return pick_device(); }
+
 /* tip states as the parsimony kernels read them (pll_parsimony.c); same pointer-table layout as
  * invariant_on_device.  Sets pll_errno on failure. */
 int pll_cuda_internal_tipsource(const pll_partition_t * partition, pll_cuda_tipsource_t * out)

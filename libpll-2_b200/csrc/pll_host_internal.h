@@ -15,6 +15,9 @@ typedef struct pll_cuda_tipsource
   void * d_ptrs;        /* backing store of the pointer arrays: plf_free(ctx, d_ptrs) when done */
 } pll_cuda_tipsource_t;
 
+/* device for objects that are not tied to a partition: pll_cuda_set_device() / $PLL_CUDA_DEVICE / $LOCAL_RANK */
+int pll_cuda_internal_pick_device(void);
+
 int pll_cuda_internal_tipsource(const pll_partition_t * partition, pll_cuda_tipsource_t * out);
 
 #endif

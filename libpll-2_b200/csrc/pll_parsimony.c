@@ -30,6 +30,13 @@ typedef struct cuda_parsimony
   unsigned int nodes_count;
   unsigned int * scratch; /* host: scores of the current call */
   unsigned int scratch_cap;
+  /* weighted (Sankoff) parsimony objects made by pll_parsimony_create: sbuffer[] / anc_states[] are managed
+   * allocations (the reference's clients read them on the host), mirrored as device pointer tables */
+  int weighted;
+  double * d_matrix;
+  double ** d_sbuf_table;
+  unsigned int ** d_anc_table;
+  double * site_min; /* host [sites] */
 } cuda_parsimony_t;
 
 static void pars_error(int code, const char * msg)
@@ -79,10 +86,24 @@ PLL_EXPORT void pll_parsimony_destroy(pll_parsimony_t * pars)
   if (cp->magic != PARS_MAGIC) return; /* not ours: nothing we can safely free */
   if (cp->ctx)
   {
+    unsigned int i;
     plf_free(cp->ctx, cp->d_vec);
+    if (cp->weighted)
+    {
+      for (i = 0; cp->pub.sbuffer && i < cp->pub.score_buffers + cp->pub.tips; ++i) plf_free(cp->ctx, cp->pub.sbuffer[i]);
+      for (i = cp->pub.tips; cp->pub.anc_states && i < cp->pub.ancestral_buffers + cp->pub.tips; ++i)
+        plf_free(cp->ctx, cp->pub.anc_states[i]);
+      plf_free(cp->ctx, cp->d_matrix);
+      plf_free(cp->ctx, cp->d_sbuf_table);
+      plf_free(cp->ctx, cp->d_anc_table);
+    }
     plf_pars_destroy(cp->ps);
     plf_ctx_destroy(cp->ctx);
   }
+  free(cp->pub.sbuffer);
+  free(cp->pub.anc_states);
+  free(cp->pub.score_matrix);
+  free(cp->site_min);
   free(cp->pub.packedvector);
   free(cp->pub.node_cost);
   free(cp->pub.informative);
@@ -271,6 +292,219 @@ PLL_EXPORT void pll_utree_create_pars_buildops(pll_unode_t * const * trav_buffer
     ops[n].parent_score_index = node->node_index;
     ops[n].child1_score_index = node->next->back->node_index;
     ops[n].child2_score_index = node->next->next->back->node_index;
+    ++n;
+  }
+  *ops_count = n;
+}
+
+/* ---- weighted (Sankoff) parsimony, src/parsimony.c -------------------------------------------------------
+ * pll_parsimony_create has no attribute argument: objects made by this library live on the GPU selected by
+ * pll_cuda_set_device() / $PLL_CUDA_DEVICE / $LOCAL_RANK.  Score and ancestral buffers are managed allocations:
+ * kernels work on them in HBM and the host may read them after any call, as the reference's clients do
+ * (examples/parsimony/npr-pars.c:240-281). */
+
+static cuda_parsimony_t * WP(const pll_parsimony_t * p)
+{
+  cuda_parsimony_t * cp = PP(p);
+  if (cp && !cp->weighted)
+  {
+    pars_error(PLL_ERROR_PARAM_INVALID, "parsimony structure has no score buffers (made by pll_fastparsimony_init)");
+    return NULL;
+  }
+  return cp;
+}
+
+PLL_EXPORT pll_parsimony_t * pll_parsimony_create(unsigned int tips, unsigned int states, unsigned int sites,
+                                                  const double * score_matrix, unsigned int score_buffers,
+                                                  unsigned int ancestral_buffers)
+{
+  cuda_parsimony_t * cp = (cuda_parsimony_t *)calloc(1, sizeof(cuda_parsimony_t));
+  const size_t nbuf = (size_t)score_buffers + tips, nanc = (size_t)ancestral_buffers + tips;
+  char err[200] = {0};
+  unsigned int i;
+  int alloc_failed = 0;
+  if (!cp)
+  {
+    pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return NULL;
+  }
+  cp->magic = PARS_MAGIC;
+  cp->weighted = 1;
+  cp->pub.tips = tips;
+  cp->pub.states = states;
+  cp->pub.sites = sites;
+  cp->pub.score_buffers = score_buffers;
+  cp->pub.ancestral_buffers = ancestral_buffers;
+  if (!plf_ctx_create(pll_cuda_internal_pick_device(), 1, &cp->ctx, err, sizeof(err)))
+  {
+    pll_errno = PLL_ERROR_CUDA;
+    snprintf(pll_errmsg, sizeof(pll_errmsg), "CUDA: %.180s", err);
+    cp->ctx = NULL;
+    pll_parsimony_destroy(&cp->pub);
+    return NULL;
+  }
+  cp->pub.score_matrix = (double *)malloc((size_t)states * states * sizeof(double));
+  cp->pub.sbuffer = (double **)calloc(nbuf ? nbuf : 1, sizeof(double *));
+  cp->pub.anc_states = (unsigned int **)calloc(nanc ? nanc : 1, sizeof(unsigned int *));
+  cp->site_min = (double *)malloc(((size_t)sites + 1) * sizeof(double));
+  if (!cp->pub.score_matrix || !cp->pub.sbuffer || !cp->pub.anc_states || !cp->site_min)
+  {
+    pll_parsimony_destroy(&cp->pub);
+    pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory for score buffers.");
+    return NULL;
+  }
+  memcpy(cp->pub.score_matrix, score_matrix, (size_t)states * states * sizeof(double));
+  cp->d_matrix = (double *)plf_alloc(cp->ctx, (size_t)states * states * sizeof(double), 0);
+  cp->d_sbuf_table = (double **)plf_alloc(cp->ctx, (nbuf + 1) * sizeof(double *), 1);
+  cp->d_anc_table = (unsigned int **)plf_alloc(cp->ctx, (nanc + 1) * sizeof(unsigned int *), 1);
+  for (i = 0; i < nbuf; ++i)
+    if (!(cp->pub.sbuffer[i] = (double *)plf_alloc(cp->ctx, ((size_t)sites * states + 1) * sizeof(double), 1)))
+      alloc_failed = 1;
+  for (i = tips; i < nanc && !alloc_failed; ++i)
+    if (!(cp->pub.anc_states[i] = (unsigned int *)plf_alloc(cp->ctx, ((size_t)sites + 1) * sizeof(unsigned int), 1)))
+      alloc_failed = 1;
+  if (!cp->d_matrix || !cp->d_sbuf_table || !cp->d_anc_table || alloc_failed ||
+      !plf_upload(cp->ctx, cp->d_matrix, score_matrix, (size_t)states * states * sizeof(double)) ||
+      !plf_upload(cp->ctx, cp->d_sbuf_table, cp->pub.sbuffer, nbuf * sizeof(double *)) ||
+      !plf_upload(cp->ctx, cp->d_anc_table, cp->pub.anc_states, nanc * sizeof(unsigned int *)))
+  {
+    pars_cuda_fail(cp);
+    pll_parsimony_destroy(&cp->pub);
+    return NULL;
+  }
+  return &cp->pub;
+}
+
+PLL_EXPORT int pll_set_parsimony_sequence(pll_parsimony_t * pars, unsigned int tip_index, const pll_state_t * map,
+                                          const char * sequence)
+{
+  cuda_parsimony_t * cp = WP(pars);
+  const unsigned int states = pars ? pars->states : 0;
+  double inf;
+  unsigned int i;
+  if (!cp) return PLL_FAILURE;
+  if (tip_index >= pars->tips + pars->score_buffers)
+  {
+    pars_error(PLL_ERROR_PARAM_INVALID, "Parsimony score buffer index out of range.");
+    return PLL_FAILURE;
+  }
+  /* "infinity" = the largest entry of the score matrix plus one (src/parsimony.c:38-43) */
+  inf = pars->score_matrix[0];
+  for (i = 1; i < states * states; ++i)
+    if (pars->score_matrix[i] > inf) inf = pars->score_matrix[i];
+  inf++;
+  for (i = 0; i < pars->sites; ++i)
+    if (map[(unsigned char)sequence[i]] == 0)
+    {
+      pll_errno = PLL_ERROR_TIPDATA_ILLEGALSTATE;
+      snprintf(pll_errmsg, 200, "Illegal state code in tip \"%c\"", sequence[i]);
+      printf("%s\n", pll_errmsg); /* as the reference does (src/parsimony.c:51) */
+      return PLL_FAILURE;
+    }
+  if (!plf_wpars_tip(cp->ctx, pars->sbuffer[tip_index], sequence, map, pars->sites, states, inf))
+    return pars_cuda_fail(cp);
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT double pll_parsimony_score(pll_parsimony_t * pars, unsigned int score_buffer_index)
+{
+  cuda_parsimony_t * cp = WP(pars);
+  double sum = 0;
+  unsigned int i;
+  if (!cp) return 0;
+  if (score_buffer_index >= pars->tips + pars->score_buffers)
+  {
+    pars_error(PLL_ERROR_PARAM_INVALID, "Parsimony score buffer index out of range.");
+    return 0;
+  }
+  if (!plf_wpars_site_min(cp->ctx, pars->sbuffer[score_buffer_index], pars->states, pars->sites, cp->site_min))
+  {
+    pars_cuda_fail(cp);
+    return 0;
+  }
+  /* the per-site minima are added in site order, as in the reference, so that the total has its bits */
+  for (i = 0; i < pars->sites; ++i) sum += cp->site_min[i];
+  return sum;
+}
+
+PLL_EXPORT double pll_parsimony_build(pll_parsimony_t * pars, const pll_pars_buildop_t * operations,
+                                      unsigned int count)
+{
+  cuda_parsimony_t * cp = WP(pars);
+  const unsigned int * idx = (const unsigned int *)operations;
+  size_t i;
+  if (!cp || !count) return 0;
+  for (i = 0; i < (size_t)3 * count; ++i)
+    if (idx[i] >= pars->tips + pars->score_buffers)
+    {
+      pars_error(PLL_ERROR_PARAM_INVALID, "Parsimony score buffer index out of range.");
+      return 0;
+    }
+  if (!plf_wpars_build(cp->ctx, cp->d_sbuf_table, idx, count, pars->states, pars->sites, cp->d_matrix))
+  {
+    pars_cuda_fail(cp);
+    return 0;
+  }
+  return pll_parsimony_score(pars, operations[count - 1].parent_score_index);
+}
+
+PLL_EXPORT void pll_parsimony_reconstruct(pll_parsimony_t * pars, const pll_state_t * map,
+                                          const pll_pars_recop_t * operations, unsigned int count)
+{
+  cuda_parsimony_t * cp = WP(pars);
+  unsigned int revmap[256];
+  unsigned int i;
+  if (!cp || !count) return;
+  for (i = 0; i < count; ++i)
+  {
+    const pll_pars_recop_t * op = operations + i;
+    if (op->node_score_index >= pars->tips + pars->score_buffers ||
+        op->node_ancestral_index < pars->tips || op->node_ancestral_index >= pars->tips + pars->ancestral_buffers ||
+        (i && (op->parent_score_index >= pars->tips + pars->score_buffers || op->parent_ancestral_index < pars->tips ||
+               op->parent_ancestral_index >= pars->tips + pars->ancestral_buffers)))
+    {
+      pars_error(PLL_ERROR_PARAM_INVALID, "Parsimony reconstruction index out of range.");
+      return;
+    }
+  }
+  /* character of every one-state code; the later character wins, as in src/parsimony.c:327-334 */
+  memset(revmap, 0, sizeof(revmap));
+  for (i = 0; i < 256; ++i)
+    if (map[i] && !(map[i] & (map[i] - 1))) revmap[__builtin_ctzll(map[i])] = i;
+  /* pll_pars_recop_t is four consecutive unsigned ints */
+  if (!plf_wpars_reconstruct(cp->ctx, cp->d_sbuf_table, cp->d_anc_table, (const unsigned int *)operations, count,
+                             pars->states, pars->sites, revmap, map))
+    pars_cuda_fail(cp);
+}
+
+/* src/rtree.c:458-520 */
+PLL_EXPORT void pll_rtree_create_pars_buildops(pll_rnode_t * const * trav_buffer, unsigned int trav_buffer_size,
+                                               pll_pars_buildop_t * ops, unsigned int * ops_count)
+{
+  unsigned int i, n = 0;
+  for (i = 0; i < trav_buffer_size; ++i)
+  {
+    const pll_rnode_t * node = trav_buffer[i];
+    if (!node->left) continue;
+    ops[n].parent_score_index = node->clv_index;
+    ops[n].child1_score_index = node->left->clv_index;
+    ops[n].child2_score_index = node->right->clv_index;
+    ++n;
+  }
+  *ops_count = n;
+}
+
+PLL_EXPORT void pll_rtree_create_pars_recops(pll_rnode_t * const * trav_buffer, unsigned int trav_buffer_size,
+                                             pll_pars_recop_t * ops, unsigned int * ops_count)
+{
+  unsigned int i, n = 0;
+  for (i = 0; i < trav_buffer_size; ++i)
+  {
+    const pll_rnode_t * node = trav_buffer[i];
+    if (!node->left) continue;
+    ops[n].node_score_index = ops[n].node_ancestral_index = node->clv_index;
+    /* the root has no parent: its entries are never read */
+    ops[n].parent_score_index = ops[n].parent_ancestral_index = node->parent ? node->parent->clv_index : 0;
     ++n;
   }
   *ops_count = n;

@@ -195,6 +195,85 @@ def test_more_than_twenty_states_need_pattern_tips(cudalib):
     eng.close()
 
 
+# ---- weighted (Sankoff) parsimony --------------------------------------------------------------------------
+
+def weighted_pair(reflib, cudalib, ds, matrix):
+    out = []
+    t = ds.tree
+    maps = []
+    for lib in (reflib, cudalib):
+        if ds.map_name.startswith("custom"):
+            m = synth.custom_map(ds.states)
+            mp = m.ctypes.data_as(C.POINTER(capi.pll_state_t))
+            maps.append((m, mp))
+        else:
+            maps.append((None, lib.map(ds.map_name)))
+        p = lib.pll_parsimony_create(t.tips, ds.states, ds.sites, matrix.ctypes.data_as(capi.c_double_p), t.inner, t.inner)
+        assert p, (lib.errno, lib.errmsg)
+        for i, seq in enumerate(ds.seqs):
+            assert lib.pll_set_parsimony_sequence(p, i, maps[-1][1], seq) == 1
+        out.append(p)
+    return out, maps
+
+
+@pytest.mark.parametrize("kind,tips,sites,integer", [("dna", 6, 1, True), ("dna", 25, 2003, True), ("dna", 25, 2003, False),
+                                                   ("aa", 18, 700, False), ("g7", 12, 333, True)])
+def test_weighted_parsimony_matches_reference(reflib, cudalib, kind, tips, sites, integer):
+    """pll_parsimony_create / _build / _score / _reconstruct (src/parsimony.c): score buffers, totals and
+    ancestral states identical to the reference; the buffers are read on the host through the struct."""
+    ds = make_ds(kind, tips, sites, seed=tips + sites)
+    st = ds.states
+    rng = np.random.default_rng(sites)
+    matrix = rng.integers(1, 5, size=(st, st)).astype(np.float64) if integer else rng.uniform(0.3, 3.0, size=(st, st))
+    np.fill_diagonal(matrix, 0.0)
+    matrix = np.ascontiguousarray(matrix)
+    (ref, gpu), maps = weighted_pair(reflib, cudalib, ds, matrix)
+    try:
+        t = ds.tree
+        triples = tree_triples(ds)
+        ops = (capi.ParsBuildOp * len(triples))(*[capi.ParsBuildOp(*x) for x in triples])
+        s_ref = reflib.pll_parsimony_build(ref, ops, len(triples))
+        s_gpu = cudalib.pll_parsimony_build(gpu, ops, len(triples))
+        assert s_gpu == s_ref
+        n = ds.sites * st
+        for node in range(t.nodes):
+            a = np.ctypeslib.as_array(ref.contents.sbuffer[node], shape=(n,))
+            b = np.ctypeslib.as_array(gpu.contents.sbuffer[node], shape=(n,))  # managed memory: host-readable
+            np.testing.assert_array_equal(a.view(np.uint64), b.view(np.uint64), err_msg=f"score buffer {node}")
+        for node in (t.tips, t.nodes - 1):
+            assert cudalib.pll_parsimony_score(gpu, node) == reflib.pll_parsimony_score(ref, node)
+        # reconstruction in pre-order: reverse of the post-order list; the first entry is the subtree root
+        parent_of = {}
+        for p_, c1, c2 in triples:
+            parent_of[c1] = p_
+            parent_of[c2] = p_
+        top = triples[-1][0]  # a second subtree root (other end of the root edge) is hung under the first one
+        rec = [(p_, p_, parent_of.get(p_, top), parent_of.get(p_, top)) for p_, _, _ in reversed(triples)]
+        recops = (capi.ParsRecOp * len(rec))(*[capi.ParsRecOp(*x) for x in rec])
+        reflib.pll_parsimony_reconstruct(ref, maps[0][1], recops, len(rec))
+        cudalib.pll_parsimony_reconstruct(gpu, maps[1][1], recops, len(rec))
+        for node in range(t.tips, t.nodes):
+            a = np.ctypeslib.as_array(ref.contents.anc_states[node], shape=(ds.sites,))
+            b = np.ctypeslib.as_array(gpu.contents.anc_states[node], shape=(ds.sites,))
+            np.testing.assert_array_equal(a, b, err_msg=f"ancestral states {node}")
+    finally:
+        reflib.pll_parsimony_destroy(ref)
+        cudalib.pll_parsimony_destroy(gpu)
+
+
+def test_weighted_parsimony_rejects_illegal_characters_and_wrong_objects(cudalib, capfd):
+    m = np.ones((4, 4))
+    p = cudalib.pll_parsimony_create(3, 4, 5, np.ascontiguousarray(m).ctypes.data_as(capi.c_double_p), 1, 1)
+    assert cudalib.pll_set_parsimony_sequence(p, 0, cudalib.map("pll_map_nt"), b"AC!GT") == 0
+    assert cudalib.errno == 114  # PLL_ERROR_TIPDATA_ILLEGALSTATE
+    assert "Illegal state code" in capfd.readouterr().out  # the reference prints the message too
+    assert cudalib.pll_set_parsimony_sequence(p, 0, cudalib.map("pll_map_nt"), b"ACNGT") == 1
+    ops = (capi.ParsBuildOp * 1)(capi.ParsBuildOp(9, 0, 1))
+    assert cudalib.pll_parsimony_build(p, ops, 1) == 0 and cudalib.errno == 113
+    cudalib.pll_fastparsimony_update_vectors(p, ops, 1)  # a score-buffer object has no bit vectors: no crash
+    cudalib.pll_parsimony_destroy(p)
+
+
 # ---- stepwise addition ------------------------------------------------------------------------------------
 
 def splits(tree_p):

@@ -159,6 +159,62 @@ def test_file_driven_examples_run(cudalib, tmp_path, name, rooted, nargs):
         assert np.isfinite(float(m)) and float(m) < 0, out[-400:]
 
 
+def test_weighted_parsimony_example(cudalib, reflib, tmp_path):
+    """examples/parsimony/npr-pars.c (rooted Newick + interleaved PHYLIP -> Sankoff parsimony with unit costs ->
+    score buffers and reconstructed ancestral sequences read on the host through the struct), unmodified, on
+    the GPU.  The score and the root's reconstructed sequence are checked against the reference library driven
+    through the same operation lists."""
+    import test_tree_cpu as tt
+
+    exe = os.path.join(BIN, "parsimony")
+    if not os.path.exists(exe):
+        pytest.skip("example binaries not built")
+    rng = np.random.default_rng(17)
+    tips, sites = 14, 90
+    newick = tt.random_newick(rng, tips, rooted=True)
+    seqs = synth.mutate_alignment(tips, sites, rng, synth.AA_CODES, synth.AA_AMBIG)
+    tree, phy = tmp_path / "tree.nwk", tmp_path / "aln.phy"
+    tree.write_text(newick + "\n")
+    with open(phy, "w") as f:
+        f.write(f"{tips} {sites}\n")
+        for i in rng.permutation(tips):
+            f.write(f"t{i}".ljust(10) + seqs[i].decode() + "\n")
+    out = run(exe, str(tree), str(phy), force_cuda=True)
+    got = float(re.search(r"Minimum parsimony score: ([\d.]+)", out).group(1))
+
+    own = tt.bind(C.CDLL(pkg.LIB_PATH), True)
+    rt = own.pll_rtree_parse_newick_string(newick.encode())
+    t = rt.contents
+    n_nodes = t.tip_count + t.inner_count
+    buf = (C.POINTER(tt.RNode) * n_nodes)()
+    size = C.c_uint(0)
+    assert own.pll_rtree_traverse(t.root, 1, tt.RCB(lambda n: 1), buf, C.byref(size)) == 1
+    ops = (capi.ParsBuildOp * n_nodes)()
+    n_ops = C.c_uint(0)
+    f = own.pll_rtree_create_pars_buildops
+    f.restype, f.argtypes = None, [C.POINTER(C.POINTER(tt.RNode)), C.c_uint, C.POINTER(capi.ParsBuildOp), capi.c_uint_p]
+    f(buf, size.value, ops, C.byref(n_ops))
+    matrix = np.ones((20, 20)) - np.eye(20)
+    p = reflib.pll_parsimony_create(tips, 20, sites, np.ascontiguousarray(matrix).ctypes.data_as(capi.c_double_p),
+                                    tips - 1, tips - 1)
+    for i in range(size.value):
+        node = buf[i].contents
+        if not node.left:
+            assert reflib.pll_set_parsimony_sequence(p, node.clv_index, reflib.map("pll_map_aa"),
+                                                     seqs[int(node.label[1:])]) == 1
+    want = reflib.pll_parsimony_build(p, ops, n_ops.value)
+    assert got == want
+    # post-order: the root's score buffer is the last "label : ..." line of the first block
+    root_clv = ops[n_ops.value - 1].parent_score_index
+    sb = np.ctypeslib.as_array(p.contents.sbuffer[root_clv], shape=(sites * 20,))
+    block = out.split("Reconstruction:")[0].strip().splitlines()
+    printed = [float(x) for x in block[-1].split(":", 1)[1].replace("+", " ").split()]
+    assert printed == [float(f"{v:.0f}") for v in sb]
+    reflib.pll_parsimony_destroy(p)
+    own.pll_rtree_destroy(rt, None)
+    assert len(out.split("Reconstruction:")[1].strip().splitlines()) == tips - 1
+
+
 def newick_splits(newick):
     """tip-label bipartitions of a Newick string (labels are plain words, lengths ignored)"""
     text = re.sub(r":[-+0-9.eE]+", "", newick.strip().rstrip(";"))
