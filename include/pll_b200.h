@@ -116,6 +116,11 @@ extern "C" {
 #define PLL_ERROR_PHYLIP_NONALIGNED 233
 #define PLL_ERROR_PHYLIP_ILLEGALCHAR 234
 #define PLL_ERROR_PHYLIP_UNPRINTABLECHAR 235
+/* src/pll.h:180-183 */
+#define PLL_ERROR_SPR_TERMINALBRANCH 123
+#define PLL_ERROR_SPR_NOCHANGE 124
+#define PLL_ERROR_NNI_INVALIDMOVE 125
+#define PLL_ERROR_NNI_TERMINALBRANCH 126
 /* src/pll.h:184-186 */
 #define PLL_ERROR_STEPWISE_STRUCT 127
 #define PLL_ERROR_STEPWISE_TIPS 128
@@ -722,6 +727,43 @@ PLL_EXPORT void pll_rtree_create_operations(pll_rnode_t * const * trav_buffer,
                                             unsigned int trav_buffer_size, double * branches,
                                             unsigned int * pmatrix_indices, pll_operation_t * ops,
                                             unsigned int * matrix_count, unsigned int * ops_count);
+
+/* ---- topological moves with rollback, src/utree_moves.c (pll.h:141-145, 440-464, 2505-2531); pll_moves.c ---- */
+#define PLL_UTREE_MOVE_SPR 1
+#define PLL_UTREE_MOVE_NNI 2
+#define PLL_UTREE_MOVE_NNI_LEFT 1
+#define PLL_UTREE_MOVE_NNI_RIGHT 2
+
+typedef struct pll_utree_rb_s
+{
+  int move_type;
+  union
+  {
+    struct
+    {
+      pll_unode_t * p;
+      pll_unode_t * r;
+      pll_unode_t * rb;
+      pll_unode_t * pnb;
+      pll_unode_t * pnnb;
+      double r_len;
+      double pnb_len;
+      double pnnb_len;
+    } spr;
+    struct
+    {
+      pll_unode_t * p;
+      int nni_type;
+    } nni;
+  };
+} pll_utree_rb_t;
+
+PLL_EXPORT int pll_utree_spr(pll_unode_t * p, pll_unode_t * r, pll_utree_rb_t * rb, double * branch_lengths,
+                             unsigned int * matrix_indices);
+PLL_EXPORT int pll_utree_spr_safe(pll_unode_t * p, pll_unode_t * r, pll_utree_rb_t * rb, double * branch_lengths,
+                                  unsigned int * matrix_indices);
+PLL_EXPORT int pll_utree_nni(pll_unode_t * p, int type, pll_utree_rb_t * rb);
+PLL_EXPORT int pll_utree_rollback(pll_utree_rb_t * rollback, double * branch_lengths, unsigned int * matrix_indices);
 
 /* ---- Fitch parsimony on packed bit vectors (src/fast_parsimony.c, src/stepwise.c) ----------------
  * SURVEY.md 8(f)-4.  The structure keeps the reference's layout (src/pll.h:467-492).  Differences of the
