@@ -728,6 +728,22 @@ PLL_EXPORT void pll_rtree_create_operations(pll_rnode_t * const * trav_buffer,
                                             unsigned int * pmatrix_indices, pll_operation_t * ops,
                                             unsigned int * matrix_count, unsigned int * ops_count);
 
+/* src/utree.c:605-633,381-392 (pll.h:965-977); src/rtree.c:106 (pll.h:1003); src/list.c (pll.h:339-344,671-673) */
+PLL_EXPORT pll_unode_t * pll_utree_graph_clone(const pll_unode_t * root);
+PLL_EXPORT pll_utree_t * pll_utree_clone(const pll_utree_t * root);
+PLL_EXPORT int pll_utree_every_const(const pll_utree_t * tree,
+                                     int (*cb)(const pll_utree_t * tree, const pll_unode_t *));
+PLL_EXPORT void pll_rtree_show_ascii(const pll_rnode_t * root, int options);
+typedef struct pll_dlist
+{
+  struct pll_dlist * next;
+  struct pll_dlist * prev;
+  void * data;
+} pll_dlist_t;
+PLL_EXPORT int pll_dlist_append(pll_dlist_t ** dlist, void * data);
+PLL_EXPORT int pll_dlist_remove(pll_dlist_t ** dlist, void * data);
+PLL_EXPORT int pll_dlist_prepend(pll_dlist_t ** dlist, void * data);
+
 /* ---- topological moves with rollback, src/utree_moves.c (pll.h:141-145, 440-464, 2505-2531); pll_moves.c ---- */
 #define PLL_UTREE_MOVE_SPR 1
 #define PLL_UTREE_MOVE_NNI 2

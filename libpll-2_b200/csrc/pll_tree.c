@@ -1647,3 +1647,185 @@ PLL_EXPORT pll_utree_t * pll_rtree_unroot(pll_rtree_t * tree)
   }
   return pll_utree_wraptree(uroot, 0);
 }
+
+/* ======================================================================== *
+ *  copies, const iteration, rooted ASCII drawing, doubly-linked lists        *
+ *  (src/utree.c:381-392,551-633; src/rtree.c:24-128; src/list.c)             *
+ * ======================================================================== */
+
+/* copy of the roundabout `entry` belongs to; returns the copy of `entry`.  Labels are duplicated once per
+ * roundabout and shared by its members, as everywhere in this file; `data` pointers are copied as they are. */
+static pll_unode_t * copy_roundabout(const pll_unode_t * entry)
+{
+  pll_unode_t * first = (pll_unode_t *)malloc(sizeof(pll_unode_t)), * tail = first;
+  const pll_unode_t * s;
+  if (!first) return NULL;
+  *first = *entry;
+  first->back = NULL;
+  first->next = NULL;
+  first->label = entry->label ? strdup(entry->label) : NULL;
+  for (s = entry->next; s && s != entry; s = s->next)
+  {
+    pll_unode_t * c = (pll_unode_t *)malloc(sizeof(pll_unode_t));
+    if (!c) break;
+    *c = *s;
+    c->back = NULL;
+    c->label = first->label;
+    c->next = NULL;
+    tail->next = c;
+    tail = c;
+  }
+  if (entry->next) tail->next = first;
+  return first;
+}
+
+/* copies what hangs behind the members of old's roundabout other than old itself (all members when
+ * `all`), attaching the copies to the corresponding members of the new roundabout */
+static void copy_below(pll_unode_t * fresh, const pll_unode_t * old, int all)
+{
+  const pll_unode_t * s = old;
+  pll_unode_t * c = fresh;
+  do
+  {
+    if ((all || s != old) && s->back)
+    {
+      pll_unode_t * child = copy_roundabout(s->back);
+      if (child)
+      {
+        c->back = child;
+        child->back = c;
+        copy_below(child, s->back, 0);
+      }
+    }
+    s = s->next;
+    c = c->next;
+  } while (s && s != old);
+}
+
+PLL_EXPORT pll_unode_t * pll_utree_graph_clone(const pll_unode_t * root)
+{
+  pll_unode_t * fresh = copy_roundabout(root);
+  if (!fresh)
+  {
+    tree_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return NULL;
+  }
+  copy_below(fresh, root, 1);
+  return fresh;
+}
+
+PLL_EXPORT pll_utree_t * pll_utree_clone(const pll_utree_t * tree)
+{
+  pll_unode_t * root = pll_utree_graph_clone(tree->vroot);
+  if (!root) return NULL;
+  return tree->binary ? pll_utree_wraptree(root, tree->tip_count)
+                      : pll_utree_wraptree_multi(root, tree->tip_count, tree->inner_count);
+}
+
+PLL_EXPORT int pll_utree_every_const(const pll_utree_t * tree, int (*cb)(const pll_utree_t *, const pll_unode_t *))
+{
+  unsigned int i;
+  int rc = 1;
+  for (i = 0; i < tree->tip_count + tree->inner_count; ++i) rc &= cb(tree, tree->nodes[i]);
+  return rc ? PLL_SUCCESS : PLL_FAILURE;
+}
+
+static void rshow_info(const pll_rnode_t * n, int options)
+{
+  if (options & PLL_UTREE_SHOW_LABEL) printf(" %s", n->label ? n->label : "(null)");
+  if (options & PLL_UTREE_SHOW_BRANCH_LENGTH) printf(" %f", n->length);
+  if (options & PLL_UTREE_SHOW_CLV_INDEX) printf(" %u", n->clv_index);
+  if (options & PLL_UTREE_SHOW_SCALER_INDEX) printf(" %d", n->scaler_index);
+  if (options & PLL_UTREE_SHOW_PMATRIX_INDEX) printf(" %u", n->pmatrix_index);
+  printf("\n");
+}
+
+/* bar[d] says whether column d still carries a branch: 1 while the left child's subtree is drawn, 2 from the
+ * moment the right child is reached (its own line still shows the bar, everything below it does not) */
+static void rshow_subtree(const pll_rnode_t * n, unsigned int depth, int * bar, int options)
+{
+  unsigned int i;
+  if (!n) return;
+  for (i = 0; i < depth; ++i) printf(bar[i] ? "|   " : "    ");
+  printf("\n");
+  for (i = 0; i + 1 < depth; ++i) printf(bar[i] ? "|   " : "    ");
+  printf((n->left || n->right) ? "+---+" : "+---");
+  rshow_info(n, options);
+  if (bar[depth - 1] == 2) bar[depth - 1] = 0;
+  bar[depth] = 1;
+  rshow_subtree(n->left, depth + 1, bar, options);
+  bar[depth] = 2;
+  rshow_subtree(n->right, depth + 1, bar, options);
+}
+
+static unsigned int rdepth(const pll_rnode_t * n, unsigned int d)
+{
+  unsigned int a, b;
+  if (!n) return d;
+  a = rdepth(n->left, d + 1);
+  b = rdepth(n->right, d + 1);
+  return a > b ? a : b;
+}
+
+PLL_EXPORT void pll_rtree_show_ascii(const pll_rnode_t * root, int options)
+{
+  int * bar = (int *)calloc((size_t)rdepth(root, 0) + 2, sizeof(int));
+  if (!bar)
+  {
+    tree_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return;
+  }
+  bar[0] = bar[1] = 1;
+  rshow_info(root, options);
+  rshow_subtree(root->left, 1, bar, options);
+  rshow_subtree(root->right, 1, bar, options);
+  free(bar);
+}
+
+/* src/list.c.  A list is addressed through the pointer to its first element.  append adds at the end;
+ * prepend puts the new element right after the first one, which is where the reference puts it (it then loses
+ * the elements that followed; here they stay linked behind the new one); remove unlinks the first element that
+ * carries `data` and keeps the rest of the list (the reference frees the wrong element when the match is not
+ * the head and truncates the list: not reproduced). */
+static int dlist_add(pll_dlist_t ** dlist, void * data, int at_end)
+{
+  pll_dlist_t * item = (pll_dlist_t *)malloc(sizeof(pll_dlist_t)), * after;
+  if (!item)
+  {
+    tree_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return PLL_FAILURE;
+  }
+  item->data = data;
+  item->next = item->prev = NULL;
+  if (!*dlist)
+  {
+    *dlist = item;
+    return PLL_SUCCESS;
+  }
+  after = *dlist;
+  if (at_end)
+    while (after->next) after = after->next;
+  item->next = after->next;
+  if (item->next) item->next->prev = item;
+  after->next = item;
+  item->prev = after;
+  return PLL_SUCCESS;
+}
+
+PLL_EXPORT int pll_dlist_append(pll_dlist_t ** dlist, void * data) { return dlist_add(dlist, data, 1); }
+
+PLL_EXPORT int pll_dlist_prepend(pll_dlist_t ** dlist, void * data) { return dlist_add(dlist, data, 0); }
+
+PLL_EXPORT int pll_dlist_remove(pll_dlist_t ** dlist, void * data)
+{
+  pll_dlist_t * item = *dlist;
+  while (item && item->data != data) item = item->next;
+  if (!item) return PLL_FAILURE;
+  if (item->next) item->next->prev = item->prev;
+  if (item->prev)
+    item->prev->next = item->next;
+  else
+    *dlist = item->next;
+  free(item);
+  return PLL_SUCCESS;
+}

@@ -307,3 +307,86 @@ def test_rtree_unroot(own):
     rt = own.pll_rtree_parse_newick_string(b"(A:1,B:2);")
     assert not own.pll_rtree_unroot(rt) and C.c_int.in_dll(own, "pll_errno").value == 116
     own.pll_rtree_destroy(rt, None)
+
+
+# ---- copies, rooted drawing, lists (appended helpers of pll_tree.c) --------------------------------------
+
+def test_utree_clone_is_an_independent_identical_tree(own, ref):
+    rng = np.random.default_rng(12)
+    for tips, multi in ((5, 0.0), (40, 0.0), (30, 0.5)):
+        newick = random_newick(rng, tips, multifurcate=multi)
+        tree = own.pll_utree_parse_newick_string(newick.encode())
+        own.pll_utree_clone.restype, own.pll_utree_clone.argtypes = C.POINTER(UTree), [C.POINTER(UTree)]
+        copy = own.pll_utree_clone(tree)
+        assert copy
+        a, b = tree.contents, copy.contents
+        assert (a.tip_count, a.inner_count, a.edge_count, a.binary) == (b.tip_count, b.inner_count, b.edge_count, b.binary)
+        n = a.tip_count + a.inner_count
+        seen = set()
+        for i in range(n):
+            x, y = a.nodes[i].contents, b.nodes[i].contents
+            assert C.addressof(x) != C.addressof(y)
+            assert (x.label, x.length, x.node_index, x.clv_index, x.scaler_index, x.pmatrix_index) == \
+                   (y.label, y.length, y.node_index, y.clv_index, y.scaler_index, y.pmatrix_index)
+            seen.add(C.addressof(y))
+        text = lambda t: C.string_at(own.pll_utree_export_newick(t.contents.nodes[n - 1], None))
+        assert text(tree) == text(copy)
+        # the reference's own clone of the same tree exports the same text
+        ref.pll_utree_graph_clone.restype, ref.pll_utree_graph_clone.argtypes = C.POINTER(UNode), [C.POINTER(UNode)]
+        rcopy = ref.pll_utree_graph_clone(a.nodes[n - 1])
+        assert C.string_at(ref.pll_utree_export_newick(rcopy, None)) == text(tree)
+        own.pll_utree_check_integrity.restype, own.pll_utree_check_integrity.argtypes = C.c_int, [C.POINTER(UTree)]
+        assert own.pll_utree_check_integrity(copy) == 1
+        own.pll_utree_destroy(tree, None)
+        assert text(copy)  # still readable after the original is gone
+        own.pll_utree_destroy(copy, None)
+
+
+def test_rtree_show_ascii_matches_reference(own, ref, capfd):
+    rng = np.random.default_rng(4)
+    libc.fflush.argtypes = [C.c_void_p]
+    for tips in (2, 3, 9, 31):
+        newick = random_newick(rng, tips, rooted=True)
+        tree = own.pll_rtree_parse_newick_string(newick.encode())
+        outs = []
+        for dll in (ref, own):
+            dll.pll_rtree_show_ascii.restype, dll.pll_rtree_show_ascii.argtypes = None, [C.POINTER(RNode), C.c_int]
+            for options in (1, 1 | 2 | 4, 31):
+                dll.pll_rtree_show_ascii(tree.contents.root, options)
+            libc.fflush(None)
+            outs.append(capfd.readouterr().out)
+        assert outs[0] == outs[1] and outs[1].count("+---") >= tips
+        own.pll_rtree_destroy(tree, None)
+
+
+def test_dlist_append_prepend_remove(own):
+    class DList(C.Structure):
+        pass
+
+    DList._fields_ = [("next", C.POINTER(DList)), ("prev", C.POINTER(DList)), ("data", C.c_void_p)]
+    for name in ("pll_dlist_append", "pll_dlist_prepend", "pll_dlist_remove"):
+        f = getattr(own, name)
+        f.restype, f.argtypes = C.c_int, [C.POINTER(C.POINTER(DList)), C.c_void_p]
+
+    def items(head):
+        out, prev = [], None
+        while head:
+            assert (C.addressof(head.contents.prev.contents) if head.contents.prev else None) == prev
+            out.append(head.contents.data)
+            prev = C.addressof(head.contents)
+            head = head.contents.next
+        return out
+
+    head = C.POINTER(DList)()
+    for v in (1, 2, 3):
+        assert own.pll_dlist_append(C.byref(head), v) == 1
+    assert items(head) == [1, 2, 3]
+    assert own.pll_dlist_prepend(C.byref(head), 9) == 1  # right after the first element, as in the reference
+    assert items(head) == [1, 9, 2, 3]
+    assert own.pll_dlist_remove(C.byref(head), 2) == 1
+    assert items(head) == [1, 9, 3]
+    assert own.pll_dlist_remove(C.byref(head), 1) == 1
+    assert items(head) == [9, 3]
+    assert own.pll_dlist_remove(C.byref(head), 77) == 0
+    assert own.pll_dlist_remove(C.byref(head), 3) == 1 and own.pll_dlist_remove(C.byref(head), 9) == 1
+    assert not head
