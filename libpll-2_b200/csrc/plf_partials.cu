@@ -469,7 +469,7 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
         }
         const unsigned int * d_run_prefix = nullptr;
         unsigned int total_tiles = 0;
-        if (!contiguous && h_ops[i].kind == PLF_OP_II && j - i > 1)
+        if (!contiguous && h_ops[i].kind == PLF_OP_II) /* single ops too: the tile-walk kernel is the faster gather */
         {
           if (!h_prefix) h_prefix = (unsigned int *)malloc(prefix_entries * sizeof(unsigned int));
           if (h_prefix && prefix_used + (j - i) + 1 <= prefix_entries)

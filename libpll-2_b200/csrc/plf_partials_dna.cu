@@ -238,6 +238,119 @@ k_clv_dna_ii_balanced(const plf_op_t * __restrict__ ops, int per_rate_and_nops,
   }
 }
 
+/* The same tile walk with the two P-matrices (and the op descriptor) staged in shared memory instead of held
+ * in 64 + ~28 registers per thread, and U = 2 instead of 4 items in flight: 64 registers, 8 instead of 3 resident
+ * CTAs per SM.  The gathers are latency-bound (class -> site -> child class -> CLV block), so resident warps are
+ * what buys bandwidth: config 4 traversal 2.23 -> 1.39 ms (3.1 -> 5.0 TB/s algorithmic); sweep over U x CTAs in
+ * profiles/r1_notes.md.  Rows are read back with 128-bit shared loads, 8 rows per (site, rate) item; the rows of
+ * the rates are 18 doubles apart so that lanes of different rates hit different banks (16 apart: 4-way conflicts,
+ * 3.04 ms). */
+template <int LOG2R, int U, int CTAS>
+__global__ void __launch_bounds__(DNA_THREADS, CTAS)
+k_clv_dna_ii_balanced_sm(const plf_op_t * __restrict__ ops, int per_rate_and_nops,
+                         const unsigned int * __restrict__ tile_prefix)
+{
+  constexpr int R = 1 << LOG2R;
+  constexpr unsigned int TILE_SITES = (DNA_THREADS * 4) >> LOG2R;
+  constexpr unsigned int PASS = DNA_THREADS >> LOG2R;
+  constexpr int MS = 18; /* doubles per rate: 16 + 2 of padding, so that the rates' rows fall into different banks */
+  __shared__ __align__(16) double Ls[R * MS];
+  __shared__ __align__(16) double Rs[R * MS];
+  __shared__ plf_op_t s_op;
+  const int per_rate = per_rate_and_nops & 1;
+  const unsigned int nops = (unsigned int)per_rate_and_nops >> 1;
+  const unsigned int total = tile_prefix[nops];
+  const unsigned int share = (total + gridDim.x - 1) / gridDim.x;
+  const unsigned int lo = blockIdx.x * share;
+  const unsigned int hi = min(lo + share, total);
+  if (lo >= hi) return;
+  const int rate = threadIdx.x & (R - 1);
+  const unsigned int site_in_tile = threadIdx.x >> LOG2R;
+
+  unsigned int cur = 0;
+  {
+    unsigned int a = 0, b = nops;
+    while (b - a > 1)
+    {
+      const unsigned int m = (a + b) >> 1;
+      if (tile_prefix[m] <= lo)
+        a = m;
+      else
+        b = m;
+    }
+    cur = a;
+  }
+  unsigned int next = tile_prefix[cur + 1], first = tile_prefix[cur];
+  bool reload = true;
+  for (unsigned int t = lo; t < hi; ++t)
+  {
+    if (t >= next)
+    {
+      do
+        ++cur;
+      while (t >= tile_prefix[cur + 1]);
+      next = tile_prefix[cur + 1];
+      first = tile_prefix[cur];
+      reload = true;
+    }
+    if (reload) /* the same for every thread of the CTA */
+    {
+      __syncthreads(); /* nobody still reads the previous op's matrices */
+      if (threadIdx.x == 0) s_op = ops[cur];
+      {
+        const plf_op_t & o = ops[cur];
+        for (int i = threadIdx.x; i < R * 16; i += DNA_THREADS)
+        {
+          Ls[(i >> 4) * MS + (i & 15)] = o.left_matrix[i];
+          Rs[(i >> 4) * MS + (i & 15)] = o.right_matrix[i];
+        }
+      }
+      __syncthreads();
+      reload = false;
+    }
+    const plf_op_t & op = s_op;
+    const double * Lm = Ls + rate * MS;
+    const double * Rm = Rs + rate * MS;
+    for (unsigned int part = 0; part < 4 / U; ++part) /* a tile is 4 items per thread, U of them in flight */
+    {
+    const unsigned int base = (t - first) * TILE_SITES + part * U * PASS;
+    SiteRef s[U];
+    dbl4 l[U], r[U];
+    unsigned int sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      s[u] = resolve_site(op, base + u * PASS + site_in_tile);
+      l[u] = r[u] = dbl4{0, 0, 0, 0};
+      sc[u] = 0;
+      if (s[u].active)
+      {
+        l[u] = ld256_stream(op.left_clv + ((size_t)s[u].lid * R + rate) * 4);
+        r[u] = ld256_stream(op.right_clv + ((size_t)s[u].rid * R + rate) * 4);
+        if (op.parent_scaler)
+        {
+          if (per_rate)
+            sc[u] = (op.left_scaler ? op.left_scaler[(size_t)s[u].lid * R + rate] : 0u) +
+                    (op.right_scaler ? op.right_scaler[(size_t)s[u].rid * R + rate] : 0u);
+          else if (rate == 0)
+            sc[u] = (op.left_scaler ? op.left_scaler[s[u].lid] : 0u) + (op.right_scaler ? op.right_scaler[s[u].rid] : 0u);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      dbl4 v;
+      v.x = dot4_pairwise(Lm + 0, l[u]) * dot4_pairwise(Rm + 0, r[u]);
+      v.y = dot4_pairwise(Lm + 4, l[u]) * dot4_pairwise(Rm + 4, r[u]);
+      v.z = dot4_pairwise(Lm + 8, l[u]) * dot4_pairwise(Rm + 8, r[u]);
+      v.w = dot4_pairwise(Lm + 12, l[u]) * dot4_pairwise(Rm + 12, r[u]);
+      scale_and_store<LOG2R>(op, s[u], rate, per_rate, sc[u], v);
+    }
+    }
+  }
+}
+
 /* ---- tip-inner (the tip is "left") --------------------------------------------- */
 template <int LOG2R, int U>
 __global__ void __launch_bounds__(DNA_THREADS, 4)
@@ -787,7 +900,7 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     return 1;
   }
 
-  if (kind == PLF_OP_II && !contiguous && d_tile_prefix && total_tiles && nops > 1 && ctx->dna_balanced)
+  if (kind == PLF_OP_II && !contiguous && d_tile_prefix && total_tiles && ctx->dna_balanced)
   {
     dna_balanced_kernel_t kb = nullptr;
     switch (log2r)
@@ -799,6 +912,16 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
       case 4: kb = k_clv_dna_ii_balanced<4, 4>; break;
       default: kb = k_clv_dna_ii_balanced<5, 4>; break;
     }
+    if (ctx->dna_balanced != 9) /* PLF_DNA_BALANCED=9 keeps the P-matrices in registers (3 CTAs per SM) for A/B runs */
+      switch (log2r)
+      {
+        case 0: kb = k_clv_dna_ii_balanced_sm<0, 2, 8>; break;
+        case 1: kb = k_clv_dna_ii_balanced_sm<1, 2, 8>; break;
+        case 2: kb = k_clv_dna_ii_balanced_sm<2, 2, 8>; break;
+        case 3: kb = k_clv_dna_ii_balanced_sm<3, 2, 8>; break;
+        case 4: kb = k_clv_dna_ii_balanced_sm<4, 2, 8>; break;
+        default: kb = k_clv_dna_ii_balanced_sm<5, 2, 8>; break;
+      }
     int & occ = ctx->dna_balanced_occupancy[log2r];
     if (!occ)
     {
