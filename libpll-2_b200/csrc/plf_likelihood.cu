@@ -374,6 +374,73 @@ __device__ __forceinline__ void deriv_accumulate(const plf_deriv_t & a, const Mo
 
   acc1 = 0;
   acc2 = 0;
+  if (ST == 4 && RT == 1)
+  {
+    /* 4 states, one rate per lane: the loads of four sweeps of the grid are issued before the first use (the
+     * loads are volatile asm and would otherwise go out one at a time); sums are added in the same order as
+     * by the plain loop below, so the result has the same bits */
+    const int rate = lane_in_site;
+    const double * d = diag + (size_t)rate * 4 * 3;
+    const double pinv = M.pinv[rate], wr = M.weights[rate];
+    for (unsigned int s0 = warp_site0; s0 < a.sites; s0 += 4 * sites_per_iter)
+    {
+      dbl4 sv[4];
+      double pw[4];
+      int inv[4];
+      bool active[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const unsigned int n = s0 + u * sites_per_iter + (my_site0 - warp_site0);
+        active[u] = n < a.sites;
+        sv[u] = dbl4{0, 0, 0, 0};
+        pw[u] = 0;
+        inv[u] = -1;
+        if (active[u])
+        {
+          sv[u] = ld256_stream(a.sumtable + (size_t)n * span + (size_t)rate * 4);
+          if (lane_in_site == 0) pw[u] = (double)a.pattern_weights[n];
+          if (a.invariant) inv[u] = a.invariant[n];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        /* warps past the end of the alignment leave together: the shuffles below stay converged */
+        if (s0 + u * sites_per_iter >= a.sites) break;
+        const double x[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+        double c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          c0 = fma(x[j], d[j * 3 + 0], c0);
+          c1 = fma(x[j], d[j * 3 + 1], c1);
+          c2 = fma(x[j], d[j * 3 + 2], c2);
+        }
+        if (pinv > 0)
+        {
+          const double inv_lk = (inv[u] == -1) ? 0.0 : M.freqs[(size_t)rate * sp + inv[u]] * pinv;
+          c0 = c0 * (1.0 - pinv) + inv_lk;
+          c1 = c1 * (1.0 - pinv);
+          c2 = c2 * (1.0 - pinv);
+        }
+        double lk0 = active[u] ? fma(c0, wr, 0.0) : 0.0;
+        double lk1 = active[u] ? fma(c1, wr, 0.0) : 0.0;
+        double lk2 = active[u] ? fma(c2, wr, 0.0) : 0.0;
+        lk0 = group_sum(lk0, L);
+        lk1 = group_sum(lk1, L);
+        lk2 = group_sum(lk2, L);
+        if (active[u] && lane_in_site == 0)
+        {
+          const double d1 = -lk1 / lk0;
+          const double d2 = d1 * d1 - lk2 / lk0;
+          acc1 = fma(pw[u], d1, acc1);
+          acc2 = fma(pw[u], d2, acc2);
+        }
+      }
+    }
+    return;
+  }
   for (unsigned int s0 = warp_site0; s0 < a.sites; s0 += sites_per_iter)
   {
     const unsigned int n = s0 + (my_site0 - warp_site0);
@@ -547,7 +614,7 @@ __device__ __forceinline__ void block_sum2(double & a, double & b, double * red)
 }
 
 template <int ST>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 k_newton(plf_deriv_t a, int R, int st_rt, int sp_rt, int L, double * __restrict__ partial, plf_newton_args nw,
          double * out, double * hout)
 {
@@ -614,16 +681,16 @@ template <int ST>
 static int newton_launch(plf_ctx * ctx, const plf_deriv_t * a, int R, int st, int sp, int L, const plf_newton_args & nw,
                          size_t smem, double * dst, double * hdst)
 {
-  /* few, large blocks: the grid barrier and the re-reduction of the partials grow with the block count, and the
-   * table is L2-resident, so occupancy buys little (PLF_NEWTON_THREADS / PLF_NEWTON_BPS override for experiments) */
+  /* few, large blocks: the grid barrier and the re-reduction of the partials grow with the block count
+   * (PLF_NEWTON_THREADS / PLF_NEWTON_BPS override for experiments) */
   static int threads = 0, bps = 0;
   if (!threads)
   {
     const char * v = getenv("PLF_NEWTON_THREADS");
     const int t = v ? atoi(v) : 0;
-    threads = (t == 256 || t == 512 || t == 1024) ? t : 1024;
+    threads = (t == 256 || t == 512) ? t : 512;
     v = getenv("PLF_NEWTON_BPS");
-    bps = (v && atoi(v) > 0) ? atoi(v) : 1;
+    bps = (v && atoi(v) > 0) ? atoi(v) : 2;
   }
   int per_sm = 0;
   PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_newton<ST>, threads, smem));
