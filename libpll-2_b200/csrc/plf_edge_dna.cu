@@ -392,7 +392,7 @@ k_deriv_dna(plf_deriv_t a, double * __restrict__ partial, unsigned int * ticket,
  *  ws = [plf_op_t (128 B)] [left R x 16] [right R x 16]                       *
  *  left[r][j][k] = pi_k Vinv[k][j] ("parent" side), right[r][j][k] = V[j][k]   *
  * ------------------------------------------------------------------------ */
-__global__ void k_sumtable_op(plf_sumtable_t a, int R, int st, int sp, unsigned char * ws)
+__global__ void k_sumtable_op(plf_sumtable_t a, int R, int st, int sp, unsigned char * ws, unsigned int ntiles)
 {
   plf_op_t * op = reinterpret_cast<plf_op_t *>(ws);
   double * lm = reinterpret_cast<double *>(ws + 128);
@@ -424,6 +424,10 @@ __global__ void k_sumtable_op(plf_sumtable_t a, int R, int st, int sp, unsigned 
     o.nsites = a.sites;
     o.kind = a.tipchars ? PLF_OP_TI : PLF_OP_II;
     *op = o;
+    /* tile list of this one op for the tile-walk gather kernel (last 8 bytes of the descriptor's slot) */
+    unsigned int * prefix = reinterpret_cast<unsigned int *>(ws + 120);
+    prefix[0] = 0;
+    prefix[1] = ntiles;
   }
 }
 
@@ -435,15 +439,18 @@ int plf_sumtable_as_clv(plf_ctx * ctx, const plf_shape_t * sh, const plf_sumtabl
   unsigned char * ws =
       (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_edge, 128 + (size_t)2 * R * st * sp * sizeof(double));
   if (!ws) return 0;
-  static_assert(sizeof(plf_op_t) <= 128, "op descriptor must fit its slot");
-  k_sumtable_op<<<1, 256, 0, ctx->stream>>>(*a, R, st, sp, ws);
-  plf_count_launch();
-  PLF_CHECK(ctx, cudaGetLastError());
+  static_assert(sizeof(plf_op_t) <= 120, "op descriptor and its two-entry tile list must fit the 128-byte slot");
   const int contiguous = !(a->p_site_id || a->c_site_id);
   const unsigned int kind = a->tipchars ? PLF_OP_TI : PLF_OP_II;
+  const int pow2 = sh->rate_cats && !(sh->rate_cats & (sh->rate_cats - 1)) && sh->rate_cats <= 32;
+  const unsigned int ntiles = (st == 4 && pow2 && !contiguous && kind == PLF_OP_II)
+                                  ? plf_dna_balanced_tiles(a->sites, sh->rate_cats) : 0;
+  k_sumtable_op<<<1, 256, 0, ctx->stream>>>(*a, R, st, sp, ws, ntiles);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
   if (st == 4)
     return plf_launch_dna_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
-                                contiguous, nullptr, 0);
+                                contiguous, ntiles ? reinterpret_cast<const unsigned int *>(ws + 120) : nullptr, ntiles);
   return plf_launch_aa_mma_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
                                  d_tipmap, maxstates, contiguous);
 }
