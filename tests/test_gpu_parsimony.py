@@ -342,6 +342,36 @@ def test_stepwise_addition_builds_the_reference_tree(reflib, cudalib, kind, tips
         gpu.close()
 
 
+def test_no_informative_site_at_all(reflib, cudalib):
+    """constant and singleton columns only: zero-length bit vectors, every placement costs the same and the first
+    edge wins; counts, costs and the stepwise tree still equal the reference's"""
+    tips, sites = 9, 64
+    ds = make_ds("dna", tips, sites, seed=77)
+    col = np.frombuffer(b"ACGT" * (sites // 4), dtype=np.uint8).copy()
+    seqs = [col.copy() for _ in range(tips)]
+    seqs[3][5] = ord("T") if seqs[3][5] != ord("T") else ord("A")  # one singleton
+    ds.seqs = [bytes(x) for x in seqs]
+    ref, gpu = pars_pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    labels = [f"x{i}" for i in range(tips)]
+    try:
+        assert gpu.c.informative_count == ref.c.informative_count == 0
+        assert gpu.c.packedvector_count == ref.c.packedvector_count == 0
+        assert gpu.c.const_cost == ref.c.const_cost == 1
+        triples = tree_triples(ds)
+        ref.update(triples)
+        gpu.update(triples)
+        np.testing.assert_array_equal(gpu.costs(), ref.costs())
+        a, b, _ = ds.tree.root_edge
+        assert cudalib.pll_fastparsimony_edge_score(gpu.p, a, b) == reflib.pll_fastparsimony_edge_score(ref.p, a, b) == 1
+        t_ref, c_ref = run_stepwise(reflib, [ref], labels, 4)
+        t_gpu, c_gpu = run_stepwise(cudalib, [gpu], labels, 4)
+        assert c_gpu == c_ref == 1
+        assert splits(t_gpu) == splits(t_ref)
+    finally:
+        ref.close()
+        gpu.close()
+
+
 def test_stepwise_over_two_partitions(reflib, cudalib):
     tips = 20
     ds1 = make_ds("dna", tips, 900, seed=31)
