@@ -727,3 +727,29 @@ def test_fused_newton_rejects_bad_arguments(cudalib):
         gpu.newton(st, 0.1, tmin=1.0, tmax=0.5)
     assert gpu.newton(st, 0.1)[3] >= 1
     gpu.close()
+
+
+@pytest.mark.parametrize("kind,attrs", [("dna", capi.PATTERN_TIP), ("dna", 0), ("dna", capi.SITE_REPEATS),
+                                        ("aa", capi.PATTERN_TIP), ("aa", 0)])
+def test_illegal_tip_character_fails_and_leaves_the_partition_intact(reflib, cudalib, kind, attrs):
+    """pll_set_tip_states with a character the map does not know (src/pll.c:900-910): PLL_FAILURE,
+    PLL_ERROR_TIPDATA_ILLEGALSTATE and the reference's message; the tip keeps its previous states."""
+    ds = make_ds(kind, 9, 203, "random", seed=5)
+    ref, gpu = pair(reflib, cudalib, ds, attrs)
+    want = ref.full_traversal()
+    assert_rel(gpu.full_traversal(), want, LOGL_RTOL, "logL before")
+    for pos in (0, 7, 8, 100, 202):
+        bad = bytearray(ds.seqs[3])
+        bad[pos] = ord("!")
+        bad[(pos + 50) % 203] = ord("#")
+        msgs = []
+        for eng in (ref, gpu):
+            rc = eng.lib.pll_set_tip_states(eng.p, 3, eng.map, bytes(bad))
+            assert rc == 0 and eng.lib.errno == 114
+            msgs.append(eng.lib.errmsg)
+        assert msgs[0] == msgs[1]
+    assert_rel(gpu.full_traversal(), want, LOGL_RTOL, "logL after the failed calls")
+    assert gpu.lib.pll_set_tip_states(gpu.p, 3, gpu.map, ds.seqs[3]) == 1
+    assert_rel(gpu.full_traversal(), want, LOGL_RTOL, "logL after re-setting the tip")
+    ref.close()
+    gpu.close()
