@@ -115,6 +115,8 @@ int plf_pool_reserve(plf_ctx_t * ctx, size_t bytes);
 int plf_upload(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_download(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_memset0(plf_ctx_t * ctx, void * dst, size_t bytes);
+void * plf_pinned_alloc(plf_ctx_t * ctx, size_t bytes);
+void plf_pinned_free(plf_ctx_t * ctx, void * p);
 int plf_sync(plf_ctx_t * ctx);
 unsigned long long plf_kernel_launches(void);
 void plf_device_description(const plf_ctx_t * ctx, char * buf, size_t len);

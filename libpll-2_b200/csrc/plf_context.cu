@@ -249,6 +249,27 @@ extern "C" int plf_download(plf_ctx_t * ctx, void * dst, const void * src, size_
   return 1;
 }
 
+/* page-locked host staging (truly asynchronous H2D copies) */
+extern "C" void * plf_pinned_alloc(plf_ctx_t * ctx, size_t bytes)
+{
+  void * p = NULL;
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMallocHost(&p, bytes) != cudaSuccess)
+  {
+    cudaGetLastError();
+    plf_set_error(ctx, "pinned host allocation of %zu bytes failed", bytes);
+    return NULL;
+  }
+  return p;
+}
+
+extern "C" void plf_pinned_free(plf_ctx_t * ctx, void * p)
+{
+  if (!p) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFreeHost(p);
+}
+
 extern "C" int plf_memset0(plf_ctx_t * ctx, void * dst, size_t bytes)
 {
   if (!bytes) return 1;

@@ -96,7 +96,8 @@ typedef struct cuda_partition
   size_t persite_cap;
 
   /* scratch for pll_set_tip_states */
-  unsigned char * tip_scratch; /* host: mapped codes of the tip being set */
+  unsigned char * tip_scratch; /* page-locked host buffer: codes of the tip being set */
+  int tip_scratch_busy;        /* its last upload may still be in flight */
   unsigned char * d_seq;
   unsigned long long * d_map;
 
@@ -289,6 +290,7 @@ static void destroy(cuda_partition_t * cp)
     plf_free(cp->ctx, cp->d_persite);
     plf_free(cp->ctx, cp->d_seq);
     plf_free(cp->ctx, cp->d_map);
+    plf_pinned_free(cp->ctx, cp->tip_scratch);
     plf_ctx_destroy(cp->ctx);
   }
   if (p->tipchars)
@@ -324,7 +326,6 @@ static void destroy(cuda_partition_t * cp)
   free(cp->asc_sc);
   free(cp->h_model);
   free(cp->h_model_sent);
-  free(cp->tip_scratch);
   free(cp->h_ops);
   free(cp->h_ops_sorted);
   free(cp->h_level);
@@ -1118,19 +1119,20 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_
 
   if (partition->attributes & PLL_ATTRIB_PATTERN_TIP)
   {
-    unsigned char * tc;
+    /* The codes are built in a page-locked scratch buffer, sent from there without waiting (the next call waits
+     * before it reuses the scratch) and copied into the host mirror while the transfer runs.  Nothing of the
+     * partition is touched when the sequence holds an illegal character. */
+    unsigned char * tc, * scratch;
     unsigned short lut[PLL_ASCII_SIZE];
+    if (!cp->tip_scratch) cp->tip_scratch = (unsigned char *)plf_pinned_alloc(cp->ctx, (size_t)sites_alloc(partition) + 8);
+    if (!cp->tip_scratch) return cuda_fail(cp);
+    if (cp->tip_scratch_busy && !plf_sync(cp->ctx)) return cuda_fail(cp);
+    cp->tip_scratch_busy = 0;
+    scratch = cp->tip_scratch;
     if (partition->states == 4)
     {
-      /* nothing of the partition is touched when the sequence holds an illegal character: scratch first */
       for (i = 0; i < PLL_ASCII_SIZE; ++i) lut[i] = map[i] ? (unsigned short)(map[i] & 255) : ILLEGAL_CHAR;
-      if (!cp->tip_scratch) cp->tip_scratch = (unsigned char *)malloc((size_t)sites_alloc(partition) + 8);
-      if (!cp->tip_scratch)
-      {
-        set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate tip mapping scratch.%s", NULL);
-        return PLL_FAILURE;
-      }
-      if (map_bytes(cp->tip_scratch, sequence, partition->sites, lut) & ILLEGAL_CHAR)
+      if (map_bytes(scratch, sequence, partition->sites, lut) & ILLEGAL_CHAR)
         return check_sequence(partition, map, sequence);
     }
     if (partition->tipchars)
@@ -1138,17 +1140,15 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_
     else if (!charmap_create(cp, map))
       return PLL_FAILURE;
     tc = partition->tipchars[tip_index];
-    if (partition->states == 4)
-      memcpy(tc, cp->tip_scratch, partition->sites);
-    else
+    if (partition->states != 4)
     {
       for (i = 0; i < PLL_ASCII_SIZE; ++i) lut[i] = partition->charmap[i];
-      map_bytes(tc, sequence, partition->sites, lut);
+      map_bytes(scratch, sequence, partition->sites, lut);
     }
     if (partition->asc_bias_alloc)
     {
       /* pseudo-site i: every tip shows state i (src/pll.c:897-905, 935-957) */
-      unsigned char * extra = tc + partition->sites;
+      unsigned char * extra = scratch + partition->sites;
       if (partition->states == 4)
         for (i = 0; i < 4; ++i) extra[i] = (unsigned char)(1u << i);
       else
@@ -1165,7 +1165,9 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_
         }
       }
     }
-    if (!plf_upload(cp->ctx, cp->d_tipchars[tip_index], tc, sites_alloc(partition))) return cuda_fail(cp);
+    if (!plf_upload_async(cp->ctx, cp->d_tipchars[tip_index], scratch, sites_alloc(partition))) return cuda_fail(cp);
+    cp->tip_scratch_busy = 1;
+    memcpy(tc, scratch, sites_alloc(partition));
     return PLL_SUCCESS;
   }
 
