@@ -753,3 +753,31 @@ def test_illegal_tip_character_fails_and_leaves_the_partition_intact(reflib, cud
     assert_rel(gpu.full_traversal(), want, LOGL_RTOL, "logL after re-setting the tip")
     ref.close()
     gpu.close()
+
+
+@pytest.mark.parametrize("cats,per_rate,tips,sites,tree", [
+    (1, False, 40, 700, "random"), (2, False, 40, 700, "random"), (8, False, 40, 700, "random"),
+    (16, True, 30, 300, "random"), (32, False, 24, 260, "random"), (3, False, 30, 400, "random"),
+    (2, False, 260, 96, "caterpillar"), (8, True, 260, 96, "caterpillar"),
+])
+def test_site_repeats_rate_counts(reflib, cudalib, cats, per_rate, tips, sites, tree):
+    """Every rate-count instantiation of the site-repeat CLV kernel (1..32 categories, the shared-memory matrix
+    tables grow with it), a count that is not a power of two (generic kernel), deep trees that scale."""
+    brlen = (0.002, 0.05) if tree == "random" else (0.02, 0.22)
+    ds = synth.dna_dataset(tips, sites, seed=41 + cats, cats=cats, tree_kind=tree, alpha=0.3, brlen=brlen)
+    ref, gpu = pair(reflib, cudalib, ds, capi.SITE_REPEATS, per_rate)
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.update_partials()
+    n_scaled = 0
+    for op in ref.ops:
+        assert ref.repeat_ids(op.parent_clv_index)[0] == gpu.repeat_ids(op.parent_clv_index)[0]
+        assert_clv_equal(ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index), True, f"clv {op.parent_clv_index}")
+        sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
+        assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
+        n_scaled += int(sa.sum())
+    if tree == "caterpillar":
+        assert n_scaled > 0
+    check_edge_and_derivatives(ref, gpu, ds, per_rate)
+    ref.close()
+    gpu.close()
