@@ -258,6 +258,13 @@ int plf_pars_pack(plf_pars_t * ps, const plf_pars_tips_t * tp,
 int plf_pars_update(plf_pars_t * ps, unsigned int * d_vec, unsigned int states,
                     unsigned int words, const unsigned int * h_ops,
                     unsigned int count, unsigned int * h_scores);
+/* the same list sorted into levels of mutually independent operations (level l =
+ * entries [h_level_start[l], h_level_start[l+1])): one launch per level */
+int plf_pars_update_levels(plf_pars_t * ps, unsigned int * d_vec,
+                           unsigned int states, unsigned int words,
+                           const unsigned int * h_ops, unsigned int count,
+                           const unsigned int * h_level_start,
+                           unsigned int nlevels, unsigned int * h_scores);
 /* h_pairs: n x {node1, node2}; one launch for the whole batch */
 int plf_pars_edge_scores(plf_pars_t * ps, const unsigned int * d_vec,
                          unsigned int states, unsigned int words,

@@ -492,6 +492,106 @@ extern "C" int plf_pars_update(plf_pars_t * ps, unsigned int * d_vec, unsigned i
   return 1;
 }
 
+/* One level of a level-scheduled list: blockIdx.y = operation, independent of all others of the launch.  Wide
+ * trees keep the chip busy this way (words x operations of a level threads instead of words threads running a
+ * chain as deep as the list); the host picks between the two forms (plf_pars_update_levels). */
+template <int ST>
+__global__ void __launch_bounds__(PARS_THREADS)
+k_pars_level(unsigned int * vec, size_t node_stride, unsigned int states, unsigned int words,
+             const unsigned int * __restrict__ ops, unsigned int * scores)
+{
+  const unsigned int o = blockIdx.y;
+  unsigned int * parent = vec + ops[3 * o] * node_stride;
+  const unsigned int * c1 = vec + ops[3 * o + 1] * node_stride;
+  const unsigned int * c2 = vec + ops[3 * o + 2] * node_stride;
+  unsigned int pc = 0;
+  for (unsigned int w = blockIdx.x * PARS_THREADS + threadIdx.x; w < words; w += gridDim.x * PARS_THREADS)
+  {
+    unsigned int orvand = 0;
+    if constexpr (ST > 0)
+    {
+      unsigned int x[ST > 0 ? ST : 1], y[ST > 0 ? ST : 1];
+#pragma unroll
+      for (int j = 0; j < ST; ++j)
+      {
+        x[j] = c1[(size_t)j * words + w];
+        y[j] = c2[(size_t)j * words + w];
+      }
+#pragma unroll
+      for (int j = 0; j < ST; ++j) orvand |= x[j] & y[j];
+#pragma unroll
+      for (int j = 0; j < ST; ++j) parent[(size_t)j * words + w] = (x[j] & y[j]) | (~orvand & (x[j] | y[j]));
+    }
+    else
+    {
+      for (unsigned int j = 0; j < states; ++j) orvand |= c1[(size_t)j * words + w] & c2[(size_t)j * words + w];
+      for (unsigned int j = 0; j < states; ++j)
+      {
+        const unsigned int a = c1[(size_t)j * words + w], b = c2[(size_t)j * words + w];
+        parent[(size_t)j * words + w] = (a & b) | (~orvand & (a | b));
+      }
+    }
+    pc += __popc(~orvand);
+  }
+  pc = __reduce_add_sync(0xffffffffu, pc);
+  if ((threadIdx.x & 31) == 0 && pc) atomicAdd(scores + o, pc);
+}
+
+/* h_ops: the list sorted by level (level l = entries [h_level_start[l], h_level_start[l+1])), no entry of a
+ * level reads or writes what another entry of the same level writes; h_scores in the same order.  One launch
+ * per level, one synchronisation at the end. */
+extern "C" int plf_pars_update_levels(plf_pars_t * ps, unsigned int * d_vec, unsigned int states, unsigned int words,
+                                      const unsigned int * h_ops, unsigned int count,
+                                      const unsigned int * h_level_start, unsigned int nlevels,
+                                      unsigned int * h_scores)
+{
+  plf_ctx * ctx = ps->ctx;
+  if (!count) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (!pars_reserve(ps, (size_t)4 * count)) return 0;
+  if (!words)
+  {
+    memset(h_scores, 0, count * sizeof(unsigned int));
+    return 1;
+  }
+  unsigned int * d_ops = ps->d_small, * d_scores = ps->d_small + (size_t)3 * count;
+  memcpy(ps->h_pin, h_ops, (size_t)3 * count * sizeof(unsigned int));
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, ps->h_pin, (size_t)3 * count * sizeof(unsigned int), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  PLF_CHECK(ctx, cudaMemsetAsync(d_scores, 0, count * sizeof(unsigned int), ctx->stream));
+  const size_t stride = (size_t)states * words;
+  const unsigned int full = (words + PARS_THREADS - 1) / PARS_THREADS;
+  for (unsigned int l = 0; l < nlevels; ++l)
+  {
+    const unsigned int a = h_level_start[l], n = h_level_start[l + 1] - a;
+    if (!n) continue;
+    /* enough CTAs along x to fill the chip when the level is narrow, one sweep of the vector otherwise */
+    unsigned int gx = full;
+    const unsigned int want = (unsigned int)(ctx->sm_count * 8 + n - 1) / n;
+    if (gx > want) gx = want ? want : 1;
+    for (unsigned int done = 0; done < n; done += 65535u) /* gridDim.y limit */
+    {
+      const unsigned int m = n - done < 65535u ? n - done : 65535u;
+      const dim3 grid(gx, m);
+      const unsigned int * o = d_ops + (size_t)3 * (a + done);
+      unsigned int * sc = d_scores + a + done;
+      if (states == 4)
+        k_pars_level<4><<<grid, PARS_THREADS, 0, ctx->stream>>>(d_vec, stride, states, words, o, sc);
+      else if (states == 20)
+        k_pars_level<20><<<grid, PARS_THREADS, 0, ctx->stream>>>(d_vec, stride, states, words, o, sc);
+      else
+        k_pars_level<0><<<grid, PARS_THREADS, 0, ctx->stream>>>(d_vec, stride, states, words, o, sc);
+      plf_count_launch();
+    }
+  }
+  PLF_CHECK(ctx, cudaGetLastError());
+  PLF_CHECK(ctx, cudaMemcpyAsync(ps->h_pin + (size_t)3 * count, d_scores, count * sizeof(unsigned int),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(h_scores, ps->h_pin + (size_t)3 * count, count * sizeof(unsigned int));
+  return 1;
+}
+
 /* ---- edge scores and the insertion scan ----------------------------------------------------------------- */
 
 /* MODE 0: score[e] = popcount of the sites where the vectors of pair e share no state.

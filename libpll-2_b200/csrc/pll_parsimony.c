@@ -30,6 +30,8 @@ typedef struct cuda_parsimony
   unsigned int nodes_count;
   unsigned int * scratch; /* host: scores of the current call */
   unsigned int scratch_cap;
+  int no_levels;          /* PLF_PARS_LEVELS=0: always the one-launch chain kernel */
+  int force_levels;       /* PLF_PARS_LEVELS=2: always one launch per level (tests) */
   /* weighted (Sankoff) parsimony objects made by pll_parsimony_create: sbuffer[] / anc_states[] are managed
    * allocations (the reference's clients read them on the host), mirrored as device pointer tables */
   int weighted;
@@ -138,6 +140,11 @@ PLL_EXPORT pll_parsimony_t * pll_fastparsimony_init(const pll_partition_t * part
     return NULL;
   }
   cp->magic = PARS_MAGIC;
+  {
+    const char * v = getenv("PLF_PARS_LEVELS");
+    cp->no_levels = v && v[0] == '0';
+    cp->force_levels = v && v[0] == '2';
+  }
   cp->pub.tips = partition->tips;
   cp->pub.inner_nodes = partition->tips - 1;
   cp->pub.sites = partition->sites;
@@ -217,18 +224,80 @@ static int pars_indices_ok(const cuda_parsimony_t * cp, const unsigned int * idx
   return 1;
 }
 
+/* Level of every operation of a list that must behave as if run in order: an operation goes one level above
+ * the last writer of its children (read after write), above the last reader of its parent (write after read) and
+ * above the last writer of its parent.  lw / lr: per vector, level of the last write / read so far (0 = none).
+ * Returns the number of levels. */
+static unsigned int pars_levels(const pll_pars_buildop_t * ops, unsigned int count, unsigned int * level,
+                                unsigned int * lw, unsigned int * lr, unsigned int nvec)
+{
+  unsigned int i, nlevels = 0;
+  memset(lw, 0, (size_t)nvec * sizeof(unsigned int));
+  memset(lr, 0, (size_t)nvec * sizeof(unsigned int));
+  for (i = 0; i < count; ++i)
+  {
+    const unsigned int p = ops[i].parent_score_index, a = ops[i].child1_score_index, b = ops[i].child2_score_index;
+    unsigned int l = lw[a] > lw[b] ? lw[a] : lw[b];
+    if (lr[p] > l) l = lr[p];
+    if (lw[p] > l) l = lw[p];
+    ++l;
+    level[i] = l;
+    lw[p] = l;
+    if (lr[a] < l) lr[a] = l;
+    if (lr[b] < l) lr[b] = l;
+    if (l > nlevels) nlevels = l;
+  }
+  return nlevels;
+}
+
 PLL_EXPORT void pll_fastparsimony_update_vectors(pll_parsimony_t * parsimony, const pll_pars_buildop_t * ops,
                                                  unsigned int count)
 {
   cuda_parsimony_t * cp = PP(parsimony);
-  unsigned int * scores, i;
+  unsigned int * scores, i, nlevels = 0;
   if (!cp || !count) return;
   /* pll_pars_buildop_t is three consecutive unsigned ints: the list goes to the device as it is */
   if (!pars_indices_ok(cp, (const unsigned int *)ops, (size_t)3 * count)) return;
-  scores = pars_scratch(cp, count);
+  /* scratch: scores [count] | level [count] | sorted ops [3 count] | position [count] | start [count + 2] |
+   * last write, last read [nvec each] */
+  scores = pars_scratch(cp, 7 * count + 2 + 2 * cp->nodes_count);
   if (!scores) return;
-  if (!plf_pars_update(cp->ps, cp->d_vec, cp->pub.states, cp->pub.packedvector_count, (const unsigned int *)ops, count,
-                       scores))
+  if ((count >= 8 || cp->force_levels) && !cp->no_levels)
+  {
+    unsigned int * level = scores + count, * sorted = level + count, * pos = sorted + 3 * (size_t)count;
+    unsigned int * start = pos + count, * lw = start + count + 2, * lr = lw + cp->nodes_count;
+    nlevels = pars_levels(ops, count, level, lw, lr, cp->nodes_count);
+    /* A launch per level costs a few microseconds, an operation in the one-launch chain a little under one:
+     * levels pay when the list is several times longer than it is deep (wide trees) */
+    if ((unsigned long long)nlevels * 4 <= count || cp->force_levels)
+    {
+      memset(start, 0, ((size_t)nlevels + 2) * sizeof(unsigned int));
+      for (i = 0; i < count; ++i) start[level[i]]++; /* level l (1-based) counted in start[l] */
+      for (i = 1; i <= nlevels; ++i) start[i] += start[i - 1];
+      /* start[l] is now the end of level l = the start of level l + 1: fill every level from its end */
+      for (i = count; i-- > 0;)
+      {
+        const unsigned int at = --start[level[i]];
+        pos[i] = at;
+        sorted[3 * (size_t)at] = ops[i].parent_score_index;
+        sorted[3 * (size_t)at + 1] = ops[i].child1_score_index;
+        sorted[3 * (size_t)at + 2] = ops[i].child2_score_index;
+      }
+      /* after the fill start[l] is the start of level l (1-based); start[nlevels + 1] closes the last one */
+      start[nlevels + 1] = count;
+      if (!plf_pars_update_levels(cp->ps, cp->d_vec, cp->pub.states, cp->pub.packedvector_count, sorted, count,
+                                  start + 1, nlevels, level))
+      {
+        pars_cuda_fail(cp);
+        return;
+      }
+      for (i = 0; i < count; ++i) scores[i] = level[pos[i]]; /* `level` received the scores in sorted order */
+    }
+    else
+      nlevels = 0;
+  }
+  if (!nlevels && !plf_pars_update(cp->ps, cp->d_vec, cp->pub.states, cp->pub.packedvector_count,
+                                   (const unsigned int *)ops, count, scores))
   {
     pars_cuda_fail(cp);
     return;

@@ -151,6 +151,40 @@ def test_partial_update_lists_and_recycled_vectors(reflib, cudalib):
         gpu.close()
 
 
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_level_scheduled_and_chained_updates_agree_with_the_reference(reflib, cudalib, monkeypatch, mode):
+    """PLF_PARS_LEVELS=2 forces one launch per level, =0 the one-launch chain.  Random operation lists over a
+    small pool of vectors: children that are rewritten later, parents that were read before, in-place updates -
+    every read-after-write, write-after-read and write-after-write order of the sequential list must hold."""
+    monkeypatch.setenv("PLF_PARS_LEVELS", mode)
+    ds = make_ds("dna", 12, 1999, seed=9)
+    ref, gpu = pars_pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    rng = np.random.default_rng(int(mode) + 1)
+    try:
+        pool = list(range(12, 24))  # twelve writable vectors on top of the twelve tips
+        init = [(v, v - 12, (v - 11) % 12) for v in pool]  # the reference's inner vectors start uninitialised
+        ref.update(init)
+        gpu.update(init)
+        for count in (1, 3, 8, 60, 400):
+            triples = []
+            for _ in range(count):
+                p_ = int(rng.choice(pool))
+                a, b = (int(x) for x in rng.integers(0, 24, size=2))
+                triples.append((p_, a, b))
+            ref.update(triples)
+            gpu.update(triples)
+            np.testing.assert_array_equal(gpu.costs(), ref.costs(), err_msg=f"count {count}")
+            for v in pool:
+                np.testing.assert_array_equal(gpu.vector(v), ref.vector(v), err_msg=f"vector {v} after {count} ops")
+        triples = tree_triples(ds)
+        ref.update(triples)
+        gpu.update(triples)
+        np.testing.assert_array_equal(gpu.costs(), ref.costs())
+    finally:
+        ref.close()
+        gpu.close()
+
+
 def test_simd_padded_reference_vectors_agree_on_the_common_prefix(reflib, cudalib):
     ds = make_ds("dna", 20, 1000, seed=8)
     ref, gpu = pars_pair(reflib, cudalib, ds, capi.PATTERN_TIP, ref_arch=capi.ARCH_AVX2)
