@@ -561,10 +561,33 @@ extern "C" int plf_pars_update_levels(plf_pars_t * ps, unsigned int * d_vec, uns
   PLF_CHECK(ctx, cudaMemsetAsync(d_scores, 0, count * sizeof(unsigned int), ctx->stream));
   const size_t stride = (size_t)states * words;
   const unsigned int full = (words + PARS_THREADS - 1) / PARS_THREADS;
+  /* Runs of narrow levels (one or two operations: the top of a tree) are not worth a launch each: a run goes
+   * to the chain kernel as one launch, in level order, which is a valid sequential order of its operations. */
+  unsigned int seg_start = 0, seg_len = 0;
+  auto flush_chain = [&]() {
+    if (!seg_len) return;
+    const unsigned int * o = d_ops + (size_t)3 * seg_start;
+    unsigned int * sc = d_scores + seg_start;
+    if (states == 4)
+      k_pars_update<4><<<full, PARS_THREADS, 0, ctx->stream>>>(d_vec, stride, states, words, o, seg_len, sc);
+    else if (states == 20)
+      k_pars_update<20><<<full, PARS_THREADS, 0, ctx->stream>>>(d_vec, stride, states, words, o, seg_len, sc);
+    else
+      k_pars_update<0><<<full, PARS_THREADS, 0, ctx->stream>>>(d_vec, stride, states, words, o, seg_len, sc);
+    plf_count_launch();
+    seg_len = 0;
+  };
   for (unsigned int l = 0; l < nlevels; ++l)
   {
     const unsigned int a = h_level_start[l], n = h_level_start[l + 1] - a;
     if (!n) continue;
+    if (n <= 2)
+    {
+      if (!seg_len) seg_start = a;
+      seg_len += n;
+      continue;
+    }
+    flush_chain();
     /* enough CTAs along x to fill the chip when the level is narrow, one sweep of the vector otherwise */
     unsigned int gx = full;
     const unsigned int want = (unsigned int)(ctx->sm_count * 8 + n - 1) / n;
@@ -584,6 +607,7 @@ extern "C" int plf_pars_update_levels(plf_pars_t * ps, unsigned int * d_vec, uns
       plf_count_launch();
     }
   }
+  flush_chain();
   PLF_CHECK(ctx, cudaGetLastError());
   PLF_CHECK(ctx, cudaMemcpyAsync(ps->h_pin + (size_t)3 * count, d_scores, count * sizeof(unsigned int),
                                  cudaMemcpyDeviceToHost, ctx->stream));

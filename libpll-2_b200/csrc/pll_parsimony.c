@@ -267,12 +267,25 @@ PLL_EXPORT void pll_fastparsimony_update_vectors(pll_parsimony_t * parsimony, co
     unsigned int * level = scores + count, * sorted = level + count, * pos = sorted + 3 * (size_t)count;
     unsigned int * start = pos + count, * lw = start + count + 2, * lr = lw + cp->nodes_count;
     nlevels = pars_levels(ops, count, level, lw, lr, cp->nodes_count);
-    /* A launch per level costs a few microseconds, an operation in the one-launch chain a little under one:
-     * levels pay when the list is several times longer than it is deep (wide trees) */
-    if ((unsigned long long)nlevels * 4 <= count || cp->force_levels)
+    unsigned int launches = 0, chained = 0, in_run = 0;
+    memset(start, 0, ((size_t)nlevels + 2) * sizeof(unsigned int));
+    for (i = 0; i < count; ++i) start[level[i]]++; /* level l (1-based) counted in start[l] */
+    /* what the level form costs: a launch per level of more than two operations and per run of narrower
+     * levels (those are chained inside one launch); a launch is worth about four chained operations */
+    for (i = 1; i <= nlevels; ++i)
+      if (start[i] > 2)
+      {
+        ++launches;
+        in_run = 0;
+      }
+      else
+      {
+        chained += start[i];
+        if (!in_run) ++launches;
+        in_run = 1;
+      }
+    if ((unsigned long long)launches * 4 + chained <= count || cp->force_levels)
     {
-      memset(start, 0, ((size_t)nlevels + 2) * sizeof(unsigned int));
-      for (i = 0; i < count; ++i) start[level[i]]++; /* level l (1-based) counted in start[l] */
       for (i = 1; i <= nlevels; ++i) start[i] += start[i - 1];
       /* start[l] is now the end of level l = the start of level l + 1: fill every level from its end */
       for (i = count; i-- > 0;)
