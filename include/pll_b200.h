@@ -786,8 +786,8 @@ PLL_EXPORT int pll_utree_rollback(pll_utree_rb_t * rollback, double * branch_len
  * CUDA engine: packedvector[i] holds DEVICE addresses (row k of node i starts at packedvector[i] +
  * k*packedvector_count; read one with pll_cuda_download_parsimony_vector); node_cost[], const_cost,
  * informative[] and the counts live on the host and are current whenever a call returns.  The weighted
- * (Sankoff) members are unused.  pll_fastparsimony_init reads the tip states from the partition's device
- * buffers; the parsimony object is independent of the partition afterwards. */
+ * (Sankoff) members belong to objects made by pll_parsimony_create (below).  pll_fastparsimony_init reads the tip
+ * states from the partition's device buffers; the parsimony object is independent of the partition afterwards. */
 typedef struct pll_parsimony_s
 {
   unsigned int tips;
