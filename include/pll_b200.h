@@ -878,6 +878,10 @@ PLL_EXPORT int pll_fastparsimony_stepwise_spr_round(pll_utree_t * tree, pll_pars
                                                     unsigned int pars_count, const unsigned int * tip_msa_idmap,
                                                     unsigned int seed, const int * clv_index_map,
                                                     unsigned int * cost);
+/* NEW (additive): the level schedule of pll_fastparsimony_update_vectors (1-based levels; operations of a
+ * level neither read nor write what another operation of the level writes); returns the level count, -1 on error */
+PLL_EXPORT int pll_cuda_schedule_parsimony_levels(const pll_pars_buildop_t * ops, unsigned int count,
+                                                  unsigned int vectors, unsigned int * level_of_op);
 /* NEW (additive): a batch of edge scores in one launch; pairs = n x {node1, node2} score indices */
 PLL_EXPORT int pll_cuda_fastparsimony_edge_scores(const pll_parsimony_t * parsimony, const unsigned int * pairs,
                                                   unsigned int n, unsigned int * scores);

@@ -271,6 +271,7 @@ _CUDA_PROTOS = {
     "pll_cuda_schedule_levels": (C.c_int, [C.POINTER(Operation), C.c_uint, c_uint_p]),
     "pll_cuda_kernel_launches": (C.c_ulonglong, []),
     "pll_cuda_fastparsimony_edge_scores": (C.c_int, [ParsimonyP, c_uint_p, C.c_uint, c_uint_p]),
+    "pll_cuda_schedule_parsimony_levels": (C.c_int, [C.POINTER(ParsBuildOp), C.c_uint, C.c_uint, c_uint_p]),
     "pll_cuda_download_parsimony_vector": (C.c_int, [ParsimonyP, C.c_uint, c_uint_p]),
     "pll_cuda_host_eigen": (
         C.c_int,

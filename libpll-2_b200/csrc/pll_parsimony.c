@@ -250,6 +250,32 @@ static unsigned int pars_levels(const pll_pars_buildop_t * ops, unsigned int cou
   return nlevels;
 }
 
+/* NEW (additive): the level schedule pll_fastparsimony_update_vectors uses, for inspection and tests.
+ * level_of_op[i] is 1-based; vectors = number of score indices in use (every index must be below it). */
+PLL_EXPORT int pll_cuda_schedule_parsimony_levels(const pll_pars_buildop_t * ops, unsigned int count,
+                                                  unsigned int vectors, unsigned int * level_of_op)
+{
+  unsigned int * lw, i;
+  int nlevels;
+  if (!count) return 0;
+  for (i = 0; i < count; ++i)
+    if (ops[i].parent_score_index >= vectors || ops[i].child1_score_index >= vectors ||
+        ops[i].child2_score_index >= vectors)
+    {
+      pars_error(PLL_ERROR_PARAM_INVALID, "Parsimony score index out of range.");
+      return -1;
+    }
+  lw = (unsigned int *)malloc((size_t)2 * vectors * sizeof(unsigned int));
+  if (!lw)
+  {
+    pars_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.");
+    return -1;
+  }
+  nlevels = (int)pars_levels(ops, count, level_of_op, lw, lw + vectors, vectors);
+  free(lw);
+  return nlevels;
+}
+
 PLL_EXPORT void pll_fastparsimony_update_vectors(pll_parsimony_t * parsimony, const pll_pars_buildop_t * ops,
                                                  unsigned int count)
 {

@@ -161,3 +161,38 @@ def test_gamma_category_rates_match_reference(lib, reflib, mode):
     out = (C.c_double * 4)()
     assert lib.lib.pll_compute_gamma_cats(0.001, 4, out, 0) == 0 and lib.errno == 113
     assert lib.lib.pll_compute_gamma_cats(1.0, 4, out, 7) == 0
+
+
+def test_parsimony_level_schedule_keeps_every_order_of_the_sequential_list():
+    """pll_cuda_schedule_parsimony_levels (host logic of pll_fastparsimony_update_vectors): for random lists over
+    a small pool of vectors every read-after-write, write-after-read and write-after-write pair is separated by
+    levels, and no operation sits higher than its conflicts demand."""
+    import ctypes as C
+    import importlib
+
+    import numpy as np
+
+    pkg = importlib.import_module("libpll-2_b200")
+    capi = pkg.capi
+    dll = C.CDLL(pkg.LIB_PATH)
+    f = dll.pll_cuda_schedule_parsimony_levels
+    f.restype, f.argtypes = C.c_int, [C.POINTER(capi.ParsBuildOp), C.c_uint, C.c_uint, capi.c_uint_p]
+    rng = np.random.default_rng(3)
+    for count, vectors in ((1, 3), (7, 5), (60, 12), (300, 40), (300, 400)):
+        trip = [(int(rng.integers(0, vectors)), int(rng.integers(0, vectors)), int(rng.integers(0, vectors)))
+                for _ in range(count)]
+        ops = (capi.ParsBuildOp * count)(*[capi.ParsBuildOp(*t) for t in trip])
+        level = np.zeros(count, dtype=np.uint32)
+        n = f(ops, count, vectors, level.ctypes.data_as(capi.c_uint_p))
+        assert n == level.max() and level.min() >= 1
+        for j, (pj, aj, bj) in enumerate(trip):
+            need = 1
+            for i in range(j):
+                pi, ai, bi = trip[i]
+                conflict = pi in (aj, bj) or pj in (ai, bi) or pi == pj  # RAW, WAR, WAW
+                if conflict:
+                    assert level[i] < level[j], (i, j, trip[i], trip[j])
+                    need = max(need, int(level[i]) + 1)
+            assert level[j] == need, (j, level[j], need)
+    bad = (capi.ParsBuildOp * 1)(capi.ParsBuildOp(9, 0, 1))
+    assert f(bad, 1, 3, np.zeros(1, dtype=np.uint32).ctypes.data_as(capi.c_uint_p)) == -1
