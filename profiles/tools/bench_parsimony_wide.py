@@ -1,3 +1,11 @@
+#!/usr/bin/env python
+"""Fitch parsimony on wide trees: one full-traversal pll_fastparsimony_update_vectors (wall time of the blocking
+call) and, with a third argument, the stepwise-addition tree.
+
+  python profiles/tools/bench_parsimony_wide.py TIPS SITES [s]
+  PLF_PARS_LEVELS=0 ...   always the one-launch chain kernel (the list is as deep as it is long)
+  default                 level-scheduled when the list is several times longer than deep (profiles/r1_notes.md)
+"""
 import sys, importlib, time, json, ctypes as C, os
 sys.path.insert(0,'/root/repo')
 import numpy as np
