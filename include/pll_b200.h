@@ -515,6 +515,24 @@ PLL_EXPORT int pll_cuda_upload_pmatrix(pll_partition_t * partition,
 PLL_EXPORT int pll_cuda_download_sumtable(const pll_partition_t * partition,
                                           const double * sumtable_handle,
                                           double * host_out);
+/* Virtual cherries (4 states, PLL_ATTRIB_PATTERN_TIP, 1/2/4 rate categories): the CLV
+ * of a node whose two children are pattern tips (src/partials.c:100-128 -> pll_core_update_partial_tt) is
+ * not written to HBM by pll_update_partials; the operation that consumes it forms the same values, to the
+ * bit, from the two tip codes.  Every entry point of this library that reads such a CLV by index
+ * (edge/root log-likelihood, sumtable, ancestral states, pll_cuda_download_clv, pll_show_clv) writes it
+ * first; a client that passes partition->clv[i] to its own kernels calls pll_cuda_materialize_clv(i).
+ * pll_cuda_virtual_cherries(): 1 when the partition works this way ($PLF_VIRTUAL_CHERRIES=0 turns it off,
+ * $PLF_VIRTUAL_CHERRY_MIN_SITES sets the narrowest alignment it applies to, default 4096 sites).
+ * pll_cuda_virtual_clvs(p, i): is node i virtual right now (i < nodes), or how many nodes are (i >= nodes). */
+PLL_EXPORT int pll_cuda_virtual_cherries(const pll_partition_t * partition);
+PLL_EXPORT unsigned int pll_cuda_virtual_clvs(const pll_partition_t * partition,
+                                              unsigned int clv_index);
+PLL_EXPORT int pll_cuda_materialize_clv(pll_partition_t * partition,
+                                        unsigned int clv_index);
+/* inspection: launches of one traversal level for ops of the given kinds (sorted by kind); a launch serves at
+ * most 65535 ops (gridDim.y).  Host arithmetic only. */
+PLL_EXPORT unsigned int pll_cuda_count_launch_runs(const unsigned int * kinds, unsigned int count,
+                                                   unsigned int * largest_run);
 /* number of elements of a scale buffer as currently allocated */
 PLL_EXPORT unsigned int pll_cuda_scaler_size(const pll_partition_t * partition,
                                              unsigned int scaler_index);

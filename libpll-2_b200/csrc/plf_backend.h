@@ -24,8 +24,21 @@ typedef struct plf_shape
 
 /* One CLV update as the device sees it (pointers already resolved).
  * kind: 0 inner-inner, 1 tip-inner (tip is always "left"), 2 tip-tip.
- * The *_id arrays are NULL unless site repeats compress the node. */
-enum { PLF_OP_II = 0, PLF_OP_TI = 1, PLF_OP_TT = 2 };
+ * The *_id arrays are NULL unless site repeats compress the node.
+ *
+ * Virtual cherries (4 states, contiguous CLVs): a tip-tip parent is not written to HBM; the op
+ * that consumes it forms the cherry's entry from the two tip codes.
+ *   3 CI  left = cherry, right = inner CLV
+ *   4 TC  left = pattern tip, right = cherry
+ *   5 CC  both children cherries
+ *   6 TT_VIRTUAL  the cherry itself: only its two P-matrices are snapshot into
+ *                 parent_clv[0 .. 2*R*16) -- a side buffer, not the CLV -- and its scaler is zeroed
+ * For a cherry child: {left,right}_tip / _tip2 are the codes of its two tips, {left,right}_cm1 / _cm2
+ * the snapshots of its two P-matrices, {left,right}_matrix the matrix of the branch above it. */
+enum { PLF_OP_II = 0, PLF_OP_TI = 1, PLF_OP_TT = 2, PLF_OP_CI = 3, PLF_OP_TC = 4, PLF_OP_CC = 5,
+       PLF_OP_TT_VIRTUAL = 6, PLF_OP_KINDS = 7 };
+/* most ops of one kernel launch (blockIdx.y selects the op) */
+#define PLF_MAX_RUN_OPS 65535u
 typedef struct plf_op
 {
   double * parent_clv;
@@ -41,6 +54,12 @@ typedef struct plf_op
   const unsigned int * parent_id_site;
   const unsigned int * left_site_id;
   const unsigned int * right_site_id;
+  const unsigned char * left_tip2;
+  const unsigned char * right_tip2;
+  const double * left_cm1;
+  const double * left_cm2;
+  const double * right_cm1;
+  const double * right_cm2;
   unsigned int nsites;
   unsigned int kind;
 } plf_op_t;
@@ -140,6 +159,17 @@ int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh,
                         unsigned int nlevels,
                         const unsigned long long * d_tipmap,
                         unsigned int maxstates);
+
+/* the same without touching the one-graph-per-traversal cache (internal single ops) */
+int plf_update_partials_once(plf_ctx_t * ctx, const plf_shape_t * sh,
+                             const plf_op_t * h_ops, unsigned int nops,
+                             const unsigned long long * d_tipmap,
+                             unsigned int maxstates);
+/* end of the launch run that starts at op i of a level ending at b (see plf_partials.cu) */
+unsigned int plf_run_end(const plf_op_t * h_ops, unsigned int i, unsigned int b,
+                         unsigned int * max_sites, int * contiguous);
+/* 1 when the 4-state streaming kernels that consume virtual cherries serve this shape */
+int plf_virtual_cherries_supported(plf_ctx_t * ctx, const plf_shape_t * sh);
 
 /* results: d_out (device, may be NULL) and/or h_out (host, may be NULL; when
  * given the call synchronises the stream) */

@@ -129,6 +129,7 @@ extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
   cudaStreamSynchronize(ctx->stream);
   plf_graph_cache_destroy(ctx);
   cudaFree(ctx->ws_ops.ptr);
+  cudaFree(ctx->ws_once.ptr);
   cudaFree(ctx->ws_small.ptr);
   cudaFree(ctx->ws_partial.ptr);
   cudaFree(ctx->d_result);

@@ -389,13 +389,13 @@ k_deriv_dna(plf_deriv_t a, double * __restrict__ partial, unsigned int * ticket,
 
 /* ------------------------------------------------------------------------ *
  *  sumtable as a CLV update: build the synthetic operation on the device      *
- *  ws = [plf_op_t (128 B)] [left R x 16] [right R x 16]                       *
+ *  ws = [plf_op_t (256 B)] [left R x 16] [right R x 16]                       *
  *  left[r][j][k] = pi_k Vinv[k][j] ("parent" side), right[r][j][k] = V[j][k]   *
  * ------------------------------------------------------------------------ */
 __global__ void k_sumtable_op(plf_sumtable_t a, int R, int st, int sp, unsigned char * ws, unsigned int ntiles)
 {
   plf_op_t * op = reinterpret_cast<plf_op_t *>(ws);
-  double * lm = reinterpret_cast<double *>(ws + 128);
+  double * lm = reinterpret_cast<double *>(ws + 256);
   double * rm = lm + R * st * sp;
   const double * freqs = a.model + 3 * R;
   const double * evecs = freqs + 2 * R * sp;
@@ -409,6 +409,7 @@ __global__ void k_sumtable_op(plf_sumtable_t a, int R, int st, int sp, unsigned 
   if (threadIdx.x == 0)
   {
     plf_op_t o;
+    memset(&o, 0, sizeof(o));
     o.parent_clv = a.sumtable;
     o.left_clv = a.clvp;
     o.right_clv = a.clvc;
@@ -425,7 +426,7 @@ __global__ void k_sumtable_op(plf_sumtable_t a, int R, int st, int sp, unsigned 
     o.kind = a.tipchars ? PLF_OP_TI : PLF_OP_II;
     *op = o;
     /* tile list of this one op for the tile-walk gather kernel (last 8 bytes of the descriptor's slot) */
-    unsigned int * prefix = reinterpret_cast<unsigned int *>(ws + 120);
+    unsigned int * prefix = reinterpret_cast<unsigned int *>(ws + 248);
     prefix[0] = 0;
     prefix[1] = ntiles;
   }
@@ -437,9 +438,9 @@ int plf_sumtable_as_clv(plf_ctx * ctx, const plf_shape_t * sh, const plf_sumtabl
 {
   const int R = (int)sh->rate_cats, st = (int)sh->states, sp = (int)sh->states_padded;
   unsigned char * ws =
-      (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_edge, 128 + (size_t)2 * R * st * sp * sizeof(double));
+      (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_edge, 256 + (size_t)2 * R * st * sp * sizeof(double));
   if (!ws) return 0;
-  static_assert(sizeof(plf_op_t) <= 120, "op descriptor and its two-entry tile list must fit the 128-byte slot");
+  static_assert(sizeof(plf_op_t) <= 248, "op descriptor and its two-entry tile list must fit the 256-byte slot");
   const int contiguous = !(a->p_site_id || a->c_site_id);
   const unsigned int kind = a->tipchars ? PLF_OP_TI : PLF_OP_II;
   const int pow2 = sh->rate_cats && !(sh->rate_cats & (sh->rate_cats - 1)) && sh->rate_cats <= 32;
@@ -450,7 +451,7 @@ int plf_sumtable_as_clv(plf_ctx * ctx, const plf_shape_t * sh, const plf_sumtabl
   PLF_CHECK(ctx, cudaGetLastError());
   if (st == 4)
     return plf_launch_dna_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
-                                contiguous, ntiles ? reinterpret_cast<const unsigned int *>(ws + 120) : nullptr, ntiles);
+                                contiguous, ntiles ? reinterpret_cast<const unsigned int *>(ws + 248) : nullptr, ntiles);
   return plf_launch_aa_mma_group(ctx, reinterpret_cast<const plf_op_t *>(ws), 1, kind, sh->rate_cats, 0, a->sites,
                                  d_tipmap, maxstates, contiguous);
 }

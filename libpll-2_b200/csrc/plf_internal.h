@@ -21,6 +21,9 @@ struct plf_ctx
   size_t lk20_smem_set;
   int dna_occupancy[3][6]; /* resident CTAs per SM of the DNA CLV kernels [kind][log2 rates] */
   int dna_stream_occupancy[2][6];
+  int dna_cherry_occupancy[3][3]; /* consumers of virtual cherries [CI, TC, CC][log2 rates] */
+  int dna_cherry_items;           /* PLF_CHERRY_ITEMS: 2 (default) or 4 (site, rate) blocks per thread and tile */
+  int dna_cherry;                 /* PLF_VIRTUAL_CHERRIES=0 writes every tip-tip parent to HBM */
   int dna_tt_bulk_occupancy[4];
   int dna_balanced_occupancy[6];
   int dna_stream;          /* -1 = read PLF_DNA_STREAM / PLF_DNA_STAGES on first use */
@@ -44,6 +47,7 @@ struct plf_ctx
   cudaStream_t stream;
   cudaMemPool_t pool;    /* stream-ordered allocator behind plf_alloc/plf_free (NULL in managed mode) */
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
+  plf_ws ws_once;     /* op descriptors of internal single ops (materialised cherries) */
   plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
   plf_ws ws_partial;  /* per-block partial sums of the reductions              */
   plf_ws ws_edge;     /* synthetic op + matrices of the DNA/AA sumtable launches */

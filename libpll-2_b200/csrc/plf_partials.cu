@@ -419,19 +419,36 @@ k_partials_gen(const plf_op_t * __restrict__ ops, int R, int per_rate, int st_rt
 
 /* ------------------------------------------------------------------------ */
 
+/* one kernel launch serves a run of same-kind ops of a level, the op selected by blockIdx.y: a run ends at
+ * the first op of another kind, at the end of the level `b`, or after PLF_MAX_RUN_OPS ops (gridDim.y limit) */
+extern "C" unsigned int plf_run_end(const plf_op_t * h_ops, unsigned int i, unsigned int b,
+                                    unsigned int * max_sites, int * contiguous)
+{
+  unsigned int j = i;
+  while (j < b && h_ops[j].kind == h_ops[i].kind && j - i < PLF_MAX_RUN_OPS)
+  {
+    if (max_sites && h_ops[j].nsites > *max_sites) *max_sites = h_ops[j].nsites;
+    if (contiguous && (h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id)) *contiguous = 0;
+    ++j;
+  }
+  return j;
+}
+
 static int is_pow2(unsigned int x) { return x && !(x & (x - 1)); }
 
 /* queues the launches of a level-sorted op list.  `upload` = 0: the op descriptors and tile-prefix arrays
  * are already in the workspace (identical call being captured into a CUDA graph): no host-to-device copy */
 static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops, unsigned int nops,
                           const unsigned int * h_level_start, unsigned int nlevels,
-                          const unsigned long long * d_tipmap, unsigned int maxstates, int upload)
+                          const unsigned long long * d_tipmap, unsigned int maxstates, int upload,
+                          plf_ws * ws = nullptr)
 {
+  if (!ws) ws = &ctx->ws_ops;
   /* workspace: the op descriptors, then one tile-prefix array per (level, kind) run of gathering
    * 4-state inner-inner ops (site repeats; see k_clv_dna_ii_balanced) */
-  const size_t prefix_entries = (size_t)nops + 3 * (size_t)nlevels + 1;
+  const size_t prefix_entries = 2 * (size_t)nops + 1; /* one array of (ops + 1) entries per run; runs <= ops */
   const size_t ops_bytes = (size_t)nops * sizeof(plf_op_t);
-  plf_op_t * d_ops = (plf_op_t *)plf_ws_reserve(ctx, &ctx->ws_ops, ops_bytes + prefix_entries * sizeof(unsigned int));
+  plf_op_t * d_ops = (plf_op_t *)plf_ws_reserve(ctx, ws, ops_bytes + prefix_entries * sizeof(unsigned int));
   if (!d_ops) return 0;
   unsigned int * d_prefix = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(d_ops) + ops_bytes);
   if (upload) PLF_CHECK(ctx, cudaMemcpyAsync(d_ops, h_ops, ops_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -459,14 +476,9 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
        * run of same-kind ops; the host layer sorts a level by kind */
       for (unsigned int i = a; i < b;)
       {
-        unsigned int j = i, run_sites = 0;
+        unsigned int run_sites = 0;
         int contiguous = 1;
-        while (j < b && h_ops[j].kind == h_ops[i].kind)
-        {
-          if (h_ops[j].nsites > run_sites) run_sites = h_ops[j].nsites;
-          if (h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id) contiguous = 0;
-          ++j;
-        }
+        const unsigned int j = plf_run_end(h_ops, i, b, &run_sites, &contiguous);
         const unsigned int * d_run_prefix = nullptr;
         unsigned int total_tiles = 0;
         if (!contiguous && h_ops[i].kind == PLF_OP_II) /* single ops too: the tile-walk kernel is the faster gather */
@@ -500,13 +512,22 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
     if (sh->states == 4)
     {
       const int threads = 256;
-      unsigned int bx = (unsigned int)(((unsigned long long)max_sites + threads - 1) / threads);
-      unsigned int cap = (unsigned int)(ctx->sm_count * 2 * 4) / (b - a);
-      if (cap < 1) cap = 1;
-      if (bx > cap) bx = cap;
-      dim3 grid(bx, b - a);
-      const size_t smem = any_tip ? (size_t)2 * 64 * R * sizeof(double) : 0;
-      k_partials_dna<0><<<grid, threads, smem, ctx->stream>>>(d_ops + a, R, sh->per_rate_scalers);
+      for (unsigned int c0 = a; c0 < b; c0 += PLF_MAX_RUN_OPS)
+      {
+        const unsigned int nrun = (b - c0 < PLF_MAX_RUN_OPS) ? b - c0 : PLF_MAX_RUN_OPS;
+        unsigned int bx = (unsigned int)(((unsigned long long)max_sites + threads - 1) / threads);
+        unsigned int cap = (unsigned int)(ctx->sm_count * 2 * 4) / nrun;
+        if (cap < 1) cap = 1;
+        if (bx > cap) bx = cap;
+        dim3 grid(bx, nrun);
+        const size_t smem = any_tip ? (size_t)2 * 64 * R * sizeof(double) : 0;
+        k_partials_dna<0><<<grid, threads, smem, ctx->stream>>>(d_ops + c0, R, sh->per_rate_scalers);
+        if (c0 + PLF_MAX_RUN_OPS < b) /* the last chunk is counted and checked below */
+        {
+          plf_count_launch();
+          PLF_CHECK(ctx, cudaGetLastError());
+        }
+      }
     }
     else
     {
@@ -514,15 +535,10 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
        * kernels of plf_partials_aa.cu, everything else to the generic kernel */
       for (unsigned int i = a; i < b;)
       {
-        unsigned int j = i, run_sites = 0;
+        unsigned int run_sites = 0;
         int run_tip = (h_ops[i].kind != PLF_OP_II);
         int contiguous = 1;
-        while (j < b && h_ops[j].kind == h_ops[i].kind)
-        {
-          if (h_ops[j].nsites > run_sites) run_sites = h_ops[j].nsites;
-          if (h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id) contiguous = 0;
-          ++j;
-        }
+        const unsigned int j = plf_run_end(h_ops, i, b, &run_sites, &contiguous);
         int done = 0;
         if (run_sites && sh->states == 20 && ctx->aa_fast)
         {
@@ -605,6 +621,17 @@ void plf_graph_cache_destroy(plf_ctx * ctx)
   free(ctx->graph_levels);
   ctx->graph_ops = nullptr;
   ctx->graph_levels = nullptr;
+}
+
+extern "C" int plf_update_partials_once(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops,
+                                        unsigned int nops, const unsigned long long * d_tipmap,
+                                        unsigned int maxstates)
+{
+  if (!nops) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  /* its own descriptor workspace: the cached graph of the last traversal keeps reading ws_ops */
+  const unsigned int level_start[2] = {0, nops};
+  return enqueue_levels(ctx, sh, h_ops, nops, level_start, 1, d_tipmap, maxstates, 1, &ctx->ws_once);
 }
 
 extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops,

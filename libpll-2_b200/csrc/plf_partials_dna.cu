@@ -616,60 +616,117 @@ k_clv_dna_tt_bulk(const plf_op_t * __restrict__ ops, int per_rate_and_nops)
  *  the copy engine keeps issuing while every warp is busy with arithmetic.   *
  * ------------------------------------------------------------------------ */
 
+/* what a child of a streamed op is: an inner CLV (tile copied into the ring, 4x4 mat-vec with the matrix
+ * held in registers), a pattern tip (code copied into the ring, 16-entry lookup table in shared memory) or a
+ * virtual cherry (the codes of its two tips copied into the ring, 256-entry lookup table in shared memory) */
+enum { CK_I = 0, CK_T = 1, CK_C = 2 };
+
 /* ITEMS = (site, rate) blocks per thread and tile */
-template <int LOG2R, int ITEMS>
+template <int LOG2R, int LK, int RK, int ITEMS>
 struct StreamLayout
 {
   static constexpr int R = 1 << LOG2R;
   static constexpr int TILE = (DNA_THREADS * ITEMS) >> LOG2R; /* sites per tile */
   static constexpr int CLV_BYTES = TILE * R * 32;
   static constexpr int SC_BYTES = TILE * R * 4; /* per-rate worst case */
+  static constexpr int CODE_BYTES = (TILE + 15) & ~15;
+  static constexpr int side_bytes(int k) { return k == CK_I ? CLV_BYTES + SC_BYTES : k == CK_T ? CODE_BYTES : 2 * CODE_BYTES; }
+  /* left side: CLV tile then scalers, or one / two code arrays; the right side follows */
   static constexpr int OFF_L = 0;
-  static constexpr int OFF_R = CLV_BYTES;
-  static constexpr int OFF_LSC = 2 * CLV_BYTES;
-  static constexpr int OFF_RSC = OFF_LSC + SC_BYTES;
-  static constexpr int OFF_CODE = OFF_RSC + SC_BYTES;
-  static constexpr int STAGE_BYTES = (OFF_CODE + TILE + 127) & ~127;
+  static constexpr int OFF_LSC = CLV_BYTES;
+  static constexpr int OFF_LCODE = 0;
+  static constexpr int OFF_LCODE2 = CODE_BYTES;
+  static constexpr int OFF_R = side_bytes(LK);
+  static constexpr int OFF_RSC = OFF_R + CLV_BYTES;
+  static constexpr int OFF_RCODE = OFF_R;
+  static constexpr int OFF_RCODE2 = OFF_R + CODE_BYTES;
+  static constexpr int STAGE_BYTES = (side_bytes(LK) + side_bytes(RK) + 127) & ~127;
+  /* lookup tables behind the ring: doubles */
+  static constexpr int table_doubles(int k) { return k == CK_T ? 64 * R : k == CK_C ? 1024 * R : 0; }
+  static constexpr int TAB_L = 0;
+  static constexpr int TAB_R = table_doubles(LK);
+  static constexpr int TAB_SCRATCH = TAB_R + table_doubles(RK); /* the two half tables a cherry table is built from */
+  static constexpr int TAB_DOUBLES = TAB_SCRATCH + ((LK == CK_C || RK == CK_C) ? 128 * R : 0);
+  static constexpr size_t smem_bytes(int nstage) { return (size_t)nstage * STAGE_BYTES + (size_t)TAB_DOUBLES * 8; }
 };
 
 /* thread 0: queue the copies of tile `t` of `op` into ring slot `slot` */
-template <int LOG2R, int KIND, int ITEMS>
+template <int LOG2R, int LK, int RK, int ITEMS>
 __device__ __forceinline__ void stream_issue(const plf_op_t & op, unsigned int t, unsigned char * slot,
                                              unsigned long long * bar, int per_rate)
 {
-  typedef StreamLayout<LOG2R, ITEMS> Ly;
+  typedef StreamLayout<LOG2R, LK, RK, ITEMS> Ly;
   const unsigned int first = t * Ly::TILE;
   const unsigned int n = min((unsigned int)Ly::TILE, op.nsites - first);
   const unsigned int clv_bytes = n * Ly::R * 32;
   /* 4-byte scalers / 1-byte codes: sizes rounded up to the 16-byte copy
    * granule; the host layer pads those allocations by 16 bytes */
   const unsigned int sc_bytes = ((per_rate ? n * Ly::R : n) * 4 + 15) & ~15u;
+  const unsigned int code_bytes = (n + 15) & ~15u;
   const size_t sc_first = per_rate ? (size_t)first * Ly::R : first;
-  unsigned int total = clv_bytes;
-  if (KIND == PLF_OP_II) total += clv_bytes + (op.left_scaler && op.parent_scaler ? sc_bytes : 0);
-  if (KIND == PLF_OP_TI) total += (n + 15) & ~15u;
-  if (op.right_scaler && op.parent_scaler) total += sc_bytes;
+  const bool lsc = LK == CK_I && op.left_scaler && op.parent_scaler;
+  const bool rsc = RK == CK_I && op.right_scaler && op.parent_scaler;
+  unsigned int total = 0;
+  total += LK == CK_I ? clv_bytes + (lsc ? sc_bytes : 0) : LK == CK_T ? code_bytes : 2 * code_bytes;
+  total += RK == CK_I ? clv_bytes + (rsc ? sc_bytes : 0) : RK == CK_T ? code_bytes : 2 * code_bytes;
   mbar_expect_tx(bar, total);
-  if (KIND == PLF_OP_II)
+  if (LK == CK_I)
   {
     bulk_g2s(slot + Ly::OFF_L, op.left_clv + (size_t)first * Ly::R * 4, clv_bytes, bar);
-    if (op.left_scaler && op.parent_scaler) bulk_g2s(slot + Ly::OFF_LSC, op.left_scaler + sc_first, sc_bytes, bar);
+    if (lsc) bulk_g2s(slot + Ly::OFF_LSC, op.left_scaler + sc_first, sc_bytes, bar);
   }
   else
-    bulk_g2s(slot + Ly::OFF_CODE, op.left_tip + first, (n + 15) & ~15u, bar);
-  bulk_g2s(slot + Ly::OFF_R, op.right_clv + (size_t)first * Ly::R * 4, clv_bytes, bar);
-  if (op.right_scaler && op.parent_scaler) bulk_g2s(slot + Ly::OFF_RSC, op.right_scaler + sc_first, sc_bytes, bar);
+  {
+    bulk_g2s(slot + Ly::OFF_LCODE, op.left_tip + first, code_bytes, bar);
+    if (LK == CK_C) bulk_g2s(slot + Ly::OFF_LCODE2, op.left_tip2 + first, code_bytes, bar);
+  }
+  if (RK == CK_I)
+  {
+    bulk_g2s(slot + Ly::OFF_R, op.right_clv + (size_t)first * Ly::R * 4, clv_bytes, bar);
+    if (rsc) bulk_g2s(slot + Ly::OFF_RSC, op.right_scaler + sc_first, sc_bytes, bar);
+  }
+  else
+  {
+    bulk_g2s(slot + Ly::OFF_RCODE, op.right_tip + first, code_bytes, bar);
+    if (RK == CK_C) bulk_g2s(slot + Ly::OFF_RCODE2, op.right_tip2 + first, code_bytes, bar);
+  }
 }
 
-template <int LOG2R, int KIND, int NSTAGE, int ITEMS>
+/* lookup table of a virtual cherry seen through the branch above it:
+ *   tab[(codeA << 4 | codeB)][rate][i] = row i of `outer` (pairwise dot, as an inner child is treated,
+ *   src/core_partials_avx.c:456-524) times the cherry's CLV entry, which is termA[k] * termB[k] with the
+ *   masked pairwise sums of the two tip matrices (the reference's tip-tip table, :295-396,1012-1028).
+ * The same operations in the same order as writing the cherry and reading it back: the same bits. */
+template <int LOG2R>
+__device__ __forceinline__ void build_cherry_table(double * tab, double * scratch, const double * __restrict__ outer,
+                                                   const double * __restrict__ cm1, const double * __restrict__ cm2)
+{
+  constexpr int R = 1 << LOG2R;
+  __syncthreads(); /* the scratch may still be read by the previous table's build */
+  build_tip_table(scratch, cm1, R);
+  build_tip_table(scratch + 64 * R, cm2, R);
+  __syncthreads();
+  for (int e = threadIdx.x; e < 1024 * R; e += blockDim.x)
+  {
+    const int i = e & 3, rate = (e >> 2) & (R - 1), cb = (e >> (2 + LOG2R)) & 15, ca = e >> (6 + LOG2R);
+    const double * a = scratch + (ca * R + rate) * 4;
+    const double * b = scratch + 64 * R + (cb * R + rate) * 4;
+    const dbl4 l = dbl4{a[0] * b[0], a[1] * b[1], a[2] * b[2], a[3] * b[3]};
+    tab[e] = dot4_pairwise(outer + rate * 16 + i * 4, l);
+  }
+}
+
+template <int LOG2R, int LK, int RK, int NSTAGE, int ITEMS>
 __global__ void __launch_bounds__(DNA_THREADS)
 k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
 {
-  typedef StreamLayout<LOG2R, ITEMS> Ly;
+  typedef StreamLayout<LOG2R, LK, RK, ITEMS> Ly;
   constexpr int R = Ly::R;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) unsigned long long full[NSTAGE];
-  __shared__ __align__(16) double tl[KIND == PLF_OP_TI ? 64 * R : 2];
+  double * tables = reinterpret_cast<double *>(ring + (size_t)NSTAGE * Ly::STAGE_BYTES);
+  double * tabL = tables + Ly::TAB_L;
+  double * tabR = tables + Ly::TAB_R;
 
   const plf_op_t op = ops[blockIdx.y];
   const unsigned int ntiles = (op.nsites + Ly::TILE - 1) / Ly::TILE;
@@ -685,21 +742,20 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
   {
     unsigned int t = blockIdx.x;
     for (int s = 0; s < NSTAGE && t < ntiles; ++s, t += gridDim.x)
-      stream_issue<LOG2R, KIND, ITEMS>(op, t, ring + (size_t)s * Ly::STAGE_BYTES, &full[s], per_rate);
+      stream_issue<LOG2R, LK, RK, ITEMS>(op, t, ring + (size_t)s * Ly::STAGE_BYTES, &full[s], per_rate);
   }
 
-  double Lm[KIND == PLF_OP_II ? 16 : 1], Rm[16];
+  double Lm[LK == CK_I ? 16 : 1], Rm[RK == CK_I ? 16 : 1];
 #pragma unroll
   for (int i = 0; i < 16; ++i)
   {
-    if (KIND == PLF_OP_II) Lm[i] = op.left_matrix[rate * 16 + i];
-    Rm[i] = op.right_matrix[rate * 16 + i];
+    if (LK == CK_I) Lm[i] = op.left_matrix[rate * 16 + i];
+    if (RK == CK_I) Rm[i] = op.right_matrix[rate * 16 + i];
   }
-  if (KIND == PLF_OP_TI)
-  {
-    build_tip_table(tl, op.left_matrix, R);
-    __syncthreads();
-  }
+  if (LK == CK_T) build_tip_table(tabL, op.left_matrix, R);
+  if (LK == CK_C) build_cherry_table<LOG2R>(tabL, tables + Ly::TAB_SCRATCH, op.left_matrix, op.left_cm1, op.left_cm2);
+  if (RK == CK_C) build_cherry_table<LOG2R>(tabR, tables + Ly::TAB_SCRATCH, op.right_matrix, op.right_cm1, op.right_cm2);
+  if (LK != CK_I || RK != CK_I) __syncthreads();
 
   unsigned int it = 0;
   for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it)
@@ -719,10 +775,9 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
       sr.n = first + ls;
       sr.lid = sr.rid = sr.n;
       sr.active = sr.n < op.nsites;
-      const dbl4 r = lds_dbl4(reinterpret_cast<const double *>(slot + Ly::OFF_R) + (size_t)item * 4);
-      dbl4 a;
+      dbl4 a, b;
       unsigned int sc = 0;
-      if (KIND == PLF_OP_II)
+      if (LK == CK_I)
       {
         const dbl4 l = lds_dbl4(reinterpret_cast<const double *>(slot + Ly::OFF_L) + (size_t)item * 4);
         a.x = dot4_pairwise(Lm + 0, l);
@@ -730,29 +785,69 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
         a.z = dot4_pairwise(Lm + 8, l);
         a.w = dot4_pairwise(Lm + 12, l);
       }
+      else if (LK == CK_T)
+      {
+        const unsigned int code = sr.active ? slot[Ly::OFF_LCODE + ls] : 0u;
+        a = lds_dbl4(tabL + (code * R + rate) * 4);
+      }
       else
       {
-        const unsigned int code = sr.active ? slot[Ly::OFF_CODE + ls] : 0u;
-        a = lds_dbl4(tl + (code * R + rate) * 4);
+        const unsigned int code = sr.active ? (((slot[Ly::OFF_LCODE + ls] & 15u) << 4) | (slot[Ly::OFF_LCODE2 + ls] & 15u)) : 0u;
+        a = lds_dbl4(tabL + (code * R + rate) * 4);
+      }
+      if (RK == CK_I)
+      {
+        const dbl4 r = lds_dbl4(reinterpret_cast<const double *>(slot + Ly::OFF_R) + (size_t)item * 4);
+        b.x = dot4_pairwise(Rm + 0, r);
+        b.y = dot4_pairwise(Rm + 4, r);
+        b.z = dot4_pairwise(Rm + 8, r);
+        b.w = dot4_pairwise(Rm + 12, r);
+      }
+      else
+      {
+        const unsigned int code = sr.active ? (((slot[Ly::OFF_RCODE + ls] & 15u) << 4) | (slot[Ly::OFF_RCODE2 + ls] & 15u)) : 0u;
+        b = lds_dbl4(tabR + (code * R + rate) * 4);
       }
       if (op.parent_scaler && sr.active && (per_rate || rate == 0))
       {
         const unsigned int k = per_rate ? item : ls;
-        if (KIND == PLF_OP_II && op.left_scaler) sc += reinterpret_cast<const unsigned int *>(slot + Ly::OFF_LSC)[k];
-        if (op.right_scaler) sc += reinterpret_cast<const unsigned int *>(slot + Ly::OFF_RSC)[k];
+        if (LK == CK_I && op.left_scaler) sc += reinterpret_cast<const unsigned int *>(slot + Ly::OFF_LSC)[k];
+        if (RK == CK_I && op.right_scaler) sc += reinterpret_cast<const unsigned int *>(slot + Ly::OFF_RSC)[k];
       }
       dbl4 v;
-      v.x = a.x * dot4_pairwise(Rm + 0, r);
-      v.y = a.y * dot4_pairwise(Rm + 4, r);
-      v.z = a.z * dot4_pairwise(Rm + 8, r);
-      v.w = a.w * dot4_pairwise(Rm + 12, r);
+      v.x = a.x * b.x;
+      v.y = a.y * b.y;
+      v.z = a.z * b.z;
+      v.w = a.w * b.w;
       if (!sr.active) v = dbl4{1.0, 1.0, 1.0, 1.0}; /* stale ring bytes must not reach the scaling vote */
       scale_and_store<LOG2R>(op, sr, rate, per_rate, sc, v);
     }
     __syncthreads(); /* every warp is done with this slot */
     const unsigned int tn = t + (unsigned int)NSTAGE * gridDim.x;
-    if (threadIdx.x == 0 && tn < ntiles) stream_issue<LOG2R, KIND, ITEMS>(op, tn, slot, &full[s], per_rate);
+    if (threadIdx.x == 0 && tn < ntiles) stream_issue<LOG2R, LK, RK, ITEMS>(op, tn, slot, &full[s], per_rate);
   }
+}
+
+/* A virtual cherry's own "operation": its CLV is never written.  The two P-matrices it was asked to be
+ * computed with are copied into the node's side buffer (consumers and a later materialisation read them
+ * there, so a P-matrix update in between changes nothing), and its scaler is zeroed as the reference's
+ * tip-tip kernel does (src/core_partials_avx.c:1005-1006). */
+__global__ void __launch_bounds__(256)
+k_cherry_prepare(const plf_op_t * __restrict__ ops, int per_rate, int R)
+{
+  const plf_op_t op = ops[blockIdx.y];
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < R * 16; i += blockDim.x)
+    {
+      op.parent_clv[i] = op.left_matrix[i];
+      op.parent_clv[R * 16 + i] = op.right_matrix[i];
+    }
+  if (!op.parent_scaler) return;
+  const size_t n = per_rate ? (size_t)op.nsites * R : op.nsites;
+  const size_t quads = (n + 3) >> 2; /* the allocation is padded by 16 bytes */
+  uint4 * dst = reinterpret_cast<uint4 *>(op.parent_scaler);
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (size_t)gridDim.x * blockDim.x)
+    dst[q] = make_uint4(0, 0, 0, 0);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -772,15 +867,16 @@ static const int DNA_UNROLL = 4;
 template <int LOG2R, int NSTAGE, int ITEMS>
 static dna_kernel_t pick_stream_kernel(unsigned int kind)
 {
-  if (kind == PLF_OP_II) return k_clv_dna_stream<LOG2R, PLF_OP_II, NSTAGE, ITEMS>;
-  return k_clv_dna_stream<LOG2R, PLF_OP_TI, NSTAGE, ITEMS>;
+  if (kind == PLF_OP_II) return k_clv_dna_stream<LOG2R, CK_I, CK_I, NSTAGE, ITEMS>;
+  return k_clv_dna_stream<LOG2R, CK_T, CK_I, NSTAGE, ITEMS>;
 }
 
 template <int LOG2R, int ITEMS>
 static dna_kernel_t pick_stream_kernel_stages(unsigned int kind, int nstage, size_t * smem, unsigned int * tile)
 {
-  *smem = (size_t)nstage * StreamLayout<LOG2R, ITEMS>::STAGE_BYTES;
-  *tile = StreamLayout<LOG2R, ITEMS>::TILE;
+  *smem = kind == PLF_OP_II ? StreamLayout<LOG2R, CK_I, CK_I, ITEMS>::smem_bytes(nstage)
+                            : StreamLayout<LOG2R, CK_T, CK_I, ITEMS>::smem_bytes(nstage);
+  *tile = StreamLayout<LOG2R, CK_I, CK_I, ITEMS>::TILE;
   switch (nstage)
   {
     case 2: return pick_stream_kernel<LOG2R, 2, ITEMS>(kind);
@@ -798,10 +894,49 @@ static dna_kernel_t pick_stream_kernel_items(unsigned int kind, int nstage, int 
   return pick_stream_kernel_stages<LOG2R, 4>(kind, nstage, smem, tile);
 }
 
+/* consumers of virtual cherries (rate_cats <= 4): ring of CHERRY_STAGES stages, `items` 2 or 4 */
+#define CHERRY_STAGES 6
+template <int LOG2R, int LK, int RK>
+static dna_kernel_t pick_cherry_items(int items, size_t * smem, unsigned int * tile)
+{
+  if (items == 4)
+  {
+    *smem = StreamLayout<LOG2R, LK, RK, 4>::smem_bytes(CHERRY_STAGES);
+    *tile = StreamLayout<LOG2R, LK, RK, 4>::TILE;
+    return k_clv_dna_stream<LOG2R, LK, RK, CHERRY_STAGES, 4>;
+  }
+  *smem = StreamLayout<LOG2R, LK, RK, 2>::smem_bytes(CHERRY_STAGES);
+  *tile = StreamLayout<LOG2R, LK, RK, 2>::TILE;
+  return k_clv_dna_stream<LOG2R, LK, RK, CHERRY_STAGES, 2>;
+}
+
+template <int LOG2R>
+static dna_kernel_t pick_cherry_kernel(unsigned int kind, int items, size_t * smem, unsigned int * tile)
+{
+  if (kind == PLF_OP_CI) return pick_cherry_items<LOG2R, CK_C, CK_I>(items, smem, tile);
+  if (kind == PLF_OP_TC) return pick_cherry_items<LOG2R, CK_T, CK_C>(items, smem, tile);
+  return pick_cherry_items<LOG2R, CK_C, CK_C>(items, smem, tile);
+}
+
 static int env_int(const char * name, int dflt)
 {
   const char * v = getenv(name);
   return (v && v[0]) ? atoi(v) : dflt;
+}
+
+/* the A/B switches of the 4-state kernels, read from the environment on first use */
+static void dna_read_switches(plf_ctx * ctx)
+{
+  if (ctx->dna_stream >= 0) return;
+  ctx->dna_stream = env_int("PLF_DNA_STREAM", 1);
+  ctx->dna_stages = env_int("PLF_DNA_STAGES", 6);
+  ctx->dna_items = env_int("PLF_DNA_ITEMS", 2);
+  ctx->dna_tt_bulk = env_int("PLF_TT_BULK", 1);
+  ctx->dna_tt_items = env_int("PLF_TT_ITEMS", 2) == 4 ? 4 : 2;
+  ctx->dna_tt_seq = env_int("PLF_TT_SEQ", 1);
+  ctx->dna_balanced = env_int("PLF_DNA_BALANCED", 1);
+  ctx->dna_cherry_items = env_int("PLF_CHERRY_ITEMS", 2) == 4 ? 4 : 2;
+  if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
 }
 
 /* launch one group of same-kind DNA ops (rate_cats a power of two <= 32) as a
@@ -823,16 +958,52 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
 {
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
-  if (ctx->dna_stream < 0)
+  dna_read_switches(ctx);
+
+  if (kind == PLF_OP_TT_VIRTUAL)
   {
-    ctx->dna_stream = env_int("PLF_DNA_STREAM", 1);
-    ctx->dna_stages = env_int("PLF_DNA_STAGES", 6);
-    ctx->dna_items = env_int("PLF_DNA_ITEMS", 2);
-    ctx->dna_tt_bulk = env_int("PLF_TT_BULK", 1);
-    ctx->dna_tt_items = env_int("PLF_TT_ITEMS", 2) == 4 ? 4 : 2;
-    ctx->dna_tt_seq = env_int("PLF_TT_SEQ", 1);
-    ctx->dna_balanced = env_int("PLF_DNA_BALANCED", 1);
-    if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
+    /* snapshot of the cherries' P-matrices + zeroed scalers: no CLV is written */
+    const unsigned long long entries = (unsigned long long)max_sites * (per_rate ? rate_cats : 1u);
+    unsigned long long bx = (entries / 4 + 255) / 256;
+    const unsigned long long cap = ((unsigned long long)ctx->sm_count * 8 + nops - 1) / nops;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    k_cherry_prepare<<<dim3((unsigned int)bx, nops), 256, 0, ctx->stream>>>(d_ops, per_rate, (int)rate_cats);
+    plf_count_launch();
+    PLF_CHECK(ctx, cudaGetLastError());
+    return 1;
+  }
+  if (kind == PLF_OP_CI || kind == PLF_OP_TC || kind == PLF_OP_CC)
+  {
+    if (!contiguous || !ctx->dna_stream || log2r > 2)
+    {
+      plf_set_error(ctx, "virtual cherry consumers need the contiguous 4-state streaming path (rate_cats <= 4)");
+      return 0;
+    }
+    dna_kernel_t k = nullptr;
+    size_t smem = 0;
+    unsigned int tile = 0;
+    switch (log2r)
+    {
+      case 0: k = pick_cherry_kernel<0>(kind, ctx->dna_cherry_items, &smem, &tile); break;
+      case 1: k = pick_cherry_kernel<1>(kind, ctx->dna_cherry_items, &smem, &tile); break;
+      default: k = pick_cherry_kernel<2>(kind, ctx->dna_cherry_items, &smem, &tile); break;
+    }
+    int & occ = ctx->dna_cherry_occupancy[kind - PLF_OP_CI][log2r];
+    if (!occ)
+    {
+      PLF_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, DNA_THREADS, smem));
+      if (occ < 1) occ = 1;
+    }
+    const unsigned long long ntiles = ((unsigned long long)max_sites + tile - 1) / tile;
+    unsigned long long bx = ((unsigned long long)ctx->sm_count * occ) / nops;
+    if (bx < 1) bx = 1;
+    if (bx > ntiles) bx = ntiles;
+    k<<<dim3((unsigned int)bx, nops), DNA_THREADS, smem, ctx->stream>>>(d_ops, per_rate);
+    plf_count_launch();
+    PLF_CHECK(ctx, cudaGetLastError());
+    return 1;
   }
 
   /* the ring copies tip codes and scalers in 16-byte granules from tile-aligned offsets: a tile must
@@ -975,4 +1146,15 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;
+}
+
+/* do the kernels that consume virtual cherries serve this shape? (the host layer asks before it leaves a
+ * tip-tip parent unwritten) */
+extern "C" int plf_virtual_cherries_supported(plf_ctx_t * ctx, const plf_shape_t * sh)
+{
+  dna_read_switches(ctx);
+  if (sh->states != 4 || !ctx->dna_stream || env_int("PLF_VIRTUAL_CHERRIES", 1) == 0) return 0;
+  if (sh->rate_cats != 1 && sh->rate_cats != 2 && sh->rate_cats != 4) return 0;
+  /* consumers that are not cherry-fed go through the ring kernels too: their tiles need >= 16 sites */
+  return ((DNA_THREADS * (unsigned int)ctx->dna_items) / sh->rate_cats) >= 16;
 }

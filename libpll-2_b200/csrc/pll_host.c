@@ -38,7 +38,9 @@ static __thread int tls_device = -1;
 
 #define PLL_CUDA_MAGIC 0xB200C0DEu
 #define EMPTY_ELEMENT 0xFFFFFFFFu
-#define MAX_SUMTABLES 8
+/* sumtables live in HBM, keyed by the caller's host pointer: this many before the least recently used one
+ * is dropped ($PLL_CUDA_MAX_SUMTABLES); the slot array grows on demand */
+#define DEFAULT_MAX_SUMTABLES 64
 /* pll_cuda_newton_branch: tables up to this size use the one-launch loop (they stay in the 126 MB L2) */
 #define NEWTON_FUSED_MAX_BYTES ((size_t)96 << 20)
 /* the streaming kernels fetch scalers and tip codes with 16-byte bulk copies:
@@ -57,6 +59,13 @@ typedef struct sumtable_slot
   unsigned long long stamp;
   double * asc_host; /* ascertainment bias: host copy of the `states` pseudo-site blocks */
 } sumtable_slot_t;
+
+typedef struct cherry_state
+{
+  unsigned int tip1, tip2;
+  int scaler_index;
+  int is_virtual; /* the node's CLV buffer does not hold its value: (tip1, tip2, snapshot matrices) do */
+} cherry_state_t;
 
 typedef struct cuda_partition
 {
@@ -89,7 +98,10 @@ typedef struct cuda_partition
   unsigned int * clv_entries;    /* site entries allocated per node          */
   unsigned int * scaler_entries; /* uints allocated per scale buffer          */
 
-  sumtable_slot_t sumtabs[MAX_SUMTABLES];
+  sumtable_slot_t * sumtabs;
+  unsigned int n_sumtabs, max_sumtabs;
+  const double ** evicted_keys; /* tables this library computed and then dropped: their host bytes were never written */
+  unsigned int n_evicted, cap_evicted;
   unsigned long long stamp;
   int sumtable_mirror;
   double * d_persite;
@@ -114,6 +126,15 @@ typedef struct cuda_partition
   int repeats_mirror;
 
   int host_expm1; /* bit-exact P-matrices: expm1 from the host libm */
+
+  /* virtual cherries: tip-tip parents of 4-state pattern-tip partitions are not
+   * written to HBM; their consumers work from the tip codes, anything else materialises them first */
+  int cherry_ok;                 /* this partition's kernels consume virtual cherries */
+  unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES) */
+  double * d_cherry_pm;          /* [clv_buffers][2][rate_cats * 16]: the P-matrices each cherry was asked with */
+  struct cherry_state * cherry;  /* [nodes] */
+  struct cherry_state * cherry_saved; /* roll-back copy while an operation list is resolved */
+  unsigned int cherries_pending; /* nodes whose CLV is virtual right now */
 
   /* reusable host scratch for operation lists */
   plf_op_t * h_ops;
@@ -153,6 +174,58 @@ static int cuda_fail(cuda_partition_t * cp)
 static unsigned int sites_alloc(const pll_partition_t * p)
 {
   return p->sites + (p->asc_bias_alloc ? p->states : 0);
+}
+
+/* ---- virtual cherries -------------------------------------------------------------------- */
+
+static double * cherry_snapshot(const cuda_partition_t * cp, unsigned int node)
+{
+  return cp->d_cherry_pm + (size_t)(node - cp->pub.tips) * 2 * cp->pub.rate_cats * 16;
+}
+
+static int is_virtual(const cuda_partition_t * cp, unsigned int node)
+{
+  return cp->cherry && node < cp->pub.nodes && cp->cherry[node].is_virtual;
+}
+
+/* write the CLV of a virtual cherry to its buffer: the tip-tip kernel with the P-matrices the cherry was
+ * asked to be computed with.  Every reader that is not a CLV operation calls this first. */
+static int ensure_real(cuda_partition_t * cp, unsigned int node)
+{
+  const pll_partition_t * p = &cp->pub;
+  const cherry_state_t * c;
+  plf_op_t op;
+  if (!is_virtual(cp, node)) return 1;
+  c = &cp->cherry[node];
+  memset(&op, 0, sizeof(op));
+  op.kind = PLF_OP_TT;
+  op.parent_clv = p->clv[node];
+  op.parent_scaler = c->scaler_index >= 0 ? p->scale_buffer[c->scaler_index] : NULL;
+  op.left_tip = cp->d_tipchars[c->tip1];
+  op.right_tip = cp->d_tipchars[c->tip2];
+  op.left_matrix = cherry_snapshot(cp, node);
+  op.right_matrix = op.left_matrix + (size_t)p->rate_cats * 16;
+  op.nsites = p->sites + (p->asc_bias_alloc ? p->states : 0);
+  if (!plf_update_partials_once(cp->ctx, &cp->shape, &op, 1, cp->d_tipmap, p->maxstates))
+  {
+    pll_errno = PLL_ERROR_CUDA;
+    snprintf(pll_errmsg, sizeof(pll_errmsg), "CUDA: %s", plf_last_error(cp->ctx));
+    return 0;
+  }
+  cp->cherry[node].is_virtual = 0;
+  --cp->cherries_pending;
+  return 1;
+}
+
+/* before the codes of `tip` change: cherries that still depend on the old ones */
+static int ensure_real_for_tip(cuda_partition_t * cp, unsigned int tip)
+{
+  unsigned int n;
+  if (!cp->cherry || !cp->cherries_pending) return 1;
+  for (n = cp->pub.tips; n < cp->pub.nodes; ++n)
+    if (cp->cherry[n].is_virtual && (cp->cherry[n].tip1 == tip || cp->cherry[n].tip2 == tip) && !ensure_real(cp, n))
+      return 0;
+  return 1;
 }
 
 static int env_flag(const char * name)
@@ -277,12 +350,13 @@ static void destroy(cuda_partition_t * cp)
       for (i = 0; i < p->scale_buffers; ++i) plf_free(cp->ctx, p->scale_buffer[i]);
     if (cp->d_tipchars)
       for (i = 0; i < p->tips; ++i) plf_free(cp->ctx, cp->d_tipchars[i]);
-    for (i = 0; i < MAX_SUMTABLES; ++i)
+    for (i = 0; i < cp->n_sumtabs; ++i)
     {
       plf_free(cp->ctx, cp->sumtabs[i].dev);
       free(cp->sumtabs[i].asc_host);
     }
     plf_free(cp->ctx, cp->d_pmatrix_block);
+    plf_free(cp->ctx, cp->d_cherry_pm);
     plf_free(cp->ctx, cp->d_model);
     plf_free(cp->ctx, cp->d_pattern_weights);
     plf_free(cp->ctx, cp->d_invariant);
@@ -324,6 +398,10 @@ static void destroy(cuda_partition_t * cp)
   free(cp->clv_entries);
   free(cp->scaler_entries);
   free(cp->asc_sc);
+  free(cp->sumtabs);
+  free(cp->evicted_keys);
+  free(cp->cherry);
+  free(cp->cherry_saved);
   free(cp->h_model);
   free(cp->h_model_sent);
   free(cp->h_ops);
@@ -549,6 +627,17 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
   NEED(cp->d_tipmap = (unsigned long long *)plf_alloc(cp->ctx, PLL_ASCII_SIZE * sizeof(unsigned long long), 1));
 
   if (attributes & PLL_ATTRIB_SITE_REPEATS) NEED(repeats_initialize(cp));
+
+  if ((attributes & PLL_ATTRIB_PATTERN_TIP) && !p->asc_bias_alloc && clv_buffers &&
+      plf_virtual_cherries_supported(cp->ctx, &cp->shape))
+  {
+    const char * v = getenv("PLF_VIRTUAL_CHERRY_MIN_SITES");
+    cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : 4096u;
+    NEED(cp->cherry = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
+    NEED(cp->cherry_saved = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
+    NEED(cp->d_cherry_pm = (double *)plf_alloc(cp->ctx, (size_t)clv_buffers * 2 * rate_cats * 16 * sizeof(double), 1));
+    cp->cherry_ok = sites >= cp->cherry_min_sites;
+  }
 #undef NEED
   return p;
 }
@@ -1165,6 +1254,7 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_
         }
       }
     }
+    if (!ensure_real_for_tip(cp, tip_index)) return PLL_FAILURE;
     if (!plf_upload_async(cp->ctx, cp->d_tipchars[tip_index], scratch, sites_alloc(partition))) return cuda_fail(cp);
     cp->tip_scratch_busy = 1;
     memcpy(tc, scratch, sites_alloc(partition));
@@ -1700,6 +1790,28 @@ PLL_EXPORT int pll_cuda_schedule_levels(const pll_operation_t * operations, unsi
   return (int)nlevels;
 }
 
+/* NEW (additive, inspection).  The kernel launches one traversal level makes for ops of the given kinds
+ * (PLF_OP_* values, already sorted by kind as launch_levels does): a launch serves a run of same-kind ops,
+ * blockIdx.y selecting the op, so a run is cut after PLF_MAX_RUN_OPS ops.  Returns the number of launches,
+ * the longest run in *largest_run.  Pure host arithmetic: callable without a device. */
+PLL_EXPORT unsigned int pll_cuda_count_launch_runs(const unsigned int * kinds, unsigned int count,
+                                                   unsigned int * largest_run)
+{
+  plf_op_t * ops = (plf_op_t *)calloc(count ? count : 1, sizeof(plf_op_t));
+  unsigned int i, runs = 0, largest = 0;
+  if (!ops) return 0;
+  for (i = 0; i < count; ++i) ops[i].kind = kinds[i];
+  for (i = 0; i < count; ++runs)
+  {
+    const unsigned int j = plf_run_end(ops, i, count, NULL, NULL);
+    if (j - i > largest) largest = j - i;
+    i = j;
+  }
+  free(ops);
+  if (largest_run) *largest_run = largest;
+  return runs;
+}
+
 /* ---- CLV updates ---------------------------------------------------------------- */
 
 static int reserve_ops(cuda_partition_t * cp, unsigned int count)
@@ -1712,7 +1824,7 @@ static int reserve_ops(cuda_partition_t * cp, unsigned int count)
   cp->h_ops = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
   cp->h_ops_sorted = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
   cp->h_level = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
-  cp->h_level_start = (unsigned int *)malloc((3 * (size_t)count + 2) * sizeof(unsigned int));
+  cp->h_level_start = (unsigned int *)malloc((PLF_OP_KINDS * (size_t)count + 2) * sizeof(unsigned int));
   cp->ops_cap = (cp->h_ops && cp->h_ops_sorted && cp->h_level && cp->h_level_start) ? count : 0;
   return cp->ops_cap != 0;
 }
@@ -1757,6 +1869,8 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
   {
     const int pattern = (p->attributes & PLL_ATTRIB_PATTERN_TIP) != 0;
     const int t1 = pattern && c1 < p->tips, t2 = pattern && c2 < p->tips;
+    /* a child whose CLV is virtual: computed from its two tips' codes by this op's kernel */
+    const int v1 = !t1 && is_virtual(cp, c1), v2 = !t2 && is_virtual(cp, c2);
     if (t1 && t2)
     {
       out->kind = PLF_OP_TT;
@@ -1765,6 +1879,18 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
       out->left_matrix = p->pmatrix[op->child1_matrix_index];
       out->right_matrix = p->pmatrix[op->child2_matrix_index];
       if (!out->left_tip || !out->right_tip) goto missing;
+      if (cp->cherry_ok && par >= p->tips && p->clv[par])
+      {
+        /* the cherry stays virtual: only its P-matrices are snapshot and its scaler zeroed */
+        out->kind = PLF_OP_TT_VIRTUAL;
+        out->parent_clv = cherry_snapshot(cp, par);
+        if (!cp->cherry[par].is_virtual) ++cp->cherries_pending;
+        cp->cherry[par].is_virtual = 1;
+        cp->cherry[par].tip1 = c1;
+        cp->cherry[par].tip2 = c2;
+        cp->cherry[par].scaler_index = op->parent_scaler_index;
+        return 1;
+      }
     }
     else if (t1 || t2)
     {
@@ -1773,13 +1899,59 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
       const unsigned int mt = t1 ? op->child1_matrix_index : op->child2_matrix_index;
       const unsigned int mi = t1 ? op->child2_matrix_index : op->child1_matrix_index;
       const int si = t1 ? op->child2_scaler_index : op->child1_scaler_index;
-      out->kind = PLF_OP_TI;
       out->left_tip = cp->d_tipchars ? cp->d_tipchars[tip] : NULL;
-      out->right_clv = p->clv[inner];
       out->left_matrix = p->pmatrix[mt];
       out->right_matrix = p->pmatrix[mi];
-      out->right_scaler = si >= 0 ? sb[si] : NULL;
-      if (!out->left_tip || !out->right_clv) goto missing;
+      if (!out->left_tip) goto missing;
+      if (t1 ? v2 : v1)
+      {
+        const cherry_state_t * c = &cp->cherry[inner];
+        out->kind = PLF_OP_TC;
+        out->right_tip = cp->d_tipchars[c->tip1];
+        out->right_tip2 = cp->d_tipchars[c->tip2];
+        out->right_cm1 = cherry_snapshot(cp, inner);
+        out->right_cm2 = out->right_cm1 + (size_t)p->rate_cats * 16;
+      }
+      else
+      {
+        out->kind = PLF_OP_TI;
+        out->right_clv = p->clv[inner];
+        out->right_scaler = si >= 0 ? sb[si] : NULL;
+        if (!out->right_clv) goto missing;
+      }
+    }
+    else if (v1 || v2)
+    {
+      /* cherries go "left"; with one of them the other child is an inner CLV on the "right"
+       * (parent entry = left term * right term, commutative to the bit) */
+      const int swap = !v1;
+      const unsigned int cl = swap ? c2 : c1, cr = swap ? c1 : c2;
+      const unsigned int ml = swap ? op->child2_matrix_index : op->child1_matrix_index;
+      const unsigned int mr = swap ? op->child1_matrix_index : op->child2_matrix_index;
+      const int sr = swap ? op->child1_scaler_index : op->child2_scaler_index;
+      const cherry_state_t * c = &cp->cherry[cl];
+      out->left_tip = cp->d_tipchars[c->tip1];
+      out->left_tip2 = cp->d_tipchars[c->tip2];
+      out->left_cm1 = cherry_snapshot(cp, cl);
+      out->left_cm2 = out->left_cm1 + (size_t)p->rate_cats * 16;
+      out->left_matrix = p->pmatrix[ml];
+      out->right_matrix = p->pmatrix[mr];
+      if (v1 && v2)
+      {
+        const cherry_state_t * d = &cp->cherry[cr];
+        out->kind = PLF_OP_CC;
+        out->right_tip = cp->d_tipchars[d->tip1];
+        out->right_tip2 = cp->d_tipchars[d->tip2];
+        out->right_cm1 = cherry_snapshot(cp, cr);
+        out->right_cm2 = out->right_cm1 + (size_t)p->rate_cats * 16;
+      }
+      else
+      {
+        out->kind = PLF_OP_CI;
+        out->right_clv = p->clv[cr];
+        out->right_scaler = sr >= 0 ? sb[sr] : NULL;
+        if (!out->right_clv) goto missing;
+      }
     }
     else
     {
@@ -1792,6 +1964,12 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
       out->right_scaler = op->child2_scaler_index >= 0 ? sb[op->child2_scaler_index] : NULL;
     }
   }
+  /* this op writes the parent's buffer: whatever cherry it stood for is gone */
+  if (cp->cherry && par < p->nodes && cp->cherry[par].is_virtual)
+  {
+    cp->cherry[par].is_virtual = 0;
+    --cp->cherries_pending;
+  }
   if (!out->parent_clv || (out->kind == PLF_OP_II && (!out->left_clv || !out->right_clv))) goto missing;
   return 1;
 missing:
@@ -1801,15 +1979,30 @@ missing:
 
 static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
 {
-  unsigned int i, nlevels;
+  unsigned int i, nlevels, saved_pending = 0;
   int nl;
   if (!reserve_ops(cp, count))
   {
     set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
     return 0;
   }
+  /* ops are resolved in list order: whether a child is a virtual cherry is the state the list has
+   * reached at that op; a list that fails to resolve leaves the state as it found it */
+  if (cp->cherry)
+  {
+    memcpy(cp->cherry_saved, cp->cherry, (size_t)cp->pub.nodes * sizeof(cherry_state_t));
+    saved_pending = cp->cherries_pending;
+  }
   for (i = 0; i < count; ++i)
-    if (!resolve_op(cp, ops + i, cp->h_ops + i)) return 0;
+    if (!resolve_op(cp, ops + i, cp->h_ops + i))
+    {
+      if (cp->cherry)
+      {
+        memcpy(cp->cherry, cp->cherry_saved, (size_t)cp->pub.nodes * sizeof(cherry_state_t));
+        cp->cherries_pending = saved_pending;
+      }
+      return 0;
+    }
   nl = pll_cuda_schedule_levels(ops, count, cp->h_level);
   if (nl < 0)
   {
@@ -1819,8 +2012,8 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
   nlevels = (unsigned int)nl;
   /* counting sort by (level, op kind), stable: each launch group is a run of
    * same-kind ops of one level */
-  for (i = 0; i < count; ++i) cp->h_level[i] = cp->h_level[i] * 3 + cp->h_ops[i].kind;
-  nlevels *= 3;
+  for (i = 0; i < count; ++i) cp->h_level[i] = cp->h_level[i] * PLF_OP_KINDS + cp->h_ops[i].kind;
+  nlevels *= PLF_OP_KINDS;
   for (i = 0; i <= nlevels; ++i) cp->h_level_start[i] = 0;
   for (i = 0; i < count; ++i) cp->h_level_start[cp->h_level[i] + 1]++;
   for (i = 0; i < nlevels; ++i) cp->h_level_start[i + 1] += cp->h_level_start[i];
@@ -1919,6 +2112,7 @@ static int fill_edge_args(cuda_partition_t * cp, plf_lk_t * a, unsigned int pare
     set_error(PLL_ERROR_PARAM_INVALID, "buffer index out of range%s", NULL);
     return 0;
   }
+  if (!ensure_real(cp, parent_clv_index) || !ensure_real(cp, child_clv_index)) return 0;
   a->sites = p->sites;
   a->pmatrix = p->pmatrix[matrix_index];
   a->pattern_weights = cp->d_pattern_weights;
@@ -1982,6 +2176,7 @@ static int fill_root_args(cuda_partition_t * cp, plf_lk_t * a, unsigned int clv_
     set_error(PLL_ERROR_PARAM_INVALID, "root CLV index out of range or never set%s", NULL);
     return 0;
   }
+  if (!ensure_real(cp, clv_index)) return 0;
   a->sites = p->sites;
   a->clvp = p->clv[clv_index];
   a->pscaler = scaler_index >= 0 ? p->scale_buffer[scaler_index] : NULL;
@@ -2202,6 +2397,11 @@ PLL_EXPORT int pll_cuda_root_loglikelihood_async(pll_partition_t * partition, un
 {
   cuda_partition_t * cp = CP(partition);
   plf_lk_t a;
+  if (cp && (partition->attributes & PLL_ATTRIB_AB_MASK))
+  {
+    set_error(PLL_ERROR_CUDA_UNSUPPORTED, "the asynchronous entry points do not apply the ascertainment bias correction%s", NULL);
+    return PLL_FAILURE;
+  }
   if (!cp || !dev_out || !fill_root_args(cp, &a, clv_index, scaler_index, freqs_indices)) return PLL_FAILURE;
   return plf_loglikelihood(cp->ctx, &cp->shape, &a, dev_out, NULL) ? PLL_SUCCESS : cuda_fail(cp);
 }
@@ -2251,6 +2451,7 @@ PLL_EXPORT int pll_compute_node_ancestral_extbuf(pll_partition_t * partition, un
     set_error(PLL_ERROR_PARAM_INVALID, "buffer index out of range or CLV never set%s", NULL);
     return PLL_FAILURE;
   }
+  if (!ensure_real(cp, node_clv_index) || !ensure_real(cp, other_clv_index)) return PLL_FAILURE;
   st = p->states;
   sp = p->states_padded;
   R = p->rate_cats;
@@ -2341,26 +2542,86 @@ PLL_EXPORT int pll_compute_node_ancestral(pll_partition_t * partition, unsigned 
 
 /* ---- sumtable and derivatives ---------------------------------------------------------- */
 
+static int key_was_evicted(const cuda_partition_t * cp, const double * key)
+{
+  unsigned int i;
+  for (i = 0; i < cp->n_evicted; ++i)
+    if (cp->evicted_keys[i] == key) return 1;
+  return 0;
+}
+
+static void forget_evicted(cuda_partition_t * cp, const double * key)
+{
+  unsigned int i;
+  for (i = 0; i < cp->n_evicted; ++i)
+    if (cp->evicted_keys[i] == key)
+    {
+      cp->evicted_keys[i] = cp->evicted_keys[--cp->n_evicted];
+      return;
+    }
+}
+
+/* The table of `victim` leaves the device.  Unless the host mirror is kept ($PLL_CUDA_SUMTABLE_MIRROR) the
+ * caller's buffer was never written, so the key is remembered: a derivative call on it fails with a clear
+ * error instead of reading those bytes (the reference writes every table into the caller's buffer,
+ * src/derivatives.c:239-330, so there any number of tables can be live). */
+static void remember_evicted(cuda_partition_t * cp, const double * key)
+{
+  if (cp->sumtable_mirror || !key || key_was_evicted(cp, key)) return;
+  if (cp->n_evicted == cp->cap_evicted)
+  {
+    const unsigned int cap = cp->cap_evicted ? 2 * cp->cap_evicted : 64;
+    const double ** grown = (const double **)realloc((void *)cp->evicted_keys, (size_t)cap * sizeof(*grown));
+    if (!grown) return;
+    cp->evicted_keys = grown;
+    cp->cap_evicted = cap;
+  }
+  cp->evicted_keys[cp->n_evicted++] = key;
+}
+
 static sumtable_slot_t * sumtable_slot(cuda_partition_t * cp, const double * key, int create)
 {
   const size_t need = (size_t)sites_alloc(&cp->pub) * cp->pub.rate_cats * cp->pub.states_padded;
-  sumtable_slot_t * victim = &cp->sumtabs[0];
-  int i;
-  for (i = 0; i < MAX_SUMTABLES; ++i)
+  sumtable_slot_t * victim = NULL;
+  unsigned int i;
+  for (i = 0; i < cp->n_sumtabs; ++i)
     if (cp->sumtabs[i].dev && cp->sumtabs[i].key == key)
     {
       cp->sumtabs[i].stamp = ++cp->stamp;
       return &cp->sumtabs[i];
     }
   if (!create) return NULL;
-  for (i = 0; i < MAX_SUMTABLES; ++i)
+  if (!cp->max_sumtabs)
   {
-    if (!cp->sumtabs[i].dev)
+    const char * v = getenv("PLL_CUDA_MAX_SUMTABLES");
+    cp->max_sumtabs = (v && atoi(v) > 0) ? (unsigned int)atoi(v) : DEFAULT_MAX_SUMTABLES;
+  }
+  for (i = 0; i < cp->n_sumtabs && !victim; ++i)
+    if (!cp->sumtabs[i].dev) victim = &cp->sumtabs[i];
+  if (!victim && cp->n_sumtabs < cp->max_sumtabs)
+  {
+    sumtable_slot_t * grown = (sumtable_slot_t *)realloc(cp->sumtabs, ((size_t)cp->n_sumtabs + 1) * sizeof(*grown));
+    if (grown)
     {
-      victim = &cp->sumtabs[i];
-      break;
+      cp->sumtabs = grown;
+      victim = &cp->sumtabs[cp->n_sumtabs++];
+      memset(victim, 0, sizeof(*victim));
+      victim->dev = (double *)plf_alloc(cp->ctx, need * sizeof(double), 0);
+      victim->doubles = victim->dev ? need : 0;
+      if (!victim->dev)
+      {
+        /* HBM is full: fall back to reusing the least recently used table's memory */
+        --cp->n_sumtabs;
+        victim = NULL;
+      }
     }
-    if (cp->sumtabs[i].stamp < victim->stamp) victim = &cp->sumtabs[i];
+  }
+  if (!victim)
+  {
+    for (i = 0; i < cp->n_sumtabs; ++i)
+      if (cp->sumtabs[i].dev && (!victim || cp->sumtabs[i].stamp < victim->stamp)) victim = &cp->sumtabs[i];
+    if (!victim) return NULL;
+    remember_evicted(cp, victim->key);
   }
   if (victim->dev && victim->doubles < need)
   {
@@ -2375,6 +2636,7 @@ static sumtable_slot_t * sumtable_slot(cuda_partition_t * cp, const double * key
   }
   victim->key = key;
   victim->stamp = ++cp->stamp;
+  forget_evicted(cp, key);
   return victim;
 }
 
@@ -2396,6 +2658,7 @@ PLL_EXPORT int pll_update_sumtable(pll_partition_t * partition, unsigned int par
     set_error(PLL_ERROR_PARAM_INVALID, "buffer index out of range%s", NULL);
     return PLL_FAILURE;
   }
+  if (!ensure_real(cp, parent_clv_index) || !ensure_real(cp, child_clv_index)) return PLL_FAILURE;
   a.sites = sites_alloc(p); /* src/derivatives.c:56-58,131-133,191-193 */
   if ((p->attributes & PLL_ATTRIB_PATTERN_TIP) && (parent_clv_index < p->tips || child_clv_index < p->tips))
   {
@@ -2467,6 +2730,14 @@ static int derivative_args(cuda_partition_t * cp, plf_deriv_t * a, double branch
   const pll_partition_t * p = &cp->pub;
   sumtable_slot_t * slot = sumtable_slot(cp, sumtable, 0);
   memset(a, 0, sizeof(*a));
+  if (!slot && sumtable && key_was_evicted(cp, sumtable))
+  {
+    pll_errno = PLL_ERROR_PARAM_INVALID;
+    snprintf(pll_errmsg, sizeof(pll_errmsg),
+             "this sumtable was dropped from the device (more than %u live tables): call pll_update_sumtable "
+             "again or raise PLL_CUDA_MAX_SUMTABLES", cp->max_sumtabs);
+    return 0;
+  }
   if (!slot)
   {
     /* a table this library did not compute: the host bytes are the data */
@@ -2625,6 +2896,13 @@ PLL_EXPORT int pll_cuda_likelihood_derivatives_async(pll_partition_t * partition
   plf_deriv_t a;
   (void)parent_scaler_index;
   (void)child_scaler_index;
+  if (cp && (partition->attributes & PLL_ATTRIB_AB_MASK) &&
+      (partition->attributes & PLL_ATTRIB_AB_MASK) != PLL_ATTRIB_AB_STAMATAKIS)
+  {
+    /* the Lewis / Felsenstein terms are formed on the host per evaluation (asc_derivatives) */
+    set_error(PLL_ERROR_CUDA_UNSUPPORTED, "the asynchronous entry points do not apply the ascertainment bias correction%s", NULL);
+    return PLL_FAILURE;
+  }
   if (!cp || !dev_out2 || !derivative_args(cp, &a, branch_length, params_indices, sumtable)) return PLL_FAILURE;
   return plf_derivatives(cp->ctx, &cp->shape, &a, dev_out2, NULL) ? PLL_SUCCESS : cuda_fail(cp);
 }
@@ -2826,10 +3104,41 @@ PLL_EXPORT int pll_cuda_download_clv(const pll_partition_t * partition, unsigned
     set_error(PLL_ERROR_PARAM_INVALID, "no such CLV%s", NULL);
     return PLL_FAILURE;
   }
+  if (!ensure_real(cp, clv_index)) return PLL_FAILURE;
   return plf_download(cp->ctx, host_out, partition->clv[clv_index],
                       (size_t)pll_get_clv_size(partition, clv_index) * sizeof(double))
              ? PLL_SUCCESS
              : cuda_fail(cp);
+}
+
+/* NEW (additive).  1 when tip-tip parents of this partition stay virtual. */
+PLL_EXPORT int pll_cuda_virtual_cherries(const pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  return cp && cp->cherry_ok;
+}
+
+/* NEW (additive).  Number of nodes whose CLV is virtual right now; `clv_index` < nodes asks about one node. */
+PLL_EXPORT unsigned int pll_cuda_virtual_clvs(const pll_partition_t * partition, unsigned int clv_index)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return 0;
+  if (clv_index < partition->nodes) return (unsigned int)is_virtual(cp, clv_index);
+  return cp->cherries_pending;
+}
+
+/* NEW (additive).  Make sure partition->clv[clv_index] holds the node's values in HBM (clients that hand the
+ * device pointer to their own kernels); every entry point of this library does it on its own. */
+PLL_EXPORT int pll_cuda_materialize_clv(pll_partition_t * partition, unsigned int clv_index)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp) return PLL_FAILURE;
+  if (clv_index >= partition->nodes)
+  {
+    set_error(PLL_ERROR_PARAM_INVALID, "no such CLV%s", NULL);
+    return PLL_FAILURE;
+  }
+  return ensure_real(cp, clv_index) ? PLL_SUCCESS : PLL_FAILURE;
 }
 
 PLL_EXPORT unsigned int pll_cuda_scaler_size(const pll_partition_t * partition, unsigned int scaler_index)

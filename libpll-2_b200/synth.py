@@ -262,6 +262,49 @@ def aa_dataset(tips: int, sites: int, seed: int, alpha: float = 0.7, cats: int =
                    pidx, seqs, "pll_map_aa")
 
 
+def lg4m_tables(ref_path: str):
+    """(rates[4][190], freqs[4][20]) of the LG4M model (Le, Dang & Gascuel 2012) as the reference build
+    exports them (``pll_aa_rates_lg4m`` / ``pll_aa_freqs_lg4m``, /root/reference/src/pll.h:596,629; set by
+    ``examples/lg4/lg4.c:298-301``), read out of the checker library's data segment: input data only,
+    nothing of the reference's code runs.  None when that library did not travel."""
+    import ctypes as C
+    import os
+
+    if not os.path.exists(ref_path):
+        return None
+    lib = C.CDLL(ref_path)
+    try:
+        r = np.array((C.c_double * 190 * 4).in_dll(lib, "pll_aa_rates_lg4m"), dtype=np.float64)
+        f = np.array((C.c_double * 20 * 4).in_dll(lib, "pll_aa_freqs_lg4m"), dtype=np.float64)
+    except ValueError:
+        return None
+    return r.copy(), f.copy()
+
+
+def lg4m_dataset(tips: int, sites: int, seed: int, ref_path: str, alpha: float = 1.0, brlen=(0.02, 0.22),
+                 simulate_down_tree: bool = True, tree_kind: str = "random") -> tuple[Dataset, str]:
+    """BASELINE config 3: protein, 4 rate categories each with its own LG4M matrix and frequencies
+    (params_indices {0,1,2,3}, examples/lg4/lg4.c:286-310).  Falls back to random LG4M-style matrices
+    when the tables are not available; the second value says which."""
+    rng = np.random.default_rng(seed)
+    tree = (caterpillar_tree if tree_kind == "caterpillar" else random_tree)(tips, rng, brlen)
+    rates = gamma_rates(alpha, 4)
+    tab = lg4m_tables(ref_path)
+    if tab is None:
+        models = [random_aa_model(rng) for _ in range(4)]
+        name = "random LG4M-style matrices (oracle/_ref not present)"
+    else:
+        models = [(tab[0][i], tab[1][i]) for i in range(4)]
+        name = "LG4M (pll_aa_rates_lg4m / pll_aa_freqs_lg4m)"
+    if simulate_down_tree:
+        qs = [gtr_q(m[0], m[1]) for m in models]
+        seqs = simulate(tree, qs, models[0][1], rates, sites, rng, AA_CODES, AA_AMBIG)
+    else:
+        seqs = mutate_alignment(tips, sites, rng, AA_CODES, AA_AMBIG)
+    return Dataset(tree, 20, sites, 4, [m[0] for m in models], [m[1] for m in models], rates, None,
+                   np.arange(4, dtype=np.uint32), seqs, "pll_map_aa"), name
+
+
 def generic_dataset(states: int, tips: int, sites: int, seed: int, cats: int = 4,
                     tree_kind: str = "random", brlen=(0.02, 0.22)) -> Dataset:
     """Odd state counts (5, 7, ...) as in test/src/00012 and derivatives-oddstates."""

@@ -1,0 +1,404 @@
+"""Parity cases added in round 2 (all against the UNMODIFIED reference, oracle/_ref, AVX2 attribute, through the
+C ABI): virtual cherries, unequal category weights, pll_set_tip_clv, +I under site repeats, BASELINE-shaped
+inputs that scale, many live sumtables, and the site-sharded evaluation (two ranks) against the reference on
+the same slices.  Tolerances are the north star's: integers and 4-state CLVs bit-exact, logL 1e-10, derivatives 1e-9."""
+import ctypes as C
+import importlib
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pkg = importlib.import_module("libpll-2_b200")
+capi = pkg.capi
+synth = importlib.import_module("libpll-2_b200.synth")
+harness = importlib.import_module("libpll-2_b200.harness")
+
+from test_gpu_parity import (DERIV_RTOL, LOGL_RTOL, assert_clv_equal, assert_rel, bits,  # noqa: E402
+                             check_edge_and_derivatives, pair)
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def traverse(*engines):
+    for e in engines:
+        e.update_pmatrices()
+        e.update_partials()
+
+
+def compare_all_nodes(ref, gpu, exact=True):
+    n_scaled = 0
+    for op in ref.ops:
+        assert_clv_equal(ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index), exact, f"clv {op.parent_clv_index}")
+        if op.parent_scaler_index >= 0:
+            sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
+            assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
+            n_scaled += int(sa.sum())
+    return n_scaled
+
+
+# ---- virtual cherries ------------------------------------------------------------------------------------
+
+def cherry_nodes(ds):
+    tips = ds.tree.tips
+    return [int(r[0]) for r in ds.tree.ops if int(r[2]) < tips and int(r[5]) < tips]
+
+
+CHERRY_CASES = [
+    # tips, sites, tree, cats, per_rate
+    (12, 97, "random", 4, False),
+    (40, 1501, "random", 4, False),
+    (40, 1501, "random", 4, True),
+    (33, 4099, "random", 2, False),
+    (21, 777, "random", 1, False),
+    (300, 61, "caterpillar", 4, False),
+    (300, 61, "caterpillar", 4, True),
+    (64, 16, "random", 4, False),
+]
+
+
+@pytest.mark.parametrize("case", CHERRY_CASES, ids=lambda c: "-".join(map(str, c)))
+@pytest.mark.parametrize("items", ["2", "4"])
+def test_virtual_cherries_parity(reflib, cudalib, monkeypatch, case, items):
+    """Tip-tip parents are not written: consumers of every kind (tip + cherry, cherry +
+    inner, cherry + cherry), scalers, edge logL before anything is materialised, then every CLV bit for bit."""
+    tips, sites, tree, cats, per_rate = case
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
+    monkeypatch.setenv("PLF_CHERRY_ITEMS", items)
+    ds = synth.dna_dataset(tips, sites, seed=100 + tips, tree_kind=tree, alpha=0.4, cats=cats)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
+    cherries = cherry_nodes(ds)
+    assert cherries
+    traverse(ref, gpu)
+    assert cudalib.pll_cuda_virtual_clvs(gpu.p, 0xFFFFFFFF) == len(cherries)
+    # the root edge first: nothing has been materialised, every consumer worked from tip codes
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL over virtual cherries")
+    n_scaled = compare_all_nodes(ref, gpu)  # downloads materialise the cherries
+    if tree == "caterpillar":
+        assert n_scaled > 0
+    assert cudalib.pll_cuda_virtual_clvs(gpu.p, 0xFFFFFFFF) == 0
+    # three more traversals: the second identical list is captured into a graph, the third replays it
+    for _ in range(3):
+        traverse(gpu)
+    assert cudalib.pll_cuda_virtual_clvs(gpu.p, 0xFFFFFFFF) == len(cherries)
+    compare_all_nodes(ref, gpu)
+    # edges that end in a cherry: log-likelihood, sumtable, derivatives materialise on their own
+    traverse(gpu)
+    t = ds.tree
+    edges = []
+    for r in t.ops:
+        for child, m in ((int(r[2]), int(r[3])), (int(r[5]), int(r[6]))):
+            if child in cherries and len(edges) < 3:
+                edges.append((int(r[0]), child, m))
+    assert edges
+    # the edge is evaluated from the CLVs as the traversal left them (both libraries hold the same state)
+    check_edge_and_derivatives(ref, gpu, ds, per_rate, edges)
+    ref.close()
+    gpu.close()
+
+
+def test_virtual_cherry_survives_pmatrix_and_tip_changes(reflib, cudalib, monkeypatch):
+    """A virtual cherry stands for the CLV the reference would hold: P-matrix updates and new tip states
+    after the traversal must not change what a later reader sees; a partial traversal over the consumers
+    alone picks the pending cherries up."""
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
+    ds = synth.dna_dataset(24, 1000, seed=7, tree_kind="random", alpha=0.5)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    cherries = cherry_nodes(ds)
+    traverse(ref, gpu)
+    # new branch lengths everywhere, and new states for the first tip of the first cherry
+    bl = ds.tree.branch_lengths[ref.matrix_indices] * 2.5
+    first = [r for r in ds.tree.ops if int(r[0]) == cherries[0]][0]
+    tip = int(first[2])
+    other = ds.seqs[(tip + 1) % ds.tree.tips]
+    for e, lib in ((ref, reflib), (gpu, cudalib)):
+        e.update_pmatrices(branch_lengths=bl)
+        assert lib.pll_set_tip_states(e.p, tip, e.map, other) == 1
+    for n in cherries:
+        assert np.array_equal(bits(ref.clv(n)), bits(gpu.clv(n))), f"cherry {n} after pmatrix / tip change"
+    # consumers only (the cherries are NOT recomputed): the first cherry is real now, the others pending again
+    traverse(ref, gpu)
+    consumers = [k for k, r in enumerate(ds.tree.ops) if int(r[0]) not in cherries]
+    ops = (capi.Operation * len(consumers))(*[ref.ops[k] for k in consumers])
+    bl2 = ds.tree.branch_lengths[ref.matrix_indices] * 0.5
+    for e, lib in ((ref, reflib), (gpu, cudalib)):
+        e.update_pmatrices(branch_lengths=bl2)
+        lib.pll_update_partials(e.p, ops, len(consumers))
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL after the consumer-only traversal")
+    compare_all_nodes(ref, gpu)
+    ref.close()
+    gpu.close()
+
+
+def test_virtual_cherries_off_switch_and_threshold(cudalib, monkeypatch):
+    ds = synth.dna_dataset(10, 200, seed=3)
+    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0  # narrower than the default threshold
+    gpu.close()
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "0")
+    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0
+    gpu.close()
+
+
+def test_virtual_cherries_large(reflib, cudalib):
+    """default switches, more sites than one sweep of the persistent grids covers"""
+    ds = synth.dna_dataset(48, 150_001, seed=9, simulate_down_tree=False)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
+    traverse(ref, gpu)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
+    compare_all_nodes(ref, gpu)
+    ref.close()
+    gpu.close()
+
+
+# ---- unequal category weights (LG4X-style) ------------------------------------------------------------------
+
+WEIGHT_CASES = [
+    ("dna", capi.PATTERN_TIP, False), ("dna", 0, False), ("dna", capi.SITE_REPEATS, False), ("dna", capi.PATTERN_TIP, True),
+    ("aa", capi.PATTERN_TIP, False), ("aa", 0, False), ("aa", capi.SITE_REPEATS, False), ("g5", 0, False),
+]
+
+
+@pytest.mark.parametrize("kind,extra,per_rate", WEIGHT_CASES)
+def test_unequal_category_weights_parity(reflib, cudalib, kind, extra, per_rate):
+    """pll_set_category_weights with unequal weights: the reference's reductions take the weighted branch
+    (core_likelihood_avx.c:1606-1684 `terma += terma_r * w_r`, core_derivatives_avx2.c:1640-1807)."""
+    if kind == "dna":
+        ds = synth.dna_dataset(60, 1003, seed=61, tree_kind="caterpillar", alpha=0.4, brlen=(0.01, 0.12))
+    elif kind == "aa":
+        ds = synth.aa_dataset(40, 301, seed=62, tree_kind="random", alpha=0.4)
+    else:
+        ds = synth.generic_dataset(5, 30, 200, seed=63)
+    ds.cat_weights = np.array([0.1, 0.2, 0.3, 0.4])
+    ds.pattern_weights = np.random.default_rng(8).integers(1, 5, size=ds.sites).astype(np.uint32)
+    ref, gpu = pair(reflib, cudalib, ds, extra, per_rate)
+    w = np.ctypeslib.as_array(gpu.part.rate_weights, shape=(4,))
+    assert np.array_equal(w, ds.cat_weights)
+    traverse(ref, gpu)
+    last = ref.ops[len(ref.ops) - 1]
+    edges = [ds.tree.root_edge, (last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index)]
+    check_edge_and_derivatives(ref, gpu, ds, per_rate, edges)
+    if not per_rate:
+        r_ref, rp_ref = ref.root_logl(persite=True)
+        r_gpu, rp_gpu = gpu.root_logl(persite=True)
+        assert_rel(r_gpu, r_ref, LOGL_RTOL, "root logL")
+        np.testing.assert_allclose(rp_gpu, rp_ref, rtol=1e-12)
+    ref.close()
+    gpu.close()
+
+
+# ---- pll_set_tip_clv (src/pll.c:1066-1129) ------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["dna", "aa", "g5"])
+@pytest.mark.parametrize("padding", [0, 1])
+@pytest.mark.parametrize("extra", [0, capi.SITE_REPEATS])
+def test_set_tip_clv_parity(reflib, cudalib, kind, padding, extra):
+    """Tip CLVs given by the caller (uncertain states): replicated over the rates, padded or not, and under
+    site repeats taken at the class representatives (src/pll.c:1085-1099)."""
+    if kind == "dna":
+        ds = synth.dna_dataset(14, 333, seed=91, brlen=(0.002, 0.08))
+    elif kind == "aa":
+        ds = synth.aa_dataset(9, 120, seed=92, brlen=(0.002, 0.08))
+    else:
+        ds = synth.generic_dataset(5, 11, 150, seed=93, brlen=(0.002, 0.08))
+    ref, gpu = pair(reflib, cudalib, ds, extra)
+    st, sp = ds.states, ref.part.states_padded
+    width = sp if padding else st
+    rng = np.random.default_rng(4)
+    # one probability vector per character: consistent with the tip's repeat classes
+    per_char = {c: rng.dirichlet(np.ones(st)) for c in range(256)}
+    for tip in (0, 3, ds.tree.tips - 1):
+        seq = np.frombuffer(ds.seqs[tip], dtype=np.uint8)
+        clv = np.zeros((ds.sites, width))
+        for s, c in enumerate(seq):
+            clv[s, :st] = per_char[int(c)]
+        if padding:
+            clv[:, st:] = 7.0  # garbage in the padding must not be copied
+        flat = np.ascontiguousarray(clv.reshape(-1))
+        for lib, e in ((reflib, ref), (cudalib, gpu)):
+            assert lib.pll_set_tip_clv(e.p, tip, flat.ctypes.data_as(capi.c_double_p), padding) == 1, lib.errmsg
+        a, b = ref.clv(tip), gpu.clv(tip)
+        keep = np.tile(np.arange(sp) < st, a.size // sp)
+        assert np.array_equal(bits(a[keep]), bits(b[keep])), f"tip clv {tip}"
+    traverse(ref, gpu)
+    compare_all_nodes(ref, gpu, exact=(kind != "aa"))
+    check_edge_and_derivatives(ref, gpu, ds, False)
+    ref.close()
+    gpu.close()
+
+
+def test_set_tip_clv_pattern_tip_rejected(cudalib):
+    ds = synth.dna_dataset(6, 64, seed=1)
+    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    clv = np.ones(64 * 4)
+    assert cudalib.pll_set_tip_clv(gpu.p, 0, clv.ctypes.data_as(capi.c_double_p), 0) == 0
+    assert "PLL_ATTRIB_PATTERN_TIP" in cudalib.errmsg
+    gpu.close()
+
+
+# ---- +I together with site repeats --------------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["dna", "aa"])
+def test_invariant_sites_with_site_repeats(reflib, cudalib, kind):
+    ds = (synth.dna_dataset(20, 800, seed=23, brlen=(0.002, 0.05)) if kind == "dna"
+          else synth.aa_dataset(12, 300, seed=24, brlen=(0.002, 0.05)))
+    seqs = [bytearray(s) for s in ds.seqs]
+    for col in range(0, ds.sites, 3):
+        for s in seqs:
+            s[col] = seqs[0][col]
+    ds.seqs = [bytes(s) for s in seqs]
+    ds.prop_invar = 0.25
+    ds.pattern_weights = np.random.default_rng(3).integers(1, 6, size=ds.sites).astype(np.uint32)
+    ref, gpu = pair(reflib, cudalib, ds, capi.SITE_REPEATS)
+    inv_ref = np.ctypeslib.as_array(ref.part.invariant, shape=(ds.sites,)).copy()
+    inv_gpu = np.ctypeslib.as_array(gpu.part.invariant, shape=(ds.sites,)).copy()
+    assert np.array_equal(inv_ref, inv_gpu) and (inv_ref >= 0).sum() > 10
+    traverse(ref, gpu)
+    last = ref.ops[len(ref.ops) - 1]
+    edges = [ds.tree.root_edge, (last.parent_clv_index, last.child1_clv_index, last.child1_matrix_index)]
+    check_edge_and_derivatives(ref, gpu, ds, False, edges)
+    assert_rel(gpu.root_logl(), ref.root_logl(), LOGL_RTOL, "root logL +I, repeats")
+    ref.close()
+    gpu.close()
+
+
+# ---- BASELINE-shaped inputs that scale -----------------------------------------------
+
+@pytest.mark.parametrize("extra", [capi.PATTERN_TIP, capi.SITE_REPEATS])
+def test_dna_1000_taxa_parity(reflib, cudalib, extra):
+    """DNA 1000 taxa x 20k sites (config 4's tree width): scaling events in the thousands, every scaler and
+    every CLV of a sample of nodes bit-exact, identifiers exact under repeats, logL and derivatives."""
+    ds = synth.dna_dataset(1000, 20_000, seed=3, alpha=0.3, brlen=(0.002, 0.05))
+    ref, gpu = pair(reflib, cudalib, ds, extra)
+    traverse(ref, gpu)
+    n_scaled = 0
+    for k, op in enumerate(ref.ops):
+        sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
+        assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
+        n_scaled += int(sa.sum())
+        if k % 37 == 0 or k >= len(ref.ops) - 5:
+            assert np.array_equal(bits(ref.clv(op.parent_clv_index)), bits(gpu.clv(op.parent_clv_index)))
+    assert n_scaled > 0, "a 1000-taxon tree was meant to scale"
+    if extra & capi.SITE_REPEATS:
+        for node in range(0, ds.tree.nodes, 53):
+            ids_r, sid_r, is_r = ref.repeat_ids(node)
+            ids_g, sid_g, is_g = gpu.repeat_ids(node)
+            assert ids_r == ids_g
+            if ids_r:
+                assert np.array_equal(sid_r, sid_g) and np.array_equal(is_r, is_g)
+    check_edge_and_derivatives(ref, gpu, ds, False)
+    ref.close()
+    gpu.close()
+
+
+def test_aa_lg4m_200_taxa_parity(reflib, cudalib):
+    """Config 3's model and tree width: LG4M matrices and frequencies per rate category, 200 taxa x 10k sites."""
+    ds, name = synth.lg4m_dataset(200, 10_000, seed=2, ref_path=pkg.REF_PATH, brlen=(0.05, 0.6))
+    assert name.startswith("LG4M")
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    traverse(ref, gpu)
+    n_scaled = 0
+    for k, op in enumerate(ref.ops):
+        sa, sb = ref.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index)
+        assert np.array_equal(sa, sb), f"scaler {op.parent_scaler_index}"
+        n_scaled += int(sa.sum())
+        if k % 17 == 0:
+            assert_clv_equal(ref.clv(op.parent_clv_index), gpu.clv(op.parent_clv_index), False, f"clv {op.parent_clv_index}")
+    assert n_scaled > 0, "the 200-taxon protein tree was meant to scale"
+    check_edge_and_derivatives(ref, gpu, ds, False)
+    ref.close()
+    gpu.close()
+
+
+# ---- more live sumtables than device slots ------------------------------------------------------------------
+
+def test_many_live_sumtables(reflib, cudalib, monkeypatch):
+    """The reference writes a sumtable into the caller's buffer, so any number can be live; here they stay
+    in HBM keyed by the caller's pointer.  More tables than slots: every derivative call must either answer
+    from the right table or fail loudly -- never from unwritten host bytes."""
+    monkeypatch.setenv("PLL_CUDA_MAX_SUMTABLES", "4")
+    ds = synth.dna_dataset(16, 500, seed=13)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    traverse(ref, gpu)
+    edges = []
+    for op in ref.ops:
+        for child, m in ((op.child1_clv_index, op.child1_matrix_index), (op.child2_clv_index, op.child2_matrix_index)):
+            if child >= ds.tree.tips or op.parent_clv_index >= ds.tree.tips:
+                edges.append((op.parent_clv_index, child, m))
+    edges = edges[:12]
+    tabs_ref = [ref.sumtable_alloc() for _ in edges]
+    tabs_gpu = [gpu.sumtable_alloc() for _ in edges]
+    for e, tr, tg in zip(edges, tabs_ref, tabs_gpu):
+        ref.update_sumtable(tr, e)
+        gpu.update_sumtable(tg, e)
+    answered = failed = 0
+    for e, tr, tg in zip(edges, tabs_ref, tabs_gpu):
+        d_ref = ref.derivatives(tr, 0.1, e)
+        try:
+            d_gpu = gpu.derivatives(tg, 0.1, e)
+        except RuntimeError as err:
+            assert "sumtable" in str(err)
+            failed += 1
+            continue
+        answered += 1
+        for a, b in zip(d_gpu, d_ref):
+            assert abs(a - b) <= DERIV_RTOL * max(abs(b), 1e-6 * ds.sites), (e, d_gpu, d_ref)
+    assert answered >= 4 and answered + failed == len(edges)
+    # recomputing an evicted table brings it back
+    gpu.update_sumtable(tabs_gpu[0], edges[0])
+    d_ref, d_gpu = ref.derivatives(tabs_ref[0], 0.2, edges[0]), gpu.derivatives(tabs_gpu[0], 0.2, edges[0])
+    for a, b in zip(d_gpu, d_ref):
+        assert abs(a - b) <= DERIV_RTOL * max(abs(b), 1e-6 * ds.sites)
+    ref.close()
+    gpu.close()
+
+
+def test_many_live_sumtables_default_slots(reflib, cudalib):
+    """with the default slot count a dozen live tables all answer"""
+    ds = synth.dna_dataset(16, 500, seed=13)
+    ref, gpu = pair(reflib, cudalib, ds, 0)
+    traverse(ref, gpu)
+    edges = [(op.parent_clv_index, op.child1_clv_index, op.child1_matrix_index) for op in ref.ops][:12]
+    tabs_ref = [ref.sumtable_alloc() for _ in edges]
+    tabs_gpu = [gpu.sumtable_alloc() for _ in edges]
+    for e, tr, tg in zip(edges, tabs_ref, tabs_gpu):
+        ref.update_sumtable(tr, e)
+        gpu.update_sumtable(tg, e)
+    for e, tr, tg in zip(edges, tabs_ref, tabs_gpu):
+        d_ref, d_gpu = ref.derivatives(tr, 0.1, e), gpu.derivatives(tg, 0.1, e)
+        for a, b in zip(d_gpu, d_ref):
+            assert abs(a - b) <= DERIV_RTOL * max(abs(b), 1e-6 * ds.sites), (e, d_gpu, d_ref)
+    ref.close()
+    gpu.close()
+
+
+# ---- site-sharded evaluation, two ranks, against the reference on the same slices ---------------------------
+
+def test_site_sharded_two_ranks_against_reference(reflib, cudalib, tmp_path):
+    """Two ranks, each owning a contiguous site slice on the CUDA engine (two GPUs over NCCL when the box has
+    them, else both ranks on cuda:0 reducing over gloo): the all-reduced {logL, d_f, dd_f} against the
+    reference evaluated on the same two slices and against the reference on the whole alignment."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "sharded.npy")
+    env = dict(os.environ, SHARDED_OUT=out)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tests", "sharded_worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    got = np.load(out)  # [gpu reduced x3, reference slices summed x3, reference whole x3]
+    gpu3, ref_slices, ref_whole = got[0:3], got[3:6], got[6:9]
+    assert_rel(gpu3[0], ref_slices[0], LOGL_RTOL, "reduced logL vs reference on the same slices")
+    assert_rel(gpu3[0], ref_whole[0], LOGL_RTOL, "reduced logL vs reference on the whole alignment")
+    for k, name in ((1, "d_f"), (2, "dd_f")):
+        assert abs(gpu3[k] - ref_slices[k]) <= DERIV_RTOL * max(abs(ref_slices[k]), 1e-3), (name, got)
+        assert abs(gpu3[k] - ref_whole[k]) <= DERIV_RTOL * max(abs(ref_whole[k]), 1e-3), (name, got)

@@ -196,3 +196,21 @@ def test_parsimony_level_schedule_keeps_every_order_of_the_sequential_list():
             assert level[j] == need, (j, level[j], need)
     bad = (capi.ParsBuildOp * 1)(capi.ParsBuildOp(9, 0, 1))
     assert f(bad, 1, 3, np.zeros(1, dtype=np.uint32).ctypes.data_as(capi.c_uint_p)) == -1
+
+
+def test_launch_runs_are_cut_at_the_grid_limit(lib):
+    """A level with more same-kind operations than gridDim.y allows (65535; a balanced tree of ~130k taxa) is
+    served by several launches instead of one invalid one; kinds never mix within a launch."""
+    def runs(kinds):
+        k = np.asarray(kinds, dtype=np.uint32)
+        largest = C.c_uint(0)
+        n = lib.pll_cuda_count_launch_runs(k.ctypes.data_as(capi.c_uint_p), len(k), C.byref(largest))
+        return n, largest.value
+
+    assert runs([]) == (0, 0)
+    assert runs([2] * 10) == (1, 10)
+    assert runs([0] * 3 + [1] * 4 + [2] * 5) == (3, 5)
+    assert runs([2] * 65535) == (1, 65535)
+    assert runs([2] * 65536) == (2, 65535)
+    assert runs([2] * 70000 + [3] * 5) == (3, 65535)
+    assert runs([1] * 200000) == (4, 65535)
