@@ -14,9 +14,11 @@
  *     with PLL_CUDA_MANAGED=1 in the environment (cudaMallocManaged).  Use
  *     pll_cuda_download_clv()/..._scaler()/..._pmatrix() to read them.
  *   - rates, rate_weights, subst_params, frequencies, prop_invar, invariant,
- *     pattern_weights, eigen*, tipchars[], charmap, tipmap and every field of
+ *     pattern_weights, eigen*, charmap, tipmap and every field of
  *     pll_repeats_t are HOST arrays exactly as in the reference; the engine
  *     keeps device mirrors and re-uploads them when they change.
+ *   - tipchars[] are host arrays too, but the codes are formed on the device:
+ *     call pll_cuda_host_tipchars(partition, tip) before reading tipchars[tip].
  */
 #ifndef PLL_B200_H_
 #define PLL_B200_H_
@@ -533,6 +535,10 @@ PLL_EXPORT int pll_cuda_materialize_clv(pll_partition_t * partition,
  * most 65535 ops (gridDim.y).  Host arithmetic only. */
 PLL_EXPORT unsigned int pll_cuda_count_launch_runs(const unsigned int * kinds, unsigned int count,
                                                    unsigned int * largest_run);
+/* tipchars[] of a PLL_ATTRIB_PATTERN_TIP partition are formed on the device from the raw characters
+ * (src/pll.c:875-957); the host copy partition->tipchars[i] is written by this call, not by
+ * pll_set_tip_states ($PLL_CUDA_TIPCHARS_MIRROR=1 writes it there too, as the reference does). */
+PLL_EXPORT const unsigned char * pll_cuda_host_tipchars(pll_partition_t * partition, unsigned int tip_index);
 /* number of elements of a scale buffer as currently allocated */
 PLL_EXPORT unsigned int pll_cuda_scaler_size(const pll_partition_t * partition,
                                              unsigned int scaler_index);

@@ -254,6 +254,7 @@ _CUDA_PROTOS = {
     "pll_cuda_download_sumtable": (C.c_int, [PartitionP, c_double_p, c_double_p]),
     "pll_cuda_scaler_size": (C.c_uint, [PartitionP, C.c_uint]),
     "pll_cuda_count_launch_runs": (C.c_uint, [c_uint_p, C.c_uint, c_uint_p]),
+    "pll_cuda_host_tipchars": (c_ubyte_p, [PartitionP, C.c_uint]),
     "pll_cuda_virtual_cherries": (C.c_int, [PartitionP]),
     "pll_cuda_virtual_clvs": (C.c_uint, [PartitionP, C.c_uint]),
     "pll_cuda_materialize_clv": (C.c_int, [PartitionP, C.c_uint]),

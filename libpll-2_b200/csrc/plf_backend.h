@@ -54,6 +54,7 @@ typedef struct plf_op
   const unsigned int * parent_id_site;
   const unsigned int * left_site_id;
   const unsigned int * right_site_id;
+  const unsigned int * pair_list; /* site repeats: (left entry, right entry) per parent entry, or NULL */
   const unsigned char * left_tip2;
   const unsigned char * right_tip2;
   const double * left_cm1;
@@ -224,6 +225,43 @@ int plf_repeats_ids_batch(plf_ctx_t * ctx, unsigned int sites,
                           const plf_rep_job_t * h_jobs, unsigned int njobs,
                           unsigned int * d_lookup_pool, unsigned int * h_ids);
 
+/* The identifiers of a whole operation list without a host synchronisation per level, for the default
+ * enable rule (pll_default_enable_repeats, src/repeats.c:100-110), which is evaluated on the device from
+ * the children's class counts.  Job j numbers node `parent` from the identifiers of `left` and `right`;
+ * its lookup keys live in the 64-bit entries [lookup_offset, lookup_offset + lookup_entries) of the pool,
+ * where lookup_entries >= ids(left) * ids(right) whenever the rule enables the node (the host passes
+ * min(upper bound of the product, lookup_buffer_size)).  d_node_ids[node] holds the class count the
+ * reference keeps in pernode_ids (0 = not compressed) for every node on entry and is updated per job;
+ * d_raw_ids[first_job + j] receives the number of classes found (0 when the rule said no).  Jobs of one
+ * call must be independent of each other (one traversal level, or a part of it).  Nothing is waited for. */
+typedef struct plf_rid_job
+{
+  const unsigned int * site_id_left;
+  const unsigned int * site_id_right;
+  unsigned int * site_id_parent;
+  unsigned int * id_site_parent;
+  unsigned long long lookup_offset;
+  unsigned int left, right, parent;
+  unsigned int lookup_entries;
+} plf_rid_job_t;
+/* bytes of scratch one call needs for `njobs` jobs over `sites` sites */
+size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int njobs);
+int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned int lookup_buffer_size,
+                     const plf_rid_job_t * d_jobs, unsigned int first_job, unsigned int njobs,
+                     unsigned long long * d_lookup_pool, unsigned int tag,
+                     unsigned int * d_node_ids, unsigned int * d_raw_ids, void * d_scratch);
+/* pair list of a gathering op: out[2n] / out[2n+1] = entry of the left / right child that parent entry n
+ * reads (parent_id_site, left_site_id, right_site_id may each be NULL = identity) */
+typedef struct plf_pair_job
+{
+  const unsigned int * parent_id_site;
+  const unsigned int * left_site_id;
+  const unsigned int * right_site_id;
+  unsigned int * out;
+  unsigned int entries;
+} plf_pair_job_t;
+int plf_repeats_pairs(plf_ctx_t * ctx, const plf_pair_job_t * h_jobs, unsigned int njobs);
+
 /* tip CLV from a sequence of state characters: entry n (site id_site[n] when
  * repeats compress the tip) gets bit j of map[seq[site]] replicated over rates
  * (src/pll.c:959-1024) */
@@ -232,6 +270,10 @@ int plf_tip_clv_from_states(plf_ctx_t * ctx, const plf_shape_t * sh,
                             const unsigned long long * d_map,
                             const unsigned int * d_id_site,
                             unsigned int entries);
+/* pattern-tip codes from raw characters: d_out[s] = low byte of d_lut[d_seq[s]], *d_first_bad = first site
+ * whose lut entry has bit 8 set (0xFFFFFFFF: none).  Both byte buffers carry 16 bytes of slack. */
+int plf_tip_map(plf_ctx_t * ctx, const unsigned char * d_seq, const unsigned short * d_lut,
+                unsigned int sites, unsigned char * d_out, unsigned int * d_first_bad);
 /* keys[s] = charmap[seq[s]] (tip class codes for plf_repeats_ids with
  * d_site_id_right == NULL, where the key is the left identifier itself) */
 int plf_tip_keys(plf_ctx_t * ctx, const unsigned char * d_seq,

@@ -25,7 +25,7 @@ struct plf_ctx
   int dna_cherry_items;           /* PLF_CHERRY_ITEMS: 2 (default) or 4 (site, rate) blocks per thread and tile */
   int dna_cherry;                 /* PLF_VIRTUAL_CHERRIES=0 writes every tip-tip parent to HBM */
   int dna_tt_bulk_occupancy[4];
-  int dna_balanced_occupancy[6];
+  int dna_balanced_occupancy[2][6]; /* [three id arrays, pair list][log2 rates] */
   int dna_stream;          /* -1 = read PLF_DNA_STREAM / PLF_DNA_STAGES on first use */
   int dna_stages;
   size_t aa_smem_set[2];
@@ -82,7 +82,7 @@ int plf_launch_aa_mma_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned
                             const unsigned long long * d_tipmap, unsigned int maxstates, int contiguous);
 int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int kind,
                          unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous,
-                         const unsigned int * d_tile_prefix, unsigned int total_tiles);
+                         const unsigned int * d_tile_prefix, unsigned int total_tiles, int pair_lists = 0);
 unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats);
 
 /* 4-state fast paths (plf_edge_dna.cu); the lk/derivative ones return -1 when the call is not eligible */

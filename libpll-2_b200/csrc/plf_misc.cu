@@ -41,6 +41,55 @@ extern "C" int plf_tip_clv_from_states(plf_ctx_t * ctx, const plf_shape_t * sh, 
   return 1;
 }
 
+/* ---- pattern-tip codes from raw characters (src/pll.c:875-957) -------------- *
+ * out[s] = low byte of lut[seq[s]]; bit 8 of a lut entry marks a character the caller's map does not know:  *
+ * the smallest such site goes to *first_bad.  16 characters per thread and step.                            */
+__global__ void k_tip_map(const unsigned char * __restrict__ seq, const unsigned short * __restrict__ lut,
+                          unsigned int sites, unsigned char * __restrict__ out, unsigned int * __restrict__ first_bad)
+{
+  __shared__ unsigned short s_lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const unsigned int chunks = (sites + 15) >> 4; /* both buffers carry >= 16 bytes of slack */
+  unsigned int bad = 0xFFFFFFFFu;
+  for (unsigned int c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += gridDim.x * blockDim.x)
+  {
+    const uint4 in = reinterpret_cast<const uint4 *>(seq)[c];
+    const unsigned int w[4] = {in.x, in.y, in.z, in.w};
+    unsigned int o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      unsigned int acc = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+      {
+        const unsigned int v = s_lut[(w[k] >> (8 * b)) & 255u];
+        const unsigned int site = c * 16 + k * 4 + b;
+        if ((v & 0x100u) && site < sites && site < bad) bad = site;
+        acc |= (v & 255u) << (8 * b);
+      }
+      o[k] = acc;
+    }
+    reinterpret_cast<uint4 *>(out)[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (bad != 0xFFFFFFFFu) atomicMin(first_bad, bad);
+}
+
+extern "C" int plf_tip_map(plf_ctx_t * ctx, const unsigned char * d_seq, const unsigned short * d_lut,
+                           unsigned int sites, unsigned char * d_out, unsigned int * d_first_bad)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaMemsetAsync(d_first_bad, 0xFF, sizeof(unsigned int), ctx->stream));
+  unsigned int blocks = ((sites + 15) / 16 + 255) / 256;
+  if (blocks > (unsigned int)ctx->sm_count * 8) blocks = (unsigned int)ctx->sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  k_tip_map<<<blocks, 256, 0, ctx->stream>>>(d_seq, d_lut, sites, d_out, d_first_bad);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
 /* ---- invariant sites ------------------------------------------------------ */
 __global__ void k_invariant(int * __restrict__ out, unsigned int sites, unsigned int tips,
                             const unsigned char * const * __restrict__ tipchars,
@@ -270,6 +319,233 @@ extern "C" int plf_repeats_ids(plf_ctx_t * ctx, unsigned int sites, const unsign
   job.ids_left = ids_left;
   job.lookup_offset = 0;
   return plf_repeats_ids_batch(ctx, sites, &job, 1, d_lookup, h_ids);
+}
+
+/* ---- identifiers of a whole operation list, no host round trip per level ------------------------- *
+ * Same numbering as above (first occurrence order), with                                              *
+ *   - the enable rule of pll_default_enable_repeats (src/repeats.c:100-110) evaluated by every block   *
+ *     of a job from the children's class counts, which the previous level left in d_node_ids;          *
+ *   - 64-bit lookup entries (tag << 32 | first site): a pass uses a tag smaller than every tag used    *
+ *     before, so atomicMin replaces whatever an earlier pass left and nothing has to be cleaned.       */
+struct RidCtx
+{
+  bool enabled;
+  unsigned int ids_left;
+  const unsigned int * idl;
+  const unsigned int * idr;
+  unsigned long long * lookup;
+};
+
+__device__ __forceinline__ RidCtx rid_ctx(const plf_rid_job_t & jb, unsigned int sites, unsigned int lookup_size,
+                                          const unsigned int * __restrict__ node_ids,
+                                          unsigned long long * __restrict__ pool)
+{
+  RidCtx c;
+  const unsigned long long nl = node_ids[jb.left], nr = node_ids[jb.right];
+  const unsigned long long pairs = nl * nr;
+  c.enabled = pairs && pairs < (unsigned long long)lookup_size && nl <= sites / 2 && nr <= sites / 2 &&
+              pairs <= jb.lookup_entries;
+  c.ids_left = (unsigned int)nl;
+  c.idl = jb.site_id_left;
+  c.idr = jb.site_id_right;
+  c.lookup = pool + jb.lookup_offset;
+  return c;
+}
+#define RID_KEY(c, s) ((c).idl[(s)] + (c).idr[(s)] * (c).ids_left)
+
+__global__ void k_rid_min(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
+                          const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+                          unsigned int tag)
+{
+  const RidCtx c = rid_ctx(jobs[blockIdx.y], sites, lookup_size, node_ids, pool);
+  if (!c.enabled) return;
+  const unsigned long long hi = (unsigned long long)tag << 32;
+  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+    atomicMin(&c.lookup[RID_KEY(c, s)], hi | s);
+}
+
+__global__ void k_rid_count(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
+                            const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+                            unsigned int * __restrict__ tile_count_all, unsigned int ntiles)
+{
+  const RidCtx c = rid_ctx(jobs[blockIdx.y], sites, lookup_size, node_ids, pool);
+  if (!c.enabled) return;
+  __shared__ unsigned int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const unsigned int base = blockIdx.x * SCAN_TILE;
+  unsigned int mine = 0;
+  for (unsigned int s = base + threadIdx.x; s < base + SCAN_TILE && s < sites; s += blockDim.x)
+    mine += ((unsigned int)c.lookup[RID_KEY(c, s)] == s);
+  atomicAdd(&cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_count_all[(size_t)blockIdx.y * ntiles + blockIdx.x] = cnt;
+}
+
+/* exclusive scan of a job's tile counts; the class count goes to raw_ids[job] and, with the reference's
+ * "no compression => 0" rule (src/repeats.c:366-372), to node_ids[parent] */
+__global__ void k_rid_scan(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
+                           unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+                           unsigned int * __restrict__ tile_count_all, unsigned int ntiles,
+                           unsigned int * __restrict__ raw_ids)
+{
+  const plf_rid_job_t jb = jobs[blockIdx.y];
+  const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
+  __shared__ unsigned int buf[1024];
+  __shared__ unsigned int carry;
+  if (!c.enabled)
+  {
+    if (threadIdx.x == 0)
+    {
+      raw_ids[blockIdx.y] = 0;
+      node_ids[jb.parent] = 0;
+    }
+    return;
+  }
+  unsigned int * tile_count = tile_count_all + (size_t)blockIdx.y * ntiles;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (unsigned int base = 0; base < ntiles; base += 1024)
+  {
+    const unsigned int i = base + threadIdx.x;
+    const unsigned int v = i < ntiles ? tile_count[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (unsigned int o = 1; o < 1024; o <<= 1)
+    {
+      unsigned int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_count[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    raw_ids[blockIdx.y] = carry;
+    /* the children's counts were read by every block of this job's earlier kernels; later levels read this */
+    node_ids[jb.parent] = carry >= sites ? 0u : carry;
+  }
+}
+
+/* NOTE: k_rid_rank / k_rid_assign run after k_rid_scan has overwritten node_ids[parent]; a job never has its
+ * own parent as a child (the host falls back to the per-op path for lists that recycle buffers), so the
+ * enable rule still sees the children's counts. */
+__global__ void k_rid_rank(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
+                           const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+                           const unsigned int * __restrict__ tile_count_all, unsigned int ntiles,
+                           unsigned int * __restrict__ rank_all)
+{
+  const plf_rid_job_t jb = jobs[blockIdx.y];
+  const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
+  if (!c.enabled) return;
+  const unsigned int * tile_offset = tile_count_all + (size_t)blockIdx.y * ntiles;
+  unsigned int * rank_of_site = rank_all + (size_t)blockIdx.y * sites;
+  __shared__ unsigned int buf[SCAN_TILE];
+  const unsigned int s = blockIdx.x * SCAN_TILE + threadIdx.x;
+  const unsigned int f = (s < sites) ? ((unsigned int)c.lookup[RID_KEY(c, s)] == s) : 0u;
+  buf[threadIdx.x] = f;
+  __syncthreads();
+  for (unsigned int o = 1; o < SCAN_TILE; o <<= 1)
+  {
+    unsigned int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+    __syncthreads();
+    buf[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (f)
+  {
+    const unsigned int r = tile_offset[blockIdx.x] + buf[threadIdx.x] - 1;
+    rank_of_site[s] = r;
+    jb.id_site_parent[r] = s;
+  }
+}
+
+__global__ void k_rid_assign(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
+                             const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+                             const unsigned int * __restrict__ rank_all)
+{
+  const plf_rid_job_t jb = jobs[blockIdx.y];
+  const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
+  if (!c.enabled) return;
+  const unsigned int * rank_of_site = rank_all + (size_t)blockIdx.y * sites;
+  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+    jb.site_id_parent[s] = rank_of_site[(unsigned int)c.lookup[RID_KEY(c, s)]];
+}
+
+extern "C" size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int njobs)
+{
+  const size_t ntiles = ((size_t)sites + SCAN_TILE - 1) / SCAN_TILE;
+  return (size_t)njobs * (ntiles + sites) * sizeof(unsigned int) + 64;
+}
+
+extern "C" int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned int lookup_buffer_size,
+                                const plf_rid_job_t * d_jobs, unsigned int first_job, unsigned int njobs,
+                                unsigned long long * d_lookup_pool, unsigned int tag, unsigned int * d_node_ids,
+                                unsigned int * d_raw_ids, void * d_scratch)
+{
+  if (!njobs) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  const unsigned int ntiles = (sites + SCAN_TILE - 1) / SCAN_TILE;
+  unsigned int * tile = (unsigned int *)d_scratch;
+  unsigned int * rank = tile + (size_t)njobs * ntiles;
+  const plf_rid_job_t * jobs = d_jobs + first_job;
+  unsigned int blocks = (sites + 255) / 256;
+  const unsigned int cap = (unsigned int)ctx->sm_count * 8;
+  const unsigned int share = cap / njobs > 4 ? cap / njobs : 4; /* one wave over the whole batch */
+  if (blocks > share) blocks = share;
+  const dim3 gs(blocks, njobs), gt(ntiles, njobs);
+  k_rid_min<<<gs, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tag);
+  k_rid_count<<<gt, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile, ntiles);
+  k_rid_scan<<<dim3(1, njobs), 1024, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile,
+                                                       ntiles, d_raw_ids + first_job);
+  k_rid_rank<<<gt, SCAN_TILE, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile, ntiles,
+                                               rank);
+  k_rid_assign<<<gs, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, rank);
+  for (int i = 0; i < 5; ++i) plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
+/* pair lists of gathering ops (see plf_backend.h): one launch for the whole batch */
+__global__ void k_rep_pairs(const plf_pair_job_t * __restrict__ jobs)
+{
+  const plf_pair_job_t jb = jobs[blockIdx.y];
+  for (unsigned int n = blockIdx.x * blockDim.x + threadIdx.x; n < jb.entries; n += gridDim.x * blockDim.x)
+  {
+    const unsigned int site = jb.parent_id_site ? jb.parent_id_site[n] : n;
+    uint2 v;
+    v.x = jb.left_site_id ? jb.left_site_id[site] : site;
+    v.y = jb.right_site_id ? jb.right_site_id[site] : site;
+    reinterpret_cast<uint2 *>(jb.out)[n] = v;
+  }
+}
+
+extern "C" int plf_repeats_pairs(plf_ctx_t * ctx, const plf_pair_job_t * h_jobs, unsigned int njobs)
+{
+  if (!njobs) return 1;
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  plf_pair_job_t * d_jobs = (plf_pair_job_t *)plf_ws_reserve(ctx, &ctx->ws_partial, (size_t)njobs * sizeof(plf_pair_job_t));
+  if (!d_jobs) return 0;
+  PLF_CHECK(ctx, cudaMemcpyAsync(d_jobs, h_jobs, (size_t)njobs * sizeof(plf_pair_job_t), cudaMemcpyHostToDevice, ctx->stream));
+  unsigned int max_entries = 0;
+  for (unsigned int i = 0; i < njobs; ++i)
+    if (h_jobs[i].entries > max_entries) max_entries = h_jobs[i].entries;
+  for (unsigned int first = 0; first < njobs; first += PLF_MAX_RUN_OPS)
+  {
+    const unsigned int n = njobs - first < PLF_MAX_RUN_OPS ? njobs - first : PLF_MAX_RUN_OPS;
+    unsigned int blocks = (max_entries + 255) / 256;
+    const unsigned int share = ((unsigned int)ctx->sm_count * 8) / n > 2 ? ((unsigned int)ctx->sm_count * 8) / n : 2;
+    if (blocks > share) blocks = share;
+    if (blocks < 1) blocks = 1;
+    k_rep_pairs<<<dim3(blocks, n), 256, 0, ctx->stream>>>(d_jobs + first);
+    plf_count_launch();
+  }
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
 }
 
 /* keys[s] = class code of the tip character at site s (repeats.c:204-216) */

@@ -499,8 +499,11 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
             prefix_used += (j - i) + 1;
           }
         }
+        int pair_lists = !contiguous;
+        for (unsigned int k = i; k < j && pair_lists; ++k) pair_lists = h_ops[k].pair_list != nullptr;
         if (run_sites && !plf_launch_dna_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
-                                               sh->per_rate_scalers, run_sites, contiguous, d_run_prefix, total_tiles))
+                                               sh->per_rate_scalers, run_sites, contiguous, d_run_prefix, total_tiles,
+                                               pair_lists))
         {
           free(h_prefix);
           return 0;

@@ -351,6 +351,142 @@ k_clv_dna_ii_balanced_sm(const plf_op_t * __restrict__ ops, int per_rate_and_nop
   }
 }
 
+/* The tile walk once more, for ops that carry a PAIR LIST (plf_op_t::pair_list, written once per identifier
+ * update by k_rep_pairs): entry n of the parent reads entry pair[n].x of the left and pair[n].y of the right
+ * child.  The chain class -> site -> child class -> CLV block of resolve_site() (three dependent loads, the
+ * first two of them 4-byte gathers) becomes ONE coalesced 8-byte load, and that load is issued one step ahead:
+ * while the CLV blocks of the current items are in flight the pairs of the next items arrive, so every step
+ * waits for a single level of gathers. */
+template <int LOG2R, int U, int CTAS>
+__global__ void __launch_bounds__(DNA_THREADS, CTAS)
+k_clv_dna_ii_pairs(const plf_op_t * __restrict__ ops, int per_rate_and_nops,
+                   const unsigned int * __restrict__ tile_prefix)
+{
+  constexpr int R = 1 << LOG2R;
+  constexpr unsigned int TILE_SITES = (DNA_THREADS * 4) >> LOG2R;
+  constexpr unsigned int PASS = DNA_THREADS >> LOG2R;
+  constexpr unsigned int PARTS = 4 / U;
+  constexpr int MS = 18;
+  __shared__ __align__(16) double Ls[R * MS];
+  __shared__ __align__(16) double Rs[R * MS];
+  __shared__ plf_op_t s_op;
+  const int per_rate = per_rate_and_nops & 1;
+  const unsigned int nops = (unsigned int)per_rate_and_nops >> 1;
+  const unsigned int total = tile_prefix[nops];
+  const unsigned int share = (total + gridDim.x - 1) / gridDim.x;
+  const unsigned int lo = blockIdx.x * share;
+  const unsigned int hi = min(lo + share, total);
+  if (lo >= hi) return;
+  const int rate = threadIdx.x & (R - 1);
+  const unsigned int site_in_tile = threadIdx.x >> LOG2R;
+
+  unsigned int cur = 0;
+  {
+    unsigned int a = 0, b = nops;
+    while (b - a > 1)
+    {
+      const unsigned int m = (a + b) >> 1;
+      if (tile_prefix[m] <= lo)
+        a = m;
+      else
+        b = m;
+    }
+    cur = a;
+  }
+  unsigned int next = tile_prefix[cur + 1], first = tile_prefix[cur];
+  bool reload = true;
+  uint2 pr[U];
+  bool have = false; /* pr[] already holds the pairs of the step about to run */
+  for (unsigned int t = lo; t < hi; ++t)
+  {
+    if (t >= next)
+    {
+      do
+        ++cur;
+      while (t >= tile_prefix[cur + 1]);
+      next = tile_prefix[cur + 1];
+      first = tile_prefix[cur];
+      reload = true;
+    }
+    if (reload)
+    {
+      __syncthreads();
+      if (threadIdx.x == 0) s_op = ops[cur];
+      {
+        const plf_op_t & o = ops[cur];
+        for (int i = threadIdx.x; i < R * 16; i += DNA_THREADS)
+        {
+          Ls[(i >> 4) * MS + (i & 15)] = o.left_matrix[i];
+          Rs[(i >> 4) * MS + (i & 15)] = o.right_matrix[i];
+        }
+      }
+      __syncthreads();
+      reload = false;
+      have = false;
+    }
+    const plf_op_t & op = s_op;
+    const uint2 * __restrict__ pairs = reinterpret_cast<const uint2 *>(op.pair_list);
+    const double * Lm = Ls + rate * MS;
+    const double * Rm = Rs + rate * MS;
+    for (unsigned int part = 0; part < PARTS; ++part)
+    {
+      const unsigned int base = (t - first) * TILE_SITES + part * U * PASS;
+      SiteRef s[U];
+      dbl4 l[U], r[U];
+      unsigned int sc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        s[u].n = base + u * PASS + site_in_tile;
+        s[u].active = s[u].n < op.nsites;
+        if (!have) pr[u] = s[u].active ? __ldg(pairs + s[u].n) : make_uint2(0, 0);
+        s[u].lid = pr[u].x;
+        s[u].rid = pr[u].y;
+        l[u] = r[u] = dbl4{0, 0, 0, 0};
+        sc[u] = 0;
+        if (s[u].active)
+        {
+          l[u] = ld256_stream(op.left_clv + ((size_t)s[u].lid * R + rate) * 4);
+          r[u] = ld256_stream(op.right_clv + ((size_t)s[u].rid * R + rate) * 4);
+          if (op.parent_scaler)
+          {
+            if (per_rate)
+              sc[u] = (op.left_scaler ? op.left_scaler[(size_t)s[u].lid * R + rate] : 0u) +
+                      (op.right_scaler ? op.right_scaler[(size_t)s[u].rid * R + rate] : 0u);
+            else if (rate == 0)
+              sc[u] = (op.left_scaler ? op.left_scaler[s[u].lid] : 0u) + (op.right_scaler ? op.right_scaler[s[u].rid] : 0u);
+          }
+        }
+      }
+      /* the pairs of the next step of the SAME op, while the CLV blocks above are on their way */
+      {
+        const bool same_tile = part + 1 < PARTS;
+        const unsigned int nbase = same_tile ? base + U * PASS : (t + 1 - first) * TILE_SITES;
+        have = same_tile || (t + 1 < hi && t + 1 < next);
+        if (have)
+        {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+          {
+            const unsigned int nn = nbase + u * PASS + site_in_tile;
+            pr[u] = nn < op.nsites ? __ldg(pairs + nn) : make_uint2(0, 0);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        dbl4 v;
+        v.x = dot4_pairwise(Lm + 0, l[u]) * dot4_pairwise(Rm + 0, r[u]);
+        v.y = dot4_pairwise(Lm + 4, l[u]) * dot4_pairwise(Rm + 4, r[u]);
+        v.z = dot4_pairwise(Lm + 8, l[u]) * dot4_pairwise(Rm + 8, r[u]);
+        v.w = dot4_pairwise(Lm + 12, l[u]) * dot4_pairwise(Rm + 12, r[u]);
+        scale_and_store<LOG2R>(op, s[u], rate, per_rate, sc[u], v);
+      }
+    }
+  }
+}
+
 /* ---- tip-inner (the tip is "left") --------------------------------------------- */
 template <int LOG2R, int U>
 __global__ void __launch_bounds__(DNA_THREADS, 4)
@@ -954,7 +1090,7 @@ unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats)
 
 int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nops, unsigned int kind,
                          unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous,
-                         const unsigned int * d_tile_prefix, unsigned int total_tiles)
+                         const unsigned int * d_tile_prefix, unsigned int total_tiles, int pair_lists)
 {
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
@@ -1093,7 +1229,17 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
         case 4: kb = k_clv_dna_ii_balanced_sm<4, 2, 8>; break;
         default: kb = k_clv_dna_ii_balanced_sm<5, 2, 8>; break;
       }
-    int & occ = ctx->dna_balanced_occupancy[log2r];
+    if (pair_lists && ctx->dna_balanced != 9 && ctx->dna_balanced != 8) /* 8: the three-array gather for A/B runs */
+      switch (log2r)
+      {
+        case 0: kb = k_clv_dna_ii_pairs<0, 2, 8>; break;
+        case 1: kb = k_clv_dna_ii_pairs<1, 2, 8>; break;
+        case 2: kb = k_clv_dna_ii_pairs<2, 2, 8>; break;
+        case 3: kb = k_clv_dna_ii_pairs<3, 2, 8>; break;
+        case 4: kb = k_clv_dna_ii_pairs<4, 2, 8>; break;
+        default: kb = k_clv_dna_ii_pairs<5, 2, 8>; break;
+      }
+    int & occ = ctx->dna_balanced_occupancy[pair_lists ? 1 : 0][log2r];
     if (!occ)
     {
       PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, DNA_THREADS, 0));

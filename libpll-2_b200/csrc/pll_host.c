@@ -60,6 +60,15 @@ typedef struct sumtable_slot
   double * asc_host; /* ascertainment bias: host copy of the `states` pseudo-site blocks */
 } sumtable_slot_t;
 
+typedef struct pair_state
+{
+  unsigned int * dev;
+  unsigned int cap, entries;
+  unsigned int c1, c2;
+  unsigned long long vp, v1, v2; /* identifier versions of parent and children the list was built from */
+  int valid;
+} pair_state_t;
+
 typedef struct cherry_state
 {
   unsigned int tip1, tip2;
@@ -112,6 +121,12 @@ typedef struct cuda_partition
   int tip_scratch_busy;        /* its last upload may still be in flight */
   unsigned char * d_seq;
   unsigned long long * d_map;
+  /* pattern-tip codes are formed on the device from the raw characters; the host copies tipchars[] are
+   * brought up to date on request (pll_cuda_host_tipchars) or at once with $PLL_CUDA_TIPCHARS_MIRROR=1 */
+  unsigned char * d_codes;       /* [sites + pseudo-sites] codes of the tip being set */
+  unsigned short * d_tip_lut;    /* 256 entries + the first-illegal-site word behind them */
+  unsigned char * tipchars_stale; /* [tips] */
+  int tipchars_mirror, tip_host_map; /* $PLL_CUDA_TIP_HOST_MAP=1: the round-1 host mapping loop */
 
   /* site repeats: device-canonical identifier arrays */
   unsigned int ** d_site_id;    /* [nodes] -> device [sites]               */
@@ -124,6 +139,21 @@ typedef struct cuda_partition
   unsigned int * d_keys;
   unsigned char * d_rep_charmap;
   int repeats_mirror;
+  /* identifiers of a whole operation list without a host round trip per level (default enable rule) */
+  unsigned int * d_node_ids;              /* [nodes] device copy of pernode_ids */
+  unsigned int * d_raw_ids;               /* [rid_cap] classes found per job */
+  plf_rid_job_t * d_rid_jobs;             /* [rid_cap] */
+  unsigned int rid_cap;
+  unsigned long long * d_lookup64;        /* tagged lookup pool */
+  unsigned long long lookup64_entries;
+  unsigned int rid_tag;                   /* next tag: decreasing, every pass below all earlier ones */
+  void * d_rid_scratch;
+  size_t rid_scratch_bytes;
+  int rid_fast;                           /* $PLL_CUDA_REPEATS_LEVEL_SYNC=1 keeps one host synchronisation per level */
+  /* pair lists of gathering operations (plf_op_t::pair_list) */
+  struct pair_state * pairs;              /* [nodes], by parent */
+  unsigned long long * ids_version;       /* [nodes] bumped whenever a node's identifiers may have changed */
+  unsigned long long ids_clock;
 
   int host_expm1; /* bit-exact P-matrices: expm1 from the host libm */
 
@@ -330,6 +360,15 @@ static void free_repeats(cuda_partition_t * cp)
   free(cp->d_id_site);
   free(cp->id_site_count);
   free(cp->ids_stale);
+  if (cp->pairs)
+    for (i = 0; i < p->nodes; ++i) plf_free(cp->ctx, cp->pairs[i].dev);
+  free(cp->pairs);
+  free(cp->ids_version);
+  plf_free(cp->ctx, cp->d_node_ids);
+  plf_free(cp->ctx, cp->d_raw_ids);
+  plf_free(cp->ctx, cp->d_rid_jobs);
+  plf_free(cp->ctx, cp->d_lookup64);
+  plf_free(cp->ctx, cp->d_rid_scratch);
   plf_free(cp->ctx, cp->d_lookup);
   plf_free(cp->ctx, cp->d_lookup_pool);
   plf_free(cp->ctx, cp->d_keys);
@@ -364,6 +403,8 @@ static void destroy(cuda_partition_t * cp)
     plf_free(cp->ctx, cp->d_persite);
     plf_free(cp->ctx, cp->d_seq);
     plf_free(cp->ctx, cp->d_map);
+    plf_free(cp->ctx, cp->d_codes);
+    plf_free(cp->ctx, cp->d_tip_lut);
     plf_pinned_free(cp->ctx, cp->tip_scratch);
     plf_ctx_destroy(cp->ctx);
   }
@@ -398,6 +439,7 @@ static void destroy(cuda_partition_t * cp)
   free(cp->clv_entries);
   free(cp->scaler_entries);
   free(cp->asc_sc);
+  free(cp->tipchars_stale);
   free(cp->sumtabs);
   free(cp->evicted_keys);
   free(cp->cherry);
@@ -452,7 +494,12 @@ static int repeats_initialize(cuda_partition_t * cp)
   }
   cp->d_keys = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->sites * sizeof(unsigned int), 0);
   cp->d_rep_charmap = (unsigned char *)plf_alloc(cp->ctx, PLL_ASCII_SIZE, 0);
-  if (!cp->d_keys || !cp->d_rep_charmap) return PLL_FAILURE;
+  cp->d_node_ids = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->nodes * sizeof(unsigned int), 1);
+  cp->pairs = (pair_state_t *)calloc(p->nodes, sizeof(pair_state_t));
+  cp->ids_version = (unsigned long long *)calloc(p->nodes, sizeof(unsigned long long));
+  cp->rid_fast = !env_flag("PLL_CUDA_REPEATS_LEVEL_SYNC");
+  cp->rid_tag = 0xFFFFFFFEu;
+  if (!cp->d_keys || !cp->d_rep_charmap || !cp->d_node_ids || !cp->pairs || !cp->ids_version) return PLL_FAILURE;
   /* the first traversal sizes every CLV and scaler to its class count (~2 allocations per node): warm the
    * pool with a quarter of the uncompressed CLV volume so that they do not each grow it through the driver */
   plf_pool_reserve(cp->ctx, (size_t)p->nodes * p->sites * p->rate_cats * p->states_padded * sizeof(double) / 4);
@@ -536,6 +583,8 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
   cp->shape.per_rate_scalers = (attributes & PLL_ATTRIB_RATE_SCALERS) ? 1 : 0;
   cp->host_expm1 = !env_flag("PLL_CUDA_DEVICE_EXPM1");
   cp->sumtable_mirror = env_flag("PLL_CUDA_SUMTABLE_MIRROR");
+  cp->tipchars_mirror = env_flag("PLL_CUDA_TIPCHARS_MIRROR");
+  cp->tip_host_map = env_flag("PLL_CUDA_TIP_HOST_MAP");
   cp->repeats_mirror = env_flag("PLL_CUDA_REPEATS_MIRROR");
   cp->weights_dirty = 1;
 
@@ -818,6 +867,7 @@ PLL_EXPORT int pll_update_repeats_tips(pll_partition_t * partition, unsigned int
     return cuda_fail(cp);
   r->pernode_ids[tip_index] = ids;
   cp->id_site_count[tip_index] = ids;
+  cp->ids_version[tip_index] = ++cp->ids_clock;
 
   free(r->pernode_id_site[tip_index]);
   r->pernode_id_site[tip_index] = (unsigned int *)malloc((size_t)(ids ? ids : 1) * sizeof(unsigned int));
@@ -846,6 +896,7 @@ static void repeats_finish_op(cuda_partition_t * cp, const pll_operation_t * op,
   const unsigned int parent = op->parent_clv_index;
   unsigned int sites_to_alloc = ids ? ids : partition->sites;
   r->pernode_ids[parent] = ids;
+  cp->ids_version[parent] = ++cp->ids_clock;
   if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = ids;
   if (ids) cp->ids_stale[parent] = 1;
   r->reallocate_repeats(partition, parent, op->parent_scaler_index, sites_to_alloc);
@@ -1005,6 +1056,206 @@ done:
   free(jobs);
   free(job_op);
   free(ids);
+  return ok;
+}
+
+/* The same without a host round trip per level, when the enable rule is the library's own
+ * (pll_default_enable_repeats or pll_no_enable_repeats): the rule is three integer compares on the
+ * children's class counts (src/repeats.c:100-110), which the device has as soon as the level below is
+ * numbered.  All levels are queued back to back; every job gets a slice of the tagged lookup pool as large
+ * as the rule can ever ask for, min(upper bound of ids(left) * ids(right), lookup_buffer_size); the host
+ * reads all class counts back ONCE at the end and then sizes CLVs, scalers and the host mirrors
+ * (reallocate_repeats, in operation order as the reference calls it). */
+#define RID_POOL_MAX_ENTRIES ((unsigned long long)1 << 29) /* 4 GiB of 64-bit entries */
+static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+{
+  pll_partition_t * partition = &cp->pub;
+  pll_repeats_t * r = partition->repeats;
+  const unsigned int sites = partition->sites;
+  const unsigned long long lsize = r->lookup_buffer_size ? r->lookup_buffer_size : PLL_REPEATS_LOOKUP_SIZE;
+  unsigned int i, nlevels;
+  unsigned int * level = NULL, * order = NULL, * start = NULL, * raw = NULL, * ub = NULL;
+  plf_rid_job_t * jobs = NULL;
+  unsigned long long need_pool = 0;
+  unsigned int max_jobs_ws;
+  int nl, ok = 0;
+  if (!r->lookup_buffer_size) r->lookup_buffer_size = PLL_REPEATS_LOOKUP_SIZE;
+
+  if (r->enable_repeats == pll_no_enable_repeats)
+  {
+    for (i = 0; i < count; ++i) repeats_finish_op(cp, ops + i, 0);
+    return 1;
+  }
+  level = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  order = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  start = (unsigned int *)calloc((size_t)count + 2, sizeof(unsigned int));
+  raw = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  ub = (unsigned int *)malloc((size_t)partition->nodes * sizeof(unsigned int));
+  jobs = (plf_rid_job_t *)malloc((size_t)count * sizeof(plf_rid_job_t));
+  nl = (level && order && start && raw && ub && jobs) ? pll_cuda_schedule_levels(ops, count, level) : -1;
+  if (nl < 0)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+    goto done;
+  }
+  nlevels = (unsigned int)nl;
+  for (i = 0; i < count; ++i) start[level[i] + 1]++;
+  for (i = 0; i < nlevels; ++i) start[i + 1] += start[i];
+  {
+    unsigned int * cursor = (unsigned int *)malloc(((size_t)nlevels + 1) * sizeof(unsigned int));
+    if (!cursor) goto done;
+    memcpy(cursor, start, ((size_t)nlevels + 1) * sizeof(unsigned int));
+    for (i = 0; i < count; ++i) order[cursor[level[i]]++] = i;
+    free(cursor);
+  }
+  /* jobs in level order; upper bounds of the class counts give the lookup slices */
+  for (i = 0; i < partition->nodes; ++i) ub[i] = r->pernode_ids[i];
+  for (i = 0; i < count; ++i)
+  {
+    const pll_operation_t * op = ops + order[i];
+    const unsigned int left = op->child1_clv_index, right = op->child2_clv_index, parent = op->parent_clv_index;
+    unsigned long long pairs = (unsigned long long)ub[left] * ub[right];
+    if (pairs > lsize) pairs = lsize;
+    jobs[i].site_id_left = cp->d_site_id[left];
+    jobs[i].site_id_right = cp->d_site_id[right];
+    jobs[i].site_id_parent = cp->d_site_id[parent];
+    jobs[i].id_site_parent = cp->d_id_site[parent];
+    jobs[i].left = left;
+    jobs[i].right = right;
+    jobs[i].parent = parent;
+    jobs[i].lookup_entries = (unsigned int)pairs;
+    jobs[i].lookup_offset = 0;
+    ub[parent] = pairs < sites ? (unsigned int)pairs : sites;
+  }
+  /* pool: the widest level, capped; levels that need more run in several parts */
+  for (i = 0; i < nlevels; ++i)
+  {
+    unsigned long long sum = 0;
+    unsigned int k;
+    for (k = start[i]; k < start[i + 1]; ++k) sum += jobs[k].lookup_entries;
+    if (sum > need_pool) need_pool = sum;
+  }
+  if (need_pool > RID_POOL_MAX_ENTRIES) need_pool = RID_POOL_MAX_ENTRIES;
+  if (need_pool < lsize) need_pool = lsize;
+  if (cp->lookup64_entries < need_pool)
+  {
+    plf_free(cp->ctx, cp->d_lookup64);
+    cp->lookup64_entries = 0;
+    cp->d_lookup64 = (unsigned long long *)plf_alloc(cp->ctx, (size_t)need_pool * sizeof(unsigned long long), 0);
+    if (!cp->d_lookup64 || !plf_fill_u32(cp->ctx, (unsigned int *)cp->d_lookup64, EMPTY_ELEMENT, (size_t)need_pool * 2))
+    {
+      cuda_fail(cp);
+      goto done;
+    }
+    cp->lookup64_entries = need_pool;
+    cp->rid_tag = 0xFFFFFFFEu;
+  }
+  if (cp->rid_cap < count)
+  {
+    plf_free(cp->ctx, cp->d_raw_ids);
+    plf_free(cp->ctx, cp->d_rid_jobs);
+    cp->d_raw_ids = (unsigned int *)plf_alloc(cp->ctx, (size_t)count * sizeof(unsigned int), 0);
+    cp->d_rid_jobs = (plf_rid_job_t *)plf_alloc(cp->ctx, (size_t)count * sizeof(plf_rid_job_t), 0);
+    cp->rid_cap = (cp->d_raw_ids && cp->d_rid_jobs) ? count : 0;
+    if (!cp->rid_cap)
+    {
+      cuda_fail(cp);
+      goto done;
+    }
+  }
+  /* scratch: rank arrays of `sites` entries per job of one part */
+  max_jobs_ws = (unsigned int)(REPEATS_BATCH_WS_BYTES / ((size_t)sites * sizeof(unsigned int) + 64));
+  if (max_jobs_ws < 1) max_jobs_ws = 1;
+  if (max_jobs_ws > PLF_MAX_RUN_OPS) max_jobs_ws = PLF_MAX_RUN_OPS;
+  {
+    unsigned int widest = 0;
+    size_t want;
+    for (i = 0; i < nlevels; ++i)
+      if (start[i + 1] - start[i] > widest) widest = start[i + 1] - start[i];
+    if (widest > max_jobs_ws) widest = max_jobs_ws;
+    want = plf_repeats_pass_workspace(sites, widest);
+    if (cp->rid_scratch_bytes < want)
+    {
+      plf_free(cp->ctx, cp->d_rid_scratch);
+      cp->d_rid_scratch = plf_alloc(cp->ctx, want, 0);
+      cp->rid_scratch_bytes = cp->d_rid_scratch ? want : 0;
+      if (!cp->d_rid_scratch)
+      {
+        cuda_fail(cp);
+        goto done;
+      }
+    }
+  }
+  /* slices within each part, then everything is queued */
+  {
+    unsigned int k = 0;
+    for (i = 0; i < nlevels; ++i)
+    {
+      k = start[i];
+      while (k < start[i + 1])
+      {
+        unsigned long long used = 0;
+        unsigned int first = k;
+        while (k < start[i + 1] && k - first < max_jobs_ws && used + jobs[k].lookup_entries <= cp->lookup64_entries)
+        {
+          jobs[k].lookup_offset = used;
+          used += jobs[k].lookup_entries;
+          ++k;
+        }
+        if (k == first) /* cannot happen: one slice never exceeds the pool */
+        {
+          set_error(PLL_ERROR_CUDA, "repeat identifier lookup pool too small%s", NULL);
+          goto done;
+        }
+        /* remember the part boundaries in `level`: level[first] = end of the part that starts at first */
+        level[first] = k;
+      }
+    }
+  }
+  if (!plf_upload_async(cp->ctx, cp->d_node_ids, r->pernode_ids, (size_t)partition->nodes * sizeof(unsigned int)) ||
+      !plf_upload_async(cp->ctx, cp->d_rid_jobs, jobs, (size_t)count * sizeof(plf_rid_job_t)))
+  {
+    cuda_fail(cp);
+    goto done;
+  }
+  for (i = 0; i < count;)
+  {
+    const unsigned int end = level[i];
+    if (cp->rid_tag == 0)
+    {
+      /* tags exhausted (2^32 passes): start over on a clean pool */
+      if (!plf_fill_u32(cp->ctx, (unsigned int *)cp->d_lookup64, EMPTY_ELEMENT, (size_t)cp->lookup64_entries * 2))
+      {
+        cuda_fail(cp);
+        goto done;
+      }
+      cp->rid_tag = 0xFFFFFFFEu;
+    }
+    if (!plf_repeats_pass(cp->ctx, sites, r->lookup_buffer_size, cp->d_rid_jobs, i, end - i, cp->d_lookup64,
+                          cp->rid_tag--, cp->d_node_ids, cp->d_raw_ids, cp->d_rid_scratch))
+    {
+      cuda_fail(cp);
+      goto done;
+    }
+    i = end;
+  }
+  /* the one synchronisation of the identifier update */
+  if (!plf_download(cp->ctx, raw, cp->d_raw_ids, (size_t)count * sizeof(unsigned int)))
+  {
+    cuda_fail(cp);
+    goto done;
+  }
+  /* bookkeeping in the order of the list, as the reference does it */
+  for (i = 0; i < count; ++i) level[order[i]] = raw[i];
+  for (i = 0; i < count; ++i) repeats_finish_op(cp, ops + i, level[i]);
+  ok = 1;
+done:
+  free(level);
+  free(order);
+  free(start);
+  free(raw);
+  free(ub);
+  free(jobs);
   return ok;
 }
 
@@ -1187,6 +1438,89 @@ static int upload_asc_tip_clv(cuda_partition_t * cp, unsigned int tip_index)
   return ok;
 }
 
+/* Pattern-tip codes on the device (src/pll.c:875-957): the raw characters go up as they are (1 byte per
+ * site), one kernel maps them and finds the first character the map does not know, the codes are installed
+ * only when there is none.  The host copy tipchars[tip] is not written here (no reference client reads it;
+ * pll_cuda_host_tipchars() brings it up to date). */
+static int set_pattern_tip_on_device(cuda_partition_t * cp, unsigned int tip_index, const pll_state_t * map,
+                                     const char * sequence)
+{
+  pll_partition_t * partition = &cp->pub;
+  const unsigned int sites = partition->sites;
+  unsigned short lut[PLL_ASCII_SIZE];
+  unsigned int i, bad = EMPTY_ELEMENT;
+  unsigned int * d_flag;
+  if (partition->tipchars)
+    charmap_update(cp, map);
+  else if (!charmap_create(cp, map))
+    return PLL_FAILURE;
+  if (!cp->tipchars_stale) cp->tipchars_stale = (unsigned char *)calloc(partition->tips ? partition->tips : 1, 1);
+  if (!cp->d_codes) cp->d_codes = (unsigned char *)plf_alloc(cp->ctx, (size_t)sites_alloc(partition) + BULK_PAD, 1);
+  if (!cp->d_tip_lut) cp->d_tip_lut = (unsigned short *)plf_alloc(cp->ctx, PLL_ASCII_SIZE * sizeof(unsigned short) + 16, 1);
+  if (!cp->tipchars_stale || !cp->d_codes || !cp->d_tip_lut)
+  {
+    set_error(PLL_ERROR_MEM_ALLOC, "Cannot allocate space for storing tip characters.%s", NULL);
+    return PLL_FAILURE;
+  }
+  d_flag = (unsigned int *)(cp->d_tip_lut + PLL_ASCII_SIZE);
+  for (i = 0; i < PLL_ASCII_SIZE; ++i)
+    lut[i] = map[i] ? (unsigned short)(partition->states == 4 ? (map[i] & 255) : partition->charmap[i]) : ILLEGAL_CHAR;
+  if (!plf_upload_async(cp->ctx, cp->d_tip_lut, lut, sizeof(lut)) ||
+      !plf_upload_async(cp->ctx, cp->d_seq, sequence, sites) ||
+      !plf_tip_map(cp->ctx, cp->d_seq, cp->d_tip_lut, sites, cp->d_codes, d_flag) ||
+      !plf_download(cp->ctx, &bad, d_flag, sizeof(bad)))
+    return cuda_fail(cp);
+  if (bad != EMPTY_ELEMENT)
+  {
+    pll_errno = PLL_ERROR_TIPDATA_ILLEGALSTATE;
+    snprintf(pll_errmsg, 200, "Illegal state code in tip \"%c\"", sequence[bad]);
+    return PLL_FAILURE;
+  }
+  if (!ensure_real_for_tip(cp, tip_index)) return PLL_FAILURE;
+  if (partition->asc_bias_alloc)
+  {
+    /* pseudo-site i: every tip shows state i (src/pll.c:897-905, 935-957) */
+    unsigned char extra[64];
+    if (partition->states == 4)
+      for (i = 0; i < 4; ++i) extra[i] = (unsigned char)(1u << i);
+    else
+    {
+      memset(extra, 0, sizeof(extra));
+      for (i = 0; i < partition->maxstates; ++i)
+      {
+        const pll_state_t state = partition->tipmap[i];
+        if (state && !(state & (state - 1)))
+        {
+          const unsigned int pos = (unsigned int)__builtin_ctzll(state);
+          if (pos < partition->states) extra[pos] = (unsigned char)i;
+        }
+      }
+    }
+    if (!plf_upload_async(cp->ctx, cp->d_codes + sites, extra, partition->states)) return cuda_fail(cp);
+  }
+  if (!plf_copy_d2d(cp->ctx, cp->d_tipchars[tip_index], cp->d_codes, sites_alloc(partition))) return cuda_fail(cp);
+  cp->tipchars_stale[tip_index] = 1;
+  if (cp->tipchars_mirror && !pll_cuda_host_tipchars(partition, tip_index)) return PLL_FAILURE;
+  return PLL_SUCCESS;
+}
+
+/* NEW (additive).  tipchars[tip_index] of a CUDA partition, brought up to date from the device copy. */
+PLL_EXPORT const unsigned char * pll_cuda_host_tipchars(pll_partition_t * partition, unsigned int tip_index)
+{
+  cuda_partition_t * cp = CP(partition);
+  if (!cp || !partition->tipchars || tip_index >= partition->tips) return NULL;
+  if (cp->tipchars_stale && cp->tipchars_stale[tip_index])
+  {
+    if (!plf_download(cp->ctx, partition->tipchars[tip_index], cp->d_tipchars[tip_index], sites_alloc(partition)))
+    {
+      cuda_fail(cp);
+      return NULL;
+    }
+    cp->tipchars_stale[tip_index] = 0;
+  }
+  return partition->tipchars[tip_index];
+}
+
 PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_index, const pll_state_t * map,
                                   const char * sequence)
 {
@@ -1198,13 +1532,17 @@ PLL_EXPORT int pll_set_tip_states(pll_partition_t * partition, unsigned int tip_
     set_error(PLL_ERROR_PARAM_INVALID, "tip index out of range%s", NULL);
     return PLL_FAILURE;
   }
-  /* 4-state pattern tips: the legality check rides on the mapping pass below */
-  if (!((partition->attributes & PLL_ATTRIB_PATTERN_TIP) && partition->states == 4 && !pll_repeats_enabled(partition)) &&
+  /* pattern tips: the legality check rides on the mapping pass (on the device, or the 4-state host loop) */
+  if (!((partition->attributes & PLL_ATTRIB_PATTERN_TIP) && (partition->states == 4 || !cp->tip_host_map) &&
+        !pll_repeats_enabled(partition)) &&
       !check_sequence(partition, map, sequence))
     return PLL_FAILURE;
 
   if (pll_repeats_enabled(partition) && !pll_update_repeats_tips(partition, tip_index, map, sequence))
     return PLL_FAILURE;
+
+  if ((partition->attributes & PLL_ATTRIB_PATTERN_TIP) && !cp->tip_host_map)
+    return set_pattern_tip_on_device(cp, tip_index, map, sequence);
 
   if (partition->attributes & PLL_ATTRIB_PATTERN_TIP)
   {
@@ -1977,6 +2315,61 @@ missing:
   return 0;
 }
 
+/* Pair lists for the gathering operations of a site-repeats list (4 states): entry n of the parent reads
+ * entry pair[n].x / pair[n].y of its children.  A list is kept per parent node and rebuilt only when the
+ * identifiers of the parent or of a child changed, or the node is fed from other children: the traversals
+ * between two identifier updates (update_repeats = 0: branch-length and model optimisation) reuse it. */
+static int attach_pair_lists(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+{
+  const pll_partition_t * p = &cp->pub;
+  plf_pair_job_t * jobs = NULL;
+  unsigned int i, njobs = 0;
+  int ok = 1;
+  if (!cp->pairs || p->states != 4 || env_flag("PLL_CUDA_NO_PAIR_LISTS")) return 1;
+  for (i = 0; i < count; ++i)
+  {
+    plf_op_t * o = cp->h_ops + i;
+    const unsigned int par = ops[i].parent_clv_index, c1 = ops[i].child1_clv_index, c2 = ops[i].child2_clv_index;
+    pair_state_t * ps;
+    if (o->kind != PLF_OP_II || !(o->parent_id_site || o->left_site_id || o->right_site_id)) continue;
+    ps = &cp->pairs[par];
+    if (!(ps->valid && ps->entries == o->nsites && ps->c1 == c1 && ps->c2 == c2 && ps->vp == cp->ids_version[par] &&
+          ps->v1 == cp->ids_version[c1] && ps->v2 == cp->ids_version[c2]))
+    {
+      if (!jobs && !(jobs = (plf_pair_job_t *)malloc((size_t)count * sizeof(plf_pair_job_t)))) return 0;
+      if (ps->cap < o->nsites)
+      {
+        plf_free(cp->ctx, ps->dev);
+        ps->dev = (unsigned int *)plf_alloc(cp->ctx, (size_t)o->nsites * 2 * sizeof(unsigned int), 0);
+        ps->cap = ps->dev ? o->nsites : 0;
+        if (!ps->dev)
+        {
+          ps->valid = 0;
+          ok = 0;
+          break;
+        }
+      }
+      jobs[njobs].parent_id_site = o->parent_id_site;
+      jobs[njobs].left_site_id = o->left_site_id;
+      jobs[njobs].right_site_id = o->right_site_id;
+      jobs[njobs].out = ps->dev;
+      jobs[njobs].entries = o->nsites;
+      ++njobs;
+      ps->entries = o->nsites;
+      ps->c1 = c1;
+      ps->c2 = c2;
+      ps->vp = cp->ids_version[par];
+      ps->v1 = cp->ids_version[c1];
+      ps->v2 = cp->ids_version[c2];
+      ps->valid = 1;
+    }
+    o->pair_list = ps->dev;
+  }
+  if (ok && njobs && !plf_repeats_pairs(cp->ctx, jobs, njobs)) ok = 0;
+  free(jobs);
+  return ok;
+}
+
 static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
 {
   unsigned int i, nlevels, saved_pending = 0;
@@ -2003,6 +2396,11 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
       }
       return 0;
     }
+  if (pll_repeats_enabled(&cp->pub) && !attach_pair_lists(cp, ops, count))
+  {
+    cuda_fail(cp);
+    return 0;
+  }
   nl = pll_cuda_schedule_levels(ops, count, cp->h_level);
   if (nl < 0)
   {
@@ -2044,6 +2442,8 @@ static int reuses_buffers(const pll_operation_t * ops, unsigned int count, unsig
   for (i = 0; i < count && !reuse; ++i)
   {
     if (ops[i].parent_clv_index < nodes && seen[ops[i].parent_clv_index]) reuse = 1;
+    if (ops[i].parent_clv_index == ops[i].child1_clv_index || ops[i].parent_clv_index == ops[i].child2_clv_index)
+      reuse = 1; /* identifiers are numbered in place */
     if (ops[i].parent_clv_index < nodes) seen[ops[i].parent_clv_index] = 1;
     if (ops[i].child1_clv_index < nodes) seen[ops[i].child1_clv_index] = 1;
     if (ops[i].child2_clv_index < nodes) seen[ops[i].child2_clv_index] = 1;
@@ -2075,7 +2475,13 @@ PLL_EXPORT void pll_update_partials_rep(pll_partition_t * partition, const pll_o
     /* identifiers depend on the children's identifiers only, not on CLV
      * values: compute them for the whole list first (one batch of launches
      * and one host synchronisation per level), then run the CLV levels */
-    if (!update_repeats_levels(cp, operations, count)) return;
+    if (cp->rid_fast && (partition->repeats->enable_repeats == pll_default_enable_repeats ||
+                         partition->repeats->enable_repeats == pll_no_enable_repeats))
+    {
+      if (!update_repeats_fast(cp, operations, count)) return;
+    }
+    else if (!update_repeats_levels(cp, operations, count))
+      return;
   }
   launch_levels(cp, operations, count);
 }

@@ -211,6 +211,17 @@ class Engine:
             return out
         return np.ctypeslib.as_array(self.part.pmatrix[idx], shape=(n,)).copy()
 
+    def tipchars(self, tip: int) -> np.ndarray:
+        """Pattern-tip codes of one tip (host copy; the CUDA engine forms them on the device and brings the
+        host array up to date on request)."""
+        if self.lib.is_cuda:
+            ptr = self.lib.pll_cuda_host_tipchars(self.p, tip)
+            if not ptr:
+                raise RuntimeError(f"host_tipchars: {self.lib.errmsg}")
+        else:
+            ptr = self.part.tipchars[tip]
+        return np.ctypeslib.as_array(ptr, shape=(self.sites,)).copy()
+
     def host_array(self, field: str, idx: int, n: int) -> np.ndarray:
         """Host-canonical per-matrix arrays: eigenvecs, inv_eigenvecs, eigenvals, frequencies."""
         return np.ctypeslib.as_array(getattr(self.part, field)[idx], shape=(n,)).copy()

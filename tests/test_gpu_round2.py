@@ -402,3 +402,36 @@ def test_site_sharded_two_ranks_against_reference(reflib, cudalib, tmp_path):
     for k, name in ((1, "d_f"), (2, "dd_f")):
         assert abs(gpu3[k] - ref_slices[k]) <= DERIV_RTOL * max(abs(ref_slices[k]), 1e-3), (name, got)
         assert abs(gpu3[k] - ref_whole[k]) <= DERIV_RTOL * max(abs(ref_whole[k]), 1e-3), (name, got)
+
+
+# ---- pattern-tip codes formed on the device -----------------------------------------------------------------
+
+@pytest.mark.parametrize("kind,sites", [("dna", 1), ("dna", 15), ("dna", 16), ("dna", 4099), ("aa", 333), ("g5", 77)])
+@pytest.mark.parametrize("host_map", ["0", "1"])
+def test_pattern_tip_codes_match_reference(reflib, cudalib, monkeypatch, kind, sites, host_map):
+    """pll_set_tip_states under PLL_ATTRIB_PATTERN_TIP (src/pll.c:875-957): the codes the device forms from the
+    raw characters (and the round-1 host loop, PLL_CUDA_TIP_HOST_MAP=1) against the reference's tipchars[]."""
+    monkeypatch.setenv("PLL_CUDA_TIP_HOST_MAP", host_map)
+    if kind == "dna":
+        ds = synth.dna_dataset(7, sites, seed=5)
+    elif kind == "aa":
+        ds = synth.aa_dataset(7, sites, seed=6)
+    else:
+        ds = synth.generic_dataset(5, 7, sites, seed=7)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP)
+    for t in range(ds.tree.tips):
+        assert np.array_equal(ref.tipchars(t), gpu.tipchars(t)), f"tip {t}"
+    assert ref.part.maxstates == gpu.part.maxstates
+    if sites > 1:
+        traverse(ref, gpu)
+        assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
+    # an illegal character: same failure, same message, the tip keeps its codes
+    bad = bytearray(ds.seqs[2])
+    bad[sites // 2] = ord("!")
+    before = gpu.tipchars(2)
+    for lib, e in ((reflib, ref), (cudalib, gpu)):
+        assert lib.pll_set_tip_states(e.p, 2, e.map, bytes(bad)) == 0
+    assert cudalib.errno == reflib.errno and cudalib.errmsg == reflib.errmsg
+    assert np.array_equal(gpu.tipchars(2), before)
+    ref.close()
+    gpu.close()

@@ -70,7 +70,7 @@ def run_oracle_traversal(orc, eng, block, per_rate):
     tipmap = None
     if pattern_tip:
         for t in range(tips):
-            tipchars[t] = np.ctypeslib.as_array(p.tipchars[t], shape=(S,)).copy()
+            tipchars[t] = eng.tipchars(t)
         tipmap = np.ctypeslib.as_array(p.tipmap, shape=(256,)).copy()
     else:
         for t in range(tips):
