@@ -32,7 +32,8 @@ typedef struct plf_shape
  *   4 TC  left = pattern tip, right = cherry
  *   5 CC  both children cherries
  *   6 TT_VIRTUAL  the cherry itself: only its two P-matrices are snapshot into
- *                 parent_clv[0 .. 2*R*16) -- a side buffer, not the CLV -- and its scaler is zeroed
+ *                 parent_clv[0 .. 2 * R * states * states_padded) -- a side buffer, not the CLV -- and
+ *                 its scaler is zeroed
  * For a cherry child: {left,right}_tip / _tip2 are the codes of its two tips, {left,right}_cm1 / _cm2
  * the snapshots of its two P-matrices, {left,right}_matrix the matrix of the branch above it. */
 enum { PLF_OP_II = 0, PLF_OP_TI = 1, PLF_OP_TT = 2, PLF_OP_CI = 3, PLF_OP_TC = 4, PLF_OP_CC = 5,
@@ -169,8 +170,8 @@ int plf_update_partials_once(plf_ctx_t * ctx, const plf_shape_t * sh,
 /* end of the launch run that starts at op i of a level ending at b (see plf_partials.cu) */
 unsigned int plf_run_end(const plf_op_t * h_ops, unsigned int i, unsigned int b,
                          unsigned int * max_sites, int * contiguous);
-/* 1 when the 4-state streaming kernels that consume virtual cherries serve this shape */
-int plf_virtual_cherries_supported(plf_ctx_t * ctx, const plf_shape_t * sh);
+/* 1 when the streaming kernels that consume virtual cherries serve this shape and this many tip codes */
+int plf_virtual_cherries_supported(plf_ctx_t * ctx, const plf_shape_t * sh, unsigned int maxstates);
 
 /* results: d_out (device, may be NULL) and/or h_out (host, may be NULL; when
  * given the call synchronises the stream) */

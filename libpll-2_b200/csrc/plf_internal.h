@@ -35,6 +35,9 @@ struct plf_ctx
   size_t aam_smem_set[5];  /* [ii, ti, tt, stream ii, stream ti] */
   int aam_occupancy[5];
   int aam_log2r[2];
+  size_t aas_smem_set[5];  /* 20-state streaming kernels [II, TI, CI, TC, CC] */
+  int aas_occupancy[5];
+  int aas_log2r[5];
   int aa_stream;           /* -1 = read PLF_AA_STREAM on first use; 0 keeps contiguous ops on the direct-load DMMA kernel */
   int dna_items;
   int dna_tt_bulk, dna_tt_items, dna_tt_seq, dna_balanced; /* PLF_TT_BULK / PLF_TT_ITEMS / PLF_TT_SEQ / PLF_DNA_BALANCED, read with dna_stream */
@@ -84,6 +87,8 @@ int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned in
                          unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous,
                          const unsigned int * d_tile_prefix, unsigned int total_tiles, int pair_lists = 0);
 unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats);
+int plf_aa_virtual_cherries_supported(plf_ctx * ctx, const struct plf_shape * sh, unsigned int maxstates);
+int plf_dna_virtual_cherries_supported(plf_ctx * ctx, const struct plf_shape * sh);
 
 /* 4-state fast paths (plf_edge_dna.cu); the lk/derivative ones return -1 when the call is not eligible */
 struct plf_lk;

@@ -434,6 +434,17 @@ extern "C" unsigned int plf_run_end(const plf_op_t * h_ops, unsigned int i, unsi
   return j;
 }
 
+/* do the kernels that consume virtual cherries serve this shape (and, for 20 states, this many tip codes)?
+ * The host layer asks before it leaves a tip-tip parent unwritten. */
+extern "C" int plf_virtual_cherries_supported(plf_ctx_t * ctx, const plf_shape_t * sh, unsigned int maxstates)
+{
+  const char * v = getenv("PLF_VIRTUAL_CHERRIES");
+  if (v && v[0] == '0') return 0;
+  if (sh->states == 4) return plf_dna_virtual_cherries_supported(ctx, sh);
+  if (sh->states == 20) return plf_aa_virtual_cherries_supported(ctx, sh, maxstates);
+  return 0;
+}
+
 static int is_pow2(unsigned int x) { return x && !(x & (x - 1)); }
 
 /* queues the launches of a level-sorted op list.  `upload` = 0: the op descriptors and tile-prefix arrays

@@ -305,7 +305,14 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long * bar)
  * rate warps of a site: each warp stores its block unscaled, publishes its flag (`flagbar` mbarrier)
  * and settles the tile one iteration later, when every flag has long arrived: the rare site that
  * scales is rescaled in place by the lanes that stored it. */
-template <int KIND, int LOG2R, int NWARPS>
+/* What a child of a streamed op is: an inner CLV (its tile comes through the ring), a pattern tip (one code
+ * per site, 24-entry table of masked row sums in shared memory: the value of the whole term) or a VIRTUAL
+ * CHERRY (the codes of its two tips; its CLV entry k is hA[codeA][k] * hB[codeB][k] with
+ * the two half tables of the reference's tip-tip kernel, formed in registers as the A fragment of the DMMA
+ * with the matrix of the branch above it -- the same operands the kernel would have read back from HBM). */
+enum { AK_I = 0, AK_T = 1, AK_C = 2 };
+
+template <int LK, int RK, int LOG2R, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 512 / (NWARPS * 32))
 k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_state_t * __restrict__ tipmap,
                     int maxstates)
@@ -314,15 +321,23 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
   constexpr int SB = NWARPS / R;          /* 8-site blocks per tile */
   constexpr int TILE = 8 * SB;            /* sites per tile */
   constexpr int CH_BYTES = TILE * R * 160; /* one child's tile: 5 KB (4 warps) or 10 KB (8 warps) */
-  constexpr int NCH = (KIND == PLF_OP_II) ? 2 : 1;
+  constexpr int NCH = (LK == AK_I ? 1 : 0) + (RK == AK_I ? 1 : 0);
   constexpr int STAGE = NCH * CH_BYTES;
+  constexpr int OFF_LCH = (RK == AK_I) ? CH_BYTES : 0; /* the right child's tile comes first */
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ __align__(8) unsigned long long full[AAS_NSTAGE];
   __shared__ __align__(8) unsigned long long empty[AAS_NSTAGE];
   __shared__ __align__(8) unsigned long long flagbar[2];
   __shared__ int flags[2][TILE][R];
   unsigned char * ring = dyn;
-  double * tl = reinterpret_cast<double *>(dyn + (size_t)AAS_NSTAGE * STAGE); /* TI: [maxstates][R][AAM_TAB_STRIDE] */
+  /* tables behind the ring: tip table of a left tip [maxstates][R][AAM_TAB_STRIDE], then the half tables of
+   * the cherries [maxstates][R][20] each: left tip A, left tip B, right tip A, right tip B */
+  double * tl = reinterpret_cast<double *>(dyn + (size_t)AAS_NSTAGE * STAGE);
+  const int half = maxstates * R * 20;
+  double * hl1 = tl + (LK == AK_T ? maxstates * R * AAM_TAB_STRIDE : 0);
+  double * hl2 = hl1 + (LK == AK_C ? half : 0);
+  double * hr1 = hl2 + (LK == AK_C ? half : 0);
+  double * hr2 = hr1 + (RK == AK_C ? half : 0);
 
   const plf_op_t op = ops[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 3, gs = lane >> 2;
@@ -342,12 +357,31 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     mbar_init(&flagbar[1], NWARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (KIND == PLF_OP_TI)
+  if (LK == AK_T)
   {
     for (int e = threadIdx.x; e < maxstates * R * AAM_TAB_STRIDE; e += blockDim.x)
     {
       const int c = e / (R * AAM_TAB_STRIDE), r = (e / AAM_TAB_STRIDE) % R, i = e % AAM_TAB_STRIDE;
       tl[e] = (i < 20) ? masked_sum_seq(op.left_matrix + r * 400 + i * 20, tipmap[c], 20) : 0.0;
+    }
+  }
+  if (LK == AK_C || RK == AK_C)
+  {
+    /* scalar sums in increasing column order, as the reference's tip-tip table (src/core_partials_avx.c:124-253) */
+    for (int e = threadIdx.x; e < half; e += blockDim.x)
+    {
+      const int c = e / (R * 20), r = (e / 20) % R, i = e % 20;
+      const plf_state_t mask = tipmap[c];
+      if (LK == AK_C)
+      {
+        hl1[e] = masked_sum_seq(op.left_cm1 + r * 400 + i * 20, mask, 20);
+        hl2[e] = masked_sum_seq(op.left_cm2 + r * 400 + i * 20, mask, 20);
+      }
+      if (RK == AK_C)
+      {
+        hr1[e] = masked_sum_seq(op.right_cm1 + r * 400 + i * 20, mask, 20);
+        hr2[e] = masked_sum_seq(op.right_cm2 + r * 400 + i * 20, mask, 20);
+      }
     }
   }
   __syncthreads();
@@ -358,33 +392,54 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     const unsigned int bytes = n * R * 160;
     unsigned char * slot = ring + (size_t)s * STAGE;
     mbar_expect_tx(&full[s], NCH * bytes);
-    if (KIND == PLF_OP_II) bulk_g2s(slot + CH_BYTES, op.left_clv + (size_t)first * span, bytes, &full[s]);
-    bulk_g2s(slot, op.right_clv + (size_t)first * span, bytes, &full[s]);
+    if (LK == AK_I) bulk_g2s(slot + OFF_LCH, op.left_clv + (size_t)first * span, bytes, &full[s]);
+    if (RK == AK_I) bulk_g2s(slot, op.right_clv + (size_t)first * span, bytes, &full[s]);
   };
-  if (threadIdx.x == 0)
+  if (NCH > 0 && threadIdx.x == 0)
   {
     unsigned int t = blockIdx.x;
     for (int s = 0; s < AAS_NSTAGE && t < ntiles; ++s, t += gridDim.x) issue(t, s);
   }
 
   /* B fragments of this warp's rate: lane holds P[8 nt + gs][state(kt, q)] */
-  double bl[KIND == PLF_OP_II ? AAM_FRAGS : 1], br[AAM_FRAGS];
+  double bl[LK != AK_T ? AAM_FRAGS : 1], br[AAM_FRAGS];
 #pragma unroll
   for (int f = 0; f < AAM_FRAGS; ++f)
   {
     const int nt = f / 5, kt = f % 5;
     const int i = 8 * nt + gs, j = aam_state(kt, q);
     br[f] = (i < 20) ? op.right_matrix[rate * 400 + i * 20 + j] : 0.0;
-    if (KIND == PLF_OP_II) bl[f] = (i < 20) ? op.left_matrix[rate * 400 + i * 20 + j] : 0.0;
+    if (LK != AK_T) bl[f] = (i < 20) ? op.left_matrix[rate * 400 + i * 20 + j] : 0.0;
   }
 
   const unsigned int my = sb * 8 + gs; /* site within the tile */
-  unsigned int code_next = 0;
-  if (KIND == PLF_OP_TI && blockIdx.x < ntiles)
-  {
-    const unsigned int n0 = blockIdx.x * TILE + my;
-    code_next = op.left_tip[n0 < op.nsites ? n0 : op.nsites - 1];
-  }
+  /* tip codes of the site this lane works on in the NEXT iteration: left tip / left cherry (2), right cherry (2) */
+  unsigned int cn_l1 = 0, cn_l2 = 0, cn_r1 = 0, cn_r2 = 0;
+  auto fetch_codes = [&](unsigned int t) {
+    const unsigned int n0 = t * TILE + my;
+    const unsigned int nn = n0 < op.nsites ? n0 : op.nsites - 1;
+    if (LK != AK_I) cn_l1 = op.left_tip[nn];
+    if (LK == AK_C) cn_l2 = op.left_tip2[nn];
+    if (RK == AK_C)
+    {
+      cn_r1 = op.right_tip[nn];
+      cn_r2 = op.right_tip2[nn];
+    }
+  };
+  if ((LK != AK_I || RK != AK_I) && blockIdx.x < ntiles) fetch_codes(blockIdx.x);
+
+  /* A fragment of a virtual cherry: entry k = hA[codeA][rate][k] * hB[codeB][rate][k] for the lane's 5 states */
+  auto cherry_frag = [&](double (&a)[5], const double * h1, const double * h2, unsigned int c1, unsigned int c2) {
+    const double * p1 = h1 + ((size_t)c1 * R + rate) * 20;
+    const double * p2 = h2 + ((size_t)c2 * R + rate) * 20;
+    const double2 u0 = *reinterpret_cast<const double2 *>(p1 + 2 * q), w0 = *reinterpret_cast<const double2 *>(p2 + 2 * q);
+    const double2 u1 = *reinterpret_cast<const double2 *>(p1 + 8 + 2 * q), w1 = *reinterpret_cast<const double2 *>(p2 + 8 + 2 * q);
+    a[0] = u0.x * w0.x;
+    a[1] = u0.y * w0.y;
+    a[2] = u1.x * w1.x;
+    a[3] = u1.y * w1.y;
+    a[4] = p1[16 + q] * p2[16 + q];
+  };
 
   /* settle per-site scaling of the tile processed in iteration `itp` (site n_prev, child scalers sc_prev) */
   unsigned int n_prev = 0, sc_prev = 0;
@@ -416,7 +471,7 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     const unsigned int parity = (it / AAS_NSTAGE) & 1u;
     const unsigned char * slot = ring + (size_t)s * STAGE;
     /* producer duty: refill the slot of the previous iteration once every warp has handed it back */
-    if (threadIdx.x == 0 && it > 0)
+    if (NCH > 0 && threadIdx.x == 0 && it > 0)
     {
       const unsigned int tn = t + (unsigned int)(AAS_NSTAGE - 1) * gridDim.x;
       if (tn < ntiles)
@@ -428,39 +483,57 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     }
     const unsigned int n = t * TILE + my;
     const bool act = n < op.nsites;
-    const unsigned int code = code_next;
-    if (KIND == PLF_OP_TI)
-    {
-      const unsigned int nn = (t + gridDim.x) * TILE + my;
-      if (t + gridDim.x < ntiles) code_next = op.left_tip[nn < op.nsites ? nn : op.nsites - 1];
-    }
-    /* child scalers of this site: needed only after the arithmetic */
+    const unsigned int c_l1 = cn_l1, c_l2 = cn_l2, c_r1 = cn_r1, c_r2 = cn_r2;
+    if ((LK != AK_I || RK != AK_I) && t + gridDim.x < ntiles) fetch_codes(t + gridDim.x);
+    /* child scalers of this site: needed only after the arithmetic (tips and cherries have none) */
     unsigned int sc = 0;
     if (op.parent_scaler && act && q == 0 && (per_rate || rate == 0))
     {
       const size_t k = per_rate ? (size_t)n * R + rate : n;
-      if (KIND == PLF_OP_II && op.left_scaler) sc += op.left_scaler[k];
-      if (op.right_scaler) sc += op.right_scaler[k];
+      if (LK == AK_I && op.left_scaler) sc += op.left_scaler[k];
+      if (RK == AK_I && op.right_scaler) sc += op.right_scaler[k];
     }
-    while (!mbar_try_wait(&full[s], parity)) {}
+    if (NCH > 0)
+      while (!mbar_try_wait(&full[s], parity)) {}
 
     double accL[3][2], accR[3][2];
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) accL[nt][0] = accL[nt][1] = accR[nt][0] = accR[nt][1] = 0.0;
-    if (KIND == PLF_OP_II)
+    /* A fragments of both children first (the slot is released before any arithmetic) */
+    double ar[5], al[LK != AK_T ? 5 : 1];
+    if (RK == AK_I)
     {
-      /* both children's A fragments first (the slot is released before any arithmetic), then the two
-       * DMMA chains interleaved: 6 independent accumulators in flight */
       const double * pr = reinterpret_cast<const double *>(slot) + ((size_t)my * R + rate) * 20;
-      const double * pl = reinterpret_cast<const double *>(slot + CH_BYTES) + ((size_t)my * R + rate) * 20;
       const double2 r0 = *reinterpret_cast<const double2 *>(pr + 2 * q);
       const double2 r1 = *reinterpret_cast<const double2 *>(pr + 8 + 2 * q);
+      ar[0] = r0.x; ar[1] = r0.y; ar[2] = r1.x; ar[3] = r1.y;
+      ar[4] = pr[16 + q];
+    }
+    else
+      cherry_frag(ar, hr1, hr2, c_r1, c_r2);
+    if (LK == AK_I)
+    {
+      const double * pl = reinterpret_cast<const double *>(slot + OFF_LCH) + ((size_t)my * R + rate) * 20;
       const double2 l0 = *reinterpret_cast<const double2 *>(pl + 2 * q);
       const double2 l1 = *reinterpret_cast<const double2 *>(pl + 8 + 2 * q);
-      const double ar[5] = {r0.x, r0.y, r1.x, r1.y, pr[16 + q]};
-      const double al[5] = {l0.x, l0.y, l1.x, l1.y, pl[16 + q]};
+      al[0] = l0.x; al[1] = l0.y; al[2] = l1.x; al[3] = l1.y;
+      al[4] = pl[16 + q];
+    }
+    else if (LK == AK_C)
+    {
+      double tmp[5];
+      cherry_frag(tmp, hl1, hl2, c_l1, c_l2);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) al[k] = tmp[k];
+    }
+    if (NCH > 0)
+    {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]); /* this warp is done with the slot */
+    }
+    if (LK != AK_T)
+    {
+      /* the two DMMA chains interleaved: 6 independent accumulators in flight */
 #pragma unroll
       for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
@@ -472,17 +545,11 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     }
     else
     {
-      const double * pr = reinterpret_cast<const double *>(slot) + ((size_t)my * R + rate) * 20;
-      const double2 v0 = *reinterpret_cast<const double2 *>(pr + 2 * q);
-      const double2 v1 = *reinterpret_cast<const double2 *>(pr + 8 + 2 * q);
-      const double a[5] = {v0.x, v0.y, v1.x, v1.y, pr[16 + q]};
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
 #pragma unroll
       for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) dmma(accR[nt], a[kt], br[nt * 5 + kt]);
-      const double * row = tl + ((size_t)code * R + rate) * AAM_TAB_STRIDE + 2 * q;
+        for (int nt = 0; nt < 3; ++nt) dmma(accR[nt], ar[kt], br[nt * 5 + kt]);
+      const double * row = tl + ((size_t)c_l1 * R + rate) * AAM_TAB_STRIDE + 2 * q;
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt)
         if (nt < 2 || q < 2)
@@ -540,6 +607,26 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     act_prev = act;
   }
   if (site_scaling && it > 0) settle(it - 1);
+}
+
+/* a virtual cherry's own "operation" (20 states): snapshot of its two P-matrices into the node's side buffer
+ * (parent_clv), scaler zeroed (src/core_partials.c:82-200 zeroes it too) */
+__global__ void __launch_bounds__(256)
+k_cherry_prepare_aa(const plf_op_t * __restrict__ ops, int per_rate, int R, int msz)
+{
+  const plf_op_t op = ops[blockIdx.y];
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < msz; i += blockDim.x)
+    {
+      op.parent_clv[i] = op.left_matrix[i];
+      op.parent_clv[msz + i] = op.right_matrix[i];
+    }
+  if (!op.parent_scaler) return;
+  const size_t n = per_rate ? (size_t)op.nsites * R : op.nsites;
+  const size_t quads = (n + 3) >> 2; /* the allocation is padded by 16 bytes */
+  uint4 * dst = reinterpret_cast<uint4 *>(op.parent_scaler);
+  for (size_t qd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (size_t)gridDim.x * blockDim.x)
+    dst[qd] = make_uint4(0, 0, 0, 0);
 }
 
 /* ------------------------------------------------------------------------ *
@@ -624,34 +711,63 @@ k_clv_aa_tt(const plf_op_t * __restrict__ ops, int R, int per_rate, const plf_st
 /* returns 1 launched, 0 error, -1 not applicable (caller falls back) */
 typedef void (*aas_kernel_t)(const plf_op_t *, int, const plf_state_t *, int);
 template <int LOG2R, int NWARPS>
-static aas_kernel_t aas_pick(int ii)
+static aas_kernel_t aas_pick(unsigned int kind)
 {
-  return ii ? k_clv_aa_mma_stream<PLF_OP_II, LOG2R, NWARPS> : k_clv_aa_mma_stream<PLF_OP_TI, LOG2R, NWARPS>;
+  switch (kind)
+  {
+    case PLF_OP_II: return k_clv_aa_mma_stream<AK_I, AK_I, LOG2R, NWARPS>;
+    case PLF_OP_TI: return k_clv_aa_mma_stream<AK_T, AK_I, LOG2R, NWARPS>;
+    case PLF_OP_CI: return k_clv_aa_mma_stream<AK_C, AK_I, LOG2R, NWARPS>;
+    case PLF_OP_TC: return k_clv_aa_mma_stream<AK_T, AK_C, LOG2R, NWARPS>;
+    default: return k_clv_aa_mma_stream<AK_C, AK_C, LOG2R, NWARPS>;
+  }
+}
+
+/* dynamic shared memory of the streaming kernel for one op kind: ring + tip table + cherry half tables */
+static size_t aas_smem_bytes(unsigned int kind, unsigned int rate_cats, int nwarps, unsigned int maxstates)
+{
+  const int left_inner = (kind == PLF_OP_II), right_inner = (kind == PLF_OP_II || kind == PLF_OP_TI || kind == PLF_OP_CI);
+  const int left_tip = (kind == PLF_OP_TI || kind == PLF_OP_TC);
+  const int cherries = (kind == PLF_OP_CI || kind == PLF_OP_TC) ? 1 : kind == PLF_OP_CC ? 2 : 0;
+  size_t smem = (size_t)AAS_NSTAGE * (left_inner + right_inner) * 1280 * nwarps;
+  if (left_tip) smem += (size_t)maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);
+  smem += (size_t)cherries * 2 * maxstates * rate_cats * 20 * sizeof(double);
+  return smem;
+}
+
+static int aas_kind_slot(unsigned int kind)
+{
+  switch (kind)
+  {
+    case PLF_OP_II: return 0;
+    case PLF_OP_TI: return 1;
+    case PLF_OP_CI: return 2;
+    case PLF_OP_TC: return 3;
+    default: return 4;
+  }
 }
 
 static int launch_aa_stream(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nops, unsigned int kind,
                             unsigned int rate_cats, int per_rate, unsigned int max_sites,
                             const unsigned long long * d_tipmap, unsigned int maxstates)
 {
-  const int ii = (kind == PLF_OP_II);
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
   const int nwarps = (log2r == 3 || ctx->aa_warps8) ? 8 : 4; /* PLF_AA_WARPS=8: 8-warp CTAs for every rate count */
-  aas_kernel_t k = log2r == 3   ? aas_pick<3, 8>(ii)
-                   : nwarps == 8 ? (log2r == 0 ? aas_pick<0, 8>(ii) : log2r == 1 ? aas_pick<1, 8>(ii) : aas_pick<2, 8>(ii))
-                                 : (log2r == 0 ? aas_pick<0, 4>(ii) : log2r == 1 ? aas_pick<1, 4>(ii) : aas_pick<2, 4>(ii));
-  size_t smem = (size_t)AAS_NSTAGE * (ii ? 2 : 1) * 1280 * nwarps;
-  if (!ii) smem += (size_t)maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);
+  aas_kernel_t k = log2r == 3   ? aas_pick<3, 8>(kind)
+                   : nwarps == 8 ? (log2r == 0 ? aas_pick<0, 8>(kind) : log2r == 1 ? aas_pick<1, 8>(kind) : aas_pick<2, 8>(kind))
+                                 : (log2r == 0 ? aas_pick<0, 4>(kind) : log2r == 1 ? aas_pick<1, 4>(kind) : aas_pick<2, 4>(kind));
+  const size_t smem = aas_smem_bytes(kind, rate_cats, nwarps, maxstates);
   if (smem > ctx->smem_optin) return -1;
-  const int slot = 3 + (ii ? 0 : 1);
-  if (smem > ctx->aam_smem_set[slot] || ctx->aam_log2r[slot - 3] != log2r)
+  const int slot = aas_kind_slot(kind);
+  if (smem > ctx->aas_smem_set[slot] || ctx->aas_log2r[slot] != log2r)
   {
     PLF_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->aam_smem_set[slot] = smem;
-    ctx->aam_log2r[slot - 3] = log2r;
-    ctx->aam_occupancy[slot] = 0;
+    ctx->aas_smem_set[slot] = smem;
+    ctx->aas_log2r[slot] = log2r;
+    ctx->aas_occupancy[slot] = 0;
   }
-  int & occ = ctx->aam_occupancy[slot];
+  int & occ = ctx->aas_occupancy[slot];
   if (!occ)
   {
     PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, nwarps * 32, smem));
@@ -683,11 +799,29 @@ int plf_launch_aa_mma_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
     v = getenv("PLF_AAM_L2PF");
     ctx->aa_l2pf = !(v && v[0] == '0');
   }
+  if (kind == PLF_OP_TT_VIRTUAL)
+  {
+    const unsigned long long entries = (unsigned long long)max_sites * (per_rate ? rate_cats : 1u);
+    unsigned long long bx = (entries / 4 + 255) / 256;
+    const unsigned long long cap = ((unsigned long long)ctx->sm_count * 8 + nops - 1) / nops;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    k_cherry_prepare_aa<<<dim3((unsigned int)bx, nops), 256, 0, ctx->stream>>>(d_ops, per_rate, (int)rate_cats,
+                                                                               (int)rate_cats * 400);
+    plf_count_launch();
+    PLF_CHECK(ctx, cudaGetLastError());
+    return 1;
+  }
   if (kind != PLF_OP_TT && contiguous && ctx->aa_stream &&
       (rate_cats == 1 || rate_cats == 2 || rate_cats == 4 || rate_cats == 8))
   {
     const int rc = launch_aa_stream(ctx, d_ops, nops, kind, rate_cats, per_rate, max_sites, d_tipmap, maxstates);
     if (rc >= 0) return rc;
+  }
+  if (kind == PLF_OP_CI || kind == PLF_OP_TC || kind == PLF_OP_CC)
+  {
+    plf_set_error(ctx, "virtual cherry consumers need the contiguous 20-state streaming path");
+    return 0;
   }
   void (*k)(const plf_op_t *, int, int, const plf_state_t *, int);
   size_t smem;
@@ -735,4 +869,24 @@ int plf_launch_aa_mma_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;
+}
+
+/* do the 20-state streaming kernels serve consumers of virtual cherries for this shape and tip alphabet? */
+int plf_aa_virtual_cherries_supported(plf_ctx * ctx, const plf_shape_t * sh, unsigned int maxstates)
+{
+  if (ctx->aa_stream < 0)
+  {
+    const char * v = getenv("PLF_AA_STREAM");
+    ctx->aa_stream = !(v && v[0] == '0');
+    v = getenv("PLF_AA_WARPS");
+    ctx->aa_warps8 = (v && v[0] == '8');
+    v = getenv("PLF_AAM_L2PF");
+    ctx->aa_l2pf = !(v && v[0] == '0');
+  }
+  if (sh->states != 20 || !ctx->aa_fast || !ctx->aa_mma || !ctx->aa_stream) return 0;
+  if (sh->rate_cats != 1 && sh->rate_cats != 2 && sh->rate_cats != 4 && sh->rate_cats != 8) return 0;
+  const int nwarps = (sh->rate_cats == 8 || ctx->aa_warps8) ? 8 : 4;
+  /* the widest table set (two cherries) must leave room for at least two CTAs per SM */
+  return 2 * (aas_smem_bytes(PLF_OP_CC, sh->rate_cats, nwarps, maxstates) + 2048) <= ctx->smem_optin &&
+         2 * (aas_smem_bytes(PLF_OP_CI, sh->rate_cats, nwarps, maxstates) + 2048) <= ctx->smem_optin;
 }

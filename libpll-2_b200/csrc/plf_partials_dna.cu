@@ -1296,10 +1296,10 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
 
 /* do the kernels that consume virtual cherries serve this shape? (the host layer asks before it leaves a
  * tip-tip parent unwritten) */
-extern "C" int plf_virtual_cherries_supported(plf_ctx_t * ctx, const plf_shape_t * sh)
+int plf_dna_virtual_cherries_supported(plf_ctx * ctx, const plf_shape_t * sh)
 {
   dna_read_switches(ctx);
-  if (sh->states != 4 || !ctx->dna_stream || env_int("PLF_VIRTUAL_CHERRIES", 1) == 0) return 0;
+  if (sh->states != 4 || !ctx->dna_stream) return 0;
   if (sh->rate_cats != 1 && sh->rate_cats != 2 && sh->rate_cats != 4) return 0;
   /* consumers that are not cherry-fed go through the ring kernels too: their tiles need >= 16 sites */
   return ((DNA_THREADS * (unsigned int)ctx->dna_items) / sh->rate_cats) >= 16;

@@ -160,6 +160,7 @@ typedef struct cuda_partition
   /* virtual cherries: tip-tip parents of 4-state pattern-tip partitions are not
    * written to HBM; their consumers work from the tip codes, anything else materialises them first */
   int cherry_ok;                 /* this partition's kernels consume virtual cherries */
+  unsigned int cherry_maxstates; /* tip alphabet size cherry_ok was decided for (0: not yet) */
   unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES) */
   double * d_cherry_pm;          /* [clv_buffers][2][rate_cats * 16]: the P-matrices each cherry was asked with */
   struct cherry_state * cherry;  /* [nodes] */
@@ -208,9 +209,17 @@ static unsigned int sites_alloc(const pll_partition_t * p)
 
 /* ---- virtual cherries -------------------------------------------------------------------- */
 
+static int tipmap_on_device(cuda_partition_t * cp);
+
+/* doubles of one P-matrix of all rate categories */
+static size_t cherry_msz(const cuda_partition_t * cp)
+{
+  return (size_t)cp->pub.rate_cats * cp->pub.states * cp->pub.states_padded;
+}
+
 static double * cherry_snapshot(const cuda_partition_t * cp, unsigned int node)
 {
-  return cp->d_cherry_pm + (size_t)(node - cp->pub.tips) * 2 * cp->pub.rate_cats * 16;
+  return cp->d_cherry_pm + (size_t)(node - cp->pub.tips) * 2 * cherry_msz(cp);
 }
 
 static int is_virtual(const cuda_partition_t * cp, unsigned int node)
@@ -234,9 +243,9 @@ static int ensure_real(cuda_partition_t * cp, unsigned int node)
   op.left_tip = cp->d_tipchars[c->tip1];
   op.right_tip = cp->d_tipchars[c->tip2];
   op.left_matrix = cherry_snapshot(cp, node);
-  op.right_matrix = op.left_matrix + (size_t)p->rate_cats * 16;
+  op.right_matrix = op.left_matrix + cherry_msz(cp);
   op.nsites = p->sites + (p->asc_bias_alloc ? p->states : 0);
-  if (!plf_update_partials_once(cp->ctx, &cp->shape, &op, 1, cp->d_tipmap, p->maxstates))
+  if (!tipmap_on_device(cp) || !plf_update_partials_once(cp->ctx, &cp->shape, &op, 1, cp->d_tipmap, p->maxstates))
   {
     pll_errno = PLL_ERROR_CUDA;
     snprintf(pll_errmsg, sizeof(pll_errmsg), "CUDA: %s", plf_last_error(cp->ctx));
@@ -244,6 +253,20 @@ static int ensure_real(cuda_partition_t * cp, unsigned int node)
   }
   cp->cherry[node].is_virtual = 0;
   --cp->cherries_pending;
+  return 1;
+}
+
+/* (re)settle whether this partition keeps tip-tip parents virtual, for the tip alphabet it has now; when
+ * the answer turns to no, the cherries that are still virtual are written out first */
+static int cherry_decide(cuda_partition_t * cp)
+{
+  unsigned int n;
+  if (!cp->cherry || cp->cherry_maxstates == cp->pub.maxstates) return 1;
+  cp->cherry_maxstates = cp->pub.maxstates;
+  cp->cherry_ok = plf_virtual_cherries_supported(cp->ctx, &cp->shape, cp->pub.maxstates);
+  if (!cp->cherry_ok && cp->cherries_pending)
+    for (n = cp->pub.tips; n < cp->pub.nodes; ++n)
+      if (!ensure_real(cp, n)) return 0;
   return 1;
 }
 
@@ -677,15 +700,19 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
 
   if (attributes & PLL_ATTRIB_SITE_REPEATS) NEED(repeats_initialize(cp));
 
-  if ((attributes & PLL_ATTRIB_PATTERN_TIP) && !p->asc_bias_alloc && clv_buffers &&
-      plf_virtual_cherries_supported(cp->ctx, &cp->shape))
+  if ((attributes & PLL_ATTRIB_PATTERN_TIP) && !p->asc_bias_alloc && clv_buffers && (states == 4 || states == 20) &&
+      plf_virtual_cherries_supported(cp->ctx, &cp->shape, states == 4 ? 16 : 24))
   {
+    /* whether tip-tip parents stay virtual is settled at the first operation list, when the tip alphabet
+     * (maxstates: table sizes of the 20-state kernels) is known: cherry_decide() */
     const char * v = getenv("PLF_VIRTUAL_CHERRY_MIN_SITES");
     cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : 4096u;
-    NEED(cp->cherry = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
-    NEED(cp->cherry_saved = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
-    NEED(cp->d_cherry_pm = (double *)plf_alloc(cp->ctx, (size_t)clv_buffers * 2 * rate_cats * 16 * sizeof(double), 1));
-    cp->cherry_ok = sites >= cp->cherry_min_sites;
+    if (sites >= cp->cherry_min_sites)
+    {
+      NEED(cp->cherry = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
+      NEED(cp->cherry_saved = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
+      NEED(cp->d_cherry_pm = (double *)plf_alloc(cp->ctx, (size_t)clv_buffers * 2 * cherry_msz(cp) * sizeof(double), 1));
+    }
   }
 #undef NEED
   return p;
@@ -2248,7 +2275,7 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
         out->right_tip = cp->d_tipchars[c->tip1];
         out->right_tip2 = cp->d_tipchars[c->tip2];
         out->right_cm1 = cherry_snapshot(cp, inner);
-        out->right_cm2 = out->right_cm1 + (size_t)p->rate_cats * 16;
+        out->right_cm2 = out->right_cm1 + cherry_msz(cp);
       }
       else
       {
@@ -2271,7 +2298,7 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
       out->left_tip = cp->d_tipchars[c->tip1];
       out->left_tip2 = cp->d_tipchars[c->tip2];
       out->left_cm1 = cherry_snapshot(cp, cl);
-      out->left_cm2 = out->left_cm1 + (size_t)p->rate_cats * 16;
+      out->left_cm2 = out->left_cm1 + cherry_msz(cp);
       out->left_matrix = p->pmatrix[ml];
       out->right_matrix = p->pmatrix[mr];
       if (v1 && v2)
@@ -2281,7 +2308,7 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
         out->right_tip = cp->d_tipchars[d->tip1];
         out->right_tip2 = cp->d_tipchars[d->tip2];
         out->right_cm1 = cherry_snapshot(cp, cr);
-        out->right_cm2 = out->right_cm1 + (size_t)p->rate_cats * 16;
+        out->right_cm2 = out->right_cm1 + cherry_msz(cp);
       }
       else
       {
@@ -2379,6 +2406,7 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
     set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
     return 0;
   }
+  if (!cherry_decide(cp)) return 0;
   /* ops are resolved in list order: whether a child is a virtual cherry is the state the list has
    * reached at that op; a list that fails to resolve leaves the state as it found it */
   if (cp->cherry)
@@ -3521,7 +3549,11 @@ PLL_EXPORT int pll_cuda_download_clv(const pll_partition_t * partition, unsigned
 PLL_EXPORT int pll_cuda_virtual_cherries(const pll_partition_t * partition)
 {
   cuda_partition_t * cp = CP(partition);
-  return cp && cp->cherry_ok;
+  if (!cp || !cp->cherry) return 0;
+  /* before the first operation list: what the decision will be for the tip alphabet known so far */
+  if (cp->cherry_maxstates != partition->maxstates)
+    return plf_virtual_cherries_supported(cp->ctx, &cp->shape, partition->maxstates);
+  return cp->cherry_ok;
 }
 
 /* NEW (additive).  Number of nodes whose CLV is virtual right now; `clv_index` < nodes asks about one node. */

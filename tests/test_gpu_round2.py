@@ -159,6 +159,52 @@ def test_virtual_cherries_large(reflib, cudalib):
     gpu.close()
 
 
+AA_CHERRY_CASES = [
+    # tips, sites, tree, cats, per_rate
+    (10, 53, "random", 4, False),
+    (40, 301, "random", 4, False),
+    (40, 301, "random", 4, True),
+    (120, 21, "caterpillar", 4, False),
+    (24, 1003, "random", 2, False),
+    (24, 500, "random", 1, False),
+    (20, 200, "random", 8, False),
+]
+
+
+@pytest.mark.parametrize("case", AA_CHERRY_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_virtual_cherries_parity_aa(reflib, cudalib, monkeypatch, case):
+    """20 states: the consumers of a virtual cherry form the cherry's entries in registers as the A operand of
+    the DMMA.  Against the reference within the DMMA tolerance (scalers exact), and against this library with
+    every tip-tip parent written to HBM: the same operands, so the same bits."""
+    tips, sites, tree, cats, per_rate = case
+    ds = synth.aa_dataset(tips, sites, seed=200 + tips, tree_kind=tree, alpha=0.4, cats=cats)
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "0")
+    plain = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP | (capi.RATE_SCALERS if per_rate else 0))
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "1")
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
+    assert cudalib.pll_cuda_virtual_cherries(plain.p) == 0
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
+    cherries = cherry_nodes(ds)
+    traverse(ref, gpu, plain)
+    assert cudalib.pll_cuda_virtual_clvs(gpu.p, 0xFFFFFFFF) == len(cherries)
+    assert cudalib.pll_cuda_virtual_clvs(plain.p, 0xFFFFFFFF) == 0
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL over virtual cherries")
+    n_scaled = compare_all_nodes(ref, gpu, exact=False)
+    if tree == "caterpillar":
+        assert n_scaled > 0
+    for op in gpu.ops:
+        assert np.array_equal(bits(plain.clv(op.parent_clv_index)), bits(gpu.clv(op.parent_clv_index))), op.parent_clv_index
+        assert np.array_equal(plain.scaler(op.parent_scaler_index), gpu.scaler(op.parent_scaler_index))
+    for _ in range(3):
+        traverse(gpu)
+    compare_all_nodes(ref, gpu, exact=False)
+    traverse(gpu)
+    check_edge_and_derivatives(ref, gpu, ds, per_rate)
+    for e in (ref, gpu, plain):
+        e.close()
+
+
 # ---- unequal category weights (LG4X-style) ------------------------------------------------------------------
 
 WEIGHT_CASES = [
