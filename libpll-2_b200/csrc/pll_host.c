@@ -166,6 +166,8 @@ typedef struct cuda_partition
   struct cherry_state * cherry;  /* [nodes] */
   struct cherry_state * cherry_saved; /* roll-back copy while an operation list is resolved */
   unsigned int cherries_pending; /* nodes whose CLV is virtual right now */
+  unsigned char * scaler_zero;   /* [scale_buffers] the buffer is known to hold zeros (written by a tip-tip op only) */
+  unsigned char * scaler_zero_saved;
 
   /* reusable host scratch for operation lists */
   plf_op_t * h_ops;
@@ -467,6 +469,8 @@ static void destroy(cuda_partition_t * cp)
   free(cp->evicted_keys);
   free(cp->cherry);
   free(cp->cherry_saved);
+  free(cp->scaler_zero);
+  free(cp->scaler_zero_saved);
   free(cp->h_model);
   free(cp->h_model_sent);
   free(cp->h_ops);
@@ -711,6 +715,8 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     {
       NEED(cp->cherry = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
       NEED(cp->cherry_saved = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
+      NEED(cp->scaler_zero = (unsigned char *)calloc(scale_buffers ? scale_buffers : 1, 1));
+      NEED(cp->scaler_zero_saved = (unsigned char *)calloc(scale_buffers ? scale_buffers : 1, 1));
       NEED(cp->d_cherry_pm = (double *)plf_alloc(cp->ctx, (size_t)clv_buffers * 2 * cherry_msz(cp) * sizeof(double), 1));
     }
   }
@@ -2249,6 +2255,12 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
         /* the cherry stays virtual: only its P-matrices are snapshot and its scaler zeroed */
         out->kind = PLF_OP_TT_VIRTUAL;
         out->parent_clv = cherry_snapshot(cp, par);
+        /* the scaler of a tip-tip parent is all zeros: written once, not again while nothing else wrote it */
+        if (op->parent_scaler_index >= 0)
+        {
+          if (cp->scaler_zero[op->parent_scaler_index]) out->parent_scaler = NULL;
+          cp->scaler_zero[op->parent_scaler_index] = 1;
+        }
         if (!cp->cherry[par].is_virtual) ++cp->cherries_pending;
         cp->cherry[par].is_virtual = 1;
         cp->cherry[par].tip1 = c1;
@@ -2335,6 +2347,8 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
     cp->cherry[par].is_virtual = 0;
     --cp->cherries_pending;
   }
+  /* only the tip-tip kernels leave a scaler all zeros */
+  if (cp->scaler_zero && op->parent_scaler_index >= 0) cp->scaler_zero[op->parent_scaler_index] = (out->kind == PLF_OP_TT);
   if (!out->parent_clv || (out->kind == PLF_OP_II && (!out->left_clv || !out->right_clv))) goto missing;
   return 1;
 missing:
@@ -2412,6 +2426,7 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
   if (cp->cherry)
   {
     memcpy(cp->cherry_saved, cp->cherry, (size_t)cp->pub.nodes * sizeof(cherry_state_t));
+    memcpy(cp->scaler_zero_saved, cp->scaler_zero, cp->pub.scale_buffers);
     saved_pending = cp->cherries_pending;
   }
   for (i = 0; i < count; ++i)
@@ -2420,6 +2435,7 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
       if (cp->cherry)
       {
         memcpy(cp->cherry, cp->cherry_saved, (size_t)cp->pub.nodes * sizeof(cherry_state_t));
+        memcpy(cp->scaler_zero, cp->scaler_zero_saved, cp->pub.scale_buffers);
         cp->cherries_pending = saved_pending;
       }
       return 0;
