@@ -126,14 +126,21 @@ def fused_traversal_bytes(ds, sites: int) -> int:
 
 def captured_traffic(key: str):
     """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the CLV launches of one
-    traversal) from the committed ncu capture of this workload (profiles/r2_traffic.json, else r1), or None."""
+    traversal) from the committed ncu capture of this workload (profiles/r2_traffic.json, else r1), or None.
+    A capture of the same tree and model at another site count is scaled linearly (every byte of a traversal
+    is per site) and says so in the source string."""
+    prefix, _, sites = key.rpartition("x")
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
             doc = json.load(open(os.path.join(REPO, "profiles", name)))
-            if key in doc:
-                return doc[key]["traffic_bytes_per_step"], name
         except Exception:
-            pass
+            continue
+        if key in doc:
+            return doc[key]["traffic_bytes_per_step"], name
+        for other, rec in doc.items():
+            if isinstance(rec, dict) and other.startswith(prefix + "x") and sites.isdigit() and other[len(prefix) + 1:].isdigit():
+                scale = int(sites) / int(other[len(prefix) + 1:])
+                return rec["traffic_bytes_per_step"] * scale, f"{name}: capture of {other} scaled by {scale:g} (bytes are per site)"
     return None, None
 
 

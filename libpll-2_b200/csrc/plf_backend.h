@@ -229,7 +229,8 @@ int plf_repeats_ids_batch(plf_ctx_t * ctx, unsigned int sites,
 /* The identifiers of a whole operation list without a host synchronisation per level, for the default
  * enable rule (pll_default_enable_repeats, src/repeats.c:100-110), which is evaluated on the device from
  * the children's class counts.  Job j numbers node `parent` from the identifiers of `left` and `right`;
- * its lookup keys live in the 64-bit entries [lookup_offset, lookup_offset + lookup_entries) of the pool,
+ * its lookup keys live in the 64-bit entries [lookup_offset, lookup_offset + lookup_entries) of the pool
+ * (d_rank_pool: as many 32-bit entries with the same indices, the class number of each key),
  * where lookup_entries >= ids(left) * ids(right) whenever the rule enables the node (the host passes
  * min(upper bound of the product, lookup_buffer_size)).  d_node_ids[node] holds the class count the
  * reference keeps in pernode_ids (0 = not compressed) for every node on entry and is updated per job;
@@ -249,7 +250,7 @@ typedef struct plf_rid_job
 size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int njobs);
 int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned int lookup_buffer_size,
                      const plf_rid_job_t * d_jobs, unsigned int first_job, unsigned int njobs,
-                     unsigned long long * d_lookup_pool, unsigned int tag,
+                     unsigned long long * d_lookup_pool, unsigned int * d_rank_pool, unsigned int tag,
                      unsigned int * d_node_ids, unsigned int * d_raw_ids, void * d_scratch);
 /* pair list of a gathering op: out[2n] / out[2n+1] = entry of the left / right child that parent entry n
  * reads (parent_id_site, left_site_id, right_site_id may each be NULL = identity) */

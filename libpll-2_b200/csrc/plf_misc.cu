@@ -340,6 +340,7 @@ __device__ __forceinline__ RidCtx rid_ctx(const plf_rid_job_t & jb, unsigned int
                                           const unsigned int * __restrict__ node_ids,
                                           unsigned long long * __restrict__ pool)
 {
+
   RidCtx c;
   const unsigned long long nl = node_ids[jb.left], nr = node_ids[jb.right];
   const unsigned long long pairs = nl * nr;
@@ -361,7 +362,13 @@ __global__ void k_rid_min(const plf_rid_job_t * __restrict__ jobs, unsigned int 
   if (!c.enabled) return;
   const unsigned long long hi = (unsigned long long)tag << 32;
   for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
-    atomicMin(&c.lookup[RID_KEY(c, s)], hi | s);
+  {
+    /* sites are visited in increasing order, so most of them find their class already claimed by an earlier
+     * site of this pass: a plain L2 read then spares the atomic (and the serialisation on popular keys) */
+    unsigned long long * e = &c.lookup[RID_KEY(c, s)];
+    const unsigned long long mine = hi | s;
+    if (__ldcg(e) > mine) atomicMin(e, mine);
+  }
 }
 
 __global__ void k_rid_count(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
@@ -433,65 +440,80 @@ __global__ void k_rid_scan(const plf_rid_job_t * __restrict__ jobs, unsigned int
 
 /* NOTE: k_rid_rank / k_rid_assign run after k_rid_scan has overwritten node_ids[parent]; a job never has its
  * own parent as a child (the host falls back to the per-op path for lists that recycle buffers), so the
- * enable rule still sees the children's counts. */
+ * enable rule still sees the children's counts.
+ * Rank of every first occurrence within its 1024-site tile by ballots (one bit per site), plus the tile's
+ * offset: the class number.  It goes to id_site_parent[rank] = site and to rank_pool[key], a table with the
+ * lookup pool's index space, from which k_rid_assign reads every site's class with ONE gather. */
 __global__ void k_rid_rank(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
                            const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
                            const unsigned int * __restrict__ tile_count_all, unsigned int ntiles,
-                           unsigned int * __restrict__ rank_all)
+                           unsigned int * __restrict__ rank_pool)
 {
   const plf_rid_job_t jb = jobs[blockIdx.y];
   const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
   if (!c.enabled) return;
   const unsigned int * tile_offset = tile_count_all + (size_t)blockIdx.y * ntiles;
-  unsigned int * rank_of_site = rank_all + (size_t)blockIdx.y * sites;
-  __shared__ unsigned int buf[SCAN_TILE];
+  unsigned int * rank_of_key = rank_pool + jb.lookup_offset;
+  __shared__ unsigned int warp_count[SCAN_TILE / 32];
   const unsigned int s = blockIdx.x * SCAN_TILE + threadIdx.x;
-  const unsigned int f = (s < sites) ? ((unsigned int)c.lookup[RID_KEY(c, s)] == s) : 0u;
-  buf[threadIdx.x] = f;
-  __syncthreads();
-  for (unsigned int o = 1; o < SCAN_TILE; o <<= 1)
+  const unsigned int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned int key = 0;
+  bool f = false;
+  if (s < sites)
   {
-    unsigned int t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
-    __syncthreads();
-    buf[threadIdx.x] += t;
-    __syncthreads();
+    key = RID_KEY(c, s);
+    f = (unsigned int)c.lookup[key] == s;
   }
+  const unsigned int bal = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) warp_count[w] = __popc(bal);
+  __syncthreads();
+  if (w == 0)
+  {
+    /* exclusive scan of the 32 warp counts */
+    unsigned int v = warp_count[lane], x = v;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, x, o);
+      if ((int)lane >= o) x += t;
+    }
+    warp_count[lane] = x - v;
+  }
+  __syncthreads();
   if (f)
   {
-    const unsigned int r = tile_offset[blockIdx.x] + buf[threadIdx.x] - 1;
-    rank_of_site[s] = r;
+    const unsigned int r = tile_offset[blockIdx.x] + warp_count[w] + __popc(bal & ((1u << lane) - 1u));
+    rank_of_key[key] = r;
     jb.id_site_parent[r] = s;
   }
 }
 
 __global__ void k_rid_assign(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
                              const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
-                             const unsigned int * __restrict__ rank_all)
+                             const unsigned int * __restrict__ rank_pool)
 {
   const plf_rid_job_t jb = jobs[blockIdx.y];
   const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
   if (!c.enabled) return;
-  const unsigned int * rank_of_site = rank_all + (size_t)blockIdx.y * sites;
+  const unsigned int * rank_of_key = rank_pool + jb.lookup_offset;
   for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
-    jb.site_id_parent[s] = rank_of_site[(unsigned int)c.lookup[RID_KEY(c, s)]];
+    jb.site_id_parent[s] = rank_of_key[RID_KEY(c, s)];
 }
 
 extern "C" size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int njobs)
 {
   const size_t ntiles = ((size_t)sites + SCAN_TILE - 1) / SCAN_TILE;
-  return (size_t)njobs * (ntiles + sites) * sizeof(unsigned int) + 64;
+  return (size_t)njobs * ntiles * sizeof(unsigned int) + 64;
 }
 
 extern "C" int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned int lookup_buffer_size,
                                 const plf_rid_job_t * d_jobs, unsigned int first_job, unsigned int njobs,
-                                unsigned long long * d_lookup_pool, unsigned int tag, unsigned int * d_node_ids,
-                                unsigned int * d_raw_ids, void * d_scratch)
+                                unsigned long long * d_lookup_pool, unsigned int * d_rank_pool, unsigned int tag,
+                                unsigned int * d_node_ids, unsigned int * d_raw_ids, void * d_scratch)
 {
   if (!njobs) return 1;
   PLF_CHECK(ctx, cudaSetDevice(ctx->device));
   const unsigned int ntiles = (sites + SCAN_TILE - 1) / SCAN_TILE;
   unsigned int * tile = (unsigned int *)d_scratch;
-  unsigned int * rank = tile + (size_t)njobs * ntiles;
   const plf_rid_job_t * jobs = d_jobs + first_job;
   unsigned int blocks = (sites + 255) / 256;
   const unsigned int cap = (unsigned int)ctx->sm_count * 8;
@@ -503,8 +525,8 @@ extern "C" int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned in
   k_rid_scan<<<dim3(1, njobs), 1024, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile,
                                                        ntiles, d_raw_ids + first_job);
   k_rid_rank<<<gt, SCAN_TILE, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile, ntiles,
-                                               rank);
-  k_rid_assign<<<gs, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, rank);
+                                               d_rank_pool);
+  k_rid_assign<<<gs, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, d_rank_pool);
   for (int i = 0; i < 5; ++i) plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;

@@ -420,12 +420,16 @@ k_partials_gen(const plf_op_t * __restrict__ ops, int R, int per_rate, int st_rt
 /* ------------------------------------------------------------------------ */
 
 /* one kernel launch serves a run of same-kind ops of a level, the op selected by blockIdx.y: a run ends at
- * the first op of another kind, at the end of the level `b`, or after PLF_MAX_RUN_OPS ops (gridDim.y limit) */
+ * the first op of another kind (or, under site repeats, at the first op that gathers / does not gather
+ * through identifiers like the first one), at the end of the level `b`, or after PLF_MAX_RUN_OPS ops
+ * (gridDim.y limit) */
 extern "C" unsigned int plf_run_end(const plf_op_t * h_ops, unsigned int i, unsigned int b,
                                     unsigned int * max_sites, int * contiguous)
 {
   unsigned int j = i;
-  while (j < b && h_ops[j].kind == h_ops[i].kind && j - i < PLF_MAX_RUN_OPS)
+  const bool gathers = h_ops[i].parent_id_site || h_ops[i].left_site_id || h_ops[i].right_site_id;
+  while (j < b && h_ops[j].kind == h_ops[i].kind && j - i < PLF_MAX_RUN_OPS &&
+         (bool)(h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id) == gathers)
   {
     if (max_sites && h_ops[j].nsites > *max_sites) *max_sites = h_ops[j].nsites;
     if (contiguous && (h_ops[j].parent_id_site || h_ops[j].left_site_id || h_ops[j].right_site_id)) *contiguous = 0;

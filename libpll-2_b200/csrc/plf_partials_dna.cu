@@ -841,15 +841,35 @@ __device__ __forceinline__ void build_cherry_table(double * tab, double * scratc
   __syncthreads(); /* the scratch may still be read by the previous table's build */
   build_tip_table(scratch, cm1, R);
   build_tip_table(scratch + 64 * R, cm2, R);
+  /* entry e = ((codeA * 16 + codeB) * R + rate) * 4 + i: a thread's (rate, i) = e mod 4R never changes
+   * (the block size is a multiple of 4R), so its row of `outer` is read from global memory once */
+  static_assert(DNA_THREADS % (4 * R) == 0, "a thread must keep its (rate, row) over the table build");
+  const int i = threadIdx.x & 3, rate = (threadIdx.x >> 2) & (R - 1);
+  const double o0 = outer[rate * 16 + i * 4 + 0], o1 = outer[rate * 16 + i * 4 + 1];
+  const double o2 = outer[rate * 16 + i * 4 + 2], o3 = outer[rate * 16 + i * 4 + 3];
   __syncthreads();
-  for (int e = threadIdx.x; e < 1024 * R; e += blockDim.x)
+#pragma unroll 4
+  for (int e = threadIdx.x; e < 1024 * R; e += DNA_THREADS)
   {
-    const int i = e & 3, rate = (e >> 2) & (R - 1), cb = (e >> (2 + LOG2R)) & 15, ca = e >> (6 + LOG2R);
-    const double * a = scratch + (ca * R + rate) * 4;
-    const double * b = scratch + 64 * R + (cb * R + rate) * 4;
-    const dbl4 l = dbl4{a[0] * b[0], a[1] * b[1], a[2] * b[2], a[3] * b[3]};
-    tab[e] = dot4_pairwise(outer + rate * 16 + i * 4, l);
+    const int cb = (e >> (2 + LOG2R)) & 15, ca = e >> (6 + LOG2R);
+    const double2 a0 = *reinterpret_cast<const double2 *>(scratch + (ca * R + rate) * 4);
+    const double2 a1 = *reinterpret_cast<const double2 *>(scratch + (ca * R + rate) * 4 + 2);
+    const double2 b0 = *reinterpret_cast<const double2 *>(scratch + 64 * R + (cb * R + rate) * 4);
+    const double2 b1 = *reinterpret_cast<const double2 *>(scratch + 64 * R + (cb * R + rate) * 4 + 2);
+    /* dot4_pairwise(outer row, cherry entry): multiplies, then the pairwise tree */
+    const double p0 = o0 * (a0.x * b0.x), p1 = o1 * (a0.y * b0.y), p2 = o2 * (a1.x * b1.x), p3 = o3 * (a1.y * b1.y);
+    tab[e] = (p0 + p1) + (p2 + p3);
   }
+}
+
+/* 32-byte table row read as two 16-byte halves; odd site groups take the halves in the other order, so that
+ * two neighbouring sites of a warp cover all 32 banks whatever rows they read (a row is 128 bytes apart from
+ * the next: without this every site of the warp would hit the same 16 banks) */
+__device__ __forceinline__ dbl4 lds_dbl4_swz(const double * p, int swap)
+{
+  const double2 a = *reinterpret_cast<const double2 *>(p + 2 * swap);
+  const double2 b = *reinterpret_cast<const double2 *>(p + 2 * (swap ^ 1));
+  return swap ? dbl4{b.x, b.y, a.x, a.y} : dbl4{a.x, a.y, b.x, b.y};
 }
 
 template <int LOG2R, int LK, int RK, int NSTAGE, int ITEMS>
@@ -867,6 +887,7 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
   const plf_op_t op = ops[blockIdx.y];
   const unsigned int ntiles = (op.nsites + Ly::TILE - 1) / Ly::TILE;
   const int rate = threadIdx.x & (R - 1);
+  const int swz = (R <= 4) ? ((threadIdx.x >> LOG2R) & 1) : 0; /* odd site of a pair: table halves swapped */
 
   if (threadIdx.x == 0)
   {
@@ -924,12 +945,12 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
       else if (LK == CK_T)
       {
         const unsigned int code = sr.active ? slot[Ly::OFF_LCODE + ls] : 0u;
-        a = lds_dbl4(tabL + (code * R + rate) * 4);
+        a = lds_dbl4_swz(tabL + (code * R + rate) * 4, swz);
       }
       else
       {
         const unsigned int code = sr.active ? (((slot[Ly::OFF_LCODE + ls] & 15u) << 4) | (slot[Ly::OFF_LCODE2 + ls] & 15u)) : 0u;
-        a = lds_dbl4(tabL + (code * R + rate) * 4);
+        a = lds_dbl4_swz(tabL + (code * R + rate) * 4, swz);
       }
       if (RK == CK_I)
       {
@@ -942,7 +963,7 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
       else
       {
         const unsigned int code = sr.active ? (((slot[Ly::OFF_RCODE + ls] & 15u) << 4) | (slot[Ly::OFF_RCODE2 + ls] & 15u)) : 0u;
-        b = lds_dbl4(tabR + (code * R + rate) * 4);
+        b = lds_dbl4_swz(tabR + (code * R + rate) * 4, swz);
       }
       if (op.parent_scaler && sr.active && (per_rate || rate == 0))
       {

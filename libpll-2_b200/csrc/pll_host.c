@@ -145,6 +145,7 @@ typedef struct cuda_partition
   plf_rid_job_t * d_rid_jobs;             /* [rid_cap] */
   unsigned int rid_cap;
   unsigned long long * d_lookup64;        /* tagged lookup pool */
+  unsigned int * d_rank_pool;             /* class number per lookup key, same index space */
   unsigned long long lookup64_entries;
   unsigned int rid_tag;                   /* next tag: decreasing, every pass below all earlier ones */
   void * d_rid_scratch;
@@ -393,6 +394,7 @@ static void free_repeats(cuda_partition_t * cp)
   plf_free(cp->ctx, cp->d_raw_ids);
   plf_free(cp->ctx, cp->d_rid_jobs);
   plf_free(cp->ctx, cp->d_lookup64);
+  plf_free(cp->ctx, cp->d_rank_pool);
   plf_free(cp->ctx, cp->d_rid_scratch);
   plf_free(cp->ctx, cp->d_lookup);
   plf_free(cp->ctx, cp->d_lookup_pool);
@@ -1173,9 +1175,12 @@ static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * op
   if (cp->lookup64_entries < need_pool)
   {
     plf_free(cp->ctx, cp->d_lookup64);
+    plf_free(cp->ctx, cp->d_rank_pool);
     cp->lookup64_entries = 0;
     cp->d_lookup64 = (unsigned long long *)plf_alloc(cp->ctx, (size_t)need_pool * sizeof(unsigned long long), 0);
-    if (!cp->d_lookup64 || !plf_fill_u32(cp->ctx, (unsigned int *)cp->d_lookup64, EMPTY_ELEMENT, (size_t)need_pool * 2))
+    cp->d_rank_pool = (unsigned int *)plf_alloc(cp->ctx, (size_t)need_pool * sizeof(unsigned int), 0);
+    if (!cp->d_lookup64 || !cp->d_rank_pool ||
+        !plf_fill_u32(cp->ctx, (unsigned int *)cp->d_lookup64, EMPTY_ELEMENT, (size_t)need_pool * 2))
     {
       cuda_fail(cp);
       goto done;
@@ -1196,10 +1201,8 @@ static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * op
       goto done;
     }
   }
-  /* scratch: rank arrays of `sites` entries per job of one part */
-  max_jobs_ws = (unsigned int)(REPEATS_BATCH_WS_BYTES / ((size_t)sites * sizeof(unsigned int) + 64));
-  if (max_jobs_ws < 1) max_jobs_ws = 1;
-  if (max_jobs_ws > PLF_MAX_RUN_OPS) max_jobs_ws = PLF_MAX_RUN_OPS;
+  /* scratch: tile counts (one per 1024 sites) per job of one part */
+  max_jobs_ws = PLF_MAX_RUN_OPS;
   {
     unsigned int widest = 0;
     size_t want;
@@ -1265,7 +1268,7 @@ static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * op
       cp->rid_tag = 0xFFFFFFFEu;
     }
     if (!plf_repeats_pass(cp->ctx, sites, r->lookup_buffer_size, cp->d_rid_jobs, i, end - i, cp->d_lookup64,
-                          cp->rid_tag--, cp->d_node_ids, cp->d_raw_ids, cp->d_rid_scratch))
+                          cp->d_rank_pool, cp->rid_tag--, cp->d_node_ids, cp->d_raw_ids, cp->d_rid_scratch))
     {
       cuda_fail(cp);
       goto done;
@@ -2195,7 +2198,7 @@ static int reserve_ops(cuda_partition_t * cp, unsigned int count)
   cp->h_ops = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
   cp->h_ops_sorted = (plf_op_t *)malloc((size_t)count * sizeof(plf_op_t));
   cp->h_level = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
-  cp->h_level_start = (unsigned int *)malloc((PLF_OP_KINDS * (size_t)count + 2) * sizeof(unsigned int));
+  cp->h_level_start = (unsigned int *)malloc(((PLF_OP_KINDS + 1) * (size_t)count + 2) * sizeof(unsigned int));
   cp->ops_cap = (cp->h_ops && cp->h_ops_sorted && cp->h_level && cp->h_level_start) ? count : 0;
   return cp->ops_cap != 0;
 }
@@ -2454,8 +2457,16 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
   nlevels = (unsigned int)nl;
   /* counting sort by (level, op kind), stable: each launch group is a run of
    * same-kind ops of one level */
-  for (i = 0; i < count; ++i) cp->h_level[i] = cp->h_level[i] * PLF_OP_KINDS + cp->h_ops[i].kind;
-  nlevels *= PLF_OP_KINDS;
+  /* (under site repeats the gathering inner-inner ops of a level form a run of their own, next to the ones
+   * whose parent and children are all uncompressed: different kernels) */
+  for (i = 0; i < count; ++i)
+  {
+    const plf_op_t * o = cp->h_ops + i;
+    const unsigned int slot =
+        (o->kind == PLF_OP_II && (o->parent_id_site || o->left_site_id || o->right_site_id)) ? PLF_OP_KINDS : o->kind;
+    cp->h_level[i] = cp->h_level[i] * (PLF_OP_KINDS + 1) + slot;
+  }
+  nlevels *= PLF_OP_KINDS + 1;
   for (i = 0; i <= nlevels; ++i) cp->h_level_start[i] = 0;
   for (i = 0; i < count; ++i) cp->h_level_start[cp->h_level[i] + 1]++;
   for (i = 0; i < nlevels; ++i) cp->h_level_start[i + 1] += cp->h_level_start[i];
