@@ -22,6 +22,8 @@ def main(d):
                   "set-up traversal + 3 more; DRAM bytes of the CLV launches divided by the traversals captured"}
     for cfg, key in KEYS.items():
         csv_path, log_path = os.path.join(d, f"r2_traffic_{cfg}.csv"), os.path.join(d, f"tr_{cfg}.log")
+        if not os.path.exists(log_path):
+            log_path = os.path.join(d, f"r2_traffic_{cfg}.log")  # as committed under profiles/
         if not (os.path.exists(csv_path) and os.path.exists(log_path)):
             continue
         info = None
