@@ -644,7 +644,7 @@ def run_b200_arm(args):
     value = updates_per_step * args.steps / (ms_total * 1e-3)
     clv_bytes, edge_bytes = traversal_bytes(ds, args.sites)
     # tip-tip parents stay virtual on the 4-state path when the library says so (pll_cuda_virtual_cherries)
-    virtual = lib.pll_cuda_virtual_cherries(eng.p) == 1
+    virtual = hasattr(lib, "pll_cuda_virtual_cherries") and lib.pll_cuda_virtual_cherries(eng.p) == 1
     fused_bytes = fused_traversal_bytes(ds, args.sites) if virtual else clv_bytes
     nwt_bytes = newton_bytes(ds, args.sites)
     peak, peak_src = measured_peak_gbs()

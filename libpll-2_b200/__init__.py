@@ -25,5 +25,6 @@ def load() -> "capi.PllLibrary":
     is deliberately no CPU or pure-Python fallback."""
     global _lib
     if _lib is None:
-        _lib = capi.PllLibrary(LIB_PATH, cuda=True)
+        # $PLL_B200_LIB: another build of the same library (A/B measurements against an earlier round)
+        _lib = capi.PllLibrary(os.environ.get("PLL_B200_LIB") or LIB_PATH, cuda=True)
     return _lib

@@ -308,6 +308,8 @@ class PllLibrary:
         self.is_cuda = hasattr(self.lib, "pll_cuda_device_count") if cuda is None else cuda
         if self.is_cuda:
             for name, (res, args) in _CUDA_PROTOS.items():
+                if not hasattr(self.lib, name):
+                    continue  # an older build of the library ($PLL_B200_LIB)
                 fn = getattr(self.lib, name)
                 fn.restype, fn.argtypes = res, args
                 setattr(self, name, fn)

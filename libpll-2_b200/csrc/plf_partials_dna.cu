@@ -765,7 +765,7 @@ struct StreamLayout
   static constexpr int TILE = (DNA_THREADS * ITEMS) >> LOG2R; /* sites per tile */
   static constexpr int CLV_BYTES = TILE * R * 32;
   static constexpr int SC_BYTES = TILE * R * 4; /* per-rate worst case */
-  static constexpr int CODE_BYTES = (TILE + 15) & ~15;
+  static constexpr int CODE_BYTES = (TILE + 127) & ~127; /* whole 128-byte lines: the CLV tile behind a code array stays line-aligned */
   static constexpr int side_bytes(int k) { return k == CK_I ? CLV_BYTES + SC_BYTES : k == CK_T ? CODE_BYTES : 2 * CODE_BYTES; }
   /* left side: CLV tile then scalers, or one / two code arrays; the right side follows */
   static constexpr int OFF_L = 0;
@@ -932,7 +932,7 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
       sr.n = first + ls;
       sr.lid = sr.rid = sr.n;
       sr.active = sr.n < op.nsites;
-      dbl4 a, b;
+      dbl4 a;
       unsigned int sc = 0;
       if (LK == CK_I)
       {
@@ -952,19 +952,6 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
         const unsigned int code = sr.active ? (((slot[Ly::OFF_LCODE + ls] & 15u) << 4) | (slot[Ly::OFF_LCODE2 + ls] & 15u)) : 0u;
         a = lds_dbl4_swz(tabL + (code * R + rate) * 4, swz);
       }
-      if (RK == CK_I)
-      {
-        const dbl4 r = lds_dbl4(reinterpret_cast<const double *>(slot + Ly::OFF_R) + (size_t)item * 4);
-        b.x = dot4_pairwise(Rm + 0, r);
-        b.y = dot4_pairwise(Rm + 4, r);
-        b.z = dot4_pairwise(Rm + 8, r);
-        b.w = dot4_pairwise(Rm + 12, r);
-      }
-      else
-      {
-        const unsigned int code = sr.active ? (((slot[Ly::OFF_RCODE + ls] & 15u) << 4) | (slot[Ly::OFF_RCODE2 + ls] & 15u)) : 0u;
-        b = lds_dbl4_swz(tabR + (code * R + rate) * 4, swz);
-      }
       if (op.parent_scaler && sr.active && (per_rate || rate == 0))
       {
         const unsigned int k = per_rate ? item : ls;
@@ -972,10 +959,23 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
         if (RK == CK_I && op.right_scaler) sc += reinterpret_cast<const unsigned int *>(slot + Ly::OFF_RSC)[k];
       }
       dbl4 v;
-      v.x = a.x * b.x;
-      v.y = a.y * b.y;
-      v.z = a.z * b.z;
-      v.w = a.w * b.w;
+      if (RK == CK_I)
+      {
+        const dbl4 r = lds_dbl4(reinterpret_cast<const double *>(slot + Ly::OFF_R) + (size_t)item * 4);
+        v.x = a.x * dot4_pairwise(Rm + 0, r);
+        v.y = a.y * dot4_pairwise(Rm + 4, r);
+        v.z = a.z * dot4_pairwise(Rm + 8, r);
+        v.w = a.w * dot4_pairwise(Rm + 12, r);
+      }
+      else
+      {
+        const unsigned int code = sr.active ? (((slot[Ly::OFF_RCODE + ls] & 15u) << 4) | (slot[Ly::OFF_RCODE2 + ls] & 15u)) : 0u;
+        const dbl4 b = lds_dbl4_swz(tabR + (code * R + rate) * 4, swz);
+        v.x = a.x * b.x;
+        v.y = a.y * b.y;
+        v.z = a.z * b.z;
+        v.w = a.w * b.w;
+      }
       if (!sr.active) v = dbl4{1.0, 1.0, 1.0, 1.0}; /* stale ring bytes must not reach the scaling vote */
       scale_and_store<LOG2R>(op, sr, rate, per_rate, sc, v);
     }

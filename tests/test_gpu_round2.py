@@ -184,8 +184,10 @@ def test_virtual_cherries_parity_aa(reflib, cudalib, monkeypatch, case):
     monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "1")
     ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
     assert cudalib.pll_cuda_virtual_cherries(plain.p) == 0
-    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
-    cherries = cherry_nodes(ds)
+    # 8 rate categories: the half tables of two cherries do not fit next to a second CTA, every parent is written
+    virtual = cats <= 4
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == int(virtual)
+    cherries = cherry_nodes(ds) if virtual else []
     traverse(ref, gpu, plain)
     assert cudalib.pll_cuda_virtual_clvs(gpu.p, 0xFFFFFFFF) == len(cherries)
     assert cudalib.pll_cuda_virtual_clvs(plain.p, 0xFFFFFFFF) == 0
