@@ -944,8 +944,9 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
       }
       else if (LK == CK_T)
       {
+        /* 16 rows, a handful of them hot: neighbouring sites mostly read the same row (broadcast) */
         const unsigned int code = sr.active ? slot[Ly::OFF_LCODE + ls] : 0u;
-        a = lds_dbl4_swz(tabL + (code * R + rate) * 4, swz);
+        a = lds_dbl4(tabL + (code * R + rate) * 4);
       }
       else
       {
