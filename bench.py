@@ -332,8 +332,8 @@ def workload_config(args, world):
     return {"workload": name, "taxa": args.tips, "sites_total": args.total_sites,
             "sites_per_gpu": -(-args.total_sites // world) if args.scaling == "strong" else args.sites,
             "states": 4 if args.kind == "dna" else 20, "rate_cats": 4, "attributes": "ARCH_CUDA|PATTERN_TIP",
-            "sharding": (f"contiguous site slices x{world}, one NCCL all-reduce of {{logL, d_f, dd_f}} per step"
-                         if world > 1 else "single GPU"),
+            "sharding": (f"contiguous site slices x{world}, one all-reduce of {{logL, d_f, dd_f}} per step (peer-memory "
+                         "kernel over NVLink; NCCL with --nccl-allreduce)" if world > 1 else "single GPU"),
             "l2": "inputs larger than L2: each step streams all CLVs of the slice (>= 12 GB per 1M sites) vs 126 MB L2"}
 
 
@@ -546,6 +546,32 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the exchange of a step: one single-block kernel over peer memory (pll_cuda_peer_allreduce); NCCL when the
+    # peer buffers cannot be mapped (or with --nccl-allreduce)
+    peer = None
+    stream_ptr = C.c_void_p(lib.pll_cuda_get_stream(eng.p))
+    if dist and not args.nccl_allreduce:
+        handle = C.create_string_buffer(64)
+        group = lib.pll_cuda_peer_group_create(local, rank, world, handle)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw if group else b"")
+        ok = bool(group) and all(len(h) == 64 for h in handles) and \
+            lib.pll_cuda_peer_group_connect(group, b"".join(handles)) == 1
+        agreed = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if int(agreed.item()) == 1:
+            peer = group
+        elif group:
+            lib.pll_cuda_peer_group_destroy(group)
+
+    def exchange(buf3):
+        if peer:
+            rc = lib.pll_cuda_peer_allreduce(peer, stream_ptr, C.c_void_p(buf3.data_ptr()), 3)
+            assert rc == 1
+        else:
+            with torch.cuda.stream(ext):
+                dist.all_reduce(buf3)
+
     def step_device(ev=None):
         """everything queued on the partition's stream, results left on the device"""
         eng.update_pmatrices()
@@ -564,8 +590,7 @@ def run_b200_arm(args):
         if ev:
             ev[2].record(ext)
         if dist:
-            with torch.cuda.stream(ext):
-                dist.all_reduce(result[:3])  # the one collective of an evaluation: {logL, d_f, dd_f}
+            exchange(result[:3])  # the one exchange of an evaluation: {logL, d_f, dd_f}
         if ev:
             ev[3].record(ext)
 
@@ -610,6 +635,34 @@ def run_b200_arm(args):
     ms_newton = sum(e[1].elapsed_time(e[2]) for e in evs)
     ms_allreduce = sum(e[2].elapsed_time(e[3]) for e in evs)
     dev_vals = [float(x) for x in result[:3].tolist()]
+
+    # the two ways of summing three doubles over the ranks, alone on the stream (50 back to back)
+    collective = None
+    if dist:
+        collective = {"kind": "peer-memory one-shot all-reduce (k_peer_allreduce over NVLink stores)" if peer else "NCCL all-reduce"}
+        scratch = torch.ones(4, dtype=torch.float64, device=dev)
+
+        def timed_exchange(fn):
+            for _ in range(5):
+                fn()
+            barrier_sync()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(ext)
+            for _ in range(50):
+                fn()
+            c1.record(ext)
+            barrier_sync()
+            return c0.elapsed_time(c1) / 50
+
+        def nccl_once():
+            with torch.cuda.stream(ext):
+                dist.all_reduce(scratch[:3])
+
+        collective["nccl_us"] = 1e3 * timed_exchange(nccl_once)
+        if peer:
+            collective["peer_us"] = 1e3 * timed_exchange(
+                lambda: lib.pll_cuda_peer_allreduce(peer, stream_ptr, C.c_void_p(scratch.data_ptr()), 3))
+            collective["peer_ok"] = lib.pll_cuda_peer_group_check(peer) == 1
 
     # end to end through the public C API with host buffers and host results
     for _ in range(2):
@@ -663,7 +716,9 @@ def run_b200_arm(args):
         "clocks": clk,
         "step_breakdown_ms": {"clv_updates": ms_partials / args.steps, "edge_logl_sumtable_derivatives": ms_newton / args.steps,
                               "allreduce_3_doubles": ms_allreduce / args.steps,
-                              "pmatrices_and_rest": (ms_total - ms_partials - ms_newton - ms_allreduce) / args.steps},
+                              "pmatrices_and_rest": max(0.0, ms_total - ms_partials - ms_newton - ms_allreduce) / args.steps,
+                              "note": "each entry is the max over ranks; the all-reduce entry includes waiting for the slowest rank"},
+        "collective": collective,
         "e2e": {"value": updates_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 24, "ms_per_step": e2e_ms / args.steps,
                 "note": "pll_update_prob_matrices + pll_update_partials + pll_compute_edge_loglikelihood + "
@@ -695,6 +750,8 @@ def run_b200_arm(args):
     }
     eng.close()
     del eng
+    if peer:
+        lib.pll_cuda_peer_group_destroy(peer)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = args.cpu_threads or host_threads()
@@ -751,6 +808,8 @@ def main():
                     help=f"sites of the workload the CPU arm evaluates per step (default {SAMPLE_SITES})")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the config 3 / config 4 sub-records (N = 1 only)")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="sum {logL, d_f, dd_f} over the ranks with NCCL instead of the peer-memory kernel")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.sites:

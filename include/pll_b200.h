@@ -535,6 +535,24 @@ PLL_EXPORT int pll_cuda_materialize_clv(pll_partition_t * partition,
  * most 65535 ops (gridDim.y).  Host arithmetic only. */
 PLL_EXPORT unsigned int pll_cuda_count_launch_runs(const unsigned int * kinds, unsigned int count,
                                                    unsigned int * largest_run);
+/* The one exchange of a site-sharded evaluation (one process per GPU of one node, each owning a contiguous
+ * site slice; the reference's clients use MPI_Allreduce here) as a single-block kernel over peer memory:
+ * every rank stores its values into every peer's buffer over NVLink, waits for all slots of its own buffer and
+ * adds them in rank order, so all ranks hold the same sum bit for bit.  Set-up: each rank creates its group
+ * and hands the 64-byte handle it gets to all other ranks (any transport: an all-gather at start-up), then
+ * connects.  pll_cuda_peer_allreduce(group, pll_cuda_get_stream(partition), dev_values, n <= 4) is queued on
+ * the stream the asynchronous entry points above left {logL, d_f, dd_f} on; every rank makes the same calls.
+ * A rank that never arrives makes the others give up after 20 s (values become NaN,
+ * pll_cuda_peer_group_check() returns 0) instead of hanging the device. */
+typedef struct pll_cuda_peer_group pll_cuda_peer_group_t;
+PLL_EXPORT pll_cuda_peer_group_t * pll_cuda_peer_group_create(int device, unsigned int rank, unsigned int world,
+                                                              void * handle_out_64_bytes);
+PLL_EXPORT int pll_cuda_peer_group_connect(pll_cuda_peer_group_t * group, const void * handles_world_x_64_bytes);
+PLL_EXPORT int pll_cuda_peer_allreduce(pll_cuda_peer_group_t * group, void * stream, double * dev_values,
+                                       unsigned int count);
+PLL_EXPORT int pll_cuda_peer_group_check(pll_cuda_peer_group_t * group);
+PLL_EXPORT void pll_cuda_peer_group_destroy(pll_cuda_peer_group_t * group);
+
 /* tipchars[] of a PLL_ATTRIB_PATTERN_TIP partition are formed on the device from the raw characters
  * (src/pll.c:875-957); the host copy partition->tipchars[i] is written by this call, not by
  * pll_set_tip_states ($PLL_CUDA_TIPCHARS_MIRROR=1 writes it there too, as the reference does). */

@@ -52,7 +52,27 @@ def main():
     eng.update_sumtable(st)
     assert lib.pll_cuda_likelihood_derivatives_async(eng.p, sa, sb, t_len, pidx, st.ctypes.data_as(capi.c_double_p),
                                                      C.c_void_p(result.data_ptr() + 8)) == 1
+    peer_sum = None
     if per_rank_gpu:
+        # the same three doubles through the peer-memory kernel (pll_cuda_peer_allreduce) first, on a copy
+        handle = C.create_string_buffer(64)
+        group = lib.pll_cuda_peer_group_create(device, rank, world, handle)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw if group else b"")
+        assert group and all(len(h) == 64 for h in handles), "peer group set-up failed"
+        assert lib.pll_cuda_peer_group_connect(group, b"".join(handles)) == 1
+        lib.pll_cuda_synchronize(eng.p)
+        copy = result.clone()
+        for _ in range(3):  # three exchanges: both slot sets and the reuse of the first
+            again = result.clone()
+            assert lib.pll_cuda_peer_allreduce(group, C.c_void_p(lib.pll_cuda_get_stream(eng.p)),
+                                               C.c_void_p(again.data_ptr()), 3) == 1
+            lib.pll_cuda_synchronize(eng.p)
+            copy = again
+        assert lib.pll_cuda_peer_group_check(group) == 1
+        peer_sum = copy.cpu()
+        dist.barrier()
+        lib.pll_cuda_peer_group_destroy(group)
         ext = torch.cuda.ExternalStream(lib.pll_cuda_get_stream(eng.p), device=dev)
         with torch.cuda.stream(ext):
             dist.all_reduce(result)
@@ -80,7 +100,8 @@ def main():
         e.update_sumtable(rst)
         whole = np.array([logl, *e.derivatives(rst, t_len)])
         e.close()
-        np.save(os.environ["SHARDED_OUT"], np.concatenate([reduced.numpy(), parts, whole]))
+        extra = peer_sum.numpy() if peer_sum is not None else np.full(3, np.nan)
+        np.save(os.environ["SHARDED_OUT"], np.concatenate([reduced.numpy(), parts, whole, extra]))
     dist.barrier()
     dist.destroy_process_group()
 

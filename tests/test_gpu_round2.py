@@ -443,8 +443,11 @@ def test_site_sharded_two_ranks_against_reference(reflib, cudalib, tmp_path):
            "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tests", "sharded_worker.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    got = np.load(out)  # [gpu reduced x3, reference slices summed x3, reference whole x3]
-    gpu3, ref_slices, ref_whole = got[0:3], got[3:6], got[6:9]
+    got = np.load(out)  # [gpu reduced x3, reference slices summed x3, reference whole x3, peer-memory sum x3]
+    gpu3, ref_slices, ref_whole, peer3 = got[0:3], got[3:6], got[6:9], got[9:12]
+    if not np.isnan(peer3).any():
+        # two GPUs: the peer-memory exchange adds the same two numbers as NCCL does
+        assert np.array_equal(peer3, gpu3), (peer3, gpu3)
     assert_rel(gpu3[0], ref_slices[0], LOGL_RTOL, "reduced logL vs reference on the same slices")
     assert_rel(gpu3[0], ref_whole[0], LOGL_RTOL, "reduced logL vs reference on the whole alignment")
     for k, name in ((1, "d_f"), (2, "dd_f")):
