@@ -986,6 +986,106 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
   }
 }
 
+/* ---- write-only consumers of virtual cherries: tip + cherry, cherry + cherry ----------------------- *
+ * Neither child is a CLV: the parent is a product of two table rows, 3 or 4 bytes of tip codes in, 132 bytes   *
+ * out per site.  Same shape as the tip-tip kernel above (tiles assembled in shared memory, one bulk async      *
+ * store each, NOUT in flight, codes of the next tile fetched while the current one is built), plus what a      *
+ * tip-inner / inner-inner operation of the reference does and a tip-tip one does not: the scaling test         *
+ * (src/core_partials_avx.c:526-563).                                                                            */
+template <int LOG2R, int ITEMS, int NOUT, int LC>
+__global__ void __launch_bounds__(DNA_THREADS)
+k_clv_dna_lookup_bulk(const plf_op_t * __restrict__ ops, int per_rate)
+{
+  constexpr int R = 1 << LOG2R;
+  constexpr int TILE = (DNA_THREADS * ITEMS) >> LOG2R;
+  constexpr int OUT_BYTES = TILE * R * 32;
+  constexpr int TABL = LC ? 1024 * R : 64 * R; /* left: cherry or tip; right: always a cherry */
+  extern __shared__ __align__(128) unsigned char dynbuf[]; /* [NOUT][OUT_BYTES] | tabL | tabR | scratch */
+  unsigned char * obuf = dynbuf;
+  double * tabL = reinterpret_cast<double *>(dynbuf + (size_t)NOUT * OUT_BYTES);
+  double * tabR = tabL + TABL;
+  double * scratch = tabR + 1024 * R;
+  const plf_op_t op = ops[blockIdx.y];
+  const int rate = threadIdx.x & (R - 1);
+  const int swz = (R <= 4) ? ((threadIdx.x >> LOG2R) & 1) : 0;
+  if (LC)
+    build_cherry_table<LOG2R>(tabL, scratch, op.left_matrix, op.left_cm1, op.left_cm2);
+  else
+    build_tip_table(tabL, op.left_matrix, R);
+  build_cherry_table<LOG2R>(tabR, scratch, op.right_matrix, op.right_cm1, op.right_cm2);
+  __syncthreads();
+  const unsigned int ntiles = (op.nsites + TILE - 1) / TILE;
+  unsigned int lc_next[ITEMS], rc_next[ITEMS];
+  auto fetch_codes = [&](unsigned int t) {
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u)
+    {
+      const unsigned int n = t * TILE + ((threadIdx.x + u * DNA_THREADS) >> LOG2R);
+      const unsigned int nn = n < op.nsites ? n : op.nsites - 1;
+      lc_next[u] = LC ? (((op.left_tip[nn] & 15u) << 4) | (op.left_tip2[nn] & 15u)) : op.left_tip[nn];
+      rc_next[u] = ((op.right_tip[nn] & 15u) << 4) | (op.right_tip2[nn] & 15u);
+    }
+  };
+  if (blockIdx.x < ntiles) fetch_codes(blockIdx.x);
+  unsigned int ob = 0;
+  for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x, ++ob)
+  {
+    unsigned int lc[ITEMS], rc[ITEMS];
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u)
+    {
+      lc[u] = lc_next[u];
+      rc[u] = rc_next[u];
+    }
+    if (t + gridDim.x < ntiles) fetch_codes(t + gridDim.x);
+    /* the buffer about to be overwritten must have been read by its bulk store */
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NOUT - 1) : "memory");
+    __syncthreads();
+    unsigned char * buf = obuf + (size_t)(ob % NOUT) * OUT_BYTES;
+    const unsigned int first = t * TILE;
+#pragma unroll
+    for (int u = 0; u < ITEMS; ++u)
+    {
+      const unsigned int item = threadIdx.x + u * DNA_THREADS;
+      const unsigned int n = first + (item >> LOG2R);
+      const dbl4 a = LC ? lds_dbl4_swz(tabL + (lc[u] * R + rate) * 4, swz) : lds_dbl4(tabL + (lc[u] * R + rate) * 4);
+      const dbl4 b = lds_dbl4_swz(tabR + (rc[u] * R + rate) * 4, swz);
+      dbl4 v = dbl4{a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w};
+      if (op.parent_scaler)
+      {
+        const int below = (v.x < PLF_SCALE_THRESHOLD) && (v.y < PLF_SCALE_THRESHOLD) && (v.z < PLF_SCALE_THRESHOLD) &&
+                          (v.w < PLF_SCALE_THRESHOLD);
+        const int fire = per_rate ? below : group_and(below, R);
+        if (fire)
+        {
+          v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
+          v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
+        }
+        if (n < op.nsites)
+        {
+          if (per_rate)
+            op.parent_scaler[(size_t)n * R + rate] = fire ? 1u : 0u;
+          else if (rate == 0)
+            op.parent_scaler[n] = fire ? 1u : 0u;
+        }
+      }
+      /* odd sites store their halves in the other order: each 16-byte store instruction covers all banks */
+      const double2 h0 = make_double2(v.x, v.y), h1 = make_double2(v.z, v.w);
+      *reinterpret_cast<double2 *>(buf + (size_t)item * 32 + 16 * swz) = swz ? h1 : h0;
+      *reinterpret_cast<double2 *>(buf + (size_t)item * 32 + 16 * (swz ^ 1)) = swz ? h0 : h1;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      const unsigned int n = min((unsigned int)TILE, op.nsites - first);
+      bulk_s2g(op.parent_clv + (size_t)first * R * 4, buf, n * R * 32);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 /* A virtual cherry's own "operation": its CLV is never written.  The two P-matrices it was asked to be
  * computed with are copied into the node's side buffer (consumers and a later materialisation read them
  * there, so a P-matrix update in between changes nothing), and its scaler is zeroed as the reference's
@@ -1052,28 +1152,34 @@ static dna_kernel_t pick_stream_kernel_items(unsigned int kind, int nstage, int 
   return pick_stream_kernel_stages<LOG2R, 4>(kind, nstage, smem, tile);
 }
 
-/* consumers of virtual cherries (rate_cats <= 4): ring of CHERRY_STAGES stages, `items` 2 or 4 */
-#define CHERRY_STAGES 6
-template <int LOG2R, int LK, int RK>
+/* consumers of virtual cherries (rate_cats <= 4): ring of 6 (default) or 4 stages, `items` 2 or 4 */
+template <int LOG2R, int LK, int RK, int NSTAGE>
 static dna_kernel_t pick_cherry_items(int items, size_t * smem, unsigned int * tile)
 {
   if (items == 4)
   {
-    *smem = StreamLayout<LOG2R, LK, RK, 4>::smem_bytes(CHERRY_STAGES);
+    *smem = StreamLayout<LOG2R, LK, RK, 4>::smem_bytes(NSTAGE);
     *tile = StreamLayout<LOG2R, LK, RK, 4>::TILE;
-    return k_clv_dna_stream<LOG2R, LK, RK, CHERRY_STAGES, 4>;
+    return k_clv_dna_stream<LOG2R, LK, RK, NSTAGE, 4>;
   }
-  *smem = StreamLayout<LOG2R, LK, RK, 2>::smem_bytes(CHERRY_STAGES);
+  *smem = StreamLayout<LOG2R, LK, RK, 2>::smem_bytes(NSTAGE);
   *tile = StreamLayout<LOG2R, LK, RK, 2>::TILE;
-  return k_clv_dna_stream<LOG2R, LK, RK, CHERRY_STAGES, 2>;
+  return k_clv_dna_stream<LOG2R, LK, RK, NSTAGE, 2>;
+}
+
+template <int LOG2R, int NSTAGE>
+static dna_kernel_t pick_cherry_kind(unsigned int kind, int items, size_t * smem, unsigned int * tile)
+{
+  if (kind == PLF_OP_CI) return pick_cherry_items<LOG2R, CK_C, CK_I, NSTAGE>(items, smem, tile);
+  if (kind == PLF_OP_TC) return pick_cherry_items<LOG2R, CK_T, CK_C, NSTAGE>(items, smem, tile);
+  return pick_cherry_items<LOG2R, CK_C, CK_C, NSTAGE>(items, smem, tile);
 }
 
 template <int LOG2R>
-static dna_kernel_t pick_cherry_kernel(unsigned int kind, int items, size_t * smem, unsigned int * tile)
+static dna_kernel_t pick_cherry_kernel(unsigned int kind, int items, int stages, size_t * smem, unsigned int * tile)
 {
-  if (kind == PLF_OP_CI) return pick_cherry_items<LOG2R, CK_C, CK_I>(items, smem, tile);
-  if (kind == PLF_OP_TC) return pick_cherry_items<LOG2R, CK_T, CK_C>(items, smem, tile);
-  return pick_cherry_items<LOG2R, CK_C, CK_C>(items, smem, tile);
+  if (stages == 4) return pick_cherry_kind<LOG2R, 4>(kind, items, smem, tile);
+  return pick_cherry_kind<LOG2R, 6>(kind, items, smem, tile);
 }
 
 static int env_int(const char * name, int dflt)
@@ -1094,6 +1200,8 @@ static void dna_read_switches(plf_ctx * ctx)
   ctx->dna_tt_seq = env_int("PLF_TT_SEQ", 1);
   ctx->dna_balanced = env_int("PLF_DNA_BALANCED", 1);
   ctx->dna_cherry_items = env_int("PLF_CHERRY_ITEMS", 2) == 4 ? 4 : 2;
+  ctx->dna_cherry_stages = env_int("PLF_CHERRY_STAGES", 6) == 4 ? 4 : 6;
+  ctx->dna_cherry_bulk = env_int("PLF_CHERRY_BULK", 1);
   if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
 }
 
@@ -1141,11 +1249,39 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
     dna_kernel_t k = nullptr;
     size_t smem = 0;
     unsigned int tile = 0;
+    if (kind != PLF_OP_CI && ctx->dna_cherry_bulk)
+    {
+      /* no CLV comes in: tiles built in shared memory and sent off by bulk stores */
+      const int lc = (kind == PLF_OP_CC);
+      switch (log2r)
+      {
+        case 0: k = lc ? k_clv_dna_lookup_bulk<0, 2, 4, 1> : k_clv_dna_lookup_bulk<0, 2, 4, 0>; break;
+        case 1: k = lc ? k_clv_dna_lookup_bulk<1, 2, 4, 1> : k_clv_dna_lookup_bulk<1, 2, 4, 0>; break;
+        default: k = lc ? k_clv_dna_lookup_bulk<2, 2, 4, 1> : k_clv_dna_lookup_bulk<2, 2, 4, 0>; break;
+      }
+      smem = (size_t)4 * 8192 + ((size_t)(lc ? 1024 : 64) + 1024 + 128) * rate_cats * sizeof(double);
+      tile = (DNA_THREADS * 2u) >> log2r;
+      int & occ = ctx->dna_cherry_occupancy[kind - PLF_OP_CI][log2r];
+      if (!occ)
+      {
+        PLF_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, DNA_THREADS, smem));
+        if (occ < 1) occ = 1;
+      }
+      const unsigned long long ntiles = ((unsigned long long)max_sites + tile - 1) / tile;
+      unsigned long long bx = ((unsigned long long)ctx->sm_count * occ) / nops;
+      if (bx < 1) bx = 1;
+      if (bx > ntiles) bx = ntiles;
+      k<<<dim3((unsigned int)bx, nops), DNA_THREADS, smem, ctx->stream>>>(d_ops, per_rate);
+      plf_count_launch();
+      PLF_CHECK(ctx, cudaGetLastError());
+      return 1;
+    }
     switch (log2r)
     {
-      case 0: k = pick_cherry_kernel<0>(kind, ctx->dna_cherry_items, &smem, &tile); break;
-      case 1: k = pick_cherry_kernel<1>(kind, ctx->dna_cherry_items, &smem, &tile); break;
-      default: k = pick_cherry_kernel<2>(kind, ctx->dna_cherry_items, &smem, &tile); break;
+      case 0: k = pick_cherry_kernel<0>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile); break;
+      case 1: k = pick_cherry_kernel<1>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile); break;
+      default: k = pick_cherry_kernel<2>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile); break;
     }
     int & occ = ctx->dna_cherry_occupancy[kind - PLF_OP_CI][log2r];
     if (!occ)

@@ -61,14 +61,23 @@ CHERRY_CASES = [
 ]
 
 
+CHERRY_VARIANTS = {
+    "default": {},                                                  # write-only consumers through bulk stores
+    "items4": {"PLF_CHERRY_ITEMS": "4"},                            # 128-site tiles in the ring consumers
+    "ring": {"PLF_CHERRY_BULK": "0"},                               # every consumer through the ring kernel
+    "ring-stages4-items4": {"PLF_CHERRY_BULK": "0", "PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4"},
+}
+
+
 @pytest.mark.parametrize("case", CHERRY_CASES, ids=lambda c: "-".join(map(str, c)))
-@pytest.mark.parametrize("items", ["2", "4"])
-def test_virtual_cherries_parity(reflib, cudalib, monkeypatch, case, items):
+@pytest.mark.parametrize("variant", list(CHERRY_VARIANTS))
+def test_virtual_cherries_parity(reflib, cudalib, monkeypatch, case, variant):
     """Tip-tip parents are not written: consumers of every kind (tip + cherry, cherry +
     inner, cherry + cherry), scalers, edge logL before anything is materialised, then every CLV bit for bit."""
     tips, sites, tree, cats, per_rate = case
     monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
-    monkeypatch.setenv("PLF_CHERRY_ITEMS", items)
+    for k, v in CHERRY_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
     ds = synth.dna_dataset(tips, sites, seed=100 + tips, tree_kind=tree, alpha=0.4, cats=cats)
     ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
     assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
