@@ -354,20 +354,44 @@ __device__ __forceinline__ RidCtx rid_ctx(const plf_rid_job_t & jb, unsigned int
 }
 #define RID_KEY(c, s) ((c).idl[(s)] + (c).idr[(s)] * (c).ids_left)
 
-__global__ void k_rid_min(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
-                          const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
-                          unsigned int tag)
+/* work items of the per-site passes: (job, chunk of RID_CHUNK sites); a persistent grid strides over them, so
+ * a level of hundreds of small jobs and a level of one large job fill the chip alike */
+#define RID_CHUNK 4096u
+#define RID_THREADS 256
+
+__global__ void __launch_bounds__(RID_THREADS)
+k_rid_min(const plf_rid_job_t * __restrict__ jobs, unsigned int njobs, unsigned int sites, unsigned int lookup_size,
+          const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool, unsigned int tag)
 {
-  const RidCtx c = rid_ctx(jobs[blockIdx.y], sites, lookup_size, node_ids, pool);
-  if (!c.enabled) return;
+  const unsigned int chunks = (sites + RID_CHUNK - 1) / RID_CHUNK;
   const unsigned long long hi = (unsigned long long)tag << 32;
-  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
+  for (unsigned int w = blockIdx.x; w < njobs * chunks; w += gridDim.x)
   {
-    /* sites are visited in increasing order, so most of them find their class already claimed by an earlier
-     * site of this pass: a plain L2 read then spares the atomic (and the serialisation on popular keys) */
-    unsigned long long * e = &c.lookup[RID_KEY(c, s)];
-    const unsigned long long mine = hi | s;
-    if (__ldcg(e) > mine) atomicMin(e, mine);
+    const RidCtx c = rid_ctx(jobs[w / chunks], sites, lookup_size, node_ids, pool);
+    if (!c.enabled) continue;
+    const unsigned int lo = (w % chunks) * RID_CHUNK, end = min(lo + RID_CHUNK, sites);
+    /* four sites in flight per thread: identifiers of both children, then the lookup entry.  Sites are visited
+     * in increasing order, so most of them find their class already claimed by an earlier site of this pass:
+     * the plain L2 read then spares the atomic (and the serialisation on popular keys) */
+    for (unsigned int s0 = lo + threadIdx.x; s0 < end; s0 += 4 * RID_THREADS)
+    {
+      unsigned long long * e[4];
+      unsigned long long seen[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const unsigned int s = s0 + u * RID_THREADS;
+        e[u] = s < end ? &c.lookup[RID_KEY(c, s)] : nullptr;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) seen[u] = e[u] ? __ldcg(e[u]) : 0ull;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const unsigned long long mine = hi | (s0 + u * RID_THREADS);
+        if (e[u] && seen[u] > mine) atomicMin(e[u], mine);
+      }
+    }
   }
 }
 
@@ -444,59 +468,96 @@ __global__ void k_rid_scan(const plf_rid_job_t * __restrict__ jobs, unsigned int
  * Rank of every first occurrence within its 1024-site tile by ballots (one bit per site), plus the tile's
  * offset: the class number.  It goes to id_site_parent[rank] = site and to rank_pool[key], a table with the
  * lookup pool's index space, from which k_rid_assign reads every site's class with ONE gather. */
-__global__ void k_rid_rank(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
-                           const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
-                           const unsigned int * __restrict__ tile_count_all, unsigned int ntiles,
-                           unsigned int * __restrict__ rank_pool)
+__global__ void __launch_bounds__(RID_THREADS)
+k_rid_rank(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
+           const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+           const unsigned int * __restrict__ tile_count_all, unsigned int ntiles, unsigned int * __restrict__ rank_pool)
 {
   const plf_rid_job_t jb = jobs[blockIdx.y];
   const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
   if (!c.enabled) return;
   const unsigned int * tile_offset = tile_count_all + (size_t)blockIdx.y * ntiles;
   unsigned int * rank_of_key = rank_pool + jb.lookup_offset;
-  __shared__ unsigned int warp_count[SCAN_TILE / 32];
-  const unsigned int s = blockIdx.x * SCAN_TILE + threadIdx.x;
+  /* a tile is 4 rows of 256 sites; thread t owns site t of every row (four independent load chains);
+   * counts[row * 8 + warp] in site order */
+  __shared__ unsigned int counts[32];
   const unsigned int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned int key = 0;
-  bool f = false;
-  if (s < sites)
+  const unsigned int base = blockIdx.x * SCAN_TILE;
+  unsigned int key[4], bal[4];
+  bool f[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
   {
-    key = RID_KEY(c, s);
-    f = (unsigned int)c.lookup[key] == s;
+    const unsigned int s = base + u * RID_THREADS + threadIdx.x;
+    key[u] = s < sites ? RID_KEY(c, s) : 0u;
   }
-  const unsigned int bal = __ballot_sync(0xffffffffu, f);
-  if (lane == 0) warp_count[w] = __popc(bal);
+  unsigned long long ent[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+  {
+    const unsigned int s = base + u * RID_THREADS + threadIdx.x;
+    ent[u] = s < sites ? c.lookup[key[u]] : ~0ull;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+  {
+    const unsigned int s = base + u * RID_THREADS + threadIdx.x;
+    f[u] = s < sites && (unsigned int)ent[u] == s;
+    bal[u] = __ballot_sync(0xffffffffu, f[u]);
+    if (lane == 0) counts[u * 8 + w] = __popc(bal[u]);
+  }
   __syncthreads();
   if (w == 0)
   {
-    /* exclusive scan of the 32 warp counts */
-    unsigned int v = warp_count[lane], x = v;
+    /* exclusive scan of the 32 counts */
+    unsigned int v = counts[lane], x = v;
     for (int o = 1; o < 32; o <<= 1)
     {
       const unsigned int t = __shfl_up_sync(0xffffffffu, x, o);
       if ((int)lane >= o) x += t;
     }
-    warp_count[lane] = x - v;
+    counts[lane] = x - v;
   }
   __syncthreads();
-  if (f)
-  {
-    const unsigned int r = tile_offset[blockIdx.x] + warp_count[w] + __popc(bal & ((1u << lane) - 1u));
-    rank_of_key[key] = r;
-    jb.id_site_parent[r] = s;
-  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (f[u])
+    {
+      const unsigned int r = tile_offset[blockIdx.x] + counts[u * 8 + w] + __popc(bal[u] & ((1u << lane) - 1u));
+      rank_of_key[key[u]] = r;
+      jb.id_site_parent[r] = base + u * RID_THREADS + threadIdx.x;
+    }
 }
 
-__global__ void k_rid_assign(const plf_rid_job_t * __restrict__ jobs, unsigned int sites, unsigned int lookup_size,
-                             const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
-                             const unsigned int * __restrict__ rank_pool)
+__global__ void __launch_bounds__(RID_THREADS)
+k_rid_assign(const plf_rid_job_t * __restrict__ jobs, unsigned int njobs, unsigned int sites, unsigned int lookup_size,
+             const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+             const unsigned int * __restrict__ rank_pool)
 {
-  const plf_rid_job_t jb = jobs[blockIdx.y];
-  const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
-  if (!c.enabled) return;
-  const unsigned int * rank_of_key = rank_pool + jb.lookup_offset;
-  for (unsigned int s = blockIdx.x * blockDim.x + threadIdx.x; s < sites; s += gridDim.x * blockDim.x)
-    jb.site_id_parent[s] = rank_of_key[RID_KEY(c, s)];
+  const unsigned int chunks = (sites + RID_CHUNK - 1) / RID_CHUNK;
+  for (unsigned int w = blockIdx.x; w < njobs * chunks; w += gridDim.x)
+  {
+    const plf_rid_job_t jb = jobs[w / chunks];
+    const RidCtx c = rid_ctx(jb, sites, lookup_size, node_ids, pool);
+    if (!c.enabled) continue;
+    const unsigned int * rank_of_key = rank_pool + jb.lookup_offset;
+    const unsigned int lo = (w % chunks) * RID_CHUNK, end = min(lo + RID_CHUNK, sites);
+    for (unsigned int s0 = lo + threadIdx.x; s0 < end; s0 += 4 * RID_THREADS)
+    {
+      unsigned int key[4], r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const unsigned int s = s0 + u * RID_THREADS;
+        key[u] = s < end ? RID_KEY(c, s) : 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = key[u] != 0xFFFFFFFFu ? rank_of_key[key[u]] : 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (key[u] != 0xFFFFFFFFu) jb.site_id_parent[s0 + u * RID_THREADS] = r[u];
+    }
+  }
 }
 
 extern "C" size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int njobs)
@@ -515,18 +576,19 @@ extern "C" int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned in
   const unsigned int ntiles = (sites + SCAN_TILE - 1) / SCAN_TILE;
   unsigned int * tile = (unsigned int *)d_scratch;
   const plf_rid_job_t * jobs = d_jobs + first_job;
-  unsigned int blocks = (sites + 255) / 256;
-  const unsigned int cap = (unsigned int)ctx->sm_count * 8;
-  const unsigned int share = cap / njobs > 4 ? cap / njobs : 4; /* one wave over the whole batch */
-  if (blocks > share) blocks = share;
-  const dim3 gs(blocks, njobs), gt(ntiles, njobs);
-  k_rid_min<<<gs, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tag);
+  const unsigned int chunks = (sites + RID_CHUNK - 1) / RID_CHUNK;
+  unsigned long long items = (unsigned long long)njobs * chunks;
+  const unsigned int cap = (unsigned int)ctx->sm_count * 8; /* resident CTAs of 256 threads */
+  const unsigned int grid = (unsigned int)(items < cap ? items : cap);
+  const dim3 gt(ntiles, njobs);
+  k_rid_min<<<grid, RID_THREADS, 0, ctx->stream>>>(jobs, njobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tag);
   k_rid_count<<<gt, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile, ntiles);
   k_rid_scan<<<dim3(1, njobs), 1024, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile,
                                                        ntiles, d_raw_ids + first_job);
-  k_rid_rank<<<gt, SCAN_TILE, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile, ntiles,
-                                               d_rank_pool);
-  k_rid_assign<<<gs, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, d_rank_pool);
+  k_rid_rank<<<gt, RID_THREADS, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile, ntiles,
+                                                 d_rank_pool);
+  k_rid_assign<<<grid, RID_THREADS, 0, ctx->stream>>>(jobs, njobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool,
+                                                     d_rank_pool);
   for (int i = 0; i < 5; ++i) plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;
