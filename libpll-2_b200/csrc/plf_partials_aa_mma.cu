@@ -331,9 +331,9 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
   __shared__ int flags[2][TILE][R];
   unsigned char * ring = dyn;
   /* tables behind the ring: tip table of a left tip [maxstates][R][AAM_TAB_STRIDE], then the half tables of
-   * the cherries [maxstates][R][20] each: left tip A, left tip B, right tip A, right tip B */
+   * the cherries [maxstates][R][AAM_TAB_STRIDE] each: left tip A, left tip B, right tip A, right tip B */
   double * tl = reinterpret_cast<double *>(dyn + (size_t)AAS_NSTAGE * STAGE);
-  const int half = maxstates * R * 20;
+  const int half = maxstates * R * AAM_TAB_STRIDE; /* rows 22 doubles apart: codes spread over the banks */
   double * hl1 = tl + (LK == AK_T ? maxstates * R * AAM_TAB_STRIDE : 0);
   double * hl2 = hl1 + (LK == AK_C ? half : 0);
   double * hr1 = hl2 + (LK == AK_C ? half : 0);
@@ -370,17 +370,17 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
     /* scalar sums in increasing column order, as the reference's tip-tip table (src/core_partials_avx.c:124-253) */
     for (int e = threadIdx.x; e < half; e += blockDim.x)
     {
-      const int c = e / (R * 20), r = (e / 20) % R, i = e % 20;
+      const int c = e / (R * AAM_TAB_STRIDE), r = (e / AAM_TAB_STRIDE) % R, i = e % AAM_TAB_STRIDE;
       const plf_state_t mask = tipmap[c];
       if (LK == AK_C)
       {
-        hl1[e] = masked_sum_seq(op.left_cm1 + r * 400 + i * 20, mask, 20);
-        hl2[e] = masked_sum_seq(op.left_cm2 + r * 400 + i * 20, mask, 20);
+        hl1[e] = (i < 20) ? masked_sum_seq(op.left_cm1 + r * 400 + i * 20, mask, 20) : 0.0;
+        hl2[e] = (i < 20) ? masked_sum_seq(op.left_cm2 + r * 400 + i * 20, mask, 20) : 0.0;
       }
       if (RK == AK_C)
       {
-        hr1[e] = masked_sum_seq(op.right_cm1 + r * 400 + i * 20, mask, 20);
-        hr2[e] = masked_sum_seq(op.right_cm2 + r * 400 + i * 20, mask, 20);
+        hr1[e] = (i < 20) ? masked_sum_seq(op.right_cm1 + r * 400 + i * 20, mask, 20) : 0.0;
+        hr2[e] = (i < 20) ? masked_sum_seq(op.right_cm2 + r * 400 + i * 20, mask, 20) : 0.0;
       }
     }
   }
@@ -430,8 +430,8 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
 
   /* A fragment of a virtual cherry: entry k = hA[codeA][rate][k] * hB[codeB][rate][k] for the lane's 5 states */
   auto cherry_frag = [&](double (&a)[5], const double * h1, const double * h2, unsigned int c1, unsigned int c2) {
-    const double * p1 = h1 + ((size_t)c1 * R + rate) * 20;
-    const double * p2 = h2 + ((size_t)c2 * R + rate) * 20;
+    const double * p1 = h1 + ((size_t)c1 * R + rate) * AAM_TAB_STRIDE;
+    const double * p2 = h2 + ((size_t)c2 * R + rate) * AAM_TAB_STRIDE;
     const double2 u0 = *reinterpret_cast<const double2 *>(p1 + 2 * q), w0 = *reinterpret_cast<const double2 *>(p2 + 2 * q);
     const double2 u1 = *reinterpret_cast<const double2 *>(p1 + 8 + 2 * q), w1 = *reinterpret_cast<const double2 *>(p2 + 8 + 2 * q);
     a[0] = u0.x * w0.x;
@@ -731,7 +731,7 @@ static size_t aas_smem_bytes(unsigned int kind, unsigned int rate_cats, int nwar
   const int cherries = (kind == PLF_OP_CI || kind == PLF_OP_TC) ? 1 : kind == PLF_OP_CC ? 2 : 0;
   size_t smem = (size_t)AAS_NSTAGE * (left_inner + right_inner) * 1280 * nwarps;
   if (left_tip) smem += (size_t)maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);
-  smem += (size_t)cherries * 2 * maxstates * rate_cats * 20 * sizeof(double);
+  smem += (size_t)cherries * 2 * maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);
   return smem;
 }
 
