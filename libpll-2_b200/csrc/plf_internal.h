@@ -24,7 +24,7 @@ struct plf_ctx
   int dna_cherry_occupancy[3][3]; /* consumers of virtual cherries [CI, TC, CC][log2 rates] */
   int dna_cherry_items;           /* PLF_CHERRY_ITEMS: 2 (default) or 4 (site, rate) blocks per thread and tile */
   int dna_cherry_stages;          /* PLF_CHERRY_STAGES: 6 (default) or 4 ring stages */
-  int dna_cherry_bulk;            /* PLF_CHERRY_BULK=0: tip + cherry / cherry + cherry through the ring kernel */
+  int dna_cherry_bulk;            /* PLF_CHERRY_BULK=1: tip + cherry / cherry + cherry through the bulk-store kernel instead of the ring kernel */
   int dna_cherry;                 /* PLF_VIRTUAL_CHERRIES=0 writes every tip-tip parent to HBM */
   int dna_tt_bulk_occupancy[4];
   int dna_balanced_occupancy[2][6]; /* [three id arrays, pair list][log2 rates] */

@@ -986,7 +986,9 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
   }
 }
 
-/* ---- write-only consumers of virtual cherries: tip + cherry, cherry + cherry ----------------------- *
+/* ---- write-only consumers of virtual cherries: tip + cherry, cherry + cherry (PLF_CHERRY_BULK=1) ----- *
+ * NOT the default: at 3 CTAs per SM (32 KB of output tiles + a 32 KB table) and two block barriers per tile   *
+ * it runs the 21 such ops of a config-2 traversal 0.53 ms slower than the ring kernel (profiles/r2_notes.md). *
  * Neither child is a CLV: the parent is a product of two table rows, 3 or 4 bytes of tip codes in, 132 bytes   *
  * out per site.  Same shape as the tip-tip kernel above (tiles assembled in shared memory, one bulk async      *
  * store each, NOUT in flight, codes of the next tile fetched while the current one is built), plus what a      *
@@ -1201,7 +1203,7 @@ static void dna_read_switches(plf_ctx * ctx)
   ctx->dna_balanced = env_int("PLF_DNA_BALANCED", 1);
   ctx->dna_cherry_items = env_int("PLF_CHERRY_ITEMS", 2) == 4 ? 4 : 2;
   ctx->dna_cherry_stages = env_int("PLF_CHERRY_STAGES", 6) == 4 ? 4 : 6;
-  ctx->dna_cherry_bulk = env_int("PLF_CHERRY_BULK", 1);
+  ctx->dna_cherry_bulk = env_int("PLF_CHERRY_BULK", 0); /* measured slower than the ring kernel: profiles/r2_notes.md */
   if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
 }
 

@@ -62,10 +62,10 @@ CHERRY_CASES = [
 
 
 CHERRY_VARIANTS = {
-    "default": {},                                                  # write-only consumers through bulk stores
-    "items4": {"PLF_CHERRY_ITEMS": "4"},                            # 128-site tiles in the ring consumers
-    "ring": {"PLF_CHERRY_BULK": "0"},                               # every consumer through the ring kernel
-    "ring-stages4-items4": {"PLF_CHERRY_BULK": "0", "PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4"},
+    "default": {},                                                  # every consumer through the ring kernel
+    "items4": {"PLF_CHERRY_ITEMS": "4"},                            # 128-site tiles
+    "bulk": {"PLF_CHERRY_BULK": "1"},                               # write-only consumers through bulk stores
+    "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4"},
 }
 
 
