@@ -250,8 +250,18 @@ typedef struct plf_rid_job
 size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int njobs);
 int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned int lookup_buffer_size,
                      const plf_rid_job_t * d_jobs, unsigned int first_job, unsigned int njobs,
-                     unsigned long long * d_lookup_pool, unsigned int * d_rank_pool, unsigned int tag,
+                     unsigned long long * d_lookup_pool, unsigned int * d_rank_pool,
+                     const unsigned int * d_tag_base, unsigned int tag_offset,
                      unsigned int * d_node_ids, unsigned int * d_raw_ids, void * d_scratch);
+/* the tag of a pass is *d_tag_base + tag_offset; one call per identifier update lowers the base by the number
+ * of passes of the update (a launch on the stream: part of the update's graph) */
+int plf_repeats_advance_tags(plf_ctx_t * ctx, unsigned int * d_tag_base, unsigned int n);
+/* stream capture / replay of a sequence of launches queued through this backend */
+int plf_capture_begin(plf_ctx_t * ctx);
+int plf_capture_end(plf_ctx_t * ctx, void ** exec_out);
+int plf_capture_abort(plf_ctx_t * ctx);
+int plf_graph_replay(plf_ctx_t * ctx, void * exec, unsigned long long launches);
+void plf_graph_free(void * exec);
 /* pair list of a gathering op: out[2n] / out[2n+1] = entry of the left / right child that parent entry n
  * reads (parent_id_site, left_site_id, right_site_id may each be NULL = identity) */
 typedef struct plf_pair_job

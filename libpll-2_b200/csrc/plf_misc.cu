@@ -361,10 +361,13 @@ __device__ __forceinline__ RidCtx rid_ctx(const plf_rid_job_t & jb, unsigned int
 
 __global__ void __launch_bounds__(RID_THREADS)
 k_rid_min(const plf_rid_job_t * __restrict__ jobs, unsigned int njobs, unsigned int sites, unsigned int lookup_size,
-          const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool, unsigned int tag)
+          const unsigned int * __restrict__ node_ids, unsigned long long * __restrict__ pool,
+          const unsigned int * __restrict__ tag_base, unsigned int tag_offset)
 {
   const unsigned int chunks = (sites + RID_CHUNK - 1) / RID_CHUNK;
-  const unsigned long long hi = (unsigned long long)tag << 32;
+  /* the tag lives in device memory so that a captured graph of the whole identifier update can be replayed:
+   * k_rid_advance lowers the base once per update, every pass of the update adds its own fixed offset */
+  const unsigned long long hi = (unsigned long long)(*tag_base + tag_offset) << 32;
   for (unsigned int w = blockIdx.x; w < njobs * chunks; w += gridDim.x)
   {
     const RidCtx c = rid_ctx(jobs[w / chunks], sites, lookup_size, node_ids, pool);
@@ -560,6 +563,67 @@ k_rid_assign(const plf_rid_job_t * __restrict__ jobs, unsigned int njobs, unsign
   }
 }
 
+__global__ void k_rid_advance(unsigned int * tag_base, unsigned int n) { *tag_base -= n; }
+
+extern "C" int plf_repeats_advance_tags(plf_ctx_t * ctx, unsigned int * d_tag_base, unsigned int n)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  k_rid_advance<<<1, 1, 0, ctx->stream>>>(d_tag_base, n);
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
+/* stream capture of a sequence of launches queued through this backend, for callers that repeat it */
+extern "C" int plf_capture_begin(plf_ctx_t * ctx)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  return 1;
+}
+extern "C" int plf_capture_end(plf_ctx_t * ctx, void ** exec_out)
+{
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  *exec_out = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (e != cudaSuccess || !graph)
+  {
+    cudaGetLastError();
+    plf_set_error(ctx, "stream capture failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess)
+  {
+    cudaGetLastError();
+    plf_set_error(ctx, "graph instantiation failed: %s", cudaGetErrorString(e2));
+    return 0;
+  }
+  *exec_out = exec;
+  return 1;
+}
+extern "C" int plf_capture_abort(plf_ctx_t * ctx)
+{
+  cudaGraph_t graph = nullptr;
+  cudaStreamEndCapture(ctx->stream, &graph);
+  if (graph) cudaGraphDestroy(graph);
+  cudaGetLastError();
+  return 1;
+}
+extern "C" int plf_graph_replay(plf_ctx_t * ctx, void * exec, unsigned long long launches)
+{
+  PLF_CHECK(ctx, cudaSetDevice(ctx->device));
+  PLF_CHECK(ctx, cudaGraphLaunch((cudaGraphExec_t)exec, ctx->stream));
+  plf_count_launches(launches);
+  return 1;
+}
+extern "C" void plf_graph_free(void * exec)
+{
+  if (exec) cudaGraphExecDestroy((cudaGraphExec_t)exec);
+}
+
 extern "C" size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int njobs)
 {
   const size_t ntiles = ((size_t)sites + SCAN_TILE - 1) / SCAN_TILE;
@@ -568,7 +632,8 @@ extern "C" size_t plf_repeats_pass_workspace(unsigned int sites, unsigned int nj
 
 extern "C" int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned int lookup_buffer_size,
                                 const plf_rid_job_t * d_jobs, unsigned int first_job, unsigned int njobs,
-                                unsigned long long * d_lookup_pool, unsigned int * d_rank_pool, unsigned int tag,
+                                unsigned long long * d_lookup_pool, unsigned int * d_rank_pool,
+                                const unsigned int * d_tag_base, unsigned int tag_offset,
                                 unsigned int * d_node_ids, unsigned int * d_raw_ids, void * d_scratch)
 {
   if (!njobs) return 1;
@@ -581,7 +646,8 @@ extern "C" int plf_repeats_pass(plf_ctx_t * ctx, unsigned int sites, unsigned in
   const unsigned int cap = (unsigned int)ctx->sm_count * 8; /* resident CTAs of 256 threads */
   const unsigned int grid = (unsigned int)(items < cap ? items : cap);
   const dim3 gt(ntiles, njobs);
-  k_rid_min<<<grid, RID_THREADS, 0, ctx->stream>>>(jobs, njobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tag);
+  k_rid_min<<<grid, RID_THREADS, 0, ctx->stream>>>(jobs, njobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool,
+                                                  d_tag_base, tag_offset);
   k_rid_count<<<gt, 256, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile, ntiles);
   k_rid_scan<<<dim3(1, njobs), 1024, 0, ctx->stream>>>(jobs, sites, lookup_buffer_size, d_node_ids, d_lookup_pool, tile,
                                                        ntiles, d_raw_ids + first_job);

@@ -147,7 +147,17 @@ typedef struct cuda_partition
   unsigned long long * d_lookup64;        /* tagged lookup pool */
   unsigned int * d_rank_pool;             /* class number per lookup key, same index space */
   unsigned long long lookup64_entries;
-  unsigned int rid_tag;                   /* next tag: decreasing, every pass below all earlier ones */
+  unsigned int rid_tag;                   /* host view of *d_rid_tag: tags below it are unused */
+  unsigned int * d_rid_tag;               /* tag base in device memory (read by k_rid_min, lowered once per update) */
+  /* one CUDA graph per repeated identifier update (same jobs, same pool): the ~5 launches per level are replayed */
+  plf_rid_job_t * rid_graph_jobs;         /* host copy of the jobs of the last update */
+  unsigned int * rid_graph_parts;         /* its part boundaries */
+  unsigned int rid_graph_count, rid_graph_nparts, rid_graph_cap;
+  unsigned long long * rid_graph_pool;
+  void * rid_graph_scratch;
+  void * rid_graph_exec;
+  unsigned long long rid_graph_launches;
+  int rid_graph_mode;                     /* $PLF_GRAPH=0: plain launches */
   void * d_rid_scratch;
   size_t rid_scratch_bytes;
   int rid_fast;                           /* $PLL_CUDA_REPEATS_LEVEL_SYNC=1 keeps one host synchronisation per level */
@@ -396,6 +406,10 @@ static void free_repeats(cuda_partition_t * cp)
   plf_free(cp->ctx, cp->d_lookup64);
   plf_free(cp->ctx, cp->d_rank_pool);
   plf_free(cp->ctx, cp->d_rid_scratch);
+  plf_free(cp->ctx, cp->d_rid_tag);
+  plf_graph_free(cp->rid_graph_exec);
+  free(cp->rid_graph_jobs);
+  free(cp->rid_graph_parts);
   plf_free(cp->ctx, cp->d_lookup);
   plf_free(cp->ctx, cp->d_lookup_pool);
   plf_free(cp->ctx, cp->d_keys);
@@ -528,7 +542,14 @@ static int repeats_initialize(cuda_partition_t * cp)
   cp->ids_version = (unsigned long long *)calloc(p->nodes, sizeof(unsigned long long));
   cp->rid_fast = !env_flag("PLL_CUDA_REPEATS_LEVEL_SYNC");
   cp->rid_tag = 0xFFFFFFFEu;
-  if (!cp->d_keys || !cp->d_rep_charmap || !cp->d_node_ids || !cp->pairs || !cp->ids_version) return PLL_FAILURE;
+  cp->d_rid_tag = (unsigned int *)plf_alloc(cp->ctx, sizeof(unsigned int), 0);
+  {
+    const char * v = getenv("PLF_GRAPH");
+    cp->rid_graph_mode = !(v && v[0] == '0');
+  }
+  if (!cp->d_keys || !cp->d_rep_charmap || !cp->d_node_ids || !cp->pairs || !cp->ids_version || !cp->d_rid_tag ||
+      !plf_upload(cp->ctx, cp->d_rid_tag, &cp->rid_tag, sizeof(unsigned int)))
+    return PLL_FAILURE;
   /* the first traversal sizes every CLV and scaler to its class count (~2 allocations per node): warm the
    * pool with a quarter of the uncompressed CLV volume so that they do not each grow it through the driver */
   plf_pool_reserve(cp->ctx, (size_t)p->nodes * p->sites * p->rate_cats * p->states_padded * sizeof(double) / 4);
@@ -1187,6 +1208,11 @@ static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * op
     }
     cp->lookup64_entries = need_pool;
     cp->rid_tag = 0xFFFFFFFEu;
+    if (!plf_upload(cp->ctx, cp->d_rid_tag, &cp->rid_tag, sizeof(unsigned int)))
+    {
+      cuda_fail(cp);
+      goto done;
+    }
   }
   if (cp->rid_cap < count)
   {
@@ -1254,26 +1280,101 @@ static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * op
     cuda_fail(cp);
     goto done;
   }
-  for (i = 0; i < count;)
+  /* parts of the update: [parts[k], parts[k+1]) are the jobs of one pass */
   {
-    const unsigned int end = level[i];
-    if (cp->rid_tag == 0)
+    unsigned int nparts = 0, k;
+    int same, replay = 0;
+    for (i = 0; i < count; i = level[i]) ++nparts;
+    /* tags: every pass of this update below every tag used so far */
+    if (cp->rid_tag < nparts + 1)
     {
-      /* tags exhausted (2^32 passes): start over on a clean pool */
-      if (!plf_fill_u32(cp->ctx, (unsigned int *)cp->d_lookup64, EMPTY_ELEMENT, (size_t)cp->lookup64_entries * 2))
+      /* exhausted (2^32 passes): start over on a clean pool */
+      cp->rid_tag = 0xFFFFFFFEu;
+      if (!plf_fill_u32(cp->ctx, (unsigned int *)cp->d_lookup64, EMPTY_ELEMENT, (size_t)cp->lookup64_entries * 2) ||
+          !plf_upload(cp->ctx, cp->d_rid_tag, &cp->rid_tag, sizeof(unsigned int)))
       {
         cuda_fail(cp);
         goto done;
       }
-      cp->rid_tag = 0xFFFFFFFEu;
     }
-    if (!plf_repeats_pass(cp->ctx, sites, r->lookup_buffer_size, cp->d_rid_jobs, i, end - i, cp->d_lookup64,
-                          cp->d_rank_pool, cp->rid_tag--, cp->d_node_ids, cp->d_raw_ids, cp->d_rid_scratch))
+    /* the same update as the last one (same jobs on the same buffers)?  The second such call is captured into
+     * a graph, later ones replay it: ~5 launches per tree level become one */
+    same = cp->rid_graph_mode && cp->rid_graph_count == count && cp->rid_graph_nparts == nparts &&
+           cp->rid_graph_pool == cp->d_lookup64 && cp->rid_graph_scratch == cp->d_rid_scratch && cp->rid_graph_jobs &&
+           !memcmp(cp->rid_graph_jobs, jobs, (size_t)count * sizeof(plf_rid_job_t));
+    if (same)
+      for (i = 0, k = 0; i < count && same; i = level[i], ++k) same = cp->rid_graph_parts[k] == i;
+    if (same && cp->rid_graph_exec)
+      replay = 1;
+    else if (!same)
     {
-      cuda_fail(cp);
-      goto done;
+      plf_graph_free(cp->rid_graph_exec);
+      cp->rid_graph_exec = NULL;
+      if (cp->rid_graph_cap < count)
+      {
+        free(cp->rid_graph_jobs);
+        free(cp->rid_graph_parts);
+        cp->rid_graph_jobs = (plf_rid_job_t *)malloc((size_t)count * sizeof(plf_rid_job_t));
+        cp->rid_graph_parts = (unsigned int *)malloc(((size_t)count + 1) * sizeof(unsigned int));
+        cp->rid_graph_cap = (cp->rid_graph_jobs && cp->rid_graph_parts) ? count : 0;
+      }
+      cp->rid_graph_count = 0;
+      if (cp->rid_graph_cap >= count)
+      {
+        memcpy(cp->rid_graph_jobs, jobs, (size_t)count * sizeof(plf_rid_job_t));
+        for (i = 0, k = 0; i < count; i = level[i], ++k) cp->rid_graph_parts[k] = i;
+        cp->rid_graph_count = count;
+        cp->rid_graph_nparts = nparts;
+        cp->rid_graph_pool = cp->d_lookup64;
+        cp->rid_graph_scratch = cp->d_rid_scratch;
+      }
     }
-    i = end;
+    if (replay)
+    {
+      if (!plf_graph_replay(cp->ctx, cp->rid_graph_exec, cp->rid_graph_launches))
+      {
+        cuda_fail(cp);
+        goto done;
+      }
+    }
+    else
+    {
+      const int capture = same && plf_capture_begin(cp->ctx);
+      const unsigned long long before = pll_cuda_kernel_launches();
+      int queued = plf_repeats_advance_tags(cp->ctx, cp->d_rid_tag, nparts);
+      for (i = 0, k = 0; i < count && queued; i = level[i], ++k)
+        queued = plf_repeats_pass(cp->ctx, sites, r->lookup_buffer_size, cp->d_rid_jobs, i, level[i] - i, cp->d_lookup64,
+                                  cp->d_rank_pool, cp->d_rid_tag, nparts - 1 - k, cp->d_node_ids, cp->d_raw_ids,
+                                  cp->d_rid_scratch);
+      if (capture)
+      {
+        void * exec = NULL;
+        const unsigned long long captured = pll_cuda_kernel_launches() - before;
+        if (!queued || !plf_capture_end(cp->ctx, &exec))
+        {
+          /* capture is not available here: plain launches from now on */
+          if (!queued) plf_capture_abort(cp->ctx);
+          cp->rid_graph_mode = 0;
+          queued = plf_repeats_advance_tags(cp->ctx, cp->d_rid_tag, nparts);
+          for (i = 0, k = 0; i < count && queued; i = level[i], ++k)
+            queued = plf_repeats_pass(cp->ctx, sites, r->lookup_buffer_size, cp->d_rid_jobs, i, level[i] - i,
+                                      cp->d_lookup64, cp->d_rank_pool, cp->d_rid_tag, nparts - 1 - k, cp->d_node_ids,
+                                      cp->d_raw_ids, cp->d_rid_scratch);
+        }
+        else
+        {
+          cp->rid_graph_exec = exec;
+          cp->rid_graph_launches = captured;
+          queued = plf_graph_replay(cp->ctx, exec, 0); /* the launches were counted while they were captured */
+        }
+      }
+      if (!queued)
+      {
+        cuda_fail(cp);
+        goto done;
+      }
+    }
+    cp->rid_tag -= nparts;
   }
   /* the one synchronisation of the identifier update */
   if (!plf_download(cp->ctx, raw, cp->d_raw_ids, (size_t)count * sizeof(unsigned int)))

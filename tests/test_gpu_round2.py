@@ -495,3 +495,37 @@ def test_pattern_tip_codes_match_reference(reflib, cudalib, monkeypatch, kind, s
     assert np.array_equal(gpu.tipchars(2), before)
     ref.close()
     gpu.close()
+
+
+# ---- repeated identifier updates: captured into a graph and replayed ----------------------------------------
+
+def test_repeated_identifier_updates_replay_a_graph(reflib, cudalib):
+    """pll_update_partials with identifier update on the same list again and again (what a tree search does
+    between topology moves): the second call is captured, later ones replay the graph; a tip whose states change
+    alters the jobs and starts over.  Identifiers, CLVs and scalers against the reference after every stage."""
+    ds = synth.dna_dataset(64, 3000, seed=31, alpha=0.3, brlen=(0.002, 0.05))
+    ref, gpu = pair(reflib, cudalib, ds, capi.SITE_REPEATS)
+
+    def check(what):
+        for node in range(ds.tree.nodes):
+            ids_r, sid_r, is_r = ref.repeat_ids(node)
+            ids_g, sid_g, is_g = gpu.repeat_ids(node)
+            assert ids_r == ids_g, f"{what}: class count of node {node}"
+            if ids_r:
+                assert np.array_equal(sid_r, sid_g) and np.array_equal(is_r, is_g), f"{what}: identifiers of node {node}"
+        compare_all_nodes(ref, gpu)
+        assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, what)
+
+    traverse(ref)
+    for k in range(4):
+        traverse(gpu)
+        check(f"traversal {k}")
+    other = ds.seqs[5]
+    for lib, e in ((reflib, ref), (cudalib, gpu)):
+        assert lib.pll_set_tip_states(e.p, 9, e.map, other) == 1
+    traverse(ref)
+    for k in range(3):
+        traverse(gpu)
+        check(f"after the tip change, traversal {k}")
+    ref.close()
+    gpu.close()
