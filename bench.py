@@ -496,6 +496,26 @@ def config4_record(lib, torch, local, threads):
     return rec
 
 
+def narrow_record(lib, torch, local):
+    """A narrow alignment (100 taxa x 1000 sites, the config-2 model): a traversal is bound by the launch path,
+    not by bytes -- 12 levels of kernels of a few microseconds, replayed as one CUDA graph."""
+    out = {}
+    for sites in (1000, 10000):
+        ds = make_dataset("dna", 100, sites, 1, 0)
+        eng = harness.Engine(lib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+        ext = torch.cuda.ExternalStream(lib.pll_cuda_get_stream(eng.p), device=torch.device("cuda", local))
+        eng.update_pmatrices()
+        us = 1e3 * device_timed(torch, ext, eng.update_partials, reps=200, warm=5)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            eng.full_traversal()
+        e2e_us = 1e6 * (time.perf_counter() - t0) / 200
+        eng.close()
+        out[f"{sites}_sites"] = {"traversal_us": us, "site_updates_per_s": len(ds.tree.ops) * sites / (us * 1e-6),
+                                 "full_evaluation_blocking_api_us": e2e_us}
+    return {"workload": "synthetic DNA 100 taxa x 1000 / 10000 sites GTR+G4, pattern-tip on (launch-bound)", **out}
+
+
 def run_b200_arm(args):
     import torch
 
@@ -777,6 +797,10 @@ def run_b200_arm(args):
     if rank == 0 and world == 1 and not args.no_configs:
         threads = args.cpu_threads or host_threads()
         line["configs"] = {}
+        try:
+            line["configs"]["dna_100_taxa_narrow"] = narrow_record(lib, torch, local)
+        except Exception as e:
+            line["configs"]["dna_100_taxa_narrow"] = {"error": f"{type(e).__name__}: {e}"}
         for name, fn in (("aa_lg4m_200x100k", config3_record), ("repeats_1000x100k_newton", config4_record)):
             try:
                 line["configs"][name] = fn(lib, torch, local, threads)

@@ -758,11 +758,11 @@ k_clv_dna_tt_bulk(const plf_op_t * __restrict__ ops, int per_rate_and_nops)
 enum { CK_I = 0, CK_T = 1, CK_C = 2 };
 
 /* ITEMS = (site, rate) blocks per thread and tile */
-template <int LOG2R, int LK, int RK, int ITEMS>
+template <int LOG2R, int LK, int RK, int ITEMS, int THREADS = DNA_THREADS>
 struct StreamLayout
 {
   static constexpr int R = 1 << LOG2R;
-  static constexpr int TILE = (DNA_THREADS * ITEMS) >> LOG2R; /* sites per tile */
+  static constexpr int TILE = (THREADS * ITEMS) >> LOG2R; /* sites per tile */
   static constexpr int CLV_BYTES = TILE * R * 32;
   static constexpr int SC_BYTES = TILE * R * 4; /* per-rate worst case */
   static constexpr int CODE_BYTES = (TILE + 127) & ~127; /* whole 128-byte lines: the CLV tile behind a code array stays line-aligned */
@@ -787,11 +787,11 @@ struct StreamLayout
 };
 
 /* thread 0: queue the copies of tile `t` of `op` into ring slot `slot` */
-template <int LOG2R, int LK, int RK, int ITEMS>
+template <int LOG2R, int LK, int RK, int ITEMS, int THREADS>
 __device__ __forceinline__ void stream_issue(const plf_op_t & op, unsigned int t, unsigned char * slot,
                                              unsigned long long * bar, int per_rate)
 {
-  typedef StreamLayout<LOG2R, LK, RK, ITEMS> Ly;
+  typedef StreamLayout<LOG2R, LK, RK, ITEMS, THREADS> Ly;
   const unsigned int first = t * Ly::TILE;
   const unsigned int n = min((unsigned int)Ly::TILE, op.nsites - first);
   const unsigned int clv_bytes = n * Ly::R * 32;
@@ -843,13 +843,13 @@ __device__ __forceinline__ void build_cherry_table(double * tab, double * scratc
   build_tip_table(scratch + 64 * R, cm2, R);
   /* entry e = ((codeA * 16 + codeB) * R + rate) * 4 + i: a thread's (rate, i) = e mod 4R never changes
    * (the block size is a multiple of 4R), so its row of `outer` is read from global memory once */
-  static_assert(DNA_THREADS % (4 * R) == 0, "a thread must keep its (rate, row) over the table build");
+  /* (block sizes are multiples of 4R = 4 .. 16) */
   const int i = threadIdx.x & 3, rate = (threadIdx.x >> 2) & (R - 1);
   const double o0 = outer[rate * 16 + i * 4 + 0], o1 = outer[rate * 16 + i * 4 + 1];
   const double o2 = outer[rate * 16 + i * 4 + 2], o3 = outer[rate * 16 + i * 4 + 3];
   __syncthreads();
 #pragma unroll 4
-  for (int e = threadIdx.x; e < 1024 * R; e += DNA_THREADS)
+  for (int e = threadIdx.x; e < 1024 * R; e += blockDim.x)
   {
     const int cb = (e >> (2 + LOG2R)) & 15, ca = e >> (6 + LOG2R);
     const double2 a0 = *reinterpret_cast<const double2 *>(scratch + (ca * R + rate) * 4);
@@ -872,11 +872,11 @@ __device__ __forceinline__ dbl4 lds_dbl4_swz(const double * p, int swap)
   return swap ? dbl4{b.x, b.y, a.x, a.y} : dbl4{a.x, a.y, b.x, b.y};
 }
 
-template <int LOG2R, int LK, int RK, int NSTAGE, int ITEMS>
-__global__ void __launch_bounds__(DNA_THREADS)
+template <int LOG2R, int LK, int RK, int NSTAGE, int ITEMS, int THREADS = DNA_THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
 {
-  typedef StreamLayout<LOG2R, LK, RK, ITEMS> Ly;
+  typedef StreamLayout<LOG2R, LK, RK, ITEMS, THREADS> Ly;
   constexpr int R = Ly::R;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) unsigned long long full[NSTAGE];
@@ -899,7 +899,7 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
   {
     unsigned int t = blockIdx.x;
     for (int s = 0; s < NSTAGE && t < ntiles; ++s, t += gridDim.x)
-      stream_issue<LOG2R, LK, RK, ITEMS>(op, t, ring + (size_t)s * Ly::STAGE_BYTES, &full[s], per_rate);
+      stream_issue<LOG2R, LK, RK, ITEMS, THREADS>(op, t, ring + (size_t)s * Ly::STAGE_BYTES, &full[s], per_rate);
   }
 
   double Lm[LK == CK_I ? 16 : 1], Rm[RK == CK_I ? 16 : 1];
@@ -926,7 +926,7 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
 #pragma unroll
     for (int u = 0; u < ITEMS; ++u)
     {
-      const unsigned int item = threadIdx.x + u * DNA_THREADS; /* (site in tile, rate) */
+      const unsigned int item = threadIdx.x + u * THREADS; /* (site in tile, rate) */
       const unsigned int ls = item >> LOG2R;
       SiteRef sr;
       sr.n = first + ls;
@@ -982,7 +982,7 @@ k_clv_dna_stream(const plf_op_t * __restrict__ ops, int per_rate)
     }
     __syncthreads(); /* every warp is done with this slot */
     const unsigned int tn = t + (unsigned int)NSTAGE * gridDim.x;
-    if (threadIdx.x == 0 && tn < ntiles) stream_issue<LOG2R, LK, RK, ITEMS>(op, tn, slot, &full[s], per_rate);
+    if (threadIdx.x == 0 && tn < ntiles) stream_issue<LOG2R, LK, RK, ITEMS, THREADS>(op, tn, slot, &full[s], per_rate);
   }
 }
 
@@ -1154,15 +1154,25 @@ static dna_kernel_t pick_stream_kernel_items(unsigned int kind, int nstage, int 
   return pick_stream_kernel_stages<LOG2R, 4>(kind, nstage, smem, tile);
 }
 
-/* consumers of virtual cherries (rate_cats <= 4): ring of 6 (default) or 4 stages, `items` 2 or 4 */
+/* consumers of virtual cherries (rate_cats <= 4): ring of 6 (default) or 4 stages; `items` 2 or 4 blocks per
+ * thread at 128 threads, or (items == 1) one block per thread at 256 threads: the same 64-site tiles and the same
+ * shared memory per CTA with twice the warps */
 template <int LOG2R, int LK, int RK, int NSTAGE>
-static dna_kernel_t pick_cherry_items(int items, size_t * smem, unsigned int * tile)
+static dna_kernel_t pick_cherry_items(int items, size_t * smem, unsigned int * tile, unsigned int * threads)
 {
+  *threads = DNA_THREADS;
   if (items == 4)
   {
     *smem = StreamLayout<LOG2R, LK, RK, 4>::smem_bytes(NSTAGE);
     *tile = StreamLayout<LOG2R, LK, RK, 4>::TILE;
     return k_clv_dna_stream<LOG2R, LK, RK, NSTAGE, 4>;
+  }
+  if (items == 1)
+  {
+    *threads = 256;
+    *smem = StreamLayout<LOG2R, LK, RK, 1, 256>::smem_bytes(NSTAGE);
+    *tile = StreamLayout<LOG2R, LK, RK, 1, 256>::TILE;
+    return k_clv_dna_stream<LOG2R, LK, RK, NSTAGE, 1, 256>;
   }
   *smem = StreamLayout<LOG2R, LK, RK, 2>::smem_bytes(NSTAGE);
   *tile = StreamLayout<LOG2R, LK, RK, 2>::TILE;
@@ -1170,18 +1180,19 @@ static dna_kernel_t pick_cherry_items(int items, size_t * smem, unsigned int * t
 }
 
 template <int LOG2R, int NSTAGE>
-static dna_kernel_t pick_cherry_kind(unsigned int kind, int items, size_t * smem, unsigned int * tile)
+static dna_kernel_t pick_cherry_kind(unsigned int kind, int items, size_t * smem, unsigned int * tile, unsigned int * threads)
 {
-  if (kind == PLF_OP_CI) return pick_cherry_items<LOG2R, CK_C, CK_I, NSTAGE>(items, smem, tile);
-  if (kind == PLF_OP_TC) return pick_cherry_items<LOG2R, CK_T, CK_C, NSTAGE>(items, smem, tile);
-  return pick_cherry_items<LOG2R, CK_C, CK_C, NSTAGE>(items, smem, tile);
+  if (kind == PLF_OP_CI) return pick_cherry_items<LOG2R, CK_C, CK_I, NSTAGE>(items, smem, tile, threads);
+  if (kind == PLF_OP_TC) return pick_cherry_items<LOG2R, CK_T, CK_C, NSTAGE>(items, smem, tile, threads);
+  return pick_cherry_items<LOG2R, CK_C, CK_C, NSTAGE>(items, smem, tile, threads);
 }
 
 template <int LOG2R>
-static dna_kernel_t pick_cherry_kernel(unsigned int kind, int items, int stages, size_t * smem, unsigned int * tile)
+static dna_kernel_t pick_cherry_kernel(unsigned int kind, int items, int stages, size_t * smem, unsigned int * tile,
+                                       unsigned int * threads)
 {
-  if (stages == 4) return pick_cherry_kind<LOG2R, 4>(kind, items, smem, tile);
-  return pick_cherry_kind<LOG2R, 6>(kind, items, smem, tile);
+  if (stages == 4) return pick_cherry_kind<LOG2R, 4>(kind, items, smem, tile, threads);
+  return pick_cherry_kind<LOG2R, 6>(kind, items, smem, tile, threads);
 }
 
 static int env_int(const char * name, int dflt)
@@ -1201,7 +1212,8 @@ static void dna_read_switches(plf_ctx * ctx)
   ctx->dna_tt_items = env_int("PLF_TT_ITEMS", 2) == 4 ? 4 : 2;
   ctx->dna_tt_seq = env_int("PLF_TT_SEQ", 1);
   ctx->dna_balanced = env_int("PLF_DNA_BALANCED", 1);
-  ctx->dna_cherry_items = env_int("PLF_CHERRY_ITEMS", 2) == 4 ? 4 : 2;
+  ctx->dna_cherry_items = env_int("PLF_CHERRY_ITEMS", 2);
+  if (ctx->dna_cherry_items != 1 && ctx->dna_cherry_items != 4) ctx->dna_cherry_items = 2;
   ctx->dna_cherry_stages = env_int("PLF_CHERRY_STAGES", 6) == 4 ? 4 : 6;
   ctx->dna_cherry_bulk = env_int("PLF_CHERRY_BULK", 0); /* measured slower than the ring kernel: profiles/r2_notes.md */
   if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
@@ -1279,24 +1291,25 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
       PLF_CHECK(ctx, cudaGetLastError());
       return 1;
     }
+    unsigned int threads = DNA_THREADS;
     switch (log2r)
     {
-      case 0: k = pick_cherry_kernel<0>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile); break;
-      case 1: k = pick_cherry_kernel<1>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile); break;
-      default: k = pick_cherry_kernel<2>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile); break;
+      case 0: k = pick_cherry_kernel<0>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile, &threads); break;
+      case 1: k = pick_cherry_kernel<1>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile, &threads); break;
+      default: k = pick_cherry_kernel<2>(kind, ctx->dna_cherry_items, ctx->dna_cherry_stages, &smem, &tile, &threads); break;
     }
     int & occ = ctx->dna_cherry_occupancy[kind - PLF_OP_CI][log2r];
     if (!occ)
     {
       PLF_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, DNA_THREADS, smem));
+      PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, (int)threads, smem));
       if (occ < 1) occ = 1;
     }
     const unsigned long long ntiles = ((unsigned long long)max_sites + tile - 1) / tile;
     unsigned long long bx = ((unsigned long long)ctx->sm_count * occ) / nops;
     if (bx < 1) bx = 1;
     if (bx > ntiles) bx = ntiles;
-    k<<<dim3((unsigned int)bx, nops), DNA_THREADS, smem, ctx->stream>>>(d_ops, per_rate);
+    k<<<dim3((unsigned int)bx, nops), threads, smem, ctx->stream>>>(d_ops, per_rate);
     plf_count_launch();
     PLF_CHECK(ctx, cudaGetLastError());
     return 1;

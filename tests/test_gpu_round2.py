@@ -66,6 +66,7 @@ CHERRY_VARIANTS = {
     "items4": {"PLF_CHERRY_ITEMS": "4"},                            # 128-site tiles
     "bulk": {"PLF_CHERRY_BULK": "1"},                               # write-only consumers through bulk stores
     "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4"},
+    "threads256": {"PLF_CHERRY_ITEMS": "1"},                        # one block per thread, 256 threads per CTA
 }
 
 
