@@ -473,16 +473,32 @@ k_clv_dna_ii_pairs(const plf_op_t * __restrict__ ops, int per_rate_and_nops,
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
+      /* ncu (profiles/r2_full_pairs_summary.txt): the L1 data pipe, not DRAM, is what this kernel fills (78 % of
+       * its peak: 16 shared-memory row reads per item next to the gathers).  Each matrix row is therefore read
+       * ONCE per step and applied to all U items before anything is stored (the stores are asm volatile with a
+       * memory clobber: between them the compiler must reload shared memory). */
+      dbl4 v[U];
       {
-        dbl4 v;
-        v.x = dot4_pairwise(Lm + 0, l[u]) * dot4_pairwise(Rm + 0, r[u]);
-        v.y = dot4_pairwise(Lm + 4, l[u]) * dot4_pairwise(Rm + 4, r[u]);
-        v.z = dot4_pairwise(Lm + 8, l[u]) * dot4_pairwise(Rm + 8, r[u]);
-        v.w = dot4_pairwise(Lm + 12, l[u]) * dot4_pairwise(Rm + 12, r[u]);
-        scale_and_store<LOG2R>(op, s[u], rate, per_rate, sc[u], v);
+        double ra[U], rb[U];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+          const dbl4 lrow = lds_dbl4(Lm + 4 * i), rrow = lds_dbl4(Rm + 4 * i);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+          {
+            ra[u] = ((lrow.x * l[u].x) + (lrow.y * l[u].y)) + ((lrow.z * l[u].z) + (lrow.w * l[u].w));
+            rb[u] = ((rrow.x * r[u].x) + (rrow.y * r[u].y)) + ((rrow.z * r[u].z) + (rrow.w * r[u].w));
+            const double e = ra[u] * rb[u];
+            if (i == 0) v[u].x = e;
+            if (i == 1) v[u].y = e;
+            if (i == 2) v[u].z = e;
+            if (i == 3) v[u].w = e;
+          }
+        }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) scale_and_store<LOG2R>(op, s[u], rate, per_rate, sc[u], v[u]);
     }
   }
 }
@@ -1212,8 +1228,9 @@ static void dna_read_switches(plf_ctx * ctx)
   ctx->dna_tt_items = env_int("PLF_TT_ITEMS", 2) == 4 ? 4 : 2;
   ctx->dna_tt_seq = env_int("PLF_TT_SEQ", 1);
   ctx->dna_balanced = env_int("PLF_DNA_BALANCED", 1);
-  ctx->dna_cherry_items = env_int("PLF_CHERRY_ITEMS", 2);
-  if (ctx->dna_cherry_items != 1 && ctx->dna_cherry_items != 4) ctx->dna_cherry_items = 2;
+  /* default 1: one block per thread at 256 threads per CTA (2.83 vs 2.89 ms per config-2 traversal) */
+  ctx->dna_cherry_items = env_int("PLF_CHERRY_ITEMS", 1);
+  if (ctx->dna_cherry_items != 2 && ctx->dna_cherry_items != 4) ctx->dna_cherry_items = 1;
   ctx->dna_cherry_stages = env_int("PLF_CHERRY_STAGES", 6) == 4 ? 4 : 6;
   ctx->dna_cherry_bulk = env_int("PLF_CHERRY_BULK", 0); /* measured slower than the ring kernel: profiles/r2_notes.md */
   if (ctx->dna_stages != 2 && ctx->dna_stages != 3 && ctx->dna_stages != 4) ctx->dna_stages = 6;
@@ -1403,15 +1420,18 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
         default: kb = k_clv_dna_ii_balanced_sm<5, 2, 8>; break;
       }
     if (pair_lists && ctx->dna_balanced != 9 && ctx->dna_balanced != 8) /* 8: the three-array gather for A/B runs */
+    {
+      const int six = env_int("PLF_PAIRS_CTAS", 8) == 6; /* 80 registers, 6 CTAs per SM (A/B) */
       switch (log2r)
       {
-        case 0: kb = k_clv_dna_ii_pairs<0, 2, 8>; break;
-        case 1: kb = k_clv_dna_ii_pairs<1, 2, 8>; break;
-        case 2: kb = k_clv_dna_ii_pairs<2, 2, 8>; break;
-        case 3: kb = k_clv_dna_ii_pairs<3, 2, 8>; break;
-        case 4: kb = k_clv_dna_ii_pairs<4, 2, 8>; break;
-        default: kb = k_clv_dna_ii_pairs<5, 2, 8>; break;
+        case 0: kb = six ? k_clv_dna_ii_pairs<0, 2, 6> : k_clv_dna_ii_pairs<0, 2, 8>; break;
+        case 1: kb = six ? k_clv_dna_ii_pairs<1, 2, 6> : k_clv_dna_ii_pairs<1, 2, 8>; break;
+        case 2: kb = six ? k_clv_dna_ii_pairs<2, 2, 6> : k_clv_dna_ii_pairs<2, 2, 8>; break;
+        case 3: kb = six ? k_clv_dna_ii_pairs<3, 2, 6> : k_clv_dna_ii_pairs<3, 2, 8>; break;
+        case 4: kb = six ? k_clv_dna_ii_pairs<4, 2, 6> : k_clv_dna_ii_pairs<4, 2, 8>; break;
+        default: kb = six ? k_clv_dna_ii_pairs<5, 2, 6> : k_clv_dna_ii_pairs<5, 2, 8>; break;
       }
+    }
     int & occ = ctx->dna_balanced_occupancy[pair_lists ? 1 : 0][log2r];
     if (!occ)
     {

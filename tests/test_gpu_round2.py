@@ -62,11 +62,11 @@ CHERRY_CASES = [
 
 
 CHERRY_VARIANTS = {
-    "default": {},                                                  # every consumer through the ring kernel
+    "default": {},                                                  # ring kernel, 256 threads x 1 block per thread
+    "items2": {"PLF_CHERRY_ITEMS": "2"},                            # 128 threads x 2 blocks per thread
     "items4": {"PLF_CHERRY_ITEMS": "4"},                            # 128-site tiles
     "bulk": {"PLF_CHERRY_BULK": "1"},                               # write-only consumers through bulk stores
     "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4"},
-    "threads256": {"PLF_CHERRY_ITEMS": "1"},                        # one block per thread, 256 threads per CTA
 }
 
 
@@ -148,13 +148,22 @@ def test_virtual_cherry_survives_pmatrix_and_tip_changes(reflib, cudalib, monkey
 def test_virtual_cherries_off_switch_and_threshold(cudalib, monkeypatch):
     ds = synth.dna_dataset(10, 200, seed=3)
     gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
-    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0  # narrower than the default threshold
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1  # default: any width
+    gpu.close()
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "1000")
+    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0  # narrower than the threshold asked for
     gpu.close()
     monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
     monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "0")
     gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
     assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0
     gpu.close()
+    # partitions the kernels do not serve: tip CLVs instead of pattern tips, odd state counts, ascertainment bias
+    for d, extra in ((ds, 0), (synth.generic_dataset(5, 8, 100, seed=4), capi.PATTERN_TIP), (ds, capi.PATTERN_TIP | capi.AB_FLAG)):
+        gpu = harness.Engine(cudalib, d, capi.ARCH_CUDA | extra)
+        assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0
+        gpu.close()
 
 
 def test_virtual_cherries_large(reflib, cudalib):
