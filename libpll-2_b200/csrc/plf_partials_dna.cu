@@ -1421,16 +1421,21 @@ int plf_launch_dna_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
       }
     if (pair_lists && ctx->dna_balanced != 9 && ctx->dna_balanced != 8) /* 8: the three-array gather for A/B runs */
     {
-      const int six = env_int("PLF_PAIRS_CTAS", 8) == 6; /* 80 registers, 6 CTAs per SM (A/B) */
+      /* items in flight x resident CTAs: 26 = 2 x 6 (80 registers; default: config 4 traversal 1.19 ms), 28 = 2 x 8
+       * (64 registers, spills 72 bytes: 1.31 ms), 45 = 4 x 5 (96 registers), 44 = 4 x 4 (128 registers) */
+      const int var = env_int("PLF_PAIRS_SHAPE", 26);
+#define PAIRS_PICK(L) (var == 28 ? k_clv_dna_ii_pairs<L, 2, 8> : var == 45 ? k_clv_dna_ii_pairs<L, 4, 5> : \
+                       var == 44 ? k_clv_dna_ii_pairs<L, 4, 4> : k_clv_dna_ii_pairs<L, 2, 6>)
       switch (log2r)
       {
-        case 0: kb = six ? k_clv_dna_ii_pairs<0, 2, 6> : k_clv_dna_ii_pairs<0, 2, 8>; break;
-        case 1: kb = six ? k_clv_dna_ii_pairs<1, 2, 6> : k_clv_dna_ii_pairs<1, 2, 8>; break;
-        case 2: kb = six ? k_clv_dna_ii_pairs<2, 2, 6> : k_clv_dna_ii_pairs<2, 2, 8>; break;
-        case 3: kb = six ? k_clv_dna_ii_pairs<3, 2, 6> : k_clv_dna_ii_pairs<3, 2, 8>; break;
-        case 4: kb = six ? k_clv_dna_ii_pairs<4, 2, 6> : k_clv_dna_ii_pairs<4, 2, 8>; break;
-        default: kb = six ? k_clv_dna_ii_pairs<5, 2, 6> : k_clv_dna_ii_pairs<5, 2, 8>; break;
+        case 0: kb = PAIRS_PICK(0); break;
+        case 1: kb = PAIRS_PICK(1); break;
+        case 2: kb = PAIRS_PICK(2); break;
+        case 3: kb = PAIRS_PICK(3); break;
+        case 4: kb = PAIRS_PICK(4); break;
+        default: kb = PAIRS_PICK(5); break;
       }
+#undef PAIRS_PICK
     }
     int & occ = ctx->dna_balanced_occupancy[pair_lists ? 1 : 0][log2r];
     if (!occ)
