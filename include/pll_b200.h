@@ -531,6 +531,13 @@ PLL_EXPORT unsigned int pll_cuda_virtual_clvs(const pll_partition_t * partition,
                                               unsigned int clv_index);
 PLL_EXPORT int pll_cuda_materialize_clv(pll_partition_t * partition,
                                         unsigned int clv_index);
+/* Guard mode: with PLL_CUDA_GUARD=1 in the environment at pll_partition_create, every device buffer of the
+ * partition is allocated between two 256-byte guard bands.  pll_cuda_check_guards() returns the number of
+ * buffers that had a band written to (0 = clean, -1 = not in guard mode): the out-of-bounds-write check of
+ * the test suite on pools where compute-sanitizer is not available.  pll_cuda_debug_overrun() writes one byte
+ * just behind a CLV buffer so that a test can see the check fire. */
+PLL_EXPORT int pll_cuda_check_guards(const pll_partition_t * partition);
+PLL_EXPORT int pll_cuda_debug_overrun(pll_partition_t * partition, unsigned int clv_index);
 /* inspection: launches of one traversal level for ops of the given kinds (sorted by kind); a launch serves at
  * most 65535 ops (gridDim.y).  Host arithmetic only. */
 PLL_EXPORT unsigned int pll_cuda_count_launch_runs(const unsigned int * kinds, unsigned int count,

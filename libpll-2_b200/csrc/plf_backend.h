@@ -133,6 +133,8 @@ const char * plf_last_error(const plf_ctx_t * ctx);
 void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero);
 void plf_free(plf_ctx_t * ctx, void * p);
 int plf_pool_reserve(plf_ctx_t * ctx, size_t bytes);
+/* guard mode ($PLL_CUDA_GUARD=1): allocations whose guard bands were written to; -1 when the mode is off */
+int plf_check_guards(plf_ctx_t * ctx);
 int plf_upload(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_download(plf_ctx_t * ctx, void * dst, const void * src, size_t bytes);
 int plf_memset0(plf_ctx_t * ctx, void * dst, size_t bytes);

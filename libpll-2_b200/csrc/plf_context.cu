@@ -68,6 +68,8 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
     ctx->aa_mma = !(v && v[0] == '0');
     v = getenv("PLF_EDGE_FAST");
     ctx->edge_fast = !(v && v[0] == '0');
+    v = getenv("PLL_CUDA_GUARD");
+    ctx->guard = (v && v[0] && v[0] != '0');
   }
   cudaError_t e = cudaSetDevice(device);
   cudaDeviceProp prop;
@@ -128,6 +130,7 @@ extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   plf_graph_cache_destroy(ctx);
+  free(ctx->guard_recs);
   cudaFree(ctx->ws_ops.ptr);
   cudaFree(ctx->ws_once.ptr);
   cudaFree(ctx->ws_small.ptr);
@@ -163,6 +166,29 @@ void * plf_ws_reserve(plf_ctx * ctx, plf_ws * ws, size_t bytes)
   return ws->ptr;
 }
 
+/* ---- guarded allocations ($PLL_CUDA_GUARD=1) -------------------------------------------------------- *
+ * compute-sanitizer is not available on every pool.  In guard mode every device buffer handed out by        *
+ * plf_alloc sits between two PLF_GUARD-byte bands of 0xA5; plf_check_guards() reads all bands back and      *
+ * counts the allocations whose bands were written to.  Catches out-of-bounds WRITES of the kernels (bulk    *
+ * stores, scaler / identifier / pair-list stores, table scatters) on the small and odd shapes of the        *
+ * parity suite; the 16 bytes of by-design slack behind a buffer lie inside the allocation, not the band.   */
+#define PLF_GUARD 256
+
+static void guard_register(plf_ctx * ctx, void * user, size_t bytes)
+{
+  if (ctx->guard_count == ctx->guard_cap)
+  {
+    const size_t cap = ctx->guard_cap ? 2 * ctx->guard_cap : 1024;
+    plf_guard_rec * g = (plf_guard_rec *)realloc(ctx->guard_recs, cap * sizeof(plf_guard_rec));
+    if (!g) return;
+    ctx->guard_recs = g;
+    ctx->guard_cap = cap;
+  }
+  ctx->guard_recs[ctx->guard_count].user = user;
+  ctx->guard_recs[ctx->guard_count].bytes = bytes;
+  ++ctx->guard_count;
+}
+
 extern "C" void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero)
 {
   void * p = NULL;
@@ -171,22 +197,54 @@ extern "C" void * plf_alloc(plf_ctx_t * ctx, size_t bytes, int zero)
    * flags) up to the 16-byte copy granule */
   bytes = (bytes + 16 + 255) & ~(size_t)255;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return NULL;
+  const size_t total = bytes + (ctx->guard ? 2 * PLF_GUARD : 0);
   cudaError_t e;
   if (ctx->managed)
   {
-    e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
-    if (e == cudaSuccess) cudaMemPrefetchAsync(p, bytes, ctx->device, ctx->stream);
+    e = cudaMallocManaged(&p, total, cudaMemAttachGlobal);
+    if (e == cudaSuccess) cudaMemPrefetchAsync(p, total, ctx->device, ctx->stream);
   }
   else
-    e = cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream);
+    e = cudaMallocFromPoolAsync(&p, total, ctx->pool, ctx->stream);
   if (e != cudaSuccess)
   {
     cudaGetLastError();
-    plf_set_error(ctx, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    plf_set_error(ctx, "device allocation of %zu bytes failed: %s", total, cudaGetErrorString(e));
     return NULL;
+  }
+  if (ctx->guard)
+  {
+    cudaMemsetAsync(p, 0xA5, PLF_GUARD, ctx->stream);
+    cudaMemsetAsync((char *)p + PLF_GUARD + bytes, 0xA5, PLF_GUARD, ctx->stream);
+    p = (char *)p + PLF_GUARD;
+    guard_register(ctx, p, bytes);
   }
   if (zero) cudaMemsetAsync(p, 0, bytes, ctx->stream);
   return p;
+}
+
+/* number of live allocations whose guard bands were written to (-1: guard mode is off); synchronises */
+extern "C" int plf_check_guards(plf_ctx_t * ctx)
+{
+  if (!ctx->guard) return -1;
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -2;
+  int damaged = 0;
+  unsigned char band[2 * PLF_GUARD];
+  for (size_t i = 0; i < ctx->guard_count; ++i)
+  {
+    const plf_guard_rec & g = ctx->guard_recs[i];
+    if (cudaMemcpy(band, (char *)g.user - PLF_GUARD, PLF_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(band + PLF_GUARD, (char *)g.user + g.bytes, PLF_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return -2;
+    int bad = 0;
+    for (int k = 0; k < 2 * PLF_GUARD && !bad; ++k) bad = band[k] != 0xA5;
+    if (bad)
+    {
+      ++damaged;
+      plf_set_error(ctx, "guard band of the %zu-byte allocation at %p was written to", g.bytes, g.user);
+    }
+  }
+  return damaged;
 }
 
 /* Grows the stream-ordered pool by `bytes` (capped at 40 % of the free device memory) and hands the block
@@ -212,6 +270,17 @@ extern "C" void plf_free(plf_ctx_t * ctx, void * p)
 {
   if (!p) return;
   cudaSetDevice(ctx->device);
+  if (ctx->guard)
+  {
+    /* forget the record (a damaged band would have been reported by the last plf_check_guards) */
+    for (size_t i = 0; i < ctx->guard_count; ++i)
+      if (ctx->guard_recs[i].user == p)
+      {
+        ctx->guard_recs[i] = ctx->guard_recs[--ctx->guard_count];
+        break;
+      }
+    p = (char *)p - PLF_GUARD;
+  }
   if (ctx->pool)
   {
     /* stream-ordered: every kernel queued so far that uses `p` finishes first */

@@ -11,8 +11,17 @@ struct plf_ws
   size_t bytes;
 };
 
+struct plf_guard_rec
+{
+  void * user;
+  size_t bytes;
+};
+
 struct plf_ctx
 {
+  int guard;               /* $PLL_CUDA_GUARD=1: allocations between guard bands (plf_context.cu) */
+  plf_guard_rec * guard_recs;
+  size_t guard_count, guard_cap;
   int device;
   int managed;
   int sm_count;

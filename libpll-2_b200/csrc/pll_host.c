@@ -778,6 +778,33 @@ PLL_EXPORT int pll_cuda_synchronize(const pll_partition_t * partition)
 
 PLL_EXPORT unsigned long long pll_cuda_kernel_launches(void) { return plf_kernel_launches(); }
 
+/* NEW (additive, debugging).  With $PLL_CUDA_GUARD=1 in the environment when the partition was created, every
+ * device buffer of the partition lies between two 256-byte guard bands; this call returns how many buffers
+ * had a band written to since they were allocated (0 = clean, -1 = the partition was not created in guard
+ * mode).  compute-sanitizer's memcheck is not available on every GPU pool: this is the bounds check the
+ * parity suite runs on small and odd shapes instead. */
+PLL_EXPORT int pll_cuda_check_guards(const pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  int n;
+  if (!cp) return -2;
+  n = plf_check_guards(cp->ctx);
+  if (n > 0) set_error(PLL_ERROR_CUDA, "CUDA: %s", plf_last_error(cp->ctx));
+  return n;
+}
+
+/* NEW (debugging).  Writes one byte just behind a CLV buffer: lets a test see that guard mode notices. */
+PLL_EXPORT int pll_cuda_debug_overrun(pll_partition_t * partition, unsigned int clv_index)
+{
+  cuda_partition_t * cp = CP(partition);
+  const unsigned char b = 0;
+  size_t bytes;
+  if (!cp || clv_index >= partition->nodes || !partition->clv[clv_index]) return PLL_FAILURE;
+  bytes = (size_t)cp->clv_entries[clv_index] * partition->states_padded * partition->rate_cats * sizeof(double);
+  bytes = (bytes + 16 + 255) & ~(size_t)255; /* the allocator's rounding: the band starts here */
+  return plf_upload(cp->ctx, (unsigned char *)partition->clv[clv_index] + bytes, &b, 1) ? PLL_SUCCESS : cuda_fail(cp);
+}
+
 /* ---- site repeats: bookkeeping (src/repeats.c) ------------------------------ */
 
 PLL_EXPORT int pll_repeats_enabled(const pll_partition_t * partition)
