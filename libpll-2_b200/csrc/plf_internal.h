@@ -52,6 +52,7 @@ struct plf_ctx
   int aa_stream;           /* -1 = read PLF_AA_STREAM on first use; 0 keeps contiguous ops on the direct-load DMMA kernel */
   int dna_items;
   int dna_tt_bulk, dna_tt_items, dna_tt_seq, dna_balanced; /* PLF_TT_BULK / PLF_TT_ITEMS / PLF_TT_SEQ / PLF_DNA_BALANCED, read with dna_stream */
+  int aa_stages;           /* PLF_AA_STAGES=6: deeper ring in the 20-state streaming kernels (A/B) */
   int aa_warps8, aa_l2pf;  /* PLF_AA_WARPS=8, PLF_AAM_L2PF=0 (A/B switches of the 20-state DMMA kernels) */
   int lka_occupancy[3][4];  /* 20-state log-likelihood kernels [mode][log2 rates] */
   size_t lka_smem_set[3][4];

@@ -292,7 +292,6 @@ k_clv_aa_mma(const plf_op_t * __restrict__ ops, int R, int per_rate, const plf_s
  *  tile then only joins the warps that must exchange scaling flags and 4      *
  *  independent CTAs per SM keep the DMMA pipe fed) or 8 warps (8 rates).      *
  * ------------------------------------------------------------------------ */
-#define AAS_NSTAGE 4
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long * bar)
 {
@@ -312,8 +311,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long * bar)
  * with the matrix of the branch above it -- the same operands the kernel would have read back from HBM). */
 enum { AK_I = 0, AK_T = 1, AK_C = 2 };
 
-template <int LK, int RK, int LOG2R, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, 512 / (NWARPS * 32))
+template <int LK, int RK, int LOG2R, int NWARPS, int NST = 4>
+__global__ void __launch_bounds__(NWARPS * 32, NST == 4 ? 512 / (NWARPS * 32) : 1)
 k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_state_t * __restrict__ tipmap,
                     int maxstates)
 {
@@ -325,14 +324,14 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
   constexpr int STAGE = NCH * CH_BYTES;
   constexpr int OFF_LCH = (RK == AK_I) ? CH_BYTES : 0; /* the right child's tile comes first */
   extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ __align__(8) unsigned long long full[AAS_NSTAGE];
-  __shared__ __align__(8) unsigned long long empty[AAS_NSTAGE];
+  __shared__ __align__(8) unsigned long long full[NST];
+  __shared__ __align__(8) unsigned long long empty[NST];
   __shared__ __align__(8) unsigned long long flagbar[2];
   __shared__ int flags[2][TILE][R];
   unsigned char * ring = dyn;
   /* tables behind the ring: tip table of a left tip [maxstates][R][AAM_TAB_STRIDE], then the half tables of
    * the cherries [maxstates][R][AAM_TAB_STRIDE] each: left tip A, left tip B, right tip A, right tip B */
-  double * tl = reinterpret_cast<double *>(dyn + (size_t)AAS_NSTAGE * STAGE);
+  double * tl = reinterpret_cast<double *>(dyn + (size_t)NST * STAGE);
   const int half = maxstates * R * AAM_TAB_STRIDE; /* rows 22 doubles apart: codes spread over the banks */
   double * hl1 = tl + (LK == AK_T ? maxstates * R * AAM_TAB_STRIDE : 0);
   double * hl2 = hl1 + (LK == AK_C ? half : 0);
@@ -348,7 +347,7 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
 
   if (threadIdx.x == 0)
   {
-    for (int s = 0; s < AAS_NSTAGE; ++s)
+    for (int s = 0; s < NST; ++s)
     {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NWARPS);
@@ -398,7 +397,7 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
   if (NCH > 0 && threadIdx.x == 0)
   {
     unsigned int t = blockIdx.x;
-    for (int s = 0; s < AAS_NSTAGE && t < ntiles; ++s, t += gridDim.x) issue(t, s);
+    for (int s = 0; s < NST && t < ntiles; ++s, t += gridDim.x) issue(t, s);
   }
 
   /* B fragments of this warp's rate: lane holds P[8 nt + gs][state(kt, q)] */
@@ -467,17 +466,17 @@ k_clv_aa_mma_stream(const plf_op_t * __restrict__ ops, int per_rate, const plf_s
   unsigned int it = 0;
   for (unsigned int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it)
   {
-    const int s = it % AAS_NSTAGE;
-    const unsigned int parity = (it / AAS_NSTAGE) & 1u;
+    const int s = it % NST;
+    const unsigned int parity = (it / NST) & 1u;
     const unsigned char * slot = ring + (size_t)s * STAGE;
     /* producer duty: refill the slot of the previous iteration once every warp has handed it back */
     if (NCH > 0 && threadIdx.x == 0 && it > 0)
     {
-      const unsigned int tn = t + (unsigned int)(AAS_NSTAGE - 1) * gridDim.x;
+      const unsigned int tn = t + (unsigned int)(NST - 1) * gridDim.x;
       if (tn < ntiles)
       {
-        const int sp = (it - 1) % AAS_NSTAGE;
-        while (!mbar_try_wait(&empty[sp], ((it - 1) / AAS_NSTAGE) & 1u)) {}
+        const int sp = (it - 1) % NST;
+        while (!mbar_try_wait(&empty[sp], ((it - 1) / NST) & 1u)) {}
         issue(tn, sp);
       }
     }
@@ -710,26 +709,34 @@ k_clv_aa_tt(const plf_op_t * __restrict__ ops, int R, int per_rate, const plf_st
 
 /* returns 1 launched, 0 error, -1 not applicable (caller falls back) */
 typedef void (*aas_kernel_t)(const plf_op_t *, int, const plf_state_t *, int);
-template <int LOG2R, int NWARPS>
+template <int LOG2R, int NWARPS, int NST>
 static aas_kernel_t aas_pick(unsigned int kind)
 {
   switch (kind)
   {
-    case PLF_OP_II: return k_clv_aa_mma_stream<AK_I, AK_I, LOG2R, NWARPS>;
-    case PLF_OP_TI: return k_clv_aa_mma_stream<AK_T, AK_I, LOG2R, NWARPS>;
-    case PLF_OP_CI: return k_clv_aa_mma_stream<AK_C, AK_I, LOG2R, NWARPS>;
-    case PLF_OP_TC: return k_clv_aa_mma_stream<AK_T, AK_C, LOG2R, NWARPS>;
-    default: return k_clv_aa_mma_stream<AK_C, AK_C, LOG2R, NWARPS>;
+    case PLF_OP_II: return k_clv_aa_mma_stream<AK_I, AK_I, LOG2R, NWARPS, NST>;
+    case PLF_OP_TI: return k_clv_aa_mma_stream<AK_T, AK_I, LOG2R, NWARPS, NST>;
+    case PLF_OP_CI: return k_clv_aa_mma_stream<AK_C, AK_I, LOG2R, NWARPS, NST>;
+    case PLF_OP_TC: return k_clv_aa_mma_stream<AK_T, AK_C, LOG2R, NWARPS, NST>;
+    default: return k_clv_aa_mma_stream<AK_C, AK_C, LOG2R, NWARPS, NST>;
   }
 }
 
+template <int NST>
+static aas_kernel_t aas_pick_shape(unsigned int kind, int log2r, int nwarps)
+{
+  return log2r == 3   ? aas_pick<3, 8, NST>(kind)
+         : nwarps == 8 ? (log2r == 0 ? aas_pick<0, 8, NST>(kind) : log2r == 1 ? aas_pick<1, 8, NST>(kind) : aas_pick<2, 8, NST>(kind))
+                       : (log2r == 0 ? aas_pick<0, 4, NST>(kind) : log2r == 1 ? aas_pick<1, 4, NST>(kind) : aas_pick<2, 4, NST>(kind));
+}
+
 /* dynamic shared memory of the streaming kernel for one op kind: ring + tip table + cherry half tables */
-static size_t aas_smem_bytes(unsigned int kind, unsigned int rate_cats, int nwarps, unsigned int maxstates)
+static size_t aas_smem_bytes(unsigned int kind, unsigned int rate_cats, int nwarps, unsigned int maxstates, int nstage = 4)
 {
   const int left_inner = (kind == PLF_OP_II), right_inner = (kind == PLF_OP_II || kind == PLF_OP_TI || kind == PLF_OP_CI);
   const int left_tip = (kind == PLF_OP_TI || kind == PLF_OP_TC);
   const int cherries = (kind == PLF_OP_CI || kind == PLF_OP_TC) ? 1 : kind == PLF_OP_CC ? 2 : 0;
-  size_t smem = (size_t)AAS_NSTAGE * (left_inner + right_inner) * 1280 * nwarps;
+  size_t smem = (size_t)nstage * (left_inner + right_inner) * 1280 * nwarps;
   if (left_tip) smem += (size_t)maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);
   smem += (size_t)cherries * 2 * maxstates * rate_cats * AAM_TAB_STRIDE * sizeof(double);
   return smem;
@@ -754,10 +761,10 @@ static int launch_aa_stream(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
   const int nwarps = (log2r == 3 || ctx->aa_warps8) ? 8 : 4; /* PLF_AA_WARPS=8: 8-warp CTAs for every rate count */
-  aas_kernel_t k = log2r == 3   ? aas_pick<3, 8>(kind)
-                   : nwarps == 8 ? (log2r == 0 ? aas_pick<0, 8>(kind) : log2r == 1 ? aas_pick<1, 8>(kind) : aas_pick<2, 8>(kind))
-                                 : (log2r == 0 ? aas_pick<0, 4>(kind) : log2r == 1 ? aas_pick<1, 4>(kind) : aas_pick<2, 4>(kind));
-  const size_t smem = aas_smem_bytes(kind, rate_cats, nwarps, maxstates);
+  /* PLF_AA_STAGES=6: a deeper ring for the ops that read CLVs (A/B; the default 4 keeps 4 CTAs per SM) */
+  const int nst = (ctx->aa_stages == 6 && (kind == PLF_OP_II || kind == PLF_OP_TI || kind == PLF_OP_CI)) ? 6 : 4;
+  aas_kernel_t k = nst == 6 ? aas_pick_shape<6>(kind, log2r, nwarps) : aas_pick_shape<4>(kind, log2r, nwarps);
+  const size_t smem = aas_smem_bytes(kind, rate_cats, nwarps, maxstates, nst);
   if (smem > ctx->smem_optin) return -1;
   const int slot = aas_kind_slot(kind);
   if (smem > ctx->aas_smem_set[slot] || ctx->aas_log2r[slot] != log2r)
@@ -798,6 +805,8 @@ int plf_launch_aa_mma_group(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int 
     ctx->aa_warps8 = (v && v[0] == '8');
     v = getenv("PLF_AAM_L2PF");
     ctx->aa_l2pf = !(v && v[0] == '0');
+    v = getenv("PLF_AA_STAGES");
+    ctx->aa_stages = (v && v[0] == '6') ? 6 : 4;
   }
   if (kind == PLF_OP_TT_VIRTUAL)
   {
@@ -882,6 +891,8 @@ int plf_aa_virtual_cherries_supported(plf_ctx * ctx, const plf_shape_t * sh, uns
     ctx->aa_warps8 = (v && v[0] == '8');
     v = getenv("PLF_AAM_L2PF");
     ctx->aa_l2pf = !(v && v[0] == '0');
+    v = getenv("PLF_AA_STAGES");
+    ctx->aa_stages = (v && v[0] == '6') ? 6 : 4;
   }
   if (sh->states != 20 || !ctx->aa_fast || !ctx->aa_mma || !ctx->aa_stream) return 0;
   if (sh->rate_cats != 1 && sh->rate_cats != 2 && sh->rate_cats != 4 && sh->rate_cats != 8) return 0;
