@@ -684,6 +684,53 @@ def run_b200_arm(args):
                 lambda: lib.pll_cuda_peer_allreduce(peer, stream_ptr, C.c_void_p(scratch.data_ptr()), 3))
             collective["peer_ok"] = lib.pll_cuda_peer_group_check(peer) == 1
 
+    # Newton-Raphson on the root edge over all ranks (examples/newton/newton.c:67-96 with the sums reduced over the
+    # site slices): per evaluation the derivative kernel of the slice, the exchange of {d_f, dd_f}, 16 bytes to the
+    # host for the step decision.  Every rank takes the same step (the exchange returns the same bits everywhere).
+    newton = None
+    if not args.no_newton:
+        nd = torch.zeros(4, dtype=torch.float64, device=dev)
+        host = torch.zeros(4, dtype=torch.float64).pin_memory()
+        rc = lib.pll_update_sumtable(eng.p, a, b, sa, sb, pidx, st_p)
+        assert rc == 1, lib.errmsg
+
+        def newton_run(t0, tol=1e-7, max_iters=32):
+            t, evals = t0, 0
+            while evals < max_iters:
+                rc = lib.pll_cuda_likelihood_derivatives_async(eng.p, sa, sb, t, pidx, st_p, C.c_void_p(nd.data_ptr()))
+                assert rc == 1, lib.errmsg
+                if dist:
+                    if peer:
+                        assert lib.pll_cuda_peer_allreduce(peer, stream_ptr, C.c_void_p(nd.data_ptr()), 2) == 1
+                    else:
+                        with torch.cuda.stream(ext):
+                            dist.all_reduce(nd[:2])
+                with torch.cuda.stream(ext):
+                    host.copy_(nd, non_blocking=True)
+                ext.synchronize()
+                evals += 1
+                d1, d2 = float(host[0]), float(host[1])
+                if abs(d1) < tol:
+                    break
+                tn = min(max(t - d1 / d2, 1e-8), 100.0)
+                if tn != tn or tn == t:
+                    break
+                t = tn
+            return t, evals
+
+        newton_run(1.5 * t_len)
+        barrier_sync()
+        t0 = time.perf_counter()
+        total_evals = 0
+        for k in range(10):
+            length, ev = newton_run((0.5 + 0.2 * k) * t_len)
+            total_evals += ev
+        barrier_sync()
+        newton = {"runs": 10, "evaluations": total_evals, "us_per_evaluation": 1e6 * (time.perf_counter() - t0) / total_evals,
+                  "branch_length": length, "sites_per_gpu": args.sites,
+                  "note": "host-driven Newton-Raphson on the root edge: derivative kernel over the slice + exchange of "
+                          "{d_f, dd_f} over the ranks + 16 bytes to the host, per evaluation (wall clock)"}
+
     # end to end through the public C API with host buffers and host results
     for _ in range(2):
         step_e2e()
@@ -738,7 +785,7 @@ def run_b200_arm(args):
                               "allreduce_3_doubles": ms_allreduce / args.steps,
                               "pmatrices_and_rest": max(0.0, ms_total - ms_partials - ms_newton - ms_allreduce) / args.steps,
                               "note": "each entry is the max over ranks; the all-reduce entry includes waiting for the slowest rank"},
-        "collective": collective,
+        "collective": collective, "newton_root_edge": newton,
         "e2e": {"value": updates_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 24, "ms_per_step": e2e_ms / args.steps,
                 "note": "pll_update_prob_matrices + pll_update_partials + pll_compute_edge_loglikelihood + "
@@ -832,6 +879,7 @@ def main():
                     help=f"sites of the workload the CPU arm evaluates per step (default {SAMPLE_SITES})")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the config 3 / config 4 sub-records (N = 1 only)")
+    ap.add_argument("--no-newton", action="store_true", help="skip the Newton-Raphson timing on the root edge")
     ap.add_argument("--nccl-allreduce", action="store_true",
                     help="sum {logL, d_f, dd_f} over the ranks with NCCL instead of the peer-memory kernel")
     args = ap.parse_args()

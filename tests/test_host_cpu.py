@@ -214,3 +214,18 @@ def test_launch_runs_are_cut_at_the_grid_limit(lib):
     assert runs([2] * 65536) == (2, 65535)
     assert runs([2] * 70000 + [3] * 5) == (3, 65535)
     assert runs([1] * 200000) == (4, 65535)
+
+
+def test_peer_group_fails_cleanly_without_a_device(lib):
+    """pll_cuda_peer_* (the exchange of a site-sharded evaluation): bad arguments and a missing device give
+    NULL / 0, never a crash."""
+    handle = C.create_string_buffer(64)
+    assert not lib.pll_cuda_peer_group_create(0, 0, 0, handle)      # world of 0
+    assert not lib.pll_cuda_peer_group_create(0, 3, 2, handle)      # rank outside the world
+    assert not lib.pll_cuda_peer_group_create(0, 0, 2, None)        # nowhere to put the handle
+    import torch
+    if not torch.cuda.is_available():
+        assert not lib.pll_cuda_peer_group_create(0, 0, 2, handle)  # no device
+    assert lib.pll_cuda_peer_allreduce(None, None, None, 3) == 0
+    assert lib.pll_cuda_peer_group_check(None) == 0
+    lib.pll_cuda_peer_group_destroy(None)
