@@ -690,7 +690,6 @@ def run_b200_arm(args):
     newton = None
     if not args.no_newton:
         nd = torch.zeros(4, dtype=torch.float64, device=dev)
-        host = torch.zeros(4, dtype=torch.float64).pin_memory()
         rc = lib.pll_update_sumtable(eng.p, a, b, sa, sb, pidx, st_p)
         assert rc == 1, lib.errmsg
 
@@ -705,11 +704,9 @@ def run_b200_arm(args):
                     else:
                         with torch.cuda.stream(ext):
                             dist.all_reduce(nd[:2])
-                with torch.cuda.stream(ext):
-                    host.copy_(nd, non_blocking=True)
-                ext.synchronize()
+                lib.pll_cuda_synchronize(eng.p)
                 evals += 1
-                d1, d2 = float(host[0]), float(host[1])
+                d1, d2 = nd[:2].tolist()
                 if abs(d1) < tol:
                     break
                 tn = min(max(t - d1 / d2, 1e-8), 100.0)
@@ -729,7 +726,8 @@ def run_b200_arm(args):
         newton = {"runs": 10, "evaluations": total_evals, "us_per_evaluation": 1e6 * (time.perf_counter() - t0) / total_evals,
                   "branch_length": length, "sites_per_gpu": args.sites,
                   "note": "host-driven Newton-Raphson on the root edge: derivative kernel over the slice + exchange of "
-                          "{d_f, dd_f} over the ranks + 16 bytes to the host, per evaluation (wall clock)"}
+                          "{d_f, dd_f} over the ranks + 16 bytes to the host, per evaluation (wall clock); on this "
+                          "synthetic alignment (columns are not evolved along the tree) the length runs to its upper bound"}
 
     # end to end through the public C API with host buffers and host results
     for _ in range(2):
@@ -815,6 +813,9 @@ def run_b200_arm(args):
                      "whole_step_gbs": (clv_bytes + edge_bytes + nwt_bytes) * args.steps / (ms_total * 1e-3) / 1e9},
         "setup": {"dataset_generation_s": gen_s, "note": note},
     }
+    # nothing of torch's may outlive the partition's stream it was used on
+    del evs, start, stop
+    torch.cuda.synchronize()
     eng.close()
     del eng
     if peer:
