@@ -423,14 +423,24 @@ def config4_record(lib, torch, local, threads):
     rep = eng.part.repeats.contents
     ids = [int(rep.pernode_ids[n]) or sites for n in range(tips, ds.tree.nodes)]
     ms_noid = device_timed(torch, ext, lambda: lib.pll_update_partials_rep(eng.p, eng.ops, n_ops, 0), reps=10)
-    for _ in range(2):
+    # identifier update of every parent of the list (the library renumbers a parent only when a child's identifiers
+    # changed: pll_cuda_invalidate_repeat_identifiers forgets that history before every traversal) ...
+    for _ in range(3):
+        lib.pll_cuda_invalidate_repeat_identifiers(eng.p)
         eng.update_partials()
     lib.pll_cuda_synchronize(eng.p)
     t0 = time.perf_counter()
     for _ in range(5):
+        lib.pll_cuda_invalidate_repeat_identifiers(eng.p)
         eng.update_partials()
     lib.pll_cuda_synchronize(eng.p)
     ms_id = 1e3 * (time.perf_counter() - t0) / 5
+    # ... and of none: the same list again with unchanged tips (nothing to renumber)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        eng.update_partials()
+    lib.pll_cuda_synchronize(eng.p)
+    ms_id_unchanged = 1e3 * (time.perf_counter() - t0) / 5
     gpu_vals = gpu_eval(lib, eng, t_len)
     t0 = time.perf_counter()
     for _ in range(5):
@@ -468,6 +478,7 @@ def config4_record(lib, torch, local, threads):
            "metric": METRIC, "value": n_ops * sites / (e2e_ms * 1e-3), "unit": UNIT,
            "class_ratio_mean": float(np.mean(ids)) / sites, "first_traversal_ms": first_ms,
            "traversal_no_id_update_ms": ms_noid, "traversal_with_id_update_ms": ms_id,
+           "traversal_with_id_update_nothing_changed_ms": ms_id_unchanged,
            "traversal_site_updates_per_s": n_ops * sites / (ms_id * 1e-3), "e2e_ms_per_step": e2e_ms,
            "newton": {"branches": len(branches), "ms_per_branch_fused": newton_ms,
                       "evaluations_per_branch_fused": evals_gpu / len(branches),

@@ -531,6 +531,10 @@ PLL_EXPORT unsigned int pll_cuda_virtual_clvs(const pll_partition_t * partition,
                                               unsigned int clv_index);
 PLL_EXPORT int pll_cuda_materialize_clv(pll_partition_t * partition,
                                         unsigned int clv_index);
+/* Site-repeat identifiers are a pure function of the children's identifiers: pll_update_partials renumbers a
+ * parent only when a child's identifiers changed since it was last numbered from the same two children
+ * ($PLL_CUDA_REPEATS_MEMO=0: always).  This call forgets that history (measurements). */
+PLL_EXPORT int pll_cuda_invalidate_repeat_identifiers(pll_partition_t * partition);
 /* Guard mode: with PLL_CUDA_GUARD=1 in the environment at pll_partition_create, every device buffer of the
  * partition is allocated between two 256-byte guard bands.  pll_cuda_check_guards() returns the number of
  * buffers that had a band written to (0 = clean, -1 = not in guard mode): the out-of-bounds-write check of

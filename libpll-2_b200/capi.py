@@ -212,6 +212,7 @@ _PROTOS = {
     "pll_count_invariant_sites": (C.c_uint, [PartitionP, c_uint_p]),
     "pll_update_partials": (None, [PartitionP, C.POINTER(Operation), C.c_uint]),
     "pll_update_partials_rep": (None, [PartitionP, C.POINTER(Operation), C.c_uint, C.c_uint]),
+    "pll_update_repeats": (None, [PartitionP, C.POINTER(Operation)]),
     "pll_compute_root_loglikelihood": (C.c_double, [PartitionP, C.c_uint, C.c_int, c_uint_p, c_double_p]),
     "pll_compute_edge_loglikelihood": (
         C.c_double,
@@ -254,6 +255,7 @@ _CUDA_PROTOS = {
     "pll_cuda_download_sumtable": (C.c_int, [PartitionP, c_double_p, c_double_p]),
     "pll_cuda_scaler_size": (C.c_uint, [PartitionP, C.c_uint]),
     "pll_cuda_count_launch_runs": (C.c_uint, [c_uint_p, C.c_uint, c_uint_p]),
+    "pll_cuda_invalidate_repeat_identifiers": (C.c_int, [PartitionP]),
     "pll_cuda_check_guards": (C.c_int, [PartitionP]),
     "pll_cuda_debug_overrun": (C.c_int, [PartitionP, C.c_uint]),
     "pll_cuda_host_tipchars": (c_ubyte_p, [PartitionP, C.c_uint]),

@@ -60,6 +60,14 @@ typedef struct sumtable_slot
   double * asc_host; /* ascertainment bias: host copy of the `states` pseudo-site blocks */
 } sumtable_slot_t;
 
+typedef struct rid_memo
+{
+  unsigned int c1, c2, lookup_size;
+  unsigned long long v1, v2;
+  void * enable;
+  int valid;
+} rid_memo_t;
+
 typedef struct pair_state
 {
   unsigned int * dev;
@@ -161,6 +169,10 @@ typedef struct cuda_partition
   void * d_rid_scratch;
   size_t rid_scratch_bytes;
   int rid_fast;                           /* $PLL_CUDA_REPEATS_LEVEL_SYNC=1 keeps one host synchronisation per level */
+  /* identifiers are a pure function of the children's identifiers: an operation whose parent was last numbered
+   * from the same children at the same identifier versions keeps what it has (rid_memo, by parent node) */
+  struct rid_memo * rid_memo;
+  int rid_memo_on;                        /* $PLL_CUDA_REPEATS_MEMO=0: every update renumbers every parent */
   /* pair lists of gathering operations (plf_op_t::pair_list) */
   struct pair_state * pairs;              /* [nodes], by parent */
   unsigned long long * ids_version;       /* [nodes] bumped whenever a node's identifiers may have changed */
@@ -400,6 +412,7 @@ static void free_repeats(cuda_partition_t * cp)
     for (i = 0; i < p->nodes; ++i) plf_free(cp->ctx, cp->pairs[i].dev);
   free(cp->pairs);
   free(cp->ids_version);
+  free(cp->rid_memo);
   plf_free(cp->ctx, cp->d_node_ids);
   plf_free(cp->ctx, cp->d_raw_ids);
   plf_free(cp->ctx, cp->d_rid_jobs);
@@ -540,6 +553,11 @@ static int repeats_initialize(cuda_partition_t * cp)
   cp->d_node_ids = (unsigned int *)plf_alloc(cp->ctx, (size_t)p->nodes * sizeof(unsigned int), 1);
   cp->pairs = (pair_state_t *)calloc(p->nodes, sizeof(pair_state_t));
   cp->ids_version = (unsigned long long *)calloc(p->nodes, sizeof(unsigned long long));
+  cp->rid_memo = (rid_memo_t *)calloc(p->nodes, sizeof(rid_memo_t));
+  {
+    const char * v = getenv("PLL_CUDA_REPEATS_MEMO");
+    cp->rid_memo_on = !(v && v[0] == '0');
+  }
   cp->rid_fast = !env_flag("PLL_CUDA_REPEATS_LEVEL_SYNC");
   cp->rid_tag = 0xFFFFFFFEu;
   cp->d_rid_tag = (unsigned int *)plf_alloc(cp->ctx, sizeof(unsigned int), 0);
@@ -884,6 +902,18 @@ PLL_EXPORT unsigned int pll_no_enable_repeats(pll_partition_t * partition, unsig
 
 PLL_EXPORT void pll_disable_bclv(pll_partition_t * partition) { (void)partition; }
 
+/* NEW (additive).  Forget which children every node's identifiers were computed from: the next
+ * pll_update_partials renumbers every parent of its list (measurements; a client never needs it). */
+PLL_EXPORT int pll_cuda_invalidate_repeat_identifiers(pll_partition_t * partition)
+{
+  cuda_partition_t * cp = CP(partition);
+  unsigned int i;
+  if (!cp) return PLL_FAILURE;
+  if (cp->rid_memo)
+    for (i = 0; i < partition->nodes; ++i) cp->rid_memo[i].valid = 0;
+  return PLL_SUCCESS;
+}
+
 /* resize the parent's CLV, scale buffer and id->site array to the class count
  * (src/repeats.c:256-296) */
 PLL_EXPORT void pll_default_reallocate_repeats(pll_partition_t * partition, unsigned int parent, int scaler_index,
@@ -982,6 +1012,7 @@ static void repeats_finish_op(cuda_partition_t * cp, const pll_operation_t * op,
   unsigned int sites_to_alloc = ids ? ids : partition->sites;
   r->pernode_ids[parent] = ids;
   cp->ids_version[parent] = ++cp->ids_clock;
+  if (cp->rid_memo) cp->rid_memo[parent].valid = 0; /* whoever numbered the node records what from (update_repeats_fast) */
   if (op->parent_scaler_index != PLL_SCALE_BUFFER_NONE) r->perscale_ids[op->parent_scaler_index] = ids;
   if (ids) cp->ids_stale[parent] = 1;
   r->reallocate_repeats(partition, parent, op->parent_scaler_index, sites_to_alloc);
@@ -1152,7 +1183,7 @@ done:
  * reads all class counts back ONCE at the end and then sizes CLVs, scalers and the host mirrors
  * (reallocate_repeats, in operation order as the reference calls it). */
 #define RID_POOL_MAX_ENTRIES ((unsigned long long)1 << 29) /* 4 GiB of 64-bit entries */
-static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+static int update_repeats_fast_run(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
 {
   pll_partition_t * partition = &cp->pub;
   pll_repeats_t * r = partition->repeats;
@@ -1422,6 +1453,60 @@ done:
   free(raw);
   free(ub);
   free(jobs);
+  return ok;
+}
+
+/* Front end of the identifier update of an operation list: identifiers are a pure function of the children's
+ * identifiers (src/repeats.c:334-347), so a parent that was last numbered from the same two children, at the
+ * identifier versions they still have, under the same enable rule and lookup size, keeps its identifiers, its
+ * class count and its buffers; only the operations above a changed node are renumbered.  A tree search that
+ * re-evaluates a list after a local move renumbers the path to the root, not the tree. */
+static int update_repeats_fast(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+{
+  pll_partition_t * partition = &cp->pub;
+  pll_repeats_t * r = partition->repeats;
+  pll_operation_t * sel;
+  unsigned char * changed;
+  unsigned int i, n = 0;
+  int ok;
+  if (!cp->rid_memo_on || !cp->rid_memo) return update_repeats_fast_run(cp, ops, count);
+  sel = (pll_operation_t *)malloc((size_t)count * sizeof(pll_operation_t));
+  changed = (unsigned char *)calloc(partition->nodes ? partition->nodes : 1, 1);
+  if (!sel || !changed)
+  {
+    free(sel);
+    free(changed);
+    set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+    return 0;
+  }
+  for (i = 0; i < count; ++i) /* list order is dependency order (src/partials.c:253 runs it sequentially) */
+  {
+    const unsigned int c1 = ops[i].child1_clv_index, c2 = ops[i].child2_clv_index, par = ops[i].parent_clv_index;
+    const rid_memo_t * m = &cp->rid_memo[par];
+    const int keep = m->valid && m->c1 == c1 && m->c2 == c2 && m->v1 == cp->ids_version[c1] &&
+                     m->v2 == cp->ids_version[c2] && !changed[c1] && !changed[c2] &&
+                     m->lookup_size == r->lookup_buffer_size && m->enable == (void *)r->enable_repeats;
+    if (!keep)
+    {
+      sel[n++] = ops[i];
+      changed[par] = 1;
+    }
+  }
+  ok = n ? update_repeats_fast_run(cp, sel, n) : 1;
+  if (ok)
+    for (i = 0; i < n; ++i)
+    {
+      rid_memo_t * m = &cp->rid_memo[sel[i].parent_clv_index];
+      m->c1 = sel[i].child1_clv_index;
+      m->c2 = sel[i].child2_clv_index;
+      m->v1 = cp->ids_version[m->c1];
+      m->v2 = cp->ids_version[m->c2];
+      m->lookup_size = r->lookup_buffer_size;
+      m->enable = (void *)r->enable_repeats;
+      m->valid = 1;
+    }
+  free(sel);
+  free(changed);
   return ok;
 }
 

@@ -30,13 +30,27 @@ def main():
     for rep in range(3):
         out[f"no_id_ms_{rep}"] = bench.device_timed(torch, ext, lambda: lib.pll_update_partials_rep(eng.p, eng.ops, n_ops, 0), reps=20)
     for _ in range(3):
+        lib.pll_cuda_invalidate_repeat_identifiers(eng.p)
         eng.update_partials()
     lib.pll_cuda_synchronize(eng.p)
     t0 = time.perf_counter()
     for _ in range(10):
+        lib.pll_cuda_invalidate_repeat_identifiers(eng.p)
         eng.update_partials()
     lib.pll_cuda_synchronize(eng.p)
     out["with_id_ms"] = 1e2 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        eng.update_partials()
+    lib.pll_cuda_synchronize(eng.p)
+    out["with_id_nothing_changed_ms"] = 1e2 * (time.perf_counter() - t0)
+    # one tip re-set: only the path above it is renumbered
+    lib.pll_set_tip_states(eng.p, 17, eng.map, ds.seqs[17])
+    lib.pll_cuda_synchronize(eng.p)
+    t0 = time.perf_counter()
+    eng.update_partials()
+    lib.pll_cuda_synchronize(eng.p)
+    out["with_id_one_tip_changed_ms"] = 1e3 * (time.perf_counter() - t0)
     out["logl"] = eng.edge_logl()
     eng.close()
     print(json.dumps(out))

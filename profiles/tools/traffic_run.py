@@ -61,6 +61,8 @@ def main():
         if args.config == "repeats":
             lib.pll_update_partials_rep(eng.p, eng.ops, n_ops, 0)
         else:
+            if args.config == "repeats_ids":
+                lib.pll_cuda_invalidate_repeat_identifiers(eng.p)  # renumber every parent, every time
             eng.update_partials()
     lib.pll_cuda_synchronize(eng.p)
     per = (lib.pll_cuda_kernel_launches() - launches0) // args.reps

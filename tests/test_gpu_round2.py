@@ -527,15 +527,26 @@ def test_repeated_identifier_updates_replay_a_graph(reflib, cudalib):
         assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, what)
 
     traverse(ref)
-    for k in range(4):
+    for k in range(3):  # nothing changes between these: parents keep their identifiers
         traverse(gpu)
         check(f"traversal {k}")
+    for k in range(4):  # every parent renumbered: plain launches, graph capture, two replays
+        assert cudalib.pll_cuda_invalidate_repeat_identifiers(gpu.p) == 1
+        traverse(gpu)
+        check(f"renumbered traversal {k}")
     other = ds.seqs[5]
     for lib, e in ((reflib, ref), (cudalib, gpu)):
         assert lib.pll_set_tip_states(e.p, 9, e.map, other) == 1
     traverse(ref)
-    for k in range(3):
+    for k in range(3):  # the first renumbers the path from tip 9 to the root only
         traverse(gpu)
         check(f"after the tip change, traversal {k}")
+    # the per-op entry point on a node in the middle of the tree, with OTHER children than the list's: the list's
+    # next update must notice that the node (and everything above it) no longer holds its identifiers
+    mid = ref.ops[len(ref.ops) // 2]
+    odd = capi.Operation(mid.parent_clv_index, mid.parent_scaler_index, 0, 0, -1, 1, 1, -1)
+    cudalib.pll_update_repeats(gpu.p, C.byref(odd))
+    traverse(gpu)
+    check("after pll_update_repeats on a node of the list")
     ref.close()
     gpu.close()
