@@ -131,15 +131,6 @@ extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
   cudaStreamSynchronize(ctx->stream);
   plf_graph_cache_destroy(ctx);
   free(ctx->guard_recs);
-  if (ctx->fork_ready == 1)
-  {
-    for (int i = 0; i < 3; ++i)
-    {
-      cudaStreamDestroy(ctx->side[i]);
-      cudaEventDestroy(ctx->ev_join[i]);
-    }
-    cudaEventDestroy(ctx->ev_fork);
-  }
   cudaFree(ctx->ws_ops.ptr);
   cudaFree(ctx->ws_once.ptr);
   cudaFree(ctx->ws_small.ptr);

@@ -60,12 +60,6 @@ struct plf_ctx
   int edge_items;           /* 0 = read PLF_EDGE_ITEMS on first use */
   int edge_fast;            /* PLF_EDGE_FAST=0 forces the generic log-likelihood / sumtable / derivative kernels */
   cudaStream_t stream;
-  /* narrow alignments: the runs of one traversal level (different op kinds, independent by construction) are
-   * queued on side streams that fork from and join the partition's stream, also inside the captured graph */
-  cudaStream_t side[3];
-  cudaEvent_t ev_fork, ev_join[3];
-  int fork_ready;              /* 0 = not set up yet, 1 = ready, -1 = unavailable */
-  unsigned int fork_max_sites; /* widest level that forks ($PLF_FORK_MAX_SITES, 0 = never) */
   cudaMemPool_t pool;    /* stream-ordered allocator behind plf_alloc/plf_free (NULL in managed mode) */
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
   plf_ws ws_once;     /* op descriptors of internal single ops (materialised cherries) */

@@ -451,35 +451,6 @@ extern "C" int plf_virtual_cherries_supported(plf_ctx_t * ctx, const plf_shape_t
 
 static int is_pow2(unsigned int x) { return x && !(x & (x - 1)); }
 
-/* side streams + events of the fork-join over the runs of a level (narrow alignments) */
-static bool fork_setup(plf_ctx * ctx)
-{
-  if (ctx->fork_ready) return ctx->fork_ready == 1;
-  ctx->fork_ready = -1;
-  cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool ok = true;
-  for (int i = 0; i < 3 && ok; ++i) ok = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) == cudaSuccess;
-  for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) == cudaSuccess;
-  if (!ok)
-  {
-    cudaGetLastError();
-    for (int i = 0; i < 3; ++i)
-      if (st[i]) cudaStreamDestroy(st[i]);
-    for (int i = 0; i < 4; ++i)
-      if (ev[i]) cudaEventDestroy(ev[i]);
-    return false;
-  }
-  for (int i = 0; i < 3; ++i)
-  {
-    ctx->side[i] = st[i];
-    ctx->ev_join[i] = ev[i];
-  }
-  ctx->ev_fork = ev[3];
-  ctx->fork_ready = 1;
-  return true;
-}
-
 /* queues the launches of a level-sorted op list.  `upload` = 0: the op descriptors and tile-prefix arrays
  * are already in the workspace (identical call being captured into a CUDA graph): no host-to-device copy */
 static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_t * h_ops, unsigned int nops,
@@ -518,28 +489,8 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
     {
       /* specialised kernels per op kind (plf_partials_dna.cu): one launch per
        * run of same-kind ops; the host layer sorts a level by kind */
-      /* Narrow alignments: a level's runs (tip + inner, tip + cherry, cherry + inner, ...) are kernels of a few
-       * microseconds that do not fill the chip, and they are independent of each other (same level).  They fork
-       * onto side streams and join before the next level; in the captured graph this becomes a fork-join, so the
-       * critical path of a traversal is its levels, not its launches. */
-      unsigned int nruns = 0;
-      for (unsigned int i = a; i < b; ++nruns) i = plf_run_end(h_ops, i, b, nullptr, nullptr);
-      const bool fork = nruns > 1 && max_sites <= ctx->fork_max_sites && fork_setup(ctx);
-      cudaStream_t const main_stream = ctx->stream;
-      unsigned int run = 0, side_used = 0;
-      if (fork) PLF_CHECK(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
-      for (unsigned int i = a; i < b; ++run)
+      for (unsigned int i = a; i < b;)
       {
-        if (fork && run > 0)
-        {
-          const unsigned int sidx = (run - 1) % 3;
-          if (!(side_used & (1u << sidx)))
-          {
-            PLF_CHECK(ctx, cudaStreamWaitEvent(ctx->side[sidx], ctx->ev_fork, 0));
-            side_used |= 1u << sidx;
-          }
-          ctx->stream = ctx->side[sidx]; /* the launch code below queues on ctx->stream */
-        }
         unsigned int run_sites = 0;
         int contiguous = 1;
         const unsigned int j = plf_run_end(h_ops, i, b, &run_sites, &contiguous);
@@ -565,24 +516,15 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
         }
         int pair_lists = !contiguous;
         for (unsigned int k = i; k < j && pair_lists; ++k) pair_lists = h_ops[k].pair_list != nullptr;
-        const int launched = !run_sites || plf_launch_dna_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
-                                                                sh->per_rate_scalers, run_sites, contiguous, d_run_prefix,
-                                                                total_tiles, pair_lists);
-        ctx->stream = main_stream;
-        if (!launched)
+        if (run_sites && !plf_launch_dna_group(ctx, d_ops + i, j - i, h_ops[i].kind, sh->rate_cats,
+                                               sh->per_rate_scalers, run_sites, contiguous, d_run_prefix, total_tiles,
+                                               pair_lists))
         {
           free(h_prefix);
           return 0;
         }
         i = j;
       }
-      if (fork)
-        for (unsigned int sidx = 0; sidx < 3; ++sidx)
-          if (side_used & (1u << sidx))
-          {
-            PLF_CHECK(ctx, cudaEventRecord(ctx->ev_join[sidx], ctx->side[sidx]));
-            PLF_CHECK(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_join[sidx], 0));
-          }
       continue;
     }
     if (sh->states == 4)
@@ -721,8 +663,6 @@ extern "C" int plf_update_partials(plf_ctx_t * ctx, const plf_shape_t * sh, cons
   {
     const char * v = getenv("PLF_GRAPH");
     ctx->graph_mode = !(v && v[0] == '0');
-    v = getenv("PLF_FORK_MAX_SITES");
-    ctx->fork_max_sites = (v && v[0]) ? (unsigned int)strtoul(v, nullptr, 10) : 32768u;
   }
   if (!ctx->graph_mode) return enqueue_levels(ctx, sh, h_ops, nops, h_level_start, nlevels, d_tipmap, maxstates, 1);
 
