@@ -58,6 +58,7 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
   ctx->device = device;
   ctx->managed = managed;
   ctx->dna_stream = -1;
+  ctx->dna_level_max_sites = -1;
   ctx->graph_mode = -1;
   ctx->aa_stream = -1;
   ctx->aam_log2r[0] = ctx->aam_log2r[1] = -1;

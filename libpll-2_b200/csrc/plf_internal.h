@@ -33,6 +33,7 @@ struct plf_ctx
   int dna_cherry_occupancy[3][3]; /* consumers of virtual cherries [CI, TC, CC][log2 rates] */
   int dna_cherry_items;           /* PLF_CHERRY_ITEMS: 2 (default) or 4 (site, rate) blocks per thread and tile */
   int dna_cherry_stages;          /* PLF_CHERRY_STAGES: 6 (default) or 4 ring stages */
+  int dna_level_max_sites;        /* PLF_LEVEL_MAX_SITES: widest alignment whose levels run as one launch each (-1 = read on first use) */
   int dna_cherry_bulk;            /* PLF_CHERRY_BULK=1: tip + cherry / cherry + cherry through the bulk-store kernel instead of the ring kernel */
   int dna_cherry;                 /* PLF_VIRTUAL_CHERRIES=0 writes every tip-tip parent to HBM */
   int dna_tt_bulk_occupancy[4];
@@ -99,6 +100,8 @@ int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned in
                          unsigned int rate_cats, int per_rate, unsigned int max_sites, int contiguous,
                          const unsigned int * d_tile_prefix, unsigned int total_tiles, int pair_lists = 0);
 unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats);
+int plf_launch_dna_level(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int rate_cats, int per_rate,
+                         unsigned int max_sites);
 int plf_aa_virtual_cherries_supported(plf_ctx * ctx, const struct plf_shape * sh, unsigned int maxstates);
 int plf_dna_virtual_cherries_supported(plf_ctx * ctx, const struct plf_shape * sh);
 

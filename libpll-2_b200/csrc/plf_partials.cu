@@ -471,6 +471,12 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
   size_t prefix_used = 0;
   const int R = (int)sh->rate_cats;
   const int one_rate = is_pow2(sh->rate_cats) && sh->rate_cats <= 32;
+  if (ctx->dna_level_max_sites < 0)
+  {
+    const char * v = getenv("PLF_LEVEL_MAX_SITES");
+    ctx->dna_level_max_sites = (v && v[0]) ? atoi(v) : 0;
+  }
+  const unsigned int level_max_sites = (unsigned int)ctx->dna_level_max_sites;
   const int L = one_rate ? R : 1;
 
   for (unsigned int lv = 0; lv < nlevels; ++lv)
@@ -485,6 +491,25 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
       any_tip |= (h_ops[i].kind != PLF_OP_II);
     }
     if (!max_sites) continue;
+    if (sh->states == 4 && one_rate && sh->rate_cats <= 4 && max_sites <= level_max_sites)
+    {
+      /* narrow alignment: the whole level in one launch (k_clv_dna_level), unless an op gathers through
+       * repeat identifiers */
+      int contiguous = 1;
+      for (unsigned int i = a; i < b && contiguous; ++i)
+        contiguous = !(h_ops[i].parent_id_site || h_ops[i].left_site_id || h_ops[i].right_site_id);
+      if (contiguous)
+      {
+        for (unsigned int c0 = a; c0 < b; c0 += PLF_MAX_RUN_OPS)
+          if (!plf_launch_dna_level(ctx, d_ops + c0, (b - c0 < PLF_MAX_RUN_OPS) ? b - c0 : PLF_MAX_RUN_OPS, sh->rate_cats,
+                                    sh->per_rate_scalers, max_sites))
+          {
+            free(h_prefix);
+            return 0;
+          }
+        continue;
+      }
+    }
     if (sh->states == 4 && one_rate)
     {
       /* specialised kernels per op kind (plf_partials_dna.cu): one launch per

@@ -1126,6 +1126,164 @@ k_cherry_prepare(const plf_op_t * __restrict__ ops, int per_rate, int R)
     dst[q] = make_uint4(0, 0, 0, 0);
 }
 
+/* ------------------------------------------------------------------------ *
+ *  Narrow alignments: ONE launch per traversal level.  A 100-taxon traversal  *
+ *  is 12 levels but 22-28 launches of the per-kind kernels above, and below   *
+ *  ~10^4 sites a launch costs what a CTA's life costs (barrier set-up, table   *
+ *  build, one tile), not what its bytes cost.  This kernel takes every op of   *
+ *  a level whatever its kind (blockIdx.y = op; the kind is uniform per CTA, so *
+ *  the branches do not diverge): children are read straight from global        *
+ *  memory (inner), looked up in a 16-row table (tip) or formed from two such   *
+ *  tables (virtual cherry: entry k = tA[codeA][k] * tB[codeB][k], then the     *
+ *  4x4 product with the matrix of the branch above it); a virtual cherry's own *
+ *  "operation" (matrix snapshot, zeroed scaler) rides along.  Same arithmetic, *
+ *  same order as the per-kind kernels: the same bits.                          *
+ * ------------------------------------------------------------------------ */
+template <int LOG2R>
+__global__ void __launch_bounds__(DNA_THREADS)
+k_clv_dna_level(const plf_op_t * __restrict__ ops, int per_rate)
+{
+  constexpr int R = 1 << LOG2R;
+  __shared__ __align__(16) double tabs[4][64 * R]; /* left A, left B, right A, right B */
+  const plf_op_t op = ops[blockIdx.y];
+  const unsigned int kind = op.kind;
+  if (kind == PLF_OP_TT_VIRTUAL)
+  {
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < R * 16; i += DNA_THREADS)
+      {
+        op.parent_clv[i] = op.left_matrix[i];
+        op.parent_clv[R * 16 + i] = op.right_matrix[i];
+      }
+    if (op.parent_scaler)
+    {
+      const size_t n = per_rate ? (size_t)op.nsites * R : op.nsites;
+      for (size_t e = (size_t)blockIdx.x * DNA_THREADS + threadIdx.x; e < n; e += (size_t)gridDim.x * DNA_THREADS)
+        op.parent_scaler[e] = 0;
+    }
+    return;
+  }
+  /* what each child is: 0 inner CLV, 1 pattern tip, 2 virtual cherry */
+  const int lk = (kind == PLF_OP_II) ? CK_I : (kind == PLF_OP_CI || kind == PLF_OP_CC) ? CK_C : CK_T;
+  const int rk = (kind == PLF_OP_TT) ? CK_T : (kind == PLF_OP_TC || kind == PLF_OP_CC) ? CK_C : CK_I;
+  if (lk == CK_T) build_tip_table(tabs[0], op.left_matrix, R);
+  if (lk == CK_C)
+  {
+    build_tip_table(tabs[0], op.left_cm1, R);
+    build_tip_table(tabs[1], op.left_cm2, R);
+  }
+  if (rk == CK_T) build_tip_table(tabs[2], op.right_matrix, R);
+  if (rk == CK_C)
+  {
+    build_tip_table(tabs[2], op.right_cm1, R);
+    build_tip_table(tabs[3], op.right_cm2, R);
+  }
+  const unsigned int tid = blockIdx.x * DNA_THREADS + threadIdx.x;
+  const int rate = tid & (R - 1);
+  const unsigned int site0 = tid >> LOG2R;
+  const unsigned int pass = (gridDim.x * DNA_THREADS) >> LOG2R;
+  double Lm[16], Rm[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+  {
+    Lm[i] = (lk != CK_T) ? op.left_matrix[rate * 16 + i] : 0.0;
+    Rm[i] = (rk != CK_T) ? op.right_matrix[rate * 16 + i] : 0.0;
+  }
+  __syncthreads();
+  const bool scales = kind != PLF_OP_TT; /* tip-tip never scales and zeroes its scaler */
+  for (unsigned int base = 0; base < op.nsites; base += pass)
+  {
+    SiteRef s;
+    s.n = base + site0;
+    s.lid = s.rid = s.n;
+    s.active = s.n < op.nsites;
+    const unsigned int n = s.active ? s.n : op.nsites - 1; /* inactive lanes recompute the last site, store nothing */
+    dbl4 a, b;
+    unsigned int sc = 0;
+    if (lk == CK_T)
+      a = lds_dbl4(tabs[0] + (op.left_tip[n] * R + rate) * 4);
+    else
+    {
+      dbl4 l;
+      if (lk == CK_I)
+        l = ld256_stream(op.left_clv + ((size_t)n * R + rate) * 4);
+      else
+      {
+        const dbl4 x = lds_dbl4(tabs[0] + ((op.left_tip[n] & 15u) * R + rate) * 4);
+        const dbl4 y = lds_dbl4(tabs[1] + ((op.left_tip2[n] & 15u) * R + rate) * 4);
+        l = dbl4{x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w};
+      }
+      a.x = dot4_pairwise(Lm + 0, l);
+      a.y = dot4_pairwise(Lm + 4, l);
+      a.z = dot4_pairwise(Lm + 8, l);
+      a.w = dot4_pairwise(Lm + 12, l);
+    }
+    if (rk == CK_T)
+      b = lds_dbl4(tabs[2] + (op.right_tip[n] * R + rate) * 4);
+    else
+    {
+      dbl4 r;
+      if (rk == CK_I)
+        r = ld256_stream(op.right_clv + ((size_t)n * R + rate) * 4);
+      else
+      {
+        const dbl4 x = lds_dbl4(tabs[2] + ((op.right_tip[n] & 15u) * R + rate) * 4);
+        const dbl4 y = lds_dbl4(tabs[3] + ((op.right_tip2[n] & 15u) * R + rate) * 4);
+        r = dbl4{x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w};
+      }
+      b.x = dot4_pairwise(Rm + 0, r);
+      b.y = dot4_pairwise(Rm + 4, r);
+      b.z = dot4_pairwise(Rm + 8, r);
+      b.w = dot4_pairwise(Rm + 12, r);
+    }
+    if (op.parent_scaler && s.active && (per_rate || rate == 0))
+    {
+      if (lk == CK_I && op.left_scaler) sc += op.left_scaler[per_rate ? (size_t)n * R + rate : n];
+      if (rk == CK_I && op.right_scaler) sc += op.right_scaler[per_rate ? (size_t)n * R + rate : n];
+    }
+    dbl4 v = dbl4{a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w};
+    if (scales)
+      scale_and_store<LOG2R>(op, s, rate, per_rate, sc, v);
+    else
+    {
+      if (s.active)
+      {
+        st256(op.parent_clv + ((size_t)s.n * R + rate) * 4, v);
+        if (op.parent_scaler)
+        {
+          if (per_rate)
+            op.parent_scaler[(size_t)s.n * R + rate] = 0;
+          else if (rate == 0)
+            op.parent_scaler[s.n] = 0;
+        }
+      }
+    }
+  }
+}
+
+/* one launch for every op of a level (any kinds, contiguous CLVs, rate_cats 1, 2 or 4) */
+int plf_launch_dna_level(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nops, unsigned int rate_cats, int per_rate,
+                         unsigned int max_sites)
+{
+  int log2r = 0;
+  while ((1u << log2r) < rate_cats) ++log2r;
+  const unsigned long long lanes = (unsigned long long)max_sites << log2r;
+  unsigned long long bx = (lanes + DNA_THREADS - 1) / DNA_THREADS;
+  const unsigned long long cap = ((unsigned long long)ctx->sm_count * 12 + nops - 1) / nops;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  const dim3 grid((unsigned int)bx, nops);
+  switch (log2r)
+  {
+    case 0: k_clv_dna_level<0><<<grid, DNA_THREADS, 0, ctx->stream>>>(d_ops, per_rate); break;
+    case 1: k_clv_dna_level<1><<<grid, DNA_THREADS, 0, ctx->stream>>>(d_ops, per_rate); break;
+    default: k_clv_dna_level<2><<<grid, DNA_THREADS, 0, ctx->stream>>>(d_ops, per_rate); break;
+  }
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
 /* ------------------------------------------------------------------------ */
 
 typedef void (*dna_kernel_t)(const plf_op_t *, int);

@@ -67,6 +67,8 @@ CHERRY_VARIANTS = {
     "items4": {"PLF_CHERRY_ITEMS": "4"},                            # 128-site tiles
     "bulk": {"PLF_CHERRY_BULK": "1"},                               # write-only consumers through bulk stores
     "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4"},
+    "level": {"PLF_LEVEL_MAX_SITES": "1000000"},                    # one launch per traversal level (k_clv_dna_level)
+    "level-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0"},
 }
 
 
@@ -81,9 +83,10 @@ def test_virtual_cherries_parity(reflib, cudalib, monkeypatch, case, variant):
         monkeypatch.setenv(k, v)
     ds = synth.dna_dataset(tips, sites, seed=100 + tips, tree_kind=tree, alpha=0.4, cats=cats)
     ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
-    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
-    cherries = cherry_nodes(ds)
-    assert cherries
+    written = CHERRY_VARIANTS[variant].get("PLF_VIRTUAL_CHERRIES") == "0"
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == (0 if written else 1)
+    cherries = [] if written else cherry_nodes(ds)
+    assert written or cherries
     traverse(ref, gpu)
     assert cudalib.pll_cuda_virtual_clvs(gpu.p, 0xFFFFFFFF) == len(cherries)
     # the root edge first: nothing has been materialised, every consumer worked from tip codes
@@ -103,7 +106,7 @@ def test_virtual_cherries_parity(reflib, cudalib, monkeypatch, case, variant):
     edges = []
     for r in t.ops:
         for child, m in ((int(r[2]), int(r[3])), (int(r[5]), int(r[6]))):
-            if child in cherries and len(edges) < 3:
+            if child in cherry_nodes(ds) and len(edges) < 3:
                 edges.append((int(r[0]), child, m))
     assert edges
     # the edge is evaluated from the CLVs as the traversal left them (both libraries hold the same state)
