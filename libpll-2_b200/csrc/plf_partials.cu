@@ -474,7 +474,7 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
   if (ctx->dna_level_max_sites < 0)
   {
     const char * v = getenv("PLF_LEVEL_MAX_SITES");
-    ctx->dna_level_max_sites = (v && v[0]) ? atoi(v) : 0;
+    ctx->dna_level_max_sites = (v && v[0]) ? atoi(v) : 2048; /* measured crossover ~2500 sites, profiles/r2_notes.md */
   }
   const unsigned int level_max_sites = (unsigned int)ctx->dna_level_max_sites;
   const int L = one_rate ? R : 1;

@@ -184,7 +184,7 @@ typedef struct cuda_partition
    * written to HBM; their consumers work from the tip codes, anything else materialises them first */
   int cherry_ok;                 /* this partition's kernels consume virtual cherries */
   unsigned int cherry_maxstates; /* tip alphabet size cherry_ok was decided for (0: not yet) */
-  unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES, default 0) */
+  unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES, default 2049) */
   double * d_cherry_pm;          /* [clv_buffers][2][rate_cats * 16]: the P-matrices each cherry was asked with */
   struct cherry_state * cherry;  /* [nodes] */
   struct cherry_state * cherry_saved; /* roll-back copy while an operation list is resolved */
@@ -751,9 +751,10 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     /* whether tip-tip parents stay virtual is settled at the first operation list, when the tip alphabet
      * (maxstates: table sizes of the 20-state kernels) is known: cherry_decide() */
     const char * v = getenv("PLF_VIRTUAL_CHERRY_MIN_SITES");
-    /* measured: virtual cherries win at every width (100 taxa x 1000 sites 86 vs 90 us, x 10k 131 vs 168 us,
-     * profiles/r2_notes.md), so the default threshold is none */
-    cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : 0u;
+    /* measured (profiles/r2_notes.md, 100 taxa): from 4096 sites up virtual cherries win (90 vs 106 us, at 10k
+     * sites 127 vs 168 us); below ~2500 sites a traversal is bound by its launches and the one-launch-per-level
+     * kernel with every parent written is fastest (1000 sites: 62 us against 78 us) */
+    cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : 2049u;
     if (sites >= cp->cherry_min_sites)
     {
       NEED(cp->cherry = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));

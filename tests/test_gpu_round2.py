@@ -62,11 +62,11 @@ CHERRY_CASES = [
 
 
 CHERRY_VARIANTS = {
-    "default": {},                                                  # ring kernel, 256 threads x 1 block per thread
-    "items2": {"PLF_CHERRY_ITEMS": "2"},                            # 128 threads x 2 blocks per thread
-    "items4": {"PLF_CHERRY_ITEMS": "4"},                            # 128-site tiles
-    "bulk": {"PLF_CHERRY_BULK": "1"},                               # write-only consumers through bulk stores
-    "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4"},
+    "default": {"PLF_LEVEL_MAX_SITES": "0"},                        # ring kernel, 256 threads x 1 block per thread
+    "items2": {"PLF_CHERRY_ITEMS": "2", "PLF_LEVEL_MAX_SITES": "0"},   # 128 threads x 2 blocks per thread
+    "items4": {"PLF_CHERRY_ITEMS": "4", "PLF_LEVEL_MAX_SITES": "0"},   # 128-site tiles
+    "bulk": {"PLF_CHERRY_BULK": "1", "PLF_LEVEL_MAX_SITES": "0"},      # write-only consumers through bulk stores
+    "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4", "PLF_LEVEL_MAX_SITES": "0"},
     "level": {"PLF_LEVEL_MAX_SITES": "1000000"},                    # one launch per traversal level (k_clv_dna_level)
     "level-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0"},
 }
@@ -149,19 +149,23 @@ def test_virtual_cherry_survives_pmatrix_and_tip_changes(reflib, cudalib, monkey
 
 
 def test_virtual_cherries_off_switch_and_threshold(cudalib, monkeypatch):
-    ds = synth.dna_dataset(10, 200, seed=3)
-    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
-    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1  # default: any width
+    narrow, wide = synth.dna_dataset(10, 200, seed=3), synth.dna_dataset(10, 5000, seed=3, simulate_down_tree=False)
+    ds = narrow
+    gpu = harness.Engine(cudalib, narrow, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0  # default: launch-bound widths write every parent
     gpu.close()
-    monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "1000")
-    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
-    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0  # narrower than the threshold asked for
+    gpu = harness.Engine(cudalib, wide, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
     gpu.close()
     monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
+    gpu = harness.Engine(cudalib, narrow, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 1
+    gpu.close()
     monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "0")
-    gpu = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+    gpu = harness.Engine(cudalib, wide, capi.ARCH_CUDA | capi.PATTERN_TIP)
     assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0
     gpu.close()
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "1")
     # partitions the kernels do not serve: tip CLVs instead of pattern tips, odd state counts, ascertainment bias
     for d, extra in ((ds, 0), (synth.generic_dataset(5, 8, 100, seed=4), capi.PATTERN_TIP), (ds, capi.PATTERN_TIP | capi.AB_FLAG)):
         gpu = harness.Engine(cudalib, d, capi.ARCH_CUDA | extra)
@@ -551,5 +555,34 @@ def test_repeated_identifier_updates_replay_a_graph(reflib, cudalib):
     cudalib.pll_update_repeats(gpu.p, C.byref(odd))
     traverse(gpu)
     check("after pll_update_repeats on a node of the list")
+    ref.close()
+    gpu.close()
+
+
+# ---- the per-kind ring / bulk kernels on the small shapes that the level kernel now takes by default ---------
+
+from test_gpu_parity import CASES as R1_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", [c for c in R1_CASES if c[0] == "dna" and c[4] & capi.PATTERN_TIP],
+                         ids=lambda c: "-".join(map(str, c)))
+@pytest.mark.parametrize("cherries", ["0", "1"], ids=["written", "virtual"])
+def test_per_kind_kernels_small_shapes(reflib, cudalib, monkeypatch, case, cherries):
+    """Alignments up to 2048 sites run one launch per level by default; the streaming per-kind kernels (ring
+    copies, bulk stores) keep their small-shape coverage here: PLF_LEVEL_MAX_SITES=0."""
+    kind, tips, sites, tree, extra, per_rate = case
+    monkeypatch.setenv("PLF_LEVEL_MAX_SITES", "0")
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", cherries)
+    monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
+    ds = synth.dna_dataset(tips, sites, seed=11, tree_kind=tree, alpha=0.4)
+    ref, gpu = pair(reflib, cudalib, ds, extra, per_rate)
+    traverse(ref, gpu)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
+    n_scaled = compare_all_nodes(ref, gpu)
+    if tree == "caterpillar":
+        assert n_scaled > 0
+    for _ in range(3):
+        traverse(gpu)
+    compare_all_nodes(ref, gpu)
     ref.close()
     gpu.close()
