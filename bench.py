@@ -403,6 +403,18 @@ def config3_record(lib, torch, local, threads):
                                "ms_per_step": 1e3 * sec,
                                "sample": f"the whole {tips} x {sites} input, 3 timed steps, AVX2+PATTERN_TIP, one partition per thread"}
         rec["parity"] = parity_block(gpu_vals, ref_vals, "reference (oracle/_ref, AVX2) on the same input, site-split")
+    # "also run once with per-rate scalers" (PLL_ATTRIB_RATE_SCALERS)
+    eng = harness.Engine(lib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP | capi.RATE_SCALERS)
+    ext = torch.cuda.ExternalStream(lib.pll_cuda_get_stream(eng.p), device=torch.device("cuda", local))
+    eng.update_pmatrices()
+    ms_rate = device_timed(torch, ext, eng.update_partials, reps=10)
+    vals_rate = gpu_eval(lib, eng, t_len)
+    eng.close()
+    rec["per_rate_scalers"] = {"traversal_ms": ms_rate, "logl": float(vals_rate[0])}
+    res = cpu_reference_eval(ds, capi.PATTERN_TIP | capi.RATE_SCALERS, 0, sites, threads, 1, 0)
+    if res is not None:
+        rec["per_rate_scalers"]["cpu_ms_per_step"] = 1e3 * res[0]
+        rec["per_rate_scalers"]["parity"] = parity_block(vals_rate, res[1], "reference (oracle/_ref, AVX2|RATE_SCALERS) on the same input")
     return rec
 
 

@@ -64,7 +64,14 @@ typedef struct plf_op
   const double * right_cm2;
   unsigned int nsites;
   unsigned int kind;
+  /* positions, in the level-sorted list this op is launched with, of the ops that write what it reads
+   * (left CLV, right CLV, left scaler, right scaler); PLF_DEP_NONE when the value is older than the list.
+   * dep[0] == PLF_DEP_ORDERED: the list also carries write-after-read / write-after-write order (buffers
+   * recycled within the list), which only the launch levels keep */
+  int dep[4];
 } plf_op_t;
+#define PLF_DEP_NONE (-1)
+#define PLF_DEP_ORDERED (-2)
 
 /* Model block in device memory, all doubles, per RATE CATEGORY (indices
  * already resolved through params_indices / freqs_indices):

@@ -59,6 +59,7 @@ extern "C" int plf_ctx_create(int device, int managed, plf_ctx_t ** out, char * 
   ctx->managed = managed;
   ctx->dna_stream = -1;
   ctx->dna_level_max_sites = -1;
+  ctx->dna_flow = -1;
   ctx->graph_mode = -1;
   ctx->aa_stream = -1;
   ctx->aam_log2r[0] = ctx->aam_log2r[1] = -1;
@@ -134,6 +135,7 @@ extern "C" void plf_ctx_destroy(plf_ctx_t * ctx)
   free(ctx->guard_recs);
   cudaFree(ctx->ws_ops.ptr);
   cudaFree(ctx->ws_once.ptr);
+  cudaFree(ctx->ws_flow.ptr);
   cudaFree(ctx->ws_small.ptr);
   cudaFree(ctx->ws_partial.ptr);
   cudaFree(ctx->d_result);

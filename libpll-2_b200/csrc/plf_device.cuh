@@ -37,6 +37,14 @@ __device__ __forceinline__ dbl4 ld256_stream(const double * p)
                : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
   return v;
 }
+/* coherent at L2: for values another CTA of the SAME launch wrote (after an acquire of its flag) */
+__device__ __forceinline__ dbl4 ld256_cg(const double * p)
+{
+  dbl4 v;
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st256(double * p, const dbl4 & v)
 {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"

@@ -34,6 +34,11 @@ struct plf_ctx
   int dna_cherry_items;           /* PLF_CHERRY_ITEMS: 2 (default) or 4 (site, rate) blocks per thread and tile */
   int dna_cherry_stages;          /* PLF_CHERRY_STAGES: 6 (default) or 4 ring stages */
   int dna_level_max_sites;        /* PLF_LEVEL_MAX_SITES: widest alignment whose levels run as one launch each (-1 = read on first use) */
+  int dna_flow;                   /* PLF_FLOW=0: narrow alignments one launch per level instead of one per traversal (-1 = read on first use) */
+  int dna_flow_max_sites;         /* PLF_FLOW_MAX_SITES: widest alignment that runs as one launch per traversal */
+  unsigned long long dna_flow_max_updates; /* PLF_FLOW_MAX_UPDATES: ... and most ops x sites */
+  int dna_flow_path_max;          /* PLF_FLOW_PATH_MAX: ops of a path (1 = every parent goes through memory) */
+  int dna_flow_occupancy[3];
   int dna_cherry_bulk;            /* PLF_CHERRY_BULK=1: tip + cherry / cherry + cherry through the bulk-store kernel instead of the ring kernel */
   int dna_cherry;                 /* PLF_VIRTUAL_CHERRIES=0 writes every tip-tip parent to HBM */
   int dna_tt_bulk_occupancy[4];
@@ -64,6 +69,8 @@ struct plf_ctx
   cudaMemPool_t pool;    /* stream-ordered allocator behind plf_alloc/plf_free (NULL in managed mode) */
   plf_ws ws_ops;      /* op descriptors of the current update_partials call   */
   plf_ws ws_once;     /* op descriptors of internal single ops (materialised cherries) */
+  plf_ws ws_flow;     /* k_clv_dna_flow: queue control block + one flag per work item */
+  void * ws_flow_zeroed; /* the allocation whose flags have been zeroed */
   plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
   plf_ws ws_partial;  /* per-block partial sums of the reductions              */
   plf_ws ws_edge;     /* synthetic op + matrices of the DNA/AA sumtable launches */
@@ -102,6 +109,25 @@ int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned in
 unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats);
 int plf_launch_dna_level(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int rate_cats, int per_rate,
                          unsigned int max_sites);
+/* k_clv_dna_flow (plf_partials_dna.cu): one op of a path, as the kernel stages it in shared memory */
+#define PLF_FLOW_PATH_MAX 8
+struct plf_flow_op
+{
+  double * parent_clv;
+  unsigned int * parent_scaler;
+  const double * clv[2];          /* inner child, NULL when that side is a pattern tip */
+  const unsigned char * tip[2];
+  const double * matrix[2];
+  const unsigned int * scaler[2]; /* child scaler to read from memory (NULL: none, or it travels in registers) */
+  int dep[2];                     /* path whose flag says clv[side] / scaler[side] has been written, or PLF_DEP_NONE */
+  unsigned int nsites;
+  unsigned int flags;
+};
+unsigned int plf_dna_flow_chunks(unsigned int rate_cats, unsigned int max_sites);
+unsigned int plf_dna_flow_plan(const struct plf_op * h_ops, unsigned int nops, unsigned int path_max,
+                               struct plf_flow_op * out_ops, unsigned int * out_start);
+int plf_launch_dna_flow(plf_ctx * ctx, const struct plf_flow_op * d_fops, const unsigned int * d_path_start,
+                        unsigned int npaths, unsigned int rate_cats, int per_rate, unsigned int max_sites, void * flow);
 int plf_aa_virtual_cherries_supported(plf_ctx * ctx, const struct plf_shape * sh, unsigned int maxstates);
 int plf_dna_virtual_cherries_supported(plf_ctx * ctx, const struct plf_shape * sh);
 

@@ -478,6 +478,65 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
   }
   const unsigned int level_max_sites = (unsigned int)ctx->dna_level_max_sites;
   const int L = one_rate ? R : 1;
+  if (ctx->dna_flow < 0)
+  {
+    const char * v = getenv("PLF_FLOW");
+    ctx->dna_flow = !(v && v[0] == '0');
+    /* 100 taxa: equal to the ring kernels near 30k sites; 1000 taxa: near 4000 sites (profiles/r2_notes.md) */
+    v = getenv("PLF_FLOW_MAX_SITES");
+    ctx->dna_flow_max_sites = (v && v[0]) ? atoi(v) : 32768;
+    v = getenv("PLF_FLOW_MAX_UPDATES");
+    ctx->dna_flow_max_updates = (v && v[0]) ? strtoull(v, nullptr, 10) : 2400000ull;
+    v = getenv("PLF_FLOW_PATH_MAX");
+    ctx->dna_flow_path_max = (v && atoi(v) >= 1 && atoi(v) <= PLF_FLOW_PATH_MAX) ? atoi(v) : PLF_FLOW_PATH_MAX;
+  }
+  if (ctx->dna_flow && ws == &ctx->ws_ops && nlevels > 1 && nops > 1 && sh->states == 4 && one_rate &&
+      sh->rate_cats <= 4 && h_ops[0].dep[0] != PLF_DEP_ORDERED && h_ops[0].nsites <= (unsigned int)ctx->dna_flow_max_sites &&
+      (unsigned long long)nops * h_ops[0].nsites <= ctx->dna_flow_max_updates)
+  {
+    /* narrow alignment, plain list (no buffer recycled, no virtual cherries, no repeat identifiers): the whole
+     * traversal as one launch of k_clv_dna_flow */
+    const unsigned int sites = h_ops[0].nsites;
+    int plain = sites > 0;
+    for (unsigned int i = 0; i < nops && plain; ++i)
+    {
+      const plf_op_t & o = h_ops[i];
+      plain = o.nsites == sites && (o.kind == PLF_OP_II || o.kind == PLF_OP_TI || o.kind == PLF_OP_TT) &&
+              !(o.parent_id_site || o.left_site_id || o.right_site_id);
+    }
+    const unsigned long long flags = (unsigned long long)nops * plf_dna_flow_chunks(sh->rate_cats, sites);
+    if (plain && flags < (1ull << 30))
+    {
+      const size_t plan_at = 64 + (size_t)flags * sizeof(unsigned long long);
+      const size_t start_at = plan_at + (size_t)nops * sizeof(plf_flow_op);
+      const size_t bytes = start_at + ((size_t)nops + 1) * sizeof(unsigned int);
+      unsigned char * h_plan = (unsigned char *)malloc(bytes - plan_at);
+      const unsigned int npaths =
+          h_plan ? plf_dna_flow_plan(h_ops, nops, (unsigned int)ctx->dna_flow_path_max, (plf_flow_op *)h_plan,
+                                     (unsigned int *)(h_plan + (start_at - plan_at)))
+                 : 0;
+      if (npaths)
+      {
+        unsigned char * flow = (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_flow, bytes);
+        cudaError_t e = flow ? cudaSuccess : cudaErrorMemoryAllocation;
+        if (flow && ctx->ws_flow_zeroed != flow)
+        {
+          /* a new allocation: epoch 0, no flag set (never inside a capture: a captured list ran once before) */
+          e = cudaMemsetAsync(flow, 0, ctx->ws_flow.bytes, ctx->stream);
+          ctx->ws_flow_zeroed = flow;
+        }
+        if (e == cudaSuccess && upload)
+          e = cudaMemcpyAsync(flow + plan_at, h_plan, bytes - plan_at, cudaMemcpyHostToDevice, ctx->stream);
+        /* (pageable source: staged by the driver before the call returns, like the descriptors above) */
+        free(h_plan);
+        if (!flow) return 0;
+        PLF_CHECK(ctx, e);
+        return plf_launch_dna_flow(ctx, (const plf_flow_op *)(flow + plan_at), (const unsigned int *)(flow + start_at),
+                                   npaths, sh->rate_cats, sh->per_rate_scalers, sites, flow);
+      }
+      free(h_plan);
+    }
+  }
 
   for (unsigned int lv = 0; lv < nlevels; ++lv)
   {

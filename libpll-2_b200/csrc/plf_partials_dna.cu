@@ -1284,6 +1284,366 @@ int plf_launch_dna_level(plf_ctx * ctx, const plf_op_t * d_ops, unsigned int nop
   return 1;
 }
 
+/* ------------------------------------------------------------------------ *
+ *  Narrow alignments, one step further: the WHOLE traversal in one launch.    *
+ *  Twelve launches of a 100-taxon traversal still cost ~5 us each although a   *
+ *  level's work is a fraction of that.  Here the op list becomes a queue of     *
+ *  work items (path, chunk of sites).  A PATH is a chain of ops in which each   *
+ *  op's parent is the next op's child and nobody else's: the host cuts the      *
+ *  tree into such chains along the heavier child (plf_dna_flow_plan), so any    *
+ *  root-to-tip walk crosses at most log2(n) of them.  Inside a path the parent  *
+ *  stays in the thread's registers (a thread owns one (site, rate) block from   *
+ *  the first op of the path to the last; sites and rates are independent), its  *
+ *  scaler count with it: no barrier, no trip through L2.  Between paths,        *
+ *  persistent CTAs claim items in queue order from an atomic counter, and an    *
+ *  op whose other child is written by an earlier item of the same launch waits  *
+ *  for exactly that item's flag (same chunk) instead of for a launch boundary.  *
+ *  Descriptors, matrices and tip codes of the whole path are staged in shared    *
+ *  memory before the first wait.                                                 *
+ *  No deadlock: an item's producers have smaller queue positions (paths are      *
+ *  queued in the order of their last ops), so they were claimed earlier by CTAs  *
+ *  that are running; the unfinished item with the smallest position never waits. *
+ *  Flags carry the launch's epoch, the last CTA to leave rewinds the queue and   *
+ *  advances the epoch: nothing to reset between launches, so the kernel replays  *
+ *  inside a CUDA graph as it is.                                                 *
+ *  Arithmetic and order as the per-kind kernels (a tip term is the masked        *
+ *  pairwise sum the tip tables hold): the same bits.                             *
+ * ------------------------------------------------------------------------ */
+struct plf_flow_ctrl
+{
+  unsigned long long epoch;
+  unsigned int next_item;
+  unsigned int exited;
+};
+
+__device__ __forceinline__ unsigned long long flow_ld_acquire(const unsigned long long * p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void flow_st_release(unsigned long long * p, unsigned long long v)
+{
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+#define FLOW_CARRY_MASK 3u   /* 1: the left child is the previous op's parent (in registers), 2: the right one */
+#define FLOW_CARRY_SCALER 4u /* ... and its scaler counts with it */
+#define FLOW_TIP_TIP 8u      /* never scales, zeroes its scaler (src/core_partials_avx.c:1005-1006) */
+
+template <int LOG2R>
+__global__ void __launch_bounds__(DNA_THREADS)
+k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __restrict__ path_start, unsigned int npaths,
+               unsigned int nchunks, int per_rate, plf_flow_ctrl * ctrl, unsigned long long * ready)
+{
+  constexpr int R = 1 << LOG2R;
+  constexpr unsigned int PASS = DNA_THREADS >> LOG2R; /* sites of a work item */
+  constexpr int MSTRIDE = 18;                         /* doubles per rate of a staged matrix: rates on different banks */
+  constexpr int DWORDS = sizeof(plf_flow_op) / 8;
+  __shared__ __align__(16) unsigned long long sdesc_raw[PLF_FLOW_PATH_MAX * DWORDS];
+  __shared__ __align__(16) double smat[PLF_FLOW_PATH_MAX][2][R * MSTRIDE];
+  __shared__ unsigned char scode[PLF_FLOW_PATH_MAX][2][PASS];
+  __shared__ unsigned int s_item;
+  __shared__ unsigned long long s_epoch;
+  const plf_flow_op * sdesc = reinterpret_cast<const plf_flow_op *>(sdesc_raw);
+  const unsigned int total = npaths * nchunks;
+  if (threadIdx.x == 0)
+  {
+    s_epoch = *reinterpret_cast<volatile unsigned long long *>(&ctrl->epoch) + 1ull;
+    s_item = atomicAdd(&ctrl->next_item, 1u);
+  }
+  __syncthreads();
+  const unsigned long long epoch1 = s_epoch;
+  const int rate = threadIdx.x & (R - 1);
+  const unsigned int lane_site = threadIdx.x >> LOG2R;
+  for (;;)
+  {
+    const unsigned int item = s_item;
+    if (item >= total) break;
+    const unsigned int path = item / nchunks, chunk = item - path * nchunks;
+    const unsigned int first_op = path_start[path], n = path_start[path + 1] - first_op;
+    unsigned int next = 0;
+    if (threadIdx.x == 0) next = atomicAdd(&ctrl->next_item, 1u); /* in flight while this item is worked on */
+    {
+      const unsigned long long * src = reinterpret_cast<const unsigned long long *>(fops + first_op);
+      for (unsigned int i = threadIdx.x; i < n * DWORDS; i += DNA_THREADS) sdesc_raw[i] = src[i];
+    }
+    __syncthreads();
+    const unsigned int nsites = sdesc[0].nsites;
+    const unsigned int first = chunk * PASS;
+    for (unsigned int i = threadIdx.x; i < n * 2 * R * 16; i += DNA_THREADS)
+    {
+      const unsigned int k = i / (2 * R * 16), rem = i - k * (2 * R * 16), side = rem / (R * 16), e = rem - side * (R * 16);
+      smat[k][side][(e >> 4) * MSTRIDE + (e & 15)] = sdesc[k].matrix[side][e];
+    }
+    for (unsigned int i = threadIdx.x; i < n * 2 * PASS; i += DNA_THREADS)
+    {
+      const unsigned int k = i / (2 * PASS), side = (i / PASS) & 1u, ls = i % PASS;
+      const unsigned char * tp = sdesc[k].tip[side];
+      if (tp) scode[k][side][ls] = tp[min(first + ls, nsites - 1)];
+    }
+    __syncthreads();
+    if (first < nsites)
+    {
+      const unsigned int site = first + lane_site;
+      const bool active = site < nsites;
+      const unsigned int nn = active ? site : nsites - 1; /* inactive lanes recompute the last site, store nothing */
+      const bool keeps_count = per_rate || rate == 0;
+      dbl4 carry_v = dbl4{0, 0, 0, 0};
+      unsigned int carry_sc = 0;
+#pragma unroll 1
+      for (unsigned int k = 0; k < n; ++k)
+      {
+        const plf_flow_op & d = sdesc[k];
+        const unsigned int flags = d.flags;
+        dbl4 term[2];
+        unsigned int sc = 0;
+#pragma unroll
+        for (int side = 0; side < 2; ++side)
+        {
+          const double * M = smat[k][side] + rate * MSTRIDE;
+          if (d.tip[side])
+          {
+            const unsigned int code = scode[k][side][lane_site];
+            term[side].x = masked_sum4(M + 0, code);
+            term[side].y = masked_sum4(M + 4, code);
+            term[side].z = masked_sum4(M + 8, code);
+            term[side].w = masked_sum4(M + 12, code);
+          }
+          else
+          {
+            dbl4 c;
+            if ((flags & FLOW_CARRY_MASK) == (unsigned int)(side + 1))
+            {
+              c = carry_v;
+              if (flags & FLOW_CARRY_SCALER) sc += carry_sc;
+            }
+            else
+            {
+              if (d.dep[side] >= 0)
+              {
+                const unsigned long long * f = ready + (size_t)d.dep[side] * nchunks + chunk;
+                while (flow_ld_acquire(f) != epoch1) {}
+              }
+              c = ld256_cg(d.clv[side] + ((size_t)nn * R + rate) * 4);
+            }
+            if (d.scaler[side] && d.parent_scaler && keeps_count)
+              sc += __ldcg(d.scaler[side] + (per_rate ? (size_t)nn * R + rate : nn));
+            term[side].x = dot4_pairwise(M + 0, c);
+            term[side].y = dot4_pairwise(M + 4, c);
+            term[side].z = dot4_pairwise(M + 8, c);
+            term[side].w = dot4_pairwise(M + 12, c);
+          }
+        }
+        dbl4 v = dbl4{term[0].x * term[1].x, term[0].y * term[1].y, term[0].z * term[1].z, term[0].w * term[1].w};
+        if (d.parent_scaler)
+        {
+          if (flags & FLOW_TIP_TIP)
+            sc = 0;
+          else
+          {
+            const int below = (v.x < PLF_SCALE_THRESHOLD) && (v.y < PLF_SCALE_THRESHOLD) && (v.z < PLF_SCALE_THRESHOLD) &&
+                              (v.w < PLF_SCALE_THRESHOLD);
+            const int fire = per_rate ? below : group_and(below, R); /* all lanes of the warp take part */
+            if (fire)
+            {
+              v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
+              v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
+              sc += 1u;
+            }
+          }
+          if (active && keeps_count) d.parent_scaler[per_rate ? (size_t)site * R + rate : site] = sc;
+        }
+        if (active) st256(d.parent_clv + ((size_t)site * R + rate) * 4, v);
+        carry_v = v;
+        carry_sc = sc;
+      }
+    }
+    __syncthreads(); /* every store of the item has been issued */
+    if (threadIdx.x == 0)
+    {
+      flow_st_release(ready + item, epoch1);
+      s_item = next;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    if (atomicAdd(&ctrl->exited, 1u) == gridDim.x - 1)
+    {
+      /* every CTA has made its last claim: rewind the queue for the next launch */
+      ctrl->next_item = 0;
+      ctrl->exited = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned long long *>(&ctrl->epoch) = epoch1;
+    }
+  }
+}
+
+unsigned int plf_dna_flow_chunks(unsigned int rate_cats, unsigned int max_sites)
+{
+  int log2r = 0;
+  while ((1u << log2r) < rate_cats) ++log2r;
+  const unsigned int pass = DNA_THREADS >> log2r;
+  return (max_sites + pass - 1) / pass;
+}
+
+/* Cuts a level-sorted, plain op list (kinds II / TI / TT, contiguous CLVs, dep[] filled by the host layer) into
+ * paths.  out_ops (nops entries) receives the ops path by path, bottom to top; out_start (nops + 1 entries) the
+ * first op of each path.  Returns the number of paths, 0 when the list cannot run as one launch. */
+unsigned int plf_dna_flow_plan(const plf_op_t * h_ops, unsigned int nops, unsigned int path_max, plf_flow_op * out_ops,
+                               unsigned int * out_start)
+{
+  if (path_max < 1) path_max = 1;
+  if (path_max > PLF_FLOW_PATH_MAX) path_max = PLF_FLOW_PATH_MAX;
+  unsigned int * buf = (unsigned int *)malloc((size_t)nops * 6 * sizeof(unsigned int));
+  if (!buf) return 0;
+  unsigned int * readers = buf, * weight = buf + nops, * path_of = buf + 2 * (size_t)nops, * chain = buf + 3 * (size_t)nops;
+  int * down = (int *)(buf + 4 * (size_t)nops); /* the child op whose parent this op keeps in registers, or -1 */
+  unsigned char * taken = (unsigned char *)(buf + 5 * (size_t)nops); /* is some op's `down` */
+  unsigned int npaths = 0, emitted = 0;
+  int ok = 1;
+  memset(readers, 0, (size_t)nops * sizeof(unsigned int));
+  memset(taken, 0, nops);
+  for (unsigned int i = 0; i < nops && ok; ++i)
+  {
+    const plf_op_t & o = h_ops[i];
+    if (o.dep[2] != PLF_DEP_NONE || o.dep[3] != PLF_DEP_NONE) ok = 0; /* a scaler written by another op than the CLV's */
+    for (int s = 0; s < 2 && ok; ++s)
+      if (o.dep[s] != PLF_DEP_NONE)
+      {
+        if (o.dep[s] < 0 || (unsigned int)o.dep[s] >= i) ok = 0;
+        else ++readers[o.dep[s]];
+      }
+  }
+  for (unsigned int i = 0; i < nops && ok; ++i)
+  {
+    const plf_op_t & o = h_ops[i];
+    weight[i] = 1;
+    down[i] = -1;
+    for (int s = 0; s < 2; ++s)
+      if (o.dep[s] >= 0 && !(s == 1 && o.dep[1] == o.dep[0])) weight[i] += weight[o.dep[s]];
+    if (path_max == 1) continue;
+    for (int s = 0; s < 2; ++s)
+    {
+      const int d = o.dep[s];
+      if (d < 0 || readers[d] != 1) continue;
+      if (down[i] < 0 || weight[d] > weight[down[i]]) down[i] = d;
+    }
+    if (down[i] >= 0) taken[down[i]] = 1;
+  }
+  /* chains in the order of their last ops (an op nobody keeps in registers ends a chain), each cut bottom to top
+   * into paths of <= path_max ops.  A lower path of a chain is read by the next path of the same chain only, which
+   * follows it directly; everything else a chain reads ends before the chain's last op and was queued earlier. */
+  for (unsigned int i = 0; i < nops && ok; ++i)
+  {
+    if (taken[i]) continue;
+    unsigned int len = 0;
+    for (int k = (int)i; k >= 0; k = down[k]) chain[len++] = (unsigned int)k; /* top to bottom */
+    for (unsigned int b = 0; b < len; b += path_max)
+    {
+      const unsigned int e = (b + path_max < len) ? b + path_max : len;
+      out_start[npaths] = emitted;
+      for (unsigned int k = b; k < e; ++k, ++emitted) path_of[chain[len - 1 - k]] = npaths;
+      ++npaths;
+    }
+  }
+  if (ok && emitted != nops) ok = 0;
+  if (ok)
+  {
+    unsigned int pos = 0;
+    out_start[npaths] = nops;
+    /* the same walk again, now that every op knows its path: the descriptors */
+    unsigned int path = 0;
+    for (unsigned int i = 0; i < nops; ++i)
+    {
+      if (taken[i]) continue;
+      unsigned int len = 0;
+      for (int k = (int)i; k >= 0; k = down[k]) chain[len++] = (unsigned int)k;
+      for (unsigned int b = 0; b < len; b += path_max, ++path)
+      {
+        const unsigned int e = (b + path_max < len) ? b + path_max : len;
+        for (unsigned int k = b; k < e; ++k, ++pos)
+        {
+          const unsigned int oi = chain[len - 1 - k];
+          const plf_op_t & o = h_ops[oi];
+          plf_flow_op & f = out_ops[pos];
+          memset(&f, 0, sizeof(f));
+          f.parent_clv = o.parent_clv;
+          f.parent_scaler = o.parent_scaler;
+          f.nsites = o.nsites;
+          f.matrix[0] = o.left_matrix;
+          f.matrix[1] = o.right_matrix;
+          f.dep[0] = f.dep[1] = PLF_DEP_NONE;
+          if (o.kind == PLF_OP_TT) f.flags |= FLOW_TIP_TIP;
+          if (o.kind != PLF_OP_II) f.tip[0] = o.left_tip; else f.clv[0] = o.left_clv;
+          if (o.kind == PLF_OP_TT) f.tip[1] = o.right_tip; else f.clv[1] = o.right_clv;
+          if (o.kind == PLF_OP_II) f.scaler[0] = o.left_scaler;
+          if (o.kind != PLF_OP_TT) f.scaler[1] = o.right_scaler;
+          for (int s = 0; s < 2; ++s)
+          {
+            const int d = o.dep[s];
+            if (d < 0) continue;
+            /* which side reads that op's parent: the host layer may have swapped the children (tip first) */
+            const double * produced = h_ops[d].parent_clv;
+            int hit = 0;
+            for (int side = 0; side < 2; ++side)
+            {
+              if (f.clv[side] != produced) continue;
+              hit = 1;
+              if (k > b && down[oi] == d && (f.flags & FLOW_CARRY_MASK) == 0)
+              {
+                f.flags |= (unsigned int)(side + 1);
+                if (f.scaler[side] && f.scaler[side] == h_ops[d].parent_scaler)
+                {
+                  f.flags |= FLOW_CARRY_SCALER;
+                  f.scaler[side] = nullptr;
+                }
+                break; /* the other side, should it read the same CLV, could not: readers == 1 */
+              }
+              f.dep[side] = (int)path_of[d];
+            }
+            if (!hit) ok = 0;
+          }
+        }
+      }
+    }
+  }
+  free(buf);
+  return ok ? npaths : 0;
+}
+
+int plf_launch_dna_flow(plf_ctx * ctx, const plf_flow_op * d_fops, const unsigned int * d_path_start, unsigned int npaths,
+                        unsigned int rate_cats, int per_rate, unsigned int max_sites, void * flow)
+{
+  int log2r = 0;
+  while ((1u << log2r) < rate_cats) ++log2r;
+  const unsigned int nchunks = plf_dna_flow_chunks(rate_cats, max_sites);
+  if (!ctx->dna_flow_occupancy[log2r])
+  {
+    int per_sm = 0;
+    const void * fn = log2r == 0 ? (const void *)k_clv_dna_flow<0>
+                                 : (log2r == 1 ? (const void *)k_clv_dna_flow<1> : (const void *)k_clv_dna_flow<2>);
+    PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, DNA_THREADS, 0));
+    ctx->dna_flow_occupancy[log2r] = per_sm > 0 ? per_sm : 1;
+  }
+  const unsigned long long items = (unsigned long long)npaths * nchunks;
+  unsigned long long grid = (unsigned long long)ctx->sm_count * ctx->dna_flow_occupancy[log2r];
+  if (grid > items) grid = items;
+  plf_flow_ctrl * ctrl = reinterpret_cast<plf_flow_ctrl *>(flow);
+  unsigned long long * ready = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(flow) + 64);
+  switch (log2r)
+  {
+    case 0: k_clv_dna_flow<0><<<(unsigned int)grid, DNA_THREADS, 0, ctx->stream>>>(d_fops, d_path_start, npaths, nchunks, per_rate, ctrl, ready); break;
+    case 1: k_clv_dna_flow<1><<<(unsigned int)grid, DNA_THREADS, 0, ctx->stream>>>(d_fops, d_path_start, npaths, nchunks, per_rate, ctrl, ready); break;
+    default: k_clv_dna_flow<2><<<(unsigned int)grid, DNA_THREADS, 0, ctx->stream>>>(d_fops, d_path_start, npaths, nchunks, per_rate, ctrl, ready); break;
+  }
+  plf_count_launch();
+  PLF_CHECK(ctx, cudaGetLastError());
+  return 1;
+}
+
 /* ------------------------------------------------------------------------ */
 
 typedef void (*dna_kernel_t)(const plf_op_t *, int);

@@ -184,7 +184,7 @@ typedef struct cuda_partition
    * written to HBM; their consumers work from the tip codes, anything else materialises them first */
   int cherry_ok;                 /* this partition's kernels consume virtual cherries */
   unsigned int cherry_maxstates; /* tip alphabet size cherry_ok was decided for (0: not yet) */
-  unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES, default 2049) */
+  unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES; default 2049, 4 states: above what runs as one launch) */
   double * d_cherry_pm;          /* [clv_buffers][2][rate_cats * 16]: the P-matrices each cherry was asked with */
   struct cherry_state * cherry;  /* [nodes] */
   struct cherry_state * cherry_saved; /* roll-back copy while an operation list is resolved */
@@ -755,6 +755,24 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
      * sites 127 vs 168 us); below ~2500 sites a traversal is bound by its launches and the one-launch-per-level
      * kernel with every parent written is fastest (1000 sites: 62 us against 78 us) */
     cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : 2049u;
+    if (!(v && v[0]) && states == 4 && rate_cats <= 4 && (rate_cats & (rate_cats - 1)) == 0)
+    {
+      /* 4 states: a plain list of up to PLF_FLOW_MAX_UPDATES site-updates (default 2.4M: 100 taxa x 24k sites,
+       * 1000 taxa x 2.4k sites) over at most PLF_FLOW_MAX_SITES sites (default 32768) runs as ONE launch whose
+       * paths keep parents in registers (k_clv_dna_flow), every parent written.  100 taxa: 1000 sites 27 us
+       * against 62 us with one launch per level, 10k sites 72 us against 127 us with virtual cherries; equal
+       * near 30k sites (2.9M site-updates); 1000 taxa x 4000 sites: equal (profiles/r2_notes.md) */
+      const char * f = getenv("PLF_FLOW"), * m = getenv("PLF_FLOW_MAX_SITES"), * u = getenv("PLF_FLOW_MAX_UPDATES");
+      if (!(f && f[0] == '0'))
+      {
+        const unsigned long long max_sites = (m && m[0]) ? strtoull(m, NULL, 10) : 32768ull;
+        const unsigned long long max_updates = (u && u[0]) ? strtoull(u, NULL, 10) : 2400000ull;
+        const unsigned long long ops = tips > 2 ? tips - 2 : 1;
+        unsigned long long lim = max_updates / ops;
+        if (lim > max_sites) lim = max_sites;
+        if (lim >= 2048ull) cp->cherry_min_sites = lim >= 0xFFFFFFFEull ? 0xFFFFFFFFu : (unsigned int)lim + 1u;
+      }
+    }
     if (sites >= cp->cherry_min_sites)
     {
       NEED(cp->cherry = (cherry_state_t *)calloc(p->nodes, sizeof(cherry_state_t)));
@@ -2427,6 +2445,7 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
   const unsigned int c1 = op->child1_clv_index, c2 = op->child2_clv_index, par = op->parent_clv_index;
   unsigned int * const * sb = p->scale_buffer;
   memset(out, 0, sizeof(*out));
+  out->dep[0] = out->dep[1] = out->dep[2] = out->dep[3] = PLF_DEP_NONE;
   if (par >= p->nodes || c1 >= p->nodes || c2 >= p->nodes || op->child1_matrix_index >= p->prob_matrices ||
       op->child2_matrix_index >= p->prob_matrices || op->parent_scaler_index >= (int)p->scale_buffers ||
       op->child1_scaler_index >= (int)p->scale_buffers || op->child2_scaler_index >= (int)p->scale_buffers)
@@ -2630,6 +2649,56 @@ static int attach_pair_lists(cuda_partition_t * cp, const pll_operation_t * ops,
   return ok;
 }
 
+/* Who writes what each op reads (plf_op_t.dep): lets a narrow alignment's whole traversal run as ONE kernel
+ * whose work items wait for their producers' items instead of for a launch boundary.  cp->h_level[i] holds
+ * the position of ops[i] in cp->h_ops_sorted.  A list that recycles buffers (an op overwrites something an
+ * earlier op read or wrote) is marked PLF_DEP_ORDERED and keeps the launch levels. */
+static void attach_dependencies(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+{
+  const pll_partition_t * p = &cp->pub;
+  const size_t nclv = p->nodes, nsc = p->scale_buffers;
+  int * writer = (int *)malloc((nclv + nsc + 1) * sizeof(int));
+  unsigned char * was_read = (unsigned char *)calloc(nclv + nsc + 1, 1);
+  unsigned int i;
+  int ordered = (!writer || !was_read);
+  if (!ordered)
+  {
+    size_t k;
+    for (k = 0; k < nclv + nsc; ++k) writer[k] = PLF_DEP_NONE;
+    for (i = 0; i < count && !ordered; ++i)
+    {
+      const pll_operation_t * o = ops + i;
+      plf_op_t * s = cp->h_ops_sorted + cp->h_level[i];
+      const size_t par = o->parent_clv_index, c1 = o->child1_clv_index, c2 = o->child2_clv_index;
+      const int psc = o->parent_scaler_index, sc1 = o->child1_scaler_index, sc2 = o->child2_scaler_index;
+      if (writer[par] != PLF_DEP_NONE || was_read[par] || par == c1 || par == c2 ||
+          (psc >= 0 && (writer[nclv + psc] != PLF_DEP_NONE || was_read[nclv + psc] || psc == sc1 || psc == sc2)))
+      {
+        ordered = 1;
+        break;
+      }
+      s->dep[0] = writer[c1];
+      s->dep[1] = writer[c2];
+      s->dep[2] = (sc1 >= 0 && writer[nclv + sc1] != s->dep[0]) ? writer[nclv + sc1] : PLF_DEP_NONE;
+      s->dep[3] = (sc2 >= 0 && writer[nclv + sc2] != s->dep[1]) ? writer[nclv + sc2] : PLF_DEP_NONE;
+      was_read[c1] = was_read[c2] = 1;
+      if (sc1 >= 0) was_read[nclv + sc1] = 1;
+      if (sc2 >= 0) was_read[nclv + sc2] = 1;
+      writer[par] = (int)cp->h_level[i];
+      if (psc >= 0) writer[nclv + psc] = (int)cp->h_level[i];
+    }
+  }
+  if (ordered)
+    for (i = 0; i < count; ++i)
+    {
+      plf_op_t * s = cp->h_ops_sorted + i;
+      s->dep[0] = PLF_DEP_ORDERED;
+      s->dep[1] = s->dep[2] = s->dep[3] = PLF_DEP_NONE;
+    }
+  free(writer);
+  free(was_read);
+}
+
 static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
 {
   unsigned int i, nlevels, saved_pending = 0;
@@ -2690,9 +2759,15 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
     unsigned int * cursor = (unsigned int *)malloc(((size_t)nlevels + 1) * sizeof(unsigned int));
     if (!cursor) return 0;
     memcpy(cursor, cp->h_level_start, ((size_t)nlevels + 1) * sizeof(unsigned int));
-    for (i = 0; i < count; ++i) cp->h_ops_sorted[cursor[cp->h_level[i]]++] = cp->h_ops[i];
+    for (i = 0; i < count; ++i)
+    {
+      const unsigned int pos = cursor[cp->h_level[i]]++;
+      cp->h_ops_sorted[pos] = cp->h_ops[i];
+      cp->h_level[i] = pos; /* from here on: the op's position in the sorted list */
+    }
     free(cursor);
   }
+  if (count > 1 && cp->shape.states == 4 && !pll_repeats_enabled(&cp->pub)) attach_dependencies(cp, ops, count);
   if (!tipmap_on_device(cp) ||
       !plf_update_partials(cp->ctx, &cp->shape, cp->h_ops_sorted, count, cp->h_level_start, nlevels, cp->d_tipmap,
                            cp->pub.maxstates))

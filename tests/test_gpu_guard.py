@@ -82,13 +82,14 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "-".join(map(str, s)))
-@pytest.mark.parametrize("level_kernel", ["0", "1000000"], ids=["per-kind", "per-level"])
-def test_guard_bands_stay_intact(reflib, cudalib, monkeypatch, shape, level_kernel):
+@pytest.mark.parametrize("launches", ["per-kind", "per-level", "per-traversal"])
+def test_guard_bands_stay_intact(reflib, cudalib, monkeypatch, shape, launches):
     kind, tips, sites, cats, attrs, per_rate = shape
-    if level_kernel != "0" and not (kind == "dna" and cats in (1, 2, 4) and not attrs & capi.SITE_REPEATS):
-        pytest.skip("the one-launch-per-level kernel serves contiguous 4-state CLVs with 1, 2 or 4 rate categories")
+    if launches != "per-kind" and not (kind == "dna" and cats in (1, 2, 4) and not attrs & capi.SITE_REPEATS):
+        pytest.skip("k_clv_dna_level / k_clv_dna_flow serve contiguous 4-state CLVs with 1, 2 or 4 rate categories")
     monkeypatch.setenv("PLL_CUDA_GUARD", "1")
-    monkeypatch.setenv("PLF_LEVEL_MAX_SITES", level_kernel)
+    monkeypatch.setenv("PLF_LEVEL_MAX_SITES", "0" if launches == "per-kind" else "1000000")
+    monkeypatch.setenv("PLF_FLOW", "1" if launches == "per-traversal" else "0")
     if kind == "dna":
         ds = synth.dna_dataset(tips, sites, seed=300 + sites, cats=cats, brlen=(0.002, 0.08))
     elif kind == "aa":

@@ -68,7 +68,11 @@ CHERRY_VARIANTS = {
     "bulk": {"PLF_CHERRY_BULK": "1", "PLF_LEVEL_MAX_SITES": "0"},      # write-only consumers through bulk stores
     "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4", "PLF_LEVEL_MAX_SITES": "0"},
     "level": {"PLF_LEVEL_MAX_SITES": "1000000"},                    # one launch per traversal level (k_clv_dna_level)
-    "level-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0"},
+    "level-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW": "0"},
+    # the whole traversal as one launch (k_clv_dna_flow): paths of up to 8 ops, of 3, and every parent through memory
+    "flow-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0"},
+    "flow-written-3": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "3"},
+    "flow-written-1": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "1"},
 }
 
 
@@ -149,7 +153,7 @@ def test_virtual_cherry_survives_pmatrix_and_tip_changes(reflib, cudalib, monkey
 
 
 def test_virtual_cherries_off_switch_and_threshold(cudalib, monkeypatch):
-    narrow, wide = synth.dna_dataset(10, 200, seed=3), synth.dna_dataset(10, 5000, seed=3, simulate_down_tree=False)
+    narrow, wide = synth.dna_dataset(10, 200, seed=3), synth.dna_dataset(10, 40000, seed=3, simulate_down_tree=False)
     ds = narrow
     gpu = harness.Engine(cudalib, narrow, capi.ARCH_CUDA | capi.PATTERN_TIP)
     assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0  # default: launch-bound widths write every parent
@@ -566,12 +570,18 @@ from test_gpu_parity import CASES as R1_CASES  # noqa: E402
 
 @pytest.mark.parametrize("case", [c for c in R1_CASES if c[0] == "dna" and c[4] & capi.PATTERN_TIP],
                          ids=lambda c: "-".join(map(str, c)))
-@pytest.mark.parametrize("cherries", ["0", "1"], ids=["written", "virtual"])
+@pytest.mark.parametrize("cherries", ["0", "1", "level"], ids=["written", "virtual", "per-level"])
 def test_per_kind_kernels_small_shapes(reflib, cudalib, monkeypatch, case, cherries):
-    """Alignments up to 2048 sites run one launch per level by default; the streaming per-kind kernels (ring
-    copies, bulk stores) keep their small-shape coverage here: PLF_LEVEL_MAX_SITES=0."""
+    """Alignments up to 2048 sites run as one launch per traversal by default (k_clv_dna_flow); the streaming
+    per-kind kernels (ring copies, bulk stores: PLF_LEVEL_MAX_SITES=0) and the one-launch-per-level kernel
+    (PLF_FLOW=0) keep their small-shape coverage here."""
     kind, tips, sites, tree, extra, per_rate = case
-    monkeypatch.setenv("PLF_LEVEL_MAX_SITES", "0")
+    if cherries == "level":
+        monkeypatch.setenv("PLF_FLOW", "0")
+        cherries = "0"
+    else:
+        monkeypatch.setenv("PLF_LEVEL_MAX_SITES", "0")
+        monkeypatch.setenv("PLF_FLOW", "0")
     monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", cherries)
     monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
     ds = synth.dna_dataset(tips, sites, seed=11, tree_kind=tree, alpha=0.4)
@@ -584,5 +594,75 @@ def test_per_kind_kernels_small_shapes(reflib, cudalib, monkeypatch, case, cherr
     for _ in range(3):
         traverse(gpu)
     compare_all_nodes(ref, gpu)
+    ref.close()
+    gpu.close()
+
+
+# ---- the whole traversal as one launch: dependencies between work items -----------------------------------
+
+def test_flow_kernel_lists(reflib, cudalib, monkeypatch):
+    """k_clv_dna_flow orders work items by who writes what an op reads (plf_op_t.dep).  Lists that put that to the
+    test: the full traversal in its given order and reordered by level (subtrees interleaved); partial lists whose
+    children are older than the list; a list that recycles a CLV buffer (keeps the launch levels); repeated replays."""
+    ds = synth.dna_dataset(40, 777, seed=21, tree_kind="random", alpha=0.4)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, False)
+    traverse(ref, gpu)
+    l0 = cudalib.pll_cuda_kernel_launches()
+    gpu.update_partials()
+    assert cudalib.pll_cuda_kernel_launches() - l0 == 1, "a narrow plain traversal is one launch"
+    compare_all_nodes(ref, gpu)
+    ops = list(gpu.ops)
+    n = len(ops)
+    # a valid reordering: stable sort by level keeps producers before consumers but interleaves subtrees
+    level = {}
+    for op in ops:
+        level[op.parent_clv_index] = 1 + max(level.get(op.child1_clv_index, 0), level.get(op.child2_clv_index, 0))
+    order = sorted(range(n), key=lambda i: (level[ops[i].parent_clv_index], -i))
+    arr = (capi.Operation * n)(*[ops[i] for i in order])
+    for e in (ref, gpu):
+        e.update_pmatrices()
+        e.lib.pll_update_partials(e.p, arr, n)
+    compare_all_nodes(ref, gpu)
+    # partial lists: the upper half of the list reads CLVs the lower half left behind; new branch lengths first
+    bl = ds.tree.branch_lengths * 1.3
+    for e in (ref, gpu):
+        e.update_pmatrices(branch_lengths=bl[e.matrix_indices])
+        half = (capi.Operation * (n - n // 2))(*ops[n // 2:])
+        for _ in range(4):  # plain, captured, replayed twice
+            e.lib.pll_update_partials(e.p, half, n - n // 2)
+    compare_all_nodes(ref, gpu)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL after the partial lists")
+    # a list that recycles a buffer: the last op again, its result then overwritten by an op with other children
+    a, b = ops[-1], ops[0]
+    recycled = capi.Operation(a.parent_clv_index, a.parent_scaler_index, b.child1_clv_index, b.child1_matrix_index,
+                              b.child1_scaler_index, b.child2_clv_index, b.child2_matrix_index, b.child2_scaler_index)
+    lst = (capi.Operation * 3)(a, recycled, a)
+    for e in (ref, gpu):
+        for _ in range(3):
+            e.lib.pll_update_partials(e.p, lst, 3)
+    compare_all_nodes(ref, gpu)
+    ref.close()
+    gpu.close()
+
+
+@pytest.mark.parametrize("sites", [1, 31, 32, 33, 64, 65, 513, 2048])
+@pytest.mark.parametrize("cats", [1, 2, 4])
+@pytest.mark.parametrize("path_max", ["8", "2"])
+def test_flow_kernel_chunk_edges(reflib, cudalib, monkeypatch, sites, cats, path_max):
+    """work-item boundaries of k_clv_dna_flow (32, 64 or 128 sites per sweep for 4, 2, 1 rate categories), per-rate
+    scalers on a caterpillar that scales, tip CLVs instead of pattern tips for the odd widths"""
+    monkeypatch.setenv("PLF_FLOW_PATH_MAX", path_max)
+    attrs = capi.PATTERN_TIP if sites % 2 else 0
+    ds = synth.dna_dataset(400, sites, seed=sites + cats, tree_kind="caterpillar", alpha=0.3, cats=cats)
+    ref, gpu = pair(reflib, cudalib, ds, attrs, cats == 4)
+    for _ in range(3):
+        traverse(gpu)
+    traverse(ref)
+    l0 = cudalib.pll_cuda_kernel_launches()
+    gpu.update_partials()
+    assert cudalib.pll_cuda_kernel_launches() - l0 == 1
+    n_scaled = compare_all_nodes(ref, gpu)
+    assert n_scaled > 0 or sites < 3
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
     ref.close()
     gpu.close()
