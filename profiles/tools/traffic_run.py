@@ -6,6 +6,7 @@ so that DRAM bytes per traversal can be divided out (profiles/tools/traffic_summ
   python profiles/tools/traffic_run.py dna|aa|repeats|repeats_ids [--sites N] [--reps K]
 
 dna          config 2 / 5 shape (100 taxa, GTR+G4, pattern tips), default 1M sites
+narrow       the same tree on 1000 sites: the whole traversal is one launch of k_clv_dna_flow
 aa           config 3 (LG4M, 200 taxa x 100k sites), the same input as bench.py's sub-record
 repeats      config 4 (1000 taxa x 100k, SITE_REPEATS): K traversals with the identifiers kept
 repeats_ids  config 4: K traversals with identifier update
@@ -29,13 +30,13 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["dna", "aa", "repeats", "repeats_ids"])
+    ap.add_argument("config", choices=["dna", "narrow", "aa", "repeats", "repeats_ids"])
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     lib = pkg.load()
-    if args.config == "dna":
-        sites = args.sites or 1_000_000
+    if args.config in ("dna", "narrow"):
+        sites = args.sites or (1_000_000 if args.config == "dna" else 1000)
         ds = bench.make_dataset("dna", 100, sites, 1, 0)
         attrs = capi.PATTERN_TIP
     elif args.config == "aa":
