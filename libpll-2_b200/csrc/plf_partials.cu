@@ -482,11 +482,11 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
   {
     const char * v = getenv("PLF_FLOW");
     ctx->dna_flow = !(v && v[0] == '0');
-    /* 100 taxa: equal to the ring kernels near 30k sites; 1000 taxa: near 4000 sites (profiles/r2_notes.md) */
+    /* 100 taxa: equal to the ring kernels near 80k sites = 7.8M site-updates (profiles/r2_notes.md) */
     v = getenv("PLF_FLOW_MAX_SITES");
-    ctx->dna_flow_max_sites = (v && v[0]) ? atoi(v) : 32768;
+    ctx->dna_flow_max_sites = (v && v[0]) ? atoi(v) : 65536;
     v = getenv("PLF_FLOW_MAX_UPDATES");
-    ctx->dna_flow_max_updates = (v && v[0]) ? strtoull(v, nullptr, 10) : 2400000ull;
+    ctx->dna_flow_max_updates = (v && v[0]) ? strtoull(v, nullptr, 10) : 6500000ull;
     v = getenv("PLF_FLOW_PATH_MAX");
     ctx->dna_flow_path_max = (v && atoi(v) >= 1 && atoi(v) <= PLF_FLOW_PATH_MAX) ? atoi(v) : PLF_FLOW_PATH_MAX;
   }

@@ -1331,18 +1331,53 @@ __device__ __forceinline__ void flow_st_release(unsigned long long * p, unsigned
 #define FLOW_CARRY_SCALER 4u /* ... and its scaler counts with it */
 #define FLOW_TIP_TIP 8u      /* never scales, zeroes its scaler (src/core_partials_avx.c:1005-1006) */
 
-template <int LOG2R>
+/* one row of a 4x4 matrix applied to U child blocks: the row is read from shared memory once */
+template <int U>
+__device__ __forceinline__ void flow_rows_inner(const double * M, const dbl4 (&c)[U], dbl4 (&t)[U])
+{
+#pragma unroll
+  for (int row = 0; row < 4; ++row)
+  {
+    const double2 a = *reinterpret_cast<const double2 *>(M + row * 4), b = *reinterpret_cast<const double2 *>(M + row * 4 + 2);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const double p0 = a.x * c[u].x, p1 = a.y * c[u].y, p2 = b.x * c[u].z, p3 = b.y * c[u].w;
+      const double v = (p0 + p1) + (p2 + p3);
+      if (row == 0) t[u].x = v; else if (row == 1) t[u].y = v; else if (row == 2) t[u].z = v; else t[u].w = v;
+    }
+  }
+}
+/* ... and the masked pairwise row sums a tip table holds (plf_stream.cuh: build_tip_table) for U codes */
+template <int U>
+__device__ __forceinline__ void flow_rows_tip(const double * M, const unsigned int (&code)[U], dbl4 (&t)[U])
+{
+#pragma unroll
+  for (int row = 0; row < 4; ++row)
+  {
+    const double2 a = *reinterpret_cast<const double2 *>(M + row * 4), b = *reinterpret_cast<const double2 *>(M + row * 4 + 2);
+    const double m[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const double v = masked_sum4(m, code[u]);
+      if (row == 0) t[u].x = v; else if (row == 1) t[u].y = v; else if (row == 2) t[u].z = v; else t[u].w = v;
+    }
+  }
+}
+
+template <int LOG2R, int U>
 __global__ void __launch_bounds__(DNA_THREADS)
 k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __restrict__ path_start, unsigned int npaths,
                unsigned int nchunks, int per_rate, plf_flow_ctrl * ctrl, unsigned long long * ready)
 {
   constexpr int R = 1 << LOG2R;
-  constexpr unsigned int PASS = DNA_THREADS >> LOG2R; /* sites of a work item */
+  constexpr unsigned int PASS = DNA_THREADS >> LOG2R; /* sites one sweep of the CTA covers; a work item is U sweeps */
   constexpr int MSTRIDE = 18;                         /* doubles per rate of a staged matrix: rates on different banks */
   constexpr int DWORDS = sizeof(plf_flow_op) / 8;
   __shared__ __align__(16) unsigned long long sdesc_raw[PLF_FLOW_PATH_MAX * DWORDS];
   __shared__ __align__(16) double smat[PLF_FLOW_PATH_MAX][2][R * MSTRIDE];
-  __shared__ unsigned char scode[PLF_FLOW_PATH_MAX][2][PASS];
+  __shared__ unsigned char scode[PLF_FLOW_PATH_MAX][2][U * PASS];
   __shared__ unsigned int s_item;
   __shared__ unsigned long long s_epoch;
   const plf_flow_op * sdesc = reinterpret_cast<const plf_flow_op *>(sdesc_raw);
@@ -1370,53 +1405,70 @@ k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __res
     }
     __syncthreads();
     const unsigned int nsites = sdesc[0].nsites;
-    const unsigned int first = chunk * PASS;
+    const unsigned int first = chunk * (U * PASS);
     for (unsigned int i = threadIdx.x; i < n * 2 * R * 16; i += DNA_THREADS)
     {
       const unsigned int k = i / (2 * R * 16), rem = i - k * (2 * R * 16), side = rem / (R * 16), e = rem - side * (R * 16);
       smat[k][side][(e >> 4) * MSTRIDE + (e & 15)] = sdesc[k].matrix[side][e];
     }
-    for (unsigned int i = threadIdx.x; i < n * 2 * PASS; i += DNA_THREADS)
+    for (unsigned int i = threadIdx.x; i < n * 2 * U * PASS; i += DNA_THREADS)
     {
-      const unsigned int k = i / (2 * PASS), side = (i / PASS) & 1u, ls = i % PASS;
+      const unsigned int k = i / (2 * U * PASS), rem = i - k * (2 * U * PASS), side = rem / (U * PASS), ls = rem - side * (U * PASS);
       const unsigned char * tp = sdesc[k].tip[side];
       if (tp) scode[k][side][ls] = tp[min(first + ls, nsites - 1)];
     }
     __syncthreads();
     if (first < nsites)
     {
-      const unsigned int site = first + lane_site;
-      const bool active = site < nsites;
-      const unsigned int nn = active ? site : nsites - 1; /* inactive lanes recompute the last site, store nothing */
+      unsigned int site[U], nn[U];
+      bool active[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        site[u] = first + u * PASS + lane_site;
+        active[u] = site[u] < nsites;
+        nn[u] = active[u] ? site[u] : nsites - 1; /* inactive lanes recompute the last site, store nothing */
+      }
       const bool keeps_count = per_rate || rate == 0;
-      dbl4 carry_v = dbl4{0, 0, 0, 0};
-      unsigned int carry_sc = 0;
+      dbl4 carry_v[U];
+      unsigned int carry_sc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        carry_v[u] = dbl4{0, 0, 0, 0};
+        carry_sc[u] = 0;
+      }
 #pragma unroll 1
       for (unsigned int k = 0; k < n; ++k)
       {
         const plf_flow_op & d = sdesc[k];
         const unsigned int flags = d.flags;
-        dbl4 term[2];
-        unsigned int sc = 0;
+        dbl4 term[2][U];
+        unsigned int sc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) sc[u] = 0;
 #pragma unroll
         for (int side = 0; side < 2; ++side)
         {
           const double * M = smat[k][side] + rate * MSTRIDE;
           if (d.tip[side])
           {
-            const unsigned int code = scode[k][side][lane_site];
-            term[side].x = masked_sum4(M + 0, code);
-            term[side].y = masked_sum4(M + 4, code);
-            term[side].z = masked_sum4(M + 8, code);
-            term[side].w = masked_sum4(M + 12, code);
+            unsigned int code[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) code[u] = scode[k][side][u * PASS + lane_site];
+            flow_rows_tip<U>(M, code, term[side]);
           }
           else
           {
-            dbl4 c;
+            dbl4 c[U];
             if ((flags & FLOW_CARRY_MASK) == (unsigned int)(side + 1))
             {
-              c = carry_v;
-              if (flags & FLOW_CARRY_SCALER) sc += carry_sc;
+#pragma unroll
+              for (int u = 0; u < U; ++u)
+              {
+                c[u] = carry_v[u];
+                if (flags & FLOW_CARRY_SCALER) sc[u] += carry_sc[u];
+              }
             }
             else
             {
@@ -1425,38 +1477,44 @@ k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __res
                 const unsigned long long * f = ready + (size_t)d.dep[side] * nchunks + chunk;
                 while (flow_ld_acquire(f) != epoch1) {}
               }
-              c = ld256_cg(d.clv[side] + ((size_t)nn * R + rate) * 4);
+#pragma unroll
+              for (int u = 0; u < U; ++u) c[u] = ld256_cg(d.clv[side] + ((size_t)nn[u] * R + rate) * 4);
             }
             if (d.scaler[side] && d.parent_scaler && keeps_count)
-              sc += __ldcg(d.scaler[side] + (per_rate ? (size_t)nn * R + rate : nn));
-            term[side].x = dot4_pairwise(M + 0, c);
-            term[side].y = dot4_pairwise(M + 4, c);
-            term[side].z = dot4_pairwise(M + 8, c);
-            term[side].w = dot4_pairwise(M + 12, c);
-          }
-        }
-        dbl4 v = dbl4{term[0].x * term[1].x, term[0].y * term[1].y, term[0].z * term[1].z, term[0].w * term[1].w};
-        if (d.parent_scaler)
-        {
-          if (flags & FLOW_TIP_TIP)
-            sc = 0;
-          else
-          {
-            const int below = (v.x < PLF_SCALE_THRESHOLD) && (v.y < PLF_SCALE_THRESHOLD) && (v.z < PLF_SCALE_THRESHOLD) &&
-                              (v.w < PLF_SCALE_THRESHOLD);
-            const int fire = per_rate ? below : group_and(below, R); /* all lanes of the warp take part */
-            if (fire)
             {
-              v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
-              v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
-              sc += 1u;
+#pragma unroll
+              for (int u = 0; u < U; ++u) sc[u] += __ldcg(d.scaler[side] + (per_rate ? (size_t)nn[u] * R + rate : nn[u]));
             }
+            flow_rows_inner<U>(M, c, term[side]);
           }
-          if (active && keeps_count) d.parent_scaler[per_rate ? (size_t)site * R + rate : site] = sc;
         }
-        if (active) st256(d.parent_clv + ((size_t)site * R + rate) * 4, v);
-        carry_v = v;
-        carry_sc = sc;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+          dbl4 v = dbl4{term[0][u].x * term[1][u].x, term[0][u].y * term[1][u].y, term[0][u].z * term[1][u].z,
+                        term[0][u].w * term[1][u].w};
+          if (d.parent_scaler)
+          {
+            if (flags & FLOW_TIP_TIP)
+              sc[u] = 0;
+            else
+            {
+              const int below = (v.x < PLF_SCALE_THRESHOLD) && (v.y < PLF_SCALE_THRESHOLD) && (v.z < PLF_SCALE_THRESHOLD) &&
+                                (v.w < PLF_SCALE_THRESHOLD);
+              const int fire = per_rate ? below : group_and(below, R); /* all lanes of the warp take part */
+              if (fire)
+              {
+                v.x *= PLF_SCALE_FACTOR; v.y *= PLF_SCALE_FACTOR;
+                v.z *= PLF_SCALE_FACTOR; v.w *= PLF_SCALE_FACTOR;
+                sc[u] += 1u;
+              }
+            }
+            if (active[u] && keeps_count) d.parent_scaler[per_rate ? (size_t)site[u] * R + rate : site[u]] = sc[u];
+          }
+          if (active[u]) st256(d.parent_clv + ((size_t)site[u] * R + rate) * 4, v);
+          carry_v[u] = v;
+          carry_sc[u] = sc[u];
+        }
       }
     }
     __syncthreads(); /* every store of the item has been issued */
@@ -1481,11 +1539,21 @@ k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __res
   }
 }
 
+/* blocks of (site, rate) a thread carries through a path: 1 while a traversal is pure latency, 2 when the matrix
+ * reads from shared memory start to count (each row is read once for both) */
+unsigned int plf_dna_flow_unroll(unsigned int max_sites)
+{
+  const char * v = getenv("PLF_FLOW_UNROLL");
+  if (v && (v[0] == '1' || v[0] == '2' || v[0] == '4')) return (unsigned int)(v[0] - '0');
+  v = getenv("PLF_FLOW_UNROLL_SITES");
+  return max_sites >= ((v && v[0]) ? strtoul(v, nullptr, 10) : 2048ul) ? 2u : 1u;
+}
+
 unsigned int plf_dna_flow_chunks(unsigned int rate_cats, unsigned int max_sites)
 {
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
-  const unsigned int pass = DNA_THREADS >> log2r;
+  const unsigned int pass = (DNA_THREADS >> log2r) * plf_dna_flow_unroll(max_sites);
   return (max_sites + pass - 1) / pass;
 }
 
@@ -1620,25 +1688,26 @@ int plf_launch_dna_flow(plf_ctx * ctx, const plf_flow_op * d_fops, const unsigne
   int log2r = 0;
   while ((1u << log2r) < rate_cats) ++log2r;
   const unsigned int nchunks = plf_dna_flow_chunks(rate_cats, max_sites);
-  if (!ctx->dna_flow_occupancy[log2r])
+  typedef void (*flow_kernel_t)(const plf_flow_op *, const unsigned int *, unsigned int, unsigned int, int, plf_flow_ctrl *,
+                                unsigned long long *);
+  static const flow_kernel_t kernels[3][3] = {{k_clv_dna_flow<0, 1>, k_clv_dna_flow<1, 1>, k_clv_dna_flow<2, 1>},
+                                              {k_clv_dna_flow<0, 2>, k_clv_dna_flow<1, 2>, k_clv_dna_flow<2, 2>},
+                                              {k_clv_dna_flow<0, 4>, k_clv_dna_flow<1, 4>, k_clv_dna_flow<2, 4>}};
+  const unsigned int unroll = plf_dna_flow_unroll(max_sites);
+  const int two = unroll == 4 ? 2 : (unroll == 2 ? 1 : 0);
+  const flow_kernel_t fn = kernels[two][log2r];
+  if (!ctx->dna_flow_occupancy[two][log2r])
   {
     int per_sm = 0;
-    const void * fn = log2r == 0 ? (const void *)k_clv_dna_flow<0>
-                                 : (log2r == 1 ? (const void *)k_clv_dna_flow<1> : (const void *)k_clv_dna_flow<2>);
     PLF_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, DNA_THREADS, 0));
-    ctx->dna_flow_occupancy[log2r] = per_sm > 0 ? per_sm : 1;
+    ctx->dna_flow_occupancy[two][log2r] = per_sm > 0 ? per_sm : 1;
   }
   const unsigned long long items = (unsigned long long)npaths * nchunks;
-  unsigned long long grid = (unsigned long long)ctx->sm_count * ctx->dna_flow_occupancy[log2r];
+  unsigned long long grid = (unsigned long long)ctx->sm_count * ctx->dna_flow_occupancy[two][log2r];
   if (grid > items) grid = items;
   plf_flow_ctrl * ctrl = reinterpret_cast<plf_flow_ctrl *>(flow);
   unsigned long long * ready = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(flow) + 64);
-  switch (log2r)
-  {
-    case 0: k_clv_dna_flow<0><<<(unsigned int)grid, DNA_THREADS, 0, ctx->stream>>>(d_fops, d_path_start, npaths, nchunks, per_rate, ctrl, ready); break;
-    case 1: k_clv_dna_flow<1><<<(unsigned int)grid, DNA_THREADS, 0, ctx->stream>>>(d_fops, d_path_start, npaths, nchunks, per_rate, ctrl, ready); break;
-    default: k_clv_dna_flow<2><<<(unsigned int)grid, DNA_THREADS, 0, ctx->stream>>>(d_fops, d_path_start, npaths, nchunks, per_rate, ctrl, ready); break;
-  }
+  fn<<<(unsigned int)grid, DNA_THREADS, 0, ctx->stream>>>(d_fops, d_path_start, npaths, nchunks, per_rate, ctrl, ready);
   plf_count_launch();
   PLF_CHECK(ctx, cudaGetLastError());
   return 1;

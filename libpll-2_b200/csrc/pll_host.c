@@ -757,16 +757,16 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : 2049u;
     if (!(v && v[0]) && states == 4 && rate_cats <= 4 && (rate_cats & (rate_cats - 1)) == 0)
     {
-      /* 4 states: a plain list of up to PLF_FLOW_MAX_UPDATES site-updates (default 2.4M: 100 taxa x 24k sites,
-       * 1000 taxa x 2.4k sites) over at most PLF_FLOW_MAX_SITES sites (default 32768) runs as ONE launch whose
+      /* 4 states: a plain list of up to PLF_FLOW_MAX_UPDATES site-updates (default 6.5M: 100 taxa x 66k sites,
+       * 1000 taxa x 6.5k sites) over at most PLF_FLOW_MAX_SITES sites (default 65536) runs as ONE launch whose
        * paths keep parents in registers (k_clv_dna_flow), every parent written.  100 taxa: 1000 sites 27 us
-       * against 62 us with one launch per level, 10k sites 72 us against 127 us with virtual cherries; equal
-       * near 30k sites (2.9M site-updates); 1000 taxa x 4000 sites: equal (profiles/r2_notes.md) */
+       * against 62 us with one launch per level, 10k sites 63 us against 127 us with virtual cherries, 60k sites
+       * 251 against 275 us; equal near 80k sites (7.8M site-updates) (profiles/r2_notes.md) */
       const char * f = getenv("PLF_FLOW"), * m = getenv("PLF_FLOW_MAX_SITES"), * u = getenv("PLF_FLOW_MAX_UPDATES");
       if (!(f && f[0] == '0'))
       {
-        const unsigned long long max_sites = (m && m[0]) ? strtoull(m, NULL, 10) : 32768ull;
-        const unsigned long long max_updates = (u && u[0]) ? strtoull(u, NULL, 10) : 2400000ull;
+        const unsigned long long max_sites = (m && m[0]) ? strtoull(m, NULL, 10) : 65536ull;
+        const unsigned long long max_updates = (u && u[0]) ? strtoull(u, NULL, 10) : 6500000ull;
         const unsigned long long ops = tips > 2 ? tips - 2 : 1;
         unsigned long long lim = max_updates / ops;
         if (lim > max_sites) lim = max_sites;

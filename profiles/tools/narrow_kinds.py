@@ -39,6 +39,14 @@ def main():
     for sites in (250, 1000):
         ds = synth.aa_dataset(200, sites, seed=2)
         out[f"aa_200x{sites}_tip_clvs"] = run(lib, ds, 0)
+    for sites in (4000, 8000):
+        ds = synth.dna_dataset(1000, sites, seed=3, alpha=0.3, brlen=(0.002, 0.05), simulate_down_tree=True)
+        for name, env in (("ring", {"PLF_FLOW": "0", "PLF_VIRTUAL_CHERRY_MIN_SITES": "0"}),
+                          ("flow", {"PLF_FLOW": "1", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_MAX_UPDATES": "1000000000"})):
+            os.environ.update(env)
+            out[f"dna_1000x{sites}_pattern_tip_{name}"] = run(lib, ds, capi.PATTERN_TIP)
+            for k in env:
+                os.environ.pop(k)
     for sites in (1000, 4000):
         ds = bench.make_dataset("dna", 100, sites, 1, 0)
         out[f"dna_100x{sites}_tip_clvs"] = run(lib, ds, 0)

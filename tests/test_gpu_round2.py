@@ -73,6 +73,9 @@ CHERRY_VARIANTS = {
     "flow-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0"},
     "flow-written-3": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "3"},
     "flow-written-1": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "1"},
+    # two and four (site, rate) blocks per thread
+    "flow-written-u2": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_UNROLL": "2"},
+    "flow-written-u4": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_UNROLL": "4", "PLF_FLOW_PATH_MAX": "5"},
 }
 
 
@@ -153,7 +156,7 @@ def test_virtual_cherry_survives_pmatrix_and_tip_changes(reflib, cudalib, monkey
 
 
 def test_virtual_cherries_off_switch_and_threshold(cudalib, monkeypatch):
-    narrow, wide = synth.dna_dataset(10, 200, seed=3), synth.dna_dataset(10, 40000, seed=3, simulate_down_tree=False)
+    narrow, wide = synth.dna_dataset(10, 200, seed=3), synth.dna_dataset(10, 70000, seed=3, simulate_down_tree=False)
     ds = narrow
     gpu = harness.Engine(cudalib, narrow, capi.ARCH_CUDA | capi.PATTERN_TIP)
     assert cudalib.pll_cuda_virtual_cherries(gpu.p) == 0  # default: launch-bound widths write every parent
@@ -647,11 +650,14 @@ def test_flow_kernel_lists(reflib, cudalib, monkeypatch):
 
 @pytest.mark.parametrize("sites", [1, 31, 32, 33, 64, 65, 513, 2048])
 @pytest.mark.parametrize("cats", [1, 2, 4])
-@pytest.mark.parametrize("path_max", ["8", "2"])
+@pytest.mark.parametrize("path_max", ["8", "2", "u2", "u4"])
 def test_flow_kernel_chunk_edges(reflib, cudalib, monkeypatch, sites, cats, path_max):
     """work-item boundaries of k_clv_dna_flow (32, 64 or 128 sites per sweep for 4, 2, 1 rate categories), per-rate
     scalers on a caterpillar that scales, tip CLVs instead of pattern tips for the odd widths"""
-    monkeypatch.setenv("PLF_FLOW_PATH_MAX", path_max)
+    if path_max.startswith("u"):
+        monkeypatch.setenv("PLF_FLOW_UNROLL", path_max[1:])
+    else:
+        monkeypatch.setenv("PLF_FLOW_PATH_MAX", path_max)
     attrs = capi.PATTERN_TIP if sites % 2 else 0
     ds = synth.dna_dataset(400, sites, seed=sites + cats, tree_kind="caterpillar", alpha=0.3, cats=cats)
     ref, gpu = pair(reflib, cudalib, ds, attrs, cats == 4)
