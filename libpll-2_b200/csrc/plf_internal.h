@@ -71,6 +71,7 @@ struct plf_ctx
   plf_ws ws_once;     /* op descriptors of internal single ops (materialised cherries) */
   plf_ws ws_flow;     /* k_clv_dna_flow: queue control block + one flag per work item */
   void * ws_flow_zeroed; /* the allocation whose flags have been zeroed */
+  size_t ws_flow_zeroed_bytes;
   plf_ws ws_small;    /* matrix indices, branch lengths, expm1 values          */
   plf_ws ws_partial;  /* per-block partial sums of the reductions              */
   plf_ws ws_edge;     /* synthetic op + matrices of the DNA/AA sumtable launches */

@@ -519,11 +519,13 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
       {
         unsigned char * flow = (unsigned char *)plf_ws_reserve(ctx, &ctx->ws_flow, bytes);
         cudaError_t e = flow ? cudaSuccess : cudaErrorMemoryAllocation;
-        if (flow && ctx->ws_flow_zeroed != flow)
+        if (flow && (ctx->ws_flow_zeroed != flow || ctx->ws_flow_zeroed_bytes != ctx->ws_flow.bytes))
         {
-          /* a new allocation: epoch 0, no flag set (never inside a capture: a captured list ran once before) */
+          /* a new allocation (it may sit at the old address): epoch 0, no flag set.  Never inside a capture: a
+           * captured list ran once before with the same sizes */
           e = cudaMemsetAsync(flow, 0, ctx->ws_flow.bytes, ctx->stream);
           ctx->ws_flow_zeroed = flow;
+          ctx->ws_flow_zeroed_bytes = ctx->ws_flow.bytes;
         }
         if (e == cudaSuccess && upload)
           e = cudaMemcpyAsync(flow + plan_at, h_plan, bytes - plan_at, cudaMemcpyHostToDevice, ctx->stream);
