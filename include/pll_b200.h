@@ -547,6 +547,14 @@ PLL_EXPORT int pll_cuda_check_guards(const pll_partition_t * partition);
 PLL_EXPORT int pll_cuda_debug_overrun(pll_partition_t * partition, unsigned int clv_index);
 /* inspection: launches of one traversal level for ops of the given kinds (sorted by kind); a launch serves at
  * most 65535 ops (gridDim.y).  Host arithmetic only. */
+/* NEW (inspection, no device needed).  How a narrow 4-state traversal would run as ONE launch (k_clv_dna_flow,
+ * DESIGN.md section 4): the list is cut into paths whose parents stay in registers.  path_of_op[i] = position
+ * in the queue of the path ops[i] belongs to; carried_child_of_op[i] = 1 / 2 when child1 / child2 of ops[i]
+ * arrives in registers.  Returns the number of paths, 0 when the list keeps one launch per level (a buffer is
+ * recycled within the list).  `tips`: CLV indices below it are pattern tips. */
+PLL_EXPORT unsigned int pll_cuda_schedule_paths(const pll_operation_t * operations, unsigned int count,
+                                                unsigned int tips, unsigned int path_max,
+                                                unsigned int * path_of_op, int * carried_child_of_op);
 PLL_EXPORT unsigned int pll_cuda_count_launch_runs(const unsigned int * kinds, unsigned int count,
                                                    unsigned int * largest_run);
 /* The one exchange of a site-sharded evaluation (one process per GPU of one node, each owning a contiguous

@@ -255,6 +255,7 @@ _CUDA_PROTOS = {
     "pll_cuda_download_sumtable": (C.c_int, [PartitionP, c_double_p, c_double_p]),
     "pll_cuda_scaler_size": (C.c_uint, [PartitionP, C.c_uint]),
     "pll_cuda_count_launch_runs": (C.c_uint, [c_uint_p, C.c_uint, c_uint_p]),
+    "pll_cuda_schedule_paths": (C.c_uint, [C.POINTER(Operation), C.c_uint, C.c_uint, C.c_uint, c_uint_p, C.POINTER(C.c_int)]),
     "pll_cuda_invalidate_repeat_identifiers": (C.c_int, [PartitionP]),
     "pll_cuda_check_guards": (C.c_int, [PartitionP]),
     "pll_cuda_debug_overrun": (C.c_int, [PartitionP, C.c_uint]),

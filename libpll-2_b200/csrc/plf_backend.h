@@ -177,6 +177,26 @@ int plf_update_partials_once(plf_ctx_t * ctx, const plf_shape_t * sh,
                              const unsigned long long * d_tipmap,
                              unsigned int maxstates);
 /* end of the launch run that starts at op i of a level ending at b (see plf_partials.cu) */
+/* k_clv_dna_flow (plf_partials_dna.cu): one op of a path, as the kernel stages it in shared memory */
+#define PLF_FLOW_PATH_MAX 8
+struct plf_flow_op
+{
+  double * parent_clv;
+  unsigned int * parent_scaler;
+  const double * clv[2];          /* inner child, NULL when that side is a pattern tip */
+  const unsigned char * tip[2];
+  const double * matrix[2];
+  const unsigned int * scaler[2]; /* child scaler to read from memory (NULL: none, or it travels in registers) */
+  int dep[2];                     /* path whose flag says clv[side] / scaler[side] has been written, or PLF_DEP_NONE */
+  unsigned int nsites;
+  unsigned int flags;
+};
+/* cuts a level-sorted plain op list (dep[] filled) into paths: out_ops (nops entries) path by path, bottom to top,
+ * out_start (nops + 1 entries) the first op of each path.  Returns the number of paths, 0 when the list cannot
+ * run as one launch.  Host arithmetic only. */
+unsigned int plf_dna_flow_plan(const plf_op_t * h_ops, unsigned int nops, unsigned int path_max,
+                               struct plf_flow_op * out_ops, unsigned int * out_start);
+
 unsigned int plf_run_end(const plf_op_t * h_ops, unsigned int i, unsigned int b,
                          unsigned int * max_sites, int * contiguous);
 /* 1 when the streaming kernels that consume virtual cherries serve this shape and this many tip codes */

@@ -110,23 +110,7 @@ int plf_launch_dna_group(plf_ctx * ctx, const struct plf_op * d_ops, unsigned in
 unsigned int plf_dna_balanced_tiles(unsigned int nsites, unsigned int rate_cats);
 int plf_launch_dna_level(plf_ctx * ctx, const struct plf_op * d_ops, unsigned int nops, unsigned int rate_cats, int per_rate,
                          unsigned int max_sites);
-/* k_clv_dna_flow (plf_partials_dna.cu): one op of a path, as the kernel stages it in shared memory */
-#define PLF_FLOW_PATH_MAX 8
-struct plf_flow_op
-{
-  double * parent_clv;
-  unsigned int * parent_scaler;
-  const double * clv[2];          /* inner child, NULL when that side is a pattern tip */
-  const unsigned char * tip[2];
-  const double * matrix[2];
-  const unsigned int * scaler[2]; /* child scaler to read from memory (NULL: none, or it travels in registers) */
-  int dep[2];                     /* path whose flag says clv[side] / scaler[side] has been written, or PLF_DEP_NONE */
-  unsigned int nsites;
-  unsigned int flags;
-};
 unsigned int plf_dna_flow_chunks(unsigned int rate_cats, unsigned int max_sites);
-unsigned int plf_dna_flow_plan(const struct plf_op * h_ops, unsigned int nops, unsigned int path_max,
-                               struct plf_flow_op * out_ops, unsigned int * out_start);
 int plf_launch_dna_flow(plf_ctx * ctx, const struct plf_flow_op * d_fops, const unsigned int * d_path_start,
                         unsigned int npaths, unsigned int rate_cats, int per_rate, unsigned int max_sites, void * flow);
 int plf_aa_virtual_cherries_supported(plf_ctx * ctx, const struct plf_shape * sh, unsigned int maxstates);

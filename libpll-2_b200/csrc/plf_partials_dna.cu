@@ -1327,6 +1327,23 @@ __device__ __forceinline__ void flow_st_release(unsigned long long * p, unsigned
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+/* waits for an item's flag.  By construction the wait ends (see above); should it not - a corrupted workspace -
+ * the launch fails loudly after FLOW_TIMEOUT_NS instead of hanging the device */
+#define FLOW_TIMEOUT_NS 10000000000ull
+__device__ __forceinline__ void flow_wait(const unsigned long long * f, unsigned long long epoch1)
+{
+  unsigned int polls = 0;
+  unsigned long long t0 = 0;
+  while (flow_ld_acquire(f) != epoch1)
+    if ((++polls & 0x3FFu) == 0)
+    {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (!t0) t0 = now;
+      else if (now - t0 > FLOW_TIMEOUT_NS) __trap();
+    }
+}
+
 #define FLOW_CARRY_MASK 3u   /* 1: the left child is the previous op's parent (in registers), 2: the right one */
 #define FLOW_CARRY_SCALER 4u /* ... and its scaler counts with it */
 #define FLOW_TIP_TIP 8u      /* never scales, zeroes its scaler (src/core_partials_avx.c:1005-1006) */
@@ -1475,7 +1492,7 @@ k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __res
               if (d.dep[side] >= 0)
               {
                 const unsigned long long * f = ready + (size_t)d.dep[side] * nchunks + chunk;
-                while (flow_ld_acquire(f) != epoch1) {}
+                flow_wait(f, epoch1);
               }
 #pragma unroll
               for (int u = 0; u < U; ++u) c[u] = ld256_cg(d.clv[side] + ((size_t)nn[u] * R + rate) * 4);
@@ -1560,8 +1577,8 @@ unsigned int plf_dna_flow_chunks(unsigned int rate_cats, unsigned int max_sites)
 /* Cuts a level-sorted, plain op list (kinds II / TI / TT, contiguous CLVs, dep[] filled by the host layer) into
  * paths.  out_ops (nops entries) receives the ops path by path, bottom to top; out_start (nops + 1 entries) the
  * first op of each path.  Returns the number of paths, 0 when the list cannot run as one launch. */
-unsigned int plf_dna_flow_plan(const plf_op_t * h_ops, unsigned int nops, unsigned int path_max, plf_flow_op * out_ops,
-                               unsigned int * out_start)
+extern "C" unsigned int plf_dna_flow_plan(const plf_op_t * h_ops, unsigned int nops, unsigned int path_max,
+                                          plf_flow_op * out_ops, unsigned int * out_start)
 {
   if (path_max < 1) path_max = 1;
   if (path_max > PLF_FLOW_PATH_MAX) path_max = PLF_FLOW_PATH_MAX;

@@ -22,6 +22,7 @@
  */
 #define _GNU_SOURCE
 #include <math.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -2653,10 +2654,9 @@ static int attach_pair_lists(cuda_partition_t * cp, const pll_operation_t * ops,
  * whose work items wait for their producers' items instead of for a launch boundary.  cp->h_level[i] holds
  * the position of ops[i] in cp->h_ops_sorted.  A list that recycles buffers (an op overwrites something an
  * earlier op read or wrote) is marked PLF_DEP_ORDERED and keeps the launch levels. */
-static void attach_dependencies(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+static void dependencies_of_list(const pll_operation_t * ops, unsigned int count, size_t nclv, size_t nsc,
+                                 const unsigned int * position, plf_op_t * sorted)
 {
-  const pll_partition_t * p = &cp->pub;
-  const size_t nclv = p->nodes, nsc = p->scale_buffers;
   int * writer = (int *)malloc((nclv + nsc + 1) * sizeof(int));
   unsigned char * was_read = (unsigned char *)calloc(nclv + nsc + 1, 1);
   unsigned int i;
@@ -2668,7 +2668,7 @@ static void attach_dependencies(cuda_partition_t * cp, const pll_operation_t * o
     for (i = 0; i < count && !ordered; ++i)
     {
       const pll_operation_t * o = ops + i;
-      plf_op_t * s = cp->h_ops_sorted + cp->h_level[i];
+      plf_op_t * s = sorted + position[i];
       const size_t par = o->parent_clv_index, c1 = o->child1_clv_index, c2 = o->child2_clv_index;
       const int psc = o->parent_scaler_index, sc1 = o->child1_scaler_index, sc2 = o->child2_scaler_index;
       if (writer[par] != PLF_DEP_NONE || was_read[par] || par == c1 || par == c2 ||
@@ -2684,19 +2684,125 @@ static void attach_dependencies(cuda_partition_t * cp, const pll_operation_t * o
       was_read[c1] = was_read[c2] = 1;
       if (sc1 >= 0) was_read[nclv + sc1] = 1;
       if (sc2 >= 0) was_read[nclv + sc2] = 1;
-      writer[par] = (int)cp->h_level[i];
-      if (psc >= 0) writer[nclv + psc] = (int)cp->h_level[i];
+      writer[par] = (int)position[i];
+      if (psc >= 0) writer[nclv + psc] = (int)position[i];
     }
   }
   if (ordered)
     for (i = 0; i < count; ++i)
     {
-      plf_op_t * s = cp->h_ops_sorted + i;
+      plf_op_t * s = sorted + i;
       s->dep[0] = PLF_DEP_ORDERED;
       s->dep[1] = s->dep[2] = s->dep[3] = PLF_DEP_NONE;
     }
   free(writer);
   free(was_read);
+}
+
+static void attach_dependencies(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)
+{
+  dependencies_of_list(ops, count, cp->pub.nodes, cp->pub.scale_buffers, cp->h_level, cp->h_ops_sorted);
+}
+
+/* NEW (additive, inspection).  How k_clv_dna_flow would run this list on a partition with `tips` pattern tips:
+ * path_of_op[i] = position in the queue of the path ops[i] belongs to, carried_child_of_op[i] = 1 / 2 when the
+ * CLV of child1 / child2 reaches ops[i] in registers (0: both children come from memory or are tips).  Returns the
+ * number of paths; 0 when the list keeps the launch levels (it recycles a buffer, or reads a scaler another op than
+ * the CLV's writer wrote).  Pure host arithmetic: callable without a device. */
+PLL_EXPORT unsigned int pll_cuda_schedule_paths(const pll_operation_t * operations, unsigned int count, unsigned int tips,
+                                                unsigned int path_max, unsigned int * path_of_op,
+                                                int * carried_child_of_op)
+{
+#define FAKE_CLV(i) ((double *)(uintptr_t)(((size_t)(i) + 1) << 12))
+  unsigned int i, nlevels, npaths = 0, max_clv = 0;
+  int max_sc = -1, nl;
+  unsigned int * level, * start, * position, * pstart, * op_of_clv;
+  plf_op_t * sorted;
+  struct plf_flow_op * plan;
+  if (!count) return 0;
+  for (i = 0; i < count; ++i)
+  {
+    const pll_operation_t * o = operations + i;
+    if (o->parent_clv_index > max_clv) max_clv = o->parent_clv_index;
+    if (o->child1_clv_index > max_clv) max_clv = o->child1_clv_index;
+    if (o->child2_clv_index > max_clv) max_clv = o->child2_clv_index;
+    if (o->parent_scaler_index > max_sc) max_sc = o->parent_scaler_index;
+    if (o->child1_scaler_index > max_sc) max_sc = o->child1_scaler_index;
+    if (o->child2_scaler_index > max_sc) max_sc = o->child2_scaler_index;
+  }
+  level = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  position = (unsigned int *)malloc((size_t)count * sizeof(unsigned int));
+  pstart = (unsigned int *)malloc(((size_t)count + 1) * sizeof(unsigned int));
+  op_of_clv = (unsigned int *)malloc(((size_t)max_clv + 1) * sizeof(unsigned int));
+  sorted = (plf_op_t *)calloc(count, sizeof(plf_op_t));
+  plan = (struct plf_flow_op *)malloc((size_t)count * sizeof(struct plf_flow_op));
+  start = NULL;
+  nl = (level && position && pstart && op_of_clv && sorted && plan) ? pll_cuda_schedule_levels(operations, count, level) : -1;
+  if (nl > 0) start = (unsigned int *)calloc((size_t)nl * (PLF_OP_KINDS + 1) + 2, sizeof(unsigned int));
+  if (start)
+  {
+    nlevels = (unsigned int)nl * (PLF_OP_KINDS + 1);
+    for (i = 0; i < count; ++i)
+    {
+      const pll_operation_t * o = operations + i;
+      const int t1 = o->child1_clv_index < tips, t2 = o->child2_clv_index < tips;
+      level[i] = level[i] * (PLF_OP_KINDS + 1) + ((t1 && t2) ? PLF_OP_TT : ((t1 || t2) ? PLF_OP_TI : PLF_OP_II));
+      start[level[i] + 1]++;
+    }
+    for (i = 0; i < nlevels; ++i) start[i + 1] += start[i];
+    for (i = 0; i < count; ++i)
+    {
+      /* as resolve_op: a pattern tip goes to the left */
+      const pll_operation_t * o = operations + i;
+      const int t1 = o->child1_clv_index < tips, t2 = o->child2_clv_index < tips;
+      const unsigned int first = (t2 && !t1) ? o->child2_clv_index : o->child1_clv_index;
+      const unsigned int second = (t2 && !t1) ? o->child1_clv_index : o->child2_clv_index;
+      plf_op_t * s;
+      position[i] = start[level[i]]++;
+      s = sorted + position[i];
+      s->kind = level[i] % (PLF_OP_KINDS + 1);
+      s->nsites = 1;
+      s->parent_clv = FAKE_CLV(o->parent_clv_index);
+      if (s->kind == PLF_OP_II) s->left_clv = FAKE_CLV(first); else s->left_tip = (const unsigned char *)FAKE_CLV(first);
+      if (s->kind == PLF_OP_TT) s->right_tip = (const unsigned char *)FAKE_CLV(second); else s->right_clv = FAKE_CLV(second);
+      s->dep[0] = s->dep[1] = s->dep[2] = s->dep[3] = PLF_DEP_NONE;
+    }
+    dependencies_of_list(operations, count, (size_t)max_clv + 1, (size_t)(max_sc + 1), position, sorted);
+    if (sorted[0].dep[0] != PLF_DEP_ORDERED) npaths = plf_dna_flow_plan(sorted, count, path_max, plan, pstart);
+    if (npaths)
+    {
+      unsigned int path = 0, k;
+      for (i = 0; i < count; ++i) op_of_clv[operations[i].parent_clv_index] = i;
+      for (k = 0; k < count; ++k)
+      {
+        const unsigned int clv = (unsigned int)(((uintptr_t)plan[k].parent_clv >> 12) - 1);
+        const unsigned int op = op_of_clv[clv];
+        const unsigned int side = plan[k].flags & 3u;
+        while (k >= pstart[path + 1]) ++path;
+        if (path_of_op) path_of_op[op] = path;
+        if (carried_child_of_op)
+        {
+          carried_child_of_op[op] = 0;
+          if (side)
+          {
+            /* the carried side holds no pointer check here: it is the child written by the previous op of the path */
+            const unsigned int prev = op_of_clv[(unsigned int)(((uintptr_t)plan[k - 1].parent_clv >> 12) - 1)];
+            carried_child_of_op[op] =
+                operations[op].child1_clv_index == operations[prev].parent_clv_index ? 1 : 2;
+          }
+        }
+      }
+    }
+  }
+  free(level);
+  free(start);
+  free(position);
+  free(pstart);
+  free(op_of_clv);
+  free(sorted);
+  free(plan);
+  return npaths;
+#undef FAKE_CLV
 }
 
 static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, unsigned int count)

@@ -229,3 +229,86 @@ def test_peer_group_fails_cleanly_without_a_device(lib):
     assert lib.pll_cuda_peer_allreduce(None, None, None, 3) == 0
     assert lib.pll_cuda_peer_group_check(None) == 0
     lib.pll_cuda_peer_group_destroy(None)
+
+
+# ---- k_clv_dna_flow: the plan of a one-launch traversal (host arithmetic) ------------------------------------
+
+def _paths(lib, rows, tips, path_max=8):
+    n = len(rows)
+    ops = (capi.Operation * n)(*[capi.Operation(*r) for r in rows])
+    path = (C.c_uint * n)()
+    carried = (C.c_int * n)()
+    npaths = lib.pll_cuda_schedule_paths(ops, n, tips, path_max, path, carried)
+    return npaths, list(path), list(carried)
+
+
+def _check_plan(rows, npaths, path, carried, path_max):
+    """every op in exactly one path; a path is a chain (each op carries the previous op's parent, nobody else
+    reads it); whatever else an op reads was written by an EARLIER path; no path is longer than path_max"""
+    writer = {r[0]: i for i, r in enumerate(rows)}
+    readers = {}
+    for i, r in enumerate(rows):
+        for c in (r[2], r[5]):
+            readers.setdefault(c, []).append(i)
+    members = {}
+    for i, p in enumerate(path):
+        assert 0 <= p < npaths
+        members.setdefault(p, []).append(i)
+    assert sorted(members) == list(range(npaths))
+    for p, ops in members.items():
+        assert len(ops) <= path_max
+        carrying = [i for i in ops if carried[i]]
+        assert len(carrying) == len(ops) - 1, "all but the first op of a path carry a child"
+        for i in carrying:
+            child = rows[i][2] if carried[i] == 1 else rows[i][5]
+            assert child in writer and path[writer[child]] == p, "the carried child is written inside the path"
+            assert readers[child] == [i], "nobody else reads a carried CLV"
+    for i, r in enumerate(rows):
+        for side, c in ((1, r[2]), (2, r[5])):
+            if c in writer and carried[i] != side:
+                assert path[writer[c]] < path[i], "a child that comes from memory was written by an earlier path"
+
+
+@pytest.mark.parametrize("tips,kind,path_max", [(64, "random", 8), (64, "random", 3), (64, "random", 1),
+                                                (50, "caterpillar", 8), (50, "caterpillar", 2), (300, "random", 8)])
+def test_flow_plan_invariants(lib, tips, kind, path_max):
+    ds = synth.dna_dataset(tips, 8, seed=tips, tree_kind=kind, simulate_down_tree=False)
+    rows = [tuple(int(x) for x in r) for r in ds.tree.ops]
+    for t in (tips, 0):  # pattern tips, and tip CLVs (every op inner-inner)
+        npaths, path, carried = _paths(lib, rows, t, path_max)
+        assert npaths > 0
+        _check_plan(rows, npaths, path, carried, path_max)
+        if path_max == 1:
+            assert npaths == len(rows) and not any(carried)
+    if kind == "caterpillar" and path_max == 8:
+        npaths, _, _ = _paths(lib, rows, tips, 8)
+        assert npaths == -(-len(rows) // 8), "a caterpillar is one chain, cut every 8 ops"
+
+
+def test_flow_plan_partial_and_shared_children(lib):
+    # ((0,1)4,(2,3)5)6: the join carries one cherry, the other one comes from memory
+    rows = [(4, 0, 0, 0, -1, 1, 1, -1), (5, 1, 2, 2, -1, 3, 3, -1), (6, 2, 4, 4, 0, 5, 5, 1)]
+    npaths, path, carried = _paths(lib, rows, 4)
+    assert npaths == 2 and carried[2] in (1, 2) and carried[:2] == [0, 0]
+    _check_plan(rows, npaths, path, carried, 8)
+    # a partial list: CLV 5 is older than the list
+    npaths, path, carried = _paths(lib, [rows[0], rows[2]], 4)
+    assert npaths == 1 and carried == [0, 1]
+    # CLV 4 read by two ops: it cannot travel in registers
+    rows2 = rows + [(7, 3, 4, 4, 0, 0, 0, -1)]
+    npaths, path, carried = _paths(lib, rows2, 4)
+    assert carried[2] != 1 and carried[3] == 0
+    _check_plan(rows2, npaths, path, carried, 8)
+    # both children the same CLV
+    rows3 = [rows[0], (6, 2, 4, 4, 0, 4, 5, 0)]
+    npaths, path, carried = _paths(lib, rows3, 4)
+    assert npaths == 2 and carried == [0, 0]
+
+
+def test_flow_plan_refuses_lists_that_recycle_buffers(lib):
+    # op 2 overwrites CLV 4 that op 1 read: only launch levels keep that order
+    rows = [(4, 0, 0, 0, -1, 1, 1, -1), (5, 1, 4, 4, 0, 2, 2, -1), (4, 2, 2, 2, -1, 3, 3, -1)]
+    assert _paths(lib, rows, 4)[0] == 0
+    # a scaler written by another op than the CLV's writer
+    rows = [(4, 0, 0, 0, -1, 1, 1, -1), (5, 1, 2, 2, -1, 3, 3, -1), (6, 2, 4, 4, 1, 5, 5, 0)]
+    assert _paths(lib, rows, 4)[0] == 0
