@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Wide alignments: the ring kernels (every parent written / virtual cherries) against the one-launch path kernel
-in its latency shape and its wide shape (every parent written, carried children never re-read).  100 taxa,
+with one and two (site, rate) blocks per thread (every parent written, carried children never re-read).  100 taxa,
 CUDA events on the partition's stream, graph replay."""
 import importlib
 import json
@@ -20,10 +20,11 @@ FLOW = {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW": "1", "PLF_FLOW_MAX_SITES": "100
 VARIANTS = (
     ("ring_written", {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW": "0"}),
     ("ring_virtual", {"PLF_VIRTUAL_CHERRIES": "1", "PLF_VIRTUAL_CHERRY_MIN_SITES": "0", "PLF_FLOW": "0"}),
-    ("flow_latency", dict(FLOW, PLF_FLOW_WIDE_SITES="4000000000")),
-    ("flow_wide", dict(FLOW, PLF_FLOW_WIDE_SITES="0")),
-    ("flow_wide_path4", dict(FLOW, PLF_FLOW_WIDE_SITES="0", PLF_FLOW_PATH_MAX="4")),
+    ("flow_u1", dict(FLOW, PLF_FLOW_UNROLL="1")),
+    ("flow_u2", dict(FLOW, PLF_FLOW_UNROLL="2")),
 )
+# (profiles/r2_wide_ab.json also holds "flow_wide": a shape of the kernel with 8 sweeps per item and all loads of a path
+# issued first, measured in session 30 and removed again - see profiles/r2_notes.md)
 KEYS = sorted({k for _, env in VARIANTS for k in env})
 
 
