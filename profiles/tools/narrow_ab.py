@@ -20,16 +20,18 @@ import bench  # noqa: E402
 def main():
     lib = pkg.load()
     out = {}
-    for sites in (250, 1000, 2048, 4096, 10000, 30000, 60000, 100000):
+    for sites in (250, 1000, 4096, 10000, 30000, 60000, 100000, 300000):
         ds = bench.make_dataset("dna", 100, sites, 1, 0)
         row = {}
         for name, env in (("written", {"PLF_VIRTUAL_CHERRIES": "0", "PLF_LEVEL_MAX_SITES": "0", "PLF_FLOW": "0"}),
                           ("virtual", {"PLF_VIRTUAL_CHERRIES": "1", "PLF_VIRTUAL_CHERRY_MIN_SITES": "0", "PLF_LEVEL_MAX_SITES": "0", "PLF_FLOW": "0"}),
-                          ("level", {"PLF_VIRTUAL_CHERRIES": "1", "PLF_VIRTUAL_CHERRY_MIN_SITES": "0", "PLF_LEVEL_MAX_SITES": "100000000"}),
+                          ("level", {"PLF_VIRTUAL_CHERRIES": "1", "PLF_VIRTUAL_CHERRY_MIN_SITES": "0", "PLF_LEVEL_MAX_SITES": "100000000", "PLF_FLOW": "0"}),
                           ("level_written", {"PLF_VIRTUAL_CHERRIES": "0", "PLF_LEVEL_MAX_SITES": "100000000", "PLF_FLOW": "0"}),
                           ("flow_u1", {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_MAX_SITES": "100000000", "PLF_FLOW_MAX_UPDATES": "100000000000", "PLF_FLOW": "1", "PLF_FLOW_UNROLL": "1"}),
-                          ("flow_u2", {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_MAX_SITES": "100000000", "PLF_FLOW_MAX_UPDATES": "100000000000", "PLF_FLOW": "1", "PLF_FLOW_UNROLL": "2"}),
-                          ("flow_u4", {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_MAX_SITES": "100000000", "PLF_FLOW_MAX_UPDATES": "100000000000", "PLF_FLOW": "1", "PLF_FLOW_UNROLL": "4"})):
+                          ("flow_u2", {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_MAX_SITES": "100000000", "PLF_FLOW_MAX_UPDATES": "100000000000", "PLF_FLOW": "1", "PLF_FLOW_UNROLL": "2"})):
+            for k in ("PLF_VIRTUAL_CHERRIES", "PLF_VIRTUAL_CHERRY_MIN_SITES", "PLF_LEVEL_MAX_SITES", "PLF_FLOW",
+                      "PLF_FLOW_MAX_SITES", "PLF_FLOW_MAX_UPDATES", "PLF_FLOW_UNROLL", "PLF_FLOW_PATH_MAX"):
+                os.environ.pop(k, None)
             os.environ.update(env)
             eng = harness.Engine(lib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
             ext = torch.cuda.ExternalStream(lib.pll_cuda_get_stream(eng.p))

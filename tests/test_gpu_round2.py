@@ -62,17 +62,17 @@ CHERRY_CASES = [
 
 
 CHERRY_VARIANTS = {
-    "default": {"PLF_LEVEL_MAX_SITES": "0"},                        # ring kernel, 256 threads x 1 block per thread
-    "items2": {"PLF_CHERRY_ITEMS": "2", "PLF_LEVEL_MAX_SITES": "0"},   # 128 threads x 2 blocks per thread
-    "items4": {"PLF_CHERRY_ITEMS": "4", "PLF_LEVEL_MAX_SITES": "0"},   # 128-site tiles
-    "bulk": {"PLF_CHERRY_BULK": "1", "PLF_LEVEL_MAX_SITES": "0"},      # write-only consumers through bulk stores
-    "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4", "PLF_LEVEL_MAX_SITES": "0"},
-    "level": {"PLF_LEVEL_MAX_SITES": "1000000"},                    # one launch per traversal level (k_clv_dna_level)
+    "default": {"PLF_LEVEL_MAX_SITES": "0", "PLF_FLOW": "0"},       # ring kernel, 256 threads x 1 block per thread
+    "items2": {"PLF_CHERRY_ITEMS": "2", "PLF_LEVEL_MAX_SITES": "0", "PLF_FLOW": "0"},   # 128 threads x 2 blocks per thread
+    "items4": {"PLF_CHERRY_ITEMS": "4", "PLF_LEVEL_MAX_SITES": "0", "PLF_FLOW": "0"},   # 128-site tiles
+    "bulk": {"PLF_CHERRY_BULK": "1", "PLF_LEVEL_MAX_SITES": "0", "PLF_FLOW": "0"},      # write-only consumers through bulk stores
+    "stages4-items4": {"PLF_CHERRY_STAGES": "4", "PLF_CHERRY_ITEMS": "4", "PLF_LEVEL_MAX_SITES": "0", "PLF_FLOW": "0"},
+    "level": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_FLOW": "0"},   # one launch per traversal level (k_clv_dna_level)
     "level-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW": "0"},
     # the whole traversal as one launch (k_clv_dna_flow): paths of up to 8 ops, of 3, and every parent through memory
-    "flow-written": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0"},
-    "flow-written-3": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "3"},
-    "flow-written-1": {"PLF_LEVEL_MAX_SITES": "1000000", "PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "1"},
+    "flow-written": {"PLF_VIRTUAL_CHERRIES": "0"},
+    "flow-written-3": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "3"},
+    "flow-written-1": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "1"},
     # two and four (site, rate) blocks per thread
     "flow-written-u2": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_UNROLL": "2"},
     "flow-written-u4": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_UNROLL": "4", "PLF_FLOW_PATH_MAX": "5"},
