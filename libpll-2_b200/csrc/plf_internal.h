@@ -38,7 +38,7 @@ struct plf_ctx
   int dna_flow_max_sites;         /* PLF_FLOW_MAX_SITES: widest alignment that runs as one launch per traversal */
   unsigned long long dna_flow_max_updates; /* PLF_FLOW_MAX_UPDATES: ... and most ops x sites */
   int dna_flow_path_max;          /* PLF_FLOW_PATH_MAX: ops of a path (1 = every parent goes through memory) */
-  int dna_flow_occupancy[3][3];   /* [1, 2 or 4 blocks per thread][log2 rates] */
+  int dna_flow_occupancy[2][3];   /* [1 or 2 blocks per thread][log2 rates] */
   int dna_cherry_bulk;            /* PLF_CHERRY_BULK=1: tip + cherry / cherry + cherry through the bulk-store kernel instead of the ring kernel */
   int dna_cherry;                 /* PLF_VIRTUAL_CHERRIES=0 writes every tip-tip parent to HBM */
   int dna_tt_bulk_occupancy[4];

@@ -1344,6 +1344,9 @@ __device__ __forceinline__ void flow_wait(const unsigned long long * f, unsigned
     }
 }
 
+/* 64 registers: in the throughput regime of the kernel resident CTAs count (two blocks per thread at 78 registers
+ * and 6 CTAs per SM: 4 - 5 % slower from 10k sites on; profiles/r2_notes.md) */
+#define FLOW_MIN_CTAS 8
 #define FLOW_CARRY_MASK 3u   /* 1: the left child is the previous op's parent (in registers), 2: the right one */
 #define FLOW_CARRY_SCALER 4u /* ... and its scaler counts with it */
 #define FLOW_TIP_TIP 8u      /* never scales, zeroes its scaler (src/core_partials_avx.c:1005-1006) */
@@ -1384,7 +1387,7 @@ __device__ __forceinline__ void flow_rows_tip(const double * M, const unsigned i
 }
 
 template <int LOG2R, int U>
-__global__ void __launch_bounds__(DNA_THREADS)
+__global__ void __launch_bounds__(DNA_THREADS, FLOW_MIN_CTAS)
 k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __restrict__ path_start, unsigned int npaths,
                unsigned int nchunks, int per_rate, plf_flow_ctrl * ctrl, unsigned long long * ready)
 {
@@ -1561,7 +1564,7 @@ k_clv_dna_flow(const plf_flow_op * __restrict__ fops, const unsigned int * __res
 unsigned int plf_dna_flow_unroll(unsigned int max_sites)
 {
   const char * v = getenv("PLF_FLOW_UNROLL");
-  if (v && (v[0] == '1' || v[0] == '2' || v[0] == '4')) return (unsigned int)(v[0] - '0');
+  if (v && (v[0] == '1' || v[0] == '2')) return (unsigned int)(v[0] - '0');
   v = getenv("PLF_FLOW_UNROLL_SITES");
   return max_sites >= ((v && v[0]) ? strtoul(v, nullptr, 10) : 2048ul) ? 2u : 1u;
 }
@@ -1707,11 +1710,9 @@ int plf_launch_dna_flow(plf_ctx * ctx, const plf_flow_op * d_fops, const unsigne
   const unsigned int nchunks = plf_dna_flow_chunks(rate_cats, max_sites);
   typedef void (*flow_kernel_t)(const plf_flow_op *, const unsigned int *, unsigned int, unsigned int, int, plf_flow_ctrl *,
                                 unsigned long long *);
-  static const flow_kernel_t kernels[3][3] = {{k_clv_dna_flow<0, 1>, k_clv_dna_flow<1, 1>, k_clv_dna_flow<2, 1>},
-                                              {k_clv_dna_flow<0, 2>, k_clv_dna_flow<1, 2>, k_clv_dna_flow<2, 2>},
-                                              {k_clv_dna_flow<0, 4>, k_clv_dna_flow<1, 4>, k_clv_dna_flow<2, 4>}};
-  const unsigned int unroll = plf_dna_flow_unroll(max_sites);
-  const int two = unroll == 4 ? 2 : (unroll == 2 ? 1 : 0);
+  static const flow_kernel_t kernels[2][3] = {{k_clv_dna_flow<0, 1>, k_clv_dna_flow<1, 1>, k_clv_dna_flow<2, 1>},
+                                              {k_clv_dna_flow<0, 2>, k_clv_dna_flow<1, 2>, k_clv_dna_flow<2, 2>}};
+  const int two = plf_dna_flow_unroll(max_sites) == 2;
   const flow_kernel_t fn = kernels[two][log2r];
   if (!ctx->dna_flow_occupancy[two][log2r])
   {

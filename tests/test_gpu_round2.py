@@ -73,9 +73,9 @@ CHERRY_VARIANTS = {
     "flow-written": {"PLF_VIRTUAL_CHERRIES": "0"},
     "flow-written-3": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "3"},
     "flow-written-1": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_PATH_MAX": "1"},
-    # two and four (site, rate) blocks per thread
+    # two (site, rate) blocks per thread (the default from 2048 sites on)
     "flow-written-u2": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_UNROLL": "2"},
-    "flow-written-u4": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_UNROLL": "4", "PLF_FLOW_PATH_MAX": "5"},
+    "flow-written-u2-5": {"PLF_VIRTUAL_CHERRIES": "0", "PLF_FLOW_UNROLL": "2", "PLF_FLOW_PATH_MAX": "5"},
 }
 
 
@@ -650,7 +650,7 @@ def test_flow_kernel_lists(reflib, cudalib, monkeypatch):
 
 @pytest.mark.parametrize("sites", [1, 31, 32, 33, 64, 65, 513, 2048])
 @pytest.mark.parametrize("cats", [1, 2, 4])
-@pytest.mark.parametrize("path_max", ["8", "2", "u2", "u4"])
+@pytest.mark.parametrize("path_max", ["8", "2", "u2"])
 def test_flow_kernel_chunk_edges(reflib, cudalib, monkeypatch, sites, cats, path_max):
     """work-item boundaries of k_clv_dna_flow (32, 64 or 128 sites per sweep for 4, 2, 1 rate categories), per-rate
     scalers on a caterpillar that scales, tip CLVs instead of pattern tips for the odd widths"""
