@@ -502,7 +502,7 @@ static int enqueue_levels(plf_ctx_t * ctx, const plf_shape_t * sh, const plf_op_
     {
       const plf_op_t & o = h_ops[i];
       plain = o.nsites == sites && (o.kind == PLF_OP_II || o.kind == PLF_OP_TI || o.kind == PLF_OP_TT) &&
-              !(o.parent_id_site || o.left_site_id || o.right_site_id);
+              o.dep[0] != PLF_DEP_ORDERED && !(o.parent_id_site || o.left_site_id || o.right_site_id);
     }
     const unsigned long long flags = (unsigned long long)nops * plf_dna_flow_chunks(sh->rate_cats, sites);
     if (plain && flags < (1ull << 30))

@@ -2446,7 +2446,10 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
   const unsigned int c1 = op->child1_clv_index, c2 = op->child2_clv_index, par = op->parent_clv_index;
   unsigned int * const * sb = p->scale_buffer;
   memset(out, 0, sizeof(*out));
-  out->dep[0] = out->dep[1] = out->dep[2] = out->dep[3] = PLF_DEP_NONE;
+  /* who writes what this op reads is not known until attach_dependencies() has seen the whole list: until then
+   * the op counts as ordered by its launch level only */
+  out->dep[0] = PLF_DEP_ORDERED;
+  out->dep[1] = out->dep[2] = out->dep[3] = PLF_DEP_NONE;
   if (par >= p->nodes || c1 >= p->nodes || c2 >= p->nodes || op->child1_matrix_index >= p->prob_matrices ||
       op->child2_matrix_index >= p->prob_matrices || op->parent_scaler_index >= (int)p->scale_buffers ||
       op->child1_scaler_index >= (int)p->scale_buffers || op->child2_scaler_index >= (int)p->scale_buffers)
@@ -2873,7 +2876,8 @@ static int launch_levels(cuda_partition_t * cp, const pll_operation_t * ops, uns
     }
     free(cursor);
   }
-  if (count > 1 && cp->shape.states == 4 && !pll_repeats_enabled(&cp->pub)) attach_dependencies(cp, ops, count);
+  /* (under site repeats too: a list whose nodes all went without identifiers is a plain list) */
+  if (count > 1 && cp->shape.states == 4) attach_dependencies(cp, ops, count);
   if (!tipmap_on_device(cp) ||
       !plf_update_partials(cp->ctx, &cp->shape, cp->h_ops_sorted, count, cp->h_level_start, nlevels, cp->d_tipmap,
                            cp->pub.maxstates))

@@ -672,3 +672,35 @@ def test_flow_kernel_chunk_edges(reflib, cudalib, monkeypatch, sites, cats, path
     assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
     ref.close()
     gpu.close()
+
+
+@pytest.mark.parametrize("per_rate", [False, True], ids=["per-site", "per-rate"])
+def test_plain_lists_under_site_repeats_run_as_one_launch(reflib, cudalib, per_rate):
+    """PLL_ATTRIB_SITE_REPEATS on columns that do not repeat: above the tips the default rule (src/repeats.c:100-111)
+    leaves the nodes without identifiers, so a list of upper operations is a plain list and takes k_clv_dna_flow -
+    with the dependencies between its operations, not without them."""
+    ds = synth.dna_dataset(300, 45, seed=77, alpha=0.6, simulate_down_tree=False)
+    ref, gpu = pair(reflib, cudalib, ds, capi.SITE_REPEATS, per_rate)
+    traverse(ref, gpu)
+    ids = gpu.part.repeats.contents.pernode_ids
+    tips = ds.tree.tips
+    upper = [op for op in gpu.ops if op.child1_clv_index >= tips and op.child2_clv_index >= tips and
+             not ids[op.child1_clv_index] and not ids[op.child2_clv_index] and not ids[op.parent_clv_index]]
+    assert len(upper) >= 8, "the data is meant to leave the upper nodes without identifiers"
+    compare_all_nodes(ref, gpu)
+    n = len(upper)
+    arr = (capi.Operation * n)(*upper)
+    levels = np.zeros(n, dtype=np.uint32)
+    assert cudalib.pll_cuda_schedule_levels(arr, n, levels.ctypes.data_as(capi.c_uint_p)) >= 3, "operations that depend on each other"
+    bl = ds.tree.branch_lengths * 0.7
+    for e in (ref, gpu):
+        e.update_pmatrices(branch_lengths=bl[e.matrix_indices])
+    ref.lib.pll_update_partials(ref.p, arr, n)
+    for _ in range(4):  # plain launch, capture, two replays
+        l0 = cudalib.pll_cuda_kernel_launches()
+        cudalib.pll_update_partials(gpu.p, arr, n)
+        assert cudalib.pll_cuda_kernel_launches() - l0 == 1, "a plain list is one launch"
+    compare_all_nodes(ref, gpu)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
+    ref.close()
+    gpu.close()
