@@ -187,6 +187,11 @@ typedef struct cuda_partition
   unsigned int cherry_maxstates; /* tip alphabet size cherry_ok was decided for (0: not yet) */
   unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES; default 2049, 4 states: above what runs as one launch) */
   double * d_cherry_pm;          /* [clv_buffers][2][rate_cats * 16]: the P-matrices each cherry was asked with */
+  /* 20 states, narrow alignments: a pattern tip that meets an inner node is ALSO kept as an expanded CLV (built on
+   * first use from its codes), so that a traversal level is one inner-inner launch instead of up to three kinds */
+  int aa_tip_clvs;
+  double ** d_tip_expanded;      /* [tips], NULL until used */
+  unsigned char * tip_expanded_valid;
   struct cherry_state * cherry;  /* [nodes] */
   struct cherry_state * cherry_saved; /* roll-back copy while an operation list is resolved */
   unsigned int cherries_pending; /* nodes whose CLV is virtual right now */
@@ -300,6 +305,7 @@ static int cherry_decide(cuda_partition_t * cp)
 static int ensure_real_for_tip(cuda_partition_t * cp, unsigned int tip)
 {
   unsigned int n;
+  if (cp->tip_expanded_valid && tip < cp->pub.tips) cp->tip_expanded_valid[tip] = 0; /* its codes are about to change */
   if (!cp->cherry || !cp->cherries_pending) return 1;
   for (n = cp->pub.tips; n < cp->pub.nodes; ++n)
     if (cp->cherry[n].is_virtual && (cp->cherry[n].tip1 == tip || cp->cherry[n].tip2 == tip) && !ensure_real(cp, n))
@@ -451,6 +457,10 @@ static void destroy(cuda_partition_t * cp)
     }
     plf_free(cp->ctx, cp->d_pmatrix_block);
     plf_free(cp->ctx, cp->d_cherry_pm);
+    if (cp->d_tip_expanded)
+      for (i = 0; i < p->tips; ++i) plf_free(cp->ctx, cp->d_tip_expanded[i]);
+    free(cp->d_tip_expanded);
+    free(cp->tip_expanded_valid);
     plf_free(cp->ctx, cp->d_model);
     plf_free(cp->ctx, cp->d_pattern_weights);
     plf_free(cp->ctx, cp->d_invariant);
@@ -782,6 +792,16 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
       NEED(cp->scaler_zero_saved = (unsigned char *)calloc(scale_buffers ? scale_buffers : 1, 1));
       NEED(cp->d_cherry_pm = (double *)plf_alloc(cp->ctx, (size_t)clv_buffers * 2 * cherry_msz(cp) * sizeof(double), 1));
     }
+  }
+  if ((attributes & PLL_ATTRIB_PATTERN_TIP) && states == 20 && clv_buffers)
+  {
+    /* 200 taxa x 250 / 1000 sites: 125 / 201 us per traversal with the tip-inner kernels (25 launches), 70 / 143 us
+     * with every tip an expanded CLV (17 launches) - profiles/r2_narrow_kinds.json.  Tip + tip keeps its kernel:
+     * it never scales and zeroes its scaler (src/core_partials_avx.c:942-990) */
+    const char * v = getenv("PLF_AA_TIP_CLV_MAX_SITES");
+    const unsigned long lim = (v && v[0]) ? strtoul(v, NULL, 10) : 2048ul;
+    const char * m = getenv("PLF_AA_MMA");
+    cp->aa_tip_clvs = sites <= lim && !(m && m[0] == '0') && !cp->cherry;
   }
 #undef NEED
   return p;
@@ -2084,6 +2104,8 @@ static int tipmap_on_device(cuda_partition_t * cp)
   {
     if (!plf_upload(cp->ctx, cp->d_tipmap, cp->pub.tipmap, PLL_ASCII_SIZE * sizeof(pll_state_t))) return 0;
     cp->tipmap_dirty = 0;
+    /* what a code stands for may have changed with it */
+    if (cp->tip_expanded_valid) memset(cp->tip_expanded_valid, 0, cp->pub.tips);
   }
   return 1;
 }
@@ -2438,6 +2460,32 @@ static int reserve_ops(cuda_partition_t * cp, unsigned int count)
   return cp->ops_cap != 0;
 }
 
+/* the expanded CLV of a pattern tip (entry j = bit j of the state mask of its code, for every rate: what
+ * pll_set_tip_states leaves in a partition without PLL_ATTRIB_PATTERN_TIP, src/pll.c:959-1024) */
+static const double * expanded_tip(cuda_partition_t * cp, unsigned int tip)
+{
+  const pll_partition_t * p = &cp->pub;
+  if (!cp->d_tip_expanded)
+  {
+    cp->d_tip_expanded = (double **)calloc(p->tips ? p->tips : 1, sizeof(double *));
+    cp->tip_expanded_valid = (unsigned char *)calloc(p->tips ? p->tips : 1, 1);
+    if (!cp->d_tip_expanded || !cp->tip_expanded_valid) return NULL;
+  }
+  if (!cp->d_tip_expanded[tip])
+    cp->d_tip_expanded[tip] = (double *)plf_alloc(
+        cp->ctx, (size_t)sites_alloc(p) * p->rate_cats * p->states_padded * sizeof(double) + BULK_PAD, 0);
+  if (!cp->d_tip_expanded[tip]) return NULL;
+  if (!cp->tip_expanded_valid[tip])
+  {
+    if (!tipmap_on_device(cp) ||
+        !plf_tip_clv_from_states(cp->ctx, &cp->shape, cp->d_tip_expanded[tip], cp->d_tipchars[tip], cp->d_tipmap, NULL,
+                                 sites_alloc(p)))
+      return NULL;
+    cp->tip_expanded_valid[tip] = 1;
+  }
+  return cp->d_tip_expanded[tip];
+}
+
 /* turn one pll_operation_t into device pointers + kernel variant
  * (dispatch of src/partials.c:245-291) */
 static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_t * out)
@@ -2522,7 +2570,23 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
       out->left_matrix = p->pmatrix[mt];
       out->right_matrix = p->pmatrix[mi];
       if (!out->left_tip) goto missing;
-      if (t1 ? v2 : v1)
+      if (cp->aa_tip_clvs && !(t1 ? v2 : v1))
+      {
+        /* narrow 20-state alignment: the tip as an expanded CLV, the op as inner-inner (scales like tip-inner:
+         * src/core_partials_avx2.c:343 vs :630; a tip has no scaler) */
+        out->kind = PLF_OP_II;
+        out->left_tip = NULL;
+        out->left_clv = expanded_tip(cp, tip);
+        out->right_clv = p->clv[inner];
+        out->right_scaler = si >= 0 ? sb[si] : NULL;
+        if (!out->left_clv)
+        {
+          set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
+          return 0;
+        }
+        if (!out->right_clv) goto missing;
+      }
+      else if (t1 ? v2 : v1)
       {
         const cherry_state_t * c = &cp->cherry[inner];
         out->kind = PLF_OP_TC;

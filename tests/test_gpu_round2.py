@@ -213,6 +213,7 @@ def test_virtual_cherries_parity_aa(reflib, cudalib, monkeypatch, case):
     ds = synth.aa_dataset(tips, sites, seed=200 + tips, tree_kind=tree, alpha=0.4, cats=cats)
     monkeypatch.setenv("PLF_VIRTUAL_CHERRY_MIN_SITES", "0")
     monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "0")
+    monkeypatch.setenv("PLF_AA_TIP_CLV_MAX_SITES", "0")  # tips through the tip kernels, as with virtual cherries
     plain = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP | (capi.RATE_SCALERS if per_rate else 0))
     monkeypatch.setenv("PLF_VIRTUAL_CHERRIES", "1")
     ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
@@ -704,3 +705,39 @@ def test_plain_lists_under_site_repeats_run_as_one_launch(reflib, cudalib, per_r
     assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
     ref.close()
     gpu.close()
+
+
+# ---- 20 states, narrow alignments: pattern tips that meet inner nodes as expanded CLVs -------------------------
+
+@pytest.mark.parametrize("per_rate", [False, True], ids=["per-site", "per-rate"])
+def test_aa_narrow_tips_as_expanded_clvs(reflib, cudalib, monkeypatch, per_rate):
+    """Up to 2048 sites a 20-state pattern tip under a tip + inner operation is read as an expanded CLV (one
+    inner-inner launch per level instead of up to three kinds; tip + tip keeps its kernel).  Same values within the
+    tensor-core tolerance, same scalers, also after a tip's sequence changed; PLF_AA_TIP_CLV_MAX_SITES=0 turns it off."""
+    ds = synth.aa_dataset(80, 333, seed=31, alpha=0.4)
+    ref, gpu = pair(reflib, cudalib, ds, capi.PATTERN_TIP, per_rate)
+    monkeypatch.setenv("PLF_AA_TIP_CLV_MAX_SITES", "0")
+    old = harness.Engine(cudalib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP | (capi.RATE_SCALERS if per_rate else 0))
+    traverse(ref, gpu, old)
+    l0 = cudalib.pll_cuda_kernel_launches()
+    gpu.update_partials()
+    l1 = cudalib.pll_cuda_kernel_launches()
+    old.update_partials()
+    l2 = cudalib.pll_cuda_kernel_launches()
+    assert l1 - l0 < l2 - l1, "fewer launches per traversal"
+    compare_all_nodes(ref, gpu, exact=False)
+    compare_all_nodes(ref, old, exact=False)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL")
+    # another sequence for two tips (one of a cherry, one under a tip + inner operation)
+    for tip in (0, ds.tree.tips - 1):
+        seq = ds.seqs[(tip + 5) % ds.tree.tips]
+        for e in (ref, gpu):
+            assert e.lib.pll_set_tip_states(e.p, tip, e.map, seq) == 1
+    for _ in range(3):
+        traverse(gpu)
+    traverse(ref)
+    n_scaled = compare_all_nodes(ref, gpu, exact=False)
+    assert_rel(gpu.edge_logl(), ref.edge_logl(), LOGL_RTOL, "edge logL after new tip states")
+    assert n_scaled >= 0
+    for e in (ref, gpu, old):
+        e.close()
