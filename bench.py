@@ -520,8 +520,8 @@ def config4_record(lib, torch, local, threads):
 
 
 def narrow_record(lib, torch, local):
-    """A narrow alignment (100 taxa x 1000 sites, the config-2 model): a traversal is bound by the launch path,
-    not by bytes -- 12 levels of kernels of a few microseconds, replayed as one CUDA graph."""
+    """A narrow alignment (100 taxa x 1000 sites, the config-2 model): a traversal is bound by launch and dependency
+    latency, not by bytes."""
     out = {}
     for sites in (1000, 10000):
         ds = make_dataset("dna", 100, sites, 1, 0)
@@ -536,7 +536,19 @@ def narrow_record(lib, torch, local):
         eng.close()
         out[f"{sites}_sites"] = {"traversal_us": us, "site_updates_per_s": len(ds.tree.ops) * sites / (us * 1e-6),
                                  "full_evaluation_blocking_api_us": e2e_us}
-    return {"workload": "synthetic DNA 100 taxa x 1000 / 10000 sites GTR+G4, pattern-tip on (launch-bound)", **out}
+    # the protein counterpart (proteins are a few hundred sites long): 200 taxa, LG4M-shaped model
+    aa = {}
+    for sites in (250, 1000):
+        ds = synth.aa_dataset(200, sites, seed=2)
+        eng = harness.Engine(lib, ds, capi.ARCH_CUDA | capi.PATTERN_TIP)
+        ext = torch.cuda.ExternalStream(lib.pll_cuda_get_stream(eng.p), device=torch.device("cuda", local))
+        eng.update_pmatrices()
+        us = 1e3 * device_timed(torch, ext, eng.update_partials, reps=100, warm=5)
+        eng.close()
+        aa[f"{sites}_sites"] = {"traversal_us": us, "site_updates_per_s": len(ds.tree.ops) * sites / (us * 1e-6)}
+    return {"workload": "synthetic DNA 100 taxa x 1000 / 10000 sites GTR+G4, pattern-tip on (latency-bound: the whole "
+                        "traversal is one launch, k_clv_dna_flow)", **out,
+            "protein_200_taxa": {"workload": "synthetic protein 200 taxa x 250 / 1000 sites, 4 rate matrices, G4, pattern-tip on", **aa}}
 
 
 def run_b200_arm(args):
