@@ -312,3 +312,32 @@ def test_flow_plan_refuses_lists_that_recycle_buffers(lib):
     # a scaler written by another op than the CLV's writer
     rows = [(4, 0, 0, 0, -1, 1, 1, -1), (5, 1, 2, 2, -1, 3, 3, -1), (6, 2, 4, 4, 1, 5, 5, 0)]
     assert _paths(lib, rows, 4)[0] == 0
+
+
+def test_flow_plan_random_lists(lib):
+    """random trees, random sub-lists (children older than the list), random path limits, some lists with a recycled
+    buffer: the plan either keeps its invariants or refuses the list"""
+    rng = np.random.default_rng(2024)
+    refused = planned = 0
+    for trial in range(120):
+        tips = int(rng.integers(4, 90))
+        ds = synth.dna_dataset(tips, 4, seed=1000 + trial, tree_kind="caterpillar" if trial % 7 == 0 else "random",
+                               simulate_down_tree=False)
+        rows = [tuple(int(x) for x in r) for r in ds.tree.ops]
+        keep = rng.random(len(rows)) < rng.choice([1.0, 0.8, 0.5])
+        rows = [r for r, k in zip(rows, keep) if k] or rows[:1]
+        recycle = trial % 5 == 0 and len(rows) > 2
+        if recycle:  # an op that overwrites the parent of an earlier op which a later op has read
+            i = int(rng.integers(0, len(rows) - 1))
+            rows = rows + [rows[i]]
+        path_max = int(rng.integers(1, 9))
+        pattern_tips = tips if trial % 2 else 0
+        npaths, path, carried = _paths(lib, rows, pattern_tips, path_max)
+        if recycle:
+            assert npaths == 0
+            refused += 1
+            continue
+        assert npaths > 0
+        _check_plan(rows, npaths, path, carried, path_max)
+        planned += 1
+    assert refused and planned
