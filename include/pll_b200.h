@@ -524,7 +524,7 @@ PLL_EXPORT int pll_cuda_download_sumtable(const pll_partition_t * partition,
  * (edge/root log-likelihood, sumtable, ancestral states, pll_cuda_download_clv, pll_show_clv) writes it
  * first; a client that passes partition->clv[i] to its own kernels calls pll_cuda_materialize_clv(i).
  * pll_cuda_virtual_cherries(): 1 when the partition works this way ($PLF_VIRTUAL_CHERRIES=0 turns it off,
- * $PLF_VIRTUAL_CHERRY_MIN_SITES sets the narrowest alignment it applies to; default 2049 sites for 20 states,
+ * $PLF_VIRTUAL_CHERRY_MIN_SITES sets the narrowest alignment it applies to; default 20000 sites for 20 states,
  * for 4 states one site more than a full traversal may have to run as ONE launch with all parents written:
  * min(65536, 6500000 / (tips - 2)) sites, $PLF_FLOW_MAX_SITES / $PLF_FLOW_MAX_UPDATES; such alignments are bound
  * by launch and dependency latency, not bytes).

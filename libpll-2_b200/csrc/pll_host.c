@@ -185,7 +185,7 @@ typedef struct cuda_partition
    * written to HBM; their consumers work from the tip codes, anything else materialises them first */
   int cherry_ok;                 /* this partition's kernels consume virtual cherries */
   unsigned int cherry_maxstates; /* tip alphabet size cherry_ok was decided for (0: not yet) */
-  unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES; default 2049, 4 states: above what runs as one launch) */
+  unsigned int cherry_min_sites; /* narrower alignments write every parent ($PLF_VIRTUAL_CHERRY_MIN_SITES; default 20 states 20000, 4 states: above what runs as one launch) */
   double * d_cherry_pm;          /* [clv_buffers][2][rate_cats * 16]: the P-matrices each cherry was asked with */
   /* 20 states, narrow alignments: a pattern tip that meets an inner node is ALSO kept as an expanded CLV (built on
    * first use from its codes), so that a traversal level is one inner-inner launch instead of up to three kinds */
@@ -765,7 +765,10 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     /* measured (profiles/r2_notes.md, 100 taxa): from 4096 sites up virtual cherries win (90 vs 106 us, at 10k
      * sites 127 vs 168 us); below ~2500 sites a traversal is bound by its launches and the one-launch-per-level
      * kernel with every parent written is fastest (1000 sites: 62 us against 78 us) */
-    cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : 2049u;
+    /* 20 states (200 taxa, profiles/r2_aa_mid_ab.json): the consumers of virtual cherries build large half tables per
+     * CTA, which pays from ~20k sites on (16k sites: 988 us against 940 us with every parent written, 32k: 1563
+     * against 1694 us; at 4000 sites 543 against 362 us) */
+    cp->cherry_min_sites = (v && v[0]) ? (unsigned int)strtoul(v, NULL, 10) : (states == 20 ? 20000u : 2049u);
     if (!(v && v[0]) && states == 4 && rate_cats <= 4 && (rate_cats & (rate_cats - 1)) == 0)
     {
       /* 4 states: a plain list of up to PLF_FLOW_MAX_UPDATES site-updates (default 6.5M: 100 taxa x 66k sites,
@@ -798,10 +801,13 @@ PLL_EXPORT pll_partition_t * pll_partition_create(unsigned int tips, unsigned in
     /* 200 taxa x 250 / 1000 sites: 125 / 201 us per traversal with the tip-inner kernels (25 launches), 70 / 143 us
      * with every tip an expanded CLV (17 launches) - profiles/r2_narrow_kinds.json.  Tip + tip keeps its kernel:
      * it never scales and zeroes its scaler (src/core_partials_avx.c:942-990) */
+    /* ... 4000 / 8000 sites: 362 / 555 us (tip kernels) against 320 / 547 us; from 16k sites the tip kernels win
+     * (profiles/r2_aa_mid_ab.json).  The expanded copies double the memory of the tips' share: at most 2 GiB */
     const char * v = getenv("PLF_AA_TIP_CLV_MAX_SITES");
-    const unsigned long lim = (v && v[0]) ? strtoul(v, NULL, 10) : 2048ul;
+    const unsigned long lim = (v && v[0]) ? strtoul(v, NULL, 10) : 8192ul;
     const char * m = getenv("PLF_AA_MMA");
-    cp->aa_tip_clvs = sites <= lim && !(m && m[0] == '0') && !cp->cherry;
+    const unsigned long long bytes = (unsigned long long)tips * sites_alloc(p) * rate_cats * p->states_padded * sizeof(double);
+    cp->aa_tip_clvs = sites <= lim && !(m && m[0] == '0') && !cp->cherry && (bytes <= (2ull << 30) || (v && v[0]));
   }
 #undef NEED
   return p;
