@@ -2576,20 +2576,17 @@ static int resolve_op(cuda_partition_t * cp, const pll_operation_t * op, plf_op_
       out->left_matrix = p->pmatrix[mt];
       out->right_matrix = p->pmatrix[mi];
       if (!out->left_tip) goto missing;
-      if (cp->aa_tip_clvs && !(t1 ? v2 : v1))
+      const double * expanded = (cp->aa_tip_clvs && !(t1 ? v2 : v1)) ? expanded_tip(cp, tip) : NULL;
+      if (cp->aa_tip_clvs && !(t1 ? v2 : v1) && !expanded) cp->aa_tip_clvs = 0; /* no memory for the copies: tip kernels */
+      if (expanded)
       {
         /* narrow 20-state alignment: the tip as an expanded CLV, the op as inner-inner (scales like tip-inner:
          * src/core_partials_avx2.c:343 vs :630; a tip has no scaler) */
         out->kind = PLF_OP_II;
         out->left_tip = NULL;
-        out->left_clv = expanded_tip(cp, tip);
+        out->left_clv = expanded;
         out->right_clv = p->clv[inner];
         out->right_scaler = si >= 0 ? sb[si] : NULL;
-        if (!out->left_clv)
-        {
-          set_error(PLL_ERROR_MEM_ALLOC, "Unable to allocate enough memory.%s", NULL);
-          return 0;
-        }
         if (!out->right_clv) goto missing;
       }
       else if (t1 ? v2 : v1)
