@@ -341,3 +341,52 @@ def test_flow_plan_random_lists(lib):
         _check_plan(rows, npaths, path, carried, path_max)
         planned += 1
     assert refused and planned
+
+
+def test_flow_queue_never_deadlocks(lib):
+    """A model of k_clv_dna_flow's queue: W persistent workers claim (path, chunk) items in queue order, each holding
+    the item it works on plus one claimed ahead; an item finishes only when the items that write what it reads have
+    finished.  For random trees and any worker count the queue drains: an item's producers sit earlier in the queue,
+    so the unfinished item with the smallest position is always some worker's CURRENT item and never waits."""
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        tips = int(rng.integers(5, 70))
+        ds = synth.dna_dataset(tips, 4, seed=3000 + trial, tree_kind="caterpillar" if trial % 6 == 0 else "random",
+                               simulate_down_tree=False)
+        rows = [tuple(int(x) for x in r) for r in ds.tree.ops]
+        path_max = int(rng.integers(1, 9))
+        npaths, path, carried = _paths(lib, rows, tips, path_max)
+        writer = {r[0]: i for i, r in enumerate(rows)}
+        needs = [set() for _ in range(npaths)]
+        for i, r in enumerate(rows):
+            for side, c in ((1, r[2]), (2, r[5])):
+                if c in writer and carried[i] != side:
+                    needs[path[i]].add(path[writer[c]])
+        assert all(q < p for p in range(npaths) for q in needs[p])
+        chunks = int(rng.integers(1, 4))
+        items = [(p, c) for p in range(npaths) for c in range(chunks)]  # queue order: path-major
+        for workers in (1, 2, 3, 7, 64):
+            done, nxt = set(), 0
+            slots = []  # per worker: [current, claimed ahead]
+            for _ in range(workers):
+                cur = items[nxt] if nxt < len(items) else None
+                nxt += cur is not None
+                ahead = items[nxt] if cur is not None and nxt < len(items) else None
+                nxt += ahead is not None
+                slots.append([cur, ahead])
+            for _ in range(4 * len(items) + 8):
+                progressed = False
+                for s in slots:
+                    cur = s[0]
+                    if cur is None:
+                        continue
+                    if all((q, cur[1]) in done for q in needs[cur[0]]):
+                        done.add(cur)
+                        s[0] = s[1]
+                        s[1] = items[nxt] if s[0] is not None and nxt < len(items) else None
+                        nxt += s[1] is not None
+                        progressed = True
+                if len(done) == len(items):
+                    break
+                assert progressed, f"deadlock: trial {trial}, {workers} workers, {len(done)} of {len(items)} items done"
+            assert len(done) == len(items)
